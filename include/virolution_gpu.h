@@ -1,0 +1,209 @@
+/*
+ * virolution_gpu.h — C ABI of the B200-native population-update path.
+ *
+ * Drop-in boundary for virolution's `trait Simulation<S>` (reference
+ * src/simulation.rs:177-219).  A Rust `impl Simulation<Nt> for GpuSimulation`
+ *  binds exactly these entry points; in this repository
+ * the C++ mirror `include/virolution_gpu.hpp` and the Python harness
+ * `virolution_b200/` call them.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *  - every function returns `int`: 0 = ok, <0 = error class (vl_status);
+ *    `vl_last_error(sim)` returns the message of the last failure on that
+ *    handle (reference: `VirolutionError`, src/errors.rs:5-15; the loop itself
+ *    panics — those panics are VL_ERR_REFERENCE_PANIC here).
+ *  - symbols (bases) are indices A=0,T=1,C=2,G=3 (src/encoding.rs:65-72).
+ *  - fitness tables are row-major L x 4 f64 (src/core/fitness/table.rs:82-84).
+ *  - transfer matrices are row-major, row = target, col = origin
+ *    (src/config/schedule.rs:96-98).
+ *  - host buffers unless the name says `_device`.
+ *  - a handle owns one CUDA stream and binds its device on every call; calls
+ *    on different handles may come from different threads (rayon workers in
+ *    the reference, src/runner.rs:388-399).
+ */
+#ifndef VIROLUTION_GPU_H
+#define VIROLUTION_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vl_sim vl_sim; /* one compartment: BasicSimulation, src/simulation.rs:221-232 */
+typedef struct vl_pop vl_pop; /* detached Population<Store<S>>, src/core/population.rs:156-163 */
+
+typedef enum vl_status {
+    VL_OK = 0,
+    VL_ERR_INITIALIZATION = -1,  /* VirolutionError::InitializationError */
+    VL_ERR_IMPLEMENTATION = -2,  /* VirolutionError::ImplementationError */
+    VL_ERR_CUDA = -3,            /* device/runtime failure (no reference analogue) */
+    VL_ERR_CAPACITY = -4,        /* device arena / table capacity exhausted */
+    VL_ERR_REFERENCE_PANIC = -5, /* the reference panics here (e.g. all-zero weights,
+                                    src/core/population.rs:386) */
+    VL_ERR_ARGUMENT = -6
+} vl_status;
+
+/* UtilityFunction, src/core/fitness/utility.rs:5-23 */
+typedef enum vl_utility_kind { VL_UTILITY_LINEAR = 0, VL_UTILITY_ALGEBRAIC = 1, VL_UTILITY_HILL = 2 } vl_utility_kind;
+typedef struct vl_utility {
+    int32_t kind;
+    int32_t _pad;
+    double upper; /* Algebraic */
+    double p, n;  /* Hill; k = (1-p)/p is derived (utility.rs:44) */
+} vl_utility;
+
+/* EpiEntry, src/core/fitness/epistasis.rs:15-21 (naturally aligned here; the
+ * .npy record is packed — the harness converts). */
+typedef struct vl_epi_entry {
+    uint64_t pos1;
+    uint64_t pos2;
+    double value;
+    uint8_t base1;
+    uint8_t base2;
+    uint8_t _pad[6];
+} vl_epi_entry;
+
+/* FitnessProvider, src/providers/fitness.rs:18-22,176-206 */
+typedef enum vl_fitness_kind {
+    VL_FITNESS_NONE = 0,          /* Option::None: host uses 1.0 (simulation.rs:62,141) */
+    VL_FITNESS_NEUTRAL = 1,       /* Neutral: raw == 1 (providers/fitness.rs:140-147) */
+    VL_FITNESS_NONEPISTATIC = 2,  /* table only */
+    VL_FITNESS_EPISTATIC = 3      /* table x sparse pair table */
+} vl_fitness_kind;
+typedef struct vl_fitness {
+    int32_t kind;
+    int32_t _pad;
+    const double *table;      /* n_sites*4, NULL for NONE/NEUTRAL */
+    const vl_epi_entry *epi;  /* n_epi entries, EPISTATIC only */
+    uint64_t n_epi;
+    vl_utility utility;
+} vl_fitness;
+
+/* HostSpec{range, host}, src/core/hosts.rs:75-78; BasicHost providers simulation.rs:22-32 */
+typedef struct vl_host_spec {
+    uint64_t lo, hi; /* range lo..hi */
+    vl_fitness reproductive;
+    vl_fitness infective;
+} vl_host_spec;
+
+/* Parameters, src/config/parameters.rs:14-47 (host_model is resolved into specs) */
+typedef struct vl_parameters {
+    double mutation_rate;
+    double recombination_rate;
+    uint64_t host_population_size;
+    double basic_reproductive_number;
+    uint64_t max_population;
+    double dilution;
+    double substitution_matrix[16]; /* [from][to] */
+    uint64_t n_hits;
+} vl_parameters;
+
+typedef struct vl_config {
+    uint64_t n_sites;
+    const uint8_t *wildtype; /* n_sites indices 0..3 */
+    vl_parameters parameters;
+    uint32_t n_specs;
+    uint32_t compartment_id;       /* Philox stream id; distinct per compartment */
+    const vl_host_spec *specs;
+    uint64_t seed;                 /* the reference is unseeded (rand::rng()); this is ours */
+    int32_t device;                /* CUDA ordinal */
+    int32_t flags;                 /* VL_FLAG_* */
+    uint64_t capacity_infectants;  /* 0 = auto (from max_population) */
+    uint64_t capacity_haplotypes;  /* 0 = auto */
+    uint64_t capacity_arena_words; /* 0 = auto; u32 words of packed mutation entries */
+} vl_config;
+
+enum {
+    VL_FLAG_ATOMIC_HOST_SUM = 1 /* sum per-host fitness with f64 atomics instead of the
+                                   reference-ordered CSR walk (not for replay) */
+};
+
+/* ---- lifecycle -------------------------------------------------------- */
+int vl_create(const vl_config *config, vl_sim **out);   /* BasicSimulation::new, simulation.rs:235-256 */
+int vl_destroy(vl_sim *sim);
+const char *vl_last_error(const vl_sim *sim);            /* NULL sim: last create error */
+int vl_abi_version(void);
+
+/* ---- Simulation trait (src/simulation.rs:177-219) ---------------------- */
+int vl_increment_generation(vl_sim *sim);                /* :178 */
+int vl_get_generation(const vl_sim *sim, uint64_t *out); /* :182 */
+int vl_set_generation(vl_sim *sim, uint64_t generation); /* shared Arc<Generation>, runner.rs:72 */
+int vl_set_parameters(vl_sim *sim, const vl_parameters *p); /* :355-363; like the reference it does
+                                                             not reach the BasicHost copies */
+int vl_population_len(vl_sim *sim, uint64_t *out);       /* get_population().len() */
+int vl_set_population_wildtype(vl_sim *sim, uint64_t n); /* population![wt; n], runner.rs:263 */
+int vl_infect(vl_sim *sim);                              /* :365-387 */
+int vl_mutate_infectants(vl_sim *sim);                   /* :389-428 */
+/* replicate_infectants, :430-485.  offspring_out may be NULL (kept on device). */
+int vl_replicate_infectants(vl_sim *sim, uint64_t *offspring_out, uint64_t n);
+/* offspring == NULL means "the device-resident map of the last replicate". */
+int vl_target_size(vl_sim *sim, const uint64_t *offspring, uint64_t n, double *out);      /* :491-503 */
+int vl_sample_indices(vl_sim *sim, const uint64_t *offspring, uint64_t n, uint64_t amount,
+                      uint64_t *indices_out);                                            /* :505-514 */
+int vl_subsample_population(vl_sim *sim, const uint64_t *offspring, uint64_t n, double factor,
+                            vl_pop **out);                                               /* :516-527 */
+int vl_select(vl_sim *sim, const uint64_t *indices, uint64_t n, vl_pop **out);            /* Population::select,
+                                                                                           population.rs:406-430 */
+/* set_population(Population::from_iter(parts)), :340-345 + population.rs:190-205. Consumes parts. */
+int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts);
+int vl_pop_len(const vl_pop *pop, uint64_t *out);
+int vl_pop_free(vl_pop *pop);
+int vl_next_generation(vl_sim *sim);                     /* default method, :200-218 */
+
+/* ---- fused, device-resident loops (what Runner::run drives, runner.rs:336-423) */
+/* n generations of a single compartment with the identity transfer; no host sync inside. */
+int vl_run(vl_sim *sim, uint64_t n_generations);
+/* one generation over several compartments living in this process.
+ * rule: 0 = parallel-build rule (runner.rs:401-416), 1 = serial-build rule (:550-631). */
+int vl_step(vl_sim *const *sims, uint32_t n_sims, const double *transfer, int rule);
+int vl_synchronize(vl_sim *sim);
+/* sum over generations of population sizes at generation start since creation/reset. */
+int vl_infectant_generations(vl_sim *sim, uint64_t *out, int reset);
+
+/* ---- replay hooks: feed recorded draws instead of Philox --------------- */
+/* infections[i] = host index or -1 (Option<usize>, hosts.rs:103). One-shot: consumed by the next vl_infect. */
+int vl_replay_infections(vl_sim *sim, const int64_t *infections, uint64_t n);
+/* per infectant CSR of (site, to-base) in the order the reference applies them (sorted sites);
+ * consumed by the next vl_mutate_infectants. */
+int vl_replay_mutations(vl_sim *sim, const uint64_t *offsets, uint64_t n, const uint32_t *sites,
+                        const uint8_t *bases);
+/* recombination events in processing order: host, slice positions i<j, window [s0,s1), which parent
+ * slot is replaced (0 -> i, 1 -> j); consumed by the next vl_mutate_infectants. */
+int vl_replay_recombinations(vl_sim *sim, uint64_t n_events, const uint64_t *host, const uint32_t *i,
+                             const uint32_t *j, const uint32_t *s0, const uint32_t *s1,
+                             const uint8_t *which);
+/* offspring counts; consumed by the next vl_replicate_infectants (λ and host sums are still computed). */
+int vl_replay_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n);
+
+/* ---- inspection / export (parity tests, final.<i>.csv, sample writers) - */
+int vl_get_infections(vl_sim *sim, int64_t *out, uint64_t n);          /* HostMapBuffer.infections */
+int vl_get_host_map(vl_sim *sim, uint64_t *offsets_out /*H+1*/, uint64_t *hosts_out /*n infected*/,
+                    uint64_t *n_infected_out);                          /* hosts.rs:166-192 */
+/* mapped fitness f_i, host sum S and lambda_i of the last replicate (NaN where not infected). */
+int vl_get_replication_terms(vl_sim *sim, double *fitness_out, double *host_sum_out, double *lambda_out,
+                             uint64_t n);
+int vl_get_offspring_prefix(vl_sim *sim, uint64_t *prefix_out, uint64_t n); /* inclusive scan */
+/* raw (pre-utility) fitness of every infectant under provider (spec, which): which 0=reproductive,1=infective */
+int vl_get_raw_fitness(vl_sim *sim, uint32_t spec, int which, double *out, uint64_t n);
+/* mutation sets: offsets_out[n+1]; then entries (pos, base) of get_mutations() sorted by pos.
+ * Call with positions_out == NULL to get the total in *n_entries. */
+int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, uint32_t *positions_out,
+                        uint8_t *bases_out, uint64_t *n_entries);
+int vl_get_base(vl_sim *sim, uint64_t infectant, uint64_t position, uint8_t *out); /* Haplotype::get_base */
+int vl_get_haplotype_ids(vl_sim *sim, uint32_t *out, uint64_t n);      /* device-local ids (labels) */
+/* counters: [0] live+dead haplotype records, [1] arena words used, [2] gc runs, [3] kernels launched */
+int vl_get_counters(vl_sim *sim, uint64_t *out4);
+int vl_collect_garbage(vl_sim *sim);
+
+/* ---- migrant exchange between handles / GPUs --------------------------- */
+/* Pack a detached population into a self-contained byte image (haplotype payload + indices) in a
+ * device buffer owned by the library; image_device/bytes stay valid until the pop is freed. */
+int vl_pop_pack_device(vl_sim *origin, vl_pop *pop, void **image_device, uint64_t *bytes);
+/* Build a detached population on `target` from a packed image located in target-device memory. */
+int vl_pop_unpack_device(vl_sim *target, const void *image_device, uint64_t bytes, vl_pop **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIROLUTION_GPU_H */
