@@ -1,0 +1,201 @@
+// vl_rng.cuh — counter-based Philox4x32-10 streams and exact samplers for the population update.
+//
+// The reference draws everything from an unseedable thread-local ChaCha12 (`rand::rng()`,
+// src/simulation.rs:368,394,413,434,462,510), so only the *distributions* of its rand/rand_distr
+// call sites can be matched:
+//   Uniform<usize>(0,n)            src/simulation.rs:47,366      -> below()
+//   rng.random::<f64>()            src/simulation.rs:64          -> u01()
+//   Bernoulli(rho)                 src/simulation.rs:49          -> bernoulli() / geometric skipping
+//   Binomial(L, mu)                src/simulation.rs:48          -> binomial()  (BINV | BTRS, exact)
+//   WeightedIndex(row of 4)        src/simulation.rs:107-110     -> weighted4()
+//   Poisson(lambda)                src/simulation.rs:148-151     -> poisson()   (Knuth | PTRS, exact)
+// Every stream is keyed by (seed, compartment) and addressed by (index, generation, phase), so a
+// draw does not depend on launch geometry, block scheduling or the number of GPUs.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+namespace vl {
+
+enum Phase : uint32_t {
+    PH_INFECT = 1, PH_MUTCOUNT = 2, PH_MUTATE = 3, PH_RECOMB = 4, PH_OFFSPRING = 5, PH_PLAN = 6,
+    PH_RESAMPLE = 7, PH_MIGRANT = 8, PH_TEST = 9
+};
+
+struct Philox {
+    uint32_t key0, key1;
+    uint32_t c0, c1, c2, c3;
+    uint32_t out[4];
+    int have;
+
+    __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+#ifdef __CUDA_ARCH__
+        hi = __umulhi(a, b);
+        lo = a * b;
+#else
+        uint64_t p = (uint64_t)a * b;
+        hi = (uint32_t)(p >> 32);
+        lo = (uint32_t)p;
+#endif
+    }
+    __host__ __device__ inline void block() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            uint32_t hi0, lo0, hi1, lo1;
+            mulhilo(0xD2511F53u, x0, hi0, lo0);
+            mulhilo(0xCD9E8D57u, x2, hi1, lo1);
+            uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        }
+        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
+        c3 += 1;  // low 24 bits of c3 count blocks within a stream
+        have = 4;
+    }
+    // stream (index, generation, phase) under key (seed ^ compartment)
+    __host__ __device__ inline Philox(uint64_t seed, uint32_t compartment, uint32_t generation, uint32_t phase,
+                                      uint64_t index) {
+        uint64_t k = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(compartment + 1);
+        k ^= k >> 31;
+        key0 = (uint32_t)k; key1 = (uint32_t)(k >> 32);
+        c0 = (uint32_t)index; c1 = (uint32_t)(index >> 32); c2 = generation; c3 = phase << 24;
+        have = 0;
+    }
+    __host__ __device__ inline uint32_t u32() {
+        if (have == 0) block();
+        return out[4 - (have--)];
+    }
+    __host__ __device__ inline uint64_t u64() {
+        uint64_t lo = u32();
+        uint64_t hi = u32();
+        return (hi << 32) | lo;
+    }
+    // rand's random::<f64>(): 53 random bits * 2^-53, in [0,1)
+    __host__ __device__ inline double u01() { return (double)(u64() >> 11) * (1.0 / 9007199254740992.0); }
+    // strictly inside (0,1): for samplers that take logs
+    __host__ __device__ inline double u01_open() { return ((double)(u64() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+    // Uniform integer in [0,n), n >= 1: widening multiply with rejection (unbiased)
+    __host__ __device__ inline uint64_t below(uint64_t n) {
+        if (n <= 0xFFFFFFFFull) {
+            uint32_t n32 = (uint32_t)n;
+            uint64_t m = (uint64_t)u32() * n32;
+            uint32_t l = (uint32_t)m;
+            if (l < n32) {
+                uint32_t t = (uint32_t)(-n32) % n32;
+                while (l < t) { m = (uint64_t)u32() * n32; l = (uint32_t)m; }
+            }
+            return m >> 32;
+        }
+        for (;;) {
+            uint64_t x = u64();
+#ifdef __CUDA_ARCH__
+            uint64_t hi = __umul64hi(x, n);
+#else
+            uint64_t hi = (uint64_t)(((unsigned __int128)x * n) >> 64);
+#endif
+            uint64_t lo = x * n;
+            if (lo >= n) return hi;
+            uint64_t t = (0 - n) % n;
+            if (lo >= t) return hi;
+        }
+    }
+    __host__ __device__ inline bool bernoulli(double p) {
+        if (p >= 1.0) return true;
+        if (!(p > 0.0)) return false;
+        return u64() < (uint64_t)(p * 18446744073709551616.0);
+    }
+};
+
+// log(k!) - Stirling tail, as used by the transformed-rejection samplers (Hoermann 1993)
+__host__ __device__ inline double stirling_tail(double k) {
+    const double tail[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509,
+                             0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,
+                             0.00925546218271273, 0.00833056343336287};
+    if (k <= 9.0) return tail[(int)k];
+    double kp1sq = (k + 1.0) * (k + 1.0);
+    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / (k + 1.0);
+}
+
+// Binomial(n, p), exact.  n*min(p,1-p) < 10: sequential inversion (the BINV branch rand_distr 0.5.1 also
+// uses for small means); otherwise BTRS transformed rejection (same distribution as rand_distr's BTPE).
+__host__ __device__ inline uint64_t binomial(Philox &g, uint64_t n, double p) {
+    if (n == 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    const bool flipped = p > 0.5;
+    if (flipped) p = 1.0 - p;
+    const double dn = (double)n;
+    uint64_t x;
+    if (dn * p < 10.0) {
+        const double q = 1.0 - p, s = p / q, a = (dn + 1.0) * s;
+        const double r0 = exp(dn * log1p(-p));
+        for (;;) {
+            double r = r0, u = g.u01();
+            uint64_t k = 0;
+            while (u > r) {
+                u -= r;
+                k += 1;
+                if (k > 200 || k > n) break;
+                r *= a / (double)k - s;
+            }
+            if (k <= 200 && k <= n) { x = k; break; }
+        }
+    } else {
+        const double spq = sqrt(dn * p * (1.0 - p));
+        const double b = 1.15 + 2.53 * spq, a = -0.0873 + 0.0248 * b + 0.01 * p, c = dn * p + 0.5;
+        const double vr = 0.92 - 4.2 / b, r = p / (1.0 - p), alpha = (2.83 + 5.1 / b) * spq;
+        const double m = floor((dn + 1.0) * p);
+        for (;;) {
+            double u = g.u01_open() - 0.5, v = g.u01_open();
+            double us = 0.5 - fabs(u);
+            double k = floor((2.0 * a / us + b) * u + c);
+            if (us >= 0.07 && v <= vr) { x = (uint64_t)k; break; }
+            if (k < 0.0 || k > dn) continue;
+            v = log(v * alpha / (a / (us * us) + b));
+            double upper = (m + 0.5) * log((m + 1.0) / (r * (dn - m + 1.0))) +
+                           (dn + 1.0) * log((dn - m + 1.0) / (dn - k + 1.0)) +
+                           (k + 0.5) * log(r * (dn - k + 1.0) / (k + 1.0)) + stirling_tail(m) +
+                           stirling_tail(dn - m) - stirling_tail(k) - stirling_tail(dn - k);
+            if (v <= upper) { x = (uint64_t)k; break; }
+        }
+    }
+    return flipped ? n - x : x;
+}
+
+// Poisson(lambda) for finite lambda > 0, exact.  lambda < 12: Knuth's product method (the branch
+// rand_distr 0.5.1 uses there); otherwise PTRS transformed rejection (same distribution as its
+// Cauchy-envelope rejection).
+__host__ __device__ inline uint64_t poisson(Philox &g, double lambda) {
+    if (lambda < 12.0) {
+        const double limit = exp(-lambda);
+        uint64_t k = 0;
+        double p = g.u01();
+        while (p > limit) { p *= g.u01(); k += 1; }
+        return k;
+    }
+    const double slam = sqrt(lambda), loglam = log(lambda);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (;;) {
+        double u = g.u01_open() - 0.5, v = g.u01_open();
+        double us = 0.5 - fabs(u);
+        double k = floor((2.0 * a / us + b) * u + lambda + 0.43);
+        if (us >= 0.07 && v <= vr) return (uint64_t)k;
+        if (k < 0.0 || (us < 0.013 && v > us)) continue;
+        if (log(v) + log(invalpha) - log(a / (us * us) + b) <= -lambda + k * loglam - lgamma(k + 1.0)) return (uint64_t)k;
+    }
+}
+
+// rand WeightedIndex<f64> over one substitution row: cumulative weights, chosen ~ U[0,total),
+// index = partition_point(cum <= chosen)
+__host__ __device__ inline int weighted4(Philox &g, const double *w) {
+    double c0 = w[0], c1 = c0 + w[1], c2 = c1 + w[2], total = c2 + w[3];
+    double chosen = g.u01() * total;
+    int idx = 0;
+    if (c0 <= chosen) idx = 1;
+    if (c1 <= chosen) idx = 2;
+    if (c2 <= chosen) idx = 3;
+    return idx;
+}
+
+}  // namespace vl

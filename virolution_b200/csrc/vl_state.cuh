@@ -1,0 +1,220 @@
+// vl_state.cuh — device-resident state of one compartment and the haplotype record format.
+//
+// Layout in HBM (structure of arrays, one set per vl_sim):
+//   population     hap_id[n]            u32   id of each infectant's haplotype      (Population.population,
+//                                                                                     src/core/population.rs:156-163)
+//   host map       host_id[n]           u32   Option<host> with NONE sentinel        (HostMapBuffer.infections,
+//                  offsets[H+1], hosts[n_infected] u32  CSR by host                   src/core/hosts.rs:133-192)
+//   replication    fit[n] f64, hsum[H] f64, offspring[n] u32, tile_sum[] u64
+//   haplotypes     h_off[u64] h_len[u32] h_parent[u32] h_raw[provider][f64]  + arena of u32 entries
+//
+// A haplotype record is the *flattened* form of the reference's delta chain (Wildtype / Mutant{changes} /
+// Recombinant{left,right,window}, src/core/haplotype.rs:45-56,241-288): the position-sorted list of sites where
+// the haplotype differs from the wildtype, one u32 entry per site:
+//       entry = pos << 8 | g << 4 | m
+//   g = what Haplotype::get_base(pos) returns            (first matching change wins,  haplotype.rs:661-667)
+//   m = what Haplotype::get_mutations()[pos] holds, 4 if absent (last change wins, back-mutation to the
+//       wildtype base removes the key,                                                   haplotype.rs:686-705)
+// The two views differ only after one mutation event hit the same site twice (sites are drawn with
+// replacement, src/simulation.rs:94-103); keeping both makes the flattened record answer every query the
+// chain answers.  Raw fitness per provider is computed once when the record is created, exactly as
+// FitnessProvider::get_fitness would on first touch (src/providers/fitness.rs:212-228), and memoised in
+// h_raw (AttributeSet, src/core/attributes.rs:196-217).
+#pragma once
+#include <stdint.h>
+#include "../../include/virolution_gpu.h"
+
+namespace vl {
+
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+constexpr int MAX_SPECS = 8;
+constexpr int MAX_PROVIDERS = 16;
+constexpr uint32_t RESAMPLE_TILE = 2048;  // infectants per resample tile (one CTA stages one tile in smem)
+
+// error bits raised by kernels (sticky until vl_* reports them)
+enum DevError : uint32_t {
+    DE_HAP_CAPACITY = 1u,       // haplotype table full
+    DE_ARENA_CAPACITY = 2u,     // arena full
+    DE_ALL_ZERO_WEIGHTS = 4u,   // WeightedAliasIndex::new panics (src/core/population.rs:386)
+    DE_UNDEFINED_OFFSPRING = 8u,// Poisson::new failed on a non-zero fitness (src/simulation.rs:148-151)
+    DE_SAME_BASE = 16u,         // assert_ne!(from, to) (src/core/haplotype.rs:250)
+    DE_INF_CAPACITY = 32u,      // population buffer too small
+    DE_OFFSPRING_RANGE = 64u,   // offspring count does not fit u32
+    DE_REPLAY = 128u            // malformed replay log
+};
+
+struct EpiDir {  // one direction of a symmetric pair entry (src/core/fitness/epistasis.rs:44-58)
+    uint32_t k1, k2;  // (pos << 2) | base
+    double v;
+};
+
+struct DevProvider {
+    int32_t kind;  // vl_fitness_kind
+    int32_t util_kind;
+    double upper, hill_k, hill_n;
+    const double *table;  // L*4
+    const EpiDir *epi;    // sorted by (k1, k2), duplicates resolved (last insert wins)
+    uint32_t n_epi;
+    uint32_t _pad;
+};
+
+struct DevSpec {
+    uint64_t lo, hi;
+    int32_t repro, infect;  // provider index or -1
+};
+
+struct DevState {
+    // ---- configuration (BasicHost.parameters are the values captured at vl_create, the simulation's
+    //      are updatable through vl_set_parameters; src/simulation.rs:41-52 vs :351-363)
+    uint32_t L;
+    uint32_t n_specs, n_providers;
+    uint32_t compartment;
+    uint64_t seed;
+    double host_mutation_rate, host_recombination_rate, host_r0;
+    double host_subst[16];
+    uint64_t H;            // simulation.parameters.host_population_size
+    uint64_t n_hits;
+    double dilution;
+    uint64_t max_population;
+    DevSpec specs[MAX_SPECS];
+    DevProvider prov[MAX_PROVIDERS];
+    const uint8_t *wildtype;
+
+    // ---- population
+    uint64_t n;            // current number of infectants
+    uint64_t n_next;       // size of the population being assembled
+    uint64_t cap_inf;
+    uint32_t *hap_id;      // current
+    uint32_t *hap_id_next; // being assembled
+    uint32_t generation;
+    uint32_t error;
+    uint64_t infectant_generations;
+
+    // ---- host map
+    uint32_t *host_id, *rank, *offsets, *hosts;
+    uint32_t *heavy_hosts; // worklist of hosts whose slice exceeds the thread tier
+    uint32_t n_heavy;
+    uint32_t n_infected_valid;
+
+    // ---- mutation worklist
+    uint32_t *mut_list;    // infectant indices with n_mut > 0
+    uint32_t *mut_count;   // n_mut per worklist entry
+    uint32_t n_mut_list;
+    uint32_t _pad0;
+
+    // ---- replication
+    double *fit, *hsum;
+    uint32_t *offspring;
+    uint64_t *tile_sum;    // per resample tile
+    uint64_t *tile_tree;   // segment tree over tile sums (plan kernel)
+    uint64_t *tile_cnt;    // draws per tree node / tile
+    uint64_t *tile_base;   // exclusive scan of draws per tile
+    uint64_t offspring_total;
+    double target_size;    // of the last plan
+
+    // ---- haplotype table (double-buffered for compaction; the live set is swapped on device)
+    uint64_t cap_hap, cap_arena;
+    unsigned long long n_hap;
+    unsigned long long arena_top;
+    uint32_t gc_active;
+    uint32_t _pad1;
+    uint64_t *h_off, *h_off_alt;
+    uint32_t *h_len, *h_len_alt;
+    uint32_t *h_parent, *h_parent_alt;
+    double *h_raw[MAX_PROVIDERS], *h_raw_alt[MAX_PROVIDERS];
+    uint32_t *arena, *arena_alt;
+    uint32_t *gc_mark, *gc_newid, *gc_len;
+    uint64_t *gc_newoff;
+    uint64_t gc_hap_threshold, gc_arena_threshold;
+    uint64_t gc_runs;
+    uint64_t kernels_launched;  // maintained by the host, mirrored here for export
+};
+
+// ---- entry helpers ---------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t make_entry(uint32_t pos, uint32_t g, uint32_t m) { return (pos << 8) | (g << 4) | m; }
+__host__ __device__ inline uint32_t entry_pos(uint32_t e) { return e >> 8; }
+__host__ __device__ inline uint32_t entry_g(uint32_t e) { return (e >> 4) & 0xF; }
+__host__ __device__ inline uint32_t entry_m(uint32_t e) { return e & 0xF; }  // 4 = not in the mutation set
+
+// lower bound by position in a sorted entry list
+__host__ __device__ inline uint32_t entries_lower(const uint32_t *e, uint32_t n, uint32_t pos) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (entry_pos(e[mid]) < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// Haplotype::get_base (src/core/haplotype.rs:402-408)
+__host__ __device__ inline uint32_t entries_get_base(const uint32_t *e, uint32_t n, uint32_t pos, const uint8_t *wt) {
+    uint32_t i = entries_lower(e, n, pos);
+    if (i < n && entry_pos(e[i]) == pos) return entry_g(e[i]);
+    return wt[pos];
+}
+// get_mutations().get(pos): base index or 4 when absent
+__host__ __device__ inline uint32_t entries_get_mut(const uint32_t *e, uint32_t n, uint32_t pos) {
+    uint32_t i = entries_lower(e, n, pos);
+    if (i < n && entry_pos(e[i]) == pos) return entry_m(e[i]);
+    return 4;
+}
+
+// UtilityFunction::apply (src/core/fitness/utility.rs:48-60); same operation order as written there
+__host__ __device__ inline double utility_apply(const DevProvider &p, double f) {
+    if (p.util_kind == VL_UTILITY_ALGEBRAIC) {
+        double factor = 1. / (p.upper - 1.);
+        return p.upper * factor * f / (1. + factor * f);
+    }
+    if (p.util_kind == VL_UTILITY_HILL) {
+        double fp = pow(f, p.hill_n);
+        return fp / (p.hill_k + fp);
+    }
+    return f;
+}
+
+// nested-map row lookup: [lo,hi) of directed entries keyed k1
+__host__ __device__ inline void epi_row(const DevProvider &p, uint32_t k1, uint32_t &lo_out, uint32_t &hi_out) {
+    uint32_t lo = 0, hi = p.n_epi;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (p.epi[mid].k1 < k1) lo = mid + 1; else hi = mid; }
+    uint32_t b = lo;
+    hi = p.n_epi;
+    uint32_t a = lo;
+    while (a < hi) { uint32_t mid = (a + hi) >> 1; if (p.epi[mid].k1 <= k1) a = mid + 1; else hi = mid; }
+    lo_out = b; hi_out = a;
+}
+__host__ __device__ inline bool epi_get(const DevProvider &p, uint32_t lo, uint32_t hi, uint32_t k2, double &v) {
+    uint32_t a = lo, b = hi;
+    while (a < b) { uint32_t mid = (a + b) >> 1; if (p.epi[mid].k2 < k2) a = mid + 1; else b = mid; }
+    if (a < hi && p.epi[a].k2 == k2) { v = p.epi[a].v; return true; }
+    return false;
+}
+__host__ __device__ inline uint32_t ekey(uint32_t pos, uint32_t base) { return (pos << 2) | base; }
+
+// FitnessTable::compute_fitness x EpistasisTable::compute_fitness over a flattened record
+// (src/core/fitness/table.rs:72-79, src/core/fitness/epistasis.rs:176-193).  The reference multiplies in
+// HashMap iteration order; here the order is ascending position (1e-12 relative tolerance applies, see
+// DESIGN.md).  The epistatic factor keeps the reference's "partner absent" rule.
+__host__ __device__ inline double compute_fitness_full(const DevProvider &p, const uint32_t *e, uint32_t n) {
+    if (p.kind == VL_FITNESS_NEUTRAL) return 1.0;
+    double acc = 1.;
+    for (uint32_t k = 0; k < n; k++) {
+        uint32_t m = entry_m(e[k]);
+        if (m < 4) acc = acc * p.table[(uint64_t)entry_pos(e[k]) * 4 + m];
+    }
+    if (p.kind == VL_FITNESS_EPISTATIC) {
+        double fitness = 1.;
+        for (uint32_t k = 0; k < n; k++) {
+            uint32_t m = entry_m(e[k]);
+            if (m >= 4) continue;
+            uint32_t lo, hi;
+            epi_row(p, ekey(entry_pos(e[k]), m), lo, hi);
+            for (uint32_t q = lo; q < hi; q++) {
+                uint32_t qpos = p.epi[q].k2 >> 2, qb = p.epi[q].k2 & 3;
+                if (qpos > entry_pos(e[k]) && entries_get_mut(e, n, qpos) != qb) fitness *= p.epi[q].v;
+            }
+        }
+        acc = acc * fitness;
+    }
+    return acc;
+}
+
+}  // namespace vl
