@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — infectant-generations/sec of the B200 population-update path (BASELINE.json metric).
+
+A "step" is one generation (infect -> mutate -> fitness -> replicate -> subsample/transmit) of the workload.
+    python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA path through the C ABI)
+    python bench.py --impl reference ...                     the reference's CPU algorithm (oracle port, host cores)
+    torchrun ... bench.py --gpus N ...                       one compartment per GPU + NCCL migrant exchange (weak scaling)
+
+Lines of the JSON object:
+  value         device-resident loop (vl_run), timed with CUDA events on the library's stream, max over ranks
+  e2e           the trait-level calls a `impl Simulation for GpuSimulation` makes, with HOST offspring vectors:
+                replicate_infectants -> Vec<usize> (D2H), subsample_population(&offspring) (H2D), set_population
+  roofline      dominant kernel: algorithmic bytes per launch / average CUDA-event duration vs measured HBM peak
+  cpu_baseline  the oracle (CPU restatement of the reference loop) on a bounded sample, rank 0, N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "infectant-generations/sec"
+UNIT = "infectant-generations/s"
+
+# Algorithmic bytes per infectant for each kernel of the generation.
+# u32 ids/hosts/offspring, f64 fitness.  "per host" terms are multiplied by H/N (= 1 for the K configs).
+ALGO_BYTES = {
+    "k_infect": 4 + 4 + 8,              # write host_id, write rank, histogram read-modify-write (4+4)
+    "k_scatter_hosts": 4 + 4 + 4 + 4,   # read host_id, rank, gather offsets[h], scatter hosts[]
+    "k_sort_slices": 8,                 # read offsets[h], offsets[h+1] (per host)
+    "k_mutation_counts": 4,             # read host_id
+    "k_fitness": 4 + 4 + 8 + 8,         # read host_id, hap_id, gather raw fitness, write fit
+    "k_host_sum": 8 + 4 + 8 + 8,        # per host: offsets pair; per infectant: hosts[], gather fit; per host: write hsum
+    "k_offspring": 4 + 8 + 8 + 4,       # read host_id, fit, gather hsum, write offspring
+    "k_resample": 4 + 4 + 4,            # read offspring, hap_id (tile staging), write next hap_id
+    "(k_scan_u32<OutT, EXCL>)": 4 + 4,  # per host: read count, write offsets
+}
+FITNESS_REPLICATION = ("k_fitness", "k_host_sum", "k_offspring", "k_resample")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="k2_hiv")
+    ap.add_argument("--n", type=int, default=0, help="override N = H = max_population")
+    ap.add_argument("--atomic-host-sum", action="store_true", help="VL_FLAG_ATOMIC_HOST_SUM (not the default path)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=10)
+    ap.add_argument("--cpu-steps", type=int, default=0, help="generations of the cpu_baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, name in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def pinned_u64(n):
+    import torch
+    t = torch.empty(max(n, 1), dtype=torch.int64, pin_memory=True)
+    return t, t.numpy().view(np.uint64)
+
+
+def trait_generation(sim, off_host):
+    """One generation the way Runner::run drives `dyn Simulation` (src/runner.rs:382-422), host offspring vector."""
+    n = sim.population_len()
+    sim.increment_generation()
+    sim.infect()
+    sim.mutate_infectants()
+    off = sim.replicate_infectants(out=off_host[:n])           # Vec<usize> back to the host
+    pop = sim.subsample_population(off, 1.0)                   # &[usize] from the host
+    sim.set_population(pop)
+    return n
+
+
+def run_b200(args, rank, world):
+    from virolution_b200 import abi
+    from virolution_b200.simulation import GpuSimulation
+    from virolution_b200.workloads import workload
+    dist = None
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = workload(args.workload, args.n or None)
+    flags = abi.VL_FLAG_ATOMIC_HOST_SUM if args.atomic_host_sum else 0
+    par = wl["parameters"]
+    N = wl["n0"]
+    sim = GpuSimulation(wl["wildtype"], par, wl["specs"], seed=2026, device=local_rank, compartment_id=rank, flags=flags)
+    sim.set_population_wildtype(N)
+    runner = None
+    if world > 1:
+        from virolution_b200.distributed import CompartmentRing
+        runner = CompartmentRing(sim, rank, world, migration=0.1)
+
+    def advance(k):
+        if runner is None:
+            sim.run(k)
+        else:
+            for _ in range(k):
+                runner.step()
+
+    def barrier():
+        sim.synchronize()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (untimed): also brings haplotype diversity towards its quasi-steady state
+    advance(max(args.warmup, 3))
+    barrier()
+    sim.infectant_generations(reset=True)
+    l0 = sim.get_counters()["kernels_launched"]
+    # ---- timed region: exactly K generations, device-resident
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_wall = time.perf_counter()
+        sim.timer_start()
+        advance(args.steps)
+        ms = sim.timer_stop()
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+    ig = sim.infectant_generations(reset=True)
+    launches = sim.get_counters()["kernels_launched"] - l0
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, float(ig)], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ig = float(tmax[0]), int(tsum[1])
+    value = ig / (ms / 1e3)
+
+    # ---- per-kernel CUDA-event durations over the same loop (separate pass: events perturb the step time)
+    roofline, kernels = None, {}
+    if rank == 0:
+        sim.profile(True)
+        sim.run(args.profile_steps) if runner is None else [runner.step() for _ in range(args.profile_steps)]
+        sim.synchronize()
+        rep = sim.profile_report()
+        sim.profile(False)
+        n_now = sim.population_len()
+        peak, peak_src = measured_peak()
+        tot_ms = sum(v[1] for v in rep.values())
+        for name, (cnt, tms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
+            per_launch_ms = tms / cnt
+            ab = ALGO_BYTES.get(name)
+            kernels[name] = {"launches_per_step": cnt / args.profile_steps, "ms_per_launch": round(per_launch_ms, 5),
+                             "share": round(tms / tot_ms, 4)}
+            if ab is not None:
+                kernels[name]["GBps"] = round(ab * n_now / (per_launch_ms * 1e-3) / 1e9, 1)
+        dom = max((k for k in rep if k in ALGO_BYTES), key=lambda k: rep[k][1])
+        dcnt, dms = rep[dom]
+        achieved = ALGO_BYTES[dom] * n_now / (dms / dcnt * 1e-3) / 1e9
+        fr_ms = sum(rep[k][1] / args.profile_steps for k in FITNESS_REPLICATION if k in rep)
+        fr_bytes = 72.0 * n_now  # fitness + replication + scan/resample
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_infectant": ALGO_BYTES[dom], "infectants_per_launch": n_now,
+                    "fitness_replication_group": {"kernels": [k for k in FITNESS_REPLICATION if k in rep],
+                                                  "ms_per_generation": round(fr_ms, 5), "algorithmic_bytes_per_infectant": 72,
+                                                  "achieved": round(fr_bytes / (fr_ms * 1e-3) / 1e9, 1),
+                                                  "frac": round(fr_bytes / (fr_ms * 1e-3) / 1e9 / peak, 4)}}
+
+    # ---- end to end through the trait-level C-ABI calls with host buffers
+    e2e = None
+    if not args.no_e2e and runner is None:
+        keep, off_host = pinned_u64(max(N, par.max_population) * 2)
+        for _ in range(3):
+            trait_generation(sim, off_host)
+        sim.synchronize()
+        k_e2e = max(5, min(args.steps, 20))
+        t0 = time.perf_counter()
+        total, bytes_d2h, bytes_h2d = 0, 0, 0
+        for _ in range(k_e2e):
+            n = trait_generation(sim, off_host)
+            total += n
+            bytes_d2h += 8 * n + 8
+            bytes_h2d += 8 * n
+        sim.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d // k_e2e, "d2h_bytes_per_step": bytes_d2h // k_e2e,
+               "steps": k_e2e, "api": "vl_infect/vl_mutate_infectants/vl_replicate_infectants(host Vec<usize>)/vl_subsample_population(host &[usize])/vl_set_population"}
+    elif runner is not None and not args.no_e2e:
+        e2e = runner.e2e(args.steps)
+
+    out = None
+    if rank == 0:
+        clk = clocks.summary()
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "impl": "b200",
+               "config": {"workload": wl["description"], "compartments": world,
+                          "parallelism": "1 compartment" if world == 1 else f"{world} compartments, 1 per GPU, NCCL all-to-all of migrants (0.9 stay / 0.1 migrate)",
+                          "l2_policy": "working set (per-infectant arrays, 32 B x N) larger than L2; no flush" if N * 32 > 126e6 else "working set fits L2 (latency-bound config); no flush",
+                          "host_sum": "atomic" if args.atomic_host_sum else "reference-ordered CSR"},
+               "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clk, "roofline": roofline, "kernels": kernels,
+               "e2e": e2e}
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, wl, threads=1)
+    sim.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_baseline(args, wl, threads):
+    """The oracle (CPU restatement of the reference loop; kind "port") on a bounded sample of the same workload."""
+    from oracle.oracle import OracleWorld
+    N = wl["n0"]
+    steps = args.cpu_steps or max(2, min(10, int(2.0e7 // max(N, 1)) + 2))
+    w = OracleWorld(wl["wildtype"], wl["parameters"], wl["specs"], n_compartments=1, seed=7, n_threads=threads)
+    w.set_population_wildtype(N)
+    w.next_generation()  # first touch of every buffer
+    ig0 = w.infectant_generations()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.next_generation()
+    dt = time.perf_counter() - t0
+    ig = w.infectant_generations() - ig0
+    return {"value": ig / dt, "unit": UNIT, "cores": w.num_threads(), "kind": "port",
+            "sample": f"{steps} generations of the same workload (N={N}) after 1 warm-up generation; oracle/vl_oracle.c, "
+                      f"{w.num_threads()} thread(s), parallel only where the reference's rayon build is (per-host mutation)",
+            "seconds": dt}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm for this path.  The Rust crate cannot be built in this image
+    (no cargo/rustc, nightly-only), so this is the oracle port with all the host threads it can use."""
+    if rank != 0:
+        return None
+    from virolution_b200.workloads import workload
+    wl = workload(args.workload, args.n or None)
+    threads = os.cpu_count() or 1
+    from oracle.oracle import OracleWorld
+    N = wl["n0"]
+    # bounded sample: the same population, as many generations as fit the budget
+    w = OracleWorld(wl["wildtype"], wl["parameters"], wl["specs"], n_compartments=1, seed=7, n_threads=threads)
+    w.set_population_wildtype(N)
+    warm = min(args.warmup, 2)
+    for _ in range(max(warm, 1)):
+        w.next_generation()
+    steps = max(1, min(args.steps, 8))
+    ig0 = w.infectant_generations()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        w.next_generation()
+    dt = time.perf_counter() - t0
+    ig = w.infectant_generations() - ig0
+    value = ig / dt
+    sample = (f"{steps} generations of the workload (N={N}), {w.num_threads()} OpenMP threads where the reference's rayon build is "
+              f"parallel (per-host mutation; infect/replicate/sample are serial like the reference)")
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warm, 1),
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference", "config": {"workload": wl["description"], "compartments": 1},
+            "gpu_launches": 0,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": w.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = run_reference(args, rank, world) if args.impl == "reference" else run_b200(args, rank, world)
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -203,6 +203,18 @@ int vl_pop_pack_device(vl_sim *origin, vl_pop *pop, void **image_device, uint64_
 /* Build a detached population on `target` from a packed image located in target-device memory. */
 int vl_pop_unpack_device(vl_sim *target, const void *image_device, uint64_t bytes, vl_pop **out);
 
+/* ---- measurement hooks (bench.py): CUDA events on the handle's own stream ------------------ */
+int vl_timer_start(vl_sim *sim);
+int vl_timer_stop(vl_sim *sim, double *ms_out);            /* synchronises; device time since vl_timer_start */
+int vl_profile(vl_sim *sim, int enable);                   /* bracket every kernel launch with events */
+int vl_profile_report(vl_sim *sim, char *buf, uint64_t cap); /* "<kernel> <launches> <total_ms>\n" per kernel */
+
+/* ---- device sampler hooks (distribution tests of the Philox-driven samplers that stand in for
+ * rand_distr 0.5.1 Poisson / Binomial and rand 0.9.0 Uniform; call sites src/simulation.rs:47-48,148-151) */
+int vl_test_poisson(uint64_t seed, double lambda, uint64_t n, uint64_t *out);
+int vl_test_binomial(uint64_t seed, uint64_t trials, double p, uint64_t n, uint64_t *out);
+int vl_test_below(uint64_t seed, uint64_t bound, uint64_t n, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,1263 @@
+// virolution_gpu.cu — the C ABI of include/virolution_gpu.h on top of the sm_100a kernels.
+//
+// One vl_sim = one compartment (BasicSimulation, reference src/simulation.rs:221-256) resident on one GPU:
+// it owns a stream, the structure-of-arrays population, the host map, the haplotype table/arena and the
+// scratch of every kernel.  All sizes that change from generation to generation (population size, number
+// of haplotypes, arena top) live in DevState on the device, so vl_next_generation / vl_run enqueue whole
+// generations without a host round trip; only the trait-level calls that hand data to the host synchronise.
+// There is no CPU fallback anywhere in this file: without a device every entry point fails with VL_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "vl_kernels.cuh"
+#include "vl_migrate.cuh"
+
+using namespace vl;
+
+#define VL_API extern "C" __attribute__((visibility("default")))
+
+struct vl_pop {
+    vl_sim *owner;
+    uint32_t *ids;   // device, haplotype ids local to owner
+    uint64_t n;      // valid after finalisation
+    uint64_t cap;
+    uint8_t *image;  // packed image (vl_pop_pack_device), device
+    uint64_t image_bytes;
+    int pending_slot;  // pinned slot that receives n, -1 when final
+};
+
+struct vl_sim {
+    int device = 0;
+    int n_sms = 148;
+    int flags = 0;
+    cudaStream_t stream = nullptr;
+    std::recursive_mutex mu;
+    DevState h;            // host mirror: configuration + buffer pointers (dynamic fields live on the device)
+    DevState *d = nullptr;
+    uint32_t *count = nullptr;   // H+1 histogram of infections
+    uint64_t cap_H = 0;
+    uint64_t *scan_work = nullptr;
+    uint64_t scan_work_words = 0;
+    uint64_t *gc_totals = nullptr;  // [0],[1] gc; [2],[3] pack; [4],[5] reserve; [6] export total
+    uint64_t *stage64 = nullptr;    // cap_inf u64: offspring/indices staging
+    uint64_t *pin = nullptr;        // pinned host scratch, PIN_SLOTS u64
+    std::vector<void *> fixed_allocs;
+    // replay logs (device copies), consumed by the next matching phase
+    int64_t *rp_inf = nullptr; bool has_rp_inf = false;
+    uint64_t *rp_mut_off = nullptr; uint32_t *rp_mut_sites = nullptr; uint8_t *rp_mut_bases = nullptr; bool has_rp_mut = false;
+    uint64_t *rp_rec_host = nullptr; uint32_t *rp_rec_i = nullptr, *rp_rec_j = nullptr, *rp_rec_s0 = nullptr, *rp_rec_s1 = nullptr;
+    uint8_t *rp_rec_which = nullptr; uint64_t rp_rec_n = 0; bool has_rp_rec = false;
+    uint64_t *rp_off = nullptr; bool has_rp_off = false;
+    std::vector<vl_pop *> pops;
+    uint64_t launches = 0;
+    uint64_t n_known = 0; bool n_valid = false;   // host knowledge of the population size
+    uint64_t n_bound = 0;                         // upper bound of the population size (launch geometry)
+    bool csr_valid = false;
+    uint32_t salt = 0;        // distinguishes the sampling streams of one generation
+    uint32_t gens_since_gc = 0, gc_period = 1;
+    int next_slot = 8;
+    // measurement hooks: per-launch CUDA events on this handle's stream
+    bool profiling = false;
+    struct ProfRec { const char *name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+    char err[512] = {0};
+};
+
+// records the start event of a profiled launch and returns the stop event to record after it
+static cudaEvent_t prof_begin(vl_sim *sim, const char *name) {
+    if (sim->prof.size() >= (1u << 20)) return nullptr;
+    vl_sim::ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return nullptr;
+    cudaEventRecord(r.a, sim->stream);
+    sim->prof.push_back(r);
+    return r.b;
+}
+
+static thread_local char g_create_err[512];
+constexpr int PIN_SLOTS = 4096;
+
+static int fail(vl_sim *sim, int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(sim ? sim->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(sim, expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return fail(sim, VL_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+#define TRY(expr)                  \
+    do {                           \
+        int r_ = (expr);           \
+        if (r_ != VL_OK) return r_; \
+    } while (0)
+#define LAUNCH(sim, kernel, grid, block, smem, ...)                         \
+    do {                                                                    \
+        cudaEvent_t pe_ = (sim)->profiling ? prof_begin(sim, #kernel) : nullptr; \
+        kernel<<<(grid), (block), (smem), (sim)->stream>>>(__VA_ARGS__);    \
+        if (pe_) cudaEventRecord(pe_, (sim)->stream);                       \
+        (sim)->launches++;                                                  \
+    } while (0)
+#define ENTER(sim)                                                   \
+    if (!(sim)) return fail(nullptr, VL_ERR_ARGUMENT, "null handle"); \
+    std::lock_guard<std::recursive_mutex> lock_((sim)->mu);           \
+    CU(sim, cudaSetDevice((sim)->device))
+
+static inline unsigned grid_for(const vl_sim *sim, uint64_t n, unsigned per_sm = 8) {
+    uint64_t g = (n + TPB - 1) / TPB;
+    uint64_t cap = (uint64_t)sim->n_sms * per_sm;
+    if (g > cap) g = cap;
+    return (unsigned)(g ? g : 1);
+}
+static inline unsigned grid_tiles(const vl_sim *sim, uint64_t n_items, uint64_t tile, unsigned per_sm = 8) {
+    uint64_t g = (n_items + tile - 1) / tile;
+    uint64_t cap = (uint64_t)sim->n_sms * per_sm;
+    if (g > cap) g = cap;
+    return (unsigned)(g ? g : 1);
+}
+
+template <typename T>
+static int dev_alloc(vl_sim *sim, T **p, uint64_t count, bool fixed = true) {
+    void *q = nullptr;
+    CU(sim, cudaMalloc(&q, std::max<uint64_t>(count, 1) * sizeof(T)));
+    *p = (T *)q;
+    if (fixed) sim->fixed_allocs.push_back(q);
+    return VL_OK;
+}
+#define FIELD_OFF(f) offsetof(DevState, f)
+template <typename T>
+static int read_field(vl_sim *sim, size_t off, T *out) {
+    CU(sim, cudaMemcpyAsync(sim->pin, (const char *)sim->d + off, sizeof(T), cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    memcpy(out, sim->pin, sizeof(T));
+    return VL_OK;
+}
+template <typename T>
+static int write_field(vl_sim *sim, size_t off, const T &v) {
+    // small parameter updates: staged through the pinned scratch, ordered on the stream
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    memcpy(sim->pin, &v, sizeof(T));
+    CU(sim, cudaMemcpyAsync((char *)sim->d + off, sim->pin, sizeof(T), cudaMemcpyHostToDevice, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    return VL_OK;
+}
+
+// sticky device error word -> status
+static int check_device_error(vl_sim *sim) {
+    uint32_t e = 0;
+    TRY(read_field(sim, FIELD_OFF(error), &e));
+    CU(sim, cudaGetLastError());
+    if (!e) return VL_OK;
+    uint32_t zero = 0;
+    write_field(sim, FIELD_OFF(error), zero);
+    if (e & (DE_HAP_CAPACITY | DE_ARENA_CAPACITY | DE_INF_CAPACITY))
+        return fail(sim, VL_ERR_CAPACITY, "device capacity exhausted (bits 0x%x: 1=haplotype table, 2=arena, 32=population buffer)", e);
+    if (e & DE_ALL_ZERO_WEIGHTS)
+        return fail(sim, VL_ERR_REFERENCE_PANIC, "all offspring weights are zero: the reference panics in WeightedAliasIndex::new (src/core/population.rs:386)");
+    if (e & DE_UNDEFINED_OFFSPRING)
+        return fail(sim, VL_ERR_REFERENCE_PANIC, "Poisson::new failed on a non-zero fitness: the reference leaves the f64 bit pattern as offspring count (src/simulation.rs:146-152)");
+    if (e & DE_SAME_BASE) return fail(sim, VL_ERR_REFERENCE_PANIC, "assert_ne!(from, to) in create_descendant (src/core/haplotype.rs:250)");
+    if (e & DE_OFFSPRING_RANGE) return fail(sim, VL_ERR_IMPLEMENTATION, "offspring count does not fit 32 bits");
+    if (e & DE_REPLAY) return fail(sim, VL_ERR_ARGUMENT, "malformed replay log or index out of range");
+    return fail(sim, VL_ERR_IMPLEMENTATION, "unknown device error 0x%x", e);
+}
+
+static int zero_scan_work(vl_sim *sim, uint64_t n_items_bound) {
+    uint64_t words = 2 + (n_items_bound + SCAN_TILE - 1) / SCAN_TILE;
+    if (words > sim->scan_work_words) {
+        CU(sim, cudaStreamSynchronize(sim->stream));
+        if (sim->scan_work) cudaFree(sim->scan_work);
+        sim->scan_work = nullptr;
+        sim->scan_work_words = words + words / 2;
+        CU(sim, cudaMalloc((void **)&sim->scan_work, sim->scan_work_words * 8));
+    }
+    CU(sim, cudaMemsetAsync(sim->scan_work, 0, words * 8, sim->stream));
+    return VL_OK;
+}
+template <typename OutT, bool EXCL>
+static int launch_scan(vl_sim *sim, const uint32_t *in, OutT *out, const uint64_t *n_ptr, uint64_t n_add, uint64_t bound,
+                       uint64_t *total_out, int write_end, const uint32_t *active) {
+    TRY(zero_scan_work(sim, bound + 1));
+    unsigned g = grid_tiles(sim, bound + 1, SCAN_TILE, 4);
+    LAUNCH(sim, (k_scan_u32<OutT, EXCL>), g, SCAN_THREADS, 0, in, out, n_ptr, n_add, sim->scan_work, total_out, write_end, active);
+    return VL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- buffers
+static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
+    DevState &h = sim->h;
+    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.hosts, h.heavy_hosts, h.mut_list, h.mut_count, h.fit, h.offspring,
+                    h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_base, sim->stage64};
+    for (void *p : olds) if (p) cudaFree(p);
+    const uint64_t nt = (cap + RESAMPLE_TILE - 1) / RESAMPLE_TILE + 1;
+    uint64_t P = 1;
+    while (P < nt) P <<= 1;
+    TRY(dev_alloc(sim, &h.hap_id, cap, false));
+    TRY(dev_alloc(sim, &h.hap_id_next, cap, false));
+    TRY(dev_alloc(sim, &h.host_id, cap, false));
+    TRY(dev_alloc(sim, &h.rank, cap, false));
+    TRY(dev_alloc(sim, &h.hosts, cap, false));
+    TRY(dev_alloc(sim, &h.heavy_hosts, cap / THREAD_TIER + 1, false));
+    TRY(dev_alloc(sim, &h.mut_list, cap, false));
+    TRY(dev_alloc(sim, &h.mut_count, cap, false));
+    TRY(dev_alloc(sim, &h.fit, cap, false));
+    TRY(dev_alloc(sim, &h.offspring, cap, false));
+    TRY(dev_alloc(sim, &h.tile_sum, nt, false));
+    TRY(dev_alloc(sim, &h.tile_tree, 2 * P, false));
+    TRY(dev_alloc(sim, &h.tile_cnt, 2 * P, false));
+    TRY(dev_alloc(sim, &h.tile_base, nt, false));
+    TRY(dev_alloc(sim, &sim->stage64, cap, false));
+    h.cap_inf = cap;
+    return VL_OK;
+}
+static void free_population_buffers(vl_sim *sim) {
+    DevState &h = sim->h;
+    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.hosts, h.heavy_hosts, h.mut_list, h.mut_count, h.fit, h.offspring,
+                    h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_base, sim->stage64};
+    for (void *p : olds) if (p) cudaFree(p);
+}
+// push the host mirror's population pointers/capacity into the device state
+static int push_population_pointers(vl_sim *sim) {
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    DevState tmp;
+    CU(sim, cudaMemcpy(&tmp, sim->d, sizeof(DevState), cudaMemcpyDeviceToHost));
+    const DevState &h = sim->h;
+    tmp.hap_id = h.hap_id; tmp.hap_id_next = h.hap_id_next; tmp.host_id = h.host_id; tmp.rank = h.rank; tmp.hosts = h.hosts;
+    tmp.heavy_hosts = h.heavy_hosts; tmp.mut_list = h.mut_list; tmp.mut_count = h.mut_count; tmp.fit = h.fit; tmp.offspring = h.offspring;
+    tmp.tile_sum = h.tile_sum; tmp.tile_tree = h.tile_tree; tmp.tile_cnt = h.tile_cnt; tmp.tile_base = h.tile_base;
+    tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.hsum = h.hsum; tmp.H = h.H;
+    CU(sim, cudaMemcpy(sim->d, &tmp, sizeof(DevState), cudaMemcpyHostToDevice));
+    return VL_OK;
+}
+static int alloc_host_buffers(vl_sim *sim, uint64_t H) {
+    DevState &h = sim->h;
+    if (h.offsets) cudaFree(h.offsets);
+    if (h.hsum) cudaFree(h.hsum);
+    if (sim->count) cudaFree(sim->count);
+    TRY(dev_alloc(sim, &h.offsets, H + 2, false));
+    TRY(dev_alloc(sim, &h.hsum, H + 1, false));
+    TRY(dev_alloc(sim, &sim->count, H + 2, false));
+    sim->cap_H = H;
+    return VL_OK;
+}
+
+static int add_provider(vl_sim *sim, const vl_fitness *f, uint64_t L, int *index_out) {
+    *index_out = -1;
+    if (f->kind == VL_FITNESS_NONE) return VL_OK;
+    if (f->kind < 0 || f->kind > VL_FITNESS_EPISTATIC) return fail(sim, VL_ERR_ARGUMENT, "unknown fitness kind %d", f->kind);
+    DevState &h = sim->h;
+    if (h.n_providers >= (uint32_t)MAX_PROVIDERS) return fail(sim, VL_ERR_ARGUMENT, "too many fitness providers");
+    DevProvider &p = h.prov[h.n_providers];
+    memset(&p, 0, sizeof(p));
+    p.kind = f->kind;
+    p.util_kind = f->utility.kind;
+    p.upper = f->utility.upper;
+    p.hill_n = f->utility.n;
+    p.hill_k = (1.0 - f->utility.p) / f->utility.p;  // UtilityFunction::new_hill, src/core/fitness/utility.rs:26-45
+    if (f->kind >= VL_FITNESS_NONEPISTATIC) {
+        if (!f->table) return fail(sim, VL_ERR_INITIALIZATION, "fitness table missing");
+        double *t = nullptr;
+        TRY(dev_alloc(sim, &t, L * 4));
+        CU(sim, cudaMemcpy(t, f->table, L * 4 * sizeof(double), cudaMemcpyHostToDevice));
+        p.table = t;
+    }
+    if (f->kind == VL_FITNESS_EPISTATIC) {
+        // EpistasisTable::from_vec (src/core/fitness/epistasis.rs:44-58): symmetric nested map, a later entry
+        // for the same ordered key pair overwrites an earlier one
+        struct Dir { uint32_t k1, k2; double v; uint64_t seq; };
+        std::vector<Dir> d;
+        d.reserve(2 * f->n_epi);
+        for (uint64_t i = 0; i < f->n_epi; i++) {
+            const vl_epi_entry &e = f->epi[i];
+            if (e.pos1 >= L || e.pos2 >= L || e.base1 > 3 || e.base2 > 3) return fail(sim, VL_ERR_INITIALIZATION, "epistasis entry %llu out of range", (unsigned long long)i);
+            uint32_t a = ekey((uint32_t)e.pos1, e.base1), b = ekey((uint32_t)e.pos2, e.base2);
+            d.push_back({a, b, e.value, d.size()});
+            d.push_back({b, a, e.value, d.size()});
+        }
+        std::sort(d.begin(), d.end(), [](const Dir &x, const Dir &y) {
+            if (x.k1 != y.k1) return x.k1 < y.k1;
+            if (x.k2 != y.k2) return x.k2 < y.k2;
+            return x.seq < y.seq;
+        });
+        std::vector<EpiDir> out;
+        for (size_t i = 0; i < d.size(); i++) {
+            if (i + 1 < d.size() && d[i + 1].k1 == d[i].k1 && d[i + 1].k2 == d[i].k2) continue;
+            out.push_back({d[i].k1, d[i].k2, d[i].v});
+        }
+        EpiDir *dev = nullptr;
+        TRY(dev_alloc(sim, &dev, out.size()));
+        if (!out.empty()) CU(sim, cudaMemcpy(dev, out.data(), out.size() * sizeof(EpiDir), cudaMemcpyHostToDevice));
+        p.epi = dev;
+        p.n_epi = (uint32_t)out.size();
+    }
+    *index_out = (int)h.n_providers++;
+    return VL_OK;
+}
+
+static void destroy_sim(vl_sim *sim) {
+    if (!sim) return;
+    cudaSetDevice(sim->device);
+    if (sim->stream) cudaStreamSynchronize(sim->stream);
+    for (vl_pop *p : sim->pops) {
+        if (p->ids) cudaFree(p->ids);
+        if (p->image) cudaFree(p->image);
+        delete p;
+    }
+    free_population_buffers(sim);
+    if (sim->h.offsets) cudaFree(sim->h.offsets);
+    if (sim->h.hsum) cudaFree(sim->h.hsum);
+    if (sim->count) cudaFree(sim->count);
+    for (void *p : sim->fixed_allocs) cudaFree(p);
+    if (sim->scan_work) cudaFree(sim->scan_work);
+    void *rp[] = {sim->rp_inf, sim->rp_mut_off, sim->rp_mut_sites, sim->rp_mut_bases, sim->rp_rec_host, sim->rp_rec_i, sim->rp_rec_j,
+                  sim->rp_rec_s0, sim->rp_rec_s1, sim->rp_rec_which, sim->rp_off};
+    for (void *p : rp) if (p) cudaFree(p);
+    if (sim->pin) cudaFreeHost(sim->pin);
+    for (auto &r : sim->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    if (sim->timer_a) { cudaEventDestroy(sim->timer_a); cudaEventDestroy(sim->timer_b); }
+    if (sim->stream) cudaStreamDestroy(sim->stream);
+    delete sim;
+}
+
+// ---------------------------------------------------------------------------------------------- lifecycle
+VL_API int vl_abi_version(void) { return 1; }
+
+VL_API const char *vl_last_error(const vl_sim *sim) { return sim ? sim->err : g_create_err; }
+
+VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
+    if (!cfg || !out) return fail(nullptr, VL_ERR_ARGUMENT, "null argument");
+    *out = nullptr;
+    const uint64_t L = cfg->n_sites;
+    if (L == 0 || L >= (1ull << 24)) return fail(nullptr, VL_ERR_INITIALIZATION, "n_sites must be in [1, 2^24)");
+    if (!cfg->wildtype) return fail(nullptr, VL_ERR_INITIALIZATION, "wildtype missing");
+    if (cfg->n_specs == 0 || cfg->n_specs > (uint32_t)MAX_SPECS) return fail(nullptr, VL_ERR_INITIALIZATION, "n_specs must be in [1, %d]", MAX_SPECS);
+    const vl_parameters &par = cfg->parameters;
+    if (par.host_population_size >= 0xFFFFFFFFull) return fail(nullptr, VL_ERR_INITIALIZATION, "host_population_size must fit 32 bits");
+    for (uint64_t i = 0; i < L; i++) if (cfg->wildtype[i] > 3) return fail(nullptr, VL_ERR_INITIALIZATION, "wildtype symbol %llu out of range", (unsigned long long)i);
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev == 0) return fail(nullptr, VL_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, VL_ERR_ARGUMENT, "device ordinal %d out of range", cfg->device);
+    vl_sim *sim = new vl_sim();
+    memset(&sim->h, 0, sizeof(DevState));
+    sim->device = cfg->device;
+    sim->flags = cfg->flags;
+    auto bail = [&](int code) { snprintf(g_create_err, sizeof g_create_err, "%s", sim->err); destroy_sim(sim); return code; };
+#define CTRY(expr) do { int r__ = (expr); if (r__ != VL_OK) return bail(r__); } while (0)
+#define CCU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail(sim, VL_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); return bail(VL_ERR_CUDA); } } while (0)
+    CCU(cudaSetDevice(sim->device));
+    CCU(cudaDeviceGetAttribute(&sim->n_sms, cudaDevAttrMultiProcessorCount, sim->device));
+    CCU(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+    CCU(cudaMallocHost((void **)&sim->pin, PIN_SLOTS * sizeof(uint64_t)));
+    DevState &h = sim->h;
+    h.L = (uint32_t)L;
+    h.n_specs = cfg->n_specs;
+    h.compartment = cfg->compartment_id;
+    h.seed = cfg->seed;
+    h.host_mutation_rate = par.mutation_rate;
+    h.host_recombination_rate = par.recombination_rate;
+    h.host_r0 = par.basic_reproductive_number;
+    memcpy(h.host_subst, par.substitution_matrix, sizeof h.host_subst);
+    h.H = par.host_population_size;
+    h.n_hits = par.n_hits;
+    h.dilution = par.dilution;
+    h.max_population = par.max_population;
+    {
+        uint8_t *wt = nullptr;
+        CTRY(dev_alloc(sim, &wt, L));
+        CCU(cudaMemcpy(wt, cfg->wildtype, L, cudaMemcpyHostToDevice));
+        h.wildtype = wt;
+    }
+    for (uint32_t s = 0; s < cfg->n_specs; s++) {
+        h.specs[s].lo = cfg->specs[s].lo;
+        h.specs[s].hi = cfg->specs[s].hi;
+        CTRY(add_provider(sim, &cfg->specs[s].reproductive, L, &h.specs[s].repro));
+        CTRY(add_provider(sim, &cfg->specs[s].infective, L, &h.specs[s].infect));
+    }
+    // ---- capacities
+    uint64_t cap_inf = cfg->capacity_infectants ? cfg->capacity_infectants : std::max<uint64_t>(2 * par.max_population, 4096);
+    uint64_t cap_hap = cfg->capacity_haplotypes ? cfg->capacity_haplotypes : 3 * cap_inf + 65536;
+    if (cap_hap >= 0xFFFFFFF0ull) cap_hap = 0xFFFFFFF0ull;
+    uint64_t cap_arena = cfg->capacity_arena_words ? cfg->capacity_arena_words : std::max<uint64_t>(16 * cap_hap, 1ull << 20);
+    {
+        size_t free_b = 0, total_b = 0;
+        CCU(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t P = std::max<uint32_t>(h.n_providers, 1);
+        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 64 + ch * (52 + 16 * P) + ca * 8; };
+        if (!cfg->capacity_haplotypes || !cfg->capacity_arena_words) {
+            for (int it = 0; it < 64 && need(cap_hap, cap_arena) > (uint64_t)(0.7 * (double)free_b); it++) {
+                if (!cfg->capacity_arena_words && cap_arena > (1ull << 20)) cap_arena = cap_arena * 3 / 4;
+                if (!cfg->capacity_haplotypes && cap_hap > cap_inf + 65536) cap_hap = std::max(cap_inf + 65536, cap_hap * 3 / 4);
+            }
+        }
+        if (need(cap_hap, cap_arena) > (uint64_t)(0.95 * (double)free_b)) {
+            fail(sim, VL_ERR_CAPACITY, "configuration needs %.1f GB of device memory, %.1f GB free", need(cap_hap, cap_arena) / 1e9, free_b / 1e9);
+            return bail(VL_ERR_CAPACITY);
+        }
+    }
+    h.cap_hap = cap_hap;
+    h.cap_arena = cap_arena;
+    h.gc_hap_threshold = cap_hap / 2;
+    h.gc_arena_threshold = cap_arena / 2;
+    CTRY(alloc_population_buffers(sim, cap_inf));
+    CTRY(alloc_host_buffers(sim, h.H));
+    CTRY(dev_alloc(sim, &h.h_off, cap_hap)); CTRY(dev_alloc(sim, &h.h_off_alt, cap_hap));
+    CTRY(dev_alloc(sim, &h.h_len, cap_hap)); CTRY(dev_alloc(sim, &h.h_len_alt, cap_hap));
+    CTRY(dev_alloc(sim, &h.h_parent, cap_hap)); CTRY(dev_alloc(sim, &h.h_parent_alt, cap_hap));
+    for (uint32_t p = 0; p < h.n_providers; p++) { CTRY(dev_alloc(sim, &h.h_raw[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_raw_alt[p], cap_hap)); }
+    CTRY(dev_alloc(sim, &h.arena, cap_arena)); CTRY(dev_alloc(sim, &h.arena_alt, cap_arena));
+    CTRY(dev_alloc(sim, &h.gc_mark, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_newid, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_len, cap_hap + 1));
+    CTRY(dev_alloc(sim, &h.gc_newoff, cap_hap + 1));
+    CTRY(dev_alloc(sim, &sim->gc_totals, 16));
+    CCU(cudaMemset(sim->gc_totals, 0, 16 * 8));
+    sim->scan_work_words = 8 + (std::max<uint64_t>(std::max<uint64_t>(cap_hap, h.H), cap_inf) + SCAN_TILE) / SCAN_TILE;
+    CTRY(dev_alloc(sim, &sim->scan_work, sim->scan_work_words, false));
+    // haplotype 0 = wildtype: no entries, raw fitness = empty product (src/core/fitness/table.rs:72-79)
+    h.n_hap = 1;
+    h.arena_top = 0;
+    {
+        uint64_t zero64 = 0; uint32_t zero32 = 0, none = NONE32; double one = 1.0;
+        CCU(cudaMemcpy(h.h_off, &zero64, 8, cudaMemcpyHostToDevice));
+        CCU(cudaMemcpy(h.h_len, &zero32, 4, cudaMemcpyHostToDevice));
+        CCU(cudaMemcpy(h.h_parent, &none, 4, cudaMemcpyHostToDevice));
+        for (uint32_t p = 0; p < h.n_providers; p++) CCU(cudaMemcpy(h.h_raw[p], &one, 8, cudaMemcpyHostToDevice));
+    }
+    CTRY(dev_alloc(sim, &sim->d, 1));
+    CCU(cudaMemcpy(sim->d, &h, sizeof(DevState), cudaMemcpyHostToDevice));
+    // garbage-collection cadence: expected new records per generation from p_mut = 1-(1-mu)^L, with slack
+    {
+        double p_mut = 1.0 - pow(1.0 - par.mutation_rate, (double)L);
+        double per_gen = (double)cap_inf * std::min(1.0, 3.0 * p_mut + 0.01 + (par.recombination_rate > 0 ? 0.05 : 0.0));
+        double room = (double)(cap_hap - h.gc_hap_threshold);
+        double period = floor(room / std::max(per_gen, 1.0));
+        sim->gc_period = (uint32_t)std::min(64.0, std::max(1.0, period));
+    }
+    sim->n_known = 0;
+    sim->n_valid = true;
+    CCU(cudaDeviceSynchronize());
+#undef CTRY
+#undef CCU
+    *out = sim;
+    return VL_OK;
+}
+
+VL_API int vl_destroy(vl_sim *sim) {
+    if (!sim) return VL_OK;
+    destroy_sim(sim);
+    return VL_OK;
+}
+
+VL_API int vl_synchronize(vl_sim *sim) {
+    ENTER(sim);
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    return check_device_error(sim);
+}
+
+// ---------------------------------------------------------------------------------------------- trait: scalars
+VL_API int vl_increment_generation(vl_sim *sim) {
+    ENTER(sim);
+    LAUNCH(sim, k_tick, 1, 1, 0, sim->d);
+    sim->salt = 0;
+    return VL_OK;
+}
+VL_API int vl_get_generation(const vl_sim *csim, uint64_t *out) {
+    vl_sim *sim = const_cast<vl_sim *>(csim);
+    ENTER(sim);
+    uint32_t g = 0;
+    TRY(read_field(sim, FIELD_OFF(generation), &g));
+    *out = g;
+    return VL_OK;
+}
+VL_API int vl_set_generation(vl_sim *sim, uint64_t generation) {
+    ENTER(sim);
+    return write_field(sim, FIELD_OFF(generation), (uint32_t)generation);
+}
+VL_API int vl_set_parameters(vl_sim *sim, const vl_parameters *p) {
+    ENTER(sim);
+    if (!p) return fail(sim, VL_ERR_ARGUMENT, "null parameters");
+    if (p->host_population_size >= 0xFFFFFFFFull) return fail(sim, VL_ERR_ARGUMENT, "host_population_size must fit 32 bits");
+    // BasicSimulation::set_parameters (src/simulation.rs:355-363) replaces the simulation's copy only; the
+    // BasicHost copies (mutation/recombination rate, R0, substitution matrix) keep their construction values.
+    DevState &h = sim->h;
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    if (p->host_population_size > sim->cap_H) TRY(alloc_host_buffers(sim, p->host_population_size));
+    h.H = p->host_population_size;
+    TRY(push_population_pointers(sim));
+    TRY(write_field(sim, FIELD_OFF(n_hits), (uint64_t)p->n_hits));
+    TRY(write_field(sim, FIELD_OFF(dilution), p->dilution));
+    TRY(write_field(sim, FIELD_OFF(max_population), (uint64_t)p->max_population));
+    h.n_hits = p->n_hits; h.dilution = p->dilution; h.max_population = p->max_population;
+    sim->csr_valid = false;
+    return VL_OK;
+}
+static int population_len(vl_sim *sim, uint64_t *out) {
+    if (!sim->n_valid) {
+        TRY(read_field(sim, FIELD_OFF(n), &sim->n_known));
+        sim->n_valid = true;
+    }
+    *out = sim->n_known;
+    return VL_OK;
+}
+VL_API int vl_population_len(vl_sim *sim, uint64_t *out) {
+    ENTER(sim);
+    TRY(population_len(sim, out));
+    return VL_OK;
+}
+VL_API int vl_set_population_wildtype(vl_sim *sim, uint64_t n) {
+    ENTER(sim);
+    if (n > sim->h.cap_inf) {
+        CU(sim, cudaStreamSynchronize(sim->stream));
+        if (!sim->pops.empty()) return fail(sim, VL_ERR_CAPACITY, "population of %llu exceeds capacity_infectants %llu", (unsigned long long)n, (unsigned long long)sim->h.cap_inf);
+        TRY(alloc_population_buffers(sim, n + n / 4));
+        TRY(push_population_pointers(sim));
+    }
+    LAUNCH(sim, k_fill_population, grid_for(sim, n), TPB, 0, sim->d, n, 0u);
+    sim->n_known = n;
+    sim->n_bound = n;
+    sim->n_valid = true;
+    sim->csr_valid = false;
+    return VL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- phases
+static bool need_csr(const vl_sim *sim) {
+    return !(sim->flags & VL_FLAG_ATOMIC_HOST_SUM) || sim->h.host_recombination_rate > 0.0 || sim->has_rp_rec;
+}
+static int enqueue_infect(vl_sim *sim) {
+    const DevState &h = sim->h;
+    const bool csr = need_csr(sim);
+    LAUNCH(sim, k_begin_phase, 1, 1, 0, sim->d);
+    if (csr) CU(sim, cudaMemsetAsync(sim->count, 0, (h.H + 2) * 4, sim->stream));
+    LAUNCH(sim, k_infect, grid_for(sim, sim->n_bound), TPB, 0, sim->d, sim->count, sim->has_rp_inf ? sim->rp_inf : nullptr, csr ? 1 : 0);
+    sim->has_rp_inf = false;
+    if (csr) {
+        TRY((launch_scan<uint32_t, true>(sim, sim->count, h.offsets, (const uint64_t *)((const char *)sim->d + FIELD_OFF(H)), 0, h.H, nullptr, 1, nullptr)));
+        LAUNCH(sim, k_scatter_hosts, grid_for(sim, sim->n_bound), TPB, 0, sim->d);
+        LAUNCH(sim, k_sort_slices, grid_for(sim, h.H), TPB, 0, sim->d);
+        LAUNCH(sim, k_sort_slices_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 4, sim->d);
+    }
+    sim->csr_valid = csr;
+    return VL_OK;
+}
+static int enqueue_mutate(vl_sim *sim) {
+    const DevState &h = sim->h;
+    const bool replay = sim->has_rp_mut || sim->has_rp_rec;
+    ReplayRecomb rr{sim->rp_rec_n, sim->rp_rec_host, sim->rp_rec_i, sim->rp_rec_j, sim->rp_rec_s0, sim->rp_rec_s1, sim->rp_rec_which};
+    ReplayMut rm{sim->rp_mut_off, sim->rp_mut_sites, sim->rp_mut_bases};
+    if (replay) {
+        if (sim->has_rp_rec && sim->rp_rec_n > 0) {
+            if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "recombination replay needs the host map");
+            LAUNCH(sim, k_recombine, grid_for(sim, h.H), TPB, 0, sim->d, rr, 1);
+        }
+    } else if (h.host_recombination_rate > 0.0) {
+        if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "recombination needs the host map: call vl_infect first");
+        LAUNCH(sim, k_recombine, grid_for(sim, h.H), TPB, 0, sim->d, rr, 0);
+    }
+    if (replay && !sim->has_rp_mut) {
+        // a replayed generation without mutation log means "no mutations"
+        sim->has_rp_rec = false;
+        return VL_OK;
+    }
+    LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
+    sim->has_rp_mut = false;
+    sim->has_rp_rec = false;
+    return VL_OK;
+}
+static int enqueue_replicate(vl_sim *sim) {
+    const DevState &h = sim->h;
+    const bool atomic = (sim->flags & VL_FLAG_ATOMIC_HOST_SUM) != 0;
+    if (atomic) CU(sim, cudaMemsetAsync(h.hsum, 0, (h.H + 1) * 8, sim->stream));
+    else if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "replicate needs the host map: call vl_infect first");
+    LAUNCH(sim, k_fitness, grid_for(sim, sim->n_bound), TPB, 0, sim->d, atomic ? 1 : 0);
+    if (!atomic) {
+        LAUNCH(sim, k_host_sum, grid_for(sim, h.H), TPB, 0, sim->d);
+        LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, 0, sim->d);
+    }
+    LAUNCH(sim, k_offspring, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, sim->has_rp_off ? sim->rp_off : nullptr);
+    sim->has_rp_off = false;
+    return VL_OK;
+}
+// Population::sample as plan + tile-local draws.  dst == nullptr writes the population being assembled.
+static int enqueue_resample(vl_sim *sim, double factor, int use_amount, uint64_t amount, uint32_t *dst, uint64_t *dst64, int mode, int set_next) {
+    const DevState &h = sim->h;
+    const uint32_t salt = ++sim->salt;
+    LAUNCH(sim, k_plan_resample, 1, PLAN_THREADS, 0, sim->d, factor, use_amount, amount, set_next, salt);
+    LAUNCH(sim, k_resample, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, dst, dst64, mode, salt);
+    return VL_OK;
+}
+static int enqueue_gc(vl_sim *sim, int force) {
+    const DevState &h = sim->h;
+    const uint32_t *active = (const uint32_t *)((const char *)sim->d + FIELD_OFF(gc_active));
+    const uint64_t *nh_ptr = (const uint64_t *)((const char *)sim->d + FIELD_OFF(n_hap));
+    LAUNCH(sim, k_gc_begin, 1, 1, 0, sim->d, force);
+    LAUNCH(sim, k_gc_clear, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
+    LAUNCH(sim, k_gc_mark, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (const uint32_t *)nullptr, (uint64_t)0, 1);
+    for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_mark, grid_for(sim, p->cap), TPB, 0, sim->d, (const uint32_t *)p->ids, p->n, 0);
+    LAUNCH(sim, k_gc_lens, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
+    TRY((launch_scan<uint32_t, true>(sim, h.gc_mark, h.gc_newid, nh_ptr, 0, h.cap_hap, sim->gc_totals + 0, 0, active)));
+    TRY((launch_scan<uint64_t, true>(sim, h.gc_len, h.gc_newoff, nh_ptr, 0, h.cap_hap, sim->gc_totals + 1, 0, active)));
+    LAUNCH(sim, k_gc_copy, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
+    LAUNCH(sim, k_gc_remap, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (uint32_t *)nullptr, (uint64_t)0, 1);
+    for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_remap, grid_for(sim, p->cap), TPB, 0, sim->d, p->ids, p->n, 0);
+    LAUNCH(sim, k_gc_end, 1, 1, 0, sim->d, sim->gc_totals);
+    sim->gens_since_gc = 0;
+    return VL_OK;
+}
+static int maybe_gc(vl_sim *sim) {
+    if (++sim->gens_since_gc >= sim->gc_period) return enqueue_gc(sim, 0);
+    return VL_OK;
+}
+static void swap_population(vl_sim *sim) {
+    LAUNCH(sim, k_swap_population, 1, 1, 0, sim->d);
+    std::swap(sim->h.hap_id, sim->h.hap_id_next);
+}
+
+VL_API int vl_infect(vl_sim *sim) {
+    ENTER(sim);
+    return enqueue_infect(sim);
+}
+VL_API int vl_mutate_infectants(vl_sim *sim) {
+    ENTER(sim);
+    return enqueue_mutate(sim);
+}
+
+static int upload_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n) {
+    uint64_t cur = 0;
+    TRY(population_len(sim, &cur));
+    if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "offspring map has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
+    if (n) CU(sim, cudaMemcpyAsync(sim->stage64, offspring, n * 8, cudaMemcpyHostToDevice, sim->stream));
+    LAUNCH(sim, k_u64_to_u32, grid_for(sim, n), TPB, 0, sim->d, sim->stage64, sim->h.offspring, n);
+    LAUNCH(sim, k_tile_sums, grid_tiles(sim, n, RESAMPLE_TILE), TPB, 0, sim->d);
+    return VL_OK;
+}
+
+VL_API int vl_replicate_infectants(vl_sim *sim, uint64_t *offspring_out, uint64_t n) {
+    ENTER(sim);
+    TRY(enqueue_replicate(sim));
+    if (offspring_out) {
+        uint64_t cur = 0;
+        TRY(population_len(sim, &cur));
+        if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "offspring buffer has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
+        LAUNCH(sim, k_u32_to_u64, grid_for(sim, n), TPB, 0, sim->h.offspring, sim->stage64, n);
+        if (n) CU(sim, cudaMemcpyAsync(offspring_out, sim->stage64, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+        CU(sim, cudaStreamSynchronize(sim->stream));
+        return check_device_error(sim);
+    }
+    return VL_OK;
+}
+
+VL_API int vl_target_size(vl_sim *sim, const uint64_t *offspring, uint64_t n, double *out) {
+    ENTER(sim);
+    if (offspring) TRY(upload_offspring(sim, offspring, n));
+    LAUNCH(sim, k_target_size, 1, TPB, 0, sim->d);
+    TRY(read_field(sim, FIELD_OFF(target_size), out));
+    return check_device_error(sim);
+}
+
+static vl_pop *new_pop(vl_sim *sim, uint64_t cap) {
+    vl_pop *p = new vl_pop();
+    p->owner = sim; p->ids = nullptr; p->n = 0; p->cap = cap; p->image = nullptr; p->image_bytes = 0; p->pending_slot = -1;
+    if (cudaMalloc((void **)&p->ids, std::max<uint64_t>(cap, 1) * 4) != cudaSuccess) { delete p; return nullptr; }
+    sim->pops.push_back(p);
+    return p;
+}
+static void drop_pop(vl_pop *p) {
+    vl_sim *sim = p->owner;
+    auto it = std::find(sim->pops.begin(), sim->pops.end(), p);
+    if (it != sim->pops.end()) sim->pops.erase(it);
+    if (p->ids) cudaFree(p->ids);
+    if (p->image) cudaFree(p->image);
+    delete p;
+}
+
+VL_API int vl_sample_indices(vl_sim *sim, const uint64_t *offspring, uint64_t n, uint64_t amount, uint64_t *indices_out) {
+    ENTER(sim);
+    if (offspring) TRY(upload_offspring(sim, offspring, n));
+    uint64_t cur = 0;
+    TRY(population_len(sim, &cur));
+    if (cur == 0) return VL_OK;  // sample_indices returns an empty vector for an empty map (src/simulation.rs:506-508)
+    uint64_t *dst = sim->stage64;
+    bool temp = false;
+    if (amount > sim->h.cap_inf) { CU(sim, cudaMalloc((void **)&dst, amount * 8)); temp = true; }
+    TRY(enqueue_resample(sim, 0.0, 1, amount, nullptr, dst, 1, 0));
+    if (amount) CU(sim, cudaMemcpyAsync(indices_out, dst, amount * 8, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    if (temp) cudaFree(dst);
+    return check_device_error(sim);
+}
+
+// enqueue plan + draws into a detached population whose capacity bounds the size; the size itself arrives
+// in a pinned slot and is read by finalize_pop after a stream synchronisation
+static int enqueue_subsample(vl_sim *sim, double factor, int use_amount, uint64_t amount, vl_pop **out) {
+    double bound = use_amount ? (double)amount : floor(factor * (double)sim->h.max_population) + 1.0;
+    if (!(bound >= 0.0)) bound = 0.0;
+    if (bound > 4.0e9) return fail(sim, VL_ERR_CAPACITY, "subsample bound too large");
+    vl_pop *p = new_pop(sim, (uint64_t)bound + 1);
+    if (!p) return fail(sim, VL_ERR_CUDA, "out of device memory for a detached population of %.0f", bound);
+    const uint32_t salt = ++sim->salt;
+    LAUNCH(sim, k_plan_resample, 1, PLAN_THREADS, 0, sim->d, factor, use_amount, amount, 0, salt);
+    LAUNCH(sim, k_resample, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, p->ids, (uint64_t *)nullptr, 0, salt);
+    int slot = sim->next_slot++;
+    if (sim->next_slot >= PIN_SLOTS) sim->next_slot = 8;
+    CU(sim, cudaMemcpyAsync(sim->pin + slot, (const char *)sim->d + FIELD_OFF(n_next), 8, cudaMemcpyDeviceToHost, sim->stream));
+    p->pending_slot = slot;
+    *out = p;
+    return VL_OK;
+}
+static void finalize_pop(vl_pop *p) {
+    if (p->pending_slot >= 0) {
+        p->n = std::min<uint64_t>(p->owner->pin[p->pending_slot], p->cap);
+        p->pending_slot = -1;
+    }
+}
+
+VL_API int vl_subsample_population(vl_sim *sim, const uint64_t *offspring, uint64_t n, double factor, vl_pop **out) {
+    ENTER(sim);
+    if (!out) return fail(sim, VL_ERR_ARGUMENT, "null out");
+    if (offspring) TRY(upload_offspring(sim, offspring, n));
+    TRY(enqueue_subsample(sim, factor, 0, 0, out));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    finalize_pop(*out);
+    int r = check_device_error(sim);
+    if (r != VL_OK) { drop_pop(*out); *out = nullptr; }
+    return r;
+}
+
+VL_API int vl_select(vl_sim *sim, const uint64_t *indices, uint64_t n, vl_pop **out) {
+    ENTER(sim);
+    if (!out) return fail(sim, VL_ERR_ARGUMENT, "null out");
+    vl_pop *p = new_pop(sim, n);
+    if (!p) return fail(sim, VL_ERR_CUDA, "out of device memory");
+    uint64_t *src = sim->stage64;
+    bool temp = false;
+    if (n > sim->h.cap_inf) { CU(sim, cudaMalloc((void **)&src, n * 8)); temp = true; }
+    if (n) CU(sim, cudaMemcpyAsync(src, indices, n * 8, cudaMemcpyHostToDevice, sim->stream));
+    LAUNCH(sim, k_select, grid_for(sim, n), TPB, 0, sim->d, src, n, p->ids);
+    p->n = n;
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    if (temp) cudaFree(src);
+    int r = check_device_error(sim);
+    if (r != VL_OK) { drop_pop(p); return r; }
+    *out = p;
+    return VL_OK;
+}
+
+VL_API int vl_pop_len(const vl_pop *pop, uint64_t *out) {
+    if (!pop || !out) return fail(nullptr, VL_ERR_ARGUMENT, "null argument");
+    *out = pop->n;
+    return VL_OK;
+}
+VL_API int vl_pop_free(vl_pop *pop) {
+    if (!pop) return VL_OK;
+    vl_sim *sim = pop->owner;
+    ENTER(sim);
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    drop_pop(pop);
+    return VL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- migrants
+static int pack_pop(vl_sim *sim, vl_pop *pop) {
+    if (pop->image) return VL_OK;
+    const DevState &h = sim->h;
+    const uint64_t *nh_ptr = (const uint64_t *)((const char *)sim->d + FIELD_OFF(n_hap));
+    LAUNCH(sim, k_pack_clear, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
+    LAUNCH(sim, k_pack_mark, grid_for(sim, pop->n), TPB, 0, sim->d, (const uint32_t *)pop->ids, pop->n);
+    LAUNCH(sim, k_pack_lens, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
+    TRY((launch_scan<uint32_t, true>(sim, h.gc_mark, h.gc_newid, nh_ptr, 0, h.cap_hap, sim->gc_totals + 2, 0, nullptr)));
+    TRY((launch_scan<uint64_t, true>(sim, h.gc_len, h.gc_newoff, nh_ptr, 0, h.cap_hap, sim->gc_totals + 3, 0, nullptr)));
+    CU(sim, cudaMemcpyAsync(sim->pin, sim->gc_totals + 2, 16, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    const uint64_t n_unique = sim->pin[0], n_words = sim->pin[1];
+    PackHeader hd = make_pack_header(pop->n, n_unique, n_words, h.n_providers);
+    CU(sim, cudaMalloc((void **)&pop->image, hd.bytes));
+    pop->image_bytes = hd.bytes;
+    LAUNCH(sim, k_pack_copy, grid_for(sim, std::max<uint64_t>(h.cap_hap, pop->n)), TPB, 0, sim->d, (const uint32_t *)pop->ids, pop->image, hd);
+    return VL_OK;
+}
+VL_API int vl_pop_pack_device(vl_sim *origin, vl_pop *pop, void **image_device, uint64_t *bytes) {
+    ENTER(origin);
+    if (!pop || pop->owner != origin || !image_device || !bytes) return fail(origin, VL_ERR_ARGUMENT, "population does not belong to this handle");
+    TRY(pack_pop(origin, pop));
+    CU(origin, cudaStreamSynchronize(origin->stream));
+    *image_device = pop->image;
+    *bytes = pop->image_bytes;
+    return check_device_error(origin);
+}
+// unpack into dst (a detached population's ids) or, when dst == nullptr, into the population being assembled
+static int unpack_image(vl_sim *sim, const uint8_t *image, uint64_t bytes, uint32_t *dst, uint64_t dst_off, uint64_t *n_pop_out) {
+    PackHeader hd;
+    if (bytes < sizeof(PackHeader)) return fail(sim, VL_ERR_ARGUMENT, "packed image too small");
+    CU(sim, cudaMemcpy(&hd, image, sizeof(PackHeader), cudaMemcpyDeviceToHost));
+    if (hd.magic != PACK_MAGIC || hd.bytes > bytes) return fail(sim, VL_ERR_ARGUMENT, "not a packed population image");
+    if (hd.n_providers != sim->h.n_providers) return fail(sim, VL_ERR_ARGUMENT, "packed image has %llu fitness providers, handle has %u", (unsigned long long)hd.n_providers, sim->h.n_providers);
+    LAUNCH(sim, k_reserve_bulk, 1, 1, 0, sim->d, hd.n_unique, hd.n_words, sim->gc_totals + 4);
+    LAUNCH(sim, k_unpack, grid_for(sim, std::max<uint64_t>(std::max<uint64_t>(hd.n_unique, hd.n_words), hd.n_pop)), TPB, 0, sim->d, image, hd,
+           (const uint64_t *)(sim->gc_totals + 4), dst, dst_off);
+    *n_pop_out = hd.n_pop;
+    return VL_OK;
+}
+VL_API int vl_pop_unpack_device(vl_sim *target, const void *image_device, uint64_t bytes, vl_pop **out) {
+    ENTER(target);
+    if (!image_device || !out) return fail(target, VL_ERR_ARGUMENT, "null argument");
+    PackHeader hd;
+    if (bytes < sizeof(PackHeader)) return fail(target, VL_ERR_ARGUMENT, "packed image too small");
+    CU(target, cudaMemcpy(&hd, image_device, sizeof(PackHeader), cudaMemcpyDeviceToHost));
+    if (hd.magic != PACK_MAGIC) return fail(target, VL_ERR_ARGUMENT, "not a packed population image");
+    vl_pop *p = new_pop(target, hd.n_pop);
+    if (!p) return fail(target, VL_ERR_CUDA, "out of device memory");
+    uint64_t n_pop = 0;
+    int r = unpack_image(target, (const uint8_t *)image_device, bytes, p->ids, 0, &n_pop);
+    if (r == VL_OK) { CU(target, cudaStreamSynchronize(target->stream)); r = check_device_error(target); }
+    if (r != VL_OK) { drop_pop(p); return r; }
+    p->n = n_pop;
+    *out = p;
+    return VL_OK;
+}
+
+VL_API int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts) {
+    ENTER(sim);
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < n_parts; k++) {
+        if (!parts[k]) return fail(sim, VL_ERR_ARGUMENT, "null part");
+        finalize_pop(parts[k]);
+        total += parts[k]->n;
+    }
+    if (total > sim->h.cap_inf) return fail(sim, VL_ERR_CAPACITY, "assembled population of %llu exceeds capacity_infectants %llu", (unsigned long long)total, (unsigned long long)sim->h.cap_inf);
+    uint64_t off = 0;
+    for (uint32_t k = 0; k < n_parts; k++) {
+        vl_pop *p = parts[k];
+        if (p->n == 0) continue;
+        if (p->owner == sim) {
+            LAUNCH(sim, k_copy_ids, grid_for(sim, p->n), TPB, 0, sim->d, (const uint32_t *)p->ids, p->n, off);
+        } else {
+            vl_sim *o = p->owner;
+            {
+                std::lock_guard<std::recursive_mutex> lk(o->mu);
+                CU(sim, cudaSetDevice(o->device));
+                int r = pack_pop(o, p);
+                if (r == VL_OK) { cudaStreamSynchronize(o->stream); r = check_device_error(o); }
+                if (r != VL_OK) { cudaSetDevice(sim->device); return fail(sim, r, "packing migrants failed: %s", o->err); }
+                CU(sim, cudaSetDevice(sim->device));
+            }
+            const uint8_t *image = p->image;
+            uint8_t *local = nullptr;
+            if (o->device != sim->device) {
+                CU(sim, cudaMalloc((void **)&local, p->image_bytes));
+                CU(sim, cudaMemcpyPeer(local, sim->device, p->image, o->device, p->image_bytes));
+                image = local;
+            }
+            uint64_t n_pop = 0;
+            int r = unpack_image(sim, image, p->image_bytes, nullptr, off, &n_pop);
+            CU(sim, cudaStreamSynchronize(sim->stream));
+            if (local) cudaFree(local);
+            TRY(r);
+        }
+        off += p->n;
+    }
+    LAUNCH(sim, k_set_next_n, 1, 1, 0, sim->d, total);
+    swap_population(sim);
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    for (uint32_t k = 0; k < n_parts; k++) {  // consumes the parts (Population is moved in, src/simulation.rs:340-345)
+        vl_sim *o = parts[k]->owner;
+        std::lock_guard<std::recursive_mutex> lk(o->mu);
+        drop_pop(parts[k]);
+    }
+    sim->n_known = total;
+    sim->n_bound = total;
+    sim->n_valid = true;
+    sim->csr_valid = false;
+    TRY(check_device_error(sim));
+    return maybe_gc(sim);
+}
+
+// ---------------------------------------------------------------------------------------------- fused loops
+static int enqueue_generation(vl_sim *sim) {
+    // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
+    LAUNCH(sim, k_tick, 1, 1, 0, sim->d);
+    sim->salt = 0;
+    TRY(enqueue_infect(sim));
+    TRY(enqueue_mutate(sim));
+    TRY(enqueue_replicate(sim));
+    TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
+    swap_population(sim);
+    sim->n_valid = false;
+    sim->n_bound = std::min<uint64_t>(sim->h.cap_inf, sim->h.max_population);
+    sim->csr_valid = false;
+    return maybe_gc(sim);
+}
+VL_API int vl_next_generation(vl_sim *sim) {
+    ENTER(sim);
+    TRY(enqueue_generation(sim));
+    CU(sim, cudaGetLastError());
+    return VL_OK;
+}
+VL_API int vl_run(vl_sim *sim, uint64_t n_generations) {
+    ENTER(sim);
+    for (uint64_t g = 0; g < n_generations; g++) TRY(enqueue_generation(sim));
+    CU(sim, cudaGetLastError());
+    return VL_OK;
+}
+
+static inline uint64_t f64_as_usize_host(double x) {
+    if (!(x > 0.0)) return 0;
+    if (x >= 18446744073709551615.0) return 0xFFFFFFFFFFFFFFFFull;
+    return (uint64_t)x;
+}
+
+VL_API int vl_step(vl_sim *const *sims, uint32_t C, const double *T, int rule) {
+    if (!sims || C == 0 || !T) return fail(nullptr, VL_ERR_ARGUMENT, "null argument");
+    std::vector<std::unique_lock<std::recursive_mutex>> locks;
+    for (uint32_t c = 0; c < C; c++) {
+        if (!sims[c]) return fail(nullptr, VL_ERR_ARGUMENT, "null handle");
+        locks.emplace_back(sims[c]->mu);
+    }
+    vl_sim *s0 = sims[0];
+#define ON(c) CU(sims[c], cudaSetDevice(sims[c]->device))
+    // runner.rs:382-399: generation++, infect, mutate, replicate on every compartment (streams overlap)
+    for (uint32_t c = 0; c < C; c++) {
+        ON(c);
+        LAUNCH(sims[c], k_tick, 1, 1, 0, sims[c]->d);
+        sims[c]->salt = 0;
+        TRY(enqueue_infect(sims[c]));
+        TRY(enqueue_mutate(sims[c]));
+        TRY(enqueue_replicate(sims[c]));
+    }
+    std::vector<vl_pop *> parts((size_t)C * C, nullptr);
+    auto cleanup = [&]() { for (vl_pop *p : parts) if (p) { cudaSetDevice(p->owner->device); cudaStreamSynchronize(p->owner->stream); drop_pop(p); } };
+    int rc = VL_OK;
+    if (rule == 0) {
+        // parallel-build rule (runner.rs:401-416): new[t] = concat_o subsample(sim[o], offspring[o], T[t][o])
+        for (uint32_t o = 0; o < C && rc == VL_OK; o++) {
+            ON(o);
+            for (uint32_t t = 0; t < C && rc == VL_OK; t++) rc = enqueue_subsample(sims[o], T[(size_t)t * C + o], 0, 0, &parts[(size_t)t * C + o]);
+        }
+    } else {
+        // serial-build rule (runner.rs:550-631)
+        std::vector<double> ts(C);
+        for (uint32_t t = 0; t < C && rc == VL_OK; t++) {
+            ON(t);
+            LAUNCH(sims[t], k_target_size, 1, TPB, 0, sims[t]->d);
+            rc = read_field(sims[t], FIELD_OFF(target_size), &ts[t]);
+        }
+        std::vector<uint64_t> amount((size_t)C * C, 0);
+        if (rc == VL_OK) {
+            uint32_t gen = 0;
+            rc = read_field(s0, FIELD_OFF(generation), &gen);
+            for (uint32_t t = 0; t < C; t++) {
+                Philox g(sims[t]->h.seed, sims[t]->h.compartment, gen, PH_MIGRANT, t);
+                for (uint32_t o = 0; o < C; o++) {
+                    if (t == o) continue;
+                    double m = ts[t] * T[(size_t)t * C + o];
+                    uint64_t residue = g.u01() < m - floor(m) ? 1 : 0;
+                    amount[(size_t)t * C + o] = f64_as_usize_host(m) + residue;
+                }
+            }
+            for (uint32_t t = 0; t < C && rc == VL_OK; t++) {
+                uint64_t mig = 0;
+                for (uint32_t o = 0; o < C; o++) mig += amount[(size_t)t * C + o];
+                if (f64_as_usize_host(ts[t]) < mig) rc = fail(s0, VL_ERR_REFERENCE_PANIC, "migrants into compartment %u exceed its target size: usize underflow panics (src/runner.rs:583-590)", t);
+                else amount[(size_t)t * C + t] = f64_as_usize_host(ts[t]) - mig;
+            }
+        }
+        for (uint32_t o = 0; o < C && rc == VL_OK; o++) {
+            ON(o);
+            for (uint32_t t = 0; t < C && rc == VL_OK; t++) rc = enqueue_subsample(sims[o], 0.0, 1, amount[(size_t)t * C + o], &parts[(size_t)t * C + o]);
+        }
+    }
+    for (uint32_t c = 0; c < C && rc == VL_OK; c++) {
+        ON(c);
+        cudaStreamSynchronize(sims[c]->stream);
+        rc = check_device_error(sims[c]);
+        if (rc != VL_OK && c != 0) fail(s0, rc, "%s", sims[c]->err);
+    }
+    if (rc != VL_OK) { cleanup(); return rc; }
+    for (vl_pop *p : parts) finalize_pop(p);
+    for (uint32_t t = 0; t < C; t++) {
+        ON(t);
+        rc = vl_set_population(sims[t], &parts[(size_t)t * C], C);
+        for (uint32_t o = 0; o < C; o++) parts[(size_t)t * C + o] = nullptr;
+        if (rc != VL_OK) { if (t != 0) fail(s0, rc, "%s", sims[t]->err); cleanup(); return rc; }
+    }
+#undef ON
+    return VL_OK;
+}
+
+VL_API int vl_infectant_generations(vl_sim *sim, uint64_t *out, int reset) {
+    ENTER(sim);
+    TRY(read_field(sim, FIELD_OFF(infectant_generations), out));
+    if (reset) TRY(write_field(sim, FIELD_OFF(infectant_generations), (uint64_t)0));
+    return VL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- replay hooks
+template <typename T>
+static int upload_replace(vl_sim *sim, T **dev, const T *src, uint64_t n) {
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    if (*dev) { cudaFree(*dev); *dev = nullptr; }
+    CU(sim, cudaMalloc((void **)dev, std::max<uint64_t>(n, 1) * sizeof(T)));
+    if (n) CU(sim, cudaMemcpy(*dev, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return VL_OK;
+}
+VL_API int vl_replay_infections(vl_sim *sim, const int64_t *infections, uint64_t n) {
+    ENTER(sim);
+    uint64_t cur = 0;
+    TRY(population_len(sim, &cur));
+    if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "infection log has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
+    TRY(upload_replace(sim, &sim->rp_inf, infections, n));
+    sim->has_rp_inf = true;
+    return VL_OK;
+}
+VL_API int vl_replay_mutations(vl_sim *sim, const uint64_t *offsets, uint64_t n, const uint32_t *sites, const uint8_t *bases) {
+    ENTER(sim);
+    uint64_t cur = 0;
+    TRY(population_len(sim, &cur));
+    if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "mutation log has %llu infectants, population has %llu", (unsigned long long)n, (unsigned long long)cur);
+    for (uint64_t i = 0; i < n; i++) if (offsets[i + 1] < offsets[i]) return fail(sim, VL_ERR_ARGUMENT, "mutation log offsets not monotone");
+    const uint64_t total = n ? offsets[n] : 0;
+    uint64_t zero = 0;
+    TRY(upload_replace(sim, &sim->rp_mut_off, n ? offsets : &zero, n + 1));
+    TRY(upload_replace(sim, &sim->rp_mut_sites, sites, total));
+    TRY(upload_replace(sim, &sim->rp_mut_bases, bases, total));
+    sim->has_rp_mut = true;
+    return VL_OK;
+}
+VL_API int vl_replay_recombinations(vl_sim *sim, uint64_t n_events, const uint64_t *host, const uint32_t *i, const uint32_t *j,
+                                    const uint32_t *s0, const uint32_t *s1, const uint8_t *which) {
+    ENTER(sim);
+    for (uint64_t e = 1; e < n_events; e++) if (host[e] < host[e - 1]) return fail(sim, VL_ERR_ARGUMENT, "recombination log must be sorted by host");
+    TRY(upload_replace(sim, &sim->rp_rec_host, host, n_events));
+    TRY(upload_replace(sim, &sim->rp_rec_i, i, n_events));
+    TRY(upload_replace(sim, &sim->rp_rec_j, j, n_events));
+    TRY(upload_replace(sim, &sim->rp_rec_s0, s0, n_events));
+    TRY(upload_replace(sim, &sim->rp_rec_s1, s1, n_events));
+    TRY(upload_replace(sim, &sim->rp_rec_which, which, n_events));
+    sim->rp_rec_n = n_events;
+    sim->has_rp_rec = true;
+    return VL_OK;
+}
+VL_API int vl_replay_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n) {
+    ENTER(sim);
+    uint64_t cur = 0;
+    TRY(population_len(sim, &cur));
+    if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "offspring log has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
+    TRY(upload_replace(sim, &sim->rp_off, offspring, n));
+    sim->has_rp_off = true;
+    return VL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- inspection
+template <typename T>
+static int download(vl_sim *sim, std::vector<T> &host, const T *dev, uint64_t n) {
+    host.resize(n);
+    if (n) CU(sim, cudaMemcpyAsync(host.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    return VL_OK;
+}
+static int expect_len(vl_sim *sim, uint64_t n) {
+    uint64_t cur = 0;
+    TRY(population_len(sim, &cur));
+    if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "buffer has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
+    return VL_OK;
+}
+VL_API int vl_get_infections(vl_sim *sim, int64_t *out, uint64_t n) {
+    ENTER(sim);
+    TRY(expect_len(sim, n));
+    std::vector<uint32_t> v;
+    TRY(download(sim, v, (const uint32_t *)sim->h.host_id, n));
+    for (uint64_t i = 0; i < n; i++) out[i] = v[i] == NONE32 ? -1 : (int64_t)v[i];
+    return VL_OK;
+}
+VL_API int vl_get_host_map(vl_sim *sim, uint64_t *offsets_out, uint64_t *hosts_out, uint64_t *n_infected_out) {
+    ENTER(sim);
+    if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no host map: vl_infect has not run (or ran with VL_FLAG_ATOMIC_HOST_SUM)");
+    std::vector<uint32_t> off, hosts;
+    TRY(download(sim, off, (const uint32_t *)sim->h.offsets, sim->h.H + 1));
+    const uint64_t ninf = off[sim->h.H];
+    TRY(download(sim, hosts, (const uint32_t *)sim->h.hosts, ninf));
+    if (offsets_out) for (uint64_t k = 0; k <= sim->h.H; k++) offsets_out[k] = off[k];
+    if (hosts_out) for (uint64_t k = 0; k < ninf; k++) hosts_out[k] = hosts[k];
+    if (n_infected_out) *n_infected_out = ninf;
+    return VL_OK;
+}
+VL_API int vl_get_replication_terms(vl_sim *sim, double *fitness_out, double *host_sum_out, double *lambda_out, uint64_t n) {
+    ENTER(sim);
+    TRY(expect_len(sim, n));
+    double *tmp = nullptr;
+    CU(sim, cudaMalloc((void **)&tmp, std::max<uint64_t>(2 * n, 1) * 8));
+    LAUNCH(sim, k_replication_terms, grid_for(sim, n), TPB, 0, sim->d, tmp, tmp + n);
+    if (n) {
+        if (fitness_out) CU(sim, cudaMemcpyAsync(fitness_out, sim->h.fit, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+        if (host_sum_out) CU(sim, cudaMemcpyAsync(host_sum_out, tmp, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+        if (lambda_out) CU(sim, cudaMemcpyAsync(lambda_out, tmp + n, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+    }
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    cudaFree(tmp);
+    return VL_OK;
+}
+VL_API int vl_get_offspring_prefix(vl_sim *sim, uint64_t *prefix_out, uint64_t n) {
+    ENTER(sim);
+    TRY(expect_len(sim, n));
+    // inclusive scan of the device-resident offspring map (the CDF Population::sample draws from)
+    TRY((launch_scan<uint64_t, false>(sim, sim->h.offspring, sim->stage64, nullptr, n, n, nullptr, 0, nullptr)));
+    if (n) CU(sim, cudaMemcpyAsync(prefix_out, sim->stage64, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    return VL_OK;
+}
+VL_API int vl_get_raw_fitness(vl_sim *sim, uint32_t spec, int which, double *out, uint64_t n) {
+    ENTER(sim);
+    TRY(expect_len(sim, n));
+    if (spec >= sim->h.n_specs) return fail(sim, VL_ERR_ARGUMENT, "spec out of range");
+    const int pi = which ? sim->h.specs[spec].infect : sim->h.specs[spec].repro;
+    if (pi < 0) { for (uint64_t i = 0; i < n; i++) out[i] = 1.0; return VL_OK; }
+    double *tmp = (double *)sim->stage64;
+    LAUNCH(sim, k_gather_raw, grid_for(sim, n), TPB, 0, sim->d, (uint32_t)pi, tmp);
+    if (n) CU(sim, cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    return VL_OK;
+}
+VL_API int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, uint32_t *positions_out, uint8_t *bases_out, uint64_t *n_entries) {
+    ENTER(sim);
+    TRY(expect_len(sim, n));
+    uint32_t *cnt = sim->h.rank;  // per-infectant scratch, free between phases
+    LAUNCH(sim, k_export_count, grid_for(sim, n), TPB, 0, sim->d, cnt);
+    TRY((launch_scan<uint64_t, true>(sim, cnt, sim->stage64, nullptr, n, n, sim->gc_totals + 6, 0, nullptr)));
+    CU(sim, cudaMemcpyAsync(sim->pin, sim->gc_totals + 6, 8, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    const uint64_t total = sim->pin[0];
+    if (n_entries) *n_entries = total;
+    if (offsets_out) {
+        if (n) CU(sim, cudaMemcpy(offsets_out, sim->stage64, n * 8, cudaMemcpyDeviceToHost));
+        offsets_out[n] = total;
+    }
+    if (positions_out && bases_out && total) {
+        uint32_t *dp = nullptr; uint8_t *db = nullptr;
+        CU(sim, cudaMalloc((void **)&dp, total * 4));
+        CU(sim, cudaMalloc((void **)&db, total));
+        LAUNCH(sim, k_export_fill, grid_for(sim, n), TPB, 0, sim->d, (const uint64_t *)sim->stage64, dp, db);
+        CU(sim, cudaMemcpyAsync(positions_out, dp, total * 4, cudaMemcpyDeviceToHost, sim->stream));
+        CU(sim, cudaMemcpyAsync(bases_out, db, total, cudaMemcpyDeviceToHost, sim->stream));
+        CU(sim, cudaStreamSynchronize(sim->stream));
+        cudaFree(dp); cudaFree(db);
+    }
+    return VL_OK;
+}
+VL_API int vl_get_base(vl_sim *sim, uint64_t infectant, uint64_t position, uint8_t *out) {
+    ENTER(sim);
+    uint32_t *tmp = (uint32_t *)(sim->gc_totals + 8);
+    LAUNCH(sim, k_get_base, 1, 1, 0, sim->d, infectant, (uint32_t)position, tmp);
+    CU(sim, cudaMemcpyAsync(sim->pin, tmp, 4, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    uint32_t v;
+    memcpy(&v, sim->pin, 4);
+    if (v > 3) return fail(sim, VL_ERR_ARGUMENT, "infectant or position out of range");
+    *out = (uint8_t)v;
+    return VL_OK;
+}
+VL_API int vl_get_haplotype_ids(vl_sim *sim, uint32_t *out, uint64_t n) {
+    ENTER(sim);
+    TRY(expect_len(sim, n));
+    if (n) CU(sim, cudaMemcpyAsync(out, sim->h.hap_id, n * 4, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    return VL_OK;
+}
+VL_API int vl_get_counters(vl_sim *sim, uint64_t *out4) {
+    ENTER(sim);
+    unsigned long long nh = 0, at = 0;
+    uint64_t runs = 0;
+    TRY(read_field(sim, FIELD_OFF(n_hap), &nh));
+    TRY(read_field(sim, FIELD_OFF(arena_top), &at));
+    TRY(read_field(sim, FIELD_OFF(gc_runs), &runs));
+    out4[0] = nh; out4[1] = at; out4[2] = runs; out4[3] = sim->launches;
+    return VL_OK;
+}
+VL_API int vl_collect_garbage(vl_sim *sim) {
+    ENTER(sim);
+    TRY(enqueue_gc(sim, 1));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    return check_device_error(sim);
+}
+
+// ---------------------------------------------------------------------------------------------- measurement hooks
+VL_API int vl_timer_start(vl_sim *sim) {
+    ENTER(sim);
+    if (!sim->timer_a) { CU(sim, cudaEventCreate(&sim->timer_a)); CU(sim, cudaEventCreate(&sim->timer_b)); }
+    CU(sim, cudaEventRecord(sim->timer_a, sim->stream));
+    return VL_OK;
+}
+VL_API int vl_timer_stop(vl_sim *sim, double *ms_out) {
+    ENTER(sim);
+    if (!sim->timer_a) return fail(sim, VL_ERR_ARGUMENT, "timer not started");
+    CU(sim, cudaEventRecord(sim->timer_b, sim->stream));
+    CU(sim, cudaEventSynchronize(sim->timer_b));
+    float ms = 0.f;
+    CU(sim, cudaEventElapsedTime(&ms, sim->timer_a, sim->timer_b));
+    if (ms_out) *ms_out = ms;
+    return check_device_error(sim);
+}
+VL_API int vl_profile(vl_sim *sim, int enable) {
+    ENTER(sim);
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    for (auto &r : sim->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    sim->prof.clear();
+    sim->profiling = enable != 0;
+    return VL_OK;
+}
+// text report, one line per kernel: "<name> <launches> <total_ms>\n"
+VL_API int vl_profile_report(vl_sim *sim, char *buf, uint64_t cap) {
+    ENTER(sim);
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    std::vector<std::string> names;
+    std::vector<double> total;
+    std::vector<uint64_t> count;
+    for (auto &r : sim->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+        size_t k = 0;
+        for (; k < names.size(); k++) if (names[k] == r.name) break;
+        if (k == names.size()) { names.push_back(r.name); total.push_back(0.0); count.push_back(0); }
+        total[k] += ms;
+        count[k] += 1;
+    }
+    std::string out;
+    char line[256];
+    for (size_t k = 0; k < names.size(); k++) {
+        snprintf(line, sizeof line, "%s %llu %.6f\n", names[k].c_str(), (unsigned long long)count[k], total[k]);
+        out += line;
+    }
+    if (buf && cap) {
+        size_t m = std::min<size_t>(out.size(), cap - 1);
+        memcpy(buf, out.data(), m);
+        buf[m] = 0;
+    }
+    return VL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- sampler test hooks
+static int run_sampler(int which, uint64_t seed, uint64_t a, double b, uint64_t n, uint64_t *out) {
+    uint64_t *dev = nullptr;
+    if (cudaMalloc((void **)&dev, std::max<uint64_t>(n, 1) * 8) != cudaSuccess) return fail(nullptr, VL_ERR_CUDA, "no CUDA device / out of memory");
+    unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256 + 1, 4096);
+    if (which == 0) k_test_poisson<<<g, 256>>>(seed, b, n, dev);
+    else if (which == 1) k_test_binomial<<<g, 256>>>(seed, a, b, n, dev);
+    else k_test_below<<<g, 256>>>(seed, a, n, dev);
+    cudaError_t e = cudaMemcpy(out, dev, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(nullptr, VL_ERR_CUDA, "sampler kernel failed: %s", cudaGetErrorString(e));
+    return VL_OK;
+}
+VL_API int vl_test_poisson(uint64_t seed, double lambda, uint64_t n, uint64_t *out) { return run_sampler(0, seed, 0, lambda, n, out); }
+VL_API int vl_test_binomial(uint64_t seed, uint64_t trials, double p, uint64_t n, uint64_t *out) { return run_sampler(1, seed, trials, p, n, out); }
+VL_API int vl_test_below(uint64_t seed, uint64_t bound, uint64_t n, uint64_t *out) { return run_sampler(2, seed, bound, 0.0, n, out); }

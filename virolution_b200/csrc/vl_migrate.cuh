@@ -1,0 +1,199 @@
+// vl_migrate.cuh — moving populations between handles (compartments / GPUs) and exporting them.
+//
+// The reference shares one Rc/Arc haplotype tree between all compartments of a process, so transmission
+// (src/runner.rs:401-422) only moves references.  Here every handle owns its arena, so a detached population
+// that crosses handles is turned into a self-contained image: every distinct haplotype once (flattened
+// entries + memoised raw fitness per provider) plus one local index per infectant.  The same image is what
+// travels over NVLink between GPUs.  Export kernels back Haplotype::get_mutations / get_base for
+// final.<i>.csv and the parity tests (src/core/haplotype.rs:402-466, src/runner.rs:137-152).
+#pragma once
+#include "vl_kernels.cuh"
+
+namespace vl {
+
+constexpr uint64_t PACK_MAGIC = 0x564c5041434b3031ull;  // "VLPACK01"
+
+struct PackHeader {
+    uint64_t magic;
+    uint64_t n_pop, n_unique, n_words, n_providers;
+    uint64_t off_idx, off_len, off_off, off_raw, off_entries;  // byte offsets from the image start
+    uint64_t bytes;
+    uint64_t _pad;
+};
+
+__host__ __device__ inline uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
+__host__ inline PackHeader make_pack_header(uint64_t n_pop, uint64_t n_unique, uint64_t n_words, uint64_t n_providers) {
+    PackHeader h;
+    h.magic = PACK_MAGIC;
+    h.n_pop = n_pop; h.n_unique = n_unique; h.n_words = n_words; h.n_providers = n_providers;
+    uint64_t o = align16(sizeof(PackHeader));
+    h.off_idx = o; o = align16(o + n_pop * 4);
+    h.off_len = o; o = align16(o + n_unique * 4);
+    h.off_off = o; o = align16(o + n_unique * 8);
+    h.off_raw = o; o = align16(o + n_providers * n_unique * 8);
+    h.off_entries = o; o = align16(o + n_words * 4);
+    h.bytes = o;
+    h._pad = 0;
+    return h;
+}
+
+__global__ void __launch_bounds__(TPB) k_pack_clear(DevState *st) {
+    const uint64_t nh = st->n_hap;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_mark[h] = 0u;
+}
+// the wildtype (id 0) exists on every handle and is never shipped
+__global__ void __launch_bounds__(TPB) k_pack_mark(DevState *st, const uint32_t *__restrict__ ids, uint64_t m) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        if (id != 0) st->gc_mark[id] = 1u;
+    }
+}
+__global__ void __launch_bounds__(TPB) k_pack_lens(DevState *st) {
+    const uint64_t nh = st->n_hap;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_len[h] = st->gc_mark[h] ? st->h_len[h] : 0u;
+}
+__global__ void __launch_bounds__(TPB) k_pack_copy(DevState *st, const uint32_t *__restrict__ ids, uint8_t *image, PackHeader hd) {
+    const uint64_t nh = st->n_hap;
+    uint32_t *o_idx = reinterpret_cast<uint32_t *>(image + hd.off_idx);
+    uint32_t *o_len = reinterpret_cast<uint32_t *>(image + hd.off_len);
+    uint64_t *o_off = reinterpret_cast<uint64_t *>(image + hd.off_off);
+    double *o_raw = reinterpret_cast<double *>(image + hd.off_raw);
+    uint32_t *o_ent = reinterpret_cast<uint32_t *>(image + hd.off_entries);
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, span = (uint64_t)gridDim.x * blockDim.x;
+    if (tid == 0) *reinterpret_cast<PackHeader *>(image) = hd;
+    for (uint64_t h = tid; h < nh; h += span) {
+        if (!st->gc_mark[h]) continue;
+        const uint32_t u = st->gc_newid[h];
+        const uint64_t noff = st->gc_newoff[h];
+        const uint32_t len = st->h_len[h];
+        o_len[u] = len;
+        o_off[u] = noff;
+        for (uint32_t p = 0; p < st->n_providers; p++) o_raw[(uint64_t)p * hd.n_unique + u] = st->h_raw[p][h];
+        const uint32_t *src = st->arena + st->h_off[h];
+        for (uint32_t k = 0; k < len; k++) o_ent[noff + k] = src[k];
+    }
+    for (uint64_t i = tid; i < hd.n_pop; i += span) {
+        const uint32_t id = ids[i];
+        o_idx[i] = id == 0 ? NONE32 : st->gc_newid[id];
+    }
+}
+
+// reserve[0] = first new haplotype id (NONE32 on failure), reserve[1] = first arena word
+__global__ void k_reserve_bulk(DevState *st, uint64_t n_records, uint64_t n_words, uint64_t *reserve) {
+    const uint64_t id0 = st->n_hap, a0 = st->arena_top;
+    if (id0 + n_records > st->cap_hap) { raise(st, DE_HAP_CAPACITY); reserve[0] = NONE32; return; }
+    if (a0 + n_words > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); reserve[0] = NONE32; return; }
+    st->n_hap = id0 + n_records;
+    st->arena_top = a0 + n_words;
+    reserve[0] = id0;
+    reserve[1] = a0;
+}
+// dst == nullptr: write into the population being assembled at dst_off
+__global__ void __launch_bounds__(TPB) k_unpack(DevState *st, const uint8_t *__restrict__ image, PackHeader hd, const uint64_t *reserve,
+                                                uint32_t *dst, uint64_t dst_off) {
+    const uint32_t *i_idx = reinterpret_cast<const uint32_t *>(image + hd.off_idx);
+    const uint32_t *i_len = reinterpret_cast<const uint32_t *>(image + hd.off_len);
+    const uint64_t *i_off = reinterpret_cast<const uint64_t *>(image + hd.off_off);
+    const double *i_raw = reinterpret_cast<const double *>(image + hd.off_raw);
+    const uint32_t *i_ent = reinterpret_cast<const uint32_t *>(image + hd.off_entries);
+    if (dst == nullptr) dst = st->hap_id_next;
+    dst += dst_off;
+    const uint64_t id0 = reserve[0], a0 = reserve[1];
+    const bool ok = id0 != NONE32;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, span = (uint64_t)gridDim.x * blockDim.x;
+    if (ok) {
+        for (uint64_t u = tid; u < hd.n_unique; u += span) {
+            const uint64_t id = id0 + u;
+            st->h_off[id] = a0 + i_off[u];
+            st->h_len[id] = i_len[u];
+            st->h_parent[id] = NONE32;
+            for (uint32_t p = 0; p < st->n_providers; p++) st->h_raw[p][id] = i_raw[(uint64_t)p * hd.n_unique + u];
+        }
+        for (uint64_t w = tid; w < hd.n_words; w += span) st->arena[a0 + w] = i_ent[w];
+    }
+    for (uint64_t i = tid; i < hd.n_pop; i += span) {
+        const uint32_t u = i_idx[i];
+        dst[i] = (u == NONE32 || !ok) ? 0u : (uint32_t)(id0 + u);
+    }
+}
+
+// population assembly from parts that already live on this handle
+__global__ void __launch_bounds__(TPB) k_copy_ids(DevState *st, const uint32_t *__restrict__ src, uint64_t m, uint64_t dst_off) {
+    uint32_t *dst = st->hap_id_next + dst_off;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_set_next_n(DevState *st, uint64_t n) { st->n_next = n; }
+__global__ void k_fill_population(DevState *st, uint64_t n, uint32_t id) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) st->hap_id[i] = id;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->n = n;
+}
+// copy of the first n_next entries of the assembled population (detached subsample of the fused path)
+__global__ void __launch_bounds__(TPB) k_copy_out_next(DevState *st, uint32_t *__restrict__ dst, uint64_t cap) {
+    const uint64_t m = st->n_next < cap ? st->n_next : cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = st->hap_id_next[i];
+}
+
+// target_size over the tile totals (src/simulation.rs:491-503); does not raise on an all-zero map
+__global__ void __launch_bounds__(TPB) k_target_size(DevState *st) {
+    __shared__ uint64_t s_red[TPB / 32];
+    const uint64_t n = st->n;
+    const uint64_t nt = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    uint64_t local = 0;
+    for (uint64_t t = threadIdx.x; t < nt; t += TPB) local += st->tile_sum[t];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t total = 0;
+        for (int w = 0; w < TPB / 32; w++) total += s_red[w];
+        double target = 0.0;
+        if (n > 0) {
+            double a = (double)total * st->dilution, b = (double)st->max_population;
+            target = a <= b ? a : b;
+        }
+        st->offspring_total = total;
+        st->target_size = target;
+    }
+}
+
+// ---- export: Haplotype::get_mutations per infectant (entries whose mutation-set view is present)
+__global__ void __launch_bounds__(TPB) k_export_count(DevState *st, uint32_t *__restrict__ cnt) {
+    const uint64_t n = st->n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = st->hap_id[i];
+        const uint32_t *e = st->arena + st->h_off[id];
+        const uint32_t len = st->h_len[id];
+        uint32_t c = 0;
+        for (uint32_t k = 0; k < len; k++) c += entry_m(e[k]) < 4 ? 1u : 0u;
+        cnt[i] = c;
+    }
+}
+__global__ void __launch_bounds__(TPB) k_export_fill(DevState *st, const uint64_t *__restrict__ offsets, uint32_t *__restrict__ pos_out,
+                                                     uint8_t *__restrict__ base_out) {
+    const uint64_t n = st->n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = st->hap_id[i];
+        const uint32_t *e = st->arena + st->h_off[id];
+        const uint32_t len = st->h_len[id];
+        uint64_t o = offsets[i];
+        for (uint32_t k = 0; k < len; k++) {
+            if (entry_m(e[k]) < 4) { pos_out[o] = entry_pos(e[k]); base_out[o] = (uint8_t)entry_m(e[k]); o++; }
+        }
+    }
+}
+__global__ void k_get_base(DevState *st, uint64_t infectant, uint32_t pos, uint32_t *out) {
+    if (infectant >= st->n || pos >= st->L) { *out = 0xFFu; return; }
+    const uint32_t id = st->hap_id[infectant];
+    *out = entries_get_base(st->arena + st->h_off[id], st->h_len[id], pos, st->wildtype);
+}
+
+// ---- direct haplotype construction (Haplotype::create_descendant / create_recombinant through the ABI;
+//      used by the known-answer tests of src/core/haplotype.rs:957-1048 and src/lib.rs:113-142)
+__global__ void k_make_recombinant(DevState *st, uint64_t dst_infectant, uint64_t left_infectant, uint64_t right_infectant, uint32_t s0,
+                                   uint32_t s1) {
+    if (dst_infectant >= st->n || left_infectant >= st->n || right_infectant >= st->n || s0 >= s1 || s1 > st->L) { raise(st, DE_REPLAY); return; }
+    st->hap_id[dst_infectant] = make_recombinant(st, st->hap_id[left_infectant], st->hap_id[right_infectant], s0, s1);
+}
+
+}  // namespace vl

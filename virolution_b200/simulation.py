@@ -1,0 +1,431 @@
+"""Host-side mirror of the reference's `trait Simulation<S>` (src/simulation.rs:177-219) over the C ABI.
+
+`GpuSimulation` has the trait's methods with the trait's names and argument meaning; every one of them is a
+thin ctypes call into libvirolution_gpu.so (include/virolution_gpu.h).  There is no CPU path here: if the
+library is missing, or no device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import abi
+from .abi import HostSpec, MarshalledConfig, Parameters, vl_config, vl_parameters
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvirolution_gpu.so")
+_LIB = None
+
+u64p, u32p, u8p, i64p, f64p = (C.POINTER(t) for t in (C.c_uint64, C.c_uint32, C.c_uint8, C.c_int64, C.c_double))
+_vp = C.c_void_p
+
+# every symbol include/virolution_gpu.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "vl_create": (C.c_int, [C.POINTER(vl_config), C.POINTER(_vp)]),
+    "vl_destroy": (C.c_int, [_vp]),
+    "vl_last_error": (C.c_char_p, [_vp]),
+    "vl_abi_version": (C.c_int, []),
+    "vl_increment_generation": (C.c_int, [_vp]),
+    "vl_get_generation": (C.c_int, [_vp, u64p]),
+    "vl_set_generation": (C.c_int, [_vp, C.c_uint64]),
+    "vl_set_parameters": (C.c_int, [_vp, C.POINTER(vl_parameters)]),
+    "vl_population_len": (C.c_int, [_vp, u64p]),
+    "vl_set_population_wildtype": (C.c_int, [_vp, C.c_uint64]),
+    "vl_infect": (C.c_int, [_vp]),
+    "vl_mutate_infectants": (C.c_int, [_vp]),
+    "vl_replicate_infectants": (C.c_int, [_vp, u64p, C.c_uint64]),
+    "vl_target_size": (C.c_int, [_vp, u64p, C.c_uint64, f64p]),
+    "vl_sample_indices": (C.c_int, [_vp, u64p, C.c_uint64, C.c_uint64, u64p]),
+    "vl_subsample_population": (C.c_int, [_vp, u64p, C.c_uint64, C.c_double, C.POINTER(_vp)]),
+    "vl_select": (C.c_int, [_vp, u64p, C.c_uint64, C.POINTER(_vp)]),
+    "vl_set_population": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32]),
+    "vl_pop_len": (C.c_int, [_vp, u64p]),
+    "vl_pop_free": (C.c_int, [_vp]),
+    "vl_next_generation": (C.c_int, [_vp]),
+    "vl_run": (C.c_int, [_vp, C.c_uint64]),
+    "vl_step": (C.c_int, [C.POINTER(_vp), C.c_uint32, f64p, C.c_int]),
+    "vl_synchronize": (C.c_int, [_vp]),
+    "vl_infectant_generations": (C.c_int, [_vp, u64p, C.c_int]),
+    "vl_replay_infections": (C.c_int, [_vp, i64p, C.c_uint64]),
+    "vl_replay_mutations": (C.c_int, [_vp, u64p, C.c_uint64, u32p, u8p]),
+    "vl_replay_recombinations": (C.c_int, [_vp, C.c_uint64, u64p, u32p, u32p, u32p, u32p, u8p]),
+    "vl_replay_offspring": (C.c_int, [_vp, u64p, C.c_uint64]),
+    "vl_get_infections": (C.c_int, [_vp, i64p, C.c_uint64]),
+    "vl_get_host_map": (C.c_int, [_vp, u64p, u64p, u64p]),
+    "vl_get_replication_terms": (C.c_int, [_vp, f64p, f64p, f64p, C.c_uint64]),
+    "vl_get_offspring_prefix": (C.c_int, [_vp, u64p, C.c_uint64]),
+    "vl_get_raw_fitness": (C.c_int, [_vp, C.c_uint32, C.c_int, f64p, C.c_uint64]),
+    "vl_export_mutations": (C.c_int, [_vp, u64p, C.c_uint64, u32p, u8p, u64p]),
+    "vl_get_base": (C.c_int, [_vp, C.c_uint64, C.c_uint64, u8p]),
+    "vl_get_haplotype_ids": (C.c_int, [_vp, u32p, C.c_uint64]),
+    "vl_get_counters": (C.c_int, [_vp, u64p]),
+    "vl_collect_garbage": (C.c_int, [_vp]),
+    "vl_pop_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), u64p]),
+    "vl_pop_unpack_device": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "vl_timer_start": (C.c_int, [_vp]),
+    "vl_timer_stop": (C.c_int, [_vp, f64p]),
+    "vl_profile": (C.c_int, [_vp, C.c_int]),
+    "vl_profile_report": (C.c_int, [_vp, C.c_char_p, C.c_uint64]),
+    "vl_test_poisson": (C.c_int, [C.c_uint64, C.c_double, C.c_uint64, u64p]),
+    "vl_test_binomial": (C.c_int, [C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, u64p]),
+    "vl_test_below": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, u64p]),
+}
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the C-ABI library and bind every declared symbol.  Raises if the library is absent: the product
+    path has no fallback."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} is missing: build it with `python -m virolution_b200.build` (nvcc, sm_100a). "
+                           "virolution_b200 has no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError = header/library mismatch
+        fn.restype, fn.argtypes = res, args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+class VirolutionError(RuntimeError):
+    """Non-zero vl_status.  `code` is the status, the message comes from vl_last_error."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+
+
+class ReferencePanic(VirolutionError):
+    """The reference panics at this point (VL_ERR_REFERENCE_PANIC)."""
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class GpuPopulation:
+    """Detached `Population<Store<S>>` (src/core/population.rs:156-163) living in device memory of its origin."""
+
+    def __init__(self, ptr, origin: "GpuSimulation"):
+        self.ptr = ptr
+        self.origin = origin
+
+    def __len__(self) -> int:
+        n = C.c_uint64()
+        load_library().vl_pop_len(self.ptr, C.byref(n))
+        return int(n.value)
+
+    def free(self):
+        if self.ptr:
+            load_library().vl_pop_free(self.ptr)
+            self.ptr = None
+
+    def pack_device(self):
+        """(device pointer, bytes) of the self-contained image that travels between GPUs."""
+        img, nbytes = _vp(), C.c_uint64()
+        self.origin._check(load_library().vl_pop_pack_device(self.origin.ptr, self.ptr, C.byref(img), C.byref(nbytes)))
+        return int(img.value), int(nbytes.value)
+
+    def __del__(self):
+        try:
+            if self.ptr and self.origin.ptr:
+                self.free()
+        except Exception:
+            pass
+
+
+class GpuSimulation:
+    """`impl Simulation<Nt>` on one B200 (one compartment).  Constructor = BasicSimulation::new
+    (src/simulation.rs:235-256) with the resolved configuration."""
+
+    def __init__(self, wildtype: np.ndarray, parameters: Parameters, host_specs: Sequence[HostSpec], seed: int = 0,
+                 device: int = 0, compartment_id: int = 0, flags: int = 0, capacity_infectants: int = 0,
+                 capacity_haplotypes: int = 0, capacity_arena_words: int = 0):
+        self.lib = load_library()
+        self._cfg = MarshalledConfig(wildtype, parameters, host_specs, seed=seed, device=device,
+                                     compartment_id=compartment_id, flags=flags,
+                                     capacity_infectants=capacity_infectants, capacity_haplotypes=capacity_haplotypes,
+                                     capacity_arena_words=capacity_arena_words)
+        self.parameters = parameters
+        self.host_specs = list(host_specs)
+        self.n_sites = int(len(wildtype))
+        self.device = device
+        ptr = _vp()
+        rc = self.lib.vl_create(self._cfg.ref(), C.byref(ptr))
+        if rc != 0:
+            raise VirolutionError(rc, (self.lib.vl_last_error(None) or b"").decode())
+        self.ptr = ptr
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = (self.lib.vl_last_error(self.ptr) or b"").decode()
+            raise (ReferencePanic if rc == abi.VL_ERR_REFERENCE_PANIC else VirolutionError)(rc, msg)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.lib.vl_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _offspring_args(self, offspring):
+        if offspring is None:
+            return None, 0, None
+        off = np.ascontiguousarray(offspring, dtype=np.uint64)
+        return _p(off, C.c_uint64), off.size, off
+
+    # ------------------------------------------------------------------ Simulation trait
+    def increment_generation(self):
+        self._check(self.lib.vl_increment_generation(self.ptr))
+
+    def get_generation(self) -> int:
+        g = C.c_uint64()
+        self._check(self.lib.vl_get_generation(self.ptr, C.byref(g)))
+        return int(g.value)
+
+    def set_generation(self, generation: int):
+        self._check(self.lib.vl_set_generation(self.ptr, generation))
+
+    def set_parameters(self, parameters: Parameters):
+        self._check(self.lib.vl_set_parameters(self.ptr, C.byref(parameters.to_c())))
+        self.parameters = parameters
+
+    def population_len(self) -> int:
+        n = C.c_uint64()
+        self._check(self.lib.vl_population_len(self.ptr, C.byref(n)))
+        return int(n.value)
+
+    def set_population_wildtype(self, n: int):
+        self._check(self.lib.vl_set_population_wildtype(self.ptr, n))
+
+    def get_host_specs(self) -> List[HostSpec]:
+        return self.host_specs
+
+    def infect(self):
+        self._check(self.lib.vl_infect(self.ptr))
+
+    def mutate_infectants(self):
+        self._check(self.lib.vl_mutate_infectants(self.ptr))
+
+    def replicate_infectants(self, out: Optional[np.ndarray] = None, to_host: bool = True):
+        """Returns the offspring map (`Vec<usize>`) unless to_host=False (kept on the device)."""
+        if not to_host:
+            self._check(self.lib.vl_replicate_infectants(self.ptr, None, 0))
+            return None
+        if out is None:
+            out = np.zeros(self.population_len(), dtype=np.uint64)
+        self._check(self.lib.vl_replicate_infectants(self.ptr, _p(out, C.c_uint64), out.size))
+        return out
+
+    def target_size(self, offspring=None) -> float:
+        ptr, n, _keep = self._offspring_args(offspring)
+        out = C.c_double()
+        self._check(self.lib.vl_target_size(self.ptr, ptr, n, C.byref(out)))
+        return float(out.value)
+
+    def sample_indices(self, offspring, amount: int) -> np.ndarray:
+        ptr, n, _keep = self._offspring_args(offspring)
+        if offspring is not None and n == 0:
+            return np.zeros(0, dtype=np.uint64)
+        out = np.zeros(max(1, amount), dtype=np.uint64)
+        self._check(self.lib.vl_sample_indices(self.ptr, ptr, n, amount, _p(out, C.c_uint64)))
+        return out[:amount]
+
+    def subsample_population(self, offspring, factor: float) -> GpuPopulation:
+        ptr, n, _keep = self._offspring_args(offspring)
+        pop = _vp()
+        self._check(self.lib.vl_subsample_population(self.ptr, ptr, n, factor, C.byref(pop)))
+        return GpuPopulation(pop, self)
+
+    def select(self, indices) -> GpuPopulation:
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        pop = _vp()
+        self._check(self.lib.vl_select(self.ptr, _p(idx, C.c_uint64), idx.size, C.byref(pop)))
+        return GpuPopulation(pop, self)
+
+    def set_population(self, parts):
+        """set_population(Population::from_iter(parts)); consumes the parts."""
+        if isinstance(parts, GpuPopulation):
+            parts = [parts]
+        arr = (_vp * max(1, len(parts)))(*[p.ptr for p in parts])
+        rc = self.lib.vl_set_population(self.ptr, arr, len(parts))
+        for p in parts:
+            p.ptr = None
+        self._check(rc)
+
+    def next_generation(self):
+        self._check(self.lib.vl_next_generation(self.ptr))
+
+    # ------------------------------------------------------------------ fused loops
+    def run(self, n_generations: int):
+        self._check(self.lib.vl_run(self.ptr, n_generations))
+
+    def synchronize(self):
+        self._check(self.lib.vl_synchronize(self.ptr))
+
+    def timer_start(self):
+        self._check(self.lib.vl_timer_start(self.ptr))
+
+    def timer_stop(self) -> float:
+        """Device milliseconds since timer_start (CUDA events on this handle's stream); synchronises."""
+        ms = C.c_double()
+        self._check(self.lib.vl_timer_stop(self.ptr, C.byref(ms)))
+        return float(ms.value)
+
+    def profile(self, enable: bool):
+        self._check(self.lib.vl_profile(self.ptr, int(enable)))
+
+    def profile_report(self) -> dict:
+        """{kernel: (launches, total_ms)} of the launches since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.vl_profile_report(self.ptr, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
+
+    def infectant_generations(self, reset: bool = False) -> int:
+        out = C.c_uint64()
+        self._check(self.lib.vl_infectant_generations(self.ptr, C.byref(out), int(reset)))
+        return int(out.value)
+
+    # ------------------------------------------------------------------ replay hooks
+    def replay_infections(self, infections):
+        inf = np.ascontiguousarray(infections, dtype=np.int64)
+        self._check(self.lib.vl_replay_infections(self.ptr, _p(inf, C.c_int64), inf.size))
+
+    def replay_mutations(self, offsets, sites, bases):
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        s = np.ascontiguousarray(sites, dtype=np.uint32)
+        b = np.ascontiguousarray(bases, dtype=np.uint8)
+        self._check(self.lib.vl_replay_mutations(self.ptr, _p(off, C.c_uint64), off.size - 1, _p(s, C.c_uint32), _p(b, C.c_uint8)))
+
+    def replay_recombinations(self, host, i, j, s0, s1, which):
+        host = np.ascontiguousarray(host, dtype=np.uint64)
+        i, j, s0, s1 = (np.ascontiguousarray(a, dtype=np.uint32) for a in (i, j, s0, s1))
+        which = np.ascontiguousarray(which, dtype=np.uint8)
+        self._check(self.lib.vl_replay_recombinations(self.ptr, host.size, _p(host, C.c_uint64), _p(i, C.c_uint32),
+                                                      _p(j, C.c_uint32), _p(s0, C.c_uint32), _p(s1, C.c_uint32),
+                                                      _p(which, C.c_uint8)))
+
+    def replay_offspring(self, offspring):
+        off = np.ascontiguousarray(offspring, dtype=np.uint64)
+        self._check(self.lib.vl_replay_offspring(self.ptr, _p(off, C.c_uint64), off.size))
+
+    # ------------------------------------------------------------------ inspection / export
+    def get_infections(self) -> np.ndarray:
+        out = np.zeros(self.population_len(), dtype=np.int64)
+        self._check(self.lib.vl_get_infections(self.ptr, _p(out, C.c_int64), out.size))
+        return out
+
+    def get_host_map(self):
+        H = int(self.parameters.host_population_size)
+        offsets = np.zeros(H + 1, dtype=np.uint64)
+        hosts = np.zeros(max(1, self.population_len()), dtype=np.uint64)
+        n = C.c_uint64()
+        self._check(self.lib.vl_get_host_map(self.ptr, _p(offsets, C.c_uint64), _p(hosts, C.c_uint64), C.byref(n)))
+        return offsets, hosts[:int(n.value)]
+
+    def get_replication_terms(self):
+        n = self.population_len()
+        f, s, l = (np.zeros(n, dtype=np.float64) for _ in range(3))
+        self._check(self.lib.vl_get_replication_terms(self.ptr, _p(f, C.c_double), _p(s, C.c_double), _p(l, C.c_double), n))
+        return f, s, l
+
+    def get_offspring_prefix(self) -> np.ndarray:
+        out = np.zeros(self.population_len(), dtype=np.uint64)
+        self._check(self.lib.vl_get_offspring_prefix(self.ptr, _p(out, C.c_uint64), out.size))
+        return out
+
+    def get_raw_fitness(self, spec: int = 0, which: int = 0) -> np.ndarray:
+        out = np.zeros(self.population_len(), dtype=np.float64)
+        self._check(self.lib.vl_get_raw_fitness(self.ptr, spec, which, _p(out, C.c_double), out.size))
+        return out
+
+    def export_mutations(self):
+        """(offsets[n+1], positions, bases): Haplotype::get_mutations of every infectant, sorted by position."""
+        n = self.population_len()
+        total = C.c_uint64()
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        self._check(self.lib.vl_export_mutations(self.ptr, _p(offsets, C.c_uint64), n, None, None, C.byref(total)))
+        t = int(total.value)
+        pos = np.zeros(max(1, t), dtype=np.uint32)
+        base = np.zeros(max(1, t), dtype=np.uint8)
+        if t:
+            self._check(self.lib.vl_export_mutations(self.ptr, _p(offsets, C.c_uint64), n, _p(pos, C.c_uint32),
+                                                     _p(base, C.c_uint8), C.byref(total)))
+        return offsets, pos[:t], base[:t]
+
+    def get_base(self, infectant: int, position: int) -> int:
+        out = C.c_uint8()
+        self._check(self.lib.vl_get_base(self.ptr, infectant, position, C.byref(out)))
+        return int(out.value)
+
+    def get_haplotype_ids(self) -> np.ndarray:
+        out = np.zeros(self.population_len(), dtype=np.uint32)
+        self._check(self.lib.vl_get_haplotype_ids(self.ptr, _p(out, C.c_uint32), out.size))
+        return out
+
+    def get_counters(self) -> dict:
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.vl_get_counters(self.ptr, _p(out, C.c_uint64)))
+        return {"haplotype_records": int(out[0]), "arena_words": int(out[1]), "gc_runs": int(out[2]),
+                "kernels_launched": int(out[3])}
+
+    def collect_garbage(self):
+        self._check(self.lib.vl_collect_garbage(self.ptr))
+
+    def unpack_device(self, image_ptr: int, nbytes: int) -> GpuPopulation:
+        pop = _vp()
+        self._check(self.lib.vl_pop_unpack_device(self.ptr, _vp(image_ptr), nbytes, C.byref(pop)))
+        return GpuPopulation(pop, self)
+
+
+def step(sims: Sequence[GpuSimulation], transfer: Optional[np.ndarray] = None, rule: int = 0):
+    """One generation over the compartments of this process as Runner::run drives it
+    (rule 0: parallel build src/runner.rs:382-422; rule 1: serial build :536-631)."""
+    lib = load_library()
+    C_ = len(sims)
+    T = np.ascontiguousarray(np.eye(C_) if transfer is None else np.asarray(transfer)[:C_, :C_], dtype=np.float64)
+    arr = (_vp * C_)(*[s.ptr for s in sims])
+    rc = lib.vl_step(arr, C_, _p(T, C.c_double), rule)
+    if rc != 0:
+        msg = (lib.vl_last_error(sims[0].ptr) or b"").decode()
+        raise (ReferencePanic if rc == abi.VL_ERR_REFERENCE_PANIC else VirolutionError)(rc, msg)
+
+
+def sampler_poisson(seed: int, lam: float, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.uint64)
+    rc = load_library().vl_test_poisson(seed, lam, n, _p(out, C.c_uint64))
+    if rc:
+        raise VirolutionError(rc, "vl_test_poisson failed")
+    return out
+
+
+def sampler_binomial(seed: int, trials: int, p: float, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.uint64)
+    rc = load_library().vl_test_binomial(seed, trials, p, n, _p(out, C.c_uint64))
+    if rc:
+        raise VirolutionError(rc, "vl_test_binomial failed")
+    return out
+
+
+def sampler_below(seed: int, bound: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.uint64)
+    rc = load_library().vl_test_below(seed, bound, n, _p(out, C.c_uint64))
+    if rc:
+        raise VirolutionError(rc, "vl_test_below failed")
+    return out
