@@ -115,8 +115,9 @@ typedef struct vl_config {
 } vl_config;
 
 enum {
-    VL_FLAG_ATOMIC_HOST_SUM = 1 /* sum per-host fitness with f64 atomics instead of the
-                                   reference-ordered CSR walk (not for replay) */
+    VL_FLAG_TREE_PLAN = 2 /* split the resampling draws over tiles with the conditional-binomial tree instead of
+                             Poissonisation (both exact; the tree is the rare-case fallback, this flag lets tests
+                             exercise it) */
 };
 
 /* ---- lifecycle -------------------------------------------------------- */

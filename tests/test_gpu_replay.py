@@ -60,26 +60,3 @@ def test_hill_utility_within_tolerance():
     for g in range(c["generations"]):
         helpers.replay_generation(gpu, helpers.oracle_generation(w), 1, rtol=1e-12)
     gpu.close()
-
-
-def test_replay_with_atomic_host_sums_within_tolerance():
-    # VL_FLAG_ATOMIC_HOST_SUM accumulates per-host sums in arrival order: same values up to f64 rounding
-    from virolution_b200.abi import VL_FLAG_ATOMIC_HOST_SUM
-    c = helpers.case("crowded")
-    w = helpers.make_oracle(c)
-    gpu = helpers.make_gpu(c, flags=VL_FLAG_ATOMIC_HOST_SUM)
-    for g in range(3):
-        log = helpers.oracle_generation(w)
-        gpu.increment_generation()
-        gpu.replay_infections(log["infections"])
-        gpu.infect()
-        gpu.replay_mutations(log["mut_offsets"], log["mut_sites"], log["mut_bases"])
-        gpu.mutate_infectants()
-        gpu.replay_offspring(log["offspring"])
-        gpu.replicate_infectants()
-        f, s, l = gpu.get_replication_terms()
-        helpers.assert_f64_equal(f, log["fit"], "fitness")
-        helpers.assert_f64_equal(s, log["hsum"], "host sums", rtol=1e-12)
-        helpers.assert_f64_equal(l, log["lam"], "lambda", rtol=1e-12)
-        gpu.set_population(gpu.select(log["sample_idx"]))
-    gpu.close()

@@ -20,7 +20,7 @@ VL_ERR_CAPACITY = -4
 VL_ERR_REFERENCE_PANIC = -5
 VL_ERR_ARGUMENT = -6
 
-VL_FLAG_ATOMIC_HOST_SUM = 1
+VL_FLAG_TREE_PLAN = 2
 
 UTILITY_LINEAR, UTILITY_ALGEBRAIC, UTILITY_HILL = 0, 1, 2
 FITNESS_NONE, FITNESS_NEUTRAL, FITNESS_NONEPISTATIC, FITNESS_EPISTATIC = 0, 1, 2, 3

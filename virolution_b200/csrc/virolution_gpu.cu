@@ -60,7 +60,11 @@ struct vl_sim {
     uint64_t launches = 0;
     uint64_t n_known = 0; bool n_valid = false;   // host knowledge of the population size
     uint64_t n_bound = 0;                         // upper bound of the population size (launch geometry)
-    bool csr_valid = false;
+    bool csr_valid = false;       // rec/offsets hold the host map of the current population
+    bool slices_ordered = false;  // ... and every slice is in the reference's descending order
+    bool layout_valid = false;    // rec/offspring/tile_sum describe an offspring map (host map or identity layout)
+    bool mutcounts_ready = false; // the fused infect pass already filled the mutation worklist
+    uint32_t plan_smem_tiles = 0;
     uint32_t salt = 0;        // distinguishes the sampling streams of one generation
     uint32_t gens_since_gc = 0, gc_period = 1;
     int next_slot = 8;
@@ -195,37 +199,35 @@ static int launch_scan(vl_sim *sim, const uint32_t *in, OutT *out, const uint64_
 }
 
 // ---------------------------------------------------------------------------------------------- buffers
+static void free_population_buffers(vl_sim *sim) {
+    DevState &h = sim->h;
+    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.rec, h.heavy_hosts, h.mut_list, h.lam, h.offspring,
+                    h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_node, h.tile_base, sim->stage64};
+    for (void *p : olds) if (p) cudaFree(p);
+}
 static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     DevState &h = sim->h;
-    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.hosts, h.heavy_hosts, h.mut_list, h.mut_count, h.fit, h.offspring,
-                    h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_base, sim->stage64};
-    for (void *p : olds) if (p) cudaFree(p);
+    free_population_buffers(sim);
     const uint64_t nt = (cap + RESAMPLE_TILE - 1) / RESAMPLE_TILE + 1;
     uint64_t P = 1;
     while (P < nt) P <<= 1;
-    TRY(dev_alloc(sim, &h.hap_id, cap, false));
-    TRY(dev_alloc(sim, &h.hap_id_next, cap, false));
-    TRY(dev_alloc(sim, &h.host_id, cap, false));
-    TRY(dev_alloc(sim, &h.rank, cap, false));
-    TRY(dev_alloc(sim, &h.hosts, cap, false));
+    TRY(dev_alloc(sim, &h.hap_id, cap + 4, false));
+    TRY(dev_alloc(sim, &h.hap_id_next, cap + 4, false));
+    TRY(dev_alloc(sim, &h.host_id, cap + 4, false));
+    TRY(dev_alloc(sim, &h.rank, cap + 4, false));
+    TRY(dev_alloc(sim, &h.rec, cap + 4, false));
     TRY(dev_alloc(sim, &h.heavy_hosts, cap / THREAD_TIER + 1, false));
-    TRY(dev_alloc(sim, &h.mut_list, cap, false));
-    TRY(dev_alloc(sim, &h.mut_count, cap, false));
-    TRY(dev_alloc(sim, &h.fit, cap, false));
-    TRY(dev_alloc(sim, &h.offspring, cap, false));
+    TRY(dev_alloc(sim, &h.mut_list, cap + 4, false));
+    TRY(dev_alloc(sim, &h.lam, cap + 4, false));
+    TRY(dev_alloc(sim, &h.offspring, cap + 4, false));
     TRY(dev_alloc(sim, &h.tile_sum, nt, false));
     TRY(dev_alloc(sim, &h.tile_tree, 2 * P, false));
-    TRY(dev_alloc(sim, &h.tile_cnt, 2 * P, false));
+    TRY(dev_alloc(sim, &h.tile_cnt, nt, false));
+    TRY(dev_alloc(sim, &h.tile_node, 2 * P, false));
     TRY(dev_alloc(sim, &h.tile_base, nt, false));
-    TRY(dev_alloc(sim, &sim->stage64, cap, false));
+    TRY(dev_alloc(sim, &sim->stage64, cap + 4, false));
     h.cap_inf = cap;
     return VL_OK;
-}
-static void free_population_buffers(vl_sim *sim) {
-    DevState &h = sim->h;
-    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.hosts, h.heavy_hosts, h.mut_list, h.mut_count, h.fit, h.offspring,
-                    h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_base, sim->stage64};
-    for (void *p : olds) if (p) cudaFree(p);
 }
 // push the host mirror's population pointers/capacity into the device state
 static int push_population_pointers(vl_sim *sim) {
@@ -233,23 +235,26 @@ static int push_population_pointers(vl_sim *sim) {
     DevState tmp;
     CU(sim, cudaMemcpy(&tmp, sim->d, sizeof(DevState), cudaMemcpyDeviceToHost));
     const DevState &h = sim->h;
-    tmp.hap_id = h.hap_id; tmp.hap_id_next = h.hap_id_next; tmp.host_id = h.host_id; tmp.rank = h.rank; tmp.hosts = h.hosts;
-    tmp.heavy_hosts = h.heavy_hosts; tmp.mut_list = h.mut_list; tmp.mut_count = h.mut_count; tmp.fit = h.fit; tmp.offspring = h.offspring;
-    tmp.tile_sum = h.tile_sum; tmp.tile_tree = h.tile_tree; tmp.tile_cnt = h.tile_cnt; tmp.tile_base = h.tile_base;
-    tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.hsum = h.hsum; tmp.H = h.H;
+    tmp.hap_id = h.hap_id; tmp.hap_id_next = h.hap_id_next; tmp.host_id = h.host_id; tmp.rank = h.rank; tmp.rec = h.rec;
+    tmp.heavy_hosts = h.heavy_hosts; tmp.mut_list = h.mut_list; tmp.lam = h.lam; tmp.offspring = h.offspring;
+    tmp.tile_sum = h.tile_sum; tmp.tile_tree = h.tile_tree; tmp.tile_cnt = h.tile_cnt; tmp.tile_node = h.tile_node; tmp.tile_base = h.tile_base;
+    tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.H = h.H; tmp.fast_infect = h.fast_infect;
     CU(sim, cudaMemcpy(sim->d, &tmp, sizeof(DevState), cudaMemcpyHostToDevice));
     return VL_OK;
 }
 static int alloc_host_buffers(vl_sim *sim, uint64_t H) {
     DevState &h = sim->h;
     if (h.offsets) cudaFree(h.offsets);
-    if (h.hsum) cudaFree(h.hsum);
     if (sim->count) cudaFree(sim->count);
-    TRY(dev_alloc(sim, &h.offsets, H + 2, false));
-    TRY(dev_alloc(sim, &h.hsum, H + 1, false));
-    TRY(dev_alloc(sim, &sim->count, H + 2, false));
+    TRY(dev_alloc(sim, &h.offsets, H + 8, false));
+    TRY(dev_alloc(sim, &sim->count, H + 8, false));
     sim->cap_H = H;
     return VL_OK;
+}
+static void update_fast_infect(vl_sim *sim) {
+    DevState &h = sim->h;
+    bool fast = h.n_specs == 1 && h.specs[0].lo == 0 && h.specs[0].hi >= h.H && h.specs[0].infect < 0 && h.n_hits == 1 && h.H > 0;
+    h.fast_infect = fast ? 1u : 0u;
 }
 
 static int add_provider(vl_sim *sim, const vl_fitness *f, uint64_t L, int *index_out) {
@@ -316,7 +321,6 @@ static void destroy_sim(vl_sim *sim) {
     }
     free_population_buffers(sim);
     if (sim->h.offsets) cudaFree(sim->h.offsets);
-    if (sim->h.hsum) cudaFree(sim->h.hsum);
     if (sim->count) cudaFree(sim->count);
     for (void *p : sim->fixed_allocs) cudaFree(p);
     if (sim->scan_work) cudaFree(sim->scan_work);
@@ -394,7 +398,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
         size_t free_b = 0, total_b = 0;
         CCU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t P = std::max<uint32_t>(h.n_providers, 1);
-        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 64 + ch * (52 + 16 * P) + ca * 8; };
+        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 72 + ch * (52 + 16 * P) + ca * 8; };
         if (!cfg->capacity_haplotypes || !cfg->capacity_arena_words) {
             for (int it = 0; it < 64 && need(cap_hap, cap_arena) > (uint64_t)(0.7 * (double)free_b); it++) {
                 if (!cfg->capacity_arena_words && cap_arena > (1ull << 20)) cap_arena = cap_arena * 3 / 4;
@@ -408,6 +412,11 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     }
     h.cap_hap = cap_hap;
     h.cap_arena = cap_arena;
+    update_fast_infect(sim);
+    h.binv = make_binv(L, par.mutation_rate);
+    CCU(cudaFuncSetAttribute(k_plan_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CCU(cudaFuncSetAttribute(k_host_fitness_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 8));
+    sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
     h.gc_arena_threshold = cap_arena / 2;
     CTRY(alloc_population_buffers(sim, cap_inf));
@@ -498,6 +507,8 @@ VL_API int vl_set_parameters(vl_sim *sim, const vl_parameters *p) {
     TRY(write_field(sim, FIELD_OFF(dilution), p->dilution));
     TRY(write_field(sim, FIELD_OFF(max_population), (uint64_t)p->max_population));
     h.n_hits = p->n_hits; h.dilution = p->dilution; h.max_population = p->max_population;
+    update_fast_infect(sim);
+    TRY(write_field(sim, FIELD_OFF(fast_infect), h.fast_infect));
     sim->csr_valid = false;
     return VL_OK;
 }
@@ -527,27 +538,51 @@ VL_API int vl_set_population_wildtype(vl_sim *sim, uint64_t n) {
     sim->n_bound = n;
     sim->n_valid = true;
     sim->csr_valid = false;
+    sim->slices_ordered = false;
+    sim->layout_valid = false;
+    sim->mutcounts_ready = false;
     return VL_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- phases
-static bool need_csr(const vl_sim *sim) {
-    return !(sim->flags & VL_FLAG_ATOMIC_HOST_SUM) || sim->h.host_recombination_rate > 0.0 || sim->has_rp_rec;
+static int zero_field32(vl_sim *sim, size_t off) {
+    CU(sim, cudaMemsetAsync((char *)sim->d + off, 0, 4, sim->stream));
+    return VL_OK;
+}
+// descending infectant order inside every slice (the reference's back-fill order); part of k_host_fitness in
+// the replicate phase, run on its own when recombination or an inspection call needs it earlier
+static int ensure_ordered_slices(vl_sim *sim) {
+    if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no host map: call vl_infect first");
+    if (sim->slices_ordered) return VL_OK;
+    TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
+    LAUNCH(sim, k_host_fitness, grid_for(sim, sim->h.H), TPB, 0, sim->d, 1);
+    LAUNCH(sim, k_host_fitness_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 8, sim->d, 1);
+    sim->slices_ordered = true;
+    return VL_OK;
 }
 static int enqueue_infect(vl_sim *sim) {
     const DevState &h = sim->h;
-    const bool csr = need_csr(sim);
+    const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec;
+    const bool fuse = !replay && h.binv.ok;
+    const bool fast = h.fast_infect != 0;
     LAUNCH(sim, k_begin_phase, 1, 1, 0, sim->d);
-    if (csr) CU(sim, cudaMemsetAsync(sim->count, 0, (h.H + 2) * 4, sim->stream));
-    LAUNCH(sim, k_infect, grid_for(sim, sim->n_bound), TPB, 0, sim->d, sim->count, sim->has_rp_inf ? sim->rp_inf : nullptr, csr ? 1 : 0);
+    CU(sim, cudaMemsetAsync(sim->count, 0, (h.H + 2) * 4, sim->stream));
+    const unsigned g = grid_for(sim, (sim->n_bound + INFECT_ITEMS - 1) / INFECT_ITEMS);
+    const int64_t *rp = sim->has_rp_inf ? sim->rp_inf : nullptr;
+    if (fuse && fast) LAUNCH(sim, (k_infect<true, true>), g, TPB, 0, sim->d, sim->count, (const int64_t *)nullptr);
+    else if (fuse) LAUNCH(sim, (k_infect<true, false>), g, TPB, 0, sim->d, sim->count, (const int64_t *)nullptr);
+    else if (fast) LAUNCH(sim, (k_infect<false, true>), g, TPB, 0, sim->d, sim->count, rp);
+    else LAUNCH(sim, (k_infect<false, false>), g, TPB, 0, sim->d, sim->count, rp);
     sim->has_rp_inf = false;
-    if (csr) {
-        TRY((launch_scan<uint32_t, true>(sim, sim->count, h.offsets, (const uint64_t *)((const char *)sim->d + FIELD_OFF(H)), 0, h.H, nullptr, 1, nullptr)));
-        LAUNCH(sim, k_scatter_hosts, grid_for(sim, sim->n_bound), TPB, 0, sim->d);
-        LAUNCH(sim, k_sort_slices, grid_for(sim, h.H), TPB, 0, sim->d);
-        LAUNCH(sim, k_sort_slices_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 4, sim->d);
-    }
-    sim->csr_valid = csr;
+    sim->mutcounts_ready = fuse;
+    // counting sort by host: exclusive scan of the histogram, then every record moves to its CSR position
+    TRY((launch_scan<uint32_t, true>(sim, sim->count, h.offsets, (const uint64_t *)((const char *)sim->d + FIELD_OFF(H)), 0, h.H,
+                                     (uint64_t *)((char *)sim->d + FIELD_OFF(n_sorted)), 1, nullptr)));
+    LAUNCH(sim, k_scatter, g, TPB, 0, sim->d);
+    sim->csr_valid = true;
+    sim->slices_ordered = false;
+    sim->layout_valid = false;
+    if (h.host_recombination_rate > 0.0 || sim->has_rp_rec) TRY(ensure_ordered_slices(sim));
     return VL_OK;
 }
 static int enqueue_mutate(vl_sim *sim) {
@@ -557,11 +592,11 @@ static int enqueue_mutate(vl_sim *sim) {
     ReplayMut rm{sim->rp_mut_off, sim->rp_mut_sites, sim->rp_mut_bases};
     if (replay) {
         if (sim->has_rp_rec && sim->rp_rec_n > 0) {
-            if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "recombination replay needs the host map");
+            TRY(ensure_ordered_slices(sim));
             LAUNCH(sim, k_recombine, grid_for(sim, h.H), TPB, 0, sim->d, rr, 1);
         }
     } else if (h.host_recombination_rate > 0.0) {
-        if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "recombination needs the host map: call vl_infect first");
+        TRY(ensure_ordered_slices(sim));
         LAUNCH(sim, k_recombine, grid_for(sim, h.H), TPB, 0, sim->d, rr, 0);
     }
     if (replay && !sim->has_rp_mut) {
@@ -569,31 +604,41 @@ static int enqueue_mutate(vl_sim *sim) {
         sim->has_rp_rec = false;
         return VL_OK;
     }
-    LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
+    if (sim->has_rp_mut || !sim->mutcounts_ready) {
+        if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "mutate needs the infections: call vl_infect first");
+        TRY(zero_field32(sim, FIELD_OFF(n_mut_list)));
+        LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
+    }
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : 0);
+    sim->mutcounts_ready = false;
     sim->has_rp_mut = false;
     sim->has_rp_rec = false;
     return VL_OK;
 }
 static int enqueue_replicate(vl_sim *sim) {
     const DevState &h = sim->h;
-    const bool atomic = (sim->flags & VL_FLAG_ATOMIC_HOST_SUM) != 0;
-    if (atomic) CU(sim, cudaMemsetAsync(h.hsum, 0, (h.H + 1) * 8, sim->stream));
-    else if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "replicate needs the host map: call vl_infect first");
-    LAUNCH(sim, k_fitness, grid_for(sim, sim->n_bound), TPB, 0, sim->d, atomic ? 1 : 0);
-    if (!atomic) {
-        LAUNCH(sim, k_host_sum, grid_for(sim, h.H), TPB, 0, sim->d);
-        LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, 0, sim->d);
-    }
-    LAUNCH(sim, k_offspring, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, sim->has_rp_off ? sim->rp_off : nullptr);
+    if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "replicate needs the host map: call vl_infect first");
+    TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
+    LAUNCH(sim, k_host_fitness, grid_for(sim, h.H), TPB, 0, sim->d, 0);
+    LAUNCH(sim, k_host_fitness_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 8, sim->d, 0);
+    sim->slices_ordered = true;
+    LAUNCH(sim, k_offspring, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, (const uint64_t *)(sim->has_rp_off ? sim->rp_off : nullptr));
     sim->has_rp_off = false;
+    sim->layout_valid = true;
+    return VL_OK;
+}
+static int launch_plan(vl_sim *sim, double factor, int use_amount, uint64_t amount, int set_next, uint32_t salt) {
+    const uint64_t nt_bound = (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE + 1;
+    const uint32_t smem_tiles = (uint32_t)std::min<uint64_t>(nt_bound, sim->plan_smem_tiles);
+    const int force_tree = (sim->flags & VL_FLAG_TREE_PLAN) ? 1 : 0;
+    LAUNCH(sim, k_plan_resample, 1, PLAN_THREADS, smem_tiles * 8, sim->d, factor, use_amount, amount, set_next, salt, force_tree, smem_tiles);
     return VL_OK;
 }
 // Population::sample as plan + tile-local draws.  dst == nullptr writes the population being assembled.
 static int enqueue_resample(vl_sim *sim, double factor, int use_amount, uint64_t amount, uint32_t *dst, uint64_t *dst64, int mode, int set_next) {
-    const DevState &h = sim->h;
+    if (!sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one");
     const uint32_t salt = ++sim->salt;
-    LAUNCH(sim, k_plan_resample, 1, PLAN_THREADS, 0, sim->d, factor, use_amount, amount, set_next, salt);
+    TRY(launch_plan(sim, factor, use_amount, amount, set_next, salt));
     LAUNCH(sim, k_resample, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, dst, dst64, mode, salt);
     return VL_OK;
 }
@@ -633,13 +678,19 @@ VL_API int vl_mutate_infectants(vl_sim *sim) {
     return enqueue_mutate(sim);
 }
 
+// An offspring map handed in by the host is aligned with the population order (Vec<usize>, one entry per
+// infectant): it is laid out as identity records so that the same plan/draw kernels consume it.
 static int upload_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n) {
     uint64_t cur = 0;
     TRY(population_len(sim, &cur));
     if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "offspring map has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
     if (n) CU(sim, cudaMemcpyAsync(sim->stage64, offspring, n * 8, cudaMemcpyHostToDevice, sim->stream));
-    LAUNCH(sim, k_u64_to_u32, grid_for(sim, n), TPB, 0, sim->d, sim->stage64, sim->h.offspring, n);
+    LAUNCH(sim, k_identity_records, grid_for(sim, n), TPB, 0, sim->d);
+    LAUNCH(sim, k_u64_to_u32, grid_for(sim, n), TPB, 0, sim->d, (const uint64_t *)sim->stage64, sim->h.offspring, n);
     LAUNCH(sim, k_tile_sums, grid_tiles(sim, n, RESAMPLE_TILE), TPB, 0, sim->d);
+    sim->csr_valid = false;
+    sim->slices_ordered = false;
+    sim->layout_valid = true;
     return VL_OK;
 }
 
@@ -650,7 +701,8 @@ VL_API int vl_replicate_infectants(vl_sim *sim, uint64_t *offspring_out, uint64_
         uint64_t cur = 0;
         TRY(population_len(sim, &cur));
         if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "offspring buffer has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
-        LAUNCH(sim, k_u32_to_u64, grid_for(sim, n), TPB, 0, sim->h.offspring, sim->stage64, n);
+        if (n) CU(sim, cudaMemsetAsync(sim->stage64, 0, n * 8, sim->stream));  // uninfected infectants: 0 offspring
+        LAUNCH(sim, k_unsort_offspring, grid_for(sim, n), TPB, 0, sim->d, sim->stage64);
         if (n) CU(sim, cudaMemcpyAsync(offspring_out, sim->stage64, n * 8, cudaMemcpyDeviceToHost, sim->stream));
         CU(sim, cudaStreamSynchronize(sim->stream));
         return check_device_error(sim);
@@ -661,6 +713,7 @@ VL_API int vl_replicate_infectants(vl_sim *sim, uint64_t *offspring_out, uint64_
 VL_API int vl_target_size(vl_sim *sim, const uint64_t *offspring, uint64_t n, double *out) {
     ENTER(sim);
     if (offspring) TRY(upload_offspring(sim, offspring, n));
+    if (!sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device");
     LAUNCH(sim, k_target_size, 1, TPB, 0, sim->d);
     TRY(read_field(sim, FIELD_OFF(target_size), out));
     return check_device_error(sim);
@@ -706,8 +759,9 @@ static int enqueue_subsample(vl_sim *sim, double factor, int use_amount, uint64_
     if (bound > 4.0e9) return fail(sim, VL_ERR_CAPACITY, "subsample bound too large");
     vl_pop *p = new_pop(sim, (uint64_t)bound + 1);
     if (!p) return fail(sim, VL_ERR_CUDA, "out of device memory for a detached population of %.0f", bound);
+    if (!sim->layout_valid) { drop_pop(p); return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one"); }
     const uint32_t salt = ++sim->salt;
-    LAUNCH(sim, k_plan_resample, 1, PLAN_THREADS, 0, sim->d, factor, use_amount, amount, 0, salt);
+    TRY(launch_plan(sim, factor, use_amount, amount, 0, salt));
     LAUNCH(sim, k_resample, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, p->ids, (uint64_t *)nullptr, 0, salt);
     int slot = sim->next_slot++;
     if (sim->next_slot >= PIN_SLOTS) sim->next_slot = 8;
@@ -879,6 +933,9 @@ VL_API int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts
     sim->n_bound = total;
     sim->n_valid = true;
     sim->csr_valid = false;
+    sim->slices_ordered = false;
+    sim->layout_valid = false;
+    sim->mutcounts_ready = false;
     TRY(check_device_error(sim));
     return maybe_gc(sim);
 }
@@ -896,6 +953,8 @@ static int enqueue_generation(vl_sim *sim) {
     sim->n_valid = false;
     sim->n_bound = std::min<uint64_t>(sim->h.cap_inf, sim->h.max_population);
     sim->csr_valid = false;
+    sim->slices_ordered = false;
+    sim->layout_valid = false;
     return maybe_gc(sim);
 }
 VL_API int vl_next_generation(vl_sim *sim) {
@@ -1082,26 +1141,30 @@ VL_API int vl_get_infections(vl_sim *sim, int64_t *out, uint64_t n) {
 }
 VL_API int vl_get_host_map(vl_sim *sim, uint64_t *offsets_out, uint64_t *hosts_out, uint64_t *n_infected_out) {
     ENTER(sim);
-    if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no host map: vl_infect has not run (or ran with VL_FLAG_ATOMIC_HOST_SUM)");
+    TRY(ensure_ordered_slices(sim));
     std::vector<uint32_t> off, hosts;
     TRY(download(sim, off, (const uint32_t *)sim->h.offsets, sim->h.H + 1));
     const uint64_t ninf = off[sim->h.H];
-    TRY(download(sim, hosts, (const uint32_t *)sim->h.hosts, ninf));
+    uint32_t *tmp = sim->h.rank;  // per-infectant scratch, free once the records are scattered
+    LAUNCH(sim, k_extract_hosts, grid_for(sim, ninf), TPB, 0, sim->d, tmp);
+    TRY(download(sim, hosts, (const uint32_t *)tmp, ninf));
     if (offsets_out) for (uint64_t k = 0; k <= sim->h.H; k++) offsets_out[k] = off[k];
     if (hosts_out) for (uint64_t k = 0; k < ninf; k++) hosts_out[k] = hosts[k];
     if (n_infected_out) *n_infected_out = ninf;
-    return VL_OK;
+    return check_device_error(sim);
 }
 VL_API int vl_get_replication_terms(vl_sim *sim, double *fitness_out, double *host_sum_out, double *lambda_out, uint64_t n) {
     ENTER(sim);
     TRY(expect_len(sim, n));
+    TRY(ensure_ordered_slices(sim));
     double *tmp = nullptr;
-    CU(sim, cudaMalloc((void **)&tmp, std::max<uint64_t>(2 * n, 1) * 8));
-    LAUNCH(sim, k_replication_terms, grid_for(sim, n), TPB, 0, sim->d, tmp, tmp + n);
+    CU(sim, cudaMalloc((void **)&tmp, std::max<uint64_t>(3 * n, 1) * 8));
+    CU(sim, cudaMemsetAsync(tmp, 0xFF, std::max<uint64_t>(3 * n, 1) * 8, sim->stream));  // NaN where not infected
+    LAUNCH(sim, k_replication_terms, grid_for(sim, sim->h.H), TPB, 0, sim->d, tmp, tmp + n, tmp + 2 * n);
     if (n) {
-        if (fitness_out) CU(sim, cudaMemcpyAsync(fitness_out, sim->h.fit, n * 8, cudaMemcpyDeviceToHost, sim->stream));
-        if (host_sum_out) CU(sim, cudaMemcpyAsync(host_sum_out, tmp, n * 8, cudaMemcpyDeviceToHost, sim->stream));
-        if (lambda_out) CU(sim, cudaMemcpyAsync(lambda_out, tmp + n, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+        if (fitness_out) CU(sim, cudaMemcpyAsync(fitness_out, tmp, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+        if (host_sum_out) CU(sim, cudaMemcpyAsync(host_sum_out, tmp + n, n * 8, cudaMemcpyDeviceToHost, sim->stream));
+        if (lambda_out) CU(sim, cudaMemcpyAsync(lambda_out, tmp + 2 * n, n * 8, cudaMemcpyDeviceToHost, sim->stream));
     }
     CU(sim, cudaStreamSynchronize(sim->stream));
     cudaFree(tmp);
@@ -1110,8 +1173,12 @@ VL_API int vl_get_replication_terms(vl_sim *sim, double *fitness_out, double *ho
 VL_API int vl_get_offspring_prefix(vl_sim *sim, uint64_t *prefix_out, uint64_t n) {
     ENTER(sim);
     TRY(expect_len(sim, n));
-    // inclusive scan of the device-resident offspring map (the CDF Population::sample draws from)
-    TRY((launch_scan<uint64_t, false>(sim, sim->h.offspring, sim->stage64, nullptr, n, n, nullptr, 0, nullptr)));
+    if (!sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device");
+    // inclusive scan of the offspring map in population order (the CDF Population::sample draws from)
+    uint32_t *tmp = sim->h.rank;
+    if (n) CU(sim, cudaMemsetAsync(tmp, 0, n * 4, sim->stream));
+    LAUNCH(sim, k_unsort_offspring32, grid_for(sim, n), TPB, 0, sim->d, tmp);
+    TRY((launch_scan<uint64_t, false>(sim, tmp, sim->stage64, nullptr, n, n, nullptr, 0, nullptr)));
     if (n) CU(sim, cudaMemcpyAsync(prefix_out, sim->stage64, n * 8, cudaMemcpyDeviceToHost, sim->stream));
     CU(sim, cudaStreamSynchronize(sim->stream));
     return VL_OK;
@@ -1131,7 +1198,7 @@ VL_API int vl_get_raw_fitness(vl_sim *sim, uint32_t spec, int which, double *out
 VL_API int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, uint32_t *positions_out, uint8_t *bases_out, uint64_t *n_entries) {
     ENTER(sim);
     TRY(expect_len(sim, n));
-    uint32_t *cnt = sim->h.rank;  // per-infectant scratch, free between phases
+    uint32_t *cnt = (uint32_t *)sim->h.mut_list;  // per-infectant scratch, free outside the mutate phase
     LAUNCH(sim, k_export_count, grid_for(sim, n), TPB, 0, sim->d, cnt);
     TRY((launch_scan<uint64_t, true>(sim, cnt, sim->stage64, nullptr, n, n, sim->gc_totals + 6, 0, nullptr)));
     CU(sim, cudaMemcpyAsync(sim->pin, sim->gc_totals + 6, 8, cudaMemcpyDeviceToHost, sim->stream));
@@ -1251,7 +1318,7 @@ static int run_sampler(int which, uint64_t seed, uint64_t a, double b, uint64_t 
     if (cudaMalloc((void **)&dev, std::max<uint64_t>(n, 1) * 8) != cudaSuccess) return fail(nullptr, VL_ERR_CUDA, "no CUDA device / out of memory");
     unsigned g = (unsigned)std::min<uint64_t>((n + 255) / 256 + 1, 4096);
     if (which == 0) k_test_poisson<<<g, 256>>>(seed, b, n, dev);
-    else if (which == 1) k_test_binomial<<<g, 256>>>(seed, a, b, n, dev);
+    else if (which == 1) k_test_binomial<<<g, 256>>>(seed, a, b, n, dev, make_binv(a, b));
     else k_test_below<<<g, 256>>>(seed, a, n, dev);
     cudaError_t e = cudaMemcpy(out, dev, n * 8, cudaMemcpyDeviceToHost);
     cudaFree(dev);

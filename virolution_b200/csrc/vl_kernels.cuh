@@ -1,17 +1,26 @@
 // vl_kernels.cuh — the per-generation population update as sm_100a kernels.
 //
-// Kernel                reference rows it replaces
-//   k_infect            BasicSimulation::infect + BasicHost::infect          src/simulation.rs:365-387,56-65
-//   k_scatter_hosts,    HostMapBuffer::build (counting sort, back-fill)       src/core/hosts.rs:166-192
-//   k_sort_slices[_heavy]   ... including the descending in-host order its back-fill produces
-//   k_recombine         BasicHost::mutate, recombination part                 src/simulation.rs:68-90
-//   k_mutation_counts,  BasicHost::mutate, mutation part + create_descendant  src/simulation.rs:93-117,
-//   k_mutate                + FitnessProvider::get_fitness for every provider  src/core/haplotype.rs:241-260
-//   k_fitness,k_host_sum[_heavy],k_offspring   BasicHost::replicate           src/simulation.rs:120-154,430-485
-//   k_plan_resample     target_size + sample size                             src/simulation.rs:491-527
-//   k_resample          Population::sample / sample_indices / select          src/core/population.rs:385-430
-//   k_gc_*              Rc/Arc drop of unreachable haplotypes                 src/references/sync.rs:107-115
-// All kernels are grid-stride over device-resident sizes (DevState::n etc.), so a whole generation is
+// Kernel                  reference rows it replaces
+//   k_infect              BasicSimulation::infect + BasicHost::infect            src/simulation.rs:365-387,56-65
+//                         (+ the Binomial(L, mu) mutation count of BasicHost::mutate, :94-95, fused: the count
+//                         depends only on (seed, generation, infectant), not on the phase that draws it)
+//   scan, k_scatter       HostMapBuffer::build (counting sort, back-fill)         src/core/hosts.rs:166-192
+//   k_host_fitness[_heavy]  ... the descending in-host order its back-fill produces, then
+//                         BasicHost::replicate's fitness, per-host sum and lambda  src/simulation.rs:120-147
+//   k_recombine           BasicHost::mutate, recombination part                   src/simulation.rs:68-90
+//   k_mutation_counts,    BasicHost::mutate, mutation part + create_descendant    src/simulation.rs:93-117,
+//   k_mutate                + FitnessProvider::get_fitness for every provider     src/core/haplotype.rs:241-260
+//   k_offspring           Poisson(lambda) per infectant                           src/simulation.rs:148-152
+//   k_plan_resample       target_size + sample size + split of the draws          src/simulation.rs:491-527
+//   k_resample            Population::sample / sample_indices / select            src/core/population.rs:385-430
+//   k_gc_*                Rc/Arc drop of unreachable haplotypes                   src/references/sync.rs:107-115
+//
+// Data flow of one generation: the counting sort by host does not only produce indices (the reference's
+// `hosts` array) but moves a record (infectant index, haplotype id) to its CSR position.  From there on every
+// pass streams over host-contiguous records: per-host sums are segment sums over neighbours, lambda and the
+// offspring counts live at CSR positions, and the resample draws positions.  Random accesses per infectant are
+// the histogram atomic, the offsets gather + record scatter, and the gather of the haplotype's raw fitness.
+// All kernels are grid-stride over device-resident sizes (DevState::n, n_sorted, ...), so a whole generation is
 // enqueued without the host ever reading a size back.
 #pragma once
 #include "vl_rng.cuh"
@@ -22,7 +31,8 @@ namespace vl {
 
 constexpr int TPB = 256;
 constexpr uint32_t THREAD_TIER = 32;      // slices up to this length are handled by one thread
-constexpr uint32_t SMEM_SORT_MAX = 8192;  // slices up to this length are sorted in shared memory
+constexpr uint32_t SMEM_SORT_MAX = 4096;  // slices up to this length are sorted in shared memory (u64 keys)
+constexpr int INFECT_ITEMS = 4;           // infectants per thread and round in k_infect / k_scatter
 
 __device__ __forceinline__ void raise(DevState *st, uint32_t bit) { atomicOr(&st->error, bit); }
 
@@ -67,119 +77,165 @@ __global__ void k_begin_phase(DevState *st) {
 }
 
 // ------------------------------------------------------------------------------------------ infect
+// BasicHost::infect with n_hits > 1, several specs or an infective provider (src/simulation.rs:56-65):
+// sequential draws from block 1 onwards of the infectant's PH_INFECT stream.
+__device__ __noinline__ uint32_t infect_general(const DevState *st, uint64_t i, uint32_t gen) {
+    Philox g(st->seed, st->compartment, gen, PH_INFECT, i, 1);
+    const uint64_t H = st->H;
+    for (uint64_t hit = 0; hit < st->n_hits; hit++) {
+        uint64_t cand = g.below(H);
+        int s = find_spec(st, cand);
+        if (s < 0) continue;
+        double infectivity = 1.;
+        int pi = st->specs[s].infect;
+        if (pi >= 0) infectivity = utility_apply(st->prov[pi], st->h_raw[pi][st->hap_id[i]]);
+        if (g.u01() < infectivity) return (uint32_t)cand;
+    }
+    return NONE32;
+}
+
+// Mutation-count uniform of infectant i: words z,w of block 0 of its PH_INFECT stream (word x is the host draw
+// of the single-spec fast path).  The same definition is used by the fused and the stand-alone count kernel.
+__device__ __noinline__ uint32_t mutation_count_general(const DevState *st, uint64_t i, uint32_t gen) {
+    Philox g(st->seed, st->compartment, gen, PH_MUTCOUNT, i);  // large-mean regime: BTRS
+    return (uint32_t)binomial(g, st->L, st->host_mutation_rate);
+}
+__device__ __noinline__ uint32_t mutation_count_binv(const DevState *st, PhiloxKey key, uint64_t i, uint32_t gen, double u) {
+    return binv_draw(st->binv, u, key, i, gen, PH_MUTCOUNT);
+}
+// small-mean regime only (BinvConst::ok): what the fused infect kernel calls
+__device__ __forceinline__ uint32_t mutation_count_small(const DevState *st, PhiloxKey key, uint64_t i, uint32_t gen, uint4 b0) {
+    const double u = u01_from(b0.z, b0.w);
+    if (!(u > st->binv.qn)) return 0;  // the common case: no mutation
+    return mutation_count_binv(st, key, i, gen, u);
+}
+__device__ __forceinline__ uint32_t mutation_count(const DevState *st, PhiloxKey key, uint64_t i, uint32_t gen, uint4 b0) {
+    if (st->binv.ok) return mutation_count_small(st, key, i, gen, b0);
+    return mutation_count_general(st, i, gen);
+}
+
+// append (infectant, n_mut) for every item with n_mut > 0: one global atomic per CTA and round
+template <int ITEMS>
+__device__ __forceinline__ void worklist_append(DevState *st, const uint64_t (&idx)[ITEMS], const uint32_t (&nm)[ITEMS]) {
+    __shared__ uint32_t s_base;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int e = 0; e < ITEMS; e++) mine += nm[e] ? 1u : 0u;
+    uint32_t tot;
+    uint32_t off = block_excl_scan(mine, &tot);
+    if (threadIdx.x == 0 && tot) s_base = atomicAdd(&st->n_mut_list, tot);
+    __syncthreads();
+    if (mine) {
+        uint32_t o = s_base + off;
+#pragma unroll
+        for (int e = 0; e < ITEMS; e++)
+            if (nm[e]) st->mut_list[o++] = make_uint2((uint32_t)idx[e], nm[e]);
+    }
+    __syncthreads();
+}
+
 // replay_inf: recorded Option<usize> per infectant (-1 = None) or nullptr.
-__global__ void __launch_bounds__(TPB) k_infect(DevState *st, uint32_t *__restrict__ count, const int64_t *__restrict__ replay_inf,
-                                                int build_csr) {
+// FAST: one spec over [0,H), no infective provider, n_hits == 1 (DevState::fast_infect).  FUSE_MUT needs BinvConst::ok.
+template <bool FUSE_MUT, bool FAST>
+__global__ void __launch_bounds__(TPB) k_infect(DevState *st, uint32_t *__restrict__ count, const int64_t *__restrict__ replay_inf) {
     const uint64_t n = st->n;
     const uint64_t H = st->H;
+    const uint32_t H32 = (uint32_t)H;
     const uint32_t gen = st->generation;
-    const uint32_t *__restrict__ hap_id = st->hap_id;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
     uint32_t *__restrict__ host_id = st->host_id;
     uint32_t *__restrict__ rank = st->rank;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->infectant_generations += n;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t h = NONE32;
-        if (replay_inf) {
-            int64_t r = replay_inf[i];
-            if (r >= 0) {
-                if ((uint64_t)r < H) h = (uint32_t)r; else raise(st, DE_REPLAY);
+    const uint64_t span = (uint64_t)gridDim.x * blockDim.x * INFECT_ITEMS;
+    const uint64_t rounds = (n + span - 1) / span;
+    for (uint64_t r = 0; r < rounds; r++) {
+        const uint64_t i0 = r * span + ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * INFECT_ITEMS;
+        uint32_t h[INFECT_ITEMS], nm[INFECT_ITEMS], rk[INFECT_ITEMS];
+        uint64_t idx[INFECT_ITEMS];
+#pragma unroll
+        for (int e = 0; e < INFECT_ITEMS; e++) {
+            const uint64_t i = i0 + e;
+            idx[e] = i;
+            h[e] = NONE32;
+            nm[e] = 0;
+            rk[e] = 0;
+            if (i >= n) continue;
+            const uint4 b0 = philox_block(key, i, gen, PH_INFECT, 0);
+            if (replay_inf) {
+                int64_t v = replay_inf[i];
+                if (v >= 0) {
+                    if ((uint64_t)v < H) h[e] = (uint32_t)v; else raise(st, DE_REPLAY);
+                }
+            } else if (H > 0) {
+                if (FAST) {
+                    // Uniform(0, H): widening multiply; a draw in the biased zone (probability < H / 2^32) is
+                    // rejected exactly and redrawn from the following blocks of the stream
+                    uint64_t m = (uint64_t)b0.x * H32;
+                    if ((uint32_t)m < H32) {
+                        const uint32_t thr = (uint32_t)(-H32) % H32;
+                        for (uint32_t blk = 1; (uint32_t)m < thr; blk++) m = (uint64_t)philox_block(key, i, gen, PH_INFECT, blk).x * H32;
+                    }
+                    h[e] = (uint32_t)(m >> 32);
+                } else {
+                    h[e] = infect_general(st, i, gen);
+                }
             }
-        } else if (H > 0) {
-            Philox g(st->seed, st->compartment, gen, PH_INFECT, i);
-            for (uint64_t hit = 0; hit < st->n_hits; hit++) {
-                uint64_t cand = g.below(H);
-                int s = find_spec(st, cand);
-                if (s < 0) continue;
-                double infectivity = 1.;
-                int pi = st->specs[s].infect;
-                if (pi >= 0) infectivity = utility_apply(st->prov[pi], st->h_raw[pi][hap_id[i]]);
-                if (g.u01() < infectivity) { h = (uint32_t)cand; break; }
-            }
+            if (FUSE_MUT && h[e] != NONE32) nm[e] = mutation_count_small(st, key, i, gen, b0);
         }
-        host_id[i] = h;
-        if (build_csr && h != NONE32) rank[i] = atomicAdd(&count[h], 1u);
+#pragma unroll
+        for (int e = 0; e < INFECT_ITEMS; e++)
+            if (h[e] != NONE32) rk[e] = atomicAdd(&count[h[e]], 1u);
+        if (i0 + INFECT_ITEMS <= n) {
+            *reinterpret_cast<uint4 *>(host_id + i0) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(rank + i0) = make_uint4(rk[0], rk[1], rk[2], rk[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < INFECT_ITEMS; e++)
+                if (i0 + e < n) { host_id[i0 + e] = h[e]; rank[i0 + e] = rk[e]; }
+        }
+        if (FUSE_MUT) worklist_append<INFECT_ITEMS>(st, idx, nm);
     }
 }
 
-__global__ void __launch_bounds__(TPB) k_scatter_hosts(DevState *st) {
+// HostMapBuffer::build back-fill (src/core/hosts.rs:182-189): the record of infectant i goes to its host's slice
+__global__ void __launch_bounds__(TPB) k_scatter(DevState *st) {
     const uint64_t n = st->n;
     const uint32_t *__restrict__ host_id = st->host_id;
     const uint32_t *__restrict__ rank = st->rank;
+    const uint32_t *__restrict__ hap_id = st->hap_id;
     const uint32_t *__restrict__ offsets = st->offsets;
-    uint32_t *__restrict__ hosts = st->hosts;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t h = host_id[i];
-        if (h != NONE32) hosts[offsets[h] + rank[i]] = (uint32_t)i;
+    uint2 *__restrict__ rec = st->rec;
+    const uint64_t span = (uint64_t)gridDim.x * blockDim.x * INFECT_ITEMS;
+    for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * INFECT_ITEMS; i0 < n; i0 += span) {
+        uint32_t h[INFECT_ITEMS], rk[INFECT_ITEMS], hp[INFECT_ITEMS], ob[INFECT_ITEMS];
+        if (i0 + INFECT_ITEMS <= n) {
+            uint4 a = *reinterpret_cast<const uint4 *>(host_id + i0), b = *reinterpret_cast<const uint4 *>(rank + i0),
+                  c = *reinterpret_cast<const uint4 *>(hap_id + i0);
+            h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w;
+            rk[0] = b.x; rk[1] = b.y; rk[2] = b.z; rk[3] = b.w;
+            hp[0] = c.x; hp[1] = c.y; hp[2] = c.z; hp[3] = c.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < INFECT_ITEMS; e++) {
+                const bool ok = i0 + e < n;
+                h[e] = ok ? host_id[i0 + e] : NONE32;
+                rk[e] = ok ? rank[i0 + e] : 0;
+                hp[e] = ok ? hap_id[i0 + e] : 0;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < INFECT_ITEMS; e++) ob[e] = h[e] != NONE32 ? offsets[h[e]] : 0;
+#pragma unroll
+        for (int e = 0; e < INFECT_ITEMS; e++)
+            if (h[e] != NONE32) rec[ob[e] + rk[e]] = make_uint2((uint32_t)(i0 + e), hp[e]);
     }
 }
 
-// The reference back-fills each host's slice while walking infectants upwards, which leaves the slice in
-// DESCENDING infectant order (KAT src/core/hosts.rs:317-318).  Slices arrive here in arrival order of the
-// atomics; sort them.  Short slices: one thread, insertion sort.  Long ones go to the heavy worklist.
-__global__ void __launch_bounds__(TPB) k_sort_slices(DevState *st) {
-    const uint64_t H = st->H;
-    const uint32_t *__restrict__ offsets = st->offsets;
-    uint32_t *__restrict__ hosts = st->hosts;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t b = offsets[h], e = offsets[h + 1];
-        uint32_t len = e - b;
-        if (len <= 1) continue;
-        if (len > THREAD_TIER) {
-            uint32_t slot = atomicAdd(&st->n_heavy, 1u);
-            st->heavy_hosts[slot] = (uint32_t)h;
-            continue;
-        }
-        for (uint32_t a = b + 1; a < e; a++) {
-            uint32_t x = hosts[a];
-            uint32_t c = a;
-            while (c > b && hosts[c - 1] < x) { hosts[c] = hosts[c - 1]; c--; }
-            hosts[c] = x;
-        }
-    }
-}
-
-// one CTA per heavy slice: normalised bitonic network (all comparators put the larger index first, missing
-// partners beyond the slice end are no-ops), in shared memory when the slice fits, else in global memory.
-__global__ void __launch_bounds__(TPB) k_sort_slices_heavy(DevState *st) {
-    extern __shared__ uint32_t s_keys[];
-    const uint32_t n_heavy = st->n_heavy;
-    for (uint32_t w = blockIdx.x; w < n_heavy; w += gridDim.x) {
-        const uint32_t h = st->heavy_hosts[w];
-        const uint32_t b = st->offsets[h], len = st->offsets[h + 1] - b;
-        uint32_t *g = st->hosts + b;
-        const bool in_smem = len <= SMEM_SORT_MAX;
-        uint32_t *a = in_smem ? s_keys : g;
-        if (in_smem) {
-            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) s_keys[i] = g[i];
-        }
-        __syncthreads();
-        uint32_t P = 1;
-        while (P < len) P <<= 1;
-        for (uint32_t k = 2; k <= P; k <<= 1) {
-            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
-                uint32_t l = i ^ (k - 1);
-                if (l > i && l < len) {
-                    uint32_t x = a[i], y = a[l];
-                    if (x < y) { a[i] = y; a[l] = x; }
-                }
-            }
-            __syncthreads();
-            for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-                for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
-                    uint32_t l = i ^ j;
-                    if (l > i && l < len) {
-                        uint32_t x = a[i], y = a[l];
-                        if (x < y) { a[i] = y; a[l] = x; }
-                    }
-                }
-                __syncthreads();
-            }
-        }
-        if (in_smem) {
-            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) g[i] = s_keys[i];
-        }
-        __syncthreads();
-    }
+// identity layout (no host map): record p = infectant p.  Used when an offspring map comes from the host.
+__global__ void __launch_bounds__(TPB) k_identity_records(DevState *st) {
+    const uint64_t n = st->n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) st->rec[i] = make_uint2((uint32_t)i, st->hap_id[i]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->n_sorted = n;
 }
 
 // ------------------------------------------------------------------------------------------ haplotype records
@@ -293,6 +349,19 @@ __device__ inline double epi_update(const DevProvider &p, const uint32_t *chs, u
     return fitness;
 }
 
+// ------------------------------------------------------------------------------------------ slice order
+// The reference back-fills each host's slice while walking infectants upwards, which leaves the slice in
+// DESCENDING infectant order (KAT src/core/hosts.rs:317-318).  Records arrive in the arrival order of the
+// histogram atomics; sorting them makes the layout (and everything keyed by CSR position) deterministic.
+__device__ __forceinline__ void sort_slice_desc(uint2 *rec, uint32_t b, uint32_t e) {
+    for (uint32_t a = b + 1; a < e; a++) {
+        const uint2 x = rec[a];
+        uint32_t c = a;
+        while (c > b && rec[c - 1].x < x.x) { rec[c] = rec[c - 1]; c--; }
+        rec[c] = x;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ recombination
 struct ReplayRecomb {
     uint64_t n_events;
@@ -325,12 +394,14 @@ __device__ inline uint32_t make_recombinant(DevState *st, uint32_t left, uint32_
     return r.id;
 }
 
+// One thread per host slice (recombination is sequential inside a host: later pairs see earlier replacements).
+// Needs ordered slices: runs after k_host_order.
 __global__ void __launch_bounds__(TPB) k_recombine(DevState *st, ReplayRecomb rp, int replay) {
     const uint64_t H = st->H;
     const uint32_t L = st->L;
     const double rho = st->host_recombination_rate;
     const uint32_t *__restrict__ offsets = st->offsets;
-    const uint32_t *__restrict__ hosts = st->hosts;
+    uint2 *rec = st->rec;
     uint32_t *hap_id = st->hap_id;
     const double log1m = (rho < 1.0) ? log1p(-rho) : 0.0;
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) {
@@ -342,9 +413,10 @@ __global__ void __launch_bounds__(TPB) k_recombine(DevState *st, ReplayRecomb rp
             for (uint64_t e = lo; e < rp.n_events && rp.host[e] == h; e++) {
                 uint32_t i = rp.i[e], j = rp.j[e];
                 if (i >= k || j >= k || rp.s0[e] >= rp.s1[e] || rp.s1[e] > L) { raise(st, DE_REPLAY); continue; }
-                uint32_t ii = hosts[b + i], jj = hosts[b + j];
-                uint32_t rec = make_recombinant(st, hap_id[ii], hap_id[jj], rp.s0[e], rp.s1[e]);
-                hap_id[rp.which[e] ? jj : ii] = rec;
+                uint32_t recid = make_recombinant(st, rec[b + i].y, rec[b + j].y, rp.s0[e], rp.s1[e]);
+                const uint32_t w = b + (rp.which[e] ? j : i);
+                rec[w].y = recid;
+                hap_id[rec[w].x] = recid;
             }
             continue;
         }
@@ -370,10 +442,10 @@ __global__ void __launch_bounds__(TPB) k_recombine(DevState *st, ReplayRecomb rp
             uint32_t s0 = (uint32_t)g.below(L), s1 = (uint32_t)g.below(L);
             while (s0 == s1) s1 = (uint32_t)g.below(L);
             if (s0 > s1) { uint32_t t = s0; s0 = s1; s1 = t; }
-            uint32_t ii = hosts[b + i], jj = hosts[b + j];
-            uint32_t rec = make_recombinant(st, hap_id[ii], hap_id[jj], s0, s1);
-            uint32_t which = (uint32_t)g.below(2);
-            hap_id[which ? jj : ii] = rec;
+            uint32_t recid = make_recombinant(st, rec[b + i].y, rec[b + j].y, s0, s1);
+            const uint32_t w = b + ((uint32_t)g.below(2) ? j : i);
+            rec[w].y = recid;
+            hap_id[rec[w].x] = recid;
             pos += 1;
             if (pos >= K) break;
         }
@@ -387,46 +459,34 @@ struct ReplayMut {
     const uint8_t *bases;
 };
 
-// n_mut ~ Binomial(L, mu) per infected infectant (src/simulation.rs:94-95); the ones with n_mut > 0 go
-// to a worklist so that the expensive part runs on dense warps.
+// Stand-alone mutation counts (replayed generations, or infections that were replayed without a mutation log):
+// n_mut per infected infectant, the ones with n_mut > 0 go to the worklist.
 __global__ void __launch_bounds__(TPB) k_mutation_counts(DevState *st, ReplayMut rp, int replay) {
-    __shared__ uint32_t s_base;
     const uint64_t n = st->n;
     const uint32_t *__restrict__ host_id = st->host_id;
-    const uint64_t L = st->L;
-    const double mu = st->host_mutation_rate;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    const uint32_t gen = st->generation;
     const uint64_t span = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (n + span - 1) / span;
     for (uint64_t r = 0; r < rounds; r++) {
-        const uint64_t i = r * span + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        uint32_t nm = 0;
+        uint64_t idx[1] = {r * span + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x};
+        uint32_t nm[1] = {0};
+        const uint64_t i = idx[0];
         if (i < n && host_id[i] != NONE32) {
-            if (replay) {
-                nm = (uint32_t)(rp.offsets[i + 1] - rp.offsets[i]);
-            } else {
-                Philox g(st->seed, st->compartment, st->generation, PH_MUTCOUNT, i);
-                nm = (uint32_t)binomial(g, L, mu);
-            }
+            if (replay) nm[0] = (uint32_t)(rp.offsets[i + 1] - rp.offsets[i]);
+            else nm[0] = mutation_count(st, key, i, gen, philox_block(key, i, gen, PH_INFECT, 0));
         } else if (i < n && replay && rp.offsets[i + 1] != rp.offsets[i]) {
             raise(st, DE_REPLAY);  // the reference never mutates an uninfected infectant
         }
-        uint32_t tot;
-        uint32_t off = block_excl_scan(nm ? 1u : 0u, &tot);
-        if (threadIdx.x == 0 && tot) s_base = atomicAdd(&st->n_mut_list, tot);
-        __syncthreads();
-        if (nm) {
-            st->mut_list[s_base + off] = (uint32_t)i;
-            st->mut_count[s_base + off] = nm;
-        }
-        __syncthreads();
+        worklist_append<1>(st, idx, nm);
     }
 }
 
 // One thread per mutated infectant: draw sites (with replacement) and sort them, look up the current base
 // on the pre-mutation haplotype, draw the substitution, merge into a new flattened record and update the
 // raw fitness of every provider incrementally: raw(parent) * fold(acc * T[pos,to] / T[pos,from])
-// (src/core/fitness/table.rs:65-68) [* epistatic update].
-__global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay) {
+// (src/core/fitness/table.rs:65-68) [* epistatic update].  The infectant's CSR record is patched in place.
+__global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records) {
     const uint32_t n_list = st->n_mut_list;
     const uint32_t L = st->L;
     const uint8_t *__restrict__ wt = st->wildtype;
@@ -437,8 +497,9 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
         const bool active = w < n_list;
         uint32_t i = 0, nm = 0, pid = 0, plen = 0;
         if (active) {
-            i = st->mut_list[w];
-            nm = st->mut_count[w];
+            const uint2 item = st->mut_list[w];
+            i = item.x;
+            nm = item.y;
             pid = st->hap_id[i];
             plen = st->h_len[pid];
         }
@@ -512,103 +573,167 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
             st->h_raw[p][rec.id] = raw;
         }
         st->hap_id[i] = rec.id;
+        if (patch_records) {
+            const uint32_t h = st->host_id[i];
+            if (h != NONE32) {
+                const uint32_t sb = st->offsets[h], se = st->offsets[h + 1];
+                for (uint32_t q = sb; q < se; q++)
+                    if (st->rec[q].x == i) { st->rec[q].y = rec.id; break; }
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------ replication
-// mapped fitness of every infectant under its host's reproductive provider (or 1.0), NaN where uninfected
-__global__ void __launch_bounds__(TPB) k_fitness(DevState *st, int atomic_sum) {
-    const uint64_t n = st->n;
-    const uint32_t *__restrict__ host_id = st->host_id;
-    const uint32_t *__restrict__ hap_id = st->hap_id;
-    double *__restrict__ fit = st->fit;
-    const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= st->H;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t h = host_id[i];
-        double f = __longlong_as_double(0x7FF8000000000000ll);
-        if (h != NONE32) {
-            const int s = single ? 0 : find_spec(st, h);
-            const int pi = s >= 0 ? st->specs[s].repro : -1;
-            f = pi >= 0 ? utility_apply(st->prov[pi], st->h_raw[pi][hap_id[i]]) : 1.;
-            if (atomic_sum) atomicAdd(&st->hsum[h], f);
-        }
-        fit[i] = f;
-    }
+// mapped fitness of a haplotype under the reproductive provider of spec s (or 1.0), src/simulation.rs:137-143
+__device__ __forceinline__ double reproductive_fitness(const DevState *st, int s, uint32_t hap) {
+    const int pi = s >= 0 ? st->specs[s].repro : -1;
+    return pi >= 0 ? utility_apply(st->prov[pi], st->h_raw[pi][hap]) : 1.;
+}
+// lambda as the offspring kernel consumes it: 0.0 stands for "no offspring".  Poisson::new fails for a mean that
+// is not finite and > 0; the reference then leaves the f64 bit pattern of f in the slot (src/simulation.rs:146-152),
+// which is 0 offspring for f == 0.0 and undefined dynamics otherwise — reported, not imitated.
+__device__ __forceinline__ double checked_lambda(DevState *st, double f, double R0, double S) {
+    const double lam = f * R0 / S;
+    if (isfinite(lam) && lam > 0.0 && lam <= 1.844e19) return lam;
+    if (__double_as_longlong(f) != 0ll) raise(st, DE_UNDEFINED_OFFSPRING);
+    return 0.0;
 }
 
-// S_h = sum of f over the host's slice in slice order, from 0.0 (iter().sum(), src/simulation.rs:144)
-__global__ void __launch_bounds__(TPB) k_host_sum(DevState *st) {
+// One thread per host: order the slice, S_h = sum of f over the slice in slice order from 0.0 (iter().sum(),
+// src/simulation.rs:144), lambda_i = f_i * R0 / S_h at the record's CSR position.  Long slices go to the heavy list.
+__global__ void __launch_bounds__(TPB) k_host_fitness(DevState *st, int order_only) {
     const uint64_t H = st->H;
     const uint32_t *__restrict__ offsets = st->offsets;
-    const uint32_t *__restrict__ hosts = st->hosts;
-    const double *__restrict__ fit = st->fit;
-    double *__restrict__ hsum = st->hsum;
+    uint2 *rec = st->rec;
+    double *__restrict__ lam = st->lam;
+    const double R0 = st->host_r0;
+    const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= st->H;
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t b = offsets[h], e = offsets[h + 1];
-        if (e - b > THREAD_TIER) continue;  // heavy tier
-        if (e == b) continue;
-        double s = 0.0;
-        for (uint32_t a = b; a < e; a++) s += fit[hosts[a]];
-        hsum[h] = s;
-    }
-}
-// one warp per heavy host: lanes gather 32 terms at a time, the additions stay strictly sequential
-__global__ void __launch_bounds__(TPB) k_host_sum_heavy(DevState *st) {
-    const uint32_t n_heavy = st->n_heavy;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t w = warp; w < n_heavy; w += n_warps) {
-        const uint32_t h = st->heavy_hosts[w];
-        const uint32_t b = st->offsets[h], e = st->offsets[h + 1];
-        double s = 0.0;
-        for (uint32_t a0 = b; a0 < e; a0 += 32) {
-            double f = (a0 + lane < e) ? st->fit[st->hosts[a0 + lane]] : 0.0;
-            const uint32_t cnt = min(32u, e - a0);
-            for (uint32_t t = 0; t < cnt; t++) s += __shfl_sync(0xFFFFFFFFu, f, t);
+        const uint32_t len = e - b;
+        if (len == 0) continue;
+        if (len > THREAD_TIER) {
+            const uint32_t slot = atomicAdd(&st->n_heavy, 1u);
+            st->heavy_hosts[slot] = (uint32_t)h;
+            continue;
         }
-        if (lane == 0) st->hsum[h] = s;
+        if (len > 1) sort_slice_desc(rec, b, e);
+        if (order_only) continue;
+        const int s = single ? 0 : find_spec(st, h);
+        if (len == 1) {
+            const double f = reproductive_fitness(st, s, rec[b].y);
+            lam[b] = checked_lambda(st, f, R0, 0.0 + f);
+            continue;
+        }
+        double S = 0.0;
+        for (uint32_t a = b; a < e; a++) S += reproductive_fitness(st, s, rec[a].y);
+        for (uint32_t a = b; a < e; a++) lam[a] = checked_lambda(st, reproductive_fitness(st, s, rec[a].y), R0, S);
     }
 }
 
-// offspring_i ~ Poisson(f_i * R0 / S_host) (src/simulation.rs:146-152); one CTA per resample tile so the
-// tile's offspring total comes out of the same pass.
-__global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t *__restrict__ replay_off) {
-    __shared__ uint64_t s_red[TPB / 32];
-    const uint64_t n = st->n;
-    const uint64_t n_tiles = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
-    const uint32_t *__restrict__ host_id = st->host_id;
-    const double *__restrict__ fit = st->fit;
-    const double *__restrict__ hsum = st->hsum;
-    uint32_t *__restrict__ offspring = st->offspring;
+// One CTA per heavy slice: normalised bitonic network on (index << 32 | haplotype) keys, larger index first
+// (missing partners beyond the slice end are no-ops), in shared memory when the slice fits, else in global
+// memory; then fitness in parallel, the sum strictly sequential in slice order, lambda in parallel.
+__global__ void __launch_bounds__(TPB) k_host_fitness_heavy(DevState *st, int order_only) {
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ double s_S;
+    const uint32_t n_heavy = st->n_heavy;
     const double R0 = st->host_r0;
-    const uint32_t gen = st->generation;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint64_t local = 0;
-#pragma unroll 1
-        for (uint32_t k = 0; k < RESAMPLE_TILE / TPB; k++) {
-            const uint64_t i = tile * RESAMPLE_TILE + (uint64_t)k * TPB + threadIdx.x;
-            if (i >= n) break;
-            const uint32_t h = host_id[i];
-            uint32_t off = 0;
-            if (replay_off) {
-                uint64_t v = replay_off[i];
-                if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0; }
-                off = (uint32_t)v;
-            } else if (h != NONE32) {
-                const double f = fit[i];
-                const double lam = f * R0 / hsum[h];
-                if (isfinite(lam) && lam > 0.0 && lam <= 1.844e19) {
-                    Philox g(st->seed, st->compartment, gen, PH_OFFSPRING, i);
-                    uint64_t v = poisson(g, lam);
-                    if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
-                    off = (uint32_t)v;
-                } else if (__double_as_longlong(f) != 0ll) {
-                    // the reference leaves the f64 bit pattern of f in the slot (src/simulation.rs:146-152):
-                    // undefined population dynamics — report instead of imitating
-                    raise(st, DE_UNDEFINED_OFFSPRING);
+    const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= st->H;
+    for (uint32_t w = blockIdx.x; w < n_heavy; w += gridDim.x) {
+        const uint32_t h = st->heavy_hosts[w];
+        const uint32_t b = st->offsets[h], len = st->offsets[h + 1] - b;
+        unsigned long long *g = reinterpret_cast<unsigned long long *>(st->rec + b);  // uint2 {x = index, y = hap}: little endian u64 = y << 32 | x
+        const bool in_smem = len <= SMEM_SORT_MAX;
+        unsigned long long *a = in_smem ? s_keys : g;
+        // key = index << 32 | hap so that comparing keys compares indices
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const unsigned long long v = g[i];
+            a[i] = (v << 32) | (v >> 32);
+        }
+        __syncthreads();
+        uint32_t P = 1;
+        while (P < len) P <<= 1;
+        for (uint32_t k = 2; k <= P; k <<= 1) {
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+                uint32_t l = i ^ (k - 1);
+                if (l > i && l < len) {
+                    unsigned long long x = a[i], y = a[l];
+                    if (x < y) { a[i] = y; a[l] = x; }
                 }
             }
-            offspring[i] = off;
+            __syncthreads();
+            for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+                    uint32_t l = i ^ j;
+                    if (l > i && l < len) {
+                        unsigned long long x = a[i], y = a[l];
+                        if (x < y) { a[i] = y; a[l] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const unsigned long long v = a[i];
+            g[i] = (v << 32) | (v >> 32);
+        }
+        __syncthreads();
+        if (order_only) continue;
+        const int s = single ? 0 : find_spec(st, h);
+        double *lam = st->lam + b;
+        const uint2 *rec = st->rec + b;
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) lam[i] = reproductive_fitness(st, s, rec[i].y);
+        __syncthreads();
+        if (threadIdx.x < 32) {  // lanes fetch 32 terms at a time, the additions stay strictly sequential
+            const uint32_t lane = threadIdx.x;
+            double S = 0.0;
+            for (uint32_t a0 = 0; a0 < len; a0 += 32) {
+                const double f = (a0 + lane < len) ? lam[a0 + lane] : 0.0;
+                const uint32_t cnt = min(32u, len - a0);
+                for (uint32_t t = 0; t < cnt; t++) S += __shfl_sync(0xFFFFFFFFu, f, t);
+            }
+            if (lane == 0) s_S = S;
+        }
+        __syncthreads();
+        const double S = s_S;
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) lam[i] = checked_lambda(st, lam[i], R0, S);
+        __syncthreads();
+    }
+}
+
+// offspring of the record at CSR position p ~ Poisson(lam[p]) (src/simulation.rs:148-152); one CTA per resample
+// tile so that the tile's offspring total comes out of the same pass.  replay_off is indexed by infectant.
+__global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t *__restrict__ replay_off) {
+    __shared__ uint64_t s_red[TPB / 32];
+    const uint64_t m = st->n_sorted;
+    const uint64_t n_tiles = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const double *__restrict__ lam = st->lam;
+    const uint2 *__restrict__ rec = st->rec;
+    uint32_t *__restrict__ offspring = st->offspring;
+    const uint32_t gen = st->generation;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint64_t local = 0;
+#pragma unroll 2
+        for (uint32_t k = 0; k < RESAMPLE_TILE / TPB; k++) {
+            const uint64_t p = tile * RESAMPLE_TILE + (uint64_t)k * TPB + threadIdx.x;
+            if (p >= m) break;
+            uint32_t off = 0;
+            if (replay_off) {
+                uint64_t v = replay_off[rec[p].x];
+                if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0; }
+                off = (uint32_t)v;
+            } else {
+                const double l = lam[p];
+                if (l > 0.0) {
+                    uint64_t v = poisson_draw(key, p, gen, PH_OFFSPRING, l);
+                    if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
+                    off = (uint32_t)v;
+                }
+            }
+            offspring[p] = off;
             local += off;
         }
 #pragma unroll
@@ -623,16 +748,16 @@ __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t 
         __syncthreads();
     }
 }
-// tile sums of an offspring map that came from the host (vl_target_size / vl_sample_indices with an explicit map)
+// tile sums of an offspring map that came from the host (identity layout)
 __global__ void __launch_bounds__(TPB) k_tile_sums(DevState *st) {
     __shared__ uint64_t s_red[TPB / 32];
-    const uint64_t n = st->n;
-    const uint64_t n_tiles = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint64_t m = st->n_sorted;
+    const uint64_t n_tiles = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint64_t local = 0;
         for (uint32_t k = 0; k < RESAMPLE_TILE / TPB; k++) {
             const uint64_t i = tile * RESAMPLE_TILE + (uint64_t)k * TPB + threadIdx.x;
-            if (i < n) local += st->offspring[i];
+            if (i < m) local += st->offspring[i];
         }
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, s);
@@ -660,67 +785,27 @@ __device__ __forceinline__ uint64_t pow2_ceil(uint64_t x) {
 }
 
 constexpr int PLAN_THREADS = 1024;
-// One CTA.  (1) segment tree over the tile totals; (2) target_size = min(sum*dilution, max_population)
-// (src/simulation.rs:491-503) and size = (factor*target) as usize (:521) or an explicit amount
-// (sample_indices, :505-514); (3) the `size` iid draws proportional to offspring (Population::sample,
-// src/core/population.rs:385-403) are split over tiles as an exact multinomial by walking the tree with
-// conditional binomials; (4) exclusive scan of the per-tile draw counts.
-__global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, double factor, int use_amount, uint64_t amount,
-                                                               int set_next, uint32_t salt) {
-    __shared__ uint64_t s_scan[PLAN_THREADS / 32];
-    __shared__ uint64_t s_carry;
-    const uint64_t n = st->n;
-    const uint64_t nt = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
-    const uint64_t P = pow2_ceil(nt ? nt : 1);
-    uint64_t *tree = st->tile_tree, *cnt = st->tile_cnt;
-    const uint32_t tid = threadIdx.x;
-    for (uint64_t t = tid; t < P; t += PLAN_THREADS) tree[P + t] = t < nt ? st->tile_sum[t] : 0;
+
+// block-wide sum of one u64 per thread (PLAN_THREADS threads)
+__device__ __forceinline__ uint64_t plan_block_sum(uint64_t x, uint64_t *s_scratch) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, s);
     __syncthreads();
-    for (uint64_t s = P >> 1; s >= 1; s >>= 1) {
-        for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) tree[node] = tree[2 * node] + tree[2 * node + 1];
-        __syncthreads();
-    }
-    if (tid == 0) {
-        const uint64_t total = tree[1];
-        double target = 0.0;
-        if (n > 0) {
-            double a = (double)total * st->dilution, b = (double)st->max_population;
-            target = a <= b ? a : b;
-        }
-        uint64_t size = use_amount ? amount : f64_as_usize(factor * target);
-        if (n == 0) size = 0;
-        if (n > 0 && total == 0) { raise(st, DE_ALL_ZERO_WEIGHTS); size = 0; }
-        if (set_next && size > st->cap_inf) { raise(st, DE_INF_CAPACITY); size = st->cap_inf; }
-        st->offspring_total = total;
-        st->target_size = target;
-        st->n_next = size;
-        cnt[1] = size;
-    }
+    if ((threadIdx.x & 31) == 0) s_scratch[threadIdx.x >> 5] = x;
     __syncthreads();
-    for (uint64_t s = 1; s < P; s <<= 1) {
-        for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) {
-            const uint64_t c = cnt[node], wl = tree[2 * node], w = tree[node];
-            uint64_t left = 0;
-            if (c > 0 && wl > 0) {
-                if (wl == w) left = c;
-                else {
-                    Philox g(st->seed, st->compartment, st->generation, PH_PLAN, node | ((uint64_t)salt << 48));
-                    left = binomial(g, c, (double)wl / (double)w);
-                }
-            }
-            cnt[2 * node] = left;
-            cnt[2 * node + 1] = c - left;
-        }
-        __syncthreads();
-    }
-    // exclusive scan of the leaf counts
-    if (tid == 0) s_carry = 0;
+    uint64_t t = 0;
+    for (int w = 0; w < PLAN_THREADS / 32; w++) t += s_scratch[w];
+    return t;
+}
+// exclusive scan of src[0..nt) into dst (may alias); returns nothing, total left in *s_carry
+__device__ __forceinline__ void plan_block_scan(const uint64_t *src, uint64_t *dst, uint64_t nt, bool inclusive, uint64_t *s_scan, uint64_t *s_carry) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) *s_carry = 0;
     __syncthreads();
     for (uint64_t t0 = 0; t0 < nt; t0 += PLAN_THREADS) {
         const uint64_t t = t0 + tid;
-        const uint64_t x = t < nt ? cnt[P + t] : 0;
+        const uint64_t x = t < nt ? src[t] : 0;
         uint64_t inc = x;
-        const uint32_t lane = tid & 31, wid = tid >> 5;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
@@ -734,76 +819,226 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
             if (w < (int)wid) woff += v;
             tot += v;
         }
-        const uint64_t carry = s_carry;
-        if (t < nt) st->tile_base[t] = carry + woff + inc - x;
+        const uint64_t carry = *s_carry;
+        if (t < nt) dst[t] = carry + woff + inc - (inclusive ? 0 : x);
         __syncthreads();
-        if (tid == 0) s_carry = carry + tot;
+        if (tid == 0) *s_carry = carry + tot;
         __syncthreads();
     }
 }
 
-// One CTA per tile: stage the tile's offspring (as an inclusive CDF) and haplotype ids in shared memory,
-// then every draw is a uniform in [0, tile total) + a binary search in shared memory + one coalesced
-// store.  No global gathers.  mode 0: write haplotype ids of the drawn infectants to dst; mode 1: write
-// the drawn infectant indices (u64) to dst64.
+// One CTA.  (1) W = sum of tile totals, target_size = min(W*dilution, max_population) (src/simulation.rs:491-503)
+// and size = (factor*target) as usize (:521) or an explicit amount (sample_indices, :505-514).
+// (2) The `size` iid draws proportional to offspring (Population::sample, src/core/population.rs:385-403) are split
+// over the tiles as an exact multinomial.  Default: Poissonisation — independent N_t ~ Poisson(mu * w_t / W) with
+// mu a few standard deviations below `size` are, given their sum K, Multinomial(K, w/W); the remaining size - K
+// draws are made one by one (binary search in the tile prefix) and added, and a multinomial plus an independent
+// multinomial with the same cell probabilities is the multinomial of the summed size.  K > size (probability
+// ~3e-7 per call) or `force_tree` falls back to walking a segment tree with conditional binomials, which is also
+// exact.  (3) exclusive scan of the per-tile draw counts.
+__global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, double factor, int use_amount, uint64_t amount, int set_next,
+                                                               uint32_t salt, int force_tree, uint32_t smem_tiles) {
+    extern __shared__ uint64_t s_prefix[];  // inclusive prefix of tile totals when nt <= smem_tiles
+    __shared__ uint64_t s_scan[PLAN_THREADS / 32];
+    __shared__ uint64_t s_carry;
+    __shared__ uint64_t s_size, s_W;
+    __shared__ int s_tree;
+    const uint64_t n = st->n;
+    const uint64_t m = st->n_sorted;
+    const uint64_t nt = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint32_t tid = threadIdx.x;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    const uint32_t gen = st->generation;
+    uint64_t *cnt = st->tile_cnt;  // final per-tile draw counts live in cnt[0..nt)
+    uint64_t *prefix = nt <= smem_tiles ? s_prefix : st->tile_tree;
+    plan_block_scan(st->tile_sum, prefix, nt, true, s_scan, &s_carry);
+    if (tid == 0) {
+        const uint64_t total = s_carry;
+        double target = 0.0;
+        if (n > 0) {
+            double a = (double)total * st->dilution, b = (double)st->max_population;
+            target = a <= b ? a : b;
+        }
+        uint64_t size = use_amount ? amount : f64_as_usize(factor * target);
+        if (n == 0) size = 0;
+        if (n > 0 && total == 0) { raise(st, DE_ALL_ZERO_WEIGHTS); size = 0; }
+        if (set_next && size > st->cap_inf) { raise(st, DE_INF_CAPACITY); size = st->cap_inf; }
+        st->offspring_total = total;
+        st->target_size = target;
+        st->n_next = size;
+        s_size = size;
+        s_W = total;
+        s_tree = force_tree;
+    }
+    __syncthreads();
+    const uint64_t size = s_size, W = s_W;
+    if (!force_tree) {
+        const double sd = sqrt((double)size);
+        double mu = (double)size - 5.0 * sd - 8.0;
+        if (!(mu > 0.0)) mu = 0.0;
+        uint64_t mine = 0;
+        for (uint64_t t = tid; t < nt; t += PLAN_THREADS) {
+            const uint64_t w = st->tile_sum[t];
+            uint64_t c = 0;
+            if (w > 0 && mu > 0.0) c = poisson_draw(key, t | ((uint64_t)salt << 48), gen, PH_PLAN, mu * ((double)w / (double)W));
+            cnt[t] = c;
+            mine += c;
+        }
+        const uint64_t K = plan_block_sum(mine, s_scan);
+        if (K > size) {
+            if (tid == 0) s_tree = 1;
+        } else {
+            const uint64_t D = size - K;
+            for (uint64_t j = tid; j < D; j += PLAN_THREADS) {
+                // Uniform(0, W): 64-bit widening multiply with rejection
+                Philox g(st->seed, st->compartment, gen, PH_PLAN_FILL, j | ((uint64_t)salt << 48));
+                const uint64_t r = g.below(W);
+                uint64_t lo = 0, hi = nt;  // first tile with prefix > r
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (prefix[mid] <= r) lo = mid + 1; else hi = mid;
+                }
+                atomicAdd((unsigned long long *)&cnt[lo], 1ull);
+            }
+        }
+        __syncthreads();
+    }
+    if (s_tree) {
+        const uint64_t P = pow2_ceil(nt ? nt : 1);
+        uint64_t *tree = st->tile_tree, *ncnt = st->tile_node;
+        for (uint64_t t = tid; t < P; t += PLAN_THREADS) tree[P + t] = t < nt ? st->tile_sum[t] : 0;
+        __syncthreads();
+        for (uint64_t s = P >> 1; s >= 1; s >>= 1) {
+            for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) tree[node] = tree[2 * node] + tree[2 * node + 1];
+            __syncthreads();
+        }
+        if (tid == 0) ncnt[1] = size;
+        __syncthreads();
+        for (uint64_t s = 1; s < P; s <<= 1) {
+            for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) {
+                const uint64_t c = ncnt[node], wl = tree[2 * node], w = tree[node];
+                uint64_t left = 0;
+                if (c > 0 && wl > 0) {
+                    if (wl == w) left = c;
+                    else {
+                        Philox g(st->seed, st->compartment, gen, PH_PLAN_TREE, node | ((uint64_t)salt << 48));
+                        left = binomial(g, c, (double)wl / (double)w);
+                    }
+                }
+                ncnt[2 * node] = left;
+                ncnt[2 * node + 1] = c - left;
+            }
+            __syncthreads();
+        }
+        for (uint64_t t = tid; t < nt; t += PLAN_THREADS) cnt[t] = ncnt[P + t];
+        __syncthreads();
+    }
+    plan_block_scan(cnt, st->tile_base, nt, false, s_scan, &s_carry);
+}
+
+// One CTA per tile of CSR positions.  The tile's records with offspring > 0 are compacted into shared memory as
+// an inclusive CDF (u32) plus their haplotype ids; a guide table maps the top 11 bits of a draw's random word
+// to the first CDF entry that can contain it (cut-point method), so a draw costs one guide lookup and ~1-2 CDF
+// probes instead of a binary search.  One Philox block serves four consecutive output slots.  No global gathers.
+// mode 0: write the haplotype ids of the drawn records to dst; mode 1: write the drawn infectant indices (u64).
+constexpr uint32_t GUIDE_BITS = 11;
+constexpr uint32_t GUIDE_SIZE = 1u << GUIDE_BITS;
 __global__ void __launch_bounds__(TPB) k_resample(DevState *st, uint32_t *__restrict__ dst, uint64_t *__restrict__ dst64, int mode,
                                                   uint32_t stream_salt) {
-    __shared__ uint64_t s_cdf[RESAMPLE_TILE];
-    __shared__ uint32_t s_hap[RESAMPLE_TILE];
-    __shared__ uint64_t s_w[TPB / 32];
-    const uint64_t n = st->n;
-    const uint64_t nt = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
-    const uint64_t P = pow2_ceil(nt ? nt : 1);
+    __shared__ uint32_t s_cdf[RESAMPLE_TILE];
+    __shared__ uint32_t s_hap[RESAMPLE_TILE];   // haplotype id (mode 0) or position inside the tile (mode 1)
+    __shared__ uint16_t s_guide[GUIDE_SIZE];
+    __shared__ uint32_t s_wsum[TPB / 32], s_wcnt[TPB / 32];
+    const uint64_t m = st->n_sorted;
+    const uint64_t nt = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
     const uint32_t *__restrict__ offspring = st->offspring;
-    const uint32_t *__restrict__ hap_id = st->hap_id;
+    const uint2 *__restrict__ rec = st->rec;
     if (dst == nullptr && mode == 0) dst = st->hap_id_next;
     constexpr uint32_t PER = RESAMPLE_TILE / TPB;  // consecutive items per thread
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    const uint32_t gen = st->generation;
+    const uint64_t salt = (uint64_t)stream_salt << 48;
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-        const uint64_t c = st->tile_cnt[P + tile];
+        const uint64_t c = st->tile_cnt[tile];
         if (c == 0) continue;  // uniform across the CTA
+        if (st->tile_sum[tile] > 0xFFFFFFFFull) {  // the tile CDF is 32-bit
+            if (tid == 0) raise(st, DE_OFFSPRING_RANGE);
+            continue;
+        }
         const uint64_t base = st->tile_base[tile];
         const uint64_t start = tile * RESAMPLE_TILE;
-        // coalesced loads into shared memory
-        for (uint32_t k = tid; k < RESAMPLE_TILE; k += TPB) {
-            const uint64_t i = start + k;
-            s_cdf[k] = i < n ? offspring[i] : 0;
-            s_hap[k] = i < n ? hap_id[i] : 0;
-        }
-        __syncthreads();
-        // inclusive scan: each thread owns PER consecutive items
-        uint64_t run = 0;
+        // ---- load PER consecutive items per thread, local scans of offspring and of the non-zero flags
+        uint32_t v[PER], hp[PER];
+        const uint64_t p0 = start + (uint64_t)tid * PER;
 #pragma unroll
-        for (uint32_t k = 0; k < PER; k++) { run += s_cdf[tid * PER + k]; s_cdf[tid * PER + k] = run; }
-        uint64_t inc = run;
+        for (uint32_t k = 0; k < PER; k++) {
+            const uint64_t p = p0 + k;
+            v[k] = p < m ? offspring[p] : 0u;
+            hp[k] = 0;
+            if (p < m && v[k]) hp[k] = mode == 0 ? rec[p].y : (uint32_t)(p - start);
+        }
+        uint32_t run = 0, nz = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < PER; k++) { run += v[k]; nz += v[k] ? 1u : 0u; }
+        uint32_t inc = run, cinc = nz;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= (uint32_t)d) inc += y;
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d), z = __shfl_up_sync(0xFFFFFFFFu, cinc, d);
+            if (lane >= (uint32_t)d) { inc += y; cinc += z; }
         }
-        if (lane == 31) s_w[wid] = inc;
+        if (lane == 31) { s_wsum[wid] = inc; s_wcnt[wid] = cinc; }
         __syncthreads();
-        uint64_t woff = 0, total = 0;
+        uint32_t woff = 0, total = 0, coff = 0;
 #pragma unroll
         for (int w = 0; w < TPB / 32; w++) {
-            uint64_t t = s_w[w];
-            if (w < (int)wid) woff += t;
+            const uint32_t t = s_wsum[w], u = s_wcnt[w];
+            if (w < (int)wid) { woff += t; coff += u; }
             total += t;
         }
-        const uint64_t excl = woff + inc - run;
+        uint32_t cdf = woff + inc - run;   // exclusive prefix of this thread's first item
+        uint32_t slot = coff + cinc - nz;  // compacted index of this thread's first non-zero item
+        const double scale = (double)GUIDE_SIZE / (double)total;
 #pragma unroll
-        for (uint32_t k = 0; k < PER; k++) s_cdf[tid * PER + k] += excl;
+        for (uint32_t k = 0; k < PER; k++) {
+            if (!v[k]) continue;
+            const uint32_t lo = cdf, hi = cdf + v[k];
+            cdf = hi;
+            s_cdf[slot] = hi;
+            s_hap[slot] = hp[k];
+            // guide[b] = this entry for every bucket b whose first reachable draw value (b*total) >> GUIDE_BITS lies in [lo, hi)
+            uint32_t bf = (uint32_t)((double)lo * scale);
+            if (bf > GUIDE_SIZE) bf = GUIDE_SIZE;
+            while (bf > 0 && (uint32_t)(((uint64_t)(bf - 1) * total) >> GUIDE_BITS) >= lo) bf--;
+            while (bf < GUIDE_SIZE && (uint32_t)(((uint64_t)bf * total) >> GUIDE_BITS) < lo) bf++;
+            for (uint32_t b = bf; b < GUIDE_SIZE && (uint32_t)(((uint64_t)b * total) >> GUIDE_BITS) < hi; b++) s_guide[b] = (uint16_t)slot;
+            slot++;
+        }
         __syncthreads();
-        for (uint64_t j = tid; j < c; j += TPB) {
-            Philox g(st->seed, st->compartment, st->generation, PH_RESAMPLE, (base + j) | ((uint64_t)stream_salt << 48));
-            const uint64_t r = g.below(total);
-            uint32_t lo = 0, hi = RESAMPLE_TILE;  // first index with cdf > r
-            while (lo < hi) {
-                uint32_t mid = (lo + hi) >> 1;
-                if (s_cdf[mid] <= r) lo = mid + 1; else hi = mid;
+        // ---- draws: output slots [base, base + c), four per Philox block
+        const uint64_t q_lo = base >> 2, q_hi = (base + c - 1) >> 2;
+        for (uint64_t q = q_lo + tid; q <= q_hi; q += TPB) {
+            const uint4 blk = philox_block(key, q | salt, gen, PH_RESAMPLE, 0);
+            const uint32_t xs[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint64_t s = q * 4 + w;
+                if (s < base || s >= base + c) continue;
+                uint32_t x = xs[w];
+                uint64_t mm = (uint64_t)x * total;
+                if ((uint32_t)mm < total) {  // biased zone of the widening multiply: exact rejection
+                    const uint32_t thr = (uint32_t)(-total) % total;
+                    if ((uint32_t)mm < thr) {
+                        Philox g(st->seed, st->compartment, gen, PH_RESAMPLE_RETRY, s | salt);
+                        do { x = g.u32(); mm = (uint64_t)x * total; } while ((uint32_t)mm < thr);
+                    }
+                }
+                const uint32_t r = (uint32_t)(mm >> 32);
+                uint32_t i = s_guide[x >> (32 - GUIDE_BITS)];
+                while (s_cdf[i] <= r) i++;
+                if (mode == 0) dst[s] = s_hap[i];
+                else dst64[s] = rec[start + s_hap[i]].x;
             }
-            if (mode == 0) dst[base + j] = s_hap[lo];
-            else dst64[base + j] = start + lo;
         }
         __syncthreads();
     }
@@ -825,6 +1060,7 @@ __global__ void k_swap_population(DevState *st) {
     st->hap_id = st->hap_id_next;
     st->hap_id_next = t;
     st->n = st->n_next;
+    st->n_sorted = 0;
 }
 
 // ------------------------------------------------------------------------------------------ garbage collection
@@ -888,6 +1124,7 @@ __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
 __global__ void __launch_bounds__(TPB) k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }
+// offspring map from the host (u64 per infectant, identity layout) -> device u32 per position
 __global__ void __launch_bounds__(TPB) k_u64_to_u32(DevState *st, const uint64_t *__restrict__ src, uint32_t *__restrict__ dst, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t v = src[i];
@@ -895,18 +1132,37 @@ __global__ void __launch_bounds__(TPB) k_u64_to_u32(DevState *st, const uint64_t
         dst[i] = (uint32_t)v;
     }
 }
-__global__ void __launch_bounds__(TPB) k_u32_to_u64(const uint32_t *__restrict__ src, uint64_t *__restrict__ dst, uint64_t n) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+// offspring per CSR position -> Vec<usize> per infectant (dst pre-zeroed: uninfected infectants have 0 offspring)
+__global__ void __launch_bounds__(TPB) k_unsort_offspring(DevState *st, uint64_t *__restrict__ dst) {
+    const uint64_t m = st->n_sorted;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (uint64_t)gridDim.x * blockDim.x) dst[st->rec[p].x] = st->offspring[p];
 }
-// per-infectant replication terms for inspection: mapped fitness, host sum and lambda (NaN where uninfected)
-__global__ void __launch_bounds__(TPB) k_replication_terms(DevState *st, double *hs_out, double *lam_out) {
-    const uint64_t n = st->n;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t h = st->host_id[i];
-        double s = __longlong_as_double(0x7FF8000000000000ll), l = s;
-        if (h != NONE32) { s = st->hsum[h]; l = st->fit[i] * st->host_r0 / s; }
-        hs_out[i] = s;
-        lam_out[i] = l;
+__global__ void __launch_bounds__(TPB) k_unsort_offspring32(DevState *st, uint32_t *__restrict__ dst) {
+    const uint64_t m = st->n_sorted;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (uint64_t)gridDim.x * blockDim.x) dst[st->rec[p].x] = st->offspring[p];
+}
+__global__ void __launch_bounds__(TPB) k_extract_hosts(DevState *st, uint32_t *__restrict__ dst) {
+    const uint64_t m = st->n_sorted;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (uint64_t)gridDim.x * blockDim.x) dst[p] = st->rec[p].x;
+}
+// per-infectant replication terms for inspection: mapped fitness, host sum and lambda exactly as
+// BasicHost::replicate forms them (outputs pre-filled with NaN for uninfected infectants); ordered slices required
+__global__ void __launch_bounds__(TPB) k_replication_terms(DevState *st, double *fit_out, double *hs_out, double *lam_out) {
+    const uint64_t H = st->H;
+    const double R0 = st->host_r0;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = st->offsets[h], e = st->offsets[h + 1];
+        if (e == b) continue;
+        const int s = find_spec(st, h);
+        double S = 0.0;
+        for (uint32_t a = b; a < e; a++) S += reproductive_fitness(st, s, st->rec[a].y);
+        for (uint32_t a = b; a < e; a++) {
+            const double f = reproductive_fitness(st, s, st->rec[a].y);
+            const uint32_t i = st->rec[a].x;
+            fit_out[i] = f;
+            hs_out[i] = S;
+            lam_out[i] = f * R0 / S;
+        }
     }
 }
 __global__ void __launch_bounds__(TPB) k_gather_raw(DevState *st, uint32_t provider, double *out) {
@@ -914,17 +1170,21 @@ __global__ void __launch_bounds__(TPB) k_gather_raw(DevState *st, uint32_t provi
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = st->h_raw[provider][st->hap_id[i]];
 }
 
-// sampler test hooks (distribution tests of the device samplers)
+// sampler test hooks (distribution tests of the device samplers the kernels above call)
 __global__ void k_test_poisson(uint64_t seed, double lambda, uint64_t n, uint64_t *out) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        Philox g(seed, 0, 0, PH_TEST, i);
-        out[i] = poisson(g, lambda);
-    }
+    const PhiloxKey key = philox_key(seed, 0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = poisson_draw(key, i, 0, PH_TEST, lambda);
 }
-__global__ void k_test_binomial(uint64_t seed, uint64_t nn, double p, uint64_t n, uint64_t *out) {
+__global__ void k_test_binomial(uint64_t seed, uint64_t nn, double p, uint64_t n, uint64_t *out, BinvConst c) {
+    const PhiloxKey key = philox_key(seed, 0);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        Philox g(seed, 0, 0, PH_TEST, i);
-        out[i] = binomial(g, nn, p);
+        if (c.ok) {
+            const uint4 b0 = philox_block(key, i, 0, PH_TEST, 0);
+            out[i] = binv_draw(c, u01_from(b0.z, b0.w), key, i, 0, PH_TEST);
+        } else {
+            Philox g(seed, 0, 0, PH_TEST, i);
+            out[i] = binomial(g, nn, p);
+        }
     }
 }
 __global__ void k_test_below(uint64_t seed, uint64_t bound, uint64_t n, uint64_t *out) {

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(TPB) k_copy_ids(DevState *st, const uint32_t *
 __global__ void k_set_next_n(DevState *st, uint64_t n) { st->n_next = n; }
 __global__ void k_fill_population(DevState *st, uint64_t n, uint32_t id) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) st->hap_id[i] = id;
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->n = n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->n = n; st->n_sorted = 0; }
 }
 // copy of the first n_next entries of the assembled population (detached subsample of the fused path)
 __global__ void __launch_bounds__(TPB) k_copy_out_next(DevState *st, uint32_t *__restrict__ dst, uint64_t cap) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(TPB) k_copy_out_next(DevState *st, uint32_t *_
 __global__ void __launch_bounds__(TPB) k_target_size(DevState *st) {
     __shared__ uint64_t s_red[TPB / 32];
     const uint64_t n = st->n;
-    const uint64_t nt = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint64_t nt = (st->n_sorted + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
     uint64_t local = 0;
     for (uint64_t t = threadIdx.x; t < nt; t += TPB) local += st->tile_sum[t];
 #pragma unroll
@@ -186,14 +186,6 @@ __global__ void k_get_base(DevState *st, uint64_t infectant, uint32_t pos, uint3
     if (infectant >= st->n || pos >= st->L) { *out = 0xFFu; return; }
     const uint32_t id = st->hap_id[infectant];
     *out = entries_get_base(st->arena + st->h_off[id], st->h_len[id], pos, st->wildtype);
-}
-
-// ---- direct haplotype construction (Haplotype::create_descendant / create_recombinant through the ABI;
-//      used by the known-answer tests of src/core/haplotype.rs:957-1048 and src/lib.rs:113-142)
-__global__ void k_make_recombinant(DevState *st, uint64_t dst_infectant, uint64_t left_infectant, uint64_t right_infectant, uint32_t s0,
-                                   uint32_t s1) {
-    if (dst_infectant >= st->n || left_infectant >= st->n || right_infectant >= st->n || s0 >= s1 || s1 > st->L) { raise(st, DE_REPLAY); return; }
-    st->hap_id[dst_infectant] = make_recombinant(st, st->hap_id[left_infectant], st->hap_id[right_infectant], s0, s1);
 }
 
 }  // namespace vl

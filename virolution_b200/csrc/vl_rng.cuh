@@ -19,49 +19,65 @@ namespace vl {
 
 enum Phase : uint32_t {
     PH_INFECT = 1, PH_MUTCOUNT = 2, PH_MUTATE = 3, PH_RECOMB = 4, PH_OFFSPRING = 5, PH_PLAN = 6,
-    PH_RESAMPLE = 7, PH_MIGRANT = 8, PH_TEST = 9
+    PH_RESAMPLE = 7, PH_MIGRANT = 8, PH_TEST = 9, PH_PLAN_FILL = 10, PH_PLAN_TREE = 11, PH_RESAMPLE_RETRY = 12
 };
 
+// ---- stateless block function: block `blk` of stream (index, generation, phase) under key (seed, compartment)
+struct PhiloxKey { uint32_t k0, k1; };
+__host__ __device__ inline PhiloxKey philox_key(uint64_t seed, uint32_t compartment) {
+    uint64_t k = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(compartment + 1);
+    k ^= k >> 31;
+    return PhiloxKey{(uint32_t)k, (uint32_t)(k >> 32)};
+}
+__host__ __device__ inline void philox_mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+#ifdef __CUDA_ARCH__
+    hi = __umulhi(a, b);
+    lo = a * b;
+#else
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
+__host__ __device__ inline uint4 philox_block(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, uint32_t blk) {
+    uint32_t x0 = (uint32_t)index, x1 = (uint32_t)(index >> 32), x2 = generation, x3 = (phase << 24) + blk;
+    uint32_t k0 = key.k0, k1 = key.k1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0, lo0, hi1, lo1;
+        philox_mulhilo(0xD2511F53u, x0, hi0, lo0);
+        philox_mulhilo(0xCD9E8D57u, x2, hi1, lo1);
+        uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+        x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(x0, x1, x2, x3);
+}
+// rand's random::<f64>() from two words: 53 random bits * 2^-53, in [0,1)
+__host__ __device__ inline double u01_from(uint32_t lo, uint32_t hi) {
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+__host__ __device__ inline double u01_open_from(uint32_t lo, uint32_t hi) {
+    return ((double)((((uint64_t)hi << 32) | lo) >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// sequential generator over the same streams (general-purpose paths)
 struct Philox {
-    uint32_t key0, key1;
-    uint32_t c0, c1, c2, c3;
+    PhiloxKey key;
+    uint64_t index;
+    uint32_t generation, phase, blk;
     uint32_t out[4];
     int have;
 
-    __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
-#ifdef __CUDA_ARCH__
-        hi = __umulhi(a, b);
-        lo = a * b;
-#else
-        uint64_t p = (uint64_t)a * b;
-        hi = (uint32_t)(p >> 32);
-        lo = (uint32_t)p;
-#endif
-    }
     __host__ __device__ inline void block() {
-        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, k0 = key0, k1 = key1;
-#pragma unroll
-        for (int r = 0; r < 10; r++) {
-            uint32_t hi0, lo0, hi1, lo1;
-            mulhilo(0xD2511F53u, x0, hi0, lo0);
-            mulhilo(0xCD9E8D57u, x2, hi1, lo1);
-            uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
-            x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-            k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-        }
-        out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
-        c3 += 1;  // low 24 bits of c3 count blocks within a stream
+        uint4 b = philox_block(key, index, generation, phase, blk);
+        out[0] = b.x; out[1] = b.y; out[2] = b.z; out[3] = b.w;
+        blk += 1;  // low 24 bits of the last counter word count blocks within a stream
         have = 4;
     }
-    // stream (index, generation, phase) under key (seed ^ compartment)
-    __host__ __device__ inline Philox(uint64_t seed, uint32_t compartment, uint32_t generation, uint32_t phase,
-                                      uint64_t index) {
-        uint64_t k = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(compartment + 1);
-        k ^= k >> 31;
-        key0 = (uint32_t)k; key1 = (uint32_t)(k >> 32);
-        c0 = (uint32_t)index; c1 = (uint32_t)(index >> 32); c2 = generation; c3 = phase << 24;
-        have = 0;
-    }
+    __host__ __device__ inline Philox(uint64_t seed, uint32_t compartment, uint32_t generation_, uint32_t phase_, uint64_t index_,
+                                      uint32_t first_block = 0)
+        : key(philox_key(seed, compartment)), index(index_), generation(generation_), phase(phase_), blk(first_block), have(0) {}
     __host__ __device__ inline uint32_t u32() {
         if (have == 0) block();
         return out[4 - (have--)];
@@ -196,6 +212,70 @@ __host__ __device__ inline int weighted4(Philox &g, const double *w) {
     if (c1 <= chosen) idx = 2;
     if (c2 <= chosen) idx = 3;
     return idx;
+}
+
+
+// ---- hot-path samplers: one Philox block per decision wherever possible -------------------------------------
+// Poisson(lambda), exact.  lambda < 12: inversion of ONE uniform (words x,y of block 0) by sequential search —
+// same law as rand_distr 0.5.1's Knuth product branch at a fraction of the random words.  Otherwise PTRS
+// (Hoermann 1993) with one block per attempt (same law as rand_distr's rejection branch).
+__device__ __forceinline__ uint64_t poisson_draw(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, double lambda) {
+    if (lambda < 12.0) {
+        const uint4 b = philox_block(key, index, generation, phase, 0);
+        const double u = u01_from(b.x, b.y);
+        double p = exp(-lambda), cdf = p;
+        uint32_t k = 0;
+        while (u >= cdf && k < 256) {
+            k += 1;
+            p = p * lambda / (double)k;
+            cdf += p;
+        }
+        return k;
+    }
+    const double slam = sqrt(lambda);
+    const double bb = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * bb;
+    const double vr = 0.9277 - 3.6224 / (bb - 2.0);
+    for (uint32_t attempt = 0;; attempt++) {
+        const uint4 b = philox_block(key, index, generation, phase, attempt);
+        const double u = u01_open_from(b.x, b.y) - 0.5, v = u01_open_from(b.z, b.w);
+        const double us = 0.5 - fabs(u);
+        const double k = floor((2.0 * a / us + bb) * u + lambda + 0.43);
+        if (us >= 0.07 && v <= vr) return (uint64_t)k;
+        if (k < 0.0 || (us < 0.013 && v > us)) continue;
+        const double invalpha = 1.1239 + 1.1328 / (bb - 3.4);
+        if (log(v) + log(invalpha) - log(a / (us * us) + bb) <= -lambda + k * log(lambda) - lgamma(k + 1.0)) return (uint64_t)k;
+    }
+}
+
+// Binomial(n, p) in the small-mean regime n*p < 10 with host-precomputed constants q^n, s = p/q, a = (n+1)s:
+// inversion of one uniform (the BINV branch of rand_distr 0.5.1).  `u` is consumed; a restart (k beyond the
+// search bound, probability < 1e-100) draws from the stream's later blocks.
+struct BinvConst { double qn, s, a; uint64_t n; int ok; };
+__host__ inline BinvConst make_binv(uint64_t n, double p) {
+    BinvConst c;
+    c.n = n;
+    c.ok = (p > 0.0 && p <= 0.5 && (double)n * p < 10.0) ? 1 : 0;
+    const double q = 1.0 - p;
+    c.qn = c.ok ? exp((double)n * log1p(-p)) : 0.0;
+    c.s = p / q;
+    c.a = ((double)n + 1.0) * c.s;
+    return c;
+}
+__device__ __forceinline__ uint32_t binv_draw(const BinvConst &c, double u, PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase) {
+    uint32_t blk = 1;
+    for (;;) {
+        double r = c.qn;
+        uint32_t k = 0;
+        while (u > r) {
+            u -= r;
+            k += 1;
+            if (k > 200 || k > c.n) break;
+            r *= c.a / (double)k - c.s;
+        }
+        if (k <= 200 && k <= c.n) return k;
+        const uint4 b = philox_block(key, index, generation, phase, blk++);
+        u = u01_from(b.x, b.y);
+    }
 }
 
 }  // namespace vl

@@ -4,8 +4,11 @@
 //   population     hap_id[n]            u32   id of each infectant's haplotype      (Population.population,
 //                                                                                     src/core/population.rs:156-163)
 //   host map       host_id[n]           u32   Option<host> with NONE sentinel        (HostMapBuffer.infections,
-//                  offsets[H+1], hosts[n_infected] u32  CSR by host                   src/core/hosts.rs:133-192)
-//   replication    fit[n] f64, hsum[H] f64, offspring[n] u32, tile_sum[] u64
+//                  offsets[H+1]         u32   CSR by host                             src/core/hosts.rs:133-192)
+//                  rec[n_infected]      uint2 (infectant index, haplotype id) in CSR order: HostMapBuffer.hosts with
+//                                             the haplotype id carried along, so everything downstream of the
+//                                             counting sort streams over host-contiguous records
+//   replication    lam[p] f64 (Poisson mean of the record at CSR position p), offspring[p] u32, tile_sum[] u64
 //   haplotypes     h_off[u64] h_len[u32] h_parent[u32] h_raw[provider][f64]  + arena of u32 entries
 //
 // A haplotype record is the *flattened* form of the reference's delta chain (Wildtype / Mutant{changes} /
@@ -23,13 +26,14 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/virolution_gpu.h"
+#include "vl_rng.cuh"
 
 namespace vl {
 
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr int MAX_SPECS = 8;
 constexpr int MAX_PROVIDERS = 16;
-constexpr uint32_t RESAMPLE_TILE = 2048;  // infectants per resample tile (one CTA stages one tile in smem)
+constexpr uint32_t RESAMPLE_TILE = 2048;  // CSR positions per resample tile (one CTA stages one tile in smem)
 
 // error bits raised by kernels (sticky until vl_* reports them)
 enum DevError : uint32_t {
@@ -90,24 +94,27 @@ struct DevState {
     uint32_t error;
     uint64_t infectant_generations;
 
-    // ---- host map
-    uint32_t *host_id, *rank, *offsets, *hosts;
+    // ---- host map (CSR positions p in [0, n_sorted))
+    uint32_t *host_id, *rank, *offsets;
+    uint2 *rec;            // (infectant index, haplotype id) per CSR position
+    uint64_t n_sorted;     // number of records = infected infectants (offsets[H])
     uint32_t *heavy_hosts; // worklist of hosts whose slice exceeds the thread tier
     uint32_t n_heavy;
-    uint32_t n_infected_valid;
+    uint32_t fast_infect;  // one spec over [0,H), no infective provider, n_hits == 1: every draw infects
 
     // ---- mutation worklist
-    uint32_t *mut_list;    // infectant indices with n_mut > 0
-    uint32_t *mut_count;   // n_mut per worklist entry
+    uint2 *mut_list;       // (infectant index, n_mut) for infectants with n_mut > 0
     uint32_t n_mut_list;
     uint32_t _pad0;
+    BinvConst binv;        // Binomial(L, mu) inversion constants (captured BasicHost parameters)
 
     // ---- replication
-    double *fit, *hsum;
-    uint32_t *offspring;
+    double *lam;           // per CSR position
+    uint32_t *offspring;   // per CSR position
     uint64_t *tile_sum;    // per resample tile
-    uint64_t *tile_tree;   // segment tree over tile sums (plan kernel)
-    uint64_t *tile_cnt;    // draws per tree node / tile
+    uint64_t *tile_tree;   // segment tree over tile sums (fallback plan) / inclusive prefix of tile sums
+    uint64_t *tile_cnt;    // draws per tile
+    uint64_t *tile_node;   // draws per tree node (fallback plan)
     uint64_t *tile_base;   // exclusive scan of draws per tile
     uint64_t offspring_total;
     double target_size;    // of the last plan
