@@ -181,7 +181,8 @@ int vl_replay_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n);
 int vl_get_infections(vl_sim *sim, int64_t *out, uint64_t n);          /* HostMapBuffer.infections */
 int vl_get_host_map(vl_sim *sim, uint64_t *offsets_out /*H+1*/, uint64_t *hosts_out /*n infected*/,
                     uint64_t *n_infected_out);                          /* hosts.rs:166-192 */
-/* mapped fitness f_i, host sum S and lambda_i of the last replicate (NaN where not infected). */
+/* mapped fitness f_i, host sum S and the Poisson mean lambda_i the last replicate used (0.0 where
+ * Poisson::new fails, i.e. no offspring); NaN where not infected. */
 int vl_get_replication_terms(vl_sim *sim, double *fitness_out, double *host_sum_out, double *lambda_out,
                              uint64_t n);
 int vl_get_offspring_prefix(vl_sim *sim, uint64_t *prefix_out, uint64_t n); /* inclusive scan */
@@ -209,6 +210,7 @@ int vl_timer_start(vl_sim *sim);
 int vl_timer_stop(vl_sim *sim, double *ms_out);            /* synchronises; device time since vl_timer_start */
 int vl_profile(vl_sim *sim, int enable);                   /* bracket every kernel launch with events */
 int vl_profile_report(vl_sim *sim, char *buf, uint64_t cap); /* "<kernel> <launches> <total_ms>\n" per kernel */
+int vl_debug_stamps(vl_sim *sim, uint64_t *out8);          /* %globaltimer stamps of the last plan kernel's phases */
 
 /* ---- device sampler hooks (distribution tests of the Philox-driven samplers that stand in for
  * rand_distr 0.5.1 Poisson / Binomial and rand 0.9.0 Uniform; call sites src/simulation.rs:47-48,148-151) */

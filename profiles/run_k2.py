@@ -15,5 +15,7 @@ sim = GpuSimulation(wl["wildtype"], wl["parameters"], wl["specs"], seed=2026, fl
 sim.set_population_wildtype(n)
 sim.run(gens)
 sim.synchronize()
+st = sim.debug_stamps().astype("int64")
+print("plan kernel phases (us): prefix+size %.1f, tile poisson %.1f, fill draws %.1f, scan %.1f" % tuple((st[k + 1] - st[k]) / 1e3 for k in range(4)))
 print("population", sim.population_len(), sim.get_counters())
 sim.close()

@@ -270,6 +270,14 @@ static int add_provider(vl_sim *sim, const vl_fitness *f, uint64_t L, int *index
     p.upper = f->utility.upper;
     p.hill_n = f->utility.n;
     p.hill_k = (1.0 - f->utility.p) / f->utility.p;  // UtilityFunction::new_hill, src/core/fitness/utility.rs:26-45
+    {
+        // UtilityFunction::apply, Algebraic arm (utility.rs:51-54): `let factor = 1. / (upper - 1.)` then
+        // `upper * factor * f / ...` — both constants are formed here with the same two roundings
+        volatile double factor = 1. / (f->utility.upper - 1.);
+        volatile double uf = f->utility.upper * factor;
+        p.alg_factor = factor;
+        p.alg_uf = uf;
+    }
     if (f->kind >= VL_FITNESS_NONEPISTATIC) {
         if (!f->table) return fail(sim, VL_ERR_INITIALIZATION, "fitness table missing");
         double *t = nullptr;
@@ -415,7 +423,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     update_fast_infect(sim);
     h.binv = make_binv(L, par.mutation_rate);
     CCU(cudaFuncSetAttribute(k_plan_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CCU(cudaFuncSetAttribute(k_host_fitness_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 8));
+    CCU(cudaFuncSetAttribute(k_host_lambda_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
     sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
     h.gc_arena_threshold = cap_arena / 2;
@@ -555,12 +563,26 @@ static int ensure_ordered_slices(vl_sim *sim) {
     if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no host map: call vl_infect first");
     if (sim->slices_ordered) return VL_OK;
     TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
-    LAUNCH(sim, k_host_fitness, grid_for(sim, sim->h.H), TPB, 0, sim->d, 1);
-    LAUNCH(sim, k_host_fitness_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 8, sim->d, 1);
+    LAUNCH(sim, k_host_lambda, grid_for(sim, sim->h.H), TPB, 0, sim->d, 1);
+    LAUNCH(sim, k_host_lambda_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 1);
     sim->slices_ordered = true;
     return VL_OK;
 }
-static int enqueue_infect(vl_sim *sim) {
+static int enqueue_host_map(vl_sim *sim) {
+    // counting sort by host: exclusive scan of the histogram, then every record moves to its CSR position
+    const DevState &h = sim->h;
+    const unsigned g = grid_for(sim, (sim->n_bound + INFECT_ITEMS - 1) / INFECT_ITEMS);
+    TRY((launch_scan<uint32_t, true>(sim, sim->count, h.offsets, (const uint64_t *)((const char *)sim->d + FIELD_OFF(H)), 0, h.H,
+                                     (uint64_t *)((char *)sim->d + FIELD_OFF(n_sorted)), 1, nullptr)));
+    LAUNCH(sim, k_scatter, g, TPB, 0, sim->d);
+    sim->csr_valid = true;
+    sim->slices_ordered = false;
+    sim->layout_valid = false;
+    return VL_OK;
+}
+// defer_host_map: the fused generation mutates first (the mutation worklist comes out of the infect pass) and
+// builds the host map from the already-mutated population, so no record needs patching afterwards
+static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
     const DevState &h = sim->h;
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec;
     const bool fuse = !replay && h.binv.ok;
@@ -575,13 +597,11 @@ static int enqueue_infect(vl_sim *sim) {
     else LAUNCH(sim, (k_infect<false, false>), g, TPB, 0, sim->d, sim->count, rp);
     sim->has_rp_inf = false;
     sim->mutcounts_ready = fuse;
-    // counting sort by host: exclusive scan of the histogram, then every record moves to its CSR position
-    TRY((launch_scan<uint32_t, true>(sim, sim->count, h.offsets, (const uint64_t *)((const char *)sim->d + FIELD_OFF(H)), 0, h.H,
-                                     (uint64_t *)((char *)sim->d + FIELD_OFF(n_sorted)), 1, nullptr)));
-    LAUNCH(sim, k_scatter, g, TPB, 0, sim->d);
-    sim->csr_valid = true;
+    sim->csr_valid = false;
     sim->slices_ordered = false;
     sim->layout_valid = false;
+    if (defer_host_map && fuse && !(h.host_recombination_rate > 0.0)) return VL_OK;
+    TRY(enqueue_host_map(sim));
     if (h.host_recombination_rate > 0.0 || sim->has_rp_rec) TRY(ensure_ordered_slices(sim));
     return VL_OK;
 }
@@ -619,10 +639,13 @@ static int enqueue_replicate(vl_sim *sim) {
     const DevState &h = sim->h;
     if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "replicate needs the host map: call vl_infect first");
     TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
-    LAUNCH(sim, k_host_fitness, grid_for(sim, h.H), TPB, 0, sim->d, 0);
-    LAUNCH(sim, k_host_fitness_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 8, sim->d, 0);
+    LAUNCH(sim, k_fitness, grid_for(sim, sim->n_bound), TPB, 0, sim->d);
+    LAUNCH(sim, k_host_lambda, grid_for(sim, h.H), TPB, 0, sim->d, 0);
+    LAUNCH(sim, k_host_lambda_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 0);
     sim->slices_ordered = true;
-    LAUNCH(sim, k_offspring, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, (const uint64_t *)(sim->has_rp_off ? sim->rp_off : nullptr));
+    const uint64_t *rpo = sim->has_rp_off ? sim->rp_off : nullptr;
+    if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring<true>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo);
+    else LAUNCH(sim, k_offspring<false>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo);
     sim->has_rp_off = false;
     sim->layout_valid = true;
     return VL_OK;
@@ -945,8 +968,9 @@ static int enqueue_generation(vl_sim *sim) {
     // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
     LAUNCH(sim, k_tick, 1, 1, 0, sim->d);
     sim->salt = 0;
-    TRY(enqueue_infect(sim));
+    TRY(enqueue_infect(sim, true));
     TRY(enqueue_mutate(sim));
+    if (!sim->csr_valid) TRY(enqueue_host_map(sim));
     TRY(enqueue_replicate(sim));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
     swap_population(sim);
@@ -1156,7 +1180,7 @@ VL_API int vl_get_host_map(vl_sim *sim, uint64_t *offsets_out, uint64_t *hosts_o
 VL_API int vl_get_replication_terms(vl_sim *sim, double *fitness_out, double *host_sum_out, double *lambda_out, uint64_t n) {
     ENTER(sim);
     TRY(expect_len(sim, n));
-    TRY(ensure_ordered_slices(sim));
+    if (!sim->csr_valid || !sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no replication terms: vl_replicate_infectants has not run on this population");
     double *tmp = nullptr;
     CU(sim, cudaMalloc((void **)&tmp, std::max<uint64_t>(3 * n, 1) * 8));
     CU(sim, cudaMemsetAsync(tmp, 0xFF, std::max<uint64_t>(3 * n, 1) * 8, sim->stream));  // NaN where not infected
@@ -1248,6 +1272,13 @@ VL_API int vl_get_counters(vl_sim *sim, uint64_t *out4) {
     TRY(read_field(sim, FIELD_OFF(arena_top), &at));
     TRY(read_field(sim, FIELD_OFF(gc_runs), &runs));
     out4[0] = nh; out4[1] = at; out4[2] = runs; out4[3] = sim->launches;
+    return VL_OK;
+}
+VL_API int vl_debug_stamps(vl_sim *sim, uint64_t *out8) {
+    ENTER(sim);
+    CU(sim, cudaMemcpyAsync(sim->pin + 16, (const char *)sim->d + FIELD_OFF(dbg), 64, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    memcpy(out8, sim->pin + 16, 64);
     return VL_OK;
 }
 VL_API int vl_collect_garbage(vl_sim *sim) {

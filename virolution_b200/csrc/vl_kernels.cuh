@@ -5,7 +5,7 @@
 //                         (+ the Binomial(L, mu) mutation count of BasicHost::mutate, :94-95, fused: the count
 //                         depends only on (seed, generation, infectant), not on the phase that draws it)
 //   scan, k_scatter       HostMapBuffer::build (counting sort, back-fill)         src/core/hosts.rs:166-192
-//   k_host_fitness[_heavy]  ... the descending in-host order its back-fill produces, then
+//   k_fitness, k_host_lambda[_heavy]  the descending in-host order that back-fill produces, then
 //                         BasicHost::replicate's fitness, per-host sum and lambda  src/simulation.rs:120-147
 //   k_recombine           BasicHost::mutate, recombination part                   src/simulation.rs:68-90
 //   k_mutation_counts,    BasicHost::mutate, mutation part + create_descendant    src/simulation.rs:93-117,
@@ -33,8 +33,14 @@ constexpr int TPB = 256;
 constexpr uint32_t THREAD_TIER = 32;      // slices up to this length are handled by one thread
 constexpr uint32_t SMEM_SORT_MAX = 4096;  // slices up to this length are sorted in shared memory (u64 keys)
 constexpr int INFECT_ITEMS = 4;           // infectants per thread and round in k_infect / k_scatter
+constexpr uint32_t SMALL_SLICE = 6;       // slices up to this length are ordered and summed in registers
 
 __device__ __forceinline__ void raise(DevState *st, uint32_t bit) { atomicOr(&st->error, bit); }
+__device__ __forceinline__ uint64_t vl_globaltimer() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // HostSpecs::try_get_spec_from_index (src/core/hosts.rs:62-64): first spec whose range contains the host
 __device__ __forceinline__ int find_spec(const DevState *st, uint64_t h) {
@@ -353,15 +359,6 @@ __device__ inline double epi_update(const DevProvider &p, const uint32_t *chs, u
 // The reference back-fills each host's slice while walking infectants upwards, which leaves the slice in
 // DESCENDING infectant order (KAT src/core/hosts.rs:317-318).  Records arrive in the arrival order of the
 // histogram atomics; sorting them makes the layout (and everything keyed by CSR position) deterministic.
-__device__ __forceinline__ void sort_slice_desc(uint2 *rec, uint32_t b, uint32_t e) {
-    for (uint32_t a = b + 1; a < e; a++) {
-        const uint2 x = rec[a];
-        uint32_t c = a;
-        while (c > b && rec[c - 1].x < x.x) { rec[c] = rec[c - 1]; c--; }
-        rec[c] = x;
-    }
-}
-
 // ------------------------------------------------------------------------------------------ recombination
 struct ReplayRecomb {
     uint64_t n_events;
@@ -600,57 +597,136 @@ __device__ __forceinline__ double checked_lambda(DevState *st, double f, double 
     return 0.0;
 }
 
+// spec of a CSR position: host ranges are contiguous, so each spec owns the position range
+// [offsets[lo], offsets[min(hi, H)]); first match wins like HostSpecs::try_get_spec_from_index
+__device__ __forceinline__ int find_spec_of_position(const DevState *st, uint64_t p) {
+    for (uint32_t s = 0; s < st->n_specs; s++) {
+        const uint64_t lo = st->specs[s].lo < st->H ? st->specs[s].lo : st->H, hi = st->specs[s].hi < st->H ? st->specs[s].hi : st->H;
+        if (lo < hi && p >= st->offsets[lo] && p < st->offsets[hi]) return (int)s;
+    }
+    return -1;
+}
+
+// One thread per CSR position: mapped reproductive fitness of the record's haplotype (the random gather of the
+// generation), parked in lam[p] until k_host_lambda turns it into the Poisson mean.
+__global__ void __launch_bounds__(TPB) k_fitness(DevState *st) {
+    const uint64_t m = st->n_sorted;
+    const uint2 *__restrict__ rec = st->rec;
+    double *__restrict__ lam = st->lam;
+    const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= st->H;
+    const int pi0 = st->specs[0].repro;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (uint64_t)gridDim.x * blockDim.x) {
+        double f;
+        if (single) f = pi0 >= 0 ? utility_apply(st->prov[pi0], st->h_raw[pi0][rec[p].y]) : 1.;
+        else f = reproductive_fitness(st, find_spec_of_position(st, p), rec[p].y);
+        lam[p] = f;
+    }
+}
+
+// sort one slice by descending infectant index, carrying the parked fitness values along
+__device__ __forceinline__ void sort_slice_desc(uint2 *rec, double *lam, uint32_t b, uint32_t e) {
+    for (uint32_t a = b + 1; a < e; a++) {
+        const uint2 x = rec[a];
+        const double fx = lam[a];
+        uint32_t c = a;
+        while (c > b && rec[c - 1].x < x.x) { rec[c] = rec[c - 1]; lam[c] = lam[c - 1]; c--; }
+        rec[c] = x;
+        lam[c] = fx;
+    }
+}
+
 // One thread per host: order the slice, S_h = sum of f over the slice in slice order from 0.0 (iter().sum(),
 // src/simulation.rs:144), lambda_i = f_i * R0 / S_h at the record's CSR position.  Long slices go to the heavy list.
-__global__ void __launch_bounds__(TPB) k_host_fitness(DevState *st, int order_only) {
+__global__ void __launch_bounds__(TPB) k_host_lambda(DevState *st, int order_only) {
     const uint64_t H = st->H;
     const uint32_t *__restrict__ offsets = st->offsets;
     uint2 *rec = st->rec;
-    double *__restrict__ lam = st->lam;
+    double *lam = st->lam;
     const double R0 = st->host_r0;
-    const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= st->H;
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t b = offsets[h], e = offsets[h + 1];
         const uint32_t len = e - b;
         if (len == 0) continue;
+        if (len == 1) {
+            if (!order_only) {
+                const double f = lam[b];
+                lam[b] = checked_lambda(st, f, R0, 0.0 + f);
+            }
+            continue;
+        }
         if (len > THREAD_TIER) {
             const uint32_t slot = atomicAdd(&st->n_heavy, 1u);
             st->heavy_hosts[slot] = (uint32_t)h;
             continue;
         }
-        if (len > 1) sort_slice_desc(rec, b, e);
-        if (order_only) continue;
-        const int s = single ? 0 : find_spec(st, h);
-        if (len == 1) {
-            const double f = reproductive_fitness(st, s, rec[b].y);
-            lam[b] = checked_lambda(st, f, R0, 0.0 + f);
+        if (len <= SMALL_SLICE) {
+            // the whole slice in registers: rank of every member by descending index (no dependent memory chain)
+            uint2 r[SMALL_SLICE];
+            double f[SMALL_SLICE];
+            uint32_t rk[SMALL_SLICE];
+#pragma unroll
+            for (uint32_t k = 0; k < SMALL_SLICE; k++) {
+                r[k] = k < len ? rec[b + k] : make_uint2(0u, 0u);
+                f[k] = k < len ? lam[b + k] : 0.0;
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < SMALL_SLICE; k++) {
+                uint32_t c = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < SMALL_SLICE; j++) c += (j < len && j != k && r[j].x > r[k].x) ? 1u : 0u;
+                rk[k] = c;
+            }
+            double S = 0.0;
+#pragma unroll
+            for (uint32_t q = 0; q < SMALL_SLICE; q++) {  // q-th term of the sum = fitness of the member with rank q
+                if (q < len) {
+                    double t = 0.0;
+#pragma unroll
+                    for (uint32_t k = 0; k < SMALL_SLICE; k++) t = (k < len && rk[k] == q) ? f[k] : t;
+                    S += t;
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < SMALL_SLICE; k++) {
+                if (k < len) {
+                    if (rk[k] != k) rec[b + rk[k]] = r[k];
+                    if (!order_only) lam[b + rk[k]] = checked_lambda(st, f[k], R0, S);
+                    else if (rk[k] != k) lam[b + rk[k]] = f[k];
+                }
+            }
             continue;
         }
+        sort_slice_desc(rec, lam, b, e);
+        if (order_only) continue;
         double S = 0.0;
-        for (uint32_t a = b; a < e; a++) S += reproductive_fitness(st, s, rec[a].y);
-        for (uint32_t a = b; a < e; a++) lam[a] = checked_lambda(st, reproductive_fitness(st, s, rec[a].y), R0, S);
+        for (uint32_t a = b; a < e; a++) S += lam[a];
+        for (uint32_t a = b; a < e; a++) lam[a] = checked_lambda(st, lam[a], R0, S);
     }
 }
 
-// One CTA per heavy slice: normalised bitonic network on (index << 32 | haplotype) keys, larger index first
-// (missing partners beyond the slice end are no-ops), in shared memory when the slice fits, else in global
-// memory; then fitness in parallel, the sum strictly sequential in slice order, lambda in parallel.
-__global__ void __launch_bounds__(TPB) k_host_fitness_heavy(DevState *st, int order_only) {
-    extern __shared__ unsigned long long s_keys[];
+// One CTA per heavy slice: normalised bitonic network on (index << 32 | haplotype) keys with the fitness as
+// payload, larger index first (missing partners beyond the slice end are no-ops), in shared memory when the
+// slice fits, else in global memory; then the sum strictly sequential in slice order, lambda in parallel.
+__global__ void __launch_bounds__(TPB) k_host_lambda_heavy(DevState *st, int order_only) {
+    extern __shared__ unsigned long long s_dyn[];
     __shared__ double s_S;
+    unsigned long long *s_keys = s_dyn;
+    double *s_f = reinterpret_cast<double *>(s_dyn + SMEM_SORT_MAX);
     const uint32_t n_heavy = st->n_heavy;
     const double R0 = st->host_r0;
-    const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= st->H;
     for (uint32_t w = blockIdx.x; w < n_heavy; w += gridDim.x) {
         const uint32_t h = st->heavy_hosts[w];
         const uint32_t b = st->offsets[h], len = st->offsets[h + 1] - b;
-        unsigned long long *g = reinterpret_cast<unsigned long long *>(st->rec + b);  // uint2 {x = index, y = hap}: little endian u64 = y << 32 | x
+        unsigned long long *g = reinterpret_cast<unsigned long long *>(st->rec + b);  // uint2 {x = index, y = hap}: as u64 = y << 32 | x
+        double *gf = st->lam + b;
         const bool in_smem = len <= SMEM_SORT_MAX;
         unsigned long long *a = in_smem ? s_keys : g;
+        double *af = in_smem ? s_f : gf;
         // key = index << 32 | hap so that comparing keys compares indices
         for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
             const unsigned long long v = g[i];
             a[i] = (v << 32) | (v >> 32);
+            if (in_smem) af[i] = gf[i];
         }
         __syncthreads();
         uint32_t P = 1;
@@ -660,7 +736,7 @@ __global__ void __launch_bounds__(TPB) k_host_fitness_heavy(DevState *st, int or
                 uint32_t l = i ^ (k - 1);
                 if (l > i && l < len) {
                     unsigned long long x = a[i], y = a[l];
-                    if (x < y) { a[i] = y; a[l] = x; }
+                    if (x < y) { a[i] = y; a[l] = x; const double t = af[i]; af[i] = af[l]; af[l] = t; }
                 }
             }
             __syncthreads();
@@ -669,7 +745,7 @@ __global__ void __launch_bounds__(TPB) k_host_fitness_heavy(DevState *st, int or
                     uint32_t l = i ^ j;
                     if (l > i && l < len) {
                         unsigned long long x = a[i], y = a[l];
-                        if (x < y) { a[i] = y; a[l] = x; }
+                        if (x < y) { a[i] = y; a[l] = x; const double t = af[i]; af[i] = af[l]; af[l] = t; }
                     }
                 }
                 __syncthreads();
@@ -678,19 +754,15 @@ __global__ void __launch_bounds__(TPB) k_host_fitness_heavy(DevState *st, int or
         for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
             const unsigned long long v = a[i];
             g[i] = (v << 32) | (v >> 32);
+            if (in_smem) gf[i] = af[i];
         }
         __syncthreads();
         if (order_only) continue;
-        const int s = single ? 0 : find_spec(st, h);
-        double *lam = st->lam + b;
-        const uint2 *rec = st->rec + b;
-        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) lam[i] = reproductive_fitness(st, s, rec[i].y);
-        __syncthreads();
         if (threadIdx.x < 32) {  // lanes fetch 32 terms at a time, the additions stay strictly sequential
             const uint32_t lane = threadIdx.x;
             double S = 0.0;
             for (uint32_t a0 = 0; a0 < len; a0 += 32) {
-                const double f = (a0 + lane < len) ? lam[a0 + lane] : 0.0;
+                const double f = (a0 + lane < len) ? gf[a0 + lane] : 0.0;
                 const uint32_t cnt = min(32u, len - a0);
                 for (uint32_t t = 0; t < cnt; t++) S += __shfl_sync(0xFFFFFFFFu, f, t);
             }
@@ -698,15 +770,20 @@ __global__ void __launch_bounds__(TPB) k_host_fitness_heavy(DevState *st, int or
         }
         __syncthreads();
         const double S = s_S;
-        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) lam[i] = checked_lambda(st, lam[i], R0, S);
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) gf[i] = checked_lambda(st, gf[i], R0, S);
         __syncthreads();
     }
 }
 
 // offspring of the record at CSR position p ~ Poisson(lam[p]) (src/simulation.rs:148-152); one CTA per resample
 // tile so that the tile's offspring total comes out of the same pass.  replay_off is indexed by infectant.
+// SMALL_ONLY: every mean is below 12 (R0 < 12 and lambda = R0 * f/S <= R0), so the rejection sampler is not compiled in.
+template <bool SMALL_ONLY>
 __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t *__restrict__ replay_off) {
     __shared__ uint64_t s_red[TPB / 32];
+    __shared__ double s_rcp[POISSON_RCP];
+    poisson_rcp_init(s_rcp);
+    __syncthreads();
     const uint64_t m = st->n_sorted;
     const uint64_t n_tiles = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
     const double *__restrict__ lam = st->lam;
@@ -728,7 +805,8 @@ __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t 
             } else {
                 const double l = lam[p];
                 if (l > 0.0) {
-                    uint64_t v = poisson_draw(key, p, gen, PH_OFFSPRING, l);
+                    if (SMALL_ONLY && !(l < 12.0)) raise(st, DE_UNDEFINED_OFFSPRING);  // f > S: negative fitness values in the slice
+                    uint64_t v = poisson_draw<SMALL_ONLY>(key, p, gen, PH_OFFSPRING, l, s_rcp);
                     if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
                     off = (uint32_t)v;
                 }
@@ -843,6 +921,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
     __shared__ uint64_t s_carry;
     __shared__ uint64_t s_size, s_W;
     __shared__ int s_tree;
+    __shared__ double s_rcp[POISSON_RCP];
+    poisson_rcp_init(s_rcp);
+    if (threadIdx.x == 0) st->dbg[0] = vl_globaltimer();
     const uint64_t n = st->n;
     const uint64_t m = st->n_sorted;
     const uint64_t nt = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
@@ -872,6 +953,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
     }
     __syncthreads();
     const uint64_t size = s_size, W = s_W;
+    if (tid == 0) st->dbg[1] = vl_globaltimer();
     if (!force_tree) {
         const double sd = sqrt((double)size);
         double mu = (double)size - 5.0 * sd - 8.0;
@@ -880,11 +962,28 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
         for (uint64_t t = tid; t < nt; t += PLAN_THREADS) {
             const uint64_t w = st->tile_sum[t];
             uint64_t c = 0;
-            if (w > 0 && mu > 0.0) c = poisson_draw(key, t | ((uint64_t)salt << 48), gen, PH_PLAN, mu * ((double)w / (double)W));
+            if (w > 0 && mu > 0.0) c = poisson_draw(key, t | ((uint64_t)salt << 48), gen, PH_PLAN, mu * ((double)w / (double)W), s_rcp);  // stage 0
             cnt[t] = c;
             mine += c;
         }
-        const uint64_t K = plan_block_sum(mine, s_scan);
+        uint64_t K = plan_block_sum(mine, s_scan);
+        if (tid == 0) st->dbg[2] = vl_globaltimer();
+        // the deficit size - K is itself Poissonised (same argument, smaller means) until a handful of draws remain
+        for (uint32_t stage = 1; stage < 4 && K <= size && size - K > 64; stage++) {
+            const double d = (double)(size - K);
+            double mu2 = d - 5.0 * sqrt(d) - 8.0;
+            if (!(mu2 > 0.0)) break;
+            uint64_t add = 0;
+            for (uint64_t t = tid; t < nt; t += PLAN_THREADS) {
+                const uint64_t w = st->tile_sum[t];
+                if (w > 0) {
+                    const uint64_t c = poisson_draw(key, t | ((uint64_t)salt << 48) | ((uint64_t)stage << 40), gen, PH_PLAN, mu2 * ((double)w / (double)W), s_rcp);
+                    cnt[t] += c;
+                    add += c;
+                }
+            }
+            K += plan_block_sum(add, s_scan);
+        }
         if (K > size) {
             if (tid == 0) s_tree = 1;
         } else {
@@ -933,7 +1032,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
         for (uint64_t t = tid; t < nt; t += PLAN_THREADS) cnt[t] = ncnt[P + t];
         __syncthreads();
     }
+    if (tid == 0) st->dbg[3] = vl_globaltimer();
     plan_block_scan(cnt, st->tile_base, nt, false, s_scan, &s_carry);
+    if (tid == 0) st->dbg[4] = vl_globaltimer();
 }
 
 // One CTA per tile of CSR positions.  The tile's records with offspring > 0 are compacted into shared memory as
@@ -1145,11 +1246,11 @@ __global__ void __launch_bounds__(TPB) k_extract_hosts(DevState *st, uint32_t *_
     const uint64_t m = st->n_sorted;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (uint64_t)gridDim.x * blockDim.x) dst[p] = st->rec[p].x;
 }
-// per-infectant replication terms for inspection: mapped fitness, host sum and lambda exactly as
-// BasicHost::replicate forms them (outputs pre-filled with NaN for uninfected infectants); ordered slices required
+// per-infectant replication terms for inspection: mapped fitness and host sum as BasicHost::replicate forms them,
+// lambda as the replicate kernels left it at the record's CSR position (0.0 where Poisson::new fails); outputs are
+// pre-filled with NaN for uninfected infectants; ordered slices required
 __global__ void __launch_bounds__(TPB) k_replication_terms(DevState *st, double *fit_out, double *hs_out, double *lam_out) {
     const uint64_t H = st->H;
-    const double R0 = st->host_r0;
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t b = st->offsets[h], e = st->offsets[h + 1];
         if (e == b) continue;
@@ -1161,7 +1262,7 @@ __global__ void __launch_bounds__(TPB) k_replication_terms(DevState *st, double 
             const uint32_t i = st->rec[a].x;
             fit_out[i] = f;
             hs_out[i] = S;
-            lam_out[i] = f * R0 / S;
+            lam_out[i] = st->lam[a];
         }
     }
 }
@@ -1172,8 +1273,11 @@ __global__ void __launch_bounds__(TPB) k_gather_raw(DevState *st, uint32_t provi
 
 // sampler test hooks (distribution tests of the device samplers the kernels above call)
 __global__ void k_test_poisson(uint64_t seed, double lambda, uint64_t n, uint64_t *out) {
+    __shared__ double s_rcp[POISSON_RCP];
+    poisson_rcp_init(s_rcp);
+    __syncthreads();
     const PhiloxKey key = philox_key(seed, 0);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = poisson_draw(key, i, 0, PH_TEST, lambda);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = poisson_draw(key, i, 0, PH_TEST, lambda, s_rcp);
 }
 __global__ void k_test_binomial(uint64_t seed, uint64_t nn, double p, uint64_t n, uint64_t *out, BinvConst c) {
     const PhiloxKey key = philox_key(seed, 0);

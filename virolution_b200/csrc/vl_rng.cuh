@@ -216,22 +216,9 @@ __host__ __device__ inline int weighted4(Philox &g, const double *w) {
 
 
 // ---- hot-path samplers: one Philox block per decision wherever possible -------------------------------------
-// Poisson(lambda), exact.  lambda < 12: inversion of ONE uniform (words x,y of block 0) by sequential search —
-// same law as rand_distr 0.5.1's Knuth product branch at a fraction of the random words.  Otherwise PTRS
-// (Hoermann 1993) with one block per attempt (same law as rand_distr's rejection branch).
-__device__ __forceinline__ uint64_t poisson_draw(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, double lambda) {
-    if (lambda < 12.0) {
-        const uint4 b = philox_block(key, index, generation, phase, 0);
-        const double u = u01_from(b.x, b.y);
-        double p = exp(-lambda), cdf = p;
-        uint32_t k = 0;
-        while (u >= cdf && k < 256) {
-            k += 1;
-            p = p * lambda / (double)k;
-            cdf += p;
-        }
-        return k;
-    }
+// Poisson(lambda >= 12): PTRS transformed rejection (Hoermann 1993), one block per attempt (same law as
+// rand_distr 0.5.1's rejection branch).
+__device__ __noinline__ uint64_t poisson_ptrs(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, double lambda) {
     const double slam = sqrt(lambda);
     const double bb = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * bb;
     const double vr = 0.9277 - 3.6224 / (bb - 2.0);
@@ -246,11 +233,38 @@ __device__ __forceinline__ uint64_t poisson_draw(PhiloxKey key, uint64_t index, 
         if (log(v) + log(invalpha) - log(a / (us * us) + bb) <= -lambda + k * log(lambda) - lgamma(k + 1.0)) return (uint64_t)k;
     }
 }
+// Poisson(lambda), exact.  lambda < 12: inversion of ONE uniform (words x,y of block 0) by sequential search —
+// same law as rand_distr 0.5.1's Knuth product branch at a fraction of the random words.  `rcp` is a table of
+// 1/k for k < POISSON_RCP (the term ratio lambda/k as a multiplication; distribution unchanged to 1 ulp of a term).
+constexpr int POISSON_RCP = 64;
+template <bool SMALL_ONLY = false>
+__device__ __forceinline__ uint64_t poisson_draw(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, double lambda,
+                                                 const double *rcp) {
+    if (SMALL_ONLY || lambda < 12.0) {
+        const uint4 b = philox_block(key, index, generation, phase, 0);
+        const double u = u01_from(b.x, b.y);
+        double p = exp(-lambda), cdf = p;
+        uint32_t k = 0;
+        while (u >= cdf && k < 256) {
+            k += 1;
+            p = (k < POISSON_RCP) ? p * (lambda * rcp[k]) : p * lambda / (double)k;
+            cdf += p;
+        }
+        return k;
+    }
+    if (SMALL_ONLY) return 0;
+    return poisson_ptrs(key, index, generation, phase, lambda);
+}
+// fills a CTA's shared reciprocal table (call by all threads, then __syncthreads())
+__device__ __forceinline__ void poisson_rcp_init(double *rcp) {
+    for (int k = threadIdx.x; k < POISSON_RCP; k += blockDim.x) rcp[k] = k ? 1.0 / (double)k : 0.0;
+}
 
 // Binomial(n, p) in the small-mean regime n*p < 10 with host-precomputed constants q^n, s = p/q, a = (n+1)s:
 // inversion of one uniform (the BINV branch of rand_distr 0.5.1).  `u` is consumed; a restart (k beyond the
 // search bound, probability < 1e-100) draws from the stream's later blocks.
-struct BinvConst { double qn, s, a; uint64_t n; int ok; };
+constexpr int BINV_STEPS = 16;
+struct BinvConst { double qn, s, a; uint64_t n; int ok; double step[BINV_STEPS]; /* a/k - s for k < BINV_STEPS */ };
 __host__ inline BinvConst make_binv(uint64_t n, double p) {
     BinvConst c;
     c.n = n;
@@ -259,6 +273,7 @@ __host__ inline BinvConst make_binv(uint64_t n, double p) {
     c.qn = c.ok ? exp((double)n * log1p(-p)) : 0.0;
     c.s = p / q;
     c.a = ((double)n + 1.0) * c.s;
+    for (int k = 0; k < BINV_STEPS; k++) c.step[k] = k ? c.a / (double)k - c.s : 0.0;
     return c;
 }
 __device__ __forceinline__ uint32_t binv_draw(const BinvConst &c, double u, PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase) {
@@ -270,7 +285,7 @@ __device__ __forceinline__ uint32_t binv_draw(const BinvConst &c, double u, Phil
             u -= r;
             k += 1;
             if (k > 200 || k > c.n) break;
-            r *= c.a / (double)k - c.s;
+            r *= (k < (uint32_t)BINV_STEPS) ? c.step[k] : c.a / (double)k - c.s;
         }
         if (k <= 200 && k <= c.n) return k;
         const uint4 b = philox_block(key, index, generation, phase, blk++);

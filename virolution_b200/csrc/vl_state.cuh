@@ -56,6 +56,7 @@ struct DevProvider {
     int32_t kind;  // vl_fitness_kind
     int32_t util_kind;
     double upper, hill_k, hill_n;
+    double alg_factor, alg_uf;  // Algebraic: factor = 1/(upper-1) and upper*factor, rounded exactly as the reference forms them
     const double *table;  // L*4
     const EpiDir *epi;    // sorted by (k1, k2), duplicates resolved (last insert wins)
     uint32_t n_epi;
@@ -135,6 +136,7 @@ struct DevState {
     uint64_t gc_hap_threshold, gc_arena_threshold;
     uint64_t gc_runs;
     uint64_t kernels_launched;  // maintained by the host, mirrored here for export
+    uint64_t dbg[8];            // %globaltimer stamps of the plan kernel's phases (profiling aid)
 };
 
 // ---- entry helpers ---------------------------------------------------------------------------------
@@ -168,8 +170,8 @@ __host__ __device__ inline uint32_t entries_get_mut(const uint32_t *e, uint32_t 
 // UtilityFunction::apply (src/core/fitness/utility.rs:48-60); same operation order as written there
 __host__ __device__ inline double utility_apply(const DevProvider &p, double f) {
     if (p.util_kind == VL_UTILITY_ALGEBRAIC) {
-        double factor = 1. / (p.upper - 1.);
-        return p.upper * factor * f / (1. + factor * f);
+        // let factor = 1. / (upper - 1.); upper * factor * f / (1. + factor * f): the two leading terms are constants
+        return p.alg_uf * f / (1. + p.alg_factor * f);
     }
     if (p.util_kind == VL_UTILITY_HILL) {
         double fp = pow(f, p.hill_n);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "vl_timer_stop": (C.c_int, [_vp, f64p]),
     "vl_profile": (C.c_int, [_vp, C.c_int]),
     "vl_profile_report": (C.c_int, [_vp, C.c_char_p, C.c_uint64]),
+    "vl_debug_stamps": (C.c_int, [_vp, u64p]),
     "vl_test_poisson": (C.c_int, [C.c_uint64, C.c_double, C.c_uint64, u64p]),
     "vl_test_binomial": (C.c_int, [C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, u64p]),
     "vl_test_below": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, u64p]),
@@ -295,6 +296,11 @@ class GpuSimulation:
         for line in buf.value.decode().splitlines():
             name, cnt, ms = line.rsplit(" ", 2)
             out[name] = (int(cnt), float(ms))
+        return out
+
+    def debug_stamps(self) -> np.ndarray:
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self.lib.vl_debug_stamps(self.ptr, _p(out, C.c_uint64)))
         return out
 
     def infectant_generations(self, reset: bool = False) -> int:
