@@ -115,6 +115,9 @@ typedef struct vl_config {
 } vl_config;
 
 enum {
+    VL_FLAG_NO_BUCKETS = 4, /* build the host map with one histogram atomic per infectant instead of the
+                               bucket-partitioned counting sort (same result; the bucketed path needs uniform host
+                               draws and H >= 65536, this flag lets tests compare the two) */
     VL_FLAG_TREE_PLAN = 2 /* split the resampling draws over tiles with the conditional-binomial tree instead of
                              Poissonisation (both exact; the tree is the rare-case fallback, this flag lets tests
                              exercise it) */

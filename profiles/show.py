@@ -2,7 +2,7 @@
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print({k: d[k] for k in ['value', 'ms_per_step', 'gpu_launches'] if k in d})
-print('e2e', d.get('e2e', {}).get('value'), 'clocks', d.get('clocks'))
+print('e2e', (d.get('e2e') or {}).get('value'), 'clocks', d.get('clocks'))
 r = d.get('roofline') or {}
 print('roofline', {k: r.get(k) for k in ('kernel', 'achieved', 'frac')}, 'group', r.get('fitness_replication_group'))
 tot = 0

@@ -220,3 +220,33 @@ def test_replicates_agree_in_distribution_with_oracle(name):
             continue
         p = stats.ks_2samp(ro[:, k], rg[:, k]).pvalue
         assert p > alpha, f"column {k}: KS p={p:.2e} (oracle mean {ro[:, k].mean():.4g}, gpu mean {rg[:, k].mean():.4g})"
+
+
+def test_bucketed_host_map_equals_atomic_host_map():
+    """The bucket-partitioned counting sort (default for uniform host draws, H >= 65536) and the one-atomic-per-
+    infectant histogram (VL_FLAG_NO_BUCKETS) must build the same host map and drive identical generations."""
+    c = big_singlehost(n=300000, mu=1e-4, seed=21)
+    a = helpers.make_gpu(c)
+    b = helpers.make_gpu(c, flags=abi.VL_FLAG_NO_BUCKETS)
+    for g in (a, b):
+        g.increment_generation()
+        g.infect()
+    assert np.array_equal(a.get_infections(), b.get_infections())
+    oa, ha = a.get_host_map()
+    ob, hb = b.get_host_map()
+    assert np.array_equal(oa, ob) and np.array_equal(ha, hb)
+    inf = a.get_infections()
+    assert oa[-1] == c["n0"] and np.array_equal(np.bincount(inf, minlength=c["n0"]), np.diff(oa.astype(np.int64)))
+    for g in (a, b):  # phase by phase: mutate patches the CSR records
+        g.mutate_infectants()
+        g.replicate_infectants(to_host=False)
+        g.set_population(g.subsample_population(None, 1.0))
+    assert population_signature(a) == population_signature(b)
+    for g in (a, b):  # fused: mutate patches the bucket-partitioned records before the host map exists
+        g.run(3)
+    sa, sb = population_signature(a), population_signature(b)
+    assert sa == sb
+    assert np.array_equal(a.get_raw_fitness().view(np.uint64), b.get_raw_fitness().view(np.uint64))
+    assert len(set(sa)) > 100
+    a.close()
+    b.close()

@@ -64,6 +64,7 @@ struct vl_sim {
     bool slices_ordered = false;  // ... and every slice is in the reference's descending order
     bool layout_valid = false;    // rec/offspring/tile_sum describe an offspring map (host map or identity layout)
     bool mutcounts_ready = false; // the fused infect pass already filled the mutation worklist
+    bool bucket_pending = false;  // records are bucket-partitioned, the host map is not built yet
     uint32_t plan_smem_tiles = 0;
     uint32_t salt = 0;        // distinguishes the sampling streams of one generation
     uint32_t gens_since_gc = 0, gc_period = 1;
@@ -88,6 +89,7 @@ static cudaEvent_t prof_begin(vl_sim *sim, const char *name) {
 
 static thread_local char g_create_err[512];
 constexpr int PIN_SLOTS = 4096;
+constexpr int BSORT_SMEM_BYTES = BUCKET_HOSTS * 4 + BSORT_SMEM_RECS * 10;
 
 static int fail(vl_sim *sim, int code, const char *fmt, ...) {
     va_list ap;
@@ -174,6 +176,7 @@ static int check_device_error(vl_sim *sim) {
     if (e & DE_SAME_BASE) return fail(sim, VL_ERR_REFERENCE_PANIC, "assert_ne!(from, to) in create_descendant (src/core/haplotype.rs:250)");
     if (e & DE_OFFSPRING_RANGE) return fail(sim, VL_ERR_IMPLEMENTATION, "offspring count does not fit 32 bits");
     if (e & DE_REPLAY) return fail(sim, VL_ERR_ARGUMENT, "malformed replay log or index out of range");
+    if (e & DE_BUCKET_OVERFLOW) return fail(sim, VL_ERR_IMPLEMENTATION, "host bucket overflow (12 sigma event): rerun with VL_FLAG_NO_BUCKETS");
     return fail(sim, VL_ERR_IMPLEMENTATION, "unknown device error 0x%x", e);
 }
 
@@ -201,9 +204,24 @@ static int launch_scan(vl_sim *sim, const uint32_t *in, OutT *out, const uint64_
 // ---------------------------------------------------------------------------------------------- buffers
 static void free_population_buffers(vl_sim *sim) {
     DevState &h = sim->h;
-    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.rec, h.heavy_hosts, h.mut_list, h.lam, h.offspring,
-                    h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_node, h.tile_base, sim->stage64};
+    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.rec, h.heavy_hosts, h.medium_hosts, h.mut_list, h.lam, h.hs, h.offspring,
+                    h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_node, h.tile_base, sim->stage64, h.tmp_rec};
     for (void *p : olds) if (p) cudaFree(p);
+    h.tmp_rec = nullptr;
+}
+static bool buckets_possible(const vl_sim *sim) {
+    const DevState &h = sim->h;
+    return h.fast_infect && h.H >= 4 * (uint64_t)BUCKET_HOSTS && h.n_buckets <= (uint32_t)MAX_BUCKETS && !(sim->flags & VL_FLAG_NO_BUCKETS);
+}
+static int alloc_bucket_buffers(vl_sim *sim) {
+    DevState &h = sim->h;
+    if (h.tmp_rec) cudaFree(h.tmp_rec);
+    h.tmp_rec = nullptr;
+    h.cap_tmp = 0;
+    if (!buckets_possible(sim)) return VL_OK;
+    h.cap_tmp = (uint64_t)h.n_buckets * bucket_stride(h.cap_inf, h.H) + 64;
+    TRY(dev_alloc(sim, &h.tmp_rec, h.cap_tmp, false));
+    return VL_OK;
 }
 static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     DevState &h = sim->h;
@@ -217,8 +235,10 @@ static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     TRY(dev_alloc(sim, &h.rank, cap + 4, false));
     TRY(dev_alloc(sim, &h.rec, cap + 4, false));
     TRY(dev_alloc(sim, &h.heavy_hosts, cap / THREAD_TIER + 1, false));
+    TRY(dev_alloc(sim, &h.medium_hosts, cap / 5 + 1, false));
     TRY(dev_alloc(sim, &h.mut_list, cap + 4, false));
     TRY(dev_alloc(sim, &h.lam, cap + 4, false));
+    TRY(dev_alloc(sim, &h.hs, cap + 4, false));
     TRY(dev_alloc(sim, &h.offspring, cap + 4, false));
     TRY(dev_alloc(sim, &h.tile_sum, nt, false));
     TRY(dev_alloc(sim, &h.tile_tree, 2 * P, false));
@@ -227,6 +247,7 @@ static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     TRY(dev_alloc(sim, &h.tile_base, nt, false));
     TRY(dev_alloc(sim, &sim->stage64, cap + 4, false));
     h.cap_inf = cap;
+    TRY(alloc_bucket_buffers(sim));
     return VL_OK;
 }
 // push the host mirror's population pointers/capacity into the device state
@@ -236,9 +257,10 @@ static int push_population_pointers(vl_sim *sim) {
     CU(sim, cudaMemcpy(&tmp, sim->d, sizeof(DevState), cudaMemcpyDeviceToHost));
     const DevState &h = sim->h;
     tmp.hap_id = h.hap_id; tmp.hap_id_next = h.hap_id_next; tmp.host_id = h.host_id; tmp.rank = h.rank; tmp.rec = h.rec;
-    tmp.heavy_hosts = h.heavy_hosts; tmp.mut_list = h.mut_list; tmp.lam = h.lam; tmp.offspring = h.offspring;
+    tmp.heavy_hosts = h.heavy_hosts; tmp.medium_hosts = h.medium_hosts; tmp.mut_list = h.mut_list; tmp.lam = h.lam; tmp.hs = h.hs; tmp.offspring = h.offspring;
     tmp.tile_sum = h.tile_sum; tmp.tile_tree = h.tile_tree; tmp.tile_cnt = h.tile_cnt; tmp.tile_node = h.tile_node; tmp.tile_base = h.tile_base;
     tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.H = h.H; tmp.fast_infect = h.fast_infect;
+    tmp.n_buckets = h.n_buckets; tmp.tmp_rec = h.tmp_rec; tmp.cap_tmp = h.cap_tmp;
     CU(sim, cudaMemcpy(sim->d, &tmp, sizeof(DevState), cudaMemcpyHostToDevice));
     return VL_OK;
 }
@@ -251,10 +273,20 @@ static int alloc_host_buffers(vl_sim *sim, uint64_t H) {
     sim->cap_H = H;
     return VL_OK;
 }
+// every host belongs to a spec, no spec has an infective provider and n_hits == 1: each draw infects its host
+// (src/simulation.rs:56-65 degenerates to one Uniform(0, H) draw), so hosts are uniform over [0, H)
 static void update_fast_infect(vl_sim *sim) {
     DevState &h = sim->h;
-    bool fast = h.n_specs == 1 && h.specs[0].lo == 0 && h.specs[0].hi >= h.H && h.specs[0].infect < 0 && h.n_hits == 1 && h.H > 0;
+    bool fast = h.n_hits == 1 && h.H > 0;
+    uint64_t covered = 0;  // specs in ascending order must tile [0, H)
+    for (uint32_t s = 0; s < h.n_specs && fast; s++) {
+        if (h.specs[s].infect >= 0) fast = false;
+        if (h.specs[s].lo > covered) fast = false;
+        covered = std::max<uint64_t>(covered, h.specs[s].hi);
+    }
+    if (covered < h.H) fast = false;
     h.fast_infect = fast ? 1u : 0u;
+    h.n_buckets = (uint32_t)std::min<uint64_t>((h.H + BUCKET_HOSTS - 1) >> BUCKET_SHIFT, 0xFFFFFFFFull);
 }
 
 static int add_provider(vl_sim *sim, const vl_fitness *f, uint64_t L, int *index_out) {
@@ -406,7 +438,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
         size_t free_b = 0, total_b = 0;
         CCU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t P = std::max<uint32_t>(h.n_providers, 1);
-        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 72 + ch * (52 + 16 * P) + ca * 8; };
+        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 80 + ch * (52 + 16 * P) + ca * 8; };
         if (!cfg->capacity_haplotypes || !cfg->capacity_arena_words) {
             for (int it = 0; it < 64 && need(cap_hap, cap_arena) > (uint64_t)(0.7 * (double)free_b); it++) {
                 if (!cfg->capacity_arena_words && cap_arena > (1ull << 20)) cap_arena = cap_arena * 3 / 4;
@@ -423,15 +455,16 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     update_fast_infect(sim);
     h.binv = make_binv(L, par.mutation_rate);
     CCU(cudaFuncSetAttribute(k_plan_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CCU(cudaFuncSetAttribute(k_host_lambda_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
+    CCU(cudaFuncSetAttribute(k_host_sum_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
     sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
     h.gc_arena_threshold = cap_arena / 2;
+    CTRY(dev_alloc(sim, &h.bucket_fill, MAX_BUCKETS + 1));
+    CTRY(dev_alloc(sim, &h.bucket_pos, MAX_BUCKETS + 2));
+    CCU(cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
-    CTRY(dev_alloc(sim, &h.h_off, cap_hap)); CTRY(dev_alloc(sim, &h.h_off_alt, cap_hap));
-    CTRY(dev_alloc(sim, &h.h_len, cap_hap)); CTRY(dev_alloc(sim, &h.h_len_alt, cap_hap));
-    CTRY(dev_alloc(sim, &h.h_parent, cap_hap)); CTRY(dev_alloc(sim, &h.h_parent_alt, cap_hap));
+    CTRY(dev_alloc(sim, &h.hm, cap_hap)); CTRY(dev_alloc(sim, &h.hm_alt, cap_hap));
     for (uint32_t p = 0; p < h.n_providers; p++) { CTRY(dev_alloc(sim, &h.h_raw[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_raw_alt[p], cap_hap)); }
     CTRY(dev_alloc(sim, &h.arena, cap_arena)); CTRY(dev_alloc(sim, &h.arena_alt, cap_arena));
     CTRY(dev_alloc(sim, &h.gc_mark, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_newid, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_len, cap_hap + 1));
@@ -444,10 +477,9 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     h.n_hap = 1;
     h.arena_top = 0;
     {
-        uint64_t zero64 = 0; uint32_t zero32 = 0, none = NONE32; double one = 1.0;
-        CCU(cudaMemcpy(h.h_off, &zero64, 8, cudaMemcpyHostToDevice));
-        CCU(cudaMemcpy(h.h_len, &zero32, 4, cudaMemcpyHostToDevice));
-        CCU(cudaMemcpy(h.h_parent, &none, 4, cudaMemcpyHostToDevice));
+        const double one = 1.0;
+        HapMeta wt{0, 0, NONE32};
+        CCU(cudaMemcpy(h.hm, &wt, sizeof(HapMeta), cudaMemcpyHostToDevice));
         for (uint32_t p = 0; p < h.n_providers; p++) CCU(cudaMemcpy(h.h_raw[p], &one, 8, cudaMemcpyHostToDevice));
     }
     CTRY(dev_alloc(sim, &sim->d, 1));
@@ -516,8 +548,10 @@ VL_API int vl_set_parameters(vl_sim *sim, const vl_parameters *p) {
     TRY(write_field(sim, FIELD_OFF(max_population), (uint64_t)p->max_population));
     h.n_hits = p->n_hits; h.dilution = p->dilution; h.max_population = p->max_population;
     update_fast_infect(sim);
-    TRY(write_field(sim, FIELD_OFF(fast_infect), h.fast_infect));
+    TRY(alloc_bucket_buffers(sim));
+    TRY(push_population_pointers(sim));
     sim->csr_valid = false;
+    sim->bucket_pending = false;
     return VL_OK;
 }
 static int population_len(vl_sim *sim, uint64_t *out) {
@@ -563,8 +597,10 @@ static int ensure_ordered_slices(vl_sim *sim) {
     if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no host map: call vl_infect first");
     if (sim->slices_ordered) return VL_OK;
     TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
-    LAUNCH(sim, k_host_lambda, grid_for(sim, sim->h.H), TPB, 0, sim->d, 1);
-    LAUNCH(sim, k_host_lambda_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 1);
+    TRY(zero_field32(sim, FIELD_OFF(n_medium)));
+    LAUNCH(sim, k_host_sum, grid_for(sim, sim->h.H), TPB, 0, sim->d, 1);
+    LAUNCH(sim, k_host_sum_medium, grid_for(sim, sim->n_bound / 5 + 1, 2), TPB, 0, sim->d, 1);
+    LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 1);
     sim->slices_ordered = true;
     return VL_OK;
 }
@@ -582,12 +618,39 @@ static int enqueue_host_map(vl_sim *sim) {
 }
 // defer_host_map: the fused generation mutates first (the mutation worklist comes out of the infect pass) and
 // builds the host map from the already-mutated population, so no record needs patching afterwards
+static int enqueue_bucket_host_map(vl_sim *sim) {
+    const DevState &h = sim->h;
+    LAUNCH(sim, k_bucket_offsets, 1, MAX_BUCKETS / 2, 0, sim->d);
+    LAUNCH(sim, k_bucket_sort, std::min<unsigned>(h.n_buckets, sim->n_sms), BSORT_TPB, BSORT_SMEM_BYTES, sim->d);
+    sim->bucket_pending = false;
+    sim->csr_valid = true;
+    sim->slices_ordered = false;
+    sim->layout_valid = false;
+    return VL_OK;
+}
 static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
     const DevState &h = sim->h;
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec;
     const bool fuse = !replay && h.binv.ok;
     const bool fast = h.fast_infect != 0;
     LAUNCH(sim, k_begin_phase, 1, 1, 0, sim->d);
+    sim->bucket_pending = false;
+    if (!replay && buckets_possible(sim) && h.cap_tmp >= (uint64_t)h.n_buckets * bucket_stride(sim->n_bound, h.H)) {
+        CU(sim, cudaMemsetAsync(h.bucket_fill, 0, (MAX_BUCKETS + 1) * 4, sim->stream));
+        const unsigned chunks = (unsigned)std::max<uint64_t>(1, (sim->n_bound + BUCKET_CHUNK - 1) / BUCKET_CHUNK);
+        const unsigned g = chunks;  // one chunk per CTA: the hardware scheduler balances the tail
+        if (fuse) LAUNCH(sim, k_infect_bucket<true>, g, BUCKET_TPB, 0, sim->d);
+        else LAUNCH(sim, k_infect_bucket<false>, g, BUCKET_TPB, 0, sim->d);
+        sim->mutcounts_ready = fuse;
+        sim->csr_valid = false;
+        sim->slices_ordered = false;
+        sim->layout_valid = false;
+        sim->bucket_pending = true;
+        if (defer_host_map && fuse && !(h.host_recombination_rate > 0.0)) return VL_OK;
+        TRY(enqueue_bucket_host_map(sim));
+        if (h.host_recombination_rate > 0.0) TRY(ensure_ordered_slices(sim));
+        return VL_OK;
+    }
     CU(sim, cudaMemsetAsync(sim->count, 0, (h.H + 2) * 4, sim->stream));
     const unsigned g = grid_for(sim, (sim->n_bound + INFECT_ITEMS - 1) / INFECT_ITEMS);
     const int64_t *rp = sim->has_rp_inf ? sim->rp_inf : nullptr;
@@ -625,27 +688,30 @@ static int enqueue_mutate(vl_sim *sim) {
         return VL_OK;
     }
     if (sim->has_rp_mut || !sim->mutcounts_ready) {
+        if (sim->bucket_pending) TRY(enqueue_bucket_host_map(sim));
         if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "mutate needs the infections: call vl_infect first");
         TRY(zero_field32(sim, FIELD_OFF(n_mut_list)));
         LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : 0);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0));
     sim->mutcounts_ready = false;
     sim->has_rp_mut = false;
     sim->has_rp_rec = false;
     return VL_OK;
 }
-static int enqueue_replicate(vl_sim *sim) {
+static int enqueue_replicate(vl_sim *sim, int store_lambda = 1) {
     const DevState &h = sim->h;
     if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "replicate needs the host map: call vl_infect first");
     TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
+    TRY(zero_field32(sim, FIELD_OFF(n_medium)));
     LAUNCH(sim, k_fitness, grid_for(sim, sim->n_bound), TPB, 0, sim->d);
-    LAUNCH(sim, k_host_lambda, grid_for(sim, h.H), TPB, 0, sim->d, 0);
-    LAUNCH(sim, k_host_lambda_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 0);
+    LAUNCH(sim, k_host_sum, grid_for(sim, h.H), TPB, 0, sim->d, 0);
+    LAUNCH(sim, k_host_sum_medium, grid_for(sim, sim->n_bound / 5 + 1, 2), TPB, 0, sim->d, 0);
+    LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 0);
     sim->slices_ordered = true;
     const uint64_t *rpo = sim->has_rp_off ? sim->rp_off : nullptr;
-    if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring<true>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo);
-    else LAUNCH(sim, k_offspring<false>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo);
+    if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring<true>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo, store_lambda);
+    else LAUNCH(sim, k_offspring<false>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo, store_lambda);
     sim->has_rp_off = false;
     sim->layout_valid = true;
     return VL_OK;
@@ -970,8 +1036,8 @@ static int enqueue_generation(vl_sim *sim) {
     sim->salt = 0;
     TRY(enqueue_infect(sim, true));
     TRY(enqueue_mutate(sim));
-    if (!sim->csr_valid) TRY(enqueue_host_map(sim));
-    TRY(enqueue_replicate(sim));
+    if (!sim->csr_valid) TRY(sim->bucket_pending ? enqueue_bucket_host_map(sim) : enqueue_host_map(sim));
+    TRY(enqueue_replicate(sim, 0));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
     swap_population(sim);
     sim->n_valid = false;

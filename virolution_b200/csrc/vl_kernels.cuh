@@ -5,7 +5,7 @@
 //                         (+ the Binomial(L, mu) mutation count of BasicHost::mutate, :94-95, fused: the count
 //                         depends only on (seed, generation, infectant), not on the phase that draws it)
 //   scan, k_scatter       HostMapBuffer::build (counting sort, back-fill)         src/core/hosts.rs:166-192
-//   k_fitness, k_host_lambda[_heavy]  the descending in-host order that back-fill produces, then
+//   k_fitness, k_host_sum[_heavy]  the descending in-host order that back-fill produces, then
 //                         BasicHost::replicate's fitness, per-host sum and lambda  src/simulation.rs:120-147
 //   k_recombine           BasicHost::mutate, recombination part                   src/simulation.rs:68-90
 //   k_mutation_counts,    BasicHost::mutate, mutation part + create_descendant    src/simulation.rs:93-117,
@@ -33,7 +33,6 @@ constexpr int TPB = 256;
 constexpr uint32_t THREAD_TIER = 32;      // slices up to this length are handled by one thread
 constexpr uint32_t SMEM_SORT_MAX = 4096;  // slices up to this length are sorted in shared memory (u64 keys)
 constexpr int INFECT_ITEMS = 4;           // infectants per thread and round in k_infect / k_scatter
-constexpr uint32_t SMALL_SLICE = 6;       // slices up to this length are ordered and summed in registers
 
 __device__ __forceinline__ void raise(DevState *st, uint32_t bit) { atomicOr(&st->error, bit); }
 __device__ __forceinline__ uint64_t vl_globaltimer() {
@@ -80,6 +79,7 @@ __global__ void k_tick(DevState *st) {  // Simulation::increment_generation (src
 __global__ void k_begin_phase(DevState *st) {
     st->n_mut_list = 0;
     st->n_heavy = 0;
+    st->n_medium = 0;
 }
 
 // ------------------------------------------------------------------------------------------ infect
@@ -94,7 +94,7 @@ __device__ __noinline__ uint32_t infect_general(const DevState *st, uint64_t i, 
         if (s < 0) continue;
         double infectivity = 1.;
         int pi = st->specs[s].infect;
-        if (pi >= 0) infectivity = utility_apply(st->prov[pi], st->h_raw[pi][st->hap_id[i]]);
+        if (pi >= 0) infectivity = utility_apply(st->prov[pi], hap_raw(st, pi, st->hap_id[i]));
         if (g.u01() < infectivity) return (uint32_t)cand;
     }
     return NONE32;
@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t mutation_count(const DevState *st, PhiloxKey
 
 // append (infectant, n_mut) for every item with n_mut > 0: one global atomic per CTA and round
 template <int ITEMS>
-__device__ __forceinline__ void worklist_append(DevState *st, const uint64_t (&idx)[ITEMS], const uint32_t (&nm)[ITEMS]) {
+__device__ __forceinline__ void worklist_append(DevState *st, const uint64_t (&idx)[ITEMS], const uint32_t (&nm)[ITEMS], const uint32_t (&pos)[ITEMS]) {
     __shared__ uint32_t s_base;
     uint32_t mine = 0;
 #pragma unroll
@@ -135,7 +135,7 @@ __device__ __forceinline__ void worklist_append(DevState *st, const uint64_t (&i
         uint32_t o = s_base + off;
 #pragma unroll
         for (int e = 0; e < ITEMS; e++)
-            if (nm[e]) st->mut_list[o++] = make_uint2((uint32_t)idx[e], nm[e]);
+            if (nm[e]) st->mut_list[o++] = make_uint4((uint32_t)idx[e], nm[e], pos[e], 0u);
     }
     __syncthreads();
 }
@@ -199,7 +199,224 @@ __global__ void __launch_bounds__(TPB) k_infect(DevState *st, uint32_t *__restri
             for (int e = 0; e < INFECT_ITEMS; e++)
                 if (i0 + e < n) { host_id[i0 + e] = h[e]; rank[i0 + e] = rk[e]; }
         }
-        if (FUSE_MUT) worklist_append<INFECT_ITEMS>(st, idx, nm);
+        if (FUSE_MUT) {
+            const uint32_t none[INFECT_ITEMS] = {NONE32, NONE32, NONE32, NONE32};
+            worklist_append<INFECT_ITEMS>(st, idx, nm, none);
+        }
+    }
+}
+
+// ---- bucketed variant (uniform host draws only: DevState::fast_infect) --------------------------------------
+// Instead of a histogram atomic per infectant on H counters spread over HBM, the record (index, haplotype, host)
+// is appended to the region of its host bucket (BUCKET_HOSTS consecutive hosts).  A CTA handles a chunk of
+// BUCKET_CHUNK infectants per round: ranks inside the chunk come from a shared-memory histogram over the buckets,
+// one global atomic per (chunk, bucket) reserves the run.  Every bucket region is an append-only stream, so the
+// scattered 4-byte stores merge in L2 and reach HBM as full sectors.
+constexpr int BUCKET_TPB = 1024;
+constexpr int BUCKET_ITEMS = 8;
+constexpr int BUCKET_CHUNK = BUCKET_TPB * BUCKET_ITEMS;
+constexpr int MAX_BUCKETS = 2048;
+
+template <bool FUSE_MUT>
+__global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
+    __shared__ uint32_t s_hist[MAX_BUCKETS];   // per-chunk count, then global base of the chunk's run per bucket
+    __shared__ uint32_t s_w[BUCKET_TPB / 32];
+    __shared__ uint32_t s_lbase;
+    const uint64_t n = st->n;
+    const uint32_t H32 = (uint32_t)st->H;
+    const uint32_t gen = st->generation;
+    const uint32_t B = st->n_buckets;
+    const uint64_t stride = bucket_stride(n, st->H);
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    uint32_t *__restrict__ host_id = st->host_id;
+    const uint32_t *__restrict__ hap_id = st->hap_id;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->infectant_generations += n;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t n_chunks = (n + BUCKET_CHUNK - 1) / BUCKET_CHUNK;
+    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        for (uint32_t b = tid; b < B; b += BUCKET_TPB) s_hist[b] = 0;
+        __syncthreads();
+        // coalesced layout: item e of thread t is infectant chunk*CHUNK + e*TPB + t
+        uint32_t h[BUCKET_ITEMS], rk[BUCKET_ITEMS], nm[BUCKET_ITEMS], hp[BUCKET_ITEMS];
+#pragma unroll
+        for (int e = 0; e < BUCKET_ITEMS; e++) {  // the haplotype ids travel with the records: issue the loads first
+            const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
+            hp[e] = i < n ? hap_id[i] : 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < BUCKET_ITEMS; e++) {
+            const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
+            h[e] = NONE32;
+            nm[e] = 0;
+            rk[e] = 0;
+            if (i >= n) continue;
+            const uint4 b0 = philox_block(key, i, gen, PH_INFECT, 0);
+            uint64_t m = (uint64_t)b0.x * H32;
+            if ((uint32_t)m < H32) {
+                const uint32_t thr = (uint32_t)(-H32) % H32;
+                for (uint32_t blk = 1; (uint32_t)m < thr; blk++) m = (uint64_t)philox_block(key, i, gen, PH_INFECT, blk).x * H32;
+            }
+            h[e] = (uint32_t)(m >> 32);
+            host_id[i] = h[e];
+            rk[e] = atomicAdd(&s_hist[h[e] >> BUCKET_SHIFT], 1u);
+            if (FUSE_MUT) nm[e] = mutation_count_small(st, key, i, gen, b0);
+        }
+        __syncthreads();
+        // one global atomic per (chunk, bucket): the run of this chunk inside the bucket's region
+        for (uint32_t b = tid; b < B; b += BUCKET_TPB) {
+            const uint32_t c = s_hist[b];
+            s_hist[b] = c ? atomicAdd(&st->bucket_fill[b], c) : 0u;
+        }
+        __syncthreads();
+        uint32_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < BUCKET_ITEMS; e++) {
+            if (h[e] == NONE32) continue;
+            const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
+            const uint32_t b = h[e] >> BUCKET_SHIFT;
+            const uint64_t r = (uint64_t)s_hist[b] + rk[e];
+            uint32_t pos = NONE32;
+            if (r < stride) {
+                pos = (uint32_t)(b * stride + r);
+                st->tmp_rec[pos] = make_uint4((uint32_t)i, hp[e], h[e], 0u);
+            } else {
+                raise(st, DE_BUCKET_OVERFLOW);
+            }
+            rk[e] = pos;
+            mine += nm[e] ? 1u : 0u;
+        }
+        if (FUSE_MUT) {
+            // mutation worklist: (infectant, n_mut, position of its partitioned record); one global atomic per chunk
+            uint32_t inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += y;
+            }
+            if (lane == 31) s_w[wid] = inc;
+            __syncthreads();
+            uint32_t woff = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < BUCKET_TPB / 32; w++) {
+                const uint32_t t = s_w[w];
+                if (w < (int)wid) woff += t;
+                tot += t;
+            }
+            if (tid == 0) s_lbase = tot ? atomicAdd(&st->n_mut_list, tot) : 0u;
+            __syncthreads();
+            if (mine) {
+                uint32_t o = s_lbase + woff + inc - mine;
+#pragma unroll
+                for (int e = 0; e < BUCKET_ITEMS; e++)
+                    if (nm[e]) st->mut_list[o++] = make_uint4((uint32_t)(chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid), nm[e], rk[e], 0u);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// first CSR position of every bucket (exclusive scan of the fills), n_sorted = total.  One CTA, two buckets per thread.
+__global__ void __launch_bounds__(MAX_BUCKETS / 2) k_bucket_offsets(DevState *st) {
+    __shared__ uint32_t s_w[MAX_BUCKETS / 64];
+    const uint32_t B = st->n_buckets, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t x0 = 2 * tid < B ? st->bucket_fill[2 * tid] : 0u, x1 = 2 * tid + 1 < B ? st->bucket_fill[2 * tid + 1] : 0u;
+    const uint32_t x = x0 + x1;
+    uint32_t inc = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += y;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+    for (int w = 0; w < MAX_BUCKETS / 64; w++) {
+        const uint32_t t = s_w[w];
+        if (w < (int)wid) woff += t;
+        tot += t;
+    }
+    const uint32_t excl = woff + inc - x;
+    if (2 * tid < B) st->bucket_pos[2 * tid] = excl;
+    if (2 * tid + 1 < B) st->bucket_pos[2 * tid + 1] = excl + x0;
+    if (tid == 0) { st->bucket_pos[B] = tot; st->n_sorted = tot; st->offsets[st->H] = tot; }
+}
+
+// One CTA per bucket: counting sort of the bucket's records by host with the histogram in shared memory.
+// The records are staged in shared memory as well when the bucket fits (one global read per record); writes
+// offsets[] for the bucket's hosts and the records at their CSR positions (a window of ~100 KB that stays in L2
+// until its sectors are complete).
+constexpr int BSORT_TPB = 1024;
+constexpr uint32_t BSORT_SMEM_RECS = 11264;  // staged records per bucket: 11264 * 12 B = 132 KB next to the 32 KB histogram
+__global__ void __launch_bounds__(BSORT_TPB) k_bucket_sort(DevState *st) {
+    extern __shared__ uint32_t s_dyn32[];
+    uint32_t *s_cnt = s_dyn32;                                               // BUCKET_HOSTS counters, then running cursors
+    uint2 *s_rec = reinterpret_cast<uint2 *>(s_dyn32 + BUCKET_HOSTS);        // BSORT_SMEM_RECS (index, haplotype)
+    uint16_t *s_hl = reinterpret_cast<uint16_t *>(s_rec + BSORT_SMEM_RECS);  // BSORT_SMEM_RECS host - first host of the bucket
+    __shared__ uint32_t s_w[BSORT_TPB / 32];
+    const uint32_t B = st->n_buckets;
+    const uint64_t H = st->H;
+    const uint64_t stride = bucket_stride(st->n, H);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr uint32_t SEG = BUCKET_HOSTS / (BSORT_TPB / 32);  // hosts scanned per warp
+    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const uint32_t fill = min(st->bucket_fill[b], (uint32_t)stride);
+        const uint4 *__restrict__ src = st->tmp_rec + (uint64_t)b * stride;
+        const uint32_t h0 = b << BUCKET_SHIFT;
+        const uint32_t pos0 = st->bucket_pos[b];
+        const uint32_t nh = (uint32_t)min((uint64_t)BUCKET_HOSTS, H - h0);
+        const bool staged = fill <= BSORT_SMEM_RECS;
+        for (uint32_t k = tid; k < BUCKET_HOSTS; k += BSORT_TPB) s_cnt[k] = 0;
+        __syncthreads();
+        for (uint32_t j0 = tid; j0 < fill; j0 += 4 * BSORT_TPB) {  // four independent loads in flight per thread
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t j = j0 + u * BSORT_TPB;
+                r[u] = j < fill ? src[j] : make_uint4(0u, 0u, h0, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t j = j0 + u * BSORT_TPB;
+                if (j >= fill) continue;
+                const uint32_t hl = r[u].z - h0;
+                atomicAdd(&s_cnt[hl], 1u);
+                if (staged) { s_rec[j] = make_uint2(r[u].x, r[u].y); s_hl[j] = (uint16_t)hl; }
+            }
+        }
+        __syncthreads();
+        // exclusive scan: each warp scans a contiguous segment 32 hosts at a time (conflict-free), then segment bases
+        uint32_t carry = 0;
+        for (uint32_t it = 0; it < SEG / 32; it++) {
+            const uint32_t k = wid * SEG + it * 32 + lane;
+            const uint32_t x = s_cnt[k];
+            uint32_t inc = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += y;
+            }
+            s_cnt[k] = carry + inc - x;
+            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        if (lane == 0) s_w[wid] = carry;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (uint32_t w = 0; w < wid; w++) wbase += s_w[w];
+        for (uint32_t it = 0; it < SEG / 32; it++) {
+            const uint32_t k = wid * SEG + it * 32 + lane;
+            const uint32_t o = s_cnt[k] + wbase;
+            s_cnt[k] = o;
+            if (k < nh) st->offsets[h0 + k] = pos0 + o;
+        }
+        __syncthreads();
+        for (uint32_t j = tid; j < fill; j += BSORT_TPB) {
+            uint2 r;
+            uint32_t hl;
+            if (staged) { r = s_rec[j]; hl = s_hl[j]; }
+            else { const uint4 q = src[j]; r = make_uint2(q.x, q.y); hl = q.z - h0; }
+            st->rec[pos0 + atomicAdd(&s_cnt[hl], 1u)] = r;
+        }
+        __syncthreads();
     }
 }
 
@@ -371,10 +588,10 @@ struct ReplayRecomb {
 // right entries outside; raw fitness by full recomputation like FitnessProvider::get_fitness does for
 // nodes without changes (src/providers/fitness.rs:224-227).
 __device__ inline uint32_t make_recombinant(DevState *st, uint32_t left, uint32_t right, uint32_t s0, uint32_t s1) {
-    const uint32_t ll = st->h_len[left], lr = st->h_len[right];
+    const uint32_t ll = st->hm[left].len, lr = st->hm[right].len;
     NewRecord r = reserve_record_single(st, ll + lr);
     if (!r.ok) return left;
-    const uint32_t *el = st->arena + st->h_off[left], *er = st->arena + st->h_off[right];
+    const uint32_t *el = st->arena + st->hm[left].off, *er = st->arena + st->hm[right].off;
     uint32_t *out = st->arena + r.off;
     uint32_t o = 0;
     uint32_t k = 0;
@@ -384,10 +601,10 @@ __device__ inline uint32_t make_recombinant(DevState *st, uint32_t left, uint32_
         if (p >= s0 && p < s1) out[o++] = el[q];
     }
     for (; k < lr; k++) if (entry_pos(er[k]) >= s1) out[o++] = er[k];
-    st->h_off[r.id] = r.off;
-    st->h_len[r.id] = o;
-    st->h_parent[r.id] = left;
-    for (uint32_t p = 0; p < st->n_providers; p++) st->h_raw[p][r.id] = compute_fitness_full(st->prov[p], out, o);
+    st->hm[r.id].off = r.off;
+    st->hm[r.id].len = o;
+    st->hm[r.id].parent = left;
+    for (uint32_t p = 0; p < st->n_providers; p++) hap_raw(st, p, r.id) = compute_fitness_full(st->prov[p], out, o);
     return r.id;
 }
 
@@ -468,6 +685,7 @@ __global__ void __launch_bounds__(TPB) k_mutation_counts(DevState *st, ReplayMut
     for (uint64_t r = 0; r < rounds; r++) {
         uint64_t idx[1] = {r * span + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x};
         uint32_t nm[1] = {0};
+        const uint32_t pos[1] = {NONE32};
         const uint64_t i = idx[0];
         if (i < n && host_id[i] != NONE32) {
             if (replay) nm[0] = (uint32_t)(rp.offsets[i + 1] - rp.offsets[i]);
@@ -475,14 +693,15 @@ __global__ void __launch_bounds__(TPB) k_mutation_counts(DevState *st, ReplayMut
         } else if (i < n && replay && rp.offsets[i + 1] != rp.offsets[i]) {
             raise(st, DE_REPLAY);  // the reference never mutates an uninfected infectant
         }
-        worklist_append<1>(st, idx, nm);
+        worklist_append<1>(st, idx, nm, pos);
     }
 }
 
 // One thread per mutated infectant: draw sites (with replacement) and sort them, look up the current base
 // on the pre-mutation haplotype, draw the substitution, merge into a new flattened record and update the
 // raw fitness of every provider incrementally: raw(parent) * fold(acc * T[pos,to] / T[pos,from])
-// (src/core/fitness/table.rs:65-68) [* epistatic update].  The infectant's CSR record is patched in place.
+// (src/core/fitness/table.rs:65-68) [* epistatic update].  patch_records: 1 = the infectant's CSR record is
+// patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist.
 __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records) {
     const uint32_t n_list = st->n_mut_list;
     const uint32_t L = st->L;
@@ -492,17 +711,20 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
     for (uint32_t r = 0; r < rounds; r++) {
         const uint32_t w = r * span + blockIdx.x * blockDim.x + threadIdx.x;
         const bool active = w < n_list;
-        uint32_t i = 0, nm = 0, pid = 0, plen = 0;
+        uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32;
+        HapMeta pm{0, 0, NONE32};
         if (active) {
-            const uint2 item = st->mut_list[w];
+            const uint4 item = st->mut_list[w];
             i = item.x;
             nm = item.y;
+            tpos = item.z;
             pid = st->hap_id[i];
-            plen = st->h_len[pid];
+            pm = st->hm[pid];  // one 16-byte load: arena offset, length, parent
+            plen = pm.len;
         }
         NewRecord rec = reserve_record(st, active, plen + 2 * nm);
         if (!rec.ok) continue;
-        const uint32_t *pe = st->arena + st->h_off[pid];
+        const uint32_t *pe = st->arena + pm.off;
         uint32_t *out = st->arena + rec.off;
         uint32_t *chs = out + plen + nm;
         if (replay) {
@@ -552,9 +774,6 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
                 if (!(first_to == w0 && m == 4u)) out[o++] = make_entry(pb, first_to, m);
             }
         }
-        st->h_off[rec.id] = rec.off;
-        st->h_len[rec.id] = o;
-        st->h_parent[rec.id] = pid;
         for (uint32_t p = 0; p < st->n_providers; p++) {
             const DevProvider &pr = st->prov[p];
             double raw = 1.0;
@@ -569,8 +788,11 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
             }
             st->h_raw[p][rec.id] = raw;
         }
+        st->hm[rec.id] = HapMeta{rec.off, o, pid};
         st->hap_id[i] = rec.id;
-        if (patch_records) {
+        if (patch_records == 2) {
+            if (tpos != NONE32) st->tmp_rec[tpos].y = rec.id;  // the bucket-partitioned record, not yet sorted
+        } else if (patch_records) {
             const uint32_t h = st->host_id[i];
             if (h != NONE32) {
                 const uint32_t sb = st->offsets[h], se = st->offsets[h + 1];
@@ -585,7 +807,7 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
 // mapped fitness of a haplotype under the reproductive provider of spec s (or 1.0), src/simulation.rs:137-143
 __device__ __forceinline__ double reproductive_fitness(const DevState *st, int s, uint32_t hap) {
     const int pi = s >= 0 ? st->specs[s].repro : -1;
-    return pi >= 0 ? utility_apply(st->prov[pi], st->h_raw[pi][hap]) : 1.;
+    return pi >= 0 ? utility_apply(st->prov[pi], hap_raw(st, pi, hap)) : 1.;
 }
 // lambda as the offspring kernel consumes it: 0.0 stands for "no offspring".  Poisson::new fails for a mean that
 // is not finite and > 0; the reference then leaves the f64 bit pattern of f in the slot (src/simulation.rs:146-152),
@@ -608,7 +830,7 @@ __device__ __forceinline__ int find_spec_of_position(const DevState *st, uint64_
 }
 
 // One thread per CSR position: mapped reproductive fitness of the record's haplotype (the random gather of the
-// generation), parked in lam[p] until k_host_lambda turns it into the Poisson mean.
+// generation), parked in lam[p] until k_host_sum turns it into the Poisson mean.
 __global__ void __launch_bounds__(TPB) k_fitness(DevState *st) {
     const uint64_t m = st->n_sorted;
     const uint2 *__restrict__ rec = st->rec;
@@ -617,7 +839,7 @@ __global__ void __launch_bounds__(TPB) k_fitness(DevState *st) {
     const int pi0 = st->specs[0].repro;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (uint64_t)gridDim.x * blockDim.x) {
         double f;
-        if (single) f = pi0 >= 0 ? utility_apply(st->prov[pi0], st->h_raw[pi0][rec[p].y]) : 1.;
+        if (single) f = pi0 >= 0 ? utility_apply(st->prov[pi0], hap_raw(st, pi0, rec[p].y)) : 1.;
         else f = reproductive_fitness(st, find_spec_of_position(st, p), rec[p].y);
         lam[p] = f;
     }
@@ -636,21 +858,40 @@ __device__ __forceinline__ void sort_slice_desc(uint2 *rec, double *lam, uint32_
 }
 
 // One thread per host: order the slice, S_h = sum of f over the slice in slice order from 0.0 (iter().sum(),
-// src/simulation.rs:144), lambda_i = f_i * R0 / S_h at the record's CSR position.  Long slices go to the heavy list.
-__global__ void __launch_bounds__(TPB) k_host_lambda(DevState *st, int order_only) {
+// src/simulation.rs:144), left at every member's CSR position (hs[p]); the division that turns (f, S) into the
+// Poisson mean happens position-parallel in k_offspring.  Long slices go to the heavy list.
+__global__ void __launch_bounds__(TPB) k_host_sum(DevState *st, int order_only) {
     const uint64_t H = st->H;
     const uint32_t *__restrict__ offsets = st->offsets;
     uint2 *rec = st->rec;
     double *lam = st->lam;
-    const double R0 = st->host_r0;
+    double *hs = st->hs;
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < H; h += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t b = offsets[h], e = offsets[h + 1];
         const uint32_t len = e - b;
         if (len == 0) continue;
-        if (len == 1) {
+        if (len <= 4) {
+            // up to four members in registers, all loads issued at once; absent members get the lowest key and
+            // f = +0.0 (adding +0.0 to a non-negative partial sum is exact), five compare-exchanges, larger index first
+            uint2 r0 = rec[b], r1 = len > 1 ? rec[b + 1] : make_uint2(0u, 0u), r2 = len > 2 ? rec[b + 2] : make_uint2(0u, 0u),
+                  r3 = len > 3 ? rec[b + 3] : make_uint2(0u, 0u);
+            double f0 = lam[b], f1 = len > 1 ? lam[b + 1] : 0.0, f2 = len > 2 ? lam[b + 2] : 0.0, f3 = len > 3 ? lam[b + 3] : 0.0;
+            if (len > 1) {
+                uint32_t k0 = r0.x + 1u, k1 = len > 1 ? r1.x + 1u : 0u, k2 = len > 2 ? r2.x + 1u : 0u, k3 = len > 3 ? r3.x + 1u : 0u;
+#define VL_CX(ka, ra, fa, kb, rb, fb) if (ka < kb) { const uint32_t tk = ka; ka = kb; kb = tk; const uint2 tr = ra; ra = rb; rb = tr; const double tf = fa; fa = fb; fb = tf; }
+                VL_CX(k0, r0, f0, k1, r1, f1) VL_CX(k2, r2, f2, k3, r3, f3) VL_CX(k0, r0, f0, k2, r2, f2) VL_CX(k1, r1, f1, k3, r3, f3) VL_CX(k1, r1, f1, k2, r2, f2)
+#undef VL_CX
+                rec[b] = r0; lam[b] = f0;
+                rec[b + 1] = r1; lam[b + 1] = f1;
+                if (len > 2) { rec[b + 2] = r2; lam[b + 2] = f2; }
+                if (len > 3) { rec[b + 3] = r3; lam[b + 3] = f3; }
+            }
             if (!order_only) {
-                const double f = lam[b];
-                lam[b] = checked_lambda(st, f, R0, 0.0 + f);
+                const double S = (((0.0 + f0) + f1) + f2) + f3;
+                hs[b] = S;
+                if (len > 1) hs[b + 1] = S;
+                if (len > 2) hs[b + 2] = S;
+                if (len > 3) hs[b + 3] = S;
             }
             continue;
         }
@@ -659,61 +900,34 @@ __global__ void __launch_bounds__(TPB) k_host_lambda(DevState *st, int order_onl
             st->heavy_hosts[slot] = (uint32_t)h;
             continue;
         }
-        if (len <= SMALL_SLICE) {
-            // the whole slice in registers: rank of every member by descending index (no dependent memory chain)
-            uint2 r[SMALL_SLICE];
-            double f[SMALL_SLICE];
-            uint32_t rk[SMALL_SLICE];
-#pragma unroll
-            for (uint32_t k = 0; k < SMALL_SLICE; k++) {
-                r[k] = k < len ? rec[b + k] : make_uint2(0u, 0u);
-                f[k] = k < len ? lam[b + k] : 0.0;
-            }
-#pragma unroll
-            for (uint32_t k = 0; k < SMALL_SLICE; k++) {
-                uint32_t c = 0;
-#pragma unroll
-                for (uint32_t j = 0; j < SMALL_SLICE; j++) c += (j < len && j != k && r[j].x > r[k].x) ? 1u : 0u;
-                rk[k] = c;
-            }
-            double S = 0.0;
-#pragma unroll
-            for (uint32_t q = 0; q < SMALL_SLICE; q++) {  // q-th term of the sum = fitness of the member with rank q
-                if (q < len) {
-                    double t = 0.0;
-#pragma unroll
-                    for (uint32_t k = 0; k < SMALL_SLICE; k++) t = (k < len && rk[k] == q) ? f[k] : t;
-                    S += t;
-                }
-            }
-#pragma unroll
-            for (uint32_t k = 0; k < SMALL_SLICE; k++) {
-                if (k < len) {
-                    if (rk[k] != k) rec[b + rk[k]] = r[k];
-                    if (!order_only) lam[b + rk[k]] = checked_lambda(st, f[k], R0, S);
-                    else if (rk[k] != k) lam[b + rk[k]] = f[k];
-                }
-            }
-            continue;
-        }
-        sort_slice_desc(rec, lam, b, e);
+        // 5 .. THREAD_TIER members: rare at N ~ H, so they are compacted into a worklist instead of stalling the warp
+        st->medium_hosts[atomicAdd(&st->n_medium, 1u)] = (uint32_t)h;
+    }
+}
+// One thread per listed host (5 .. THREAD_TIER members): insertion sort, sequential sum
+__global__ void __launch_bounds__(TPB) k_host_sum_medium(DevState *st, int order_only) {
+    const uint32_t n_medium = st->n_medium;
+    const uint32_t *__restrict__ offsets = st->offsets;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_medium; w += gridDim.x * blockDim.x) {
+        const uint32_t h = st->medium_hosts[w];
+        const uint32_t b = offsets[h], e = offsets[h + 1];
+        sort_slice_desc(st->rec, st->lam, b, e);
         if (order_only) continue;
         double S = 0.0;
-        for (uint32_t a = b; a < e; a++) S += lam[a];
-        for (uint32_t a = b; a < e; a++) lam[a] = checked_lambda(st, lam[a], R0, S);
+        for (uint32_t a = b; a < e; a++) S += st->lam[a];
+        for (uint32_t a = b; a < e; a++) st->hs[a] = S;
     }
 }
 
 // One CTA per heavy slice: normalised bitonic network on (index << 32 | haplotype) keys with the fitness as
 // payload, larger index first (missing partners beyond the slice end are no-ops), in shared memory when the
 // slice fits, else in global memory; then the sum strictly sequential in slice order, lambda in parallel.
-__global__ void __launch_bounds__(TPB) k_host_lambda_heavy(DevState *st, int order_only) {
+__global__ void __launch_bounds__(TPB) k_host_sum_heavy(DevState *st, int order_only) {
     extern __shared__ unsigned long long s_dyn[];
     __shared__ double s_S;
     unsigned long long *s_keys = s_dyn;
     double *s_f = reinterpret_cast<double *>(s_dyn + SMEM_SORT_MAX);
     const uint32_t n_heavy = st->n_heavy;
-    const double R0 = st->host_r0;
     for (uint32_t w = blockIdx.x; w < n_heavy; w += gridDim.x) {
         const uint32_t h = st->heavy_hosts[w];
         const uint32_t b = st->offsets[h], len = st->offsets[h + 1] - b;
@@ -770,7 +984,8 @@ __global__ void __launch_bounds__(TPB) k_host_lambda_heavy(DevState *st, int ord
         }
         __syncthreads();
         const double S = s_S;
-        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) gf[i] = checked_lambda(st, gf[i], R0, S);
+        double *ghs = st->hs + b;
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) ghs[i] = S;
         __syncthreads();
     }
 }
@@ -778,18 +993,21 @@ __global__ void __launch_bounds__(TPB) k_host_lambda_heavy(DevState *st, int ord
 // offspring of the record at CSR position p ~ Poisson(lam[p]) (src/simulation.rs:148-152); one CTA per resample
 // tile so that the tile's offspring total comes out of the same pass.  replay_off is indexed by infectant.
 // SMALL_ONLY: every mean is below 12 (R0 < 12 and lambda = R0 * f/S <= R0), so the rejection sampler is not compiled in.
+// store_lambda: keep the Poisson mean in lam[p] for vl_get_replication_terms (trait-level calls; the fused loop skips the store)
 template <bool SMALL_ONLY>
-__global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t *__restrict__ replay_off) {
+__global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda) {
     __shared__ uint64_t s_red[TPB / 32];
     __shared__ double s_rcp[POISSON_RCP];
     poisson_rcp_init(s_rcp);
     __syncthreads();
     const uint64_t m = st->n_sorted;
     const uint64_t n_tiles = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
-    const double *__restrict__ lam = st->lam;
+    double *__restrict__ lam = st->lam;
+    const double *__restrict__ hs = st->hs;
     const uint2 *__restrict__ rec = st->rec;
     uint32_t *__restrict__ offspring = st->offspring;
     const uint32_t gen = st->generation;
+    const double R0 = st->host_r0;
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint64_t local = 0;
@@ -798,12 +1016,13 @@ __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t 
             const uint64_t p = tile * RESAMPLE_TILE + (uint64_t)k * TPB + threadIdx.x;
             if (p >= m) break;
             uint32_t off = 0;
+            const double l = checked_lambda(st, lam[p], R0, hs[p]);  // lambda_i = f_i * R0 / S_host (src/simulation.rs:148-150)
+            if (store_lambda) lam[p] = l;
             if (replay_off) {
                 uint64_t v = replay_off[rec[p].x];
                 if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0; }
                 off = (uint32_t)v;
             } else {
-                const double l = lam[p];
                 if (l > 0.0) {
                     if (SMALL_ONLY && !(l < 12.0)) raise(st, DE_UNDEFINED_OFFSPRING);  // f > S: negative fitness values in the slice
                     uint64_t v = poisson_draw<SMALL_ONLY>(key, p, gen, PH_OFFSPRING, l, s_rcp);
@@ -1183,7 +1402,7 @@ __global__ void __launch_bounds__(TPB) k_gc_mark(DevState *st, const uint32_t *_
 __global__ void __launch_bounds__(TPB) k_gc_lens(DevState *st) {
     if (!st->gc_active) return;
     const uint64_t nh = st->n_hap;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_len[h] = st->gc_mark[h] ? st->h_len[h] : 0u;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_len[h] = st->gc_mark[h] ? st->hm[h].len : 0u;
 }
 __global__ void __launch_bounds__(TPB) k_gc_copy(DevState *st) {
     if (!st->gc_active) return;
@@ -1192,15 +1411,15 @@ __global__ void __launch_bounds__(TPB) k_gc_copy(DevState *st) {
         if (!st->gc_mark[h]) continue;
         const uint32_t nid = st->gc_newid[h];
         const uint64_t noff = st->gc_newoff[h];
-        const uint32_t len = st->h_len[h];
-        const uint32_t *src = st->arena + st->h_off[h];
+        const uint32_t len = st->hm[h].len;
+        const uint32_t *src = st->arena + st->hm[h].off;
         uint32_t *dst = st->arena_alt + noff;
         for (uint32_t k = 0; k < len; k++) dst[k] = src[k];
-        st->h_off_alt[nid] = noff;
-        st->h_len_alt[nid] = len;
-        const uint32_t par = st->h_parent[h];
-        st->h_parent_alt[nid] = (par != NONE32 && st->gc_mark[par]) ? st->gc_newid[par] : NONE32;
-        for (uint32_t p = 0; p < st->n_providers; p++) st->h_raw_alt[p][nid] = st->h_raw[p][h];
+        st->hm_alt[nid].off = noff;
+        st->hm_alt[nid].len = len;
+        const uint32_t par = st->hm[h].parent;
+        st->hm_alt[nid].parent = (par != NONE32 && st->gc_mark[par]) ? st->gc_newid[par] : NONE32;
+        for (uint32_t p = 0; p < st->n_providers; p++) hap_raw_alt(st, p, nid) = hap_raw(st, p, h);
     }
 }
 __global__ void __launch_bounds__(TPB) k_gc_remap(DevState *st, uint32_t *ids, uint64_t m, int use_population) {
@@ -1214,7 +1433,7 @@ __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
     st->n_hap = gc_totals[0];
     st->arena_top = gc_totals[1];
 #define VL_SWAP(a, b) { auto t = st->a; st->a = st->b; st->b = t; }
-    VL_SWAP(h_off, h_off_alt) VL_SWAP(h_len, h_len_alt) VL_SWAP(h_parent, h_parent_alt) VL_SWAP(arena, arena_alt)
+    VL_SWAP(hm, hm_alt) VL_SWAP(arena, arena_alt)
     for (uint32_t p = 0; p < st->n_providers; p++) VL_SWAP(h_raw[p], h_raw_alt[p])
 #undef VL_SWAP
     st->gc_runs += 1;
@@ -1268,7 +1487,7 @@ __global__ void __launch_bounds__(TPB) k_replication_terms(DevState *st, double 
 }
 __global__ void __launch_bounds__(TPB) k_gather_raw(DevState *st, uint32_t provider, double *out) {
     const uint64_t n = st->n;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = st->h_raw[provider][st->hap_id[i]];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = hap_raw(st, provider, st->hap_id[i]);
 }
 
 // sampler test hooks (distribution tests of the device samplers the kernels above call)

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(TPB) k_pack_mark(DevState *st, const uint32_t 
 }
 __global__ void __launch_bounds__(TPB) k_pack_lens(DevState *st) {
     const uint64_t nh = st->n_hap;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_len[h] = st->gc_mark[h] ? st->h_len[h] : 0u;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_len[h] = st->gc_mark[h] ? st->hm[h].len : 0u;
 }
 __global__ void __launch_bounds__(TPB) k_pack_copy(DevState *st, const uint32_t *__restrict__ ids, uint8_t *image, PackHeader hd) {
     const uint64_t nh = st->n_hap;
@@ -65,11 +65,11 @@ __global__ void __launch_bounds__(TPB) k_pack_copy(DevState *st, const uint32_t 
         if (!st->gc_mark[h]) continue;
         const uint32_t u = st->gc_newid[h];
         const uint64_t noff = st->gc_newoff[h];
-        const uint32_t len = st->h_len[h];
+        const uint32_t len = st->hm[h].len;
         o_len[u] = len;
         o_off[u] = noff;
-        for (uint32_t p = 0; p < st->n_providers; p++) o_raw[(uint64_t)p * hd.n_unique + u] = st->h_raw[p][h];
-        const uint32_t *src = st->arena + st->h_off[h];
+        for (uint32_t p = 0; p < st->n_providers; p++) o_raw[(uint64_t)p * hd.n_unique + u] = hap_raw(st, p, h);
+        const uint32_t *src = st->arena + st->hm[h].off;
         for (uint32_t k = 0; k < len; k++) o_ent[noff + k] = src[k];
     }
     for (uint64_t i = tid; i < hd.n_pop; i += span) {
@@ -104,10 +104,10 @@ __global__ void __launch_bounds__(TPB) k_unpack(DevState *st, const uint8_t *__r
     if (ok) {
         for (uint64_t u = tid; u < hd.n_unique; u += span) {
             const uint64_t id = id0 + u;
-            st->h_off[id] = a0 + i_off[u];
-            st->h_len[id] = i_len[u];
-            st->h_parent[id] = NONE32;
-            for (uint32_t p = 0; p < st->n_providers; p++) st->h_raw[p][id] = i_raw[(uint64_t)p * hd.n_unique + u];
+            st->hm[id].off = a0 + i_off[u];
+            st->hm[id].len = i_len[u];
+            st->hm[id].parent = NONE32;
+            for (uint32_t p = 0; p < st->n_providers; p++) hap_raw(st, p, id) = i_raw[(uint64_t)p * hd.n_unique + u];
         }
         for (uint64_t w = tid; w < hd.n_words; w += span) st->arena[a0 + w] = i_ent[w];
     }
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(TPB) k_export_count(DevState *st, uint32_t *__
     const uint64_t n = st->n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t id = st->hap_id[i];
-        const uint32_t *e = st->arena + st->h_off[id];
-        const uint32_t len = st->h_len[id];
+        const uint32_t *e = st->arena + st->hm[id].off;
+        const uint32_t len = st->hm[id].len;
         uint32_t c = 0;
         for (uint32_t k = 0; k < len; k++) c += entry_m(e[k]) < 4 ? 1u : 0u;
         cnt[i] = c;
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(TPB) k_export_fill(DevState *st, const uint64_
     const uint64_t n = st->n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t id = st->hap_id[i];
-        const uint32_t *e = st->arena + st->h_off[id];
-        const uint32_t len = st->h_len[id];
+        const uint32_t *e = st->arena + st->hm[id].off;
+        const uint32_t len = st->hm[id].len;
         uint64_t o = offsets[i];
         for (uint32_t k = 0; k < len; k++) {
             if (entry_m(e[k]) < 4) { pos_out[o] = entry_pos(e[k]); base_out[o] = (uint8_t)entry_m(e[k]); o++; }
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TPB) k_export_fill(DevState *st, const uint64_
 __global__ void k_get_base(DevState *st, uint64_t infectant, uint32_t pos, uint32_t *out) {
     if (infectant >= st->n || pos >= st->L) { *out = 0xFFu; return; }
     const uint32_t id = st->hap_id[infectant];
-    *out = entries_get_base(st->arena + st->h_off[id], st->h_len[id], pos, st->wildtype);
+    *out = entries_get_base(st->arena + st->hm[id].off, st->hm[id].len, pos, st->wildtype);
 }
 
 }  // namespace vl

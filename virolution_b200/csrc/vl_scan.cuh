@@ -33,7 +33,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_u32(const uint32_t *__res
                                                             const uint64_t *n_ptr, uint64_t n_add, uint64_t *work,
                                                             uint64_t *total_out, int write_end, const uint32_t *active) {
     __shared__ uint64_t s_warp[SCAN_THREADS / 32];
-    __shared__ uint64_t s_carry;
     __shared__ uint32_t s_tile;
     __shared__ uint64_t s_excl;
     if (active && !*active) return;

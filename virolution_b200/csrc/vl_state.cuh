@@ -9,7 +9,8 @@
 //                                             the haplotype id carried along, so everything downstream of the
 //                                             counting sort streams over host-contiguous records
 //   replication    lam[p] f64 (Poisson mean of the record at CSR position p), offspring[p] u32, tile_sum[] u64
-//   haplotypes     h_off[u64] h_len[u32] h_parent[u32] h_raw[provider][f64]  + arena of u32 entries
+//   haplotypes     hm[id] = {arena offset u64, length u32, parent u32} (16 B) + h_raw[provider][id] f64
+//                  + arena of u32 entries
 //
 // A haplotype record is the *flattened* form of the reference's delta chain (Wildtype / Mutant{changes} /
 // Recombinant{left,right,window}, src/core/haplotype.rs:45-56,241-288): the position-sorted list of sites where
@@ -22,7 +23,7 @@
 // replacement, src/simulation.rs:94-103); keeping both makes the flattened record answer every query the
 // chain answers.  Raw fitness per provider is computed once when the record is created, exactly as
 // FitnessProvider::get_fitness would on first touch (src/providers/fitness.rs:212-228), and memoised in
-// h_raw (AttributeSet, src/core/attributes.rs:196-217).
+// the haplotype's metadata (AttributeSet, src/core/attributes.rs:196-217).
 #pragma once
 #include <stdint.h>
 #include "../../include/virolution_gpu.h"
@@ -44,8 +45,16 @@ enum DevError : uint32_t {
     DE_SAME_BASE = 16u,         // assert_ne!(from, to) (src/core/haplotype.rs:250)
     DE_INF_CAPACITY = 32u,      // population buffer too small
     DE_OFFSPRING_RANGE = 64u,   // offspring count does not fit u32
-    DE_REPLAY = 128u            // malformed replay log
+    DE_REPLAY = 128u,           // malformed replay log
+    DE_BUCKET_OVERFLOW = 256u   // a host bucket received 12 standard deviations more records than its mean
 };
+constexpr uint32_t BUCKET_SHIFT = 13;
+constexpr uint32_t BUCKET_HOSTS = 1u << BUCKET_SHIFT;  // hosts per bucket: their histogram lives in shared memory
+// records reserved per bucket: mean + 12 sd of Binomial(n, BUCKET_HOSTS / H) + slack (never reached in practice)
+__host__ __device__ inline uint64_t bucket_stride(uint64_t n, uint64_t H) {
+    const double m = (double)n * (double)BUCKET_HOSTS / (double)(H ? H : 1);
+    return (uint64_t)(m + 12.0 * sqrt(m) + 64.0);
+}
 
 struct EpiDir {  // one direction of a symmetric pair entry (src/core/fitness/epistasis.rs:44-58)
     uint32_t k1, k2;  // (pos << 2) | base
@@ -66,6 +75,12 @@ struct DevProvider {
 struct DevSpec {
     uint64_t lo, hi;
     int32_t repro, infect;  // provider index or -1
+};
+
+struct alignas(16) HapMeta {
+    uint64_t off;    // first arena word
+    uint32_t len;    // entries
+    uint32_t parent; // id of the haplotype it was derived from (NONE32 for the wildtype / migrants)
 };
 
 struct DevState {
@@ -100,17 +115,28 @@ struct DevState {
     uint2 *rec;            // (infectant index, haplotype id) per CSR position
     uint64_t n_sorted;     // number of records = infected infectants (offsets[H])
     uint32_t *heavy_hosts; // worklist of hosts whose slice exceeds the thread tier
+    uint32_t *medium_hosts; // worklist of hosts with 5 .. THREAD_TIER members
+    uint32_t n_medium;
     uint32_t n_heavy;
-    uint32_t fast_infect;  // one spec over [0,H), no infective provider, n_hits == 1: every draw infects
+    uint32_t _pad3;
+    uint32_t fast_infect;  // specs cover [0,H), no infective provider, n_hits == 1: every draw infects, hosts uniform
+    // ---- bucketed counting sort (hosts split into buckets of BUCKET_HOSTS consecutive hosts)
+    uint32_t n_buckets;
+    uint32_t _pad2;
+    uint32_t *bucket_fill; // records appended per bucket
+    uint32_t *bucket_pos;  // n_buckets + 1: first CSR position of every bucket
+    uint4 *tmp_rec;        // bucket-partitioned records (index, haplotype, host, -), bucket b at [b * stride, b * stride + fill)
+    uint64_t cap_tmp;
 
     // ---- mutation worklist
-    uint2 *mut_list;       // (infectant index, n_mut) for infectants with n_mut > 0
+    uint4 *mut_list;       // (infectant index, n_mut, position in the bucket-partitioned records, -) where n_mut > 0
     uint32_t n_mut_list;
     uint32_t _pad0;
     BinvConst binv;        // Binomial(L, mu) inversion constants (captured BasicHost parameters)
 
     // ---- replication
-    double *lam;           // per CSR position
+    double *lam;           // per CSR position: mapped fitness f, later the Poisson mean
+    double *hs;            // per CSR position: fitness sum of the record's host
     uint32_t *offspring;   // per CSR position
     uint64_t *tile_sum;    // per resample tile
     uint64_t *tile_tree;   // segment tree over tile sums (fallback plan) / inclusive prefix of tile sums
@@ -126,10 +152,8 @@ struct DevState {
     unsigned long long arena_top;
     uint32_t gc_active;
     uint32_t _pad1;
-    uint64_t *h_off, *h_off_alt;
-    uint32_t *h_len, *h_len_alt;
-    uint32_t *h_parent, *h_parent_alt;
-    double *h_raw[MAX_PROVIDERS], *h_raw_alt[MAX_PROVIDERS];
+    HapMeta *hm, *hm_alt;  // 16 bytes per haplotype: arena offset, length, parent
+    double *h_raw[MAX_PROVIDERS], *h_raw_alt[MAX_PROVIDERS];  // memoised raw fitness per provider
     uint32_t *arena, *arena_alt;
     uint32_t *gc_mark, *gc_newid, *gc_len;
     uint64_t *gc_newoff;
@@ -138,6 +162,12 @@ struct DevState {
     uint64_t kernels_launched;  // maintained by the host, mirrored here for export
     uint64_t dbg[8];            // %globaltimer stamps of the plan kernel's phases (profiling aid)
 };
+
+// memoised raw fitness of haplotype `id` under provider p (AttributeSet::get_or_compute_raw, src/core/attributes.rs:196-217)
+// (kept apart from HapMeta: the per-infectant fitness gather wants the densest possible array)
+__host__ __device__ inline double &hap_raw(DevState *st, uint32_t p, uint64_t id) { return st->h_raw[p][id]; }
+__host__ __device__ inline const double &hap_raw(const DevState *st, uint32_t p, uint64_t id) { return st->h_raw[p][id]; }
+__host__ __device__ inline double &hap_raw_alt(DevState *st, uint32_t p, uint64_t id) { return st->h_raw_alt[p][id]; }
 
 // ---- entry helpers ---------------------------------------------------------------------------------
 __host__ __device__ inline uint32_t make_entry(uint32_t pos, uint32_t g, uint32_t m) { return (pos << 8) | (g << 4) | m; }
