@@ -236,19 +236,14 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         for (uint32_t b = tid; b < B; b += BUCKET_TPB) s_hist[b] = 0;
         __syncthreads();
-        // coalesced layout: item e of thread t is infectant chunk*CHUNK + e*TPB + t
-        uint32_t h[BUCKET_ITEMS], rk[BUCKET_ITEMS], nm[BUCKET_ITEMS], hp[BUCKET_ITEMS];
-#pragma unroll
-        for (int e = 0; e < BUCKET_ITEMS; e++) {  // the haplotype ids travel with the records: issue the loads first
-            const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
-            hp[e] = i < n ? hap_id[i] : 0u;
-        }
+        // coalesced layout: item e of thread t is infectant chunk*CHUNK + e*TPB + t.  Per item two registers survive
+        // the barriers: the host, and (rank inside the chunk's bucket run | n_mut << 16).
+        uint32_t h[BUCKET_ITEMS], rn[BUCKET_ITEMS];
 #pragma unroll
         for (int e = 0; e < BUCKET_ITEMS; e++) {
             const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
             h[e] = NONE32;
-            nm[e] = 0;
-            rk[e] = 0;
+            rn[e] = 0;
             if (i >= n) continue;
             const uint4 b0 = philox_block(key, i, gen, PH_INFECT, 0);
             uint64_t m = (uint64_t)b0.x * H32;
@@ -258,8 +253,9 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
             }
             h[e] = (uint32_t)(m >> 32);
             host_id[i] = h[e];
-            rk[e] = atomicAdd(&s_hist[h[e] >> BUCKET_SHIFT], 1u);
-            if (FUSE_MUT) nm[e] = mutation_count_small(st, key, i, gen, b0);
+            uint32_t nm = 0;
+            if (FUSE_MUT) nm = min(mutation_count_small(st, key, i, gen, b0), 0xFFFFu);
+            rn[e] = atomicAdd(&s_hist[h[e] >> BUCKET_SHIFT], 1u) | (nm << 16);
         }
         __syncthreads();
         // one global atomic per (chunk, bucket): the run of this chunk inside the bucket's region
@@ -274,16 +270,18 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
             if (h[e] == NONE32) continue;
             const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
             const uint32_t b = h[e] >> BUCKET_SHIFT;
-            const uint64_t r = (uint64_t)s_hist[b] + rk[e];
+            const uint64_t r = (uint64_t)s_hist[b] + (rn[e] & 0xFFFFu);
+            const uint32_t nm = rn[e] >> 16;
             uint32_t pos = NONE32;
             if (r < stride) {
                 pos = (uint32_t)(b * stride + r);
-                st->tmp_rec[pos] = make_uint4((uint32_t)i, hp[e], h[e], 0u);
+                st->tmp_rec[pos] = make_uint4((uint32_t)i, hap_id[i], h[e], 0u);
             } else {
                 raise(st, DE_BUCKET_OVERFLOW);
             }
-            rk[e] = pos;
-            mine += nm[e] ? 1u : 0u;
+            h[e] = pos;   // the host is not needed any more: keep the record position for the worklist
+            rn[e] = nm;
+            mine += nm ? 1u : 0u;
         }
         if (FUSE_MUT) {
             // mutation worklist: (infectant, n_mut, position of its partitioned record); one global atomic per chunk
@@ -308,7 +306,7 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
                 uint32_t o = s_lbase + woff + inc - mine;
 #pragma unroll
                 for (int e = 0; e < BUCKET_ITEMS; e++)
-                    if (nm[e]) st->mut_list[o++] = make_uint4((uint32_t)(chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid), nm[e], rk[e], 0u);
+                    if (rn[e]) st->mut_list[o++] = make_uint4((uint32_t)(chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid), rn[e], h[e], 0u);
             }
         }
         __syncthreads();
