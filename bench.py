@@ -55,8 +55,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="k2_hiv")
-    ap.add_argument("--n", type=int, default=0, help="override N = H = max_population")
-    ap.add_argument("--atomic-host-sum", action="store_true", help="VL_FLAG_ATOMIC_HOST_SUM (not the default path)")
+    ap.add_argument("--n", "--population", dest="n", type=int, default=0, help="override N = H = max_population")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=10)
@@ -152,15 +151,15 @@ def run_b200(args, rank, world):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = workload(args.workload, args.n or None)
-    flags = abi.VL_FLAG_ATOMIC_HOST_SUM if args.atomic_host_sum else 0
+    flags = 0
     par = wl["parameters"]
     N = wl["n0"]
     sim = GpuSimulation(wl["wildtype"], par, wl["specs"], seed=2026, device=local_rank, compartment_id=rank, flags=flags)
     sim.set_population_wildtype(N)
     runner = None
     if world > 1:
-        from virolution_b200.distributed import CompartmentRing
-        runner = CompartmentRing(sim, rank, world, migration=0.1)
+        from virolution_b200.distributed import CompartmentExchange, GpuCompartment
+        runner = CompartmentExchange(GpuCompartment(sim), rank, world, migration=0.1)
 
     def advance(k):
         if runner is None:
@@ -176,10 +175,14 @@ def run_b200(args, rank, world):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if runner is not None and os.environ.get("VL_TRACE"):
+        runner.trace = {}
     # ---- warm-up (untimed): also brings haplotype diversity towards its quasi-steady state
     advance(max(args.warmup, 3))
     barrier()
     sim.infectant_generations(reset=True)
+    if runner is not None and runner.trace is not None:
+        runner.trace = {}
     l0 = sim.get_counters()["kernels_launched"]
     # ---- timed region: exactly K generations, device-resident
     with ClockSampler(local_rank) as clocks:
@@ -190,6 +193,8 @@ def run_b200(args, rank, world):
         ms = sim.timer_stop()
         barrier()
         t_wall = time.perf_counter() - t_wall
+    if runner is not None and runner.trace is not None and rank == 0:
+        print("exchange host seconds per phase over the timed steps:", {k: round(v, 4) for k, v in runner.trace.items()}, file=sys.stderr)
     ig = sim.infectant_generations(reset=True)
     launches = sim.get_counters()["kernels_launched"] - l0
     if dist is not None:
@@ -204,10 +209,12 @@ def run_b200(args, rank, world):
 
     # ---- per-kernel CUDA-event durations over the same loop (separate pass: events perturb the step time)
     roofline, kernels = None, {}
+    # (every rank runs the generations — the exchange is collective — rank 0 alone records events)
     if rank == 0:
         sim.profile(True)
-        sim.run(args.profile_steps) if runner is None else [runner.step() for _ in range(args.profile_steps)]
-        sim.synchronize()
+    advance(args.profile_steps)
+    barrier()
+    if rank == 0:
         rep = sim.profile_report()
         sim.profile(False)
         n_now = sim.population_len()
@@ -253,7 +260,37 @@ def run_b200(args, rank, world):
         e2e = {"value": total / dt, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d // k_e2e, "d2h_bytes_per_step": bytes_d2h // k_e2e,
                "steps": k_e2e, "api": "vl_infect/vl_mutate_infectants/vl_replicate_infectants(host Vec<usize>)/vl_subsample_population(host &[usize])/vl_set_population"}
     elif runner is not None and not args.no_e2e:
-        e2e = runner.e2e(args.steps)
+        # the same trait-level generation per rank (offspring Vec<usize> to the host and back), then the NCCL exchange
+        keep, off_host = pinned_u64(max(N, par.max_population) * 2)
+
+        def dist_generation():
+            n = sim.population_len()
+            sim.increment_generation()
+            sim.infect()
+            sim.mutate_infectants()
+            off = sim.replicate_infectants(out=off_host[:n])
+            sim.target_size(off)      # &[usize] from the host: uploads the map the subsamples below draw from
+            runner.transmit()
+            return n
+        for _ in range(2):
+            dist_generation()
+        barrier()
+        k_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        total = 0
+        for _ in range(k_e2e):
+            total += dist_generation()
+        barrier()
+        dt = time.perf_counter() - t0
+        import torch
+        t = torch.tensor([float(total), dt], dtype=torch.float64, device="cuda")
+        tsum, tmax = t.clone(), t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(tsum[0]) / float(tmax[1]), "unit": UNIT, "h2d_bytes_per_step": int(8 * total // k_e2e) * world,
+               "d2h_bytes_per_step": int((8 * total + 8 * k_e2e) // k_e2e) * world, "steps": k_e2e,
+               "api": "per rank: vl_infect/vl_mutate_infectants/vl_replicate_infectants(host Vec<usize>)/vl_target_size(host &[usize])/"
+                      "vl_subsample_populations + NCCL all-to-all-v of migrant images + vl_set_population"}
 
     out = None
     if rank == 0:
@@ -261,10 +298,10 @@ def run_b200(args, rank, world):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "impl": "b200",
-               "config": {"workload": wl["description"], "compartments": world,
-                          "parallelism": "1 compartment" if world == 1 else f"{world} compartments, 1 per GPU, NCCL all-to-all of migrants (0.9 stay / 0.1 migrate)",
+               "config": {"workload": wl["description"] + ("" if world == 1 else f" per compartment x {world} compartments"), "compartments": world,
+                          "parallelism": "1 compartment" if world == 1 else f"{world} compartments, 1 per GPU, NCCL all-to-all-v of migrant images (0.9 stay / 0.1 migrate uniformly)",
                           "l2_policy": "working set (per-infectant arrays, 32 B x N) larger than L2; no flush" if N * 32 > 126e6 else "working set fits L2 (latency-bound config); no flush",
-                          "host_sum": "atomic" if args.atomic_host_sum else "reference-ordered CSR"},
+                          "host_sum": "reference-ordered CSR"},
                "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clk, "roofline": roofline, "kernels": kernels,
                "e2e": e2e}
         if not args.no_cpu_baseline and world == 1:

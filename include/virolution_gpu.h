@@ -208,6 +208,26 @@ int vl_pop_pack_device(vl_sim *origin, vl_pop *pop, void **image_device, uint64_
 /* Build a detached population on `target` from a packed image located in target-device memory. */
 int vl_pop_unpack_device(vl_sim *target, const void *image_device, uint64_t bytes, vl_pop **out);
 
+/* ---- migrant exchange between processes (one process per GPU) ------------ */
+/* The transmission block (src/runner.rs:401-422) when compartments live in different processes: the origin turns
+ * its per-target parts into ONE flat image whose per-target ranges are contiguous, the caller moves the ranges
+ * with its collective (NCCL all-to-all-v over NVLink in virolution_b200/distributed.py) and every target imports
+ * what it received.  Pointers are device memory owned by the origin handle, valid until its next export. */
+typedef struct vl_migrant_image {
+    const uint32_t *len_device;     /* n_migrants: entries of each migrant's haplotype; 0x80000000 = wildtype */
+    const double *raw_device;       /* n_migrants * n_providers memoised raw fitness, migrant-major */
+    const uint32_t *entries_device; /* n_words flattened haplotype entries, migrant after migrant */
+    uint64_t n_migrants, n_words, n_providers;
+} vl_migrant_image;
+int vl_migrants_export_device(vl_sim *origin, vl_pop *const *parts, uint32_t n_parts, vl_migrant_image *image,
+                              uint64_t *migrants_per_part, uint64_t *words_per_part);
+/* Buffers are device memory of the target's GPU, complete before the call (synchronise the stream that wrote them). */
+int vl_migrants_import_device(vl_sim *target, const uint32_t *len_device, const double *raw_device,
+                              const uint32_t *entries_device, uint64_t n_migrants, uint64_t n_words, vl_pop **out);
+/* n subsamples of the device-resident offspring map, out[k] = subsample_population(&offspring, factors[k]);
+ * one synchronisation for all of them (the per-target parts of one origin, src/runner.rs:404-416). */
+int vl_subsample_populations(vl_sim *sim, const double *factors, uint32_t n, vl_pop **out);
+
 /* ---- measurement hooks (bench.py): CUDA events on the handle's own stream ------------------ */
 int vl_timer_start(vl_sim *sim);
 int vl_timer_stop(vl_sim *sim, double *ms_out);            /* synchronises; device time since vl_timer_start */

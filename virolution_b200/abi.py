@@ -60,6 +60,11 @@ class vl_config(C.Structure):
                 ("capacity_arena_words", C.c_uint64)]
 
 
+class vl_migrant_image(C.Structure):
+    _fields_ = [("len_device", C.c_void_p), ("raw_device", C.c_void_p), ("entries_device", C.c_void_p),
+                ("n_migrants", C.c_uint64), ("n_words", C.c_uint64), ("n_providers", C.c_uint64)]
+
+
 # ----------------------------------------------------------------------------- python-side description
 
 @dataclass

@@ -29,6 +29,7 @@ struct vl_pop {
     uint32_t *ids;   // device, haplotype ids local to owner
     uint64_t n;      // valid after finalisation
     uint64_t cap;
+    uint64_t cap_alloc;  // allocated entries of ids (>= cap when the buffer came from the pool)
     uint8_t *image;  // packed image (vl_pop_pack_device), device
     uint64_t image_bytes;
     int pending_slot;  // pinned slot that receives n, -1 when final
@@ -57,6 +58,10 @@ struct vl_sim {
     uint8_t *rp_rec_which = nullptr; uint64_t rp_rec_n = 0; bool has_rp_rec = false;
     uint64_t *rp_off = nullptr; bool has_rp_off = false;
     std::vector<vl_pop *> pops;
+    struct IdBuf { uint32_t *p; uint64_t cap; };
+    std::vector<IdBuf> id_pool;  // id buffers of dropped populations: reused in stream order, no malloc/free per generation
+    struct DevBuf { void *p = nullptr; uint64_t bytes = 0; };
+    DevBuf mig[9];               // migrant image staging (export: 0-4, import: 5-8), grown on demand
     uint64_t launches = 0;
     uint64_t n_known = 0; bool n_valid = false;   // host knowledge of the population size
     uint64_t n_bound = 0;                         // upper bound of the population size (launch geometry)
@@ -359,6 +364,7 @@ static void destroy_sim(vl_sim *sim) {
         if (p->image) cudaFree(p->image);
         delete p;
     }
+    for (auto &b : sim->id_pool) cudaFree(b.p);
     free_population_buffers(sim);
     if (sim->h.offsets) cudaFree(sim->h.offsets);
     if (sim->count) cudaFree(sim->count);
@@ -367,6 +373,7 @@ static void destroy_sim(vl_sim *sim) {
     void *rp[] = {sim->rp_inf, sim->rp_mut_off, sim->rp_mut_sites, sim->rp_mut_bases, sim->rp_rec_host, sim->rp_rec_i, sim->rp_rec_j,
                   sim->rp_rec_s0, sim->rp_rec_s1, sim->rp_rec_which, sim->rp_off};
     for (void *p : rp) if (p) cudaFree(p);
+    for (auto &b : sim->mig) if (b.p) cudaFree(b.p);
     if (sim->pin) cudaFreeHost(sim->pin);
     for (auto &r : sim->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     if (sim->timer_a) { cudaEventDestroy(sim->timer_a); cudaEventDestroy(sim->timer_b); }
@@ -808,10 +815,23 @@ VL_API int vl_target_size(vl_sim *sim, const uint64_t *offspring, uint64_t n, do
     return check_device_error(sim);
 }
 
+// Detached populations come and go every generation of a multi-compartment run: their id buffers are pooled per
+// handle.  Every user of a buffer is enqueued on the handle's stream, so reuse in stream order needs no synchronisation.
 static vl_pop *new_pop(vl_sim *sim, uint64_t cap) {
     vl_pop *p = new vl_pop();
     p->owner = sim; p->ids = nullptr; p->n = 0; p->cap = cap; p->image = nullptr; p->image_bytes = 0; p->pending_slot = -1;
-    if (cudaMalloc((void **)&p->ids, std::max<uint64_t>(cap, 1) * 4) != cudaSuccess) { delete p; return nullptr; }
+    const uint64_t want = std::max<uint64_t>(cap, 1);
+    int best = -1;
+    for (size_t k = 0; k < sim->id_pool.size(); k++)
+        if (sim->id_pool[k].cap >= want && (best < 0 || sim->id_pool[k].cap < sim->id_pool[best].cap)) best = (int)k;
+    if (best >= 0 && sim->id_pool[best].cap <= 4 * want + 4096) {
+        p->ids = sim->id_pool[best].p;
+        p->cap_alloc = sim->id_pool[best].cap;
+        sim->id_pool.erase(sim->id_pool.begin() + best);
+    } else {
+        if (cudaMalloc((void **)&p->ids, want * 4) != cudaSuccess) { delete p; return nullptr; }
+        p->cap_alloc = want;
+    }
     sim->pops.push_back(p);
     return p;
 }
@@ -819,7 +839,10 @@ static void drop_pop(vl_pop *p) {
     vl_sim *sim = p->owner;
     auto it = std::find(sim->pops.begin(), sim->pops.end(), p);
     if (it != sim->pops.end()) sim->pops.erase(it);
-    if (p->ids) cudaFree(p->ids);
+    if (p->ids) {
+        if (sim->id_pool.size() < 64) sim->id_pool.push_back({p->ids, p->cap_alloc});
+        else cudaFree(p->ids);
+    }
     if (p->image) cudaFree(p->image);
     delete p;
 }
@@ -906,7 +929,7 @@ VL_API int vl_pop_free(vl_pop *pop) {
     if (!pop) return VL_OK;
     vl_sim *sim = pop->owner;
     ENTER(sim);
-    CU(sim, cudaStreamSynchronize(sim->stream));
+    if (pop->image) CU(sim, cudaStreamSynchronize(sim->stream));  // the image is freed, the id buffer goes back to the pool
     drop_pop(pop);
     return VL_OK;
 }
@@ -968,6 +991,121 @@ VL_API int vl_pop_unpack_device(vl_sim *target, const void *image_device, uint64
     p->n = n_pop;
     *out = p;
     return VL_OK;
+}
+
+// ---- migrants between processes: flat per-migrant images (vl_migrate.cuh), moved by the caller's collective
+static int ensure_buf(vl_sim *sim, vl_sim::DevBuf &b, uint64_t bytes) {
+    if (bytes <= b.bytes) return VL_OK;
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = bytes + bytes / 2 + 256;
+    CU(sim, cudaMalloc(&b.p, b.bytes));
+    return VL_OK;
+}
+VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts, vl_migrant_image *image,
+                                     uint64_t *migrants_per_part, uint64_t *words_per_part) {
+    ENTER(sim);
+    if (!image || (n_parts && (!parts || !migrants_per_part || !words_per_part))) return fail(sim, VL_ERR_ARGUMENT, "null argument");
+    if (n_parts > 1024) return fail(sim, VL_ERR_ARGUMENT, "too many parts");
+    bool pending = false;
+    for (uint32_t k = 0; k < n_parts; k++) pending = pending || (parts[k] && parts[k]->pending_slot >= 0);
+    if (pending) CU(sim, cudaStreamSynchronize(sim->stream));
+    uint64_t M = 0;
+    for (uint32_t k = 0; k < n_parts; k++) {
+        if (!parts[k] || parts[k]->owner != sim) return fail(sim, VL_ERR_ARGUMENT, "part %u does not belong to this handle", k);
+        finalize_pop(parts[k]);
+        migrants_per_part[k] = parts[k]->n;
+        M += parts[k]->n;
+    }
+    const uint64_t P = sim->h.n_providers;
+    TRY(ensure_buf(sim, sim->mig[0], (M + 1) * 4));
+    TRY(ensure_buf(sim, sim->mig[1], (M + 1) * 4));
+    TRY(ensure_buf(sim, sim->mig[2], (M * P + 1) * 8));
+    TRY(ensure_buf(sim, sim->mig[3], (M + 2) * 8));
+    uint32_t *len = (uint32_t *)sim->mig[0].p, *words = (uint32_t *)sim->mig[1].p;
+    double *raw = (double *)sim->mig[2].p;
+    uint64_t *off = (uint64_t *)sim->mig[3].p;
+    uint64_t m0 = 0;
+    for (uint32_t k = 0; k < n_parts; k++) {
+        if (parts[k]->n) LAUNCH(sim, k_mig_lens, grid_for(sim, parts[k]->n), TPB, 0, sim->d, (const uint32_t *)parts[k]->ids, parts[k]->n, m0, len, words, raw);
+        m0 += parts[k]->n;
+    }
+    TRY((launch_scan<uint64_t, true>(sim, words, off, nullptr, M, M, sim->gc_totals + 10, 1, nullptr)));
+    m0 = 0;
+    for (uint32_t k = 0; k < n_parts; k++) {  // word offset of every part boundary
+        CU(sim, cudaMemcpyAsync(sim->pin + 64 + k, off + m0, 8, cudaMemcpyDeviceToHost, sim->stream));
+        m0 += parts[k]->n;
+    }
+    CU(sim, cudaMemcpyAsync(sim->pin + 64 + n_parts, sim->gc_totals + 10, 8, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    const uint64_t W = sim->pin[64 + n_parts];
+    for (uint32_t k = 0; k < n_parts; k++) words_per_part[k] = sim->pin[64 + k + 1] - sim->pin[64 + k];
+    TRY(ensure_buf(sim, sim->mig[4], (W + 1) * 4));
+    uint32_t *entries = (uint32_t *)sim->mig[4].p;
+    m0 = 0;
+    for (uint32_t k = 0; k < n_parts; k++) {
+        if (parts[k]->n) LAUNCH(sim, k_mig_copy, grid_for(sim, parts[k]->n), TPB, 0, sim->d, (const uint32_t *)parts[k]->ids, parts[k]->n, m0, (const uint64_t *)off, entries);
+        m0 += parts[k]->n;
+    }
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    image->len_device = len;
+    image->raw_device = raw;
+    image->entries_device = entries;
+    image->n_migrants = M;
+    image->n_words = W;
+    image->n_providers = P;
+    return check_device_error(sim);
+}
+VL_API int vl_migrants_import_device(vl_sim *sim, const uint32_t *len_device, const double *raw_device, const uint32_t *entries_device,
+                                     uint64_t M, uint64_t W, vl_pop **out) {
+    ENTER(sim);
+    if (!out || (M && (!len_device || (sim->h.n_providers && !raw_device))) || (W && !entries_device)) return fail(sim, VL_ERR_ARGUMENT, "null argument");
+    vl_pop *p = new_pop(sim, M);
+    if (!p) return fail(sim, VL_ERR_CUDA, "out of device memory");
+    int r = VL_OK;
+    if (M) {
+        r = ensure_buf(sim, sim->mig[5], (M + 1) * 4);
+        if (r == VL_OK) r = ensure_buf(sim, sim->mig[6], (M + 1) * 4);
+        if (r == VL_OK) r = ensure_buf(sim, sim->mig[7], (M + 2) * 4);
+        if (r == VL_OK) r = ensure_buf(sim, sim->mig[8], (M + 2) * 8);
+        if (r != VL_OK) { drop_pop(p); return r; }
+        uint32_t *words = (uint32_t *)sim->mig[5].p, *rec = (uint32_t *)sim->mig[6].p, *rec_off = (uint32_t *)sim->mig[7].p;
+        uint64_t *word_off = (uint64_t *)sim->mig[8].p;
+        LAUNCH(sim, k_mig_words, grid_for(sim, M), TPB, 0, len_device, M, words, rec);
+        r = launch_scan<uint32_t, true>(sim, rec, rec_off, nullptr, M, M, sim->gc_totals + 12, 0, nullptr);
+        if (r == VL_OK) r = launch_scan<uint64_t, true>(sim, words, word_off, nullptr, M, M, sim->gc_totals + 13, 0, nullptr);
+        if (r != VL_OK) { drop_pop(p); return r; }
+        LAUNCH(sim, k_mig_reserve, 1, 1, 0, sim->d, (const uint64_t *)(sim->gc_totals + 12), W, sim->gc_totals + 14);
+        LAUNCH(sim, k_mig_import, grid_for(sim, M), TPB, 0, sim->d, len_device, raw_device, entries_device, M, (const uint32_t *)rec_off,
+               (const uint64_t *)word_off, (const uint64_t *)(sim->gc_totals + 14), p->ids);
+    }
+    p->n = M;
+    cudaError_t ce = cudaStreamSynchronize(sim->stream);
+    if (ce != cudaSuccess) { drop_pop(p); return fail(sim, VL_ERR_CUDA, "import failed: %s", cudaGetErrorString(ce)); }
+    r = check_device_error(sim);
+    if (r != VL_OK) { drop_pop(p); return r; }
+    *out = p;
+    return VL_OK;
+}
+// several subsamples of the same offspring map with one synchronisation (the per-target parts of one origin,
+// src/runner.rs:404-416)
+VL_API int vl_subsample_populations(vl_sim *sim, const double *factors, uint32_t n, vl_pop **out) {
+    ENTER(sim);
+    if (!factors || !out) return fail(sim, VL_ERR_ARGUMENT, "null argument");
+    if (n >= (uint32_t)PIN_SLOTS - 16) return fail(sim, VL_ERR_ARGUMENT, "too many parts");
+    int r = VL_OK;
+    uint32_t made = 0;
+    for (; made < n && r == VL_OK; made++) { out[made] = nullptr; r = enqueue_subsample(sim, factors[made], 0, 0, &out[made]); }
+    cudaError_t ce = cudaStreamSynchronize(sim->stream);
+    if (r == VL_OK && ce != cudaSuccess) r = fail(sim, VL_ERR_CUDA, "subsample failed: %s", cudaGetErrorString(ce));
+    if (r == VL_OK) r = check_device_error(sim);
+    for (uint32_t k = 0; k < made; k++) {
+        if (!out[k]) continue;
+        if (r == VL_OK) finalize_pop(out[k]);
+        else { drop_pop(out[k]); out[k] = nullptr; }
+    }
+    return r;
 }
 
 VL_API int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts) {

@@ -117,6 +117,77 @@ __global__ void __launch_bounds__(TPB) k_unpack(DevState *st, const uint8_t *__r
     }
 }
 
+// ---- migrants between processes (one process per GPU): per-migrant images, no dedup --------------------------
+// The image of a set of detached populations is three flat arrays over the concatenated migrants:
+//   len[m]      entries of migrant m's haplotype, MIG_WILDTYPE for the wildtype (exists on every handle)
+//   raw[m*P+p]  memoised raw fitness under provider p (AttributeSet, src/core/attributes.rs:196-217)
+//   entries[]   the flattened records, migrant after migrant
+// so the part destined for one target is a contiguous range of each array — what an all-to-all-v wants.  The
+// reference shares one haplotype tree between compartments and moves references (src/runner.rs:401-422); every
+// migrant gets a record of its own on the target, like every mutant gets its own node there.
+constexpr uint32_t MIG_WILDTYPE = 0x80000000u;
+__global__ void __launch_bounds__(TPB) k_mig_lens(DevState *st, const uint32_t *__restrict__ ids, uint64_t m, uint64_t m0,
+                                                  uint32_t *__restrict__ len_out, uint32_t *__restrict__ words_out, double *__restrict__ raw_out) {
+    const uint32_t P = st->n_providers;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        const uint32_t len = id == 0 ? 0u : st->hm[id].len;
+        len_out[m0 + i] = id == 0 ? MIG_WILDTYPE : len;
+        words_out[m0 + i] = len;
+        for (uint32_t p = 0; p < P; p++) raw_out[(m0 + i) * P + p] = hap_raw(st, p, id);
+    }
+}
+__global__ void __launch_bounds__(TPB) k_mig_copy(DevState *st, const uint32_t *__restrict__ ids, uint64_t m, uint64_t m0,
+                                                  const uint64_t *__restrict__ word_off, uint32_t *__restrict__ entries_out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        if (id == 0) continue;
+        const HapMeta hm = st->hm[id];
+        const uint32_t *src = st->arena + hm.off;
+        uint32_t *dst = entries_out + word_off[m0 + i];
+        for (uint32_t k = 0; k < hm.len; k++) dst[k] = src[k];
+    }
+}
+// words per migrant of a received image (the wildtype marker carries no words)
+__global__ void __launch_bounds__(TPB) k_mig_words(const uint32_t *__restrict__ len_in, uint64_t m, uint32_t *__restrict__ words_out,
+                                                   uint32_t *__restrict__ rec_out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t l = len_in[i];
+        words_out[i] = l == MIG_WILDTYPE ? 0u : l;
+        rec_out[i] = l == MIG_WILDTYPE ? 0u : 1u;
+    }
+}
+// totals[0] = records needed, totals[1] = words needed (from the two scans); reserve[0] = first id (NONE32 on failure)
+__global__ void k_mig_reserve(DevState *st, const uint64_t *totals, uint64_t n_words_expected, uint64_t *reserve) {
+    const uint64_t id0 = st->n_hap, a0 = st->arena_top;
+    reserve[0] = NONE32;
+    if (totals[1] != n_words_expected) { raise(st, DE_REPLAY); return; }
+    if (id0 + totals[0] > st->cap_hap) { raise(st, DE_HAP_CAPACITY); return; }
+    if (a0 + totals[1] > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); return; }
+    st->n_hap = id0 + totals[0];
+    st->arena_top = a0 + totals[1];
+    reserve[0] = id0;
+    reserve[1] = a0;
+}
+__global__ void __launch_bounds__(TPB) k_mig_import(DevState *st, const uint32_t *__restrict__ len_in, const double *__restrict__ raw_in,
+                                                    const uint32_t *__restrict__ entries_in, uint64_t m, const uint32_t *__restrict__ rec_off,
+                                                    const uint64_t *__restrict__ word_off, const uint64_t *reserve, uint32_t *__restrict__ ids_out) {
+    const uint64_t id0 = reserve[0], a0 = reserve[1];
+    const bool ok = id0 != NONE32;
+    const uint32_t P = st->n_providers;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t l = len_in[i];
+        if (l == MIG_WILDTYPE || !ok) { ids_out[i] = 0u; continue; }
+        const uint64_t id = id0 + rec_off[i], off = a0 + word_off[i];
+        st->hm[id] = HapMeta{off, l, NONE32};
+        for (uint32_t p = 0; p < P; p++) hap_raw(st, p, id) = raw_in[i * P + p];
+        const uint32_t *src = entries_in + word_off[i];
+        uint32_t *dst = st->arena + off;
+        for (uint32_t k = 0; k < l; k++) dst[k] = src[k];
+        ids_out[i] = (uint32_t)id;
+    }
+}
+
 // population assembly from parts that already live on this handle
 __global__ void __launch_bounds__(TPB) k_copy_ids(DevState *st, const uint32_t *__restrict__ src, uint64_t m, uint64_t dst_off) {
     uint32_t *dst = st->hap_id_next + dst_off;

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import abi
-from .abi import HostSpec, MarshalledConfig, Parameters, vl_config, vl_parameters
+from .abi import HostSpec, MarshalledConfig, Parameters, vl_config, vl_migrant_image, vl_parameters
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvirolution_gpu.so")
@@ -65,6 +65,9 @@ SIGNATURES = {
     "vl_collect_garbage": (C.c_int, [_vp]),
     "vl_pop_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), u64p]),
     "vl_pop_unpack_device": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
+    "vl_migrants_export_device": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32, C.POINTER(vl_migrant_image), u64p, u64p]),
+    "vl_migrants_import_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
+    "vl_subsample_populations": (C.c_int, [_vp, f64p, C.c_uint32, C.POINTER(_vp)]),
     "vl_timer_start": (C.c_int, [_vp]),
     "vl_timer_stop": (C.c_int, [_vp, f64p]),
     "vl_profile": (C.c_int, [_vp, C.c_int]),
@@ -250,6 +253,13 @@ class GpuSimulation:
         self._check(self.lib.vl_subsample_population(self.ptr, ptr, n, factor, C.byref(pop)))
         return GpuPopulation(pop, self)
 
+    def subsample_populations(self, factors) -> List[GpuPopulation]:
+        """[subsample_population(&offspring, f) for f in factors] on the device-resident offspring map, one sync."""
+        f = np.ascontiguousarray(factors, dtype=np.float64)
+        arr = (_vp * max(1, f.size))()
+        self._check(self.lib.vl_subsample_populations(self.ptr, _p(f, C.c_double), f.size, arr))
+        return [GpuPopulation(_vp(arr[k]), self) for k in range(f.size)]
+
     def select(self, indices) -> GpuPopulation:
         idx = np.ascontiguousarray(indices, dtype=np.uint64)
         pop = _vp()
@@ -393,6 +403,23 @@ class GpuSimulation:
 
     def collect_garbage(self):
         self._check(self.lib.vl_collect_garbage(self.ptr))
+
+    def export_migrants(self, parts: Sequence[GpuPopulation]):
+        """Flat image of the parts (one contiguous range per part): -> (vl_migrant_image, migrants_per_part, words_per_part).
+        The image's device pointers stay valid until the next export on this handle."""
+        k = len(parts)
+        arr = (_vp * max(1, k))(*[p.ptr for p in parts])
+        img = vl_migrant_image()
+        m, w = np.zeros(max(1, k), dtype=np.uint64), np.zeros(max(1, k), dtype=np.uint64)
+        self._check(self.lib.vl_migrants_export_device(self.ptr, arr, k, C.byref(img), _p(m, C.c_uint64), _p(w, C.c_uint64)))
+        return img, m[:k], w[:k]
+
+    def import_migrants(self, len_ptr: int, raw_ptr: int, entries_ptr: int, n_migrants: int, n_words: int) -> GpuPopulation:
+        """Detached population from a received image range (device pointers on this handle's GPU, already complete)."""
+        pop = _vp()
+        self._check(self.lib.vl_migrants_import_device(self.ptr, _vp(len_ptr), _vp(raw_ptr), _vp(entries_ptr), n_migrants, n_words,
+                                                       C.byref(pop)))
+        return GpuPopulation(pop, self)
 
     def unpack_device(self, image_ptr: int, nbytes: int) -> GpuPopulation:
         pop = _vp()
