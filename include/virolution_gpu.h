@@ -118,6 +118,8 @@ enum {
     VL_FLAG_NO_BUCKETS = 4, /* build the host map with one histogram atomic per infectant instead of the
                                bucket-partitioned counting sort (same result; the bucketed path needs uniform host
                                draws and H >= 65536, this flag lets tests compare the two) */
+    VL_FLAG_GENERAL_REPLICATE = 8, /* never use the fused replicate kernel (one pass over whole hosts per CTA); the
+                                      general kernels give the same result, this flag lets tests compare the two */
     VL_FLAG_TREE_PLAN = 2 /* split the resampling draws over tiles with the conditional-binomial tree instead of
                              Poissonisation (both exact; the tree is the rare-case fallback, this flag lets tests
                              exercise it) */
@@ -238,6 +240,9 @@ int vl_debug_stamps(vl_sim *sim, uint64_t *out8);          /* %globaltimer stamp
 /* ---- device sampler hooks (distribution tests of the Philox-driven samplers that stand in for
  * rand_distr 0.5.1 Poisson / Binomial and rand 0.9.0 Uniform; call sites src/simulation.rs:47-48,148-151) */
 int vl_test_poisson(uint64_t seed, double lambda, uint64_t n, uint64_t *out);
+/* out2n[0..n) = the replicate kernels' f32-guarded Poisson inversion, out2n[n..2n) = the plain f64 inversion of the
+ * same uniforms (lambda <= 0: a per-draw mean spread over (0,12)); the two halves must be equal. */
+int vl_test_poisson_fast(uint64_t seed, double lambda, uint64_t n, uint64_t *out2n);
 int vl_test_binomial(uint64_t seed, uint64_t trials, double p, uint64_t n, uint64_t *out);
 int vl_test_below(uint64_t seed, uint64_t bound, uint64_t n, uint64_t *out);
 

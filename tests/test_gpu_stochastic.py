@@ -42,6 +42,7 @@ def test_device_poisson_matches_pmf(lam):
 def test_device_binomial_matches_pmf(trials, p):
     n = 400000
     x = S.sampler_binomial(13, trials, p, n).astype(np.int64)
+    assert x.max() <= trials, "the integer thresholds of the product path disagree with the f64 inversion they stand for"
     hi = int(stats.binom.ppf(1 - 1e-7, trials, p)) + 2
     lo = max(0, int(stats.binom.ppf(1e-7, trials, p)) - 2)
     obs = np.bincount(np.clip(x, lo, hi) - lo, minlength=hi - lo + 1)
@@ -248,5 +249,52 @@ def test_bucketed_host_map_equals_atomic_host_map():
     assert sa == sb
     assert np.array_equal(a.get_raw_fitness().view(np.uint64), b.get_raw_fitness().view(np.uint64))
     assert len(set(sa)) > 100
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.05, 0.9, 3.8, 6.0, 11.99])
+def test_guarded_f32_poisson_inversion_equals_f64_inversion(lam):
+    """The replicate kernels decide the Poisson inversion in f32 when the uniform is outside a guard band around every
+    CDF value and in f64 otherwise: the result must be the f64 inversion's for every draw."""
+    from virolution_b200.simulation import sampler_poisson_fast
+    fast, exact = sampler_poisson_fast(17, lam, 4_000_000)
+    assert np.array_equal(fast, exact)
+    if lam > 0:
+        assert abs(fast.mean() - lam) < 6 * np.sqrt(lam / fast.size)
+
+
+@pytest.mark.parametrize("name,n", [("singlehost", 0), ("multihost", 0), ("big", 300000)])
+def test_fused_replicate_equals_general_kernels(name, n):
+    """k_replicate_fused (one pass, whole hosts per CTA, host-range resample tiles) against k_fitness + k_host_sum* +
+    k_offspring (VL_FLAG_GENERAL_REPLICATE, position tiles): same offspring map, same lambda, and — because the
+    resample draws depend on the tile layout — the same *law* of the next generation, checked on sizes."""
+    c = big_singlehost(n=n, mu=1e-4, seed=33) if name == "big" else helpers.case(name)
+    if name == "multihost":  # make every host reachable and populated like the fused path expects (n <= 1.5 H)
+        c = dict(c, n0=1400)
+        c["parameters"].max_population = 1400
+    a = helpers.make_gpu(c)
+    b = helpers.make_gpu(c, flags=abi.VL_FLAG_GENERAL_REPLICATE)
+    for g in range(3):
+        offs = []
+        for s in (a, b):
+            s.increment_generation()
+            s.infect()
+            s.mutate_infectants()
+            offs.append(s.replicate_infectants())
+        assert np.array_equal(offs[0], offs[1]), f"generation {g}: offspring maps differ"
+        fa, sa, la = a.get_replication_terms()
+        fb, sb, lb = b.get_replication_terms()
+        helpers.assert_f64_equal(fa, fb, "mapped fitness")
+        helpers.assert_f64_equal(sa, sb, "host sums")
+        helpers.assert_f64_equal(la, lb, "lambda")
+        assert a.target_size() == b.target_size()
+        assert np.array_equal(a.get_offspring_prefix(), b.get_offspring_prefix())
+        # install the same next population on both (indices drawn on a): the two arms stay comparable generation after generation
+        idx = a.sample_indices(None, int(a.target_size()))
+        w = offs[0].astype(np.float64)
+        assert np.all(w[idx] > 0), "a drawn index must have offspring"
+        a.set_population(a.select(idx))
+        b.set_population(b.select(idx))
     a.close()
     b.close()

@@ -39,6 +39,7 @@ struct vl_sim {
     int device = 0;
     int n_sms = 148;
     int flags = 0;
+    int experiment = 0;  // VL_EXPERIMENT bit mask: kernel-variant switches for A/B timing (development aid, default 0)
     cudaStream_t stream = nullptr;
     std::recursive_mutex mu;
     DevState h;            // host mirror: configuration + buffer pointers (dynamic fields live on the device)
@@ -70,6 +71,7 @@ struct vl_sim {
     bool layout_valid = false;    // rec/offspring/tile_sum describe an offspring map (host map or identity layout)
     bool mutcounts_ready = false; // the fused infect pass already filled the mutation worklist
     bool bucket_pending = false;  // records are bucket-partitioned, the host map is not built yet
+    bool uniform_infection = false;  // the host map came from uniform Philox draws over [0, H) (no replay, DevState::fast_infect)
     uint32_t plan_smem_tiles = 0;
     uint32_t salt = 0;        // distinguishes the sampling streams of one generation
     uint32_t gens_since_gc = 0, gc_period = 1;
@@ -94,7 +96,7 @@ static cudaEvent_t prof_begin(vl_sim *sim, const char *name) {
 
 static thread_local char g_create_err[512];
 constexpr int PIN_SLOTS = 4096;
-constexpr int BSORT_SMEM_BYTES = BUCKET_HOSTS * 4 + BSORT_SMEM_RECS * 10;
+constexpr int BSORT_SMEM_BYTES = BUCKET_HOSTS * 4 + BSORT_STAGE_RECS * 10;
 
 static int fail(vl_sim *sim, int code, const char *fmt, ...) {
     va_list ap;
@@ -181,6 +183,7 @@ static int check_device_error(vl_sim *sim) {
     if (e & DE_SAME_BASE) return fail(sim, VL_ERR_REFERENCE_PANIC, "assert_ne!(from, to) in create_descendant (src/core/haplotype.rs:250)");
     if (e & DE_OFFSPRING_RANGE) return fail(sim, VL_ERR_IMPLEMENTATION, "offspring count does not fit 32 bits");
     if (e & DE_REPLAY) return fail(sim, VL_ERR_ARGUMENT, "malformed replay log or index out of range");
+    if (e & DE_TILE_OVERFLOW) return fail(sim, VL_ERR_IMPLEMENTATION, "host tile overflow (> 13 sigma under uniform infection): rerun with VL_FLAG_GENERAL_REPLICATE");
     if (e & DE_BUCKET_OVERFLOW) return fail(sim, VL_ERR_IMPLEMENTATION, "host bucket overflow (12 sigma event): rerun with VL_FLAG_NO_BUCKETS");
     return fail(sim, VL_ERR_IMPLEMENTATION, "unknown device error 0x%x", e);
 }
@@ -214,6 +217,18 @@ static void free_population_buffers(vl_sim *sim) {
     for (void *p : olds) if (p) cudaFree(p);
     h.tmp_rec = nullptr;
 }
+// tiles the plan/resample arrays can describe: position tiles of the largest population, or host tiles of as many hosts
+static inline uint64_t tile_capacity(uint64_t cap_inf) { return (cap_inf + HT_MIN_HOSTS - 1) / HT_MIN_HOSTS + 2; }
+// hosts per tile of the fused replicate kernel: expected records per tile 8 standard deviations below what a CTA
+// stages (RESAMPLE_TILE), for at most n infectants spread uniformly over H hosts; 0 = do not use host tiles
+static inline uint32_t host_tile_size(uint64_t n, uint64_t H) {
+    if (H == 0) return 0;
+    const double mean_max = 1700.0;  // 1700 + 8 * sqrt(1700) < 2048
+    double ht = floor(mean_max * (double)H / (double)std::max<uint64_t>(n, 1));
+    if (ht > (double)HT_MAX_HOSTS) ht = (double)HT_MAX_HOSTS;
+    if (ht > (double)H) ht = (double)H;
+    return ht < (double)HT_MIN_HOSTS ? 0u : (uint32_t)ht;
+}
 static bool buckets_possible(const vl_sim *sim) {
     const DevState &h = sim->h;
     return h.fast_infect && h.H >= 4 * (uint64_t)BUCKET_HOSTS && h.n_buckets <= (uint32_t)MAX_BUCKETS && !(sim->flags & VL_FLAG_NO_BUCKETS);
@@ -231,7 +246,7 @@ static int alloc_bucket_buffers(vl_sim *sim) {
 static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     DevState &h = sim->h;
     free_population_buffers(sim);
-    const uint64_t nt = (cap + RESAMPLE_TILE - 1) / RESAMPLE_TILE + 1;
+    const uint64_t nt = tile_capacity(cap);
     uint64_t P = 1;
     while (P < nt) P <<= 1;
     TRY(dev_alloc(sim, &h.hap_id, cap + 4, false));
@@ -438,7 +453,8 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     }
     // ---- capacities
     uint64_t cap_inf = cfg->capacity_infectants ? cfg->capacity_infectants : std::max<uint64_t>(2 * par.max_population, 4096);
-    uint64_t cap_hap = cfg->capacity_haplotypes ? cfg->capacity_haplotypes : 3 * cap_inf + 65536;
+    // room for several generations of new records between compactions (HBM is plentiful: 180 GB)
+    uint64_t cap_hap = cfg->capacity_haplotypes ? cfg->capacity_haplotypes : 6 * cap_inf + 65536;
     if (cap_hap >= 0xFFFFFFF0ull) cap_hap = 0xFFFFFFF0ull;
     uint64_t cap_arena = cfg->capacity_arena_words ? cfg->capacity_arena_words : std::max<uint64_t>(16 * cap_hap, 1ull << 20);
     {
@@ -468,7 +484,8 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     h.gc_arena_threshold = cap_arena / 2;
     CTRY(dev_alloc(sim, &h.bucket_fill, MAX_BUCKETS + 1));
     CTRY(dev_alloc(sim, &h.bucket_pos, MAX_BUCKETS + 2));
-    CCU(cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
+    CCU(cudaFuncSetAttribute((k_bucket_sort<1024, BSORT_STAGE_RECS>), cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
+    { const char *e = getenv("VL_EXPERIMENT"); sim->experiment = e ? atoi(e) : 0; }
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
     CTRY(dev_alloc(sim, &h.hm, cap_hap)); CTRY(dev_alloc(sim, &h.hm_alt, cap_hap));
@@ -598,16 +615,21 @@ static int zero_field32(vl_sim *sim, size_t off) {
     CU(sim, cudaMemsetAsync((char *)sim->d + off, 0, 4, sim->stream));
     return VL_OK;
 }
+// n_medium, n_heavy, fused_failed (adjacent in DevState)
+static int zero_replicate_counters(vl_sim *sim) {
+    static_assert(FIELD_OFF(n_heavy) == FIELD_OFF(n_medium) + 4 && FIELD_OFF(fused_failed) == FIELD_OFF(n_medium) + 8, "counters must be adjacent");
+    CU(sim, cudaMemsetAsync((char *)sim->d + FIELD_OFF(n_medium), 0, 12, sim->stream));
+    return VL_OK;
+}
 // descending infectant order inside every slice (the reference's back-fill order); part of k_host_fitness in
 // the replicate phase, run on its own when recombination or an inspection call needs it earlier
 static int ensure_ordered_slices(vl_sim *sim) {
     if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no host map: call vl_infect first");
     if (sim->slices_ordered) return VL_OK;
-    TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
-    TRY(zero_field32(sim, FIELD_OFF(n_medium)));
-    LAUNCH(sim, k_host_sum, grid_for(sim, sim->h.H), TPB, 0, sim->d, 1);
-    LAUNCH(sim, k_host_sum_medium, grid_for(sim, sim->n_bound / 5 + 1, 2), TPB, 0, sim->d, 1);
-    LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 1);
+    TRY(zero_replicate_counters(sim));
+    LAUNCH(sim, k_host_sum, grid_for(sim, sim->h.H), TPB, 0, sim->d, 1, 0);
+    LAUNCH(sim, k_host_sum_medium, grid_for(sim, sim->n_bound / 5 + 1, 2), TPB, 0, sim->d, 1, 0);
+    LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 1, 0);
     sim->slices_ordered = true;
     return VL_OK;
 }
@@ -628,7 +650,8 @@ static int enqueue_host_map(vl_sim *sim) {
 static int enqueue_bucket_host_map(vl_sim *sim) {
     const DevState &h = sim->h;
     LAUNCH(sim, k_bucket_offsets, 1, MAX_BUCKETS / 2, 0, sim->d);
-    LAUNCH(sim, k_bucket_sort, std::min<unsigned>(h.n_buckets, sim->n_sms), BSORT_TPB, BSORT_SMEM_BYTES, sim->d);
+    if (!(sim->experiment & 4)) LAUNCH(sim, (k_bucket_sort<1024, BSORT_STAGE_RECS>), std::min<unsigned>(h.n_buckets, sim->n_sms), 1024, BSORT_SMEM_BYTES, sim->d);
+    else LAUNCH(sim, (k_bucket_sort<512, 0>), std::min<unsigned>(h.n_buckets, sim->n_sms * 4), 512, BUCKET_HOSTS * 4, sim->d);
     sim->bucket_pending = false;
     sim->csr_valid = true;
     sim->slices_ordered = false;
@@ -642,12 +665,18 @@ static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
     const bool fast = h.fast_infect != 0;
     LAUNCH(sim, k_begin_phase, 1, 1, 0, sim->d);
     sim->bucket_pending = false;
+    sim->uniform_infection = fast && !sim->has_rp_inf;
     if (!replay && buckets_possible(sim) && h.cap_tmp >= (uint64_t)h.n_buckets * bucket_stride(sim->n_bound, h.H)) {
         CU(sim, cudaMemsetAsync(h.bucket_fill, 0, (MAX_BUCKETS + 1) * 4, sim->stream));
-        const unsigned chunks = (unsigned)std::max<uint64_t>(1, (sim->n_bound + BUCKET_CHUNK - 1) / BUCKET_CHUNK);
-        const unsigned g = chunks;  // one chunk per CTA: the hardware scheduler balances the tail
-        if (fuse) LAUNCH(sim, k_infect_bucket<true>, g, BUCKET_TPB, 0, sim->d);
-        else LAUNCH(sim, k_infect_bucket<false>, g, BUCKET_TPB, 0, sim->d);
+        const int btpb = (sim->experiment & 2) ? 512 : 1024;
+        const unsigned g = (unsigned)std::max<uint64_t>(1, (sim->n_bound + btpb * BUCKET_ITEMS - 1) / (btpb * BUCKET_ITEMS));  // one chunk per CTA
+        if (btpb == 1024) {
+            if (fuse) LAUNCH(sim, (k_infect_bucket<true, true, 1024>), g, 1024, 0, sim->d);
+            else LAUNCH(sim, (k_infect_bucket<false, true, 1024>), g, 1024, 0, sim->d);
+        } else {
+            if (fuse) LAUNCH(sim, (k_infect_bucket<true, true, 512>), g, 512, 0, sim->d);
+            else LAUNCH(sim, (k_infect_bucket<false, true, 512>), g, 512, 0, sim->d);
+        }
         sim->mutcounts_ready = fuse;
         sim->csr_valid = false;
         sim->slices_ordered = false;
@@ -709,25 +738,49 @@ static int enqueue_mutate(vl_sim *sim) {
 static int enqueue_replicate(vl_sim *sim, int store_lambda = 1) {
     const DevState &h = sim->h;
     if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "replicate needs the host map: call vl_infect first");
-    TRY(zero_field32(sim, FIELD_OFF(n_heavy)));
-    TRY(zero_field32(sim, FIELD_OFF(n_medium)));
-    LAUNCH(sim, k_fitness, grid_for(sim, sim->n_bound), TPB, 0, sim->d);
-    LAUNCH(sim, k_host_sum, grid_for(sim, h.H), TPB, 0, sim->d, 0);
-    LAUNCH(sim, k_host_sum_medium, grid_for(sim, sim->n_bound / 5 + 1, 2), TPB, 0, sim->d, 0);
-    LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 0);
-    sim->slices_ordered = true;
+    TRY(zero_replicate_counters(sim));
     const uint64_t *rpo = sim->has_rp_off ? sim->rp_off : nullptr;
-    if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring<true>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo, store_lambda);
-    else LAUNCH(sim, k_offspring<false>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo, store_lambda);
+    const bool small = h.host_r0 < 12.0;
+    // Fused kernel (one pass, whole hosts per CTA) when a host tile is expected to fit a CTA's staging area; the general
+    // kernels follow guarded by DevState::fused_failed unless the infection was uniform (then a failure is an error).
+    const uint32_t ht = host_tile_size(sim->n_bound, h.H);
+    const uint64_t n_host_tiles = ht ? (h.H + ht - 1) / ht : 0;
+    const bool fused = !(sim->flags & VL_FLAG_GENERAL_REPLICATE) && ht > 0 && n_host_tiles + 1 <= tile_capacity(h.cap_inf);
+    const bool fused_only = fused && sim->uniform_infection;
+    int guarded = 0;
+    if (fused) {
+        const unsigned g = (unsigned)std::min<uint64_t>(n_host_tiles, (uint64_t)sim->n_sms * 16);
+        if (small) LAUNCH(sim, k_replicate_fused<true>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht);
+        else LAUNCH(sim, k_replicate_fused<false>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht);
+        guarded = 1;
+    }
+    if (!fused_only) {
+        LAUNCH(sim, k_fitness, grid_for(sim, sim->n_bound), TPB, 0, sim->d, guarded);
+        LAUNCH(sim, k_host_sum, grid_for(sim, h.H), TPB, 0, sim->d, 0, guarded);
+        LAUNCH(sim, k_host_sum_medium, grid_for(sim, sim->n_bound / 5 + 1, 2), TPB, 0, sim->d, 0, guarded);
+        LAUNCH(sim, k_host_sum_heavy, sim->n_sms, TPB, SMEM_SORT_MAX * 16, sim->d, 0, guarded);
+        if (small) LAUNCH(sim, k_offspring<true>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo, store_lambda, guarded);
+        else LAUNCH(sim, k_offspring<false>, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, rpo, store_lambda, guarded);
+    }
+    sim->slices_ordered = true;
     sim->has_rp_off = false;
     sim->layout_valid = true;
     return VL_OK;
 }
+// upper bound of the number of resample tiles of the current offspring map (either tile kind)
+static inline uint64_t tile_bound(const vl_sim *sim) {
+    const uint32_t ht = host_tile_size(sim->n_bound, sim->h.H);
+    return std::max<uint64_t>((sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE, ht ? (sim->h.H + ht - 1) / ht : 0) + 1;
+}
+static inline unsigned grid_resample(const vl_sim *sim) { return (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8); }
 static int launch_plan(vl_sim *sim, double factor, int use_amount, uint64_t amount, int set_next, uint32_t salt) {
-    const uint64_t nt_bound = (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE + 1;
+    const uint64_t nt_bound = tile_bound(sim);
     const uint32_t smem_tiles = (uint32_t)std::min<uint64_t>(nt_bound, sim->plan_smem_tiles);
     const int force_tree = (sim->flags & VL_FLAG_TREE_PLAN) ? 1 : 0;
-    LAUNCH(sim, k_plan_resample, 1, PLAN_THREADS, smem_tiles * 8, sim->d, factor, use_amount, amount, set_next, salt, force_tree, smem_tiles);
+    CU(sim, cudaMemsetAsync((char *)sim->d + FIELD_OFF(plan_sync), 0, 8 + 4 * 8, sim->stream));
+    // a handful of co-resident CTAs: each draws for its slice of tiles, a counter in DevState is the grid barrier
+    const unsigned ctas = (unsigned)std::min<uint64_t>(PLAN_CTAS, std::max<uint64_t>(1, nt_bound / 256));
+    LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, factor, use_amount, amount, set_next, salt, force_tree, smem_tiles);
     return VL_OK;
 }
 // Population::sample as plan + tile-local draws.  dst == nullptr writes the population being assembled.
@@ -735,7 +788,7 @@ static int enqueue_resample(vl_sim *sim, double factor, int use_amount, uint64_t
     if (!sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one");
     const uint32_t salt = ++sim->salt;
     TRY(launch_plan(sim, factor, use_amount, amount, set_next, salt));
-    LAUNCH(sim, k_resample, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, dst, dst64, mode, salt);
+    LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, dst, dst64, mode, salt);
     return VL_OK;
 }
 static int enqueue_gc(vl_sim *sim, int force) {
@@ -787,6 +840,7 @@ static int upload_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n) 
     sim->csr_valid = false;
     sim->slices_ordered = false;
     sim->layout_valid = true;
+    sim->uniform_infection = false;
     return VL_OK;
 }
 
@@ -874,7 +928,7 @@ static int enqueue_subsample(vl_sim *sim, double factor, int use_amount, uint64_
     if (!sim->layout_valid) { drop_pop(p); return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one"); }
     const uint32_t salt = ++sim->salt;
     TRY(launch_plan(sim, factor, use_amount, amount, 0, salt));
-    LAUNCH(sim, k_resample, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d, p->ids, (uint64_t *)nullptr, 0, salt);
+    LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, p->ids, (uint64_t *)nullptr, 0, salt);
     int slot = sim->next_slot++;
     if (sim->next_slot >= PIN_SLOTS) sim->next_slot = 8;
     CU(sim, cudaMemcpyAsync(sim->pin + slot, (const char *)sim->d + FIELD_OFF(n_next), 8, cudaMemcpyDeviceToHost, sim->stream));
@@ -1170,11 +1224,29 @@ VL_API int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts
 // ---------------------------------------------------------------------------------------------- fused loops
 static int enqueue_generation(vl_sim *sim) {
     // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
-    LAUNCH(sim, k_tick, 1, 1, 0, sim->d);
+    const DevState &h = sim->h;
+    const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
     sim->salt = 0;
-    TRY(enqueue_infect(sim, true));
-    TRY(enqueue_mutate(sim));
-    if (!sim->csr_valid) TRY(sim->bucket_pending ? enqueue_bucket_host_map(sim) : enqueue_host_map(sim));
+    if (!(sim->experiment & 1) && !replay && h.binv.ok && !(h.host_recombination_rate > 0.0) && buckets_possible(sim) &&
+        h.cap_tmp >= (uint64_t)h.n_buckets * bucket_stride(sim->n_bound, h.H)) {
+        // uniform infection (every infectant is infected, hosts iid uniform): the mutation count of an infectant does not
+        // depend on its host, so mutate first and build the host map from the already-mutated population
+        LAUNCH(sim, k_begin_generation, 1, 1024, 0, sim->d);
+        LAUNCH(sim, k_mutcount_fast, grid_tiles(sim, sim->n_bound, (uint64_t)TPB * MC_ITEMS, 8), TPB, 0, sim->d);
+        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, 0, sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0);
+        const int btpb = (sim->experiment & 2) ? 512 : 1024;
+        const unsigned chunks = (unsigned)std::max<uint64_t>(1, (sim->n_bound + btpb * BUCKET_ITEMS - 1) / (btpb * BUCKET_ITEMS));
+        if (btpb == 1024) LAUNCH(sim, (k_infect_bucket<false, false, 1024>), chunks, 1024, 0, sim->d);
+        else LAUNCH(sim, (k_infect_bucket<false, false, 512>), chunks, 512, 0, sim->d);
+        sim->uniform_infection = true;
+        sim->mutcounts_ready = false;
+        TRY(enqueue_bucket_host_map(sim));
+    } else {
+        LAUNCH(sim, k_tick, 1, 1, 0, sim->d);
+        TRY(enqueue_infect(sim, true));
+        TRY(enqueue_mutate(sim));
+        if (!sim->csr_valid) TRY(sim->bucket_pending ? enqueue_bucket_host_map(sim) : enqueue_host_map(sim));
+    }
     TRY(enqueue_replicate(sim, 0));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
     swap_population(sim);
@@ -1556,6 +1628,15 @@ static int run_sampler(int which, uint64_t seed, uint64_t a, double b, uint64_t 
     else if (which == 1) k_test_binomial<<<g, 256>>>(seed, a, b, n, dev, make_binv(a, b));
     else k_test_below<<<g, 256>>>(seed, a, n, dev);
     cudaError_t e = cudaMemcpy(out, dev, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(nullptr, VL_ERR_CUDA, "sampler kernel failed: %s", cudaGetErrorString(e));
+    return VL_OK;
+}
+VL_API int vl_test_poisson_fast(uint64_t seed, double lambda, uint64_t n, uint64_t *out2n) {
+    uint64_t *dev = nullptr;
+    if (cudaMalloc((void **)&dev, std::max<uint64_t>(2 * n, 1) * 8) != cudaSuccess) return fail(nullptr, VL_ERR_CUDA, "no CUDA device / out of memory");
+    k_test_poisson_fast<<<(unsigned)std::min<uint64_t>((n + 255) / 256 + 1, 4096), 256>>>(seed, lambda, n, dev);
+    cudaError_t e = cudaMemcpy(out2n, dev, 2 * n * 8, cudaMemcpyDeviceToHost);
     cudaFree(dev);
     if (e != cudaSuccess) return fail(nullptr, VL_ERR_CUDA, "sampler kernel failed: %s", cudaGetErrorString(e));
     return VL_OK;

@@ -30,6 +30,7 @@
 namespace vl {
 
 constexpr int TPB = 256;
+constexpr uint32_t MAX_BUCKETS_C = 2048;  // = MAX_BUCKETS (declared with the bucketed kernels)
 constexpr uint32_t THREAD_TIER = 32;      // slices up to this length are handled by one thread
 constexpr uint32_t SMEM_SORT_MAX = 4096;  // slices up to this length are sorted in shared memory (u64 keys)
 constexpr int INFECT_ITEMS = 4;           // infectants per thread and round in k_infect / k_scatter
@@ -81,6 +82,17 @@ __global__ void k_begin_phase(DevState *st) {
     st->n_heavy = 0;
     st->n_medium = 0;
 }
+// everything the fused generation clears or bumps before its first real kernel, in one launch
+__global__ void __launch_bounds__(1024) k_begin_generation(DevState *st) {
+    for (uint32_t b = threadIdx.x; b <= MAX_BUCKETS_C; b += blockDim.x) st->bucket_fill[b] = 0u;
+    if (threadIdx.x == 0) {
+        st->generation += 1;  // Simulation::increment_generation (src/simulation.rs:178)
+        st->n_mut_list = 0;
+        st->n_heavy = 0;
+        st->n_medium = 0;
+        st->fused_failed = 0;
+    }
+}
 
 // ------------------------------------------------------------------------------------------ infect
 // BasicHost::infect with n_hits > 1, several specs or an infective provider (src/simulation.rs:56-65):
@@ -111,9 +123,12 @@ __device__ __noinline__ uint32_t mutation_count_binv(const DevState *st, PhiloxK
 }
 // small-mean regime only (BinvConst::ok): what the fused infect kernel calls
 __device__ __forceinline__ uint32_t mutation_count_small(const DevState *st, PhiloxKey key, uint64_t i, uint32_t gen, uint4 b0) {
-    const double u = u01_from(b0.z, b0.w);
-    if (!(u > st->binv.qn)) return 0;  // the common case: no mutation
-    return mutation_count_binv(st, key, i, gen, u);
+    const uint64_t U = (((uint64_t)b0.w << 32) | b0.z) >> 11;  // u01_from(b0.z, b0.w) = U * 2^-53
+    if (U < st->binv.thr[0]) return 0;  // the common case: no mutation
+    uint32_t k = 1;
+    while (k < (uint32_t)BINV_THRESHOLDS && U >= st->binv.thr[k]) k++;
+    if (k < (uint32_t)BINV_THRESHOLDS) return k;
+    return mutation_count_binv(st, key, i, gen, u01_from(b0.z, b0.w));
 }
 __device__ __forceinline__ uint32_t mutation_count(const DevState *st, PhiloxKey key, uint64_t i, uint32_t gen, uint4 b0) {
     if (st->binv.ok) return mutation_count_small(st, key, i, gen, b0);
@@ -217,10 +232,12 @@ constexpr int BUCKET_ITEMS = 8;
 constexpr int BUCKET_CHUNK = BUCKET_TPB * BUCKET_ITEMS;
 constexpr int MAX_BUCKETS = 2048;
 
-template <bool FUSE_MUT>
-__global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
+// STORE_HOST: keep host_id[] (the reference's `infections`) for the trait-level phases and inspection calls; the fused
+// generation does not read it back.
+template <bool FUSE_MUT, bool STORE_HOST, int BTPB>
+__global__ void __launch_bounds__(BTPB) k_infect_bucket(DevState *st) {
     __shared__ uint32_t s_hist[MAX_BUCKETS];   // per-chunk count, then global base of the chunk's run per bucket
-    __shared__ uint32_t s_w[BUCKET_TPB / 32];
+    __shared__ uint32_t s_w[BTPB / 32];
     __shared__ uint32_t s_lbase;
     const uint64_t n = st->n;
     const uint32_t H32 = (uint32_t)st->H;
@@ -232,16 +249,16 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
     const uint32_t *__restrict__ hap_id = st->hap_id;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->infectant_generations += n;
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t n_chunks = (n + BUCKET_CHUNK - 1) / BUCKET_CHUNK;
+    const uint64_t n_chunks = (n + (BTPB * BUCKET_ITEMS) - 1) / (BTPB * BUCKET_ITEMS);
     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        for (uint32_t b = tid; b < B; b += BUCKET_TPB) s_hist[b] = 0;
+        for (uint32_t b = tid; b < B; b += BTPB) s_hist[b] = 0;
         __syncthreads();
         // coalesced layout: item e of thread t is infectant chunk*CHUNK + e*TPB + t.  Per item two registers survive
         // the barriers: the host, and (rank inside the chunk's bucket run | n_mut << 16).
         uint32_t h[BUCKET_ITEMS], rn[BUCKET_ITEMS];
 #pragma unroll
         for (int e = 0; e < BUCKET_ITEMS; e++) {
-            const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
+            const uint64_t i = chunk * (BTPB * BUCKET_ITEMS) + (uint64_t)e * BTPB + tid;
             h[e] = NONE32;
             rn[e] = 0;
             if (i >= n) continue;
@@ -252,14 +269,14 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
                 for (uint32_t blk = 1; (uint32_t)m < thr; blk++) m = (uint64_t)philox_block(key, i, gen, PH_INFECT, blk).x * H32;
             }
             h[e] = (uint32_t)(m >> 32);
-            host_id[i] = h[e];
+            if (STORE_HOST) host_id[i] = h[e];
             uint32_t nm = 0;
             if (FUSE_MUT) nm = min(mutation_count_small(st, key, i, gen, b0), 0xFFFFu);
             rn[e] = atomicAdd(&s_hist[h[e] >> BUCKET_SHIFT], 1u) | (nm << 16);
         }
         __syncthreads();
         // one global atomic per (chunk, bucket): the run of this chunk inside the bucket's region
-        for (uint32_t b = tid; b < B; b += BUCKET_TPB) {
+        for (uint32_t b = tid; b < B; b += BTPB) {
             const uint32_t c = s_hist[b];
             s_hist[b] = c ? atomicAdd(&st->bucket_fill[b], c) : 0u;
         }
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
 #pragma unroll
         for (int e = 0; e < BUCKET_ITEMS; e++) {
             if (h[e] == NONE32) continue;
-            const uint64_t i = chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid;
+            const uint64_t i = chunk * (BTPB * BUCKET_ITEMS) + (uint64_t)e * BTPB + tid;
             const uint32_t b = h[e] >> BUCKET_SHIFT;
             const uint64_t r = (uint64_t)s_hist[b] + (rn[e] & 0xFFFFu);
             const uint32_t nm = rn[e] >> 16;
@@ -295,7 +312,7 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
             __syncthreads();
             uint32_t woff = 0, tot = 0;
 #pragma unroll
-            for (int w = 0; w < BUCKET_TPB / 32; w++) {
+            for (int w = 0; w < BTPB / 32; w++) {
                 const uint32_t t = s_w[w];
                 if (w < (int)wid) woff += t;
                 tot += t;
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(BUCKET_TPB) k_infect_bucket(DevState *st) {
                 uint32_t o = s_lbase + woff + inc - mine;
 #pragma unroll
                 for (int e = 0; e < BUCKET_ITEMS; e++)
-                    if (rn[e]) st->mut_list[o++] = make_uint4((uint32_t)(chunk * BUCKET_CHUNK + (uint64_t)e * BUCKET_TPB + tid), rn[e], h[e], 0u);
+                    if (rn[e]) st->mut_list[o++] = make_uint4((uint32_t)(chunk * (BTPB * BUCKET_ITEMS) + (uint64_t)e * BTPB + tid), rn[e], h[e], 0u);
             }
         }
         __syncthreads();
@@ -343,38 +360,40 @@ __global__ void __launch_bounds__(MAX_BUCKETS / 2) k_bucket_offsets(DevState *st
 // The records are staged in shared memory as well when the bucket fits (one global read per record); writes
 // offsets[] for the bucket's hosts and the records at their CSR positions (a window of ~100 KB that stays in L2
 // until its sectors are complete).
-constexpr int BSORT_TPB = 1024;
-constexpr uint32_t BSORT_SMEM_RECS = 11264;  // staged records per bucket: 11264 * 12 B = 132 KB next to the 32 KB histogram
-__global__ void __launch_bounds__(BSORT_TPB) k_bucket_sort(DevState *st) {
+// SRECS > 0: records of a bucket that fits are staged in shared memory between the two passes (one CTA per SM);
+// SRECS == 0: the second pass re-reads them through L2, which leaves room for several CTAs per SM.
+constexpr uint32_t BSORT_STAGE_RECS = 11264;  // 11264 * 10 B = 110 KB next to the 32 KB histogram
+template <int STPB, uint32_t SRECS>
+__global__ void __launch_bounds__(STPB) k_bucket_sort(DevState *st) {
     extern __shared__ uint32_t s_dyn32[];
     uint32_t *s_cnt = s_dyn32;                                               // BUCKET_HOSTS counters, then running cursors
-    uint2 *s_rec = reinterpret_cast<uint2 *>(s_dyn32 + BUCKET_HOSTS);        // BSORT_SMEM_RECS (index, haplotype)
-    uint16_t *s_hl = reinterpret_cast<uint16_t *>(s_rec + BSORT_SMEM_RECS);  // BSORT_SMEM_RECS host - first host of the bucket
-    __shared__ uint32_t s_w[BSORT_TPB / 32];
+    uint2 *s_rec = reinterpret_cast<uint2 *>(s_dyn32 + BUCKET_HOSTS);        // SRECS (index, haplotype)
+    uint16_t *s_hl = reinterpret_cast<uint16_t *>(s_rec + SRECS);  // SRECS host - first host of the bucket
+    __shared__ uint32_t s_w[STPB / 32];
     const uint32_t B = st->n_buckets;
     const uint64_t H = st->H;
     const uint64_t stride = bucket_stride(st->n, H);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr uint32_t SEG = BUCKET_HOSTS / (BSORT_TPB / 32);  // hosts scanned per warp
+    constexpr uint32_t SEG = BUCKET_HOSTS / (STPB / 32);  // hosts scanned per warp
     for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
         const uint32_t fill = min(st->bucket_fill[b], (uint32_t)stride);
         const uint4 *__restrict__ src = st->tmp_rec + (uint64_t)b * stride;
         const uint32_t h0 = b << BUCKET_SHIFT;
         const uint32_t pos0 = st->bucket_pos[b];
         const uint32_t nh = (uint32_t)min((uint64_t)BUCKET_HOSTS, H - h0);
-        const bool staged = fill <= BSORT_SMEM_RECS;
-        for (uint32_t k = tid; k < BUCKET_HOSTS; k += BSORT_TPB) s_cnt[k] = 0;
+        const bool staged = fill <= SRECS;
+        for (uint32_t k = tid; k < BUCKET_HOSTS; k += STPB) s_cnt[k] = 0;
         __syncthreads();
-        for (uint32_t j0 = tid; j0 < fill; j0 += 4 * BSORT_TPB) {  // four independent loads in flight per thread
+        for (uint32_t j0 = tid; j0 < fill; j0 += 4 * STPB) {  // four independent loads in flight per thread
             uint4 r[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint32_t j = j0 + u * BSORT_TPB;
+                const uint32_t j = j0 + u * STPB;
                 r[u] = j < fill ? src[j] : make_uint4(0u, 0u, h0, 0u);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint32_t j = j0 + u * BSORT_TPB;
+                const uint32_t j = j0 + u * STPB;
                 if (j >= fill) continue;
                 const uint32_t hl = r[u].z - h0;
                 atomicAdd(&s_cnt[hl], 1u);
@@ -407,12 +426,22 @@ __global__ void __launch_bounds__(BSORT_TPB) k_bucket_sort(DevState *st) {
             if (k < nh) st->offsets[h0 + k] = pos0 + o;
         }
         __syncthreads();
-        for (uint32_t j = tid; j < fill; j += BSORT_TPB) {
-            uint2 r;
-            uint32_t hl;
-            if (staged) { r = s_rec[j]; hl = s_hl[j]; }
-            else { const uint4 q = src[j]; r = make_uint2(q.x, q.y); hl = q.z - h0; }
-            st->rec[pos0 + atomicAdd(&s_cnt[hl], 1u)] = r;
+        if (staged) {
+            for (uint32_t j = tid; j < fill; j += STPB) st->rec[pos0 + atomicAdd(&s_cnt[s_hl[j]], 1u)] = s_rec[j];
+        } else {
+            for (uint32_t j0 = tid; j0 < fill; j0 += 4 * STPB) {  // second read: L2 hits, four in flight per thread
+                uint4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t j = j0 + u * STPB;
+                    q[u] = j < fill ? src[j] : make_uint4(0u, 0u, h0, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t j = j0 + u * STPB;
+                    if (j < fill) st->rec[pos0 + atomicAdd(&s_cnt[q[u].z - h0], 1u)] = make_uint2(q[u].x, q[u].y);
+                }
+            }
         }
         __syncthreads();
     }
@@ -456,7 +485,7 @@ __global__ void __launch_bounds__(TPB) k_scatter(DevState *st) {
 __global__ void __launch_bounds__(TPB) k_identity_records(DevState *st) {
     const uint64_t n = st->n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) st->rec[i] = make_uint2((uint32_t)i, st->hap_id[i]);
-    if (blockIdx.x == 0 && threadIdx.x == 0) st->n_sorted = n;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_sorted = n; st->host_tiles = 0; }
 }
 
 // ------------------------------------------------------------------------------------------ haplotype records
@@ -695,19 +724,59 @@ __global__ void __launch_bounds__(TPB) k_mutation_counts(DevState *st, ReplayMut
     }
 }
 
+// Mutation worklist of a uniformly infected population (DevState::fast_infect: every infectant is infected): the count
+// of infectant i is a function of (seed, generation, i) alone — words z,w of block 0 of its PH_INFECT stream, the same
+// uniform the fused infect kernels use — so the fused generation can mutate BEFORE it builds the host map and no
+// record needs patching afterwards.  One global atomic per CTA and round.
+constexpr int MC_ITEMS = 8;
+__global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
+    __shared__ uint32_t s_base;
+    const uint64_t n = st->n;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    const uint32_t gen = st->generation;
+    const uint64_t chunk = (uint64_t)TPB * MC_ITEMS;
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        uint32_t nm[MC_ITEMS];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < MC_ITEMS; e++) {
+            const uint64_t i = c * chunk + (uint64_t)e * TPB + threadIdx.x;
+            nm[e] = 0;
+            if (i < n) nm[e] = mutation_count_small(st, key, i, gen, philox_block(key, i, gen, PH_INFECT, 0));
+            mine += nm[e] ? 1u : 0u;
+        }
+        uint32_t tot;
+        const uint32_t off = block_excl_scan(mine, &tot);
+        if (threadIdx.x == 0 && tot) s_base = atomicAdd(&st->n_mut_list, tot);
+        __syncthreads();
+        if (mine) {
+            uint32_t o = s_base + off;
+#pragma unroll
+            for (int e = 0; e < MC_ITEMS; e++)
+                if (nm[e]) st->mut_list[o++] = make_uint4((uint32_t)(c * chunk + (uint64_t)e * TPB + threadIdx.x), nm[e], NONE32, 0u);
+        }
+        __syncthreads();
+    }
+}
+
 // One thread per mutated infectant: draw sites (with replacement) and sort them, look up the current base
 // on the pre-mutation haplotype, draw the substitution, merge into a new flattened record and update the
 // raw fitness of every provider incrementally: raw(parent) * fold(acc * T[pos,to] / T[pos,from])
 // (src/core/fitness/table.rs:65-68) [* epistatic update].  patch_records: 1 = the infectant's CSR record is
 // patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist.
+constexpr uint32_t MUT_LOCAL_PARENT = 16;  // parent records up to this length are staged in thread-local memory
+constexpr uint32_t MUT_LOCAL_CHANGES = 8;  // mutation events up to this many sites keep their change words there too
 __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records) {
     const uint32_t n_list = st->n_mut_list;
     const uint32_t L = st->L;
     const uint8_t *__restrict__ wt = st->wildtype;
     const uint32_t span = gridDim.x * blockDim.x;
-    const uint32_t rounds = (n_list + span - 1) / span;
-    for (uint32_t r = 0; r < rounds; r++) {
-        const uint32_t w = r * span + blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    // every warp walks the worklist 32 items at a time: record ids and arena words are reserved per warp (two atomics
+    // per 32 records, no CTA-wide barrier anywhere in this kernel)
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_list; base += span) {
+        const uint32_t w = base + lane;
         const bool active = w < n_list;
         uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32;
         HapMeta pm{0, 0, NONE32};
@@ -720,11 +789,39 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
             pm = st->hm[pid];  // one 16-byte load: arena offset, length, parent
             plen = pm.len;
         }
-        NewRecord rec = reserve_record(st, active, plen + 2 * nm);
-        if (!rec.ok) continue;
+        const uint32_t words = active ? plen + 2 * nm : 0u;
+        uint32_t inc = words;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
+        unsigned long long abase = 0, ibase = 0;
+        if (lane == 0) {
+            abase = atomicAdd(&st->arena_top, (unsigned long long)wtot);
+            ibase = atomicAdd(&st->n_hap, (unsigned long long)__popc(amask));
+        }
+        abase = __shfl_sync(0xFFFFFFFFu, abase, 0);
+        ibase = __shfl_sync(0xFFFFFFFFu, ibase, 0);
+        if (!active) continue;
+        const uint64_t roff = abase + (inc - words);
+        const uint64_t id64 = ibase + __popc(amask & ((1u << lane) - 1u));
+        if (id64 >= st->cap_hap) { raise(st, DE_HAP_CAPACITY); continue; }
+        if (roff + words > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); continue; }
+        const uint32_t new_id = (uint32_t)id64;
+        uint32_t *out = st->arena + roff;
+        // parent entries and change words in thread-local memory when they are short (the usual case): every lookup
+        // below is then an L1 hit instead of a dependent trip to L2/HBM
+        uint32_t pe_local[MUT_LOCAL_PARENT], ch_local[MUT_LOCAL_CHANGES];
         const uint32_t *pe = st->arena + pm.off;
-        uint32_t *out = st->arena + rec.off;
-        uint32_t *chs = out + plen + nm;
+        if (plen <= MUT_LOCAL_PARENT) {
+#pragma unroll
+            for (uint32_t k = 0; k < MUT_LOCAL_PARENT; k++) pe_local[k] = k < plen ? pe[k] : 0xFFFFFFFFu;
+            pe = pe_local;
+        }
+        uint32_t *chs = nm <= MUT_LOCAL_CHANGES ? ch_local : out + plen + nm;
         if (replay) {
             const uint64_t ro = rp.offsets[i];
             for (uint32_t k = 0; k < nm; k++) {
@@ -776,26 +873,27 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
             const DevProvider &pr = st->prov[p];
             double raw = 1.0;
             if (pr.kind != VL_FITNESS_NEUTRAL) {
+                const double praw = st->h_raw[p][pid];
                 double acc = 1.;
                 for (uint32_t k = 0; k < nm; k++) {
                     const uint64_t row = (uint64_t)ch_pos(chs[k]) * 4;
                     acc = acc * pr.table[row + ch_to(chs[k])] / pr.table[row + ch_from(chs[k])];
                 }
                 if (pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, out, o);
-                raw = st->h_raw[p][pid] * acc;
+                raw = praw * acc;
             }
-            st->h_raw[p][rec.id] = raw;
+            st->h_raw[p][new_id] = raw;
         }
-        st->hm[rec.id] = HapMeta{rec.off, o, pid};
-        st->hap_id[i] = rec.id;
+        st->hm[new_id] = HapMeta{roff, o, pid};
+        st->hap_id[i] = new_id;
         if (patch_records == 2) {
-            if (tpos != NONE32) st->tmp_rec[tpos].y = rec.id;  // the bucket-partitioned record, not yet sorted
+            if (tpos != NONE32) st->tmp_rec[tpos].y = new_id;  // the bucket-partitioned record, not yet sorted
         } else if (patch_records) {
             const uint32_t h = st->host_id[i];
             if (h != NONE32) {
                 const uint32_t sb = st->offsets[h], se = st->offsets[h + 1];
                 for (uint32_t q = sb; q < se; q++)
-                    if (st->rec[q].x == i) { st->rec[q].y = rec.id; break; }
+                    if (st->rec[q].x == i) { st->rec[q].y = new_id; break; }
             }
         }
     }
@@ -829,7 +927,9 @@ __device__ __forceinline__ int find_spec_of_position(const DevState *st, uint64_
 
 // One thread per CSR position: mapped reproductive fitness of the record's haplotype (the random gather of the
 // generation), parked in lam[p] until k_host_sum turns it into the Poisson mean.
-__global__ void __launch_bounds__(TPB) k_fitness(DevState *st) {
+// `guarded`: run only if the fused replicate kernel gave up on this population (DevState::fused_failed)
+__global__ void __launch_bounds__(TPB) k_fitness(DevState *st, int guarded) {
+    if (guarded && !st->fused_failed) return;
     const uint64_t m = st->n_sorted;
     const uint2 *__restrict__ rec = st->rec;
     double *__restrict__ lam = st->lam;
@@ -858,7 +958,8 @@ __device__ __forceinline__ void sort_slice_desc(uint2 *rec, double *lam, uint32_
 // One thread per host: order the slice, S_h = sum of f over the slice in slice order from 0.0 (iter().sum(),
 // src/simulation.rs:144), left at every member's CSR position (hs[p]); the division that turns (f, S) into the
 // Poisson mean happens position-parallel in k_offspring.  Long slices go to the heavy list.
-__global__ void __launch_bounds__(TPB) k_host_sum(DevState *st, int order_only) {
+__global__ void __launch_bounds__(TPB) k_host_sum(DevState *st, int order_only, int guarded) {
+    if (guarded && !st->fused_failed) return;
     const uint64_t H = st->H;
     const uint32_t *__restrict__ offsets = st->offsets;
     uint2 *rec = st->rec;
@@ -903,7 +1004,8 @@ __global__ void __launch_bounds__(TPB) k_host_sum(DevState *st, int order_only) 
     }
 }
 // One thread per listed host (5 .. THREAD_TIER members): insertion sort, sequential sum
-__global__ void __launch_bounds__(TPB) k_host_sum_medium(DevState *st, int order_only) {
+__global__ void __launch_bounds__(TPB) k_host_sum_medium(DevState *st, int order_only, int guarded) {
+    if (guarded && !st->fused_failed) return;
     const uint32_t n_medium = st->n_medium;
     const uint32_t *__restrict__ offsets = st->offsets;
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_medium; w += gridDim.x * blockDim.x) {
@@ -920,7 +1022,8 @@ __global__ void __launch_bounds__(TPB) k_host_sum_medium(DevState *st, int order
 // One CTA per heavy slice: normalised bitonic network on (index << 32 | haplotype) keys with the fitness as
 // payload, larger index first (missing partners beyond the slice end are no-ops), in shared memory when the
 // slice fits, else in global memory; then the sum strictly sequential in slice order, lambda in parallel.
-__global__ void __launch_bounds__(TPB) k_host_sum_heavy(DevState *st, int order_only) {
+__global__ void __launch_bounds__(TPB) k_host_sum_heavy(DevState *st, int order_only, int guarded) {
+    if (guarded && !st->fused_failed) return;
     extern __shared__ unsigned long long s_dyn[];
     __shared__ double s_S;
     unsigned long long *s_keys = s_dyn;
@@ -993,9 +1096,11 @@ __global__ void __launch_bounds__(TPB) k_host_sum_heavy(DevState *st, int order_
 // SMALL_ONLY: every mean is below 12 (R0 < 12 and lambda = R0 * f/S <= R0), so the rejection sampler is not compiled in.
 // store_lambda: keep the Poisson mean in lam[p] for vl_get_replication_terms (trait-level calls; the fused loop skips the store)
 template <bool SMALL_ONLY>
-__global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda) {
+__global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda, int guarded) {
     __shared__ uint64_t s_red[TPB / 32];
     __shared__ double s_rcp[POISSON_RCP];
+    if (guarded && !st->fused_failed) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->host_tiles = 0;  // this kernel's tile totals are per RESAMPLE_TILE positions
     poisson_rcp_init(s_rcp);
     __syncthreads();
     const uint64_t m = st->n_sorted;
@@ -1043,9 +1148,168 @@ __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t 
         __syncthreads();
     }
 }
+// ---- fused replicate: fitness gather + in-host order + per-host sum + lambda + Poisson in ONE pass -----------------
+// One CTA per host tile (`ht` consecutive hosts = a contiguous range of CSR positions, whole hosts only), every phase
+// position-parallel with the tile's records, fitness values and host boundaries in shared memory:
+//   1. stage offsets and records (coalesced), gather the mapped fitness of every record (the generation's random
+//      gather), mark the first position of every non-empty host in a bit mask;
+//   2. every record finds its slice in the bit mask, ranks itself by descending infectant index (the reference's
+//      in-host order) and moves to its rank (written back to rec[] only where that changes something);
+//   3. every position sums its slice in slice order from 0.0, forms lambda = f * R0 / S, draws Poisson(lambda),
+//      stores the offspring count (coalesced) and adds to the tile total.
+// Same arithmetic, same Philox addresses and the same results as k_fitness + k_host_sum* + k_offspring; what it saves
+// is three round trips of per-position f64 arrays through HBM and the host-parallel passes' idle lanes.  A tile that
+// does not fit (more than RESAMPLE_TILE records, or a slice beyond the thread tier) sets DevState::fused_failed and
+// the general kernels redo the phase (`fail_is_error`: the caller enqueued no fallback because uniform infection
+// makes that a > 8 sigma event).
+constexpr int REPL_TPB = 512;
+constexpr int REPL_PER = RESAMPLE_TILE / REPL_TPB;
+template <bool SMALL_ONLY>
+__global__ void __launch_bounds__(REPL_TPB, 2) k_replicate_fused(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda,
+                                                                 int fail_is_error, uint32_t ht) {
+    __shared__ uint32_t s_off[HT_MAX_HOSTS + 1];
+    __shared__ uint32_t s_head[RESAMPLE_TILE / 32 + 2];
+    __shared__ double s_f[RESAMPLE_TILE];
+    __shared__ uint2 s_rec[RESAMPLE_TILE];
+    __shared__ uint32_t s_red[REPL_TPB / 32];
+    __shared__ double s_rcp[POISSON_RCP];
+    poisson_rcp_init(s_rcp);
+    const uint64_t H = st->H;
+    const uint64_t nt = (H + ht - 1) / ht;
+    const uint32_t *__restrict__ offsets = st->offsets;
+    uint2 *rec = st->rec;
+    uint32_t *__restrict__ offspring = st->offspring;
+    double *__restrict__ lam = st->lam;
+    const uint32_t gen = st->generation;
+    const double R0 = st->host_r0;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= H;
+    const int pi0 = st->specs[0].repro;
+    const uint32_t tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) st->host_tiles = ht;
+    for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        const uint64_t h0 = tile * ht;
+        const uint32_t nh = (uint32_t)(H - h0 < ht ? H - h0 : ht);
+        __syncthreads();  // shared arrays of the previous tile are free (and s_rcp is filled)
+        for (uint32_t k = tid; k <= nh; k += REPL_TPB) s_off[k] = offsets[h0 + k];
+        for (uint32_t k = tid; k < RESAMPLE_TILE / 32 + 2; k += REPL_TPB) s_head[k] = 0u;
+        __syncthreads();
+        const uint32_t p0 = s_off[0], cnt = s_off[nh] - p0;
+        if (cnt > RESAMPLE_TILE) {  // uniform across the CTA
+            if (tid == 0) { st->fused_failed = 1u; st->tile_sum[tile] = 0; if (fail_is_error) raise(st, DE_TILE_OVERFLOW); }
+            continue;
+        }
+        // ---- 1. records and fitness into registers and shared memory (slot j of thread t is position t + j * TPB)
+        uint2 r[REPL_PER];
+        double f[REPL_PER];
+#pragma unroll
+        for (int j = 0; j < REPL_PER; j++) {
+            const uint32_t q = tid + j * REPL_TPB;
+            r[j] = q < cnt ? rec[p0 + q] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < REPL_PER; j++) {
+            const uint32_t q = tid + j * REPL_TPB;
+            f[j] = 0.0;
+            if (q < cnt) {
+                if (single) f[j] = pi0 >= 0 ? hap_raw(st, pi0, r[j].y) : 1.;
+                else f[j] = reproductive_fitness(st, find_spec_of_position(st, (uint64_t)p0 + q), r[j].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < REPL_PER; j++) {
+            const uint32_t q = tid + j * REPL_TPB;
+            if (q < cnt) {
+                if (single && pi0 >= 0) f[j] = utility_apply(st->prov[pi0], f[j]);
+                s_rec[q] = r[j];
+                s_f[q] = f[j];
+            }
+        }
+        bool failed = false;
+        for (uint32_t k = tid; k < nh; k += REPL_TPB) {
+            const uint32_t b = s_off[k] - p0, len = s_off[k + 1] - s_off[k];
+            if (len) atomicOr(&s_head[b >> 5], 1u << (b & 31));
+            if (len > THREAD_TIER) failed = true;
+        }
+        if (tid == 0) atomicOr(&s_head[cnt >> 5], 1u << (cnt & 31));  // sentinel: the position after the last slice
+        if (__syncthreads_or(failed ? 1 : 0)) {
+            if (tid == 0) { st->fused_failed = 1u; st->tile_sum[tile] = 0; if (fail_is_error) raise(st, DE_TILE_OVERFLOW); }
+            continue;
+        }
+        // ---- 2. slice bounds from the bit mask (a slice spans at most two words), rank by descending infectant index
+        uint32_t seg[REPL_PER];  // first position of the slice | length << 16
+        uint32_t dst[REPL_PER];
+#pragma unroll
+        for (int j = 0; j < REPL_PER; j++) {
+            const uint32_t q = tid + j * REPL_TPB;
+            seg[j] = 0;
+            dst[j] = q;
+            if (q >= cnt) continue;
+            const uint32_t w = q >> 5, bit = q & 31;
+            const uint32_t below = s_head[w] & (0xFFFFFFFFu >> (31 - bit));
+            const uint32_t b = below ? (w << 5) + 31 - __clz(below) : ((w - 1) << 5) + 31 - __clz(s_head[w - 1]);
+            const uint32_t above = bit == 31 ? 0u : s_head[w] & (0xFFFFFFFFu << (bit + 1));
+            const uint32_t e = above ? (w << 5) + __ffs(above) - 1 : ((w + 1) << 5) + __ffs(s_head[w + 1]) - 1;
+            uint32_t rank = 0;
+            for (uint32_t a = b; a < e; a++) rank += s_rec[a].x > r[j].x ? 1u : 0u;
+            seg[j] = b | ((e - b) << 16);
+            dst[j] = b + rank;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < REPL_PER; j++) {
+            const uint32_t q = tid + j * REPL_TPB;
+            if (q < cnt && dst[j] != q) {
+                s_rec[dst[j]] = r[j];
+                s_f[dst[j]] = f[j];
+                rec[p0 + dst[j]] = r[j];
+            }
+        }
+        __syncthreads();
+        // ---- 3. per position: S in slice order, lambda, Poisson(lambda), offspring, tile total
+        uint32_t local = 0;
+#pragma unroll
+        for (int j = 0; j < REPL_PER; j++) {
+            const uint32_t q = tid + j * REPL_TPB;
+            if (q >= cnt) continue;
+            const uint32_t b = seg[j] & 0xFFFFu, e = b + (seg[j] >> 16);
+            double S = 0.0;
+            for (uint32_t a = b; a < e; a++) S += s_f[a];
+            const double l = checked_lambda(st, s_f[q], R0, S);  // lambda_i = f_i * R0 / S_host (src/simulation.rs:148-150)
+            const uint64_t p = (uint64_t)p0 + q;
+            uint32_t off = 0;
+            if (replay_off) {
+                uint64_t v = replay_off[s_rec[q].x];
+                if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0; }
+                off = (uint32_t)v;
+            } else if (l > 0.0) {
+                uint64_t v;
+                if (l < 12.0) v = poisson_draw_small_fast(key, p, gen, PH_OFFSPRING, l, s_rcp);
+                else if (SMALL_ONLY) { raise(st, DE_UNDEFINED_OFFSPRING); v = 0; }  // f > S: negative fitness values in the slice
+                else v = poisson_ptrs(key, p, gen, PH_OFFSPRING, l);
+                if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
+                off = (uint32_t)v;
+            }
+            offspring[p] = off;
+            if (store_lambda) lam[p] = l;
+            local += off;
+        }
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, sh);
+        if ((tid & 31) == 0) s_red[tid >> 5] = local;
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t t = 0;
+            for (int w = 0; w < REPL_TPB / 32; w++) t += s_red[w];
+            st->tile_sum[tile] = t;
+        }
+    }
+}
+
 // tile sums of an offspring map that came from the host (identity layout)
 __global__ void __launch_bounds__(TPB) k_tile_sums(DevState *st) {
     __shared__ uint64_t s_red[TPB / 32];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->host_tiles = 0;
     const uint64_t m = st->n_sorted;
     const uint64_t n_tiles = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1093,13 +1357,14 @@ __device__ __forceinline__ uint64_t plan_block_sum(uint64_t x, uint64_t *s_scrat
     return t;
 }
 // exclusive scan of src[0..nt) into dst (may alias); returns nothing, total left in *s_carry
-__device__ __forceinline__ void plan_block_scan(const uint64_t *src, uint64_t *dst, uint64_t nt, bool inclusive, uint64_t *s_scan, uint64_t *s_carry) {
+__device__ __forceinline__ void plan_block_scan(const uint64_t *src, uint64_t *dst, uint64_t nt, bool inclusive, uint64_t init, uint64_t *s_scan, uint64_t *s_carry) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) *s_carry = 0;
+    __syncthreads();
+    if (tid == 0) *s_carry = init;
     __syncthreads();
     for (uint64_t t0 = 0; t0 < nt; t0 += PLAN_THREADS) {
         const uint64_t t = t0 + tid;
-        const uint64_t x = t < nt ? src[t] : 0;
+        const uint64_t x = t < nt ? __ldcg(&src[t]) : 0;  // (other CTAs may have added to it: read past L1)
         uint64_t inc = x;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1122,34 +1387,57 @@ __device__ __forceinline__ void plan_block_scan(const uint64_t *src, uint64_t *d
     }
 }
 
-// One CTA.  (1) W = sum of tile totals, target_size = min(W*dilution, max_population) (src/simulation.rs:491-503)
-// and size = (factor*target) as usize (:521) or an explicit amount (sample_indices, :505-514).
+// PLAN_CTAS co-resident CTAs (far fewer than SMs) with a grid barrier on a counter in DevState.
+// (1) Every CTA scans the tile totals for itself: W = sum, target_size = min(W*dilution, max_population)
+// (src/simulation.rs:491-503) and size = (factor*target) as usize (:521) or an explicit amount (sample_indices, :505-514).
 // (2) The `size` iid draws proportional to offspring (Population::sample, src/core/population.rs:385-403) are split
-// over the tiles as an exact multinomial.  Default: Poissonisation — independent N_t ~ Poisson(mu * w_t / W) with
-// mu a few standard deviations below `size` are, given their sum K, Multinomial(K, w/W); the remaining size - K
-// draws are made one by one (binary search in the tile prefix) and added, and a multinomial plus an independent
-// multinomial with the same cell probabilities is the multinomial of the summed size.  K > size (probability
-// ~3e-7 per call) or `force_tree` falls back to walking a segment tree with conditional binomials, which is also
-// exact.  (3) exclusive scan of the per-tile draw counts.
+// over the tiles as an exact multinomial, every CTA drawing for its own slice of tiles.  Default: Poissonisation —
+// independent N_t ~ Poisson(mu * w_t / W) with mu a few standard deviations below `size` are, given their sum K,
+// Multinomial(K, w/W); the deficit size - K is Poissonised again (same argument, smaller means) until a handful of
+// draws remain, which are made one by one (binary search in the tile prefix) and added: a multinomial plus an
+// independent multinomial with the same cell probabilities is the multinomial of the summed size.  K > size
+// (probability ~3e-7 per call) or `force_tree` falls back to walking a segment tree with conditional binomials on
+// CTA 0, which is also exact.  (3) exclusive scan of the per-tile draw counts, slice by slice.
+constexpr int PLAN_CTAS = 16;
+__device__ __forceinline__ void plan_grid_barrier(DevState *st, uint32_t &epoch) {
+    __syncthreads();
+    epoch += 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&st->plan_sync, 1u);
+        const uint32_t target = epoch * gridDim.x;
+        uint32_t seen;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&st->plan_sync) : "memory"); } while (seen < target);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ uint64_t plan_ld(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, double factor, int use_amount, uint64_t amount, int set_next,
                                                                uint32_t salt, int force_tree, uint32_t smem_tiles) {
     extern __shared__ uint64_t s_prefix[];  // inclusive prefix of tile totals when nt <= smem_tiles
     __shared__ uint64_t s_scan[PLAN_THREADS / 32];
     __shared__ uint64_t s_carry;
     __shared__ uint64_t s_size, s_W;
-    __shared__ int s_tree;
     __shared__ double s_rcp[POISSON_RCP];
     poisson_rcp_init(s_rcp);
-    if (threadIdx.x == 0) st->dbg[0] = vl_globaltimer();
+    const bool lead = blockIdx.x == 0;
+    if (lead && threadIdx.x == 0) st->dbg[0] = vl_globaltimer();
     const uint64_t n = st->n;
-    const uint64_t m = st->n_sorted;
-    const uint64_t nt = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint64_t nt = tile_count(st);
     const uint32_t tid = threadIdx.x;
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t gen = st->generation;
+    uint32_t epoch = 0;
     uint64_t *cnt = st->tile_cnt;  // final per-tile draw counts live in cnt[0..nt)
-    uint64_t *prefix = nt <= smem_tiles ? s_prefix : st->tile_tree;
-    plan_block_scan(st->tile_sum, prefix, nt, true, s_scan, &s_carry);
+    // this CTA's slice of tiles
+    const uint64_t per = (nt + gridDim.x - 1) / gridDim.x;
+    const uint64_t t_lo = per * blockIdx.x < nt ? per * blockIdx.x : nt, t_hi = t_lo + per < nt ? t_lo + per : nt;
+    uint64_t *prefix = nt <= smem_tiles ? s_prefix : st->tile_tree;  // (global fallback: every CTA writes the same values)
+    plan_block_scan(st->tile_sum, prefix, nt, true, 0, s_scan, &s_carry);
     if (tid == 0) {
         const uint64_t total = s_carry;
         double target = 0.0;
@@ -1159,39 +1447,44 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
         }
         uint64_t size = use_amount ? amount : f64_as_usize(factor * target);
         if (n == 0) size = 0;
-        if (n > 0 && total == 0) { raise(st, DE_ALL_ZERO_WEIGHTS); size = 0; }
-        if (set_next && size > st->cap_inf) { raise(st, DE_INF_CAPACITY); size = st->cap_inf; }
-        st->offspring_total = total;
-        st->target_size = target;
-        st->n_next = size;
+        if (n > 0 && total == 0) { if (lead) raise(st, DE_ALL_ZERO_WEIGHTS); size = 0; }
+        if (set_next && size > st->cap_inf) { if (lead) raise(st, DE_INF_CAPACITY); size = st->cap_inf; }
+        if (lead) {
+            st->offspring_total = total;
+            st->target_size = target;
+            st->n_next = size;
+        }
         s_size = size;
         s_W = total;
-        s_tree = force_tree;
     }
     __syncthreads();
     const uint64_t size = s_size, W = s_W;
-    if (tid == 0) st->dbg[1] = vl_globaltimer();
-    if (!force_tree) {
+    if (lead && tid == 0) st->dbg[1] = vl_globaltimer();
+    bool tree = force_tree != 0;
+    if (!tree) {
         const double sd = sqrt((double)size);
         double mu = (double)size - 5.0 * sd - 8.0;
         if (!(mu > 0.0)) mu = 0.0;
         uint64_t mine = 0;
-        for (uint64_t t = tid; t < nt; t += PLAN_THREADS) {
+        for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) {
             const uint64_t w = st->tile_sum[t];
             uint64_t c = 0;
             if (w > 0 && mu > 0.0) c = poisson_draw(key, t | ((uint64_t)salt << 48), gen, PH_PLAN, mu * ((double)w / (double)W), s_rcp);  // stage 0
             cnt[t] = c;
             mine += c;
         }
-        uint64_t K = plan_block_sum(mine, s_scan);
-        if (tid == 0) st->dbg[2] = vl_globaltimer();
+        mine = plan_block_sum(mine, s_scan);
+        if (tid == 0 && mine) atomicAdd((unsigned long long *)&st->plan_acc[0], (unsigned long long)mine);
+        plan_grid_barrier(st, epoch);
+        uint64_t K = plan_ld(&st->plan_acc[0]);
+        if (lead && tid == 0) st->dbg[2] = vl_globaltimer();
         // the deficit size - K is itself Poissonised (same argument, smaller means) until a handful of draws remain
         for (uint32_t stage = 1; stage < 4 && K <= size && size - K > 64; stage++) {
             const double d = (double)(size - K);
             double mu2 = d - 5.0 * sqrt(d) - 8.0;
             if (!(mu2 > 0.0)) break;
             uint64_t add = 0;
-            for (uint64_t t = tid; t < nt; t += PLAN_THREADS) {
+            for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) {
                 const uint64_t w = st->tile_sum[t];
                 if (w > 0) {
                     const uint64_t c = poisson_draw(key, t | ((uint64_t)salt << 48) | ((uint64_t)stage << 40), gen, PH_PLAN, mu2 * ((double)w / (double)W), s_rcp);
@@ -1199,13 +1492,16 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
                     add += c;
                 }
             }
-            K += plan_block_sum(add, s_scan);
+            add = plan_block_sum(add, s_scan);
+            if (tid == 0 && add) atomicAdd((unsigned long long *)&st->plan_acc[stage], (unsigned long long)add);
+            plan_grid_barrier(st, epoch);
+            K += plan_ld(&st->plan_acc[stage]);
         }
         if (K > size) {
-            if (tid == 0) s_tree = 1;
+            tree = true;
         } else {
             const uint64_t D = size - K;
-            for (uint64_t j = tid; j < D; j += PLAN_THREADS) {
+            for (uint64_t j = (uint64_t)blockIdx.x * PLAN_THREADS + tid; j < D; j += (uint64_t)gridDim.x * PLAN_THREADS) {
                 // Uniform(0, W): 64-bit widening multiply with rejection
                 Philox g(st->seed, st->compartment, gen, PH_PLAN_FILL, j | ((uint64_t)salt << 48));
                 const uint64_t r = g.below(W);
@@ -1217,22 +1513,22 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
                 atomicAdd((unsigned long long *)&cnt[lo], 1ull);
             }
         }
-        __syncthreads();
     }
-    if (s_tree) {
+    if (tree && lead) {
+        __syncthreads();
         const uint64_t P = pow2_ceil(nt ? nt : 1);
-        uint64_t *tree = st->tile_tree, *ncnt = st->tile_node;
-        for (uint64_t t = tid; t < P; t += PLAN_THREADS) tree[P + t] = t < nt ? st->tile_sum[t] : 0;
+        uint64_t *tr = st->tile_tree, *ncnt = st->tile_node;
+        for (uint64_t t = tid; t < P; t += PLAN_THREADS) tr[P + t] = t < nt ? st->tile_sum[t] : 0;
         __syncthreads();
         for (uint64_t s = P >> 1; s >= 1; s >>= 1) {
-            for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) tree[node] = tree[2 * node] + tree[2 * node + 1];
+            for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) tr[node] = tr[2 * node] + tr[2 * node + 1];
             __syncthreads();
         }
         if (tid == 0) ncnt[1] = size;
         __syncthreads();
         for (uint64_t s = 1; s < P; s <<= 1) {
             for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) {
-                const uint64_t c = ncnt[node], wl = tree[2 * node], w = tree[node];
+                const uint64_t c = ncnt[node], wl = tr[2 * node], w = tr[node];
                 uint64_t left = 0;
                 if (c > 0 && wl > 0) {
                     if (wl == w) left = c;
@@ -1249,9 +1545,18 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
         for (uint64_t t = tid; t < nt; t += PLAN_THREADS) cnt[t] = ncnt[P + t];
         __syncthreads();
     }
-    if (tid == 0) st->dbg[3] = vl_globaltimer();
-    plan_block_scan(cnt, st->tile_base, nt, false, s_scan, &s_carry);
-    if (tid == 0) st->dbg[4] = vl_globaltimer();
+    plan_grid_barrier(st, epoch);  // every count is final
+    if (lead && tid == 0) st->dbg[3] = vl_globaltimer();
+    // ---- (3) exclusive scan of the counts: slice totals first, then every CTA scans its slice from its base
+    uint64_t part = 0;
+    for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) part += __ldcg(&cnt[t]);
+    part = plan_block_sum(part, s_scan);
+    if (tid == 0) st->plan_part[blockIdx.x] = part;
+    plan_grid_barrier(st, epoch);
+    uint64_t base = 0;
+    for (uint32_t g = 0; g < blockIdx.x; g++) base += plan_ld(&st->plan_part[g]);
+    plan_block_scan(cnt + t_lo, st->tile_base + t_lo, t_hi - t_lo, false, base, s_scan, &s_carry);
+    if (lead && tid == 0) st->dbg[4] = vl_globaltimer();
 }
 
 // One CTA per tile of CSR positions.  The tile's records with offspring > 0 are compacted into shared memory as
@@ -1267,8 +1572,7 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, uint32_t *__rest
     __shared__ uint32_t s_hap[RESAMPLE_TILE];   // haplotype id (mode 0) or position inside the tile (mode 1)
     __shared__ uint16_t s_guide[GUIDE_SIZE];
     __shared__ uint32_t s_wsum[TPB / 32], s_wcnt[TPB / 32];
-    const uint64_t m = st->n_sorted;
-    const uint64_t nt = (m + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint64_t nt = tile_count(st);
     const uint32_t *__restrict__ offspring = st->offspring;
     const uint2 *__restrict__ rec = st->rec;
     if (dst == nullptr && mode == 0) dst = st->hap_id_next;
@@ -1285,16 +1589,23 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, uint32_t *__rest
             continue;
         }
         const uint64_t base = st->tile_base[tile];
-        const uint64_t start = tile * RESAMPLE_TILE;
+        uint64_t start;
+        uint32_t tlen;
+        tile_range(st, tile, start, tlen);
+        if (tlen > RESAMPLE_TILE) {  // cannot happen: host tiles are only declared by a kernel that staged every tile
+            if (tid == 0) raise(st, DE_TILE_OVERFLOW);
+            continue;
+        }
         // ---- load PER consecutive items per thread, local scans of offspring and of the non-zero flags
         uint32_t v[PER], hp[PER];
         const uint64_t p0 = start + (uint64_t)tid * PER;
 #pragma unroll
         for (uint32_t k = 0; k < PER; k++) {
             const uint64_t p = p0 + k;
-            v[k] = p < m ? offspring[p] : 0u;
+            const bool in = tid * PER + k < tlen;
+            v[k] = in ? offspring[p] : 0u;
             hp[k] = 0;
-            if (p < m && v[k]) hp[k] = mode == 0 ? rec[p].y : (uint32_t)(p - start);
+            if (in && v[k]) hp[k] = mode == 0 ? rec[p].y : (uint32_t)(p - start);
         }
         uint32_t run = 0, nz = 0;
 #pragma unroll
@@ -1496,12 +1807,32 @@ __global__ void k_test_poisson(uint64_t seed, double lambda, uint64_t n, uint64_
     const PhiloxKey key = philox_key(seed, 0);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = poisson_draw(key, i, 0, PH_TEST, lambda, s_rcp);
 }
+// out[i] = the f32-guarded inversion, out[n + i] = the plain f64 inversion of the same uniform: must be equal draw for draw
+__global__ void k_test_poisson_fast(uint64_t seed, double lambda, uint64_t n, uint64_t *out) {
+    __shared__ double s_rcp[POISSON_RCP];
+    poisson_rcp_init(s_rcp);
+    __syncthreads();
+    const PhiloxKey key = philox_key(seed, 0);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        // lambda <= 0 selects a per-draw mean spread over (0, 12) so that the guard band is exercised at every scale
+        const double l = lambda > 0.0 ? lambda : 12.0 * u01_open_from(philox_block(key, i, 1, PH_TEST, 0).x, philox_block(key, i, 1, PH_TEST, 0).y);
+        out[i] = poisson_draw_small_fast(key, i, 0, PH_TEST, l, s_rcp);
+        const uint4 b = philox_block(key, i, 0, PH_TEST, 0);
+        out[n + i] = poisson_inversion_f64(u01_from(b.x, b.y), l, s_rcp);
+    }
+}
 __global__ void k_test_binomial(uint64_t seed, uint64_t nn, double p, uint64_t n, uint64_t *out, BinvConst c) {
     const PhiloxKey key = philox_key(seed, 0);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         if (c.ok) {
             const uint4 b0 = philox_block(key, i, 0, PH_TEST, 0);
-            out[i] = binv_draw(c, u01_from(b0.z, b0.w), key, i, 0, PH_TEST);
+            // the product path's integer thresholds against the f64 search they were derived from; a disagreement
+            // is reported as a value no binomial can take
+            const uint64_t U = (((uint64_t)b0.w << 32) | b0.z) >> 11;
+            uint32_t k = 0;
+            while (k < (uint32_t)BINV_THRESHOLDS && U >= c.thr[k]) k++;
+            const uint32_t ref = binv_draw(c, u01_from(b0.z, b0.w), key, i, 0, PH_TEST);
+            out[i] = (k < (uint32_t)BINV_THRESHOLDS && k != ref) ? (1ull << 62) : ref;
         } else {
             Philox g(seed, 0, 0, PH_TEST, i);
             out[i] = binomial(g, nn, p);

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(TPB) k_copy_out_next(DevState *st, uint32_t *_
 __global__ void __launch_bounds__(TPB) k_target_size(DevState *st) {
     __shared__ uint64_t s_red[TPB / 32];
     const uint64_t n = st->n;
-    const uint64_t nt = (st->n_sorted + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint64_t nt = tile_count(st);
     uint64_t local = 0;
     for (uint64_t t = threadIdx.x; t < nt; t += TPB) local += st->tile_sum[t];
 #pragma unroll

@@ -255,6 +255,38 @@ __device__ __forceinline__ uint64_t poisson_draw(PhiloxKey key, uint64_t index, 
     if (SMALL_ONLY) return 0;
     return poisson_ptrs(key, index, generation, phase, lambda);
 }
+// The same inversion, decided in f32 whenever that is provably the f64 decision: the search runs on f32 copies of u
+// and of the CDF; the f32 CDF is within 2e-5 of the f64 one for lambda < 12 (expf to 2e-6 relative, <= 64 products
+// and sums at 6e-8 each), so if u stays more than POISSON_GUARD away from every CDF value it is compared with, both
+// searches stop at the same k.  Otherwise (about 2 draws in 1000) the f64 search above decides.  The result is the
+// f64 inversion's for every (u, lambda): vl_test_poisson_fast checks that draw for draw.
+constexpr float POISSON_GUARD = 1.0e-4f;
+__device__ __forceinline__ uint32_t poisson_inversion_f64(double u, double lambda, const double *rcp) {
+    double p = exp(-lambda), cdf = p;
+    uint32_t k = 0;
+    while (u >= cdf && k < 256) {
+        k += 1;
+        p = (k < POISSON_RCP) ? p * (lambda * rcp[k]) : p * lambda / (double)k;
+        cdf += p;
+    }
+    return k;
+}
+__device__ __forceinline__ uint32_t poisson_draw_small_fast(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, double lambda,
+                                                            const double *rcp) {
+    const uint4 b = philox_block(key, index, generation, phase, 0);
+    const double u = u01_from(b.x, b.y);
+    const float uf = (float)u, lf = (float)lambda;
+    float p = __expf(-lf), cdf = p, mind = fabsf(uf - cdf);
+    uint32_t k = 0;
+    while (uf >= cdf && k < 48) {
+        k += 1;
+        p *= lf * __frcp_rn((float)k);
+        cdf += p;
+        mind = fminf(mind, fabsf(uf - cdf));
+    }
+    if (mind > POISSON_GUARD && k < 48) return k;
+    return poisson_inversion_f64(u, lambda, rcp);
+}
 // fills a CTA's shared reciprocal table (call by all threads, then __syncthreads())
 __device__ __forceinline__ void poisson_rcp_init(double *rcp) {
     for (int k = threadIdx.x; k < POISSON_RCP; k += blockDim.x) rcp[k] = k ? 1.0 / (double)k : 0.0;
@@ -264,7 +296,26 @@ __device__ __forceinline__ void poisson_rcp_init(double *rcp) {
 // inversion of one uniform (the BINV branch of rand_distr 0.5.1).  `u` is consumed; a restart (k beyond the
 // search bound, probability < 1e-100) draws from the stream's later blocks.
 constexpr int BINV_STEPS = 16;
-struct BinvConst { double qn, s, a; uint64_t n; int ok; double step[BINV_STEPS]; /* a/k - s for k < BINV_STEPS */ };
+constexpr int BINV_THRESHOLDS = 16;
+struct BinvConst {
+    double qn, s, a; uint64_t n; int ok; double step[BINV_STEPS]; /* a/k - s for k < BINV_STEPS */
+    // thr[k] = the smallest 53-bit integer U for which the inversion of u = U * 2^-53 returns more than k: the count
+    // is the number of thresholds U reaches.  Found on the host by bisection over the very search the device runs
+    // (binv_count below, IEEE operations only), so comparing integers gives the inversion's answer bit for bit.
+    uint64_t thr[BINV_THRESHOLDS];
+};
+// first pass of the inversion (no restart): steps taken for this uniform
+__host__ __device__ inline uint32_t binv_count(const BinvConst &c, double u) {
+    double r = c.qn;
+    uint32_t k = 0;
+    while (u > r) {
+        u -= r;
+        k += 1;
+        if (k > 200 || k > c.n) break;
+        r *= (k < (uint32_t)BINV_STEPS) ? c.step[k] : c.a / (double)k - c.s;
+    }
+    return k;
+}
 __host__ inline BinvConst make_binv(uint64_t n, double p) {
     BinvConst c;
     c.n = n;
@@ -274,6 +325,15 @@ __host__ inline BinvConst make_binv(uint64_t n, double p) {
     c.s = p / q;
     c.a = ((double)n + 1.0) * c.s;
     for (int k = 0; k < BINV_STEPS; k++) c.step[k] = k ? c.a / (double)k - c.s : 0.0;
+    for (int k = 0; k < BINV_THRESHOLDS; k++) {
+        // binv_count is non-decreasing in u (every step subtracts the same constants): bisect for the first U with count > k
+        uint64_t lo = 0, hi = 1ull << 53;  // hi = "never"
+        while (c.ok && lo < hi) {
+            const uint64_t mid = lo + ((hi - lo) >> 1);
+            if (binv_count(c, (double)mid * (1.0 / 9007199254740992.0)) > (uint32_t)k) hi = mid; else lo = mid + 1;
+        }
+        c.thr[k] = c.ok ? lo : (1ull << 53);
+    }
     return c;
 }
 __device__ __forceinline__ uint32_t binv_draw(const BinvConst &c, double u, PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase) {

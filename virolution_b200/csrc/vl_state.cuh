@@ -35,6 +35,8 @@ constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr int MAX_SPECS = 8;
 constexpr int MAX_PROVIDERS = 16;
 constexpr uint32_t RESAMPLE_TILE = 2048;  // CSR positions per resample tile (one CTA stages one tile in smem)
+constexpr uint32_t HT_MAX_HOSTS = 2048;   // most hosts a host-range tile may span (DevState::host_tiles holds the actual number)
+constexpr uint32_t HT_MIN_HOSTS = 256;    // below this the fused replicate kernel is not worth launching
 
 // error bits raised by kernels (sticky until vl_* reports them)
 enum DevError : uint32_t {
@@ -46,7 +48,8 @@ enum DevError : uint32_t {
     DE_INF_CAPACITY = 32u,      // population buffer too small
     DE_OFFSPRING_RANGE = 64u,   // offspring count does not fit u32
     DE_REPLAY = 128u,           // malformed replay log
-    DE_BUCKET_OVERFLOW = 256u   // a host bucket received 12 standard deviations more records than its mean
+    DE_BUCKET_OVERFLOW = 256u,  // a host bucket received 12 standard deviations more records than its mean
+    DE_TILE_OVERFLOW = 512u     // a host tile holds more records than a CTA stages (uniform infection: > 13 sd)
 };
 constexpr uint32_t BUCKET_SHIFT = 13;
 constexpr uint32_t BUCKET_HOSTS = 1u << BUCKET_SHIFT;  // hosts per bucket: their histogram lives in shared memory
@@ -116,8 +119,10 @@ struct DevState {
     uint64_t n_sorted;     // number of records = infected infectants (offsets[H])
     uint32_t *heavy_hosts; // worklist of hosts whose slice exceeds the thread tier
     uint32_t *medium_hosts; // worklist of hosts with 5 .. THREAD_TIER members
-    uint32_t n_medium;
+    uint32_t n_medium;     // n_medium, n_heavy, fused_failed are cleared together before a replicate phase
     uint32_t n_heavy;
+    uint32_t fused_failed; // a tile of the fused replicate kernel did not fit: the general kernels redo the phase
+    uint32_t host_tiles;   // > 0: resample tiles are ranges of that many hosts, 0: ranges of RESAMPLE_TILE CSR positions
     uint32_t _pad3;
     uint32_t fast_infect;  // specs cover [0,H), no infective provider, n_hits == 1: every draw infects, hosts uniform
     // ---- bucketed counting sort (hosts split into buckets of BUCKET_HOSTS consecutive hosts)
@@ -145,6 +150,10 @@ struct DevState {
     uint64_t *tile_base;   // exclusive scan of draws per tile
     uint64_t offspring_total;
     double target_size;    // of the last plan
+    uint32_t plan_sync;    // grid barrier counter of the plan kernel; plan_sync .. plan_acc are cleared before every launch
+    uint32_t _pad4;
+    uint64_t plan_acc[4];  // draws made per Poissonisation stage, summed over the plan CTAs
+    uint64_t plan_part[32]; // draws per CTA slice of tiles
 
     // ---- haplotype table (double-buffered for compaction; the live set is swapped on device)
     uint64_t cap_hap, cap_arena;
@@ -162,6 +171,25 @@ struct DevState {
     uint64_t kernels_launched;  // maintained by the host, mirrored here for export
     uint64_t dbg[8];            // %globaltimer stamps of the plan kernel's phases (profiling aid)
 };
+
+// ---- resample tiles: a tile is what one CTA stages in shared memory, either RESAMPLE_TILE consecutive CSR positions
+// or the records of DevState::host_tiles consecutive hosts (what the fused replicate kernel produces: whole hosts per CTA)
+__device__ __forceinline__ uint64_t tile_count(const DevState *st) {
+    const uint64_t ht = st->host_tiles;
+    return ht ? (st->H + ht - 1) / ht : (st->n_sorted + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+}
+__device__ __forceinline__ void tile_range(const DevState *st, uint64_t tile, uint64_t &start, uint32_t &len) {
+    if (st->host_tiles) {
+        const uint64_t ht = st->host_tiles;
+        const uint64_t h0 = tile * ht, h1 = h0 + ht < st->H ? h0 + ht : st->H;
+        start = st->offsets[h0];
+        len = st->offsets[h1] - (uint32_t)start;
+    } else {
+        start = tile * RESAMPLE_TILE;
+        const uint64_t rest = st->n_sorted - start;
+        len = rest < RESAMPLE_TILE ? (uint32_t)rest : RESAMPLE_TILE;
+    }
+}
 
 // memoised raw fitness of haplotype `id` under provider p (AttributeSet::get_or_compute_raw, src/core/attributes.rs:196-217)
 // (kept apart from HapMeta: the per-infectant fitness gather wants the densest possible array)

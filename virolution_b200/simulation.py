@@ -74,6 +74,7 @@ SIGNATURES = {
     "vl_profile_report": (C.c_int, [_vp, C.c_char_p, C.c_uint64]),
     "vl_debug_stamps": (C.c_int, [_vp, u64p]),
     "vl_test_poisson": (C.c_int, [C.c_uint64, C.c_double, C.c_uint64, u64p]),
+    "vl_test_poisson_fast": (C.c_int, [C.c_uint64, C.c_double, C.c_uint64, u64p]),
     "vl_test_binomial": (C.c_int, [C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, u64p]),
     "vl_test_below": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, u64p]),
 }
@@ -446,6 +447,15 @@ def sampler_poisson(seed: int, lam: float, n: int) -> np.ndarray:
     if rc:
         raise VirolutionError(rc, "vl_test_poisson failed")
     return out
+
+
+def sampler_poisson_fast(seed: int, lam: float, n: int):
+    """(f32-guarded inversion, f64 inversion) of the same uniforms; lam <= 0 spreads the mean over (0, 12) per draw."""
+    out = np.zeros(2 * n, dtype=np.uint64)
+    rc = load_library().vl_test_poisson_fast(seed, lam, n, _p(out, C.c_uint64))
+    if rc:
+        raise VirolutionError(rc, "vl_test_poisson_fast failed")
+    return out[:n], out[n:]
 
 
 def sampler_binomial(seed: int, trials: int, p: float, n: int) -> np.ndarray:
