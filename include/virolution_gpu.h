@@ -160,6 +160,9 @@ int vl_next_generation(vl_sim *sim);                     /* default method, :200
 /* ---- fused, device-resident loops (what Runner::run drives, runner.rs:336-423) */
 /* n generations of a single compartment with the identity transfer; no host sync inside. */
 int vl_run(vl_sim *sim, uint64_t n_generations);
+/* increment_generation + infect + mutate_infectants + replicate_infectants as one enqueue, offspring map left on the
+ * device: everything Runner::run does per compartment before the transmission block (runner.rs:382-399). */
+int vl_advance_to_offspring(vl_sim *sim);
 /* one generation over several compartments living in this process.
  * rule: 0 = parallel-build rule (runner.rs:401-416), 1 = serial-build rule (:550-631). */
 int vl_step(vl_sim *const *sims, uint32_t n_sims, const double *transfer, int rule);

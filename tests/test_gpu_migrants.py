@@ -76,3 +76,57 @@ def test_empty_export():
     img, m, w = a.export_migrants([])
     assert int(img.n_migrants) == 0 and int(img.n_words) == 0 and m.size == 0
     a.close()
+
+
+def test_many_parts_in_one_pass_follow_the_sampling_law():
+    """vl_subsample_populations draws up to 16 parts per plan/resample pass (more parts = more passes): every part has
+    exactly floor(factor * target_size) members, each an iid draw proportional to offspring
+    (Population::sample, src/core/population.rs:385-403), and the parts are independent draws."""
+    from test_gpu_stochastic import big_singlehost
+    n = 6000
+    c = big_singlehost(n=n, mu=1e-4, seed=77)
+    L = len(c["wildtype"])
+    g = helpers.make_gpu(c)
+    rng = np.random.default_rng(5)
+    # give every infectant its own haplotype: one unique (site, base) change each
+    g.increment_generation()
+    g.replay_infections(rng.integers(0, n, size=n))
+    g.infect()
+    sites = (np.arange(n) // 3).astype(np.uint32)
+    assert sites.max() < L
+    bases = ((c["wildtype"][sites] + 1 + np.arange(n) % 3) % 4).astype(np.uint8)
+    g.replay_mutations(np.arange(n + 1, dtype=np.uint64), sites, bases)
+    g.mutate_infectants()
+    ids = g.get_haplotype_ids().astype(np.int64)
+    assert np.unique(ids).size == n
+    parent_of = np.full(ids.max() + 1, -1, dtype=np.int64)
+    parent_of[ids] = np.arange(n)
+    off = rng.poisson(1.3, size=n).astype(np.uint64)
+    off[rng.integers(0, n, 20)] = 30
+    off[1000:1500] = 0
+    ts = g.target_size(off)  # uploads the map the parts are drawn from
+    assert ts == float(min(int(off.sum()), n))
+    factors = [0.3, 0.2, 0.1] + [0.02] * 17  # 20 parts: two passes
+    parts = g.subsample_populations(factors)
+    sizes = [len(p) for p in parts]
+    assert sizes == [int(f * ts) for f in factors]
+    g.set_population(parts)
+    drawn = parent_of[g.get_haplotype_ids().astype(np.int64)]
+    assert drawn.min() >= 0 and np.all(off[drawn] > 0)
+    bounds = np.cumsum([0] + sizes)
+    w = off / off.sum()
+    for k in range(len(parts)):
+        d = drawn[bounds[k]:bounds[k + 1]]
+        counts = np.bincount(d, minlength=n)
+        for cls in np.unique(off[off > 0]):
+            sel = off == cls
+            e = w[sel].sum() * d.size
+            if e > 20:
+                assert abs(counts[sel].sum() - e) / np.sqrt(e) < 5.5, (k, cls)
+    # all parts together are one big iid sample as well
+    counts = np.bincount(drawn, minlength=n)
+    heavy = np.nonzero(off == 30)[0]
+    e = w[heavy] * drawn.size
+    assert abs(counts[heavy].sum() - e.sum()) / np.sqrt(e.sum()) < 5.5
+    assert not np.array_equal(drawn[bounds[3]:bounds[4]], drawn[bounds[4]:bounds[5]]), "equal-sized parts must be different draws"
+    g.close()

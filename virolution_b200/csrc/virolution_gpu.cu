@@ -75,7 +75,7 @@ struct vl_sim {
     uint32_t plan_smem_tiles = 0;
     uint32_t salt = 0;        // distinguishes the sampling streams of one generation
     uint32_t gens_since_gc = 0, gc_period = 1;
-    int next_slot = 8;
+    int next_slot = 128;  // pinned slots [128, PIN_SLOTS) carry detached-population sizes; lower slots are scratch
     // measurement hooks: per-launch CUDA events on this handle's stream
     bool profiling = false;
     struct ProfRec { const char *name; cudaEvent_t a, b; };
@@ -262,9 +262,10 @@ static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     TRY(dev_alloc(sim, &h.offspring, cap + 4, false));
     TRY(dev_alloc(sim, &h.tile_sum, nt, false));
     TRY(dev_alloc(sim, &h.tile_tree, 2 * P, false));
-    TRY(dev_alloc(sim, &h.tile_cnt, nt, false));
+    TRY(dev_alloc(sim, &h.tile_cnt, nt * MAX_PARTS, false));
     TRY(dev_alloc(sim, &h.tile_node, 2 * P, false));
-    TRY(dev_alloc(sim, &h.tile_base, nt, false));
+    TRY(dev_alloc(sim, &h.tile_base, nt * MAX_PARTS, false));
+    h.tile_stride = nt;
     TRY(dev_alloc(sim, &sim->stage64, cap + 4, false));
     h.cap_inf = cap;
     TRY(alloc_bucket_buffers(sim));
@@ -279,6 +280,7 @@ static int push_population_pointers(vl_sim *sim) {
     tmp.hap_id = h.hap_id; tmp.hap_id_next = h.hap_id_next; tmp.host_id = h.host_id; tmp.rank = h.rank; tmp.rec = h.rec;
     tmp.heavy_hosts = h.heavy_hosts; tmp.medium_hosts = h.medium_hosts; tmp.mut_list = h.mut_list; tmp.lam = h.lam; tmp.hs = h.hs; tmp.offspring = h.offspring;
     tmp.tile_sum = h.tile_sum; tmp.tile_tree = h.tile_tree; tmp.tile_cnt = h.tile_cnt; tmp.tile_node = h.tile_node; tmp.tile_base = h.tile_base;
+    tmp.tile_stride = h.tile_stride;
     tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.H = h.H; tmp.fast_infect = h.fast_infect;
     tmp.n_buckets = h.n_buckets; tmp.tmp_rec = h.tmp_rec; tmp.cap_tmp = h.cap_tmp;
     CU(sim, cudaMemcpy(sim->d, &tmp, sizeof(DevState), cudaMemcpyHostToDevice));
@@ -773,23 +775,38 @@ static inline uint64_t tile_bound(const vl_sim *sim) {
     return std::max<uint64_t>((sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE, ht ? (sim->h.H + ht - 1) / ht : 0) + 1;
 }
 static inline unsigned grid_resample(const vl_sim *sim) { return (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8); }
-static int launch_plan(vl_sim *sim, double factor, int use_amount, uint64_t amount, int set_next, uint32_t salt) {
+// plan + draws of n parts of the current offspring map in one pass each (n <= MAX_PARTS)
+static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, int use_amount, const uint64_t *amount, int set_next,
+                                uint32_t *const *dst, uint64_t *dst64, int mode) {
+    if (n == 0 || n > (uint32_t)MAX_PARTS) return fail(sim, VL_ERR_ARGUMENT, "between 1 and %d parts per pass", MAX_PARTS);
+    PlanArgs pa;
+    ResampleArgs ra;
+    memset(&pa, 0, sizeof pa);
+    memset(&ra, 0, sizeof ra);
+    pa.n_parts = ra.n_parts = n;
+    pa.use_amount = use_amount;
+    pa.set_next = set_next;
+    pa.force_tree = (sim->flags & VL_FLAG_TREE_PLAN) ? 1 : 0;
+    for (uint32_t k = 0; k < n; k++) {
+        pa.factor[k] = factor ? factor[k] : 0.0;
+        pa.amount[k] = amount ? amount[k] : 0;
+        pa.salt[k] = ra.salt[k] = ++sim->salt;
+        ra.dst[k] = dst ? dst[k] : nullptr;
+    }
     const uint64_t nt_bound = tile_bound(sim);
     const uint32_t smem_tiles = (uint32_t)std::min<uint64_t>(nt_bound, sim->plan_smem_tiles);
-    const int force_tree = (sim->flags & VL_FLAG_TREE_PLAN) ? 1 : 0;
-    CU(sim, cudaMemsetAsync((char *)sim->d + FIELD_OFF(plan_sync), 0, 8 + 4 * 8, sim->stream));
+    CU(sim, cudaMemsetAsync((char *)sim->d + FIELD_OFF(plan_sync), 0, 8 + sizeof(((DevState *)0)->plan_acc), sim->stream));
     // a handful of co-resident CTAs: each draws for its slice of tiles, a counter in DevState is the grid barrier
     const unsigned ctas = (unsigned)std::min<uint64_t>(PLAN_CTAS, std::max<uint64_t>(1, nt_bound / 256));
-    LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, factor, use_amount, amount, set_next, salt, force_tree, smem_tiles);
+    LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, pa, smem_tiles);
+    LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, ra, dst64, mode);
     return VL_OK;
 }
 // Population::sample as plan + tile-local draws.  dst == nullptr writes the population being assembled.
 static int enqueue_resample(vl_sim *sim, double factor, int use_amount, uint64_t amount, uint32_t *dst, uint64_t *dst64, int mode, int set_next) {
     if (!sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one");
-    const uint32_t salt = ++sim->salt;
-    TRY(launch_plan(sim, factor, use_amount, amount, set_next, salt));
-    LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, dst, dst64, mode, salt);
-    return VL_OK;
+    uint32_t *dsts[1] = {dst};
+    return launch_plan_resample(sim, 1, &factor, use_amount, &amount, set_next, dsts, dst64, mode);
 }
 static int enqueue_gc(vl_sim *sim, int force) {
     const DevState &h = sim->h;
@@ -917,24 +934,35 @@ VL_API int vl_sample_indices(vl_sim *sim, const uint64_t *offspring, uint64_t n,
     return check_device_error(sim);
 }
 
-// enqueue plan + draws into a detached population whose capacity bounds the size; the size itself arrives
-// in a pinned slot and is read by finalize_pop after a stream synchronisation
-static int enqueue_subsample(vl_sim *sim, double factor, int use_amount, uint64_t amount, vl_pop **out) {
-    double bound = use_amount ? (double)amount : floor(factor * (double)sim->h.max_population) + 1.0;
-    if (!(bound >= 0.0)) bound = 0.0;
-    if (bound > 4.0e9) return fail(sim, VL_ERR_CAPACITY, "subsample bound too large");
-    vl_pop *p = new_pop(sim, (uint64_t)bound + 1);
-    if (!p) return fail(sim, VL_ERR_CUDA, "out of device memory for a detached population of %.0f", bound);
-    if (!sim->layout_valid) { drop_pop(p); return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one"); }
-    const uint32_t salt = ++sim->salt;
-    TRY(launch_plan(sim, factor, use_amount, amount, 0, salt));
-    LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, p->ids, (uint64_t *)nullptr, 0, salt);
-    int slot = sim->next_slot++;
-    if (sim->next_slot >= PIN_SLOTS) sim->next_slot = 8;
-    CU(sim, cudaMemcpyAsync(sim->pin + slot, (const char *)sim->d + FIELD_OFF(n_next), 8, cudaMemcpyDeviceToHost, sim->stream));
-    p->pending_slot = slot;
-    *out = p;
+// enqueue plan + draws of n detached populations (batches of MAX_PARTS share one pass over the offspring map); each
+// capacity bounds its size, the sizes themselves arrive in pinned slots and are read by finalize_pop after a stream
+// synchronisation
+static int enqueue_subsamples(vl_sim *sim, uint32_t n, const double *factor, int use_amount, const uint64_t *amount, vl_pop **out) {
+    if (!sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one");
+    for (uint32_t k = 0; k < n; k++) out[k] = nullptr;
+    for (uint32_t k0 = 0; k0 < n; k0 += MAX_PARTS) {
+        const uint32_t m = std::min<uint32_t>(MAX_PARTS, n - k0);
+        uint32_t *dsts[MAX_PARTS];
+        for (uint32_t k = 0; k < m; k++) {
+            double bound = use_amount ? (double)amount[k0 + k] : floor(factor[k0 + k] * (double)sim->h.max_population) + 1.0;
+            if (!(bound >= 0.0)) bound = 0.0;
+            if (bound > 4.0e9) return fail(sim, VL_ERR_CAPACITY, "subsample bound too large");
+            vl_pop *p = new_pop(sim, (uint64_t)bound + 1);
+            if (!p) return fail(sim, VL_ERR_CUDA, "out of device memory for a detached population of %.0f", bound);
+            out[k0 + k] = p;
+            dsts[k] = p->ids;
+        }
+        TRY(launch_plan_resample(sim, m, factor ? factor + k0 : nullptr, use_amount, amount ? amount + k0 : nullptr, 0, dsts, nullptr, 0));
+        if (sim->next_slot + (int)m >= PIN_SLOTS) sim->next_slot = 128;
+        const int slot = sim->next_slot;
+        sim->next_slot += (int)m;
+        CU(sim, cudaMemcpyAsync(sim->pin + slot, (const char *)sim->d + FIELD_OFF(plan_size), 8 * m, cudaMemcpyDeviceToHost, sim->stream));
+        for (uint32_t k = 0; k < m; k++) out[k0 + k]->pending_slot = slot + (int)k;
+    }
     return VL_OK;
+}
+static int enqueue_subsample(vl_sim *sim, double factor, int use_amount, uint64_t amount, vl_pop **out) {
+    return enqueue_subsamples(sim, 1, &factor, use_amount, &amount, out);
 }
 static void finalize_pop(vl_pop *p) {
     if (p->pending_slot >= 0) {
@@ -1057,11 +1085,14 @@ static int ensure_buf(vl_sim *sim, vl_sim::DevBuf &b, uint64_t bytes) {
     CU(sim, cudaMalloc(&b.p, b.bytes));
     return VL_OK;
 }
+static double g_seg[8];
+static inline double now_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts, vl_migrant_image *image,
                                      uint64_t *migrants_per_part, uint64_t *words_per_part) {
     ENTER(sim);
+    double t0 = now_s();
     if (!image || (n_parts && (!parts || !migrants_per_part || !words_per_part))) return fail(sim, VL_ERR_ARGUMENT, "null argument");
-    if (n_parts > 1024) return fail(sim, VL_ERR_ARGUMENT, "too many parts");
+    if (n_parts > 60) return fail(sim, VL_ERR_ARGUMENT, "too many parts");
     bool pending = false;
     for (uint32_t k = 0; k < n_parts; k++) pending = pending || (parts[k] && parts[k]->pending_slot >= 0);
     if (pending) CU(sim, cudaStreamSynchronize(sim->stream));
@@ -1086,6 +1117,7 @@ VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t
         m0 += parts[k]->n;
     }
     TRY((launch_scan<uint64_t, true>(sim, words, off, nullptr, M, M, sim->gc_totals + 10, 1, nullptr)));
+    g_seg[0] += now_s() - t0; t0 = now_s();
     m0 = 0;
     for (uint32_t k = 0; k < n_parts; k++) {  // word offset of every part boundary
         CU(sim, cudaMemcpyAsync(sim->pin + 64 + k, off + m0, 8, cudaMemcpyDeviceToHost, sim->stream));
@@ -1094,8 +1126,10 @@ VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t
     CU(sim, cudaMemcpyAsync(sim->pin + 64 + n_parts, sim->gc_totals + 10, 8, cudaMemcpyDeviceToHost, sim->stream));
     CU(sim, cudaStreamSynchronize(sim->stream));
     const uint64_t W = sim->pin[64 + n_parts];
+    g_seg[1] += now_s() - t0; t0 = now_s();
     for (uint32_t k = 0; k < n_parts; k++) words_per_part[k] = sim->pin[64 + k + 1] - sim->pin[64 + k];
     TRY(ensure_buf(sim, sim->mig[4], (W + 1) * 4));
+    g_seg[2] += now_s() - t0; t0 = now_s();
     uint32_t *entries = (uint32_t *)sim->mig[4].p;
     m0 = 0;
     for (uint32_t k = 0; k < n_parts; k++) {
@@ -1103,6 +1137,8 @@ VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t
         m0 += parts[k]->n;
     }
     CU(sim, cudaStreamSynchronize(sim->stream));
+    g_seg[3] += now_s() - t0;
+    if (sim->experiment & 8) fprintf(stderr, "export segs (cum s): launch %.4f sync1 %.4f ensure %.4f copy+sync %.4f\n", g_seg[0], g_seg[1], g_seg[2], g_seg[3]);
     image->len_device = len;
     image->raw_device = raw;
     image->entries_device = entries;
@@ -1148,9 +1184,8 @@ VL_API int vl_subsample_populations(vl_sim *sim, const double *factors, uint32_t
     ENTER(sim);
     if (!factors || !out) return fail(sim, VL_ERR_ARGUMENT, "null argument");
     if (n >= (uint32_t)PIN_SLOTS - 16) return fail(sim, VL_ERR_ARGUMENT, "too many parts");
-    int r = VL_OK;
-    uint32_t made = 0;
-    for (; made < n && r == VL_OK; made++) { out[made] = nullptr; r = enqueue_subsample(sim, factors[made], 0, 0, &out[made]); }
+    int r = enqueue_subsamples(sim, n, factors, 0, nullptr, out);
+    const uint32_t made = n;
     cudaError_t ce = cudaStreamSynchronize(sim->stream);
     if (r == VL_OK && ce != cudaSuccess) r = fail(sim, VL_ERR_CUDA, "subsample failed: %s", cudaGetErrorString(ce));
     if (r == VL_OK) r = check_device_error(sim);
@@ -1222,8 +1257,9 @@ VL_API int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts
 }
 
 // ---------------------------------------------------------------------------------------------- fused loops
-static int enqueue_generation(vl_sim *sim) {
-    // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
+// increment_generation + infect + mutate_infectants + replicate_infectants with the offspring map left on the device
+// (src/runner.rs:382-399; the first half of Simulation::next_generation, src/simulation.rs:200-214)
+static int enqueue_generation_front(vl_sim *sim) {
     const DevState &h = sim->h;
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
     sim->salt = 0;
@@ -1248,6 +1284,11 @@ static int enqueue_generation(vl_sim *sim) {
         if (!sim->csr_valid) TRY(sim->bucket_pending ? enqueue_bucket_host_map(sim) : enqueue_host_map(sim));
     }
     TRY(enqueue_replicate(sim, 0));
+    return VL_OK;
+}
+static int enqueue_generation(vl_sim *sim) {
+    // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
+    TRY(enqueue_generation_front(sim));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
     swap_population(sim);
     sim->n_valid = false;
@@ -1256,6 +1297,12 @@ static int enqueue_generation(vl_sim *sim) {
     sim->slices_ordered = false;
     sim->layout_valid = false;
     return maybe_gc(sim);
+}
+VL_API int vl_advance_to_offspring(vl_sim *sim) {
+    ENTER(sim);
+    TRY(enqueue_generation_front(sim));
+    CU(sim, cudaGetLastError());
+    return VL_OK;
 }
 VL_API int vl_next_generation(vl_sim *sim) {
     ENTER(sim);

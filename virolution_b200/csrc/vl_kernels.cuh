@@ -1416,94 +1416,125 @@ __device__ __forceinline__ uint64_t plan_ld(const uint64_t *p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, double factor, int use_amount, uint64_t amount, int set_next,
-                                                               uint32_t salt, int force_tree, uint32_t smem_tiles) {
+// what to draw: n_parts subsamples of the same offspring map (the per-target parts of one origin, src/runner.rs:404-416,
+// or the single part of next_generation); every part has its own Philox stream (salt)
+struct PlanArgs {
+    uint32_t n_parts;
+    int use_amount, set_next, force_tree;
+    double factor[MAX_PARTS];
+    uint64_t amount[MAX_PARTS];
+    uint32_t salt[MAX_PARTS];
+};
+__global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, PlanArgs pa, uint32_t smem_tiles) {
     extern __shared__ uint64_t s_prefix[];  // inclusive prefix of tile totals when nt <= smem_tiles
     __shared__ uint64_t s_scan[PLAN_THREADS / 32];
     __shared__ uint64_t s_carry;
-    __shared__ uint64_t s_size, s_W;
+    __shared__ uint64_t s_size[MAX_PARTS], s_W;
     __shared__ double s_rcp[POISSON_RCP];
     poisson_rcp_init(s_rcp);
     const bool lead = blockIdx.x == 0;
     if (lead && threadIdx.x == 0) st->dbg[0] = vl_globaltimer();
     const uint64_t n = st->n;
     const uint64_t nt = tile_count(st);
+    const uint64_t stride = st->tile_stride;
     const uint32_t tid = threadIdx.x;
+    const uint32_t NP = pa.n_parts;
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t gen = st->generation;
     uint32_t epoch = 0;
-    uint64_t *cnt = st->tile_cnt;  // final per-tile draw counts live in cnt[0..nt)
     // this CTA's slice of tiles
     const uint64_t per = (nt + gridDim.x - 1) / gridDim.x;
     const uint64_t t_lo = per * blockIdx.x < nt ? per * blockIdx.x : nt, t_hi = t_lo + per < nt ? t_lo + per : nt;
     uint64_t *prefix = nt <= smem_tiles ? s_prefix : st->tile_tree;  // (global fallback: every CTA writes the same values)
     plan_block_scan(st->tile_sum, prefix, nt, true, 0, s_scan, &s_carry);
-    if (tid == 0) {
+    if (tid < NP) {
         const uint64_t total = s_carry;
         double target = 0.0;
         if (n > 0) {
             double a = (double)total * st->dilution, b = (double)st->max_population;
             target = a <= b ? a : b;
         }
-        uint64_t size = use_amount ? amount : f64_as_usize(factor * target);
+        uint64_t size = pa.use_amount ? pa.amount[tid] : f64_as_usize(pa.factor[tid] * target);
         if (n == 0) size = 0;
         if (n > 0 && total == 0) { if (lead) raise(st, DE_ALL_ZERO_WEIGHTS); size = 0; }
-        if (set_next && size > st->cap_inf) { if (lead) raise(st, DE_INF_CAPACITY); size = st->cap_inf; }
+        if (pa.set_next && size > st->cap_inf) { if (lead) raise(st, DE_INF_CAPACITY); size = st->cap_inf; }
         if (lead) {
-            st->offspring_total = total;
-            st->target_size = target;
-            st->n_next = size;
+            if (tid == 0) {
+                st->offspring_total = total;
+                st->target_size = target;
+                st->n_next = size;
+            }
+            st->plan_size[tid] = size;
         }
-        s_size = size;
-        s_W = total;
+        s_size[tid] = size;
+        if (tid == 0) s_W = total;
     }
     __syncthreads();
-    const uint64_t size = s_size, W = s_W;
+    const uint64_t W = s_W;
     if (lead && tid == 0) st->dbg[1] = vl_globaltimer();
-    bool tree = force_tree != 0;
-    if (!tree) {
-        const double sd = sqrt((double)size);
-        double mu = (double)size - 5.0 * sd - 8.0;
-        if (!(mu > 0.0)) mu = 0.0;
-        uint64_t mine = 0;
-        for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) {
-            const uint64_t w = st->tile_sum[t];
-            uint64_t c = 0;
-            if (w > 0 && mu > 0.0) c = poisson_draw(key, t | ((uint64_t)salt << 48), gen, PH_PLAN, mu * ((double)w / (double)W), s_rcp);  // stage 0
-            cnt[t] = c;
-            mine += c;
-        }
-        mine = plan_block_sum(mine, s_scan);
-        if (tid == 0 && mine) atomicAdd((unsigned long long *)&st->plan_acc[0], (unsigned long long)mine);
-        plan_grid_barrier(st, epoch);
-        uint64_t K = plan_ld(&st->plan_acc[0]);
-        if (lead && tid == 0) st->dbg[2] = vl_globaltimer();
-        // the deficit size - K is itself Poissonised (same argument, smaller means) until a handful of draws remain
-        for (uint32_t stage = 1; stage < 4 && K <= size && size - K > 64; stage++) {
-            const double d = (double)(size - K);
-            double mu2 = d - 5.0 * sqrt(d) - 8.0;
-            if (!(mu2 > 0.0)) break;
-            uint64_t add = 0;
+    uint32_t tree_mask = pa.force_tree ? (NP >= 32 ? 0xFFFFFFFFu : (1u << NP) - 1u) : 0u;
+    uint64_t K[MAX_PARTS];
+    if (!pa.force_tree) {
+        for (uint32_t p = 0; p < NP; p++) {  // stage 0
+            const uint64_t size = s_size[p];
+            double mu = (double)size - 5.0 * sqrt((double)size) - 8.0;
+            if (!(mu > 0.0)) mu = 0.0;
+            uint64_t *cnt = st->tile_cnt + p * stride;
+            const uint64_t salt = (uint64_t)pa.salt[p] << 48;
+            uint64_t mine = 0;
             for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) {
                 const uint64_t w = st->tile_sum[t];
-                if (w > 0) {
-                    const uint64_t c = poisson_draw(key, t | ((uint64_t)salt << 48) | ((uint64_t)stage << 40), gen, PH_PLAN, mu2 * ((double)w / (double)W), s_rcp);
-                    cnt[t] += c;
-                    add += c;
+                uint64_t c = 0;
+                if (w > 0 && mu > 0.0) c = poisson_draw(key, t | salt, gen, PH_PLAN, mu * ((double)w / (double)W), s_rcp);
+                cnt[t] = c;
+                mine += c;
+            }
+            mine = plan_block_sum(mine, s_scan);
+            if (tid == 0 && mine) atomicAdd((unsigned long long *)&st->plan_acc[0][p], (unsigned long long)mine);
+        }
+        plan_grid_barrier(st, epoch);
+        for (uint32_t p = 0; p < NP; p++) K[p] = plan_ld(&st->plan_acc[0][p]);
+        if (lead && tid == 0) st->dbg[2] = vl_globaltimer();
+        // the deficit size - K of every part is itself Poissonised (same argument, smaller means) until a handful of draws remain
+        for (uint32_t stage = 1; stage < 4; stage++) {
+            uint32_t active = 0;
+            for (uint32_t p = 0; p < NP; p++) {
+                const uint64_t size = s_size[p];
+                if (K[p] <= size && size - K[p] > 64) {
+                    const double d = (double)(size - K[p]);
+                    if (d - 5.0 * sqrt(d) - 8.0 > 0.0) active |= 1u << p;
                 }
             }
-            add = plan_block_sum(add, s_scan);
-            if (tid == 0 && add) atomicAdd((unsigned long long *)&st->plan_acc[stage], (unsigned long long)add);
+            if (!active) break;  // the same decision in every CTA: K comes from the shared accumulators
+            for (uint32_t p = 0; p < NP; p++) {
+                if (!(active >> p & 1u)) continue;
+                const double d = (double)(s_size[p] - K[p]);
+                const double mu2 = d - 5.0 * sqrt(d) - 8.0;
+                uint64_t *cnt = st->tile_cnt + p * stride;
+                const uint64_t salt = ((uint64_t)pa.salt[p] << 48) | ((uint64_t)stage << 40);
+                uint64_t add = 0;
+                for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) {
+                    const uint64_t w = st->tile_sum[t];
+                    if (w > 0) {
+                        const uint64_t c = poisson_draw(key, t | salt, gen, PH_PLAN, mu2 * ((double)w / (double)W), s_rcp);
+                        cnt[t] += c;
+                        add += c;
+                    }
+                }
+                add = plan_block_sum(add, s_scan);
+                if (tid == 0 && add) atomicAdd((unsigned long long *)&st->plan_acc[stage][p], (unsigned long long)add);
+            }
             plan_grid_barrier(st, epoch);
-            K += plan_ld(&st->plan_acc[stage]);
+            for (uint32_t p = 0; p < NP; p++) if (active >> p & 1u) K[p] += plan_ld(&st->plan_acc[stage][p]);
         }
-        if (K > size) {
-            tree = true;
-        } else {
-            const uint64_t D = size - K;
+        for (uint32_t p = 0; p < NP; p++) {
+            const uint64_t size = s_size[p];
+            if (K[p] > size) { tree_mask |= 1u << p; continue; }
+            const uint64_t D = size - K[p];
+            uint64_t *cnt = st->tile_cnt + p * stride;
             for (uint64_t j = (uint64_t)blockIdx.x * PLAN_THREADS + tid; j < D; j += (uint64_t)gridDim.x * PLAN_THREADS) {
                 // Uniform(0, W): 64-bit widening multiply with rejection
-                Philox g(st->seed, st->compartment, gen, PH_PLAN_FILL, j | ((uint64_t)salt << 48));
+                Philox g(st->seed, st->compartment, gen, PH_PLAN_FILL, j | ((uint64_t)pa.salt[p] << 48));
                 const uint64_t r = g.below(W);
                 uint64_t lo = 0, hi = nt;  // first tile with prefix > r
                 while (lo < hi) {
@@ -1514,48 +1545,58 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
             }
         }
     }
-    if (tree && lead) {
-        __syncthreads();
+    if (tree_mask) plan_grid_barrier(st, epoch);  // (uniform) stage counts of the parts that fall back are about to be overwritten
+    if (tree_mask && lead) {
         const uint64_t P = pow2_ceil(nt ? nt : 1);
         uint64_t *tr = st->tile_tree, *ncnt = st->tile_node;
+        __syncthreads();
         for (uint64_t t = tid; t < P; t += PLAN_THREADS) tr[P + t] = t < nt ? st->tile_sum[t] : 0;
         __syncthreads();
         for (uint64_t s = P >> 1; s >= 1; s >>= 1) {
             for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) tr[node] = tr[2 * node] + tr[2 * node + 1];
             __syncthreads();
         }
-        if (tid == 0) ncnt[1] = size;
-        __syncthreads();
-        for (uint64_t s = 1; s < P; s <<= 1) {
-            for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) {
-                const uint64_t c = ncnt[node], wl = tr[2 * node], w = tr[node];
-                uint64_t left = 0;
-                if (c > 0 && wl > 0) {
-                    if (wl == w) left = c;
-                    else {
-                        Philox g(st->seed, st->compartment, gen, PH_PLAN_TREE, node | ((uint64_t)salt << 48));
-                        left = binomial(g, c, (double)wl / (double)w);
+        for (uint32_t p = 0; p < NP; p++) {
+            if (!(tree_mask >> p & 1u)) continue;
+            uint64_t *cnt = st->tile_cnt + p * stride;
+            if (tid == 0) ncnt[1] = s_size[p];
+            __syncthreads();
+            for (uint64_t s = 1; s < P; s <<= 1) {
+                for (uint64_t node = s + tid; node < 2 * s; node += PLAN_THREADS) {
+                    const uint64_t c = ncnt[node], wl = tr[2 * node], w = tr[node];
+                    uint64_t left = 0;
+                    if (c > 0 && wl > 0) {
+                        if (wl == w) left = c;
+                        else {
+                            Philox g(st->seed, st->compartment, gen, PH_PLAN_TREE, node | ((uint64_t)pa.salt[p] << 48));
+                            left = binomial(g, c, (double)wl / (double)w);
+                        }
                     }
+                    ncnt[2 * node] = left;
+                    ncnt[2 * node + 1] = c - left;
                 }
-                ncnt[2 * node] = left;
-                ncnt[2 * node + 1] = c - left;
+                __syncthreads();
             }
+            for (uint64_t t = tid; t < nt; t += PLAN_THREADS) cnt[t] = ncnt[P + t];
             __syncthreads();
         }
-        for (uint64_t t = tid; t < nt; t += PLAN_THREADS) cnt[t] = ncnt[P + t];
-        __syncthreads();
     }
     plan_grid_barrier(st, epoch);  // every count is final
     if (lead && tid == 0) st->dbg[3] = vl_globaltimer();
     // ---- (3) exclusive scan of the counts: slice totals first, then every CTA scans its slice from its base
-    uint64_t part = 0;
-    for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) part += __ldcg(&cnt[t]);
-    part = plan_block_sum(part, s_scan);
-    if (tid == 0) st->plan_part[blockIdx.x] = part;
+    for (uint32_t p = 0; p < NP; p++) {
+        const uint64_t *cnt = st->tile_cnt + p * stride;
+        uint64_t part = 0;
+        for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) part += __ldcg(&cnt[t]);
+        part = plan_block_sum(part, s_scan);
+        if (tid == 0) st->plan_part[blockIdx.x][p] = part;
+    }
     plan_grid_barrier(st, epoch);
-    uint64_t base = 0;
-    for (uint32_t g = 0; g < blockIdx.x; g++) base += plan_ld(&st->plan_part[g]);
-    plan_block_scan(cnt + t_lo, st->tile_base + t_lo, t_hi - t_lo, false, base, s_scan, &s_carry);
+    for (uint32_t p = 0; p < NP; p++) {
+        uint64_t base = 0;
+        for (uint32_t g = 0; g < blockIdx.x; g++) base += plan_ld(&st->plan_part[g][p]);
+        plan_block_scan(st->tile_cnt + p * stride + t_lo, st->tile_base + p * stride + t_lo, t_hi - t_lo, false, base, s_scan, &s_carry);
+    }
     if (lead && tid == 0) st->dbg[4] = vl_globaltimer();
 }
 
@@ -1566,8 +1607,14 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, do
 // mode 0: write the haplotype ids of the drawn records to dst; mode 1: write the drawn infectant indices (u64).
 constexpr uint32_t GUIDE_BITS = 11;
 constexpr uint32_t GUIDE_SIZE = 1u << GUIDE_BITS;
-__global__ void __launch_bounds__(TPB) k_resample(DevState *st, uint32_t *__restrict__ dst, uint64_t *__restrict__ dst64, int mode,
-                                                  uint32_t stream_salt) {
+// Several parts (subsamples of the same offspring map) are drawn in the same pass: the tile is staged once, every part
+// has its own draw counts, output buffer and Philox stream.
+struct ResampleArgs {
+    uint32_t n_parts;
+    uint32_t salt[MAX_PARTS];
+    uint32_t *dst[MAX_PARTS];  // nullptr = the population being assembled (hap_id_next)
+};
+__global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra, uint64_t *__restrict__ dst64, int mode) {
     __shared__ uint32_t s_cdf[RESAMPLE_TILE];
     __shared__ uint32_t s_hap[RESAMPLE_TILE];   // haplotype id (mode 0) or position inside the tile (mode 1)
     __shared__ uint16_t s_guide[GUIDE_SIZE];
@@ -1575,20 +1622,19 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, uint32_t *__rest
     const uint64_t nt = tile_count(st);
     const uint32_t *__restrict__ offspring = st->offspring;
     const uint2 *__restrict__ rec = st->rec;
-    if (dst == nullptr && mode == 0) dst = st->hap_id_next;
     constexpr uint32_t PER = RESAMPLE_TILE / TPB;  // consecutive items per thread
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t gen = st->generation;
-    const uint64_t salt = (uint64_t)stream_salt << 48;
+    const uint64_t stride = st->tile_stride;
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-        const uint64_t c = st->tile_cnt[tile];
-        if (c == 0) continue;  // uniform across the CTA
+        uint64_t any = 0;
+        for (uint32_t p = 0; p < ra.n_parts; p++) any |= st->tile_cnt[p * stride + tile];
+        if (any == 0) continue;  // uniform across the CTA
         if (st->tile_sum[tile] > 0xFFFFFFFFull) {  // the tile CDF is 32-bit
             if (tid == 0) raise(st, DE_OFFSPRING_RANGE);
             continue;
         }
-        const uint64_t base = st->tile_base[tile];
         uint64_t start;
         uint32_t tlen;
         tile_range(st, tile, start, tlen);
@@ -1644,7 +1690,13 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, uint32_t *__rest
             slot++;
         }
         __syncthreads();
-        // ---- draws: output slots [base, base + c), four per Philox block
+        // ---- draws of every part: output slots [base, base + c), four per Philox block
+        for (uint32_t part = 0; part < ra.n_parts; part++) {
+        const uint64_t c = st->tile_cnt[part * stride + tile];
+        if (c == 0) continue;
+        const uint64_t base = st->tile_base[part * stride + tile];
+        const uint64_t salt = (uint64_t)ra.salt[part] << 48;
+        uint32_t *__restrict__ dst = ra.dst[part] ? ra.dst[part] : st->hap_id_next;
         const uint64_t q_lo = base >> 2, q_hi = (base + c - 1) >> 2;
         for (uint64_t q = q_lo + tid; q <= q_hi; q += TPB) {
             const uint4 blk = philox_block(key, q | salt, gen, PH_RESAMPLE, 0);
@@ -1668,6 +1720,7 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, uint32_t *__rest
                 if (mode == 0) dst[s] = s_hap[i];
                 else dst64[s] = rec[start + s_hap[i]].x;
             }
+        }
         }
         __syncthreads();
     }

@@ -35,6 +35,7 @@ constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr int MAX_SPECS = 8;
 constexpr int MAX_PROVIDERS = 16;
 constexpr uint32_t RESAMPLE_TILE = 2048;  // CSR positions per resample tile (one CTA stages one tile in smem)
+constexpr int MAX_PARTS = 16;              // subsamples of one offspring map that one plan + one resample pass can draw together
 constexpr uint32_t HT_MAX_HOSTS = 2048;   // most hosts a host-range tile may span (DevState::host_tiles holds the actual number)
 constexpr uint32_t HT_MIN_HOSTS = 256;    // below this the fused replicate kernel is not worth launching
 
@@ -145,15 +146,17 @@ struct DevState {
     uint32_t *offspring;   // per CSR position
     uint64_t *tile_sum;    // per resample tile
     uint64_t *tile_tree;   // segment tree over tile sums (fallback plan) / inclusive prefix of tile sums
-    uint64_t *tile_cnt;    // draws per tile
+    uint64_t *tile_cnt;    // draws per tile, one row of tile_stride entries per part
     uint64_t *tile_node;   // draws per tree node (fallback plan)
-    uint64_t *tile_base;   // exclusive scan of draws per tile
+    uint64_t *tile_base;   // exclusive scan of draws per tile, per part
     uint64_t offspring_total;
     double target_size;    // of the last plan
     uint32_t plan_sync;    // grid barrier counter of the plan kernel; plan_sync .. plan_acc are cleared before every launch
     uint32_t _pad4;
-    uint64_t plan_acc[4];  // draws made per Poissonisation stage, summed over the plan CTAs
-    uint64_t plan_part[32]; // draws per CTA slice of tiles
+    uint64_t plan_acc[4][MAX_PARTS];   // draws made per Poissonisation stage and part, summed over the plan CTAs
+    uint64_t plan_part[32][MAX_PARTS]; // draws per CTA slice of tiles and part
+    uint64_t plan_size[MAX_PARTS];     // sample size of every part of the last plan
+    uint64_t tile_stride;              // tile_cnt / tile_base hold MAX_PARTS rows of this many tiles
 
     // ---- haplotype table (double-buffered for compaction; the live set is swapped on device)
     uint64_t cap_hap, cap_arena;

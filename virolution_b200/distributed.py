@@ -59,11 +59,7 @@ class GpuCompartment:
         self.n_providers = None
 
     def begin_generation(self):
-        s = self.sim
-        s.increment_generation()
-        s.infect()
-        s.mutate_infectants()
-        s.replicate_infectants(to_host=False)
+        self.sim.advance_to_offspring()
 
     def subsample_parts(self, factors: Sequence[float]):
         return self.sim.subsample_populations(factors)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "vl_pop_free": (C.c_int, [_vp]),
     "vl_next_generation": (C.c_int, [_vp]),
     "vl_run": (C.c_int, [_vp, C.c_uint64]),
+    "vl_advance_to_offspring": (C.c_int, [_vp]),
     "vl_step": (C.c_int, [C.POINTER(_vp), C.c_uint32, f64p, C.c_int]),
     "vl_synchronize": (C.c_int, [_vp]),
     "vl_infectant_generations": (C.c_int, [_vp, u64p, C.c_int]),
@@ -281,6 +282,10 @@ class GpuSimulation:
         self._check(self.lib.vl_next_generation(self.ptr))
 
     # ------------------------------------------------------------------ fused loops
+    def advance_to_offspring(self):
+        """increment_generation + infect + mutate_infectants + replicate_infectants, offspring map kept on the device."""
+        self._check(self.lib.vl_advance_to_offspring(self.ptr))
+
     def run(self, n_generations: int):
         self._check(self.lib.vl_run(self.ptr, n_generations))
 
