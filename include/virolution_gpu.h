@@ -223,6 +223,8 @@ typedef struct vl_migrant_image {
     const double *raw_device;       /* n_migrants * n_providers memoised raw fitness, migrant-major */
     const uint32_t *entries_device; /* n_words flattened haplotype entries, migrant after migrant */
     uint64_t n_migrants, n_words, n_providers;
+    uint64_t cap_migrants, cap_words; /* elements the buffers can hold before the library reallocates them (lets a caller
+                                         cache its views of the buffers across generations) */
 } vl_migrant_image;
 int vl_migrants_export_device(vl_sim *origin, vl_pop *const *parts, uint32_t n_parts, vl_migrant_image *image,
                               uint64_t *migrants_per_part, uint64_t *words_per_part);

@@ -63,7 +63,8 @@ class vl_config(C.Structure):
 
 class vl_migrant_image(C.Structure):
     _fields_ = [("len_device", C.c_void_p), ("raw_device", C.c_void_p), ("entries_device", C.c_void_p),
-                ("n_migrants", C.c_uint64), ("n_words", C.c_uint64), ("n_providers", C.c_uint64)]
+                ("n_migrants", C.c_uint64), ("n_words", C.c_uint64), ("n_providers", C.c_uint64),
+                ("cap_migrants", C.c_uint64), ("cap_words", C.c_uint64)]
 
 
 # ----------------------------------------------------------------------------- python-side description

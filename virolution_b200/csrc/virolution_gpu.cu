@@ -1145,6 +1145,8 @@ VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t
     image->n_migrants = M;
     image->n_words = W;
     image->n_providers = P;
+    image->cap_migrants = std::min<uint64_t>(sim->mig[0].bytes / 4, P ? sim->mig[2].bytes / (8 * P) : ~0ull);
+    image->cap_words = sim->mig[4].bytes / 4;
     return check_device_error(sim);
 }
 VL_API int vl_migrants_import_device(vl_sim *sim, const uint32_t *len_device, const double *raw_device, const uint32_t *entries_device,

@@ -43,10 +43,21 @@ class _DevicePointer:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def _view(ptr: int, n: int, typestr: str, dtype: torch.dtype, device) -> torch.Tensor:
+_VIEWS = {}  # (device pointer, typestr) -> longest torch view made of it; the library's staging buffers only ever grow
+
+
+def _view(ptr: int, n: int, cap: int, typestr: str, dtype: torch.dtype, device) -> torch.Tensor:
+    """torch view of n elements of a library buffer that holds `cap`; the view of the whole buffer is made once."""
     if n == 0 or not ptr:
         return torch.empty(0, dtype=dtype, device=device)
-    return torch.as_tensor(_DevicePointer(ptr, n, typestr), device=device)
+    key = (ptr, typestr, str(device))
+    v = _VIEWS.get(key)
+    if v is None or v.numel() < n:
+        if len(_VIEWS) > 64:
+            _VIEWS.clear()
+        v = torch.as_tensor(_DevicePointer(ptr, max(n, cap), typestr), device=device)
+        _VIEWS[key] = v
+    return v[:n]
 
 
 class GpuCompartment:
@@ -65,13 +76,18 @@ class GpuCompartment:
         return self.sim.subsample_populations(factors)
 
     def export_parts(self, parts):
+        import os, time
+        t0 = time.perf_counter()
         img, m, w = self.sim.export_migrants(parts)
+        if os.environ.get("VL_TRACE"):
+            self.t_export_c = getattr(self, "t_export_c", 0.0) + time.perf_counter() - t0
         P = int(img.n_providers)
         self.n_providers = P
         M, W = int(img.n_migrants), int(img.n_words)
-        return (_view(img.len_device, M, "<i4", torch.int32, self.device),
-                _view(img.raw_device, M * P, "<f8", torch.float64, self.device),
-                _view(img.entries_device, W, "<i4", torch.int32, self.device), m.astype(np.int64), w.astype(np.int64), P)
+        cm, cw = int(img.cap_migrants), int(img.cap_words)
+        return (_view(img.len_device, M, cm, "<i4", torch.int32, self.device),
+                _view(img.raw_device, M * P, cm * P, "<f8", torch.float64, self.device),
+                _view(img.entries_device, W, cw, "<i4", torch.int32, self.device), m.astype(np.int64), w.astype(np.int64), P)
 
     def import_part(self, lens: torch.Tensor, raw: torch.Tensor, entries: torch.Tensor):
         return self.sim.import_migrants(lens.data_ptr() if lens.numel() else 0, raw.data_ptr() if raw.numel() else 0,
