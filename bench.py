@@ -32,20 +32,22 @@ if ROOT not in sys.path:
 METRIC = "infectant-generations/sec"
 UNIT = "infectant-generations/s"
 
-# Algorithmic bytes per infectant for each kernel of the generation.
-# u32 ids/hosts/offspring, f64 fitness.  "per host" terms are multiplied by H/N (= 1 for the K configs).
+# Algorithmic bytes per unit for each kernel of the fused generation: u32 ids/hosts/offspring,
+# f64 fitness, 16-byte bucket records, 8-byte CSR records.  "per host" terms are multiplied by H/N (= 1 for the K configs).
+# Unit = one infectant at generation start, except k_mutate (one mutated infectant, measured separately below).
 ALGO_BYTES = {
-    "k_infect": 4 + 4 + 8,              # write host_id, write rank, histogram read-modify-write (4+4)
-    "k_scatter_hosts": 4 + 4 + 4 + 4,   # read host_id, rank, gather offsets[h], scatter hosts[]
-    "k_sort_slices": 8,                 # read offsets[h], offsets[h+1] (per host)
-    "k_mutation_counts": 4,             # read host_id
-    "k_fitness": 4 + 4 + 8 + 8,         # read host_id, hap_id, gather raw fitness, write fit
-    "k_host_sum": 8 + 4 + 8 + 8,        # per host: offsets pair; per infectant: hosts[], gather fit; per host: write hsum
-    "k_offspring": 4 + 8 + 8 + 4,       # read host_id, fit, gather hsum, write offspring
-    "k_resample": 4 + 4 + 4,            # read offspring, hap_id (tile staging), write next hap_id
-    "(k_scan_u32<OutT, EXCL>)": 4 + 4,  # per host: read count, write offsets
+    "k_replicate_fused<true>": 4 + 8 + 8 + 4,   # offsets[h] (per host), rec[p], gather raw fitness, write offspring
+    "k_replicate_fused<false>": 4 + 8 + 8 + 4,
+    "(k_infect_bucket<false, false, 1024>)": 4 + 16,  # read hap_id, append (index, haplotype, host) to the host bucket
+    "(k_infect_bucket<true, true, 1024>)": 4 + 4 + 16,  # ... + host_id[] kept for the trait-level phases
+    "(k_bucket_sort<1024, BSORT_STAGE_RECS>)": 16 + 8 + 4,  # read bucket record, write rec[p], offsets[h] (per host)
+    "k_resample": 4 + 8 + 4,                    # offspring[p], rec[p] (tile staging), write next hap_id
+    "k_fitness": 8 + 8 + 8, "k_host_sum": 8 + 8 + 8 + 8, "k_offspring<true>": 8 + 8 + 4, "k_offspring<false>": 8 + 8 + 4,
+    "k_infect<true, true>": 4 + 4 + 8, "k_scatter": 4 + 4 + 4 + 4 + 8,
 }
-FITNESS_REPLICATION = ("k_fitness", "k_host_sum", "k_offspring", "k_resample")
+# the kernels SURVEY.md §8d's 72 B figure covers (fitness gather + per-host sum + offspring + scan/plan + resample)
+FITNESS_REPLICATION = ("k_replicate_fused<true>", "k_replicate_fused<false>", "k_fitness", "k_host_sum", "k_host_sum_medium",
+                       "k_host_sum_heavy", "k_offspring<true>", "k_offspring<false>", "k_plan_resample", "k_resample")
 
 
 def parse_args():
@@ -233,8 +235,15 @@ def run_b200(args, rank, world):
         achieved = ALGO_BYTES[dom] * n_now / (dms / dcnt * 1e-3) / 1e9
         fr_ms = sum(rep[k][1] / args.profile_steps for k in FITNESS_REPLICATION if k in rep)
         fr_bytes = 72.0 * n_now  # fitness + replication + scan/resample
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (same workload size only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tj.get("n") == n_now and dom in tj:
+                traffic = tj[dom]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_infectant": ALGO_BYTES[dom], "infectants_per_launch": n_now,
                     "fitness_replication_group": {"kernels": [k for k in FITNESS_REPLICATION if k in rep],
                                                   "ms_per_generation": round(fr_ms, 5), "algorithmic_bytes_per_infectant": 72,

@@ -463,7 +463,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
         size_t free_b = 0, total_b = 0;
         CCU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t P = std::max<uint32_t>(h.n_providers, 1);
-        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 80 + ch * (52 + 16 * P) + ca * 8; };
+        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 80 + ch * (52 + 32 * P) + ca * 8; };
         if (!cfg->capacity_haplotypes || !cfg->capacity_arena_words) {
             for (int it = 0; it < 64 && need(cap_hap, cap_arena) > (uint64_t)(0.7 * (double)free_b); it++) {
                 if (!cfg->capacity_arena_words && cap_arena > (1ull << 20)) cap_arena = cap_arena * 3 / 4;
@@ -491,7 +491,10 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
     CTRY(dev_alloc(sim, &h.hm, cap_hap)); CTRY(dev_alloc(sim, &h.hm_alt, cap_hap));
-    for (uint32_t p = 0; p < h.n_providers; p++) { CTRY(dev_alloc(sim, &h.h_raw[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_raw_alt[p], cap_hap)); }
+    for (uint32_t p = 0; p < h.n_providers; p++) {
+        CTRY(dev_alloc(sim, &h.h_raw[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_raw_alt[p], cap_hap));
+        CTRY(dev_alloc(sim, &h.h_fit[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_fit_alt[p], cap_hap));
+    }
     CTRY(dev_alloc(sim, &h.arena, cap_arena)); CTRY(dev_alloc(sim, &h.arena_alt, cap_arena));
     CTRY(dev_alloc(sim, &h.gc_mark, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_newid, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_len, cap_hap + 1));
     CTRY(dev_alloc(sim, &h.gc_newoff, cap_hap + 1));
@@ -503,13 +506,12 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     h.n_hap = 1;
     h.arena_top = 0;
     {
-        const double one = 1.0;
         HapMeta wt{0, 0, NONE32};
         CCU(cudaMemcpy(h.hm, &wt, sizeof(HapMeta), cudaMemcpyHostToDevice));
-        for (uint32_t p = 0; p < h.n_providers; p++) CCU(cudaMemcpy(h.h_raw[p], &one, 8, cudaMemcpyHostToDevice));
     }
     CTRY(dev_alloc(sim, &sim->d, 1));
     CCU(cudaMemcpy(sim->d, &h, sizeof(DevState), cudaMemcpyHostToDevice));
+    k_init_wildtype<<<1, 1, 0, sim->stream>>>(sim->d);  // raw fitness 1 and its mapped value under every provider
     // garbage-collection cadence: expected new records per generation from p_mut = 1-(1-mu)^L, with slack
     {
         double p_mut = 1.0 - pow(1.0 - par.mutation_rate, (double)L);

@@ -36,6 +36,16 @@ constexpr uint32_t SMEM_SORT_MAX = 4096;  // slices up to this length are sorted
 constexpr int INFECT_ITEMS = 4;           // infectants per thread and round in k_infect / k_scatter
 
 __device__ __forceinline__ void raise(DevState *st, uint32_t bit) { atomicOr(&st->error, bit); }
+// memoise a record's raw fitness under provider p together with the mapped value utility(raw): the raw value is what
+// descendants multiply (FitnessProvider::get_fitness, src/providers/fitness.rs:212-223), the mapped value is what
+// infect and replicate read (AttributeSet::get_or_compute, src/core/attributes.rs:220-241) — N reads per generation
+__device__ __forceinline__ void set_fitness(DevState *st, uint32_t p, uint64_t id, double raw) {
+    st->h_raw[p][id] = raw;
+    st->h_fit[p][id] = utility_apply(st->prov[p], raw);
+}
+__global__ void k_init_wildtype(DevState *st) {  // haplotype 0: no entries, raw fitness = empty product (src/core/fitness/table.rs:72-79)
+    for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, 0, 1.0);
+}
 __device__ __forceinline__ uint64_t vl_globaltimer() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -106,7 +116,7 @@ __device__ __noinline__ uint32_t infect_general(const DevState *st, uint64_t i, 
         if (s < 0) continue;
         double infectivity = 1.;
         int pi = st->specs[s].infect;
-        if (pi >= 0) infectivity = utility_apply(st->prov[pi], hap_raw(st, pi, st->hap_id[i]));
+        if (pi >= 0) infectivity = st->h_fit[pi][st->hap_id[i]];
         if (g.u01() < infectivity) return (uint32_t)cand;
     }
     return NONE32;
@@ -631,7 +641,7 @@ __device__ inline uint32_t make_recombinant(DevState *st, uint32_t left, uint32_
     st->hm[r.id].off = r.off;
     st->hm[r.id].len = o;
     st->hm[r.id].parent = left;
-    for (uint32_t p = 0; p < st->n_providers; p++) hap_raw(st, p, r.id) = compute_fitness_full(st->prov[p], out, o);
+    for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, r.id, compute_fitness_full(st->prov[p], out, o));
     return r.id;
 }
 
@@ -882,7 +892,7 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
                 if (pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, out, o);
                 raw = praw * acc;
             }
-            st->h_raw[p][new_id] = raw;
+            set_fitness(st, p, new_id, raw);
         }
         st->hm[new_id] = HapMeta{roff, o, pid};
         st->hap_id[i] = new_id;
@@ -903,7 +913,7 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
 // mapped fitness of a haplotype under the reproductive provider of spec s (or 1.0), src/simulation.rs:137-143
 __device__ __forceinline__ double reproductive_fitness(const DevState *st, int s, uint32_t hap) {
     const int pi = s >= 0 ? st->specs[s].repro : -1;
-    return pi >= 0 ? utility_apply(st->prov[pi], hap_raw(st, pi, hap)) : 1.;
+    return pi >= 0 ? st->h_fit[pi][hap] : 1.;
 }
 // lambda as the offspring kernel consumes it: 0.0 stands for "no offspring".  Poisson::new fails for a mean that
 // is not finite and > 0; the reference then leaves the f64 bit pattern of f in the slot (src/simulation.rs:146-152),
@@ -937,7 +947,7 @@ __global__ void __launch_bounds__(TPB) k_fitness(DevState *st, int guarded) {
     const int pi0 = st->specs[0].repro;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (uint64_t)gridDim.x * blockDim.x) {
         double f;
-        if (single) f = pi0 >= 0 ? utility_apply(st->prov[pi0], hap_raw(st, pi0, rec[p].y)) : 1.;
+        if (single) f = pi0 >= 0 ? st->h_fit[pi0][rec[p].y] : 1.;
         else f = reproductive_fitness(st, find_spec_of_position(st, p), rec[p].y);
         lam[p] = f;
     }
@@ -1165,7 +1175,7 @@ __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t 
 constexpr int REPL_TPB = 512;
 constexpr int REPL_PER = RESAMPLE_TILE / REPL_TPB;
 template <bool SMALL_ONLY>
-__global__ void __launch_bounds__(REPL_TPB, 2) k_replicate_fused(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda,
+__global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda,
                                                                  int fail_is_error, uint32_t ht) {
     __shared__ uint32_t s_off[HT_MAX_HOSTS + 1];
     __shared__ uint32_t s_head[RESAMPLE_TILE / 32 + 2];
@@ -1186,6 +1196,7 @@ __global__ void __launch_bounds__(REPL_TPB, 2) k_replicate_fused(DevState *st, c
     const bool single = st->n_specs == 1 && st->specs[0].lo == 0 && st->specs[0].hi >= H;
     const int pi0 = st->specs[0].repro;
     const uint32_t tid = threadIdx.x;
+    const uint32_t kmax = poisson_kmax(R0 < 12.0 ? R0 : 12.0);  // lambda = R0 * f / S <= R0 for non-negative fitness
     if (blockIdx.x == 0 && tid == 0) st->host_tiles = ht;
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
         const uint64_t h0 = tile * ht;
@@ -1212,7 +1223,7 @@ __global__ void __launch_bounds__(REPL_TPB, 2) k_replicate_fused(DevState *st, c
             const uint32_t q = tid + j * REPL_TPB;
             f[j] = 0.0;
             if (q < cnt) {
-                if (single) f[j] = pi0 >= 0 ? hap_raw(st, pi0, r[j].y) : 1.;
+                if (single) f[j] = pi0 >= 0 ? st->h_fit[pi0][r[j].y] : 1.;
                 else f[j] = reproductive_fitness(st, find_spec_of_position(st, (uint64_t)p0 + q), r[j].y);
             }
         }
@@ -1220,7 +1231,6 @@ __global__ void __launch_bounds__(REPL_TPB, 2) k_replicate_fused(DevState *st, c
         for (int j = 0; j < REPL_PER; j++) {
             const uint32_t q = tid + j * REPL_TPB;
             if (q < cnt) {
-                if (single && pi0 >= 0) f[j] = utility_apply(st->prov[pi0], f[j]);
                 s_rec[q] = r[j];
                 s_f[q] = f[j];
             }
@@ -1284,7 +1294,7 @@ __global__ void __launch_bounds__(REPL_TPB, 2) k_replicate_fused(DevState *st, c
                 off = (uint32_t)v;
             } else if (l > 0.0) {
                 uint64_t v;
-                if (l < 12.0) v = poisson_draw_small_fast(key, p, gen, PH_OFFSPRING, l, s_rcp);
+                if (l < 12.0) v = poisson_draw_small_fast(key, p, gen, PH_OFFSPRING, l, s_rcp, kmax);
                 else if (SMALL_ONLY) { raise(st, DE_UNDEFINED_OFFSPRING); v = 0; }  // f > S: negative fitness values in the slice
                 else v = poisson_ptrs(key, p, gen, PH_OFFSPRING, l);
                 if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
@@ -1781,7 +1791,7 @@ __global__ void __launch_bounds__(TPB) k_gc_copy(DevState *st) {
         st->hm_alt[nid].len = len;
         const uint32_t par = st->hm[h].parent;
         st->hm_alt[nid].parent = (par != NONE32 && st->gc_mark[par]) ? st->gc_newid[par] : NONE32;
-        for (uint32_t p = 0; p < st->n_providers; p++) hap_raw_alt(st, p, nid) = hap_raw(st, p, h);
+        for (uint32_t p = 0; p < st->n_providers; p++) { hap_raw_alt(st, p, nid) = hap_raw(st, p, h); st->h_fit_alt[p][nid] = st->h_fit[p][h]; }
     }
 }
 __global__ void __launch_bounds__(TPB) k_gc_remap(DevState *st, uint32_t *ids, uint64_t m, int use_population) {
@@ -1796,7 +1806,7 @@ __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
     st->arena_top = gc_totals[1];
 #define VL_SWAP(a, b) { auto t = st->a; st->a = st->b; st->b = t; }
     VL_SWAP(hm, hm_alt) VL_SWAP(arena, arena_alt)
-    for (uint32_t p = 0; p < st->n_providers; p++) VL_SWAP(h_raw[p], h_raw_alt[p])
+    for (uint32_t p = 0; p < st->n_providers; p++) { VL_SWAP(h_raw[p], h_raw_alt[p]) VL_SWAP(h_fit[p], h_fit_alt[p]) }
 #undef VL_SWAP
     st->gc_runs += 1;
     st->gc_active = 0;
@@ -1869,7 +1879,7 @@ __global__ void k_test_poisson_fast(uint64_t seed, double lambda, uint64_t n, ui
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         // lambda <= 0 selects a per-draw mean spread over (0, 12) so that the guard band is exercised at every scale
         const double l = lambda > 0.0 ? lambda : 12.0 * u01_open_from(philox_block(key, i, 1, PH_TEST, 0).x, philox_block(key, i, 1, PH_TEST, 0).y);
-        out[i] = poisson_draw_small_fast(key, i, 0, PH_TEST, l, s_rcp);
+        out[i] = poisson_draw_small_fast(key, i, 0, PH_TEST, l, s_rcp, poisson_kmax(lambda > 0.0 ? lambda : 12.0));
         const uint4 b = philox_block(key, i, 0, PH_TEST, 0);
         out[n + i] = poisson_inversion_f64(u01_from(b.x, b.y), l, s_rcp);
     }

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(TPB) k_unpack(DevState *st, const uint8_t *__r
             st->hm[id].off = a0 + i_off[u];
             st->hm[id].len = i_len[u];
             st->hm[id].parent = NONE32;
-            for (uint32_t p = 0; p < st->n_providers; p++) hap_raw(st, p, id) = i_raw[(uint64_t)p * hd.n_unique + u];
+            for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, id, i_raw[(uint64_t)p * hd.n_unique + u]);
         }
         for (uint64_t w = tid; w < hd.n_words; w += span) st->arena[a0 + w] = i_ent[w];
     }
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(TPB) k_mig_import(DevState *st, const uint32_t
         if (l == MIG_WILDTYPE || !ok) { ids_out[i] = 0u; continue; }
         const uint64_t id = id0 + rec_off[i], off = a0 + word_off[i];
         st->hm[id] = HapMeta{off, l, NONE32};
-        for (uint32_t p = 0; p < P; p++) hap_raw(st, p, id) = raw_in[i * P + p];
+        for (uint32_t p = 0; p < P; p++) set_fitness(st, p, id, raw_in[i * P + p]);
         const uint32_t *src = entries_in + word_off[i];
         uint32_t *dst = st->arena + off;
         for (uint32_t k = 0; k < l; k++) dst[k] = src[k];

@@ -271,21 +271,29 @@ __device__ __forceinline__ uint32_t poisson_inversion_f64(double u, double lambd
     }
     return k;
 }
+// `kmax` is the same for every lane (it comes from the largest mean a launch can see): all lanes walk the CDF up to
+// kmax without a data-dependent branch — in a warp the search would run to the slowest lane's answer anyway — and the
+// answer is the number of CDF values that u has reached.
 __device__ __forceinline__ uint32_t poisson_draw_small_fast(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, double lambda,
-                                                            const double *rcp) {
+                                                            const double *rcp, uint32_t kmax) {
     const uint4 b = philox_block(key, index, generation, phase, 0);
     const double u = u01_from(b.x, b.y);
     const float uf = (float)u, lf = (float)lambda;
     float p = __expf(-lf), cdf = p, mind = fabsf(uf - cdf);
-    uint32_t k = 0;
-    while (uf >= cdf && k < 48) {
-        k += 1;
-        p *= lf * __frcp_rn((float)k);
+    uint32_t k = uf >= cdf ? 1u : 0u;
+    for (uint32_t j = 1; j <= kmax; j++) {
+        p *= lf * __frcp_rn((float)j);
         cdf += p;
         mind = fminf(mind, fabsf(uf - cdf));
+        k += uf >= cdf ? 1u : 0u;
     }
-    if (mind > POISSON_GUARD && k < 48) return k;
+    if (k <= kmax && mind > POISSON_GUARD) return k;  // u < CDF(kmax) and clear of every CDF value it was compared with
     return poisson_inversion_f64(u, lambda, rcp);
+}
+// kmax for means up to `max_mean` (< 12): beyond it lies less than 1e-3 of the mass, those draws take the f64 search
+__host__ __device__ inline uint32_t poisson_kmax(double max_mean) {
+    double k = max_mean + 3.2 * sqrt(max_mean > 0.0 ? max_mean : 0.0) + 2.0;
+    return k < 46.0 ? (uint32_t)k : 46u;
 }
 // fills a CTA's shared reciprocal table (call by all threads, then __syncthreads())
 __device__ __forceinline__ void poisson_rcp_init(double *rcp) {

@@ -166,6 +166,7 @@ struct DevState {
     uint32_t _pad1;
     HapMeta *hm, *hm_alt;  // 16 bytes per haplotype: arena offset, length, parent
     double *h_raw[MAX_PROVIDERS], *h_raw_alt[MAX_PROVIDERS];  // memoised raw fitness per provider
+    double *h_fit[MAX_PROVIDERS], *h_fit_alt[MAX_PROVIDERS];  // utility(raw): what readers of get_or_compute see (attributes.rs:220-241)
     uint32_t *arena, *arena_alt;
     uint32_t *gc_mark, *gc_newid, *gc_len;
     uint64_t *gc_newoff;
