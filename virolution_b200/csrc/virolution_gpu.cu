@@ -733,7 +733,7 @@ static int enqueue_mutate(vl_sim *sim) {
         TRY(zero_field32(sim, FIELD_OFF(n_mut_list)));
         LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0));
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0);
     sim->mutcounts_ready = false;
     sim->has_rp_mut = false;
     sim->has_rp_rec = false;
@@ -753,9 +753,10 @@ static int enqueue_replicate(vl_sim *sim, int store_lambda = 1) {
     const bool fused_only = fused && sim->uniform_infection;
     int guarded = 0;
     if (fused) {
-        const unsigned g = (unsigned)std::min<uint64_t>(n_host_tiles, (uint64_t)sim->n_sms * 16);
-        if (small) LAUNCH(sim, k_replicate_fused<true>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht);
-        else LAUNCH(sim, k_replicate_fused<false>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht);
+        const uint32_t per = n_host_tiles >= (uint64_t)sim->n_sms * 12 ? 2u : 1u;  // consecutive tiles per CTA (prefetch of the second)
+        const unsigned g = (unsigned)((n_host_tiles + per - 1) / per);
+        if (small) LAUNCH(sim, k_replicate_fused<true>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht, per);
+        else LAUNCH(sim, k_replicate_fused<false>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht, per);
         guarded = 1;
     }
     if (!fused_only) {
@@ -1273,7 +1274,7 @@ static int enqueue_generation_front(vl_sim *sim) {
         // depend on its host, so mutate first and build the host map from the already-mutated population
         LAUNCH(sim, k_begin_generation, 1, 1024, 0, sim->d);
         LAUNCH(sim, k_mutcount_fast, grid_tiles(sim, sim->n_bound, (uint64_t)TPB * MC_ITEMS, 8), TPB, 0, sim->d);
-        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, 0, sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0);
+        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, 0, sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0, 1);
         const int btpb = (sim->experiment & 2) ? 512 : 1024;
         const unsigned chunks = (unsigned)std::max<uint64_t>(1, (sim->n_bound + btpb * BUCKET_ITEMS - 1) / (btpb * BUCKET_ITEMS));
         if (btpb == 1024) LAUNCH(sim, (k_infect_bucket<false, false, 1024>), chunks, 1024, 0, sim->d);

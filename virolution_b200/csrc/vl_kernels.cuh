@@ -746,9 +746,15 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
     const uint32_t gen = st->generation;
     const uint64_t chunk = (uint64_t)TPB * MC_ITEMS;
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const uint32_t *__restrict__ hap_id = st->hap_id;
     for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        uint32_t nm[MC_ITEMS];
+        uint32_t nm[MC_ITEMS], hp[MC_ITEMS];
         uint32_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < MC_ITEMS; e++) {  // the haplotype id travels with the item: read here it is a coalesced stream
+            const uint64_t i = c * chunk + (uint64_t)e * TPB + threadIdx.x;
+            hp[e] = i < n ? hap_id[i] : 0u;
+        }
 #pragma unroll
         for (int e = 0; e < MC_ITEMS; e++) {
             const uint64_t i = c * chunk + (uint64_t)e * TPB + threadIdx.x;
@@ -764,7 +770,7 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
             uint32_t o = s_base + off;
 #pragma unroll
             for (int e = 0; e < MC_ITEMS; e++)
-                if (nm[e]) st->mut_list[o++] = make_uint4((uint32_t)(c * chunk + (uint64_t)e * TPB + threadIdx.x), nm[e], NONE32, 0u);
+                if (nm[e]) st->mut_list[o++] = make_uint4((uint32_t)(c * chunk + (uint64_t)e * TPB + threadIdx.x), nm[e], NONE32, hp[e]);
         }
         __syncthreads();
     }
@@ -777,7 +783,10 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
 // patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist.
 constexpr uint32_t MUT_LOCAL_PARENT = 16;  // parent records up to this length are staged in thread-local memory
 constexpr uint32_t MUT_LOCAL_CHANGES = 8;  // mutation events up to this many sites keep their change words there too
-__global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records) {
+constexpr uint32_t MUT_SCRATCH_STRIDE = MUT_LOCAL_PARENT + MUT_LOCAL_CHANGES + 1;  // odd: consecutive threads hit distinct banks
+// parent_in_item: the worklist items carry the infectant's current haplotype id in .w (k_mutcount_fast)
+__global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
+    __shared__ uint32_t s_scratch[TPB * MUT_SCRATCH_STRIDE];
     const uint32_t n_list = st->n_mut_list;
     const uint32_t L = st->L;
     const uint8_t *__restrict__ wt = st->wildtype;
@@ -795,7 +804,7 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
             i = item.x;
             nm = item.y;
             tpos = item.z;
-            pid = st->hap_id[i];
+            pid = parent_in_item ? item.w : st->hap_id[i];
             pm = st->hm[pid];  // one 16-byte load: arena offset, length, parent
             plen = pm.len;
         }
@@ -822,9 +831,10 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
         if (roff + words > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); continue; }
         const uint32_t new_id = (uint32_t)id64;
         uint32_t *out = st->arena + roff;
-        // parent entries and change words in thread-local memory when they are short (the usual case): every lookup
-        // below is then an L1 hit instead of a dependent trip to L2/HBM
-        uint32_t pe_local[MUT_LOCAL_PARENT], ch_local[MUT_LOCAL_CHANGES];
+        // parent entries and change words in the thread's slice of shared memory when they are short (the usual case):
+        // every lookup below is then a shared-memory access instead of a dependent trip to L2/HBM (thread-local arrays
+        // would be indexed dynamically, i.e. live in local memory and cost L2 write traffic of their own)
+        uint32_t *pe_local = s_scratch + threadIdx.x * MUT_SCRATCH_STRIDE, *ch_local = pe_local + MUT_LOCAL_PARENT;
         const uint32_t *pe = st->arena + pm.off;
         if (plen <= MUT_LOCAL_PARENT) {
 #pragma unroll
@@ -1176,7 +1186,7 @@ constexpr int REPL_TPB = 512;
 constexpr int REPL_PER = RESAMPLE_TILE / REPL_TPB;
 template <bool SMALL_ONLY>
 __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda,
-                                                                 int fail_is_error, uint32_t ht) {
+                                                                 int fail_is_error, uint32_t ht, uint32_t tiles_per_cta) {
     __shared__ uint32_t s_off[HT_MAX_HOSTS + 1];
     __shared__ uint32_t s_head[RESAMPLE_TILE / 32 + 2];
     __shared__ double s_f[RESAMPLE_TILE];
@@ -1197,8 +1207,11 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
     const int pi0 = st->specs[0].repro;
     const uint32_t tid = threadIdx.x;
     const uint32_t kmax = poisson_kmax(R0 < 12.0 ? R0 : 12.0);  // lambda = R0 * f / S <= R0 for non-negative fitness
+    const uint64_t n_sorted = st->n_sorted;
     if (blockIdx.x == 0 && tid == 0) st->host_tiles = ht;
-    for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+    // a CTA takes consecutive tiles, so while it works on one it knows where the next one's offsets and records are
+    const uint64_t tile_end = (uint64_t)(blockIdx.x + 1) * tiles_per_cta < nt ? (uint64_t)(blockIdx.x + 1) * tiles_per_cta : nt;
+    for (uint64_t tile = (uint64_t)blockIdx.x * tiles_per_cta; tile < tile_end; tile++) {
         const uint64_t h0 = tile * ht;
         const uint32_t nh = (uint32_t)(H - h0 < ht ? H - h0 : ht);
         __syncthreads();  // shared arrays of the previous tile are free (and s_rcp is filled)
@@ -1234,6 +1247,11 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
                 s_rec[q] = r[j];
                 s_f[q] = f[j];
             }
+        }
+        if (tile + 1 < tile_end) {  // pull the next tile's offsets and records towards L2 while this one is computed
+            const uint64_t hn = h0 + ht + (uint64_t)tid * 8;
+            if (hn <= H) asm volatile("prefetch.global.L2 [%0];" ::"l"(offsets + hn));
+            if ((uint64_t)p0 + cnt + (uint64_t)tid * 4 < n_sorted) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (uint64_t)p0 + cnt + (uint64_t)tid * 4));
         }
         bool failed = false;
         for (uint32_t k = tid; k < nh; k += REPL_TPB) {

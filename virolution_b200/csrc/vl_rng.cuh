@@ -237,6 +237,9 @@ __device__ __noinline__ uint64_t poisson_ptrs(PhiloxKey key, uint64_t index, uin
 // same law as rand_distr 0.5.1's Knuth product branch at a fraction of the random words.  `rcp` is a table of
 // 1/k for k < POISSON_RCP (the term ratio lambda/k as a multiplication; distribution unchanged to 1 ulp of a term).
 constexpr int POISSON_RCP = 64;
+// 1/k, correctly rounded (what 1.0 / (double)k and __frcp_rn((float)k) return), so no kernel spends divisions on them
+__constant__ double c_rcp64[POISSON_RCP] = {0.0, 1.0, 0.5, 0.3333333333333333, 0.25, 0.2, 0.16666666666666666, 0.14285714285714285, 0.125, 0.1111111111111111, 0.1, 0.09090909090909091, 0.08333333333333333, 0.07692307692307693, 0.07142857142857142, 0.06666666666666667, 0.0625, 0.058823529411764705, 0.05555555555555555, 0.05263157894736842, 0.05, 0.047619047619047616, 0.045454545454545456, 0.043478260869565216, 0.041666666666666664, 0.04, 0.038461538461538464, 0.037037037037037035, 0.03571428571428571, 0.034482758620689655, 0.03333333333333333, 0.03225806451612903, 0.03125, 0.030303030303030304, 0.029411764705882353, 0.02857142857142857, 0.027777777777777776, 0.02702702702702703, 0.02631578947368421, 0.02564102564102564, 0.025, 0.024390243902439025, 0.023809523809523808, 0.023255813953488372, 0.022727272727272728, 0.022222222222222223, 0.021739130434782608, 0.02127659574468085, 0.020833333333333332, 0.02040816326530612, 0.02, 0.0196078431372549, 0.019230769230769232, 0.018867924528301886, 0.018518518518518517, 0.01818181818181818, 0.017857142857142856, 0.017543859649122806, 0.017241379310344827, 0.01694915254237288, 0.016666666666666666, 0.01639344262295082, 0.016129032258064516, 0.015873015873015872};
+__constant__ float c_rcp32[48] = {0.0f, 1.0f, 0.5f, 0.3333333432674408f, 0.25f, 0.20000000298023224f, 0.1666666716337204f, 0.1428571492433548f, 0.125f, 0.1111111119389534f, 0.10000000149011612f, 0.09090909361839294f, 0.0833333358168602f, 0.07692307978868484f, 0.0714285746216774f, 0.06666667014360428f, 0.0625f, 0.05882352963089943f, 0.0555555559694767f, 0.05263157933950424f, 0.05000000074505806f, 0.0476190485060215f, 0.04545454680919647f, 0.043478261679410934f, 0.0416666679084301f, 0.03999999910593033f, 0.03846153989434242f, 0.03703703731298447f, 0.0357142873108387f, 0.03448275849223137f, 0.03333333507180214f, 0.032258063554763794f, 0.03125f, 0.03030303120613098f, 0.029411764815449715f, 0.02857142873108387f, 0.02777777798473835f, 0.027027027681469917f, 0.02631578966975212f, 0.025641025975346565f, 0.02500000037252903f, 0.024390242993831635f, 0.02380952425301075f, 0.023255813866853714f, 0.022727273404598236f, 0.02222222276031971f, 0.021739130839705467f, 0.021276595070958138f};
 template <bool SMALL_ONLY = false>
 __device__ __forceinline__ uint64_t poisson_draw(PhiloxKey key, uint64_t index, uint32_t generation, uint32_t phase, double lambda,
                                                  const double *rcp) {
@@ -282,7 +285,7 @@ __device__ __forceinline__ uint32_t poisson_draw_small_fast(PhiloxKey key, uint6
     float p = __expf(-lf), cdf = p, mind = fabsf(uf - cdf);
     uint32_t k = uf >= cdf ? 1u : 0u;
     for (uint32_t j = 1; j <= kmax; j++) {
-        p *= lf * __frcp_rn((float)j);
+        p *= lf * c_rcp32[j];  // j is uniform: one constant-bank operand for the warp
         cdf += p;
         mind = fminf(mind, fabsf(uf - cdf));
         k += uf >= cdf ? 1u : 0u;
@@ -293,11 +296,11 @@ __device__ __forceinline__ uint32_t poisson_draw_small_fast(PhiloxKey key, uint6
 // kmax for means up to `max_mean` (< 12): beyond it lies less than 1e-3 of the mass, those draws take the f64 search
 __host__ __device__ inline uint32_t poisson_kmax(double max_mean) {
     double k = max_mean + 3.2 * sqrt(max_mean > 0.0 ? max_mean : 0.0) + 2.0;
-    return k < 46.0 ? (uint32_t)k : 46u;
+    return k < 46.0 ? (uint32_t)k : 46u;  // < the 48 entries of c_rcp32
 }
 // fills a CTA's shared reciprocal table (call by all threads, then __syncthreads())
 __device__ __forceinline__ void poisson_rcp_init(double *rcp) {
-    for (int k = threadIdx.x; k < POISSON_RCP; k += blockDim.x) rcp[k] = k ? 1.0 / (double)k : 0.0;
+    for (int k = threadIdx.x; k < POISSON_RCP; k += blockDim.x) rcp[k] = c_rcp64[k];
 }
 
 // Binomial(n, p) in the small-mean regime n*p < 10 with host-precomputed constants q^n, s = p/q, a = (n+1)s:
