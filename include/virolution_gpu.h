@@ -235,6 +235,31 @@ int vl_migrants_import_device(vl_sim *target, const uint32_t *len_device, const 
  * one synchronisation for all of them (the per-target parts of one origin, src/runner.rs:404-416). */
 int vl_subsample_populations(vl_sim *sim, const double *factors, uint32_t n, vl_pop **out);
 
+/* ---- peer exchange: the transmission block fused with its transport --------------------------------------------
+ * One compartment per process/GPU of one NVLink domain (src/runner.rs:401-416 with compartment c on rank c).  Every
+ * rank owns a receive buffer that the other ranks map through CUDA IPC; per generation an origin writes its migrants
+ * (length, raw fitness, entries) straight into the targets' buffers and raises a flag, the target waits on its flags
+ * on the device and builds its new population.  Nothing is synchronised with or read back by the host.
+ * `transfer` is row-major world x world, row = target, col = origin, fixed for the lifetime of the exchange; all ranks
+ * must pass the same matrix, max_population, providers and words_per_migrant (the capacity of a block's entry area is
+ * words_per_migrant x its migrant capacity; 0 = 64). */
+typedef struct vl_exchange vl_exchange;
+int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const double *transfer, uint64_t words_per_migrant,
+                       vl_exchange **out, void *ipc_handle_out /* 64 bytes: cudaIpcMemHandle_t of the receive buffer */);
+int vl_exchange_recv_buffer(vl_exchange *ex, void **ptr, uint64_t *bytes);
+/* ipc_handles: world x 64 bytes gathered from all ranks (own slot ignored).  local_ptrs (optional): a non-NULL entry
+ * is that rank's receive buffer in THIS process (vl_exchange_recv_buffer), used instead of its handle. */
+int vl_exchange_connect(vl_exchange *ex, const void *ipc_handles, void *const *local_ptrs);
+/* increment_generation .. replicate_infectants, then the transmission block, for this rank (runner.rs:382-422):
+ * push = the generation up to the offspring map, the part of every target, the writes into the targets' buffers;
+ * pull = device-side wait for every origin's block, import, set_population.  step = push + pull.  Ranks that share a
+ * process push all before they pull any (a stream waiting on the device must not depend on work of the same process
+ * that has not been submitted yet). */
+int vl_exchange_push(vl_exchange *ex);
+int vl_exchange_pull(vl_exchange *ex);
+int vl_exchange_step(vl_exchange *ex);
+int vl_exchange_destroy(vl_exchange *ex);
+
 /* ---- measurement hooks (bench.py): CUDA events on the handle's own stream ------------------ */
 int vl_timer_start(vl_sim *sim);
 int vl_timer_stop(vl_sim *sim, double *ms_out);            /* synchronises; device time since vl_timer_start */

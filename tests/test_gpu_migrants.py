@@ -130,3 +130,38 @@ def test_many_parts_in_one_pass_follow_the_sampling_law():
     assert abs(counts[heavy].sum() - e.sum()) / np.sqrt(e.sum()) < 5.5
     assert not np.array_equal(drawn[bounds[3]:bounds[4]], drawn[bounds[4]:bounds[5]]), "equal-sized parts must be different draws"
     g.close()
+
+
+def test_peer_exchange_equals_in_process_transmission():
+    """vl_exchange_step (migrants written by the kernels into the peer's receive buffer, flags waited on by the device;
+    both "ranks" live in this process here and hand each other raw pointers instead of IPC handles) against vl_step's
+    parallel-build rule (src/runner.rs:401-416) on the same seeds: the same populations generation after generation."""
+    from test_gpu_stochastic import big_singlehost, population_signature
+    from virolution_b200.simulation import PeerExchangeHandle, step
+    c = big_singlehost(n=120000, mu=1e-4, seed=55)
+    T = np.array([[0.8, 0.3], [0.2, 0.7]])
+    a = [helpers.make_gpu(c, compartment_id=k) for k in range(2)]  # reference arm: vl_step
+    b = [helpers.make_gpu(c, compartment_id=k) for k in range(2)]  # peer exchange
+    ex = [PeerExchangeHandle(b[k], k, 2, T, words_per_migrant=32) for k in range(2)]
+    bufs = [e.recv_buffer() for e in ex]
+    for k in range(2):
+        ex[k].connect(None, [bufs[t] if t != k else 0 for t in range(2)])
+    for g in range(4):
+        step(a, T, rule=0)
+        for e in ex:      # ranks of one process push all before they pull any
+            e.push()
+        for s in b:
+            s.synchronize()
+        for e in ex:
+            e.pull()
+        for s in b:
+            s.synchronize()
+        for k in range(2):
+            assert a[k].population_len() == b[k].population_len(), (g, k)
+            assert population_signature(a[k]) == population_signature(b[k]), f"generation {g}, compartment {k}"
+            helpers.assert_f64_equal(a[k].get_raw_fitness(), b[k].get_raw_fitness(), "raw fitness")
+    assert a[0].population_len() == int(0.8 * 120000) + int(0.3 * 120000)
+    for e in ex:
+        e.close()
+    for s in a + b:
+        s.close()

@@ -19,6 +19,7 @@
 
 #include "vl_kernels.cuh"
 #include "vl_migrate.cuh"
+#include "vl_exchange.cuh"
 
 using namespace vl;
 
@@ -183,11 +184,18 @@ static int check_device_error(vl_sim *sim) {
     if (e & DE_SAME_BASE) return fail(sim, VL_ERR_REFERENCE_PANIC, "assert_ne!(from, to) in create_descendant (src/core/haplotype.rs:250)");
     if (e & DE_OFFSPRING_RANGE) return fail(sim, VL_ERR_IMPLEMENTATION, "offspring count does not fit 32 bits");
     if (e & DE_REPLAY) return fail(sim, VL_ERR_ARGUMENT, "malformed replay log or index out of range");
+    if (e & DE_EXCHANGE_TIMEOUT) return fail(sim, VL_ERR_CUDA, "migrant exchange timed out: a peer's block did not arrive");
     if (e & DE_TILE_OVERFLOW) return fail(sim, VL_ERR_IMPLEMENTATION, "host tile overflow (> 13 sigma under uniform infection): rerun with VL_FLAG_GENERAL_REPLICATE");
     if (e & DE_BUCKET_OVERFLOW) return fail(sim, VL_ERR_IMPLEMENTATION, "host bucket overflow (12 sigma event): rerun with VL_FLAG_NO_BUCKETS");
     return fail(sim, VL_ERR_IMPLEMENTATION, "unknown device error 0x%x", e);
 }
 
+// stream-ordered clear of a (4-byte aligned) device range by a kernel
+static inline void zero_device(vl_sim *sim, void *p, uint64_t bytes) {
+    const uint64_t n = (bytes + 3) / 4;
+    const unsigned g = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (n + TPB - 1) / TPB), (uint64_t)sim->n_sms * 8);
+    k_zero_words<<<g, TPB, 0, sim->stream>>>((uint32_t *)p, n);
+}
 static int zero_scan_work(vl_sim *sim, uint64_t n_items_bound) {
     uint64_t words = 2 + (n_items_bound + SCAN_TILE - 1) / SCAN_TILE;
     if (words > sim->scan_work_words) {
@@ -197,7 +205,7 @@ static int zero_scan_work(vl_sim *sim, uint64_t n_items_bound) {
         sim->scan_work_words = words + words / 2;
         CU(sim, cudaMalloc((void **)&sim->scan_work, sim->scan_work_words * 8));
     }
-    CU(sim, cudaMemsetAsync(sim->scan_work, 0, words * 8, sim->stream));
+    zero_device(sim, sim->scan_work, words * 8);
     return VL_OK;
 }
 template <typename OutT, bool EXCL>
@@ -219,16 +227,6 @@ static void free_population_buffers(vl_sim *sim) {
 }
 // tiles the plan/resample arrays can describe: position tiles of the largest population, or host tiles of as many hosts
 static inline uint64_t tile_capacity(uint64_t cap_inf) { return (cap_inf + HT_MIN_HOSTS - 1) / HT_MIN_HOSTS + 2; }
-// hosts per tile of the fused replicate kernel: expected records per tile 8 standard deviations below what a CTA
-// stages (RESAMPLE_TILE), for at most n infectants spread uniformly over H hosts; 0 = do not use host tiles
-static inline uint32_t host_tile_size(uint64_t n, uint64_t H) {
-    if (H == 0) return 0;
-    const double mean_max = 1700.0;  // 1700 + 8 * sqrt(1700) < 2048
-    double ht = floor(mean_max * (double)H / (double)std::max<uint64_t>(n, 1));
-    if (ht > (double)HT_MAX_HOSTS) ht = (double)HT_MAX_HOSTS;
-    if (ht > (double)H) ht = (double)H;
-    return ht < (double)HT_MIN_HOSTS ? 0u : (uint32_t)ht;
-}
 static bool buckets_possible(const vl_sim *sim) {
     const DevState &h = sim->h;
     return h.fast_infect && h.H >= 4 * (uint64_t)BUCKET_HOSTS && h.n_buckets <= (uint32_t)MAX_BUCKETS && !(sim->flags & VL_FLAG_NO_BUCKETS);
@@ -616,13 +614,13 @@ VL_API int vl_set_population_wildtype(vl_sim *sim, uint64_t n) {
 
 // ---------------------------------------------------------------------------------------------- phases
 static int zero_field32(vl_sim *sim, size_t off) {
-    CU(sim, cudaMemsetAsync((char *)sim->d + off, 0, 4, sim->stream));
+    zero_device(sim, (char *)sim->d + off, 4);
     return VL_OK;
 }
 // n_medium, n_heavy, fused_failed (adjacent in DevState)
 static int zero_replicate_counters(vl_sim *sim) {
     static_assert(FIELD_OFF(n_heavy) == FIELD_OFF(n_medium) + 4 && FIELD_OFF(fused_failed) == FIELD_OFF(n_medium) + 8, "counters must be adjacent");
-    CU(sim, cudaMemsetAsync((char *)sim->d + FIELD_OFF(n_medium), 0, 12, sim->stream));
+    zero_device(sim, (char *)sim->d + FIELD_OFF(n_medium), 12);
     return VL_OK;
 }
 // descending infectant order inside every slice (the reference's back-fill order); part of k_host_fitness in
@@ -671,7 +669,7 @@ static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
     sim->bucket_pending = false;
     sim->uniform_infection = fast && !sim->has_rp_inf;
     if (!replay && buckets_possible(sim) && h.cap_tmp >= (uint64_t)h.n_buckets * bucket_stride(sim->n_bound, h.H)) {
-        CU(sim, cudaMemsetAsync(h.bucket_fill, 0, (MAX_BUCKETS + 1) * 4, sim->stream));
+        zero_device(sim, h.bucket_fill, (MAX_BUCKETS + 1) * 4);
         const int btpb = (sim->experiment & 2) ? 512 : 1024;
         const unsigned g = (unsigned)std::max<uint64_t>(1, (sim->n_bound + btpb * BUCKET_ITEMS - 1) / (btpb * BUCKET_ITEMS));  // one chunk per CTA
         if (btpb == 1024) {
@@ -691,7 +689,7 @@ static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
         if (h.host_recombination_rate > 0.0) TRY(ensure_ordered_slices(sim));
         return VL_OK;
     }
-    CU(sim, cudaMemsetAsync(sim->count, 0, (h.H + 2) * 4, sim->stream));
+    zero_device(sim, sim->count, (h.H + 2) * 4);
     const unsigned g = grid_for(sim, (sim->n_bound + INFECT_ITEMS - 1) / INFECT_ITEMS);
     const int64_t *rp = sim->has_rp_inf ? sim->rp_inf : nullptr;
     if (fuse && fast) LAUNCH(sim, (k_infect<true, true>), g, TPB, 0, sim->d, sim->count, (const int64_t *)nullptr);
@@ -755,8 +753,8 @@ static int enqueue_replicate(vl_sim *sim, int store_lambda = 1) {
     if (fused) {
         const uint32_t per = n_host_tiles >= (uint64_t)sim->n_sms * 12 ? 2u : 1u;  // consecutive tiles per CTA (prefetch of the second)
         const unsigned g = (unsigned)((n_host_tiles + per - 1) / per);
-        if (small) LAUNCH(sim, k_replicate_fused<true>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht, per);
-        else LAUNCH(sim, k_replicate_fused<false>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, ht, per);
+        if (small) LAUNCH(sim, k_replicate_fused<true>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, per);
+        else LAUNCH(sim, k_replicate_fused<false>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, per);
         guarded = 1;
     }
     if (!fused_only) {
@@ -798,7 +796,7 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
     }
     const uint64_t nt_bound = tile_bound(sim);
     const uint32_t smem_tiles = (uint32_t)std::min<uint64_t>(nt_bound, sim->plan_smem_tiles);
-    CU(sim, cudaMemsetAsync((char *)sim->d + FIELD_OFF(plan_sync), 0, 8 + sizeof(((DevState *)0)->plan_acc), sim->stream));
+    zero_device(sim, (char *)sim->d + FIELD_OFF(plan_sync), 8 + sizeof(((DevState *)0)->plan_acc));
     // a handful of co-resident CTAs: each draws for its slice of tiles, a counter in DevState is the grid barrier
     const unsigned ctas = (unsigned)std::min<uint64_t>(PLAN_CTAS, std::max<uint64_t>(1, nt_bound / 256));
     LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, pa, smem_tiles);
@@ -1320,6 +1318,233 @@ VL_API int vl_run(vl_sim *sim, uint64_t n_generations) {
     for (uint64_t g = 0; g < n_generations; g++) TRY(enqueue_generation(sim));
     CU(sim, cudaGetLastError());
     return VL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- peer exchange
+// One compartment per process/GPU; migrants are written by the origin straight into the target's receive buffer
+// (vl_exchange.cuh).  Create -> exchange the 64-byte IPC handles with whatever the caller has (torch.distributed in
+// virolution_b200/distributed.py) -> connect -> vl_exchange_step per generation.
+struct vl_exchange {
+    vl_sim *sim = nullptr;
+    uint32_t rank = 0, world = 0;
+    uint64_t wpm = 0, seq = 0;
+    std::vector<double> T;
+    uint8_t *recv = nullptr;       // my receive buffer (IPC-exported)
+    uint64_t recv_bytes = 0;
+    void *peer[EX_MAX_WORLD] = {nullptr};
+    bool peer_ipc[EX_MAX_WORLD] = {false};
+    bool connected = false, pushed = false;
+    ExArgs args;
+    ExScratch *scratch = nullptr;
+    uint32_t *part_ids[EX_MAX_WORLD] = {nullptr};
+    uint32_t *words_out = nullptr, *words_in = nullptr, *recs_in = nullptr, *rec_off = nullptr;
+    uint64_t *woff = nullptr, *word_off = nullptr;
+    uint64_t m_out_bound = 0, m_in_bound = 0;
+};
+struct ExLayout {
+    uint64_t flag_off[2][EX_MAX_WORLD], header_off[2][EX_MAX_WORLD], len_off[2][EX_MAX_WORLD], raw_off[2][EX_MAX_WORLD], ent_off[2][EX_MAX_WORLD];
+    uint64_t m_cap[EX_MAX_WORLD], w_cap[EX_MAX_WORLD];
+    uint64_t bytes;
+};
+// layout of rank `target`'s receive buffer; every rank computes the same layout for every rank
+static ExLayout ex_layout(uint32_t world, uint32_t target, const double *T, uint64_t max_pop, uint32_t P, uint64_t wpm) {
+    ExLayout L;
+    memset(&L, 0, sizeof L);
+    uint64_t off = 0;
+    for (int par = 0; par < 2; par++)
+        for (uint32_t o = 0; o < world; o++) { L.flag_off[par][o] = off; off += 8; }
+    off = (off + 255) & ~255ull;
+    for (uint32_t o = 0; o < world; o++) {
+        double m = floor(T[(size_t)target * world + o] * (double)max_pop) + 1.0;
+        if (!(m >= 1.0)) m = 1.0;
+        L.m_cap[o] = o == target ? 0 : (uint64_t)m;
+        L.w_cap[o] = L.m_cap[o] * wpm;
+    }
+    for (int par = 0; par < 2; par++)
+        for (uint32_t o = 0; o < world; o++) {
+            if (o == target) continue;
+            L.header_off[par][o] = off; off += EX_HEADER_BYTES;
+            L.len_off[par][o] = off; off = (off + L.m_cap[o] * 4 + 255) & ~255ull;
+            L.raw_off[par][o] = off; off = (off + L.m_cap[o] * P * 8 + 255) & ~255ull;
+            L.ent_off[par][o] = off; off = (off + L.w_cap[o] * 4 + 255) & ~255ull;
+        }
+    L.bytes = off;
+    return L;
+}
+static void ex_block(ExBlock &b, uint8_t *base, const ExLayout &L, uint32_t origin) {
+    for (int par = 0; par < 2; par++) {
+        b.header[par] = (uint64_t *)(base + L.header_off[par][origin]);
+        b.len[par] = (uint32_t *)(base + L.len_off[par][origin]);
+        b.raw[par] = (double *)(base + L.raw_off[par][origin]);
+        b.entries[par] = (uint32_t *)(base + L.ent_off[par][origin]);
+        b.flag[par] = (unsigned long long *)(base + L.flag_off[par][origin]);
+    }
+    b.m_cap = L.m_cap[origin];
+    b.w_cap = L.w_cap[origin];
+}
+static void ex_free(vl_exchange *ex) {
+    if (!ex) return;
+    vl_sim *sim = ex->sim;
+    cudaSetDevice(sim->device);
+    cudaStreamSynchronize(sim->stream);
+    for (uint32_t t = 0; t < ex->world; t++) {
+        if (ex->peer[t] && ex->peer_ipc[t]) cudaIpcCloseMemHandle(ex->peer[t]);
+        if (ex->part_ids[t]) cudaFree(ex->part_ids[t]);
+    }
+    void *bufs[] = {ex->recv, ex->scratch, ex->words_out, ex->words_in, ex->recs_in, ex->rec_off, ex->woff, ex->word_off};
+    for (void *b : bufs) if (b) cudaFree(b);
+    delete ex;
+}
+VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const double *transfer, uint64_t words_per_migrant,
+                              vl_exchange **out, void *ipc_handle_out) {
+    ENTER(sim);
+    if (!out || !transfer || !ipc_handle_out) return fail(sim, VL_ERR_ARGUMENT, "null argument");
+    if (world < 2 || world > EX_MAX_WORLD || rank >= world) return fail(sim, VL_ERR_ARGUMENT, "world must be in [2, %u] and rank below it", EX_MAX_WORLD);
+    vl_exchange *ex = new vl_exchange();
+    ex->sim = sim; ex->rank = rank; ex->world = world;
+    ex->wpm = words_per_migrant ? words_per_migrant : 64;
+    ex->T.assign(transfer, transfer + (size_t)world * world);
+    const DevState &h = sim->h;
+    const ExLayout L = ex_layout(world, rank, ex->T.data(), h.max_population, h.n_providers, ex->wpm);
+    ex->recv_bytes = L.bytes;
+#define XCU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ex_free(ex); return fail(sim, VL_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+    XCU(cudaMalloc((void **)&ex->recv, L.bytes));
+    XCU(cudaMemset(ex->recv, 0, L.bytes));
+    XCU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)ipc_handle_out, ex->recv));
+    XCU(cudaMalloc((void **)&ex->scratch, sizeof(ExScratch)));
+    XCU(cudaMemset(ex->scratch, 0, sizeof(ExScratch)));
+    memset(&ex->args, 0, sizeof ex->args);
+    ex->args.world = world; ex->args.rank = rank; ex->args.n_providers = h.n_providers;
+    for (uint32_t o = 0; o < world; o++) {
+        if (o == rank) continue;
+        ex_block(ex->args.in[o], ex->recv, L, o);
+        ex->m_in_bound += L.m_cap[o];
+    }
+    for (uint32_t t = 0; t < world; t++) {  // one id buffer per target part (my column of T)
+        double m = floor(ex->T[(size_t)t * world + rank] * (double)h.max_population) + 2.0;
+        if (!(m >= 2.0)) m = 2.0;
+        XCU(cudaMalloc((void **)&ex->part_ids[t], (uint64_t)m * 4));
+        ex->args.part[t] = ex->part_ids[t];
+        if (t != rank) ex->m_out_bound += (uint64_t)m;
+    }
+    XCU(cudaMalloc((void **)&ex->words_out, (ex->m_out_bound + 2) * 4));
+    XCU(cudaMalloc((void **)&ex->woff, (ex->m_out_bound + 2) * 8));
+    XCU(cudaMalloc((void **)&ex->words_in, (ex->m_in_bound + 2) * 4));
+    XCU(cudaMalloc((void **)&ex->recs_in, (ex->m_in_bound + 2) * 4));
+    XCU(cudaMalloc((void **)&ex->rec_off, (ex->m_in_bound + 2) * 4));
+    XCU(cudaMalloc((void **)&ex->word_off, (ex->m_in_bound + 2) * 8));
+#undef XCU
+    *out = ex;
+    return VL_OK;
+}
+VL_API int vl_exchange_recv_buffer(vl_exchange *ex, void **ptr, uint64_t *bytes) {
+    if (!ex || !ptr) return fail(nullptr, VL_ERR_ARGUMENT, "null argument");
+    *ptr = ex->recv;
+    if (bytes) *bytes = ex->recv_bytes;
+    return VL_OK;
+}
+// ipc_handles: world x 64 bytes (cudaIpcMemHandle_t of every rank's receive buffer, own slot ignored); local_ptrs: optional,
+// a non-null entry is used as that rank's receive buffer directly (ranks living in this process)
+VL_API int vl_exchange_connect(vl_exchange *ex, const void *ipc_handles, void *const *local_ptrs) {
+    if (!ex) return fail(nullptr, VL_ERR_ARGUMENT, "null exchange");
+    vl_sim *sim = ex->sim;
+    ENTER(sim);
+    const DevState &h = sim->h;
+    for (uint32_t t = 0; t < ex->world; t++) {
+        if (t == ex->rank) continue;
+        if (local_ptrs && local_ptrs[t]) {
+            ex->peer[t] = local_ptrs[t];
+        } else {
+            if (!ipc_handles) return fail(sim, VL_ERR_ARGUMENT, "no handle for rank %u", t);
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char *)ipc_handles + (size_t)t * sizeof(cudaIpcMemHandle_t), sizeof hd);
+            CU(sim, cudaIpcOpenMemHandle(&ex->peer[t], hd, cudaIpcMemLazyEnablePeerAccess));
+            ex->peer_ipc[t] = true;
+        }
+        const ExLayout L = ex_layout(ex->world, t, ex->T.data(), h.max_population, h.n_providers, ex->wpm);
+        ex_block(ex->args.out[t], (uint8_t *)ex->peer[t], L, ex->rank);
+    }
+    ex->connected = true;
+    return VL_OK;
+}
+VL_API int vl_exchange_destroy(vl_exchange *ex) {
+    if (!ex) return VL_OK;
+    std::lock_guard<std::recursive_mutex> lock_(ex->sim->mu);
+    ex_free(ex);
+    return VL_OK;
+}
+// first half: the generation up to the offspring map, the parts of every target, and the push into the targets' buffers
+VL_API int vl_exchange_push(vl_exchange *ex) {
+    if (!ex) return fail(nullptr, VL_ERR_ARGUMENT, "null exchange");
+    vl_sim *sim = ex->sim;
+    ENTER(sim);
+    if (!ex->connected) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_connect has not run");
+    if (ex->pushed) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_pull must follow vl_exchange_push");
+    const uint32_t W = ex->world, r = ex->rank;
+    TRY(enqueue_generation_front(sim));
+    double factors[EX_MAX_WORLD];
+    uint32_t *dsts[EX_MAX_WORLD];
+    for (uint32_t t = 0; t < W; t++) { factors[t] = ex->T[(size_t)t * W + r]; dsts[t] = ex->part_ids[t]; }
+    TRY(launch_plan_resample(sim, W, factors, 0, nullptr, 0, dsts, nullptr, 0));
+    ex->seq += 1;
+    ExArgs a = ex->args;
+    a.seq = ex->seq;
+    a.parity = (uint32_t)(ex->seq & 1);
+    ExScratch *sc = ex->scratch;
+    const uint64_t *n_out = (const uint64_t *)((const char *)sc + offsetof(ExScratch, n_out));
+    // ---- push
+    LAUNCH(sim, k_ex_out_starts, 1, 1, 0, sim->d, a, sc);
+    LAUNCH(sim, k_ex_lens, grid_for(sim, ex->m_out_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, ex->words_out);
+    TRY((launch_scan<uint64_t, true>(sim, ex->words_out, ex->woff, n_out, 0, ex->m_out_bound, nullptr, 1, nullptr)));
+    LAUNCH(sim, k_ex_copy, grid_for(sim, ex->m_out_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, (const uint64_t *)ex->woff);
+    LAUNCH(sim, k_ex_publish, 1, 32, 0, sim->d, a, (const ExScratch *)sc, (const uint64_t *)ex->woff);
+    ex->pushed = true;
+    CU(sim, cudaGetLastError());
+    return VL_OK;
+}
+// second half: wait (on the device) for every origin's block of this generation, import, install the new population
+VL_API int vl_exchange_pull(vl_exchange *ex) {
+    if (!ex) return fail(nullptr, VL_ERR_ARGUMENT, "null exchange");
+    vl_sim *sim = ex->sim;
+    ENTER(sim);
+    if (!ex->pushed) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_push has not run for this generation");
+    ex->pushed = false;
+    const uint32_t W = ex->world;
+    ExArgs a = ex->args;
+    a.seq = ex->seq;
+    a.parity = (uint32_t)(ex->seq & 1);
+    ExScratch *sc = ex->scratch;
+    const uint64_t *n_imp = (const uint64_t *)((const char *)sc + offsetof(ExScratch, n_imp));
+    uint64_t *totals = (uint64_t *)((char *)sc + offsetof(ExScratch, totals));
+    LAUNCH(sim, k_ex_wait, 1, 32, 0, sim->d, a, 20ull * 1000000000ull);
+    LAUNCH(sim, k_ex_in_starts, 1, 1, 0, sim->d, a, sc);
+    LAUNCH(sim, k_ex_in_words, grid_for(sim, ex->m_in_bound), TPB, 0, a, (const ExScratch *)sc, ex->words_in, ex->recs_in);
+    TRY((launch_scan<uint32_t, true>(sim, ex->recs_in, ex->rec_off, n_imp, 0, ex->m_in_bound, totals + 0, 0, nullptr)));
+    TRY((launch_scan<uint64_t, true>(sim, ex->words_in, ex->word_off, n_imp, 0, ex->m_in_bound, totals + 1, 1, nullptr)));
+    LAUNCH(sim, k_ex_reserve, 1, 1, 0, sim->d, sc);
+    LAUNCH(sim, k_ex_import, grid_for(sim, ex->m_in_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, (const uint32_t *)ex->rec_off, (const uint64_t *)ex->word_off);
+    LAUNCH(sim, k_ex_own, grid_for(sim, sim->h.max_population), TPB, 0, sim->d, a, (const ExScratch *)sc);
+    swap_population(sim);
+    sim->n_valid = false;
+    {   // upper bound of the new population: every origin sends at most its block capacity, the own part its cap
+        uint64_t bound = 0;
+        for (uint32_t o = 0; o < W; o++) {
+            double m = floor(ex->T[(size_t)ex->rank * W + o] * (double)sim->h.max_population) + 1.0;
+            bound += (uint64_t)(m >= 1.0 ? m : 1.0);
+        }
+        sim->n_bound = std::min<uint64_t>(sim->h.cap_inf, bound);
+    }
+    sim->csr_valid = false;
+    sim->slices_ordered = false;
+    sim->layout_valid = false;
+    CU(sim, cudaGetLastError());
+    return maybe_gc(sim);
+}
+// one generation of Runner::run's loop body (src/runner.rs:382-422) for this rank's compartment, transmission included;
+// everything is enqueued, nothing is read back
+VL_API int vl_exchange_step(vl_exchange *ex) {
+    TRY(vl_exchange_push(ex));
+    return vl_exchange_pull(ex);
 }
 
 static inline uint64_t f64_as_usize_host(double x) {

@@ -1186,7 +1186,7 @@ constexpr int REPL_TPB = 512;
 constexpr int REPL_PER = RESAMPLE_TILE / REPL_TPB;
 template <bool SMALL_ONLY>
 __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda,
-                                                                 int fail_is_error, uint32_t ht, uint32_t tiles_per_cta) {
+                                                                 int fail_is_error, uint32_t tiles_per_cta) {
     __shared__ uint32_t s_off[HT_MAX_HOSTS + 1];
     __shared__ uint32_t s_head[RESAMPLE_TILE / 32 + 2];
     __shared__ double s_f[RESAMPLE_TILE];
@@ -1195,6 +1195,11 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
     __shared__ double s_rcp[POISSON_RCP];
     poisson_rcp_init(s_rcp);
     const uint64_t H = st->H;
+    const uint32_t ht = host_tile_size(st->n, H);  // from the state, not from the launch: see host_tile_size
+    if (ht == 0) {  // more infectants per host than whole-host tiles can stage
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->fused_failed = 1u; if (fail_is_error) raise(st, DE_TILE_OVERFLOW); }
+        return;
+    }
     const uint64_t nt = (H + ht - 1) / ht;
     const uint32_t *__restrict__ offsets = st->offsets;
     uint2 *rec = st->rec;
@@ -1831,6 +1836,12 @@ __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
 }
 
 // ------------------------------------------------------------------------------------------ small helpers
+// clears n 32-bit words.  Used instead of cudaMemsetAsync on the enqueue paths: a device memset is one of the commands
+// that can implicitly serialise streams of one process, and compartments of one process must be able to run side by
+// side (one waits on the device for the other's migrants).
+__global__ void __launch_bounds__(TPB) k_zero_words(uint32_t *p, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
 __global__ void __launch_bounds__(TPB) k_fill_u32(uint32_t *p, uint64_t n, uint32_t v) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }

@@ -50,7 +50,8 @@ enum DevError : uint32_t {
     DE_OFFSPRING_RANGE = 64u,   // offspring count does not fit u32
     DE_REPLAY = 128u,           // malformed replay log
     DE_BUCKET_OVERFLOW = 256u,  // a host bucket received 12 standard deviations more records than its mean
-    DE_TILE_OVERFLOW = 512u     // a host tile holds more records than a CTA stages (uniform infection: > 13 sd)
+    DE_TILE_OVERFLOW = 512u,    // a host tile holds more records than a CTA stages (uniform infection: > 8 sd)
+    DE_EXCHANGE_TIMEOUT = 1024u // a peer's migrants did not arrive in time (vl_exchange_step)
 };
 constexpr uint32_t BUCKET_SHIFT = 13;
 constexpr uint32_t BUCKET_HOSTS = 1u << BUCKET_SHIFT;  // hosts per bucket: their histogram lives in shared memory
@@ -175,6 +176,19 @@ struct DevState {
     uint64_t kernels_launched;  // maintained by the host, mirrored here for export
     uint64_t dbg[8];            // %globaltimer stamps of the plan kernel's phases (profiling aid)
 };
+
+// hosts per tile of the fused replicate kernel: expected records per tile 8 standard deviations below what a CTA
+// stages (RESAMPLE_TILE) when n infectants are spread uniformly over H hosts; 0 = host tiles cannot be used.
+// The kernel evaluates it on the device from the population size, so the tiling (and with it the resampling streams)
+// is a function of the simulation state alone; the host evaluates it on an upper bound of n to size grids.
+__host__ __device__ inline uint32_t host_tile_size(uint64_t n, uint64_t H) {
+    if (H == 0) return 0;
+    const double mean_max = 1700.0;  // 1700 + 8 * sqrt(1700) < 2048
+    double ht = floor(mean_max * (double)H / (double)(n ? n : 1));
+    if (ht > (double)HT_MAX_HOSTS) ht = (double)HT_MAX_HOSTS;
+    if (ht > (double)H) ht = (double)H;
+    return ht < (double)HT_MIN_HOSTS ? 0u : (uint32_t)ht;
+}
 
 // ---- resample tiles: a tile is what one CTA stages in shared memory, either RESAMPLE_TILE consecutive CSR positions
 // or the records of DevState::host_tiles consecutive hosts (what the fused replicate kernel produces: whole hosts per CTA)

@@ -178,3 +178,32 @@ class CompartmentExchange:
         if self.trace is not None:
             self.trace["begin_generation(enqueue)"] = self.trace.get("begin_generation(enqueue)", 0.0) + time.perf_counter() - t0
         self.transmit()
+
+
+class PeerExchange:
+    """The same loop body with the transport fused into the kernels: every origin writes its migrants straight into the
+    targets' device memory over NVLink (CUDA IPC mappings), sizes stay on the device, the host only enqueues
+    (vl_exchange_* in include/virolution_gpu.h, kernels in csrc/vl_exchange.cuh).  `torch.distributed` is used once, to
+    hand the 64-byte IPC handles around."""
+
+    def __init__(self, sim, rank: int, world: int, transfer: Optional[np.ndarray] = None, migration: float = 0.1,
+                 words_per_migrant: int = 0, group=None):
+        from .simulation import PeerExchangeHandle
+        self.sim, self.rank, self.world = sim, rank, world
+        self.T = np.asarray(migration_matrix(world, migration) if transfer is None else transfer, dtype=np.float64)
+        self.handle = PeerExchangeHandle(sim, rank, world, self.T, words_per_migrant)
+        dev = torch.device("cuda", sim.device)
+        mine = torch.from_numpy(self.handle.ipc_handle.copy()).to(dev)
+        allh = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        self.handle.connect(allh.cpu().numpy().reshape(world, -1))
+        dist.barrier(group=group)  # every rank has mapped every buffer before anybody writes
+        self.trace = None
+
+    def step(self):
+        self.handle.step()
+
+    def close(self):
+        self.sim.synchronize()
+        dist.barrier()
+        self.handle.close()

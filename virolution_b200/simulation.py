@@ -69,6 +69,13 @@ SIGNATURES = {
     "vl_migrants_export_device": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32, C.POINTER(vl_migrant_image), u64p, u64p]),
     "vl_migrants_import_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
     "vl_subsample_populations": (C.c_int, [_vp, f64p, C.c_uint32, C.POINTER(_vp)]),
+    "vl_exchange_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, f64p, C.c_uint64, C.POINTER(_vp), _vp]),
+    "vl_exchange_recv_buffer": (C.c_int, [_vp, C.POINTER(_vp), u64p]),
+    "vl_exchange_connect": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "vl_exchange_step": (C.c_int, [_vp]),
+    "vl_exchange_push": (C.c_int, [_vp]),
+    "vl_exchange_pull": (C.c_int, [_vp]),
+    "vl_exchange_destroy": (C.c_int, [_vp]),
     "vl_timer_start": (C.c_int, [_vp]),
     "vl_timer_stop": (C.c_int, [_vp, f64p]),
     "vl_profile": (C.c_int, [_vp, C.c_int]),
@@ -431,6 +438,55 @@ class GpuSimulation:
         pop = _vp()
         self._check(self.lib.vl_pop_unpack_device(self.ptr, _vp(image_ptr), nbytes, C.byref(pop)))
         return GpuPopulation(pop, self)
+
+
+class PeerExchangeHandle:
+    """vl_exchange of one rank: receive buffer + peer mappings + the per-generation enqueue (include/virolution_gpu.h)."""
+    IPC_BYTES = 64
+
+    def __init__(self, sim: GpuSimulation, rank: int, world: int, transfer, words_per_migrant: int = 0):
+        self.sim, self.rank, self.world = sim, rank, world
+        T = np.ascontiguousarray(transfer, dtype=np.float64)
+        if T.shape != (world, world):
+            raise ValueError(f"transfer matrix is {T.shape}, expected {(world, world)}")
+        self.ipc_handle = np.zeros(self.IPC_BYTES, dtype=np.uint8)
+        ptr = _vp()
+        sim._check(sim.lib.vl_exchange_create(sim.ptr, rank, world, _p(T, C.c_double), words_per_migrant, C.byref(ptr),
+                                              self.ipc_handle.ctypes.data_as(_vp)))
+        self.ptr = ptr
+
+    def recv_buffer(self) -> int:
+        out, nbytes = _vp(), C.c_uint64()
+        self.sim._check(self.sim.lib.vl_exchange_recv_buffer(self.ptr, C.byref(out), C.byref(nbytes)))
+        return int(out.value)
+
+    def connect(self, ipc_handles: Optional[np.ndarray] = None, local_ptrs: Optional[Sequence[int]] = None):
+        """ipc_handles: (world, 64) uint8 gathered from all ranks; local_ptrs: receive buffers of ranks in this process."""
+        h = None if ipc_handles is None else np.ascontiguousarray(ipc_handles, dtype=np.uint8)
+        lp = None
+        if local_ptrs is not None:
+            lp = (_vp * self.world)(*[_vp(p) if p else _vp() for p in local_ptrs])
+        self.sim._check(self.sim.lib.vl_exchange_connect(self.ptr, None if h is None else h.ctypes.data_as(_vp), lp))
+
+    def step(self):
+        self.sim._check(self.sim.lib.vl_exchange_step(self.ptr))
+
+    def push(self):
+        self.sim._check(self.sim.lib.vl_exchange_push(self.ptr))
+
+    def pull(self):
+        self.sim._check(self.sim.lib.vl_exchange_pull(self.ptr))
+
+    def close(self):
+        if getattr(self, "ptr", None) and self.sim.ptr:
+            self.sim.lib.vl_exchange_destroy(self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def step(sims: Sequence[GpuSimulation], transfer: Optional[np.ndarray] = None, rule: int = 0):
