@@ -1339,6 +1339,7 @@ struct vl_exchange {
     uint32_t *part_ids[EX_MAX_WORLD] = {nullptr};
     uint32_t *words_out = nullptr, *words_in = nullptr, *recs_in = nullptr, *rec_off = nullptr;
     uint64_t *woff = nullptr, *word_off = nullptr;
+    uint32_t *stage = nullptr;  // leaving entries in concatenation order, before they are streamed to the targets
     uint64_t m_out_bound = 0, m_in_bound = 0;
 };
 struct ExLayout {
@@ -1391,7 +1392,7 @@ static void ex_free(vl_exchange *ex) {
         if (ex->peer[t] && ex->peer_ipc[t]) cudaIpcCloseMemHandle(ex->peer[t]);
         if (ex->part_ids[t]) cudaFree(ex->part_ids[t]);
     }
-    void *bufs[] = {ex->recv, ex->scratch, ex->words_out, ex->words_in, ex->recs_in, ex->rec_off, ex->woff, ex->word_off};
+    void *bufs[] = {ex->recv, ex->scratch, ex->words_out, ex->words_in, ex->recs_in, ex->rec_off, ex->woff, ex->word_off, ex->stage};
     for (void *b : bufs) if (b) cudaFree(b);
     delete ex;
 }
@@ -1429,6 +1430,7 @@ VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const 
     }
     XCU(cudaMalloc((void **)&ex->words_out, (ex->m_out_bound + 2) * 4));
     XCU(cudaMalloc((void **)&ex->woff, (ex->m_out_bound + 2) * 8));
+    XCU(cudaMalloc((void **)&ex->stage, (ex->m_out_bound * ex->wpm + 64) * 4));
     XCU(cudaMalloc((void **)&ex->words_in, (ex->m_in_bound + 2) * 4));
     XCU(cudaMalloc((void **)&ex->recs_in, (ex->m_in_bound + 2) * 4));
     XCU(cudaMalloc((void **)&ex->rec_off, (ex->m_in_bound + 2) * 4));
@@ -1496,7 +1498,9 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
     LAUNCH(sim, k_ex_out_starts, 1, 1, 0, sim->d, a, sc);
     LAUNCH(sim, k_ex_lens, grid_for(sim, ex->m_out_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, ex->words_out);
     TRY((launch_scan<uint64_t, true>(sim, ex->words_out, ex->woff, n_out, 0, ex->m_out_bound, nullptr, 1, nullptr)));
-    LAUNCH(sim, k_ex_copy, grid_for(sim, ex->m_out_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, (const uint64_t *)ex->woff);
+    LAUNCH(sim, k_ex_copy, grid_for(sim, ex->m_out_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, (const uint64_t *)ex->woff, ex->stage, ex->m_out_bound * ex->wpm);
+    LAUNCH(sim, k_ex_stream, grid_for(sim, ex->m_out_bound * 4), TPB, 0, sim->d, a, (const ExScratch *)sc, (const uint64_t *)ex->woff, (const uint32_t *)ex->stage,
+           ex->m_out_bound * ex->wpm);
     LAUNCH(sim, k_ex_publish, 1, 32, 0, sim->d, a, (const ExScratch *)sc, (const uint64_t *)ex->woff);
     ex->pushed = true;
     CU(sim, cudaGetLastError());

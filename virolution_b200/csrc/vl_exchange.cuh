@@ -83,19 +83,35 @@ __global__ void __launch_bounds__(TPB) k_ex_lens(DevState *st, ExArgs ex, const 
         words[idx] = len;
     }
 }
-__global__ void __launch_bounds__(TPB) k_ex_copy(DevState *st, ExArgs ex, const ExScratch *sc, const uint64_t *__restrict__ woff) {
+// entries of every leaving migrant, first gathered into a local staging buffer in concatenation order (random reads of
+// the arena, local writes), then streamed to the targets word by word: consecutive threads write consecutive words of
+// the same block, so what crosses NVLink are full 128-byte lines instead of one short store per migrant
+__global__ void __launch_bounds__(TPB) k_ex_copy(DevState *st, ExArgs ex, const ExScratch *sc, const uint64_t *__restrict__ woff,
+                                                 uint32_t *__restrict__ stage, uint64_t stage_cap) {
     const uint64_t M = sc->n_out;
-    const uint32_t par = ex.parity;
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M; idx += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t t = ex_find(sc->part_start, ex.world, idx);
         const uint32_t id = ex.part[t][idx - sc->part_start[t]];
         if (id == 0) continue;
         const HapMeta hm = st->hm[id];
-        const uint64_t w0 = woff[idx] - woff[sc->part_start[t]];
-        if (w0 + hm.len > ex.out[t].w_cap) { raise(st, DE_ARENA_CAPACITY); continue; }  // block too small: vl_exchange_create's words_per_migrant
         const uint32_t *src = st->arena + hm.off;
-        uint32_t *dst = ex.out[t].entries[par] + w0;
+        if (woff[idx] + hm.len > stage_cap) { raise(st, DE_ARENA_CAPACITY); continue; }  // (the target's block would overflow too)
+        uint32_t *dst = stage + woff[idx];
         for (uint32_t k = 0; k < hm.len; k++) dst[k] = src[k];
+    }
+}
+__global__ void __launch_bounds__(TPB) k_ex_stream(DevState *st, ExArgs ex, const ExScratch *sc, const uint64_t *__restrict__ woff,
+                                                   const uint32_t *__restrict__ stage, uint64_t stage_cap) {
+    __shared__ uint64_t s_wstart[EX_MAX_WORLD + 1];
+    if (threadIdx.x <= ex.world) s_wstart[threadIdx.x] = woff[sc->part_start[threadIdx.x]];
+    __syncthreads();
+    const uint64_t W = s_wstart[ex.world] < stage_cap ? s_wstart[ex.world] : stage_cap;
+    const uint32_t par = ex.parity;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < W; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = ex_find(s_wstart, ex.world, g);
+        const uint64_t w0 = g - s_wstart[t];
+        if (w0 >= ex.out[t].w_cap) { if (w0 == ex.out[t].w_cap) raise(st, DE_ARENA_CAPACITY); continue; }  // block too small: words_per_migrant
+        ex.out[t].entries[par][w0] = stage[g];
     }
 }
 // headers, then (after a system-scope fence: the stores of the kernels before this one are complete, this makes them
