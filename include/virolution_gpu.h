@@ -201,6 +201,9 @@ int vl_get_raw_fitness(vl_sim *sim, uint32_t spec, int which, double *out, uint6
 int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, uint32_t *positions_out,
                         uint8_t *bases_out, uint64_t *n_entries);
 int vl_get_base(vl_sim *sim, uint64_t infectant, uint64_t position, uint8_t *out); /* Haplotype::get_base */
+/* population statistics of the `stats` schedule event (src/stats/population.rs, src/runner.rs:634-673) */
+int vl_stats_frequencies(vl_sim *sim, double *out /* n_sites x 4, row-major */, uint64_t n_sites);   /* :15-40 */
+int vl_stats_mean_fitness(vl_sim *sim, uint32_t spec, int which, double *out);                       /* :50-56 */
 int vl_get_haplotype_ids(vl_sim *sim, uint32_t *out, uint64_t n);      /* device-local ids (labels) */
 /* counters: [0] live+dead haplotype records, [1] arena words used, [2] gc runs, [3] kernels launched */
 int vl_get_counters(vl_sim *sim, uint64_t *out4);

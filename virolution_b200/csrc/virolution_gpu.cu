@@ -737,7 +737,7 @@ static int enqueue_mutate(vl_sim *sim) {
     sim->has_rp_rec = false;
     return VL_OK;
 }
-static int enqueue_replicate(vl_sim *sim, int store_lambda = 1) {
+static int enqueue_replicate(vl_sim *sim, int store_lambda = 1, bool tiles_planned = false) {
     const DevState &h = sim->h;
     if (!sim->csr_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "replicate needs the host map: call vl_infect first");
     TRY(zero_replicate_counters(sim));
@@ -751,6 +751,7 @@ static int enqueue_replicate(vl_sim *sim, int store_lambda = 1) {
     const bool fused_only = fused && sim->uniform_infection;
     int guarded = 0;
     if (fused) {
+        if (!tiles_planned) LAUNCH(sim, k_plan_host_tiles, 1, 1, 0, sim->d);  // (k_begin_generation did it for the fused generation)
         const uint32_t per = n_host_tiles >= (uint64_t)sim->n_sms * 12 ? 2u : 1u;  // consecutive tiles per CTA (prefetch of the second)
         const unsigned g = (unsigned)((n_host_tiles + per - 1) / per);
         if (small) LAUNCH(sim, k_replicate_fused<true>, g, REPL_TPB, 0, sim->d, rpo, store_lambda, fused_only ? 1 : 0, per);
@@ -1266,8 +1267,9 @@ static int enqueue_generation_front(vl_sim *sim) {
     const DevState &h = sim->h;
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
     sim->salt = 0;
-    if (!(sim->experiment & 1) && !replay && h.binv.ok && !(h.host_recombination_rate > 0.0) && buckets_possible(sim) &&
-        h.cap_tmp >= (uint64_t)h.n_buckets * bucket_stride(sim->n_bound, h.H)) {
+    const bool fast_flow = !(sim->experiment & 1) && !replay && h.binv.ok && !(h.host_recombination_rate > 0.0) && buckets_possible(sim) &&
+                           h.cap_tmp >= (uint64_t)h.n_buckets * bucket_stride(sim->n_bound, h.H);
+    if (fast_flow) {
         // uniform infection (every infectant is infected, hosts iid uniform): the mutation count of an infectant does not
         // depend on its host, so mutate first and build the host map from the already-mutated population
         LAUNCH(sim, k_begin_generation, 1, 1024, 0, sim->d);
@@ -1286,7 +1288,7 @@ static int enqueue_generation_front(vl_sim *sim) {
         TRY(enqueue_mutate(sim));
         if (!sim->csr_valid) TRY(sim->bucket_pending ? enqueue_bucket_host_map(sim) : enqueue_host_map(sim));
     }
-    TRY(enqueue_replicate(sim, 0));
+    TRY(enqueue_replicate(sim, 0, fast_flow));
     return VL_OK;
 }
 static int enqueue_generation(vl_sim *sim) {
@@ -1800,6 +1802,52 @@ VL_API int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, u
         CU(sim, cudaStreamSynchronize(sim->stream));
         cudaFree(dp); cudaFree(db);
     }
+    return VL_OK;
+}
+// PopulationFrequencies::frequencies (src/stats/population.rs:15-40): L x 4 relative frequencies, row-major
+VL_API int vl_stats_frequencies(vl_sim *sim, double *out, uint64_t n_sites) {
+    ENTER(sim);
+    const uint64_t L = sim->h.L;
+    if (!out || n_sites != L) return fail(sim, VL_ERR_ARGUMENT, "frequency buffer must hold n_sites x 4 values");
+    uint64_t n = 0;
+    TRY(population_len(sim, &n));
+    uint32_t *cnt = nullptr;
+    CU(sim, cudaMalloc((void **)&cnt, L * 4 * 4));
+    zero_device(sim, cnt, L * 4 * 4);
+    LAUNCH(sim, k_stats_counts, grid_for(sim, n), TPB, 0, sim->d, cnt);
+    std::vector<uint32_t> c(L * 4);
+    std::vector<uint8_t> wt(L);
+    cudaError_t e1 = cudaMemcpyAsync(c.data(), cnt, L * 16, cudaMemcpyDeviceToHost, sim->stream);
+    cudaError_t e2 = cudaMemcpyAsync(wt.data(), sim->h.wildtype, L, cudaMemcpyDeviceToHost, sim->stream);
+    cudaError_t e3 = cudaStreamSynchronize(sim->stream);
+    cudaFree(cnt);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail(sim, VL_ERR_CUDA, "frequency download failed");
+    for (uint64_t pos = 0; pos < L; pos++) {
+        // counts[wildtype] = population_size - sum of the row (the reference overwrites the slot, :28-33)
+        int64_t row = (int64_t)c[pos * 4] + c[pos * 4 + 1] + c[pos * 4 + 2] + c[pos * 4 + 3];
+        int64_t v[4] = {c[pos * 4], c[pos * 4 + 1], c[pos * 4 + 2], c[pos * 4 + 3]};
+        v[wt[pos]] = (int64_t)n - row;
+        for (int b = 0; b < 4; b++) out[pos * 4 + b] = (double)v[b] / (double)n;
+    }
+    return VL_OK;
+}
+// PopulationStatistics::mean (src/stats/population.rs:50-56) of the mapped fitness under provider (spec, which)
+VL_API int vl_stats_mean_fitness(vl_sim *sim, uint32_t spec, int which, double *out) {
+    ENTER(sim);
+    if (!out) return fail(sim, VL_ERR_ARGUMENT, "null out");
+    if (spec >= sim->h.n_specs) return fail(sim, VL_ERR_ARGUMENT, "spec out of range");
+    const int pi = which ? sim->h.specs[spec].infect : sim->h.specs[spec].repro;
+    uint64_t n = 0;
+    TRY(population_len(sim, &n));
+    const unsigned g = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (n + 4 * TPB - 1) / (4 * TPB)), 1024);
+    double *partial = (double *)sim->stage64;  // >= 4096 doubles
+    LAUNCH(sim, k_stats_fitness_sum, g, TPB, 0, sim->d, pi, partial);
+    std::vector<double> p(g);
+    CU(sim, cudaMemcpyAsync(p.data(), partial, g * 8, cudaMemcpyDeviceToHost, sim->stream));
+    CU(sim, cudaStreamSynchronize(sim->stream));
+    double sum = 0.0;
+    for (unsigned k = 0; k < g; k++) sum += p[k];
+    *out = sum / (double)n;  // NaN for an empty population, like 0.0 / 0 in the reference
     return VL_OK;
 }
 VL_API int vl_get_base(vl_sim *sim, uint64_t infectant, uint64_t position, uint8_t *out) {

@@ -92,6 +92,7 @@ __global__ void k_begin_phase(DevState *st) {
     st->n_heavy = 0;
     st->n_medium = 0;
 }
+__global__ void k_plan_host_tiles(DevState *st) { st->ht_planned = host_tile_size(st->n, st->H); }
 // everything the fused generation clears or bumps before its first real kernel, in one launch
 __global__ void __launch_bounds__(1024) k_begin_generation(DevState *st) {
     for (uint32_t b = threadIdx.x; b <= MAX_BUCKETS_C; b += blockDim.x) st->bucket_fill[b] = 0u;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(1024) k_begin_generation(DevState *st) {
         st->n_heavy = 0;
         st->n_medium = 0;
         st->fused_failed = 0;
+        st->ht_planned = host_tile_size(st->n, st->H);
     }
 }
 
@@ -738,7 +740,7 @@ __global__ void __launch_bounds__(TPB) k_mutation_counts(DevState *st, ReplayMut
 // of infectant i is a function of (seed, generation, i) alone — words z,w of block 0 of its PH_INFECT stream, the same
 // uniform the fused infect kernels use — so the fused generation can mutate BEFORE it builds the host map and no
 // record needs patching afterwards.  One global atomic per CTA and round.
-constexpr int MC_ITEMS = 8;
+constexpr int MC_ITEMS = 4;
 __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
     __shared__ uint32_t s_base;
     const uint64_t n = st->n;
@@ -1195,7 +1197,7 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
     __shared__ double s_rcp[POISSON_RCP];
     poisson_rcp_init(s_rcp);
     const uint64_t H = st->H;
-    const uint32_t ht = host_tile_size(st->n, H);  // from the state, not from the launch: see host_tile_size
+    const uint32_t ht = st->ht_planned;  // host_tile_size(n, H), from the state, not from the launch (k_plan_host_tiles)
     if (ht == 0) {  // more infectants per host than whole-host tiles can stage
         if (blockIdx.x == 0 && threadIdx.x == 0) { st->fused_failed = 1u; if (fail_is_error) raise(st, DE_TILE_OVERFLOW); }
         return;

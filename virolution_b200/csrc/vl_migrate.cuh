@@ -253,6 +253,38 @@ __global__ void __launch_bounds__(TPB) k_export_fill(DevState *st, const uint64_
         }
     }
 }
+// ---- population statistics (src/stats/population.rs) ---------------------------------------------------------------
+// PopulationFrequencies::frequencies (:15-40): per (site, base) the number of infectants whose mutation set holds that
+// base there; the wildtype column is filled in by the caller as n minus the row sum, like the reference does
+__global__ void __launch_bounds__(TPB) k_stats_counts(DevState *st, uint32_t *__restrict__ counts) {
+    const uint64_t n = st->n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = st->hap_id[i];
+        const HapMeta hm = st->hm[id];
+        const uint32_t *e = st->arena + hm.off;
+        for (uint32_t k = 0; k < hm.len; k++) {
+            const uint32_t m = entry_m(e[k]);
+            if (m < 4) atomicAdd(&counts[(uint64_t)entry_pos(e[k]) * 4 + m], 1u);
+        }
+    }
+}
+// PopulationStatistics::mean (:50-56): sum of the mapped attribute over infectants; one partial sum per CTA in a fixed
+// tree order (the caller adds the partials in order), so the result does not depend on scheduling
+__global__ void __launch_bounds__(TPB) k_stats_fitness_sum(DevState *st, int provider, double *__restrict__ partial) {
+    __shared__ double s_red[TPB];
+    const uint64_t n = st->n;
+    const uint64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = per * blockIdx.x < n ? per * blockIdx.x : n, hi = lo + per < n ? lo + per : n;
+    double acc = 0.0;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += TPB) acc += provider >= 0 ? st->h_fit[provider][st->hap_id[i]] : 1.0;
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = TPB / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) s_red[threadIdx.x] += s_red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = s_red[0];
+}
 __global__ void k_get_base(DevState *st, uint64_t infectant, uint32_t pos, uint32_t *out) {
     if (infectant >= st->n || pos >= st->L) { *out = 0xFFu; return; }
     const uint32_t id = st->hap_id[infectant];

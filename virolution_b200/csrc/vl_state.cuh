@@ -125,7 +125,7 @@ struct DevState {
     uint32_t n_heavy;
     uint32_t fused_failed; // a tile of the fused replicate kernel did not fit: the general kernels redo the phase
     uint32_t host_tiles;   // > 0: resample tiles are ranges of that many hosts, 0: ranges of RESAMPLE_TILE CSR positions
-    uint32_t _pad3;
+    uint32_t ht_planned;   // host_tile_size(n, H) of the current population, set before the fused replicate kernel runs
     uint32_t fast_infect;  // specs cover [0,H), no infective provider, n_hits == 1: every draw infects, hosts uniform
     // ---- bucketed counting sort (hosts split into buckets of BUCKET_HOSTS consecutive hosts)
     uint32_t n_buckets;

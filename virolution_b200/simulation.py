@@ -61,6 +61,8 @@ SIGNATURES = {
     "vl_get_raw_fitness": (C.c_int, [_vp, C.c_uint32, C.c_int, f64p, C.c_uint64]),
     "vl_export_mutations": (C.c_int, [_vp, u64p, C.c_uint64, u32p, u8p, u64p]),
     "vl_get_base": (C.c_int, [_vp, C.c_uint64, C.c_uint64, u8p]),
+    "vl_stats_frequencies": (C.c_int, [_vp, f64p, C.c_uint64]),
+    "vl_stats_mean_fitness": (C.c_int, [_vp, C.c_uint32, C.c_int, f64p]),
     "vl_get_haplotype_ids": (C.c_int, [_vp, u32p, C.c_uint64]),
     "vl_get_counters": (C.c_int, [_vp, u64p]),
     "vl_collect_garbage": (C.c_int, [_vp]),
@@ -397,6 +399,46 @@ class GpuSimulation:
             self._check(self.lib.vl_export_mutations(self.ptr, _p(offsets, C.c_uint64), n, _p(pos, C.c_uint32),
                                                      _p(base, C.c_uint8), C.byref(total)))
         return offsets, pos[:t], base[:t]
+
+    # ------------------------------------------------------------------ statistics and final.<i>.csv
+    def frequencies(self) -> np.ndarray:
+        """PopulationFrequencies::frequencies (src/stats/population.rs:15-40): (n_sites, 4) relative frequencies."""
+        out = np.zeros((self.n_sites, 4), dtype=np.float64)
+        self._check(self.lib.vl_stats_frequencies(self.ptr, _p(out, C.c_double), self.n_sites))
+        return out
+
+    def distance(self, other: "GpuSimulation") -> float:
+        """PopulationDistance::distance (:66-75): sum of absolute per-site frequency differences, summed in index order."""
+        d = np.abs(self.frequencies().ravel() - other.frequencies().ravel())
+        return float(np.cumsum(d)[-1]) if d.size else 0.0
+
+    def mean_fitness(self, spec: int = 0, which: int = 0) -> float:
+        """PopulationStatistics::mean of the mapped fitness (:50-56)."""
+        out = C.c_double()
+        self._check(self.lib.vl_stats_mean_fitness(self.ptr, spec, which, C.byref(out)))
+        return float(out.value)
+
+    def haplotype_rows(self, wildtype: np.ndarray):
+        """Rows of final.<i>.csv (src/runner.rs:137-152): one (Haplotype::get_string, count) per haplotype *record*
+        (the reference counts by reference identity), in first-occurrence order."""
+        letters = "ATCG"
+        ids = self.get_haplotype_ids()
+        off, pos, base = self.export_mutations()
+        uniq, first, counts = np.unique(ids, return_index=True, return_counts=True)
+        rows = []
+        for k in np.argsort(first):
+            i = int(first[k])
+            a, b = int(off[i]), int(off[i + 1])
+            text = ";".join(f"{int(p)}:{letters[int(wildtype[int(p)])]}->{letters[int(t)]}" for p, t in zip(pos[a:b], base[a:b]))
+            rows.append((text or "wt", int(counts[k])))
+        return rows
+
+    def write_final_csv(self, path: str, wildtype: np.ndarray):
+        import csv
+        with open(path, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["haplotype", "count"])
+            w.writerows(self.haplotype_rows(wildtype))
 
     def get_base(self, infectant: int, position: int) -> int:
         out = C.c_uint8()
