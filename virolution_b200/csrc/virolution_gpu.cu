@@ -486,6 +486,14 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CTRY(dev_alloc(sim, &h.bucket_pos, MAX_BUCKETS + 2));
     CCU(cudaFuncSetAttribute((k_bucket_sort<1024, BSORT_STAGE_RECS>), cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
     { const char *e = getenv("VL_EXPERIMENT"); sim->experiment = e ? atoi(e) : 0; }
+    if (sim->experiment & 16) {
+        size_t g = 0;
+        cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity);
+        cudaError_t ge = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (sim->experiment & 32) ? 128 : 32);
+        size_t g2 = 0;
+        cudaDeviceGetLimit(&g2, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "L2 fetch granularity %zu -> %zu (%s)\n", g, g2, cudaGetErrorString(ge));
+    }
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
     CTRY(dev_alloc(sim, &h.hm, cap_hap)); CTRY(dev_alloc(sim, &h.hm_alt, cap_hap));
@@ -1582,9 +1590,13 @@ VL_API int vl_step(vl_sim *const *sims, uint32_t C, const double *T, int rule) {
     int rc = VL_OK;
     if (rule == 0) {
         // parallel-build rule (runner.rs:401-416): new[t] = concat_o subsample(sim[o], offspring[o], T[t][o])
-        for (uint32_t o = 0; o < C && rc == VL_OK; o++) {
+        std::vector<double> col(C);
+        std::vector<vl_pop *> out(C);
+        for (uint32_t o = 0; o < C && rc == VL_OK; o++) {  // the C parts of one origin share one plan + resample pass
             ON(o);
-            for (uint32_t t = 0; t < C && rc == VL_OK; t++) rc = enqueue_subsample(sims[o], T[(size_t)t * C + o], 0, 0, &parts[(size_t)t * C + o]);
+            for (uint32_t t = 0; t < C; t++) col[t] = T[(size_t)t * C + o];
+            rc = enqueue_subsamples(sims[o], C, col.data(), 0, nullptr, out.data());
+            for (uint32_t t = 0; t < C; t++) parts[(size_t)t * C + o] = out[t];
         }
     } else {
         // serial-build rule (runner.rs:550-631)
@@ -1614,9 +1626,13 @@ VL_API int vl_step(vl_sim *const *sims, uint32_t C, const double *T, int rule) {
                 else amount[(size_t)t * C + t] = f64_as_usize_host(ts[t]) - mig;
             }
         }
+        std::vector<uint64_t> col(C);
+        std::vector<vl_pop *> out(C);
         for (uint32_t o = 0; o < C && rc == VL_OK; o++) {
             ON(o);
-            for (uint32_t t = 0; t < C && rc == VL_OK; t++) rc = enqueue_subsample(sims[o], 0.0, 1, amount[(size_t)t * C + o], &parts[(size_t)t * C + o]);
+            for (uint32_t t = 0; t < C; t++) col[t] = amount[(size_t)t * C + o];
+            rc = enqueue_subsamples(sims[o], C, nullptr, 1, col.data(), out.data());
+            for (uint32_t t = 0; t < C; t++) parts[(size_t)t * C + o] = out[t];
         }
     }
     for (uint32_t c = 0; c < C && rc == VL_OK; c++) {
