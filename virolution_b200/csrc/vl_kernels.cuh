@@ -249,6 +249,7 @@ constexpr int MAX_BUCKETS = 2048;
 template <bool FUSE_MUT, bool STORE_HOST, int BTPB>
 __global__ void __launch_bounds__(BTPB) k_infect_bucket(DevState *st) {
     __shared__ uint32_t s_hist[MAX_BUCKETS];   // per-chunk count, then global base of the chunk's run per bucket
+    __shared__ uint32_t s_hap[BTPB * BUCKET_ITEMS];  // the chunk's haplotype ids, copied asynchronously while the hosts are drawn
     __shared__ uint32_t s_w[BTPB / 32];
     __shared__ uint32_t s_lbase;
     const uint64_t n = st->n;
@@ -264,6 +265,17 @@ __global__ void __launch_bounds__(BTPB) k_infect_bucket(DevState *st) {
     const uint64_t n_chunks = (n + (BTPB * BUCKET_ITEMS) - 1) / (BTPB * BUCKET_ITEMS);
     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         for (uint32_t b = tid; b < B; b += BTPB) s_hist[b] = 0;
+        // every thread starts the copy of its own items' haplotype ids into shared memory (cp.async: no register is held,
+        // the latency hides under the Philox rounds below) and is the only reader of those words later
+#pragma unroll
+        for (int e = 0; e < BUCKET_ITEMS; e++) {
+            const uint64_t i = chunk * (BTPB * BUCKET_ITEMS) + (uint64_t)e * BTPB + tid;
+            if (i < n) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_hap[e * BTPB + tid]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(hap_id + i) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         __syncthreads();
         // coalesced layout: item e of thread t is infectant chunk*CHUNK + e*TPB + t.  Per item two registers survive
         // the barriers: the host, and (rank inside the chunk's bucket run | n_mut << 16).
@@ -292,6 +304,7 @@ __global__ void __launch_bounds__(BTPB) k_infect_bucket(DevState *st) {
             const uint32_t c = s_hist[b];
             s_hist[b] = c ? atomicAdd(&st->bucket_fill[b], c) : 0u;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         uint32_t mine = 0;
 #pragma unroll
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(BTPB) k_infect_bucket(DevState *st) {
             uint32_t pos = NONE32;
             if (r < stride) {
                 pos = (uint32_t)(b * stride + r);
-                st->tmp_rec[pos] = make_uint4((uint32_t)i, hap_id[i], h[e], 0u);
+                st->tmp_rec[pos] = make_uint4((uint32_t)i, s_hap[e * BTPB + tid], h[e], 0u);
             } else {
                 raise(st, DE_BUCKET_OVERFLOW);
             }
@@ -396,15 +409,15 @@ __global__ void __launch_bounds__(STPB) k_bucket_sort(DevState *st) {
         const bool staged = fill <= SRECS;
         for (uint32_t k = tid; k < BUCKET_HOSTS; k += STPB) s_cnt[k] = 0;
         __syncthreads();
-        for (uint32_t j0 = tid; j0 < fill; j0 += 4 * STPB) {  // four independent loads in flight per thread
-            uint4 r[4];
+        for (uint32_t j0 = tid; j0 < fill; j0 += 8 * STPB) {  // eight independent loads in flight per thread
+            uint4 r[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const uint32_t j = j0 + u * STPB;
                 r[u] = j < fill ? src[j] : make_uint4(0u, 0u, h0, 0u);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const uint32_t j = j0 + u * STPB;
                 if (j >= fill) continue;
                 const uint32_t hl = r[u].z - h0;
