@@ -40,6 +40,12 @@ struct vl_sim {
     int device = 0;
     int n_sms = 148;
     int flags = 0;
+    // one fused generation captured as a CUDA graph: small populations are launch-bound (a dozen kernels of a few
+    // microseconds each), replaying the graph halves the time per generation there
+    cudaGraphExec_t gen_graph = nullptr;
+    uint64_t graph_key[5] = {0, 0, 0, 0, 0};
+    uint64_t graph_launches = 0;
+    bool graph_disabled = false;
     int experiment = 0;  // VL_EXPERIMENT bit mask: kernel-variant switches for A/B timing (development aid, default 0)
     cudaStream_t stream = nullptr;
     std::recursive_mutex mu;
@@ -379,6 +385,7 @@ static void destroy_sim(vl_sim *sim) {
         if (p->image) cudaFree(p->image);
         delete p;
     }
+    if (sim->gen_graph) cudaGraphExecDestroy(sim->gen_graph);
     for (auto &b : sim->id_pool) cudaFree(b.p);
     free_population_buffers(sim);
     if (sim->h.offsets) cudaFree(sim->h.offsets);
@@ -1299,11 +1306,61 @@ static int enqueue_generation_front(vl_sim *sim) {
     TRY(enqueue_replicate(sim, 0, fast_flow));
     return VL_OK;
 }
-static int enqueue_generation(vl_sim *sim) {
-    // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
+// the kernels of one whole generation (everything but the occasional compaction)
+static int enqueue_generation_kernels(vl_sim *sim) {
     TRY(enqueue_generation_front(sim));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
-    swap_population(sim);
+    LAUNCH(sim, k_swap_population, 1, 1, 0, sim->d);
+    return VL_OK;
+}
+constexpr uint64_t GRAPH_MAX_POPULATION = 4u << 20;  // above this a generation is milliseconds of kernels, launches do not matter
+static bool graph_wanted(const vl_sim *sim) {
+    const DevState &h = sim->h;
+    const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
+    return !sim->graph_disabled && !sim->profiling && !(sim->experiment & 64) && !replay && sim->n_bound <= GRAPH_MAX_POPULATION &&
+           sim->n_bound == std::min<uint64_t>(h.cap_inf, h.max_population);  // the bound every later generation has too
+}
+static int enqueue_generation(vl_sim *sim) {
+    // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
+    if (graph_wanted(sim)) {
+        const DevState &h = sim->h;
+        const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets, (uint64_t)sim->flags};
+        if (!sim->gen_graph || memcmp(key, sim->graph_key, sizeof key) != 0) {
+            if (sim->gen_graph) { cudaGraphExecDestroy(sim->gen_graph); sim->gen_graph = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const uint64_t l0 = sim->launches;
+            if (cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = enqueue_generation_kernels(sim);
+                const cudaError_t ce = cudaStreamEndCapture(sim->stream, &graph);
+                if (rc == VL_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&sim->gen_graph, graph, 0) == cudaSuccess) {
+                    memcpy(sim->graph_key, key, sizeof key);
+                    sim->graph_launches = sim->launches - l0;
+                } else {
+                    sim->gen_graph = nullptr;
+                    sim->graph_disabled = true;  // whatever made the capture fail would fail again: enqueue directly from now on
+                }
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+            } else {
+                sim->graph_disabled = true;
+                cudaGetLastError();
+            }
+            sim->launches = l0;  // (a failed capture enqueued nothing: the direct path below runs the generation)
+        }
+        if (sim->gen_graph) {
+            CU(sim, cudaGraphLaunch(sim->gen_graph, sim->stream));
+            sim->launches += sim->graph_launches;
+            sim->salt = 1;
+            sim->mutcounts_ready = false;
+            sim->bucket_pending = false;
+            sim->has_rp_off = false;
+        } else {
+            TRY(enqueue_generation_kernels(sim));
+        }
+    } else {
+        TRY(enqueue_generation_kernels(sim));
+    }
+    std::swap(sim->h.hap_id, sim->h.hap_id_next);
     sim->n_valid = false;
     sim->n_bound = std::min<uint64_t>(sim->h.cap_inf, sim->h.max_population);
     sim->csr_valid = false;
