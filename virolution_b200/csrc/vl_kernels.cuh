@@ -1207,8 +1207,6 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
     __shared__ double s_f[RESAMPLE_TILE];
     __shared__ uint2 s_rec[RESAMPLE_TILE];
     __shared__ uint32_t s_red[REPL_TPB / 32];
-    __shared__ double s_rcp[POISSON_RCP];
-    poisson_rcp_init(s_rcp);
     const uint64_t H = st->H;
     const uint32_t ht = st->ht_planned;  // host_tile_size(n, H), from the state, not from the launch (k_plan_host_tiles)
     if (ht == 0) {  // more infectants per host than whole-host tiles can stage
@@ -1234,7 +1232,7 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
     for (uint64_t tile = (uint64_t)blockIdx.x * tiles_per_cta; tile < tile_end; tile++) {
         const uint64_t h0 = tile * ht;
         const uint32_t nh = (uint32_t)(H - h0 < ht ? H - h0 : ht);
-        __syncthreads();  // shared arrays of the previous tile are free (and s_rcp is filled)
+        __syncthreads();  // shared arrays of the previous tile are free
         for (uint32_t k = tid; k <= nh; k += REPL_TPB) s_off[k] = offsets[h0 + k];
         for (uint32_t k = tid; k < RESAMPLE_TILE / 32 + 2; k += REPL_TPB) s_head[k] = 0u;
         __syncthreads();
@@ -1332,7 +1330,7 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
                 off = (uint32_t)v;
             } else if (l > 0.0) {
                 uint64_t v;
-                if (l < 12.0) v = poisson_draw_small_fast(key, p, gen, PH_OFFSPRING, l, s_rcp, kmax);
+                if (l < 12.0) v = poisson_draw_small_fast(key, p, gen, PH_OFFSPRING, l, c_rcp64, kmax)  /* the f64 fallback reads 1/k from constant memory */;
                 else if (SMALL_ONLY) { raise(st, DE_UNDEFINED_OFFSPRING); v = 0; }  // f > S: negative fitness values in the slice
                 else v = poisson_ptrs(key, p, gen, PH_OFFSPRING, l);
                 if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
