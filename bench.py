@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="k2_hiv")
     ap.add_argument("--n", "--population", dest="n", type=int, default=0, help="override N = H = max_population")
+    ap.add_argument("--sharded", action="store_true", help="N > 1: ONE compartment of the workload split over the GPUs (strong scaling) "
+                    "instead of one compartment per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=10)
@@ -156,10 +158,18 @@ def run_b200(args, rank, world):
     flags = 0
     par = wl["parameters"]
     N = wl["n0"]
-    sim = GpuSimulation(wl["wildtype"], par, wl["specs"], seed=2026, device=local_rank, compartment_id=rank, flags=flags)
-    sim.set_population_wildtype(N)
+    sharded = args.sharded and world > 1
+    if sharded:
+        from virolution_b200.distributed import PeerExchange, sharded_simulation
+        sim = sharded_simulation(wl["wildtype"], par, wl["specs"], rank, world, seed=2026, device=local_rank, n0=N)
+    else:
+        sim = GpuSimulation(wl["wildtype"], par, wl["specs"], seed=2026, device=local_rank, compartment_id=rank, flags=flags)
+        sim.set_population_wildtype(N)
     runner = None
-    if world > 1:
+    if sharded:
+        runner = PeerExchange(sim, rank, world, sharded=True, shard_seed=2026)
+        args.no_e2e = True  # the trait-level calls address one handle; a sharded compartment is driven through the exchange only
+    elif world > 1:
         from virolution_b200.distributed import CompartmentExchange, GpuCompartment, PeerExchange
         collective = CompartmentExchange(GpuCompartment(sim), rank, world, migration=0.1)  # e2e leg: host vectors + NCCL all-to-all-v
         # device-resident loop: migrants are pushed by the kernels into peer memory (VL_EXCHANGE=nccl keeps the collective path)
@@ -327,10 +337,12 @@ def run_b200(args, rank, world):
     if rank == 0:
         clk = clocks.summary()
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "impl": "b200",
-               "config": {"workload": wl["description"] + ("" if world == 1 else f" per compartment x {world} compartments"), "compartments": world,
-                          "parallelism": "1 compartment" if world == 1 else f"{world} compartments, 1 per GPU, migrants pushed into peer memory over NVLink by the kernels (0.9 stay / 0.1 migrate uniformly)",
+               "config": {"workload": wl["description"] + ("" if world == 1 or sharded else f" per compartment x {world} compartments"), "compartments": 1 if sharded else world,
+                          "parallelism": "1 compartment" if world == 1 else (f"1 compartment sharded over {world} GPUs (hosts split in {world} ranges; the (target, origin) cells of the "
+                                                                              "resampling are pushed into peer memory over NVLink)" if sharded else
+                                                                              f"{world} compartments, 1 per GPU, migrants pushed into peer memory over NVLink by the kernels (0.9 stay / 0.1 migrate uniformly)"),
                           "l2_policy": "working set (per-infectant arrays, 32 B x N) larger than L2; no flush" if N * 32 > 126e6 else "working set fits L2 (latency-bound config); no flush",
                           "host_sum": "reference-ordered CSR"},
                "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clk, "roofline": roofline, "kernels": kernels,

@@ -248,7 +248,15 @@ int vl_subsample_populations(vl_sim *sim, const double *factors, uint32_t n, vl_
  * words_per_migrant x its migrant capacity; 0 = 64). */
 typedef struct vl_exchange vl_exchange;
 int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const double *transfer, uint64_t words_per_migrant,
-                       vl_exchange **out, void *ipc_handle_out /* 64 bytes: cudaIpcMemHandle_t of the receive buffer */);
+                       int sharded, uint64_t shard_seed, vl_exchange **out,
+                       void *ipc_handle_out /* 64 bytes: cudaIpcMemHandle_t of the receive buffer */);
+/* sharded != 0: ONE compartment split over the ranks.  Rank g owns host_population_size hosts
+ * (its handle is created with the LOCAL host count, the GLOBAL max_population and dilution, and a capacity_infectants
+ * of about 1.3 x max_population / world) and the infectants that infect them.  Per generation every rank publishes its
+ * offspring total to all ranks, every rank splits the N' = (min(W * dilution, max_population)) as usize draws of
+ * Population::sample (src/simulation.rs:491-527) over the world^2 (target, origin) cells with the same multinomial
+ * (cell weight W_origin: a new infectant's host, hence rank, is uniform — src/simulation.rs:365-387), and the cells
+ * travel like migrants.  `transfer` is ignored (may be NULL); shard_seed must be the same on every rank. */
 int vl_exchange_recv_buffer(vl_exchange *ex, void **ptr, uint64_t *bytes);
 /* ipc_handles: world x 64 bytes gathered from all ranks (own slot ignored).  local_ptrs (optional): a non-NULL entry
  * is that rank's receive buffer in THIS process (vl_exchange_recv_buffer), used instead of its handle. */
@@ -258,7 +266,8 @@ int vl_exchange_connect(vl_exchange *ex, const void *ipc_handles, void *const *l
  * pull = device-side wait for every origin's block, import, set_population.  step = push + pull.  Ranks that share a
  * process push all before they pull any (a stream waiting on the device must not depend on work of the same process
  * that has not been submitted yet). */
-int vl_exchange_push(vl_exchange *ex);
+int vl_exchange_begin(vl_exchange *ex); /* increment_generation .. replicate_infectants (+ totals of a sharded compartment) */
+int vl_exchange_push(vl_exchange *ex);  /* calls vl_exchange_begin if the caller has not */
 int vl_exchange_pull(vl_exchange *ex);
 int vl_exchange_step(vl_exchange *ex);
 int vl_exchange_destroy(vl_exchange *ex);

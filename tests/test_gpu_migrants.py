@@ -165,3 +165,79 @@ def test_peer_exchange_equals_in_process_transmission():
         e.close()
     for s in a + b:
         s.close()
+
+
+def _sharded_pair(c, seed, shards=2):
+    """`shards` handles that together hold ONE compartment: local host ranges, global max_population."""
+    from virolution_b200.abi import Parameters
+    from virolution_b200.simulation import GpuSimulation, PeerExchangeHandle
+    p = c["parameters"]
+    H, M = int(p.host_population_size), int(p.max_population)
+    local = Parameters(p.mutation_rate, p.recombination_rate, H // shards, p.basic_reproductive_number, M, p.dilution,
+                       p.substitution_matrix, p.n_hits)
+    specs = []
+    for s in c["specs"]:
+        specs.append(type(s)(0, H // shards, s.reproductive, s.infective))
+    sims = [GpuSimulation(c["wildtype"], local, specs, seed=seed, compartment_id=k, capacity_infectants=int(1.4 * M / shards) + 65536)
+            for k in range(shards)]
+    for s in sims:
+        s.set_population_wildtype(c["n0"] // shards)
+    ex = [PeerExchangeHandle(sims[k], k, shards, None, words_per_migrant=64, sharded=True, shard_seed=seed) for k in range(shards)]
+    bufs = [e.recv_buffer() for e in ex]
+    for k in range(shards):
+        ex[k].connect(None, [bufs[t] if t != k else 0 for t in range(shards)])
+    return sims, ex
+
+
+def _sharded_step(sims, ex):
+    for phase in ("begin", "push", "pull"):  # ranks of one process finish a phase before any starts the next
+        for e in ex:
+            getattr(e, phase)()
+        for s in sims:
+            s.synchronize()
+
+
+def test_sharded_compartment_agrees_with_the_unsharded_one():
+    """One compartment split over two ranks (vl_exchange_create sharded: device-side multinomial over the (target,
+    origin) cells, cells travel like migrants) against the same compartment on one handle: the total population is
+    exactly N' every generation, and the trajectory statistics agree in distribution over seeded replicates."""
+    from scipy import stats
+    from test_gpu_stochastic import big_singlehost
+    R, G = 30, 5
+    rows_a, rows_b = [], []
+    for r in range(R):
+        c = big_singlehost(n=40000, mu=1e-4, r0=6.0, dilution=1.0, seed=700 + r)
+        a = helpers.make_gpu(c)
+        row = []
+        for _ in range(G):
+            a.run(1)
+            row += [a.population_len(), a.mean_fitness()]
+        off, pos, base = a.export_mutations()
+        row += [pos.size / a.population_len(), len(set(helpers.mutation_sets(off, pos, base)))]
+        rows_a.append(row)
+        a.close()
+        sims, ex = _sharded_pair(c, seed=1700 + r)
+        row = []
+        for _ in range(G):
+            _sharded_step(sims, ex)
+            sizes = [s.population_len() for s in sims]
+            assert sum(sizes) == 40000, sizes                     # N' = min(W * dilution, max_population) exactly
+            assert abs(sizes[0] - 20000) < 6 * 100, sizes           # each new infectant picks its rank uniformly: sd = 100
+            mf = sum(s.mean_fitness() * n for s, n in zip(sims, sizes)) / sum(sizes)
+            row += [sum(sizes), mf]
+        tot, distinct = 0, set()
+        for k, s in enumerate(sims):
+            off, pos, base = s.export_mutations()
+            tot += pos.size
+            distinct |= set(helpers.mutation_sets(off, pos, base))
+        row += [tot / 40000, len(distinct)]
+        rows_b.append(row)
+        for e in ex:
+            e.close()
+        for s in sims:
+            s.close()
+    ra, rb = np.array(rows_a, dtype=float), np.array(rows_b, dtype=float)
+    cols = [k for k in range(ra.shape[1]) if not (np.all(ra[:, k] == ra[0, k]) and np.all(rb[:, k] == ra[0, k]))]
+    for k in cols:
+        p = stats.ks_2samp(ra[:, k], rb[:, k]).pvalue
+        assert p > 0.01 / len(cols), f"column {k}: KS p={p:.2e} (one handle mean {ra[:, k].mean():.6g}, sharded mean {rb[:, k].mean():.6g})"

@@ -1400,7 +1400,9 @@ struct vl_exchange {
     uint64_t recv_bytes = 0;
     void *peer[EX_MAX_WORLD] = {nullptr};
     bool peer_ipc[EX_MAX_WORLD] = {false};
-    bool connected = false, pushed = false;
+    bool connected = false, pushed = false, begun = false;
+    bool sharded = false;         // one compartment split over the ranks: amounts come from the device-side multinomial
+    uint64_t max_pop = 0;
     ExArgs args;
     ExScratch *scratch = nullptr;
     uint32_t *part_ids[EX_MAX_WORLD] = {nullptr};
@@ -1410,20 +1412,29 @@ struct vl_exchange {
     uint64_t m_out_bound = 0, m_in_bound = 0;
 };
 struct ExLayout {
+    uint64_t tflag_off[2], tot_off[2];  // sharded compartment: world flags + world offspring totals per parity
     uint64_t flag_off[2][EX_MAX_WORLD], header_off[2][EX_MAX_WORLD], len_off[2][EX_MAX_WORLD], raw_off[2][EX_MAX_WORLD], ent_off[2][EX_MAX_WORLD];
     uint64_t m_cap[EX_MAX_WORLD], w_cap[EX_MAX_WORLD];
     uint64_t bytes;
 };
 // layout of rank `target`'s receive buffer; every rank computes the same layout for every rank
-static ExLayout ex_layout(uint32_t world, uint32_t target, const double *T, uint64_t max_pop, uint32_t P, uint64_t wpm) {
+// migrants one (target <- origin) cell of a sharded compartment can hold: mean max_pop / world^2 with a quarter of slack
+// for unequal shard totals plus 8 standard deviations
+static uint64_t shard_cell_capacity(uint64_t max_pop, uint32_t world) {
+    const double mean = (double)max_pop / ((double)world * (double)world);
+    return (uint64_t)(1.25 * mean + 8.0 * sqrt(mean) + 1024.0);
+}
+static ExLayout ex_layout(uint32_t world, uint32_t target, const double *T, uint64_t max_pop, uint32_t P, uint64_t wpm, bool sharded) {
     ExLayout L;
     memset(&L, 0, sizeof L);
     uint64_t off = 0;
     for (int par = 0; par < 2; par++)
         for (uint32_t o = 0; o < world; o++) { L.flag_off[par][o] = off; off += 8; }
+    for (int par = 0; par < 2; par++) { L.tflag_off[par] = off; off += 8ull * world; }
+    for (int par = 0; par < 2; par++) { L.tot_off[par] = off; off += 8ull * world; }
     off = (off + 255) & ~255ull;
     for (uint32_t o = 0; o < world; o++) {
-        double m = floor(T[(size_t)target * world + o] * (double)max_pop) + 1.0;
+        double m = sharded ? (double)shard_cell_capacity(max_pop, world) : floor(T[(size_t)target * world + o] * (double)max_pop) + 1.0;
         if (!(m >= 1.0)) m = 1.0;
         L.m_cap[o] = o == target ? 0 : (uint64_t)m;
         L.w_cap[o] = L.m_cap[o] * wpm;
@@ -1464,16 +1475,19 @@ static void ex_free(vl_exchange *ex) {
     delete ex;
 }
 VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const double *transfer, uint64_t words_per_migrant,
-                              vl_exchange **out, void *ipc_handle_out) {
+                              int sharded, uint64_t shard_seed, vl_exchange **out, void *ipc_handle_out) {
     ENTER(sim);
-    if (!out || !transfer || !ipc_handle_out) return fail(sim, VL_ERR_ARGUMENT, "null argument");
+    if (!out || (!transfer && !sharded) || !ipc_handle_out) return fail(sim, VL_ERR_ARGUMENT, "null argument");
     if (world < 2 || world > EX_MAX_WORLD || rank >= world) return fail(sim, VL_ERR_ARGUMENT, "world must be in [2, %u] and rank below it", EX_MAX_WORLD);
     vl_exchange *ex = new vl_exchange();
     ex->sim = sim; ex->rank = rank; ex->world = world;
     ex->wpm = words_per_migrant ? words_per_migrant : 64;
-    ex->T.assign(transfer, transfer + (size_t)world * world);
+    ex->sharded = sharded != 0;
+    if (transfer) ex->T.assign(transfer, transfer + (size_t)world * world);
+    else ex->T.assign((size_t)world * world, 1.0 / (double)world);
     const DevState &h = sim->h;
-    const ExLayout L = ex_layout(world, rank, ex->T.data(), h.max_population, h.n_providers, ex->wpm);
+    ex->max_pop = h.max_population;
+    const ExLayout L = ex_layout(world, rank, ex->T.data(), h.max_population, h.n_providers, ex->wpm, ex->sharded);
     ex->recv_bytes = L.bytes;
 #define XCU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ex_free(ex); return fail(sim, VL_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
     XCU(cudaMalloc((void **)&ex->recv, L.bytes));
@@ -1483,13 +1497,21 @@ VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const 
     XCU(cudaMemset(ex->scratch, 0, sizeof(ExScratch)));
     memset(&ex->args, 0, sizeof ex->args);
     ex->args.world = world; ex->args.rank = rank; ex->args.n_providers = h.n_providers;
+    ex->args.shard_seed = shard_seed;
+    for (int par = 0; par < 2; par++) {
+        ex->args.tot_in[par] = (uint64_t *)(ex->recv + L.tot_off[par]);
+        ex->args.tot_flag_in[par] = (unsigned long long *)(ex->recv + L.tflag_off[par]);
+        ex->args.tot_out[rank][par] = ex->args.tot_in[par] + rank;
+        ex->args.tot_flag_out[rank][par] = ex->args.tot_flag_in[par] + rank;
+    }
     for (uint32_t o = 0; o < world; o++) {
         if (o == rank) continue;
         ex_block(ex->args.in[o], ex->recv, L, o);
         ex->m_in_bound += L.m_cap[o];
     }
     for (uint32_t t = 0; t < world; t++) {  // one id buffer per target part (my column of T)
-        double m = floor(ex->T[(size_t)t * world + rank] * (double)h.max_population) + 2.0;
+        double m = ex->sharded ? (double)shard_cell_capacity(h.max_population, world) + 1.0
+                               : floor(ex->T[(size_t)t * world + rank] * (double)h.max_population) + 2.0;
         if (!(m >= 2.0)) m = 2.0;
         XCU(cudaMalloc((void **)&ex->part_ids[t], (uint64_t)m * 4));
         ex->args.part[t] = ex->part_ids[t];
@@ -1530,8 +1552,12 @@ VL_API int vl_exchange_connect(vl_exchange *ex, const void *ipc_handles, void *c
             CU(sim, cudaIpcOpenMemHandle(&ex->peer[t], hd, cudaIpcMemLazyEnablePeerAccess));
             ex->peer_ipc[t] = true;
         }
-        const ExLayout L = ex_layout(ex->world, t, ex->T.data(), h.max_population, h.n_providers, ex->wpm);
+        const ExLayout L = ex_layout(ex->world, t, ex->T.data(), h.max_population, h.n_providers, ex->wpm, ex->sharded);
         ex_block(ex->args.out[t], (uint8_t *)ex->peer[t], L, ex->rank);
+        for (int par = 0; par < 2; par++) {
+            ex->args.tot_out[t][par] = (uint64_t *)((uint8_t *)ex->peer[t] + L.tot_off[par]) + ex->rank;
+            ex->args.tot_flag_out[t][par] = (unsigned long long *)((uint8_t *)ex->peer[t] + L.tflag_off[par]) + ex->rank;
+        }
     }
     ex->connected = true;
     return VL_OK;
@@ -1542,7 +1568,26 @@ VL_API int vl_exchange_destroy(vl_exchange *ex) {
     ex_free(ex);
     return VL_OK;
 }
-// first half: the generation up to the offspring map, the parts of every target, and the push into the targets' buffers
+// the generation up to the offspring map; a sharded compartment also publishes its offspring total to every rank
+VL_API int vl_exchange_begin(vl_exchange *ex) {
+    if (!ex) return fail(nullptr, VL_ERR_ARGUMENT, "null exchange");
+    vl_sim *sim = ex->sim;
+    ENTER(sim);
+    if (!ex->connected) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_connect has not run");
+    if (ex->begun || ex->pushed) return fail(sim, VL_ERR_IMPLEMENTATION, "the previous generation of this exchange is not finished");
+    TRY(enqueue_generation_front(sim));
+    ex->seq += 1;
+    if (ex->sharded) {
+        ExArgs a = ex->args;
+        a.seq = ex->seq;
+        a.parity = (uint32_t)(ex->seq & 1);
+        LAUNCH(sim, k_shard_publish_total, 1, TPB, 0, sim->d, a);
+    }
+    ex->begun = true;
+    CU(sim, cudaGetLastError());
+    return VL_OK;
+}
+// the parts of every target and the push into the targets' buffers
 VL_API int vl_exchange_push(vl_exchange *ex) {
     if (!ex) return fail(nullptr, VL_ERR_ARGUMENT, "null exchange");
     vl_sim *sim = ex->sim;
@@ -1550,15 +1595,22 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
     if (!ex->connected) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_connect has not run");
     if (ex->pushed) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_pull must follow vl_exchange_push");
     const uint32_t W = ex->world, r = ex->rank;
-    TRY(enqueue_generation_front(sim));
-    double factors[EX_MAX_WORLD];
-    uint32_t *dsts[EX_MAX_WORLD];
-    for (uint32_t t = 0; t < W; t++) { factors[t] = ex->T[(size_t)t * W + r]; dsts[t] = ex->part_ids[t]; }
-    TRY(launch_plan_resample(sim, W, factors, 0, nullptr, 0, dsts, nullptr, 0));
-    ex->seq += 1;
+    if (!ex->begun) TRY(vl_exchange_begin(ex));
+    ex->begun = false;
     ExArgs a = ex->args;
     a.seq = ex->seq;
     a.parity = (uint32_t)(ex->seq & 1);
+    double factors[EX_MAX_WORLD];
+    uint32_t *dsts[EX_MAX_WORLD];
+    for (uint32_t t = 0; t < W; t++) { factors[t] = ex->T[(size_t)t * W + r]; dsts[t] = ex->part_ids[t]; }
+    if (ex->sharded) {
+        // every rank's offspring total has been published (vl_exchange_begin): wait for them, split the N' draws over
+        // the (target, origin) cells, draw my row of parts with the amounts the split left in DevState::plan_amount
+        LAUNCH(sim, k_shard_split, 1, 32, 0, sim->d, a, 20ull * 1000000000ull);
+        TRY(launch_plan_resample(sim, W, nullptr, 2, nullptr, 0, dsts, nullptr, 0));
+    } else {
+        TRY(launch_plan_resample(sim, W, factors, 0, nullptr, 0, dsts, nullptr, 0));
+    }
     ExScratch *sc = ex->scratch;
     const uint64_t *n_out = (const uint64_t *)((const char *)sc + offsetof(ExScratch, n_out));
     // ---- push
@@ -1600,7 +1652,8 @@ VL_API int vl_exchange_pull(vl_exchange *ex) {
     {   // upper bound of the new population: every origin sends at most its block capacity, the own part its cap
         uint64_t bound = 0;
         for (uint32_t o = 0; o < W; o++) {
-            double m = floor(ex->T[(size_t)ex->rank * W + o] * (double)sim->h.max_population) + 1.0;
+            double m = ex->sharded ? (double)shard_cell_capacity(ex->max_pop, W) + 1.0
+                                   : floor(ex->T[(size_t)ex->rank * W + o] * (double)sim->h.max_population) + 1.0;
             bound += (uint64_t)(m >= 1.0 ? m : 1.0);
         }
         sim->n_bound = std::min<uint64_t>(sim->h.cap_inf, bound);

@@ -34,6 +34,12 @@ struct ExBlock {
 struct ExArgs {
     uint32_t world, rank, parity, n_providers;
     uint64_t seq;
+    // sharded compartment: every rank's offspring total of this generation, written by its owner into every buffer
+    uint64_t *tot_out[EX_MAX_WORLD][2];            // my slot in every rank's buffer (own buffer included)
+    unsigned long long *tot_flag_out[EX_MAX_WORLD][2];
+    uint64_t *tot_in[2];                           // world slots in my buffer
+    unsigned long long *tot_flag_in[2];
+    uint64_t shard_seed;                           // the same on every rank: the split of the draws must be the same everywhere
     ExBlock out[EX_MAX_WORLD];        // my block on every target (peer memory), [rank] unused
     ExBlock in[EX_MAX_WORLD];         // the block of every origin in my own buffer, [rank] unused
     const uint32_t *part[EX_MAX_WORLD];  // ids of the part drawn for every target (my memory)
@@ -213,6 +219,82 @@ __global__ void __launch_bounds__(TPB) k_ex_own(DevState *st, ExArgs ex, const E
     const uint32_t *__restrict__ src = ex.part[ex.rank];
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (uint64_t)gridDim.x * blockDim.x)
         if (s0 + k < cap) st->hap_id_next[s0 + k] = src[k];
+}
+
+// ---- one compartment sharded over the ranks ----------------------------------------------------
+// Hosts are split into `world` equal ranges, rank g keeps the infectants that infect its hosts.  The reference draws
+// N' = (min(W * dilution, max_population)) as usize parents iid proportional to offspring over the whole population and
+// gives every new infectant an iid uniform host (src/simulation.rs:365-387,491-527).  A new infectant's rank is therefore
+// uniform, its parent's rank is proportional to that rank's offspring total W_o, independently:
+//     n[target][origin] ~ Multinomial(N'; W_origin / (world * W))           over all world^2 cells,
+// and given n, origin o draws n[t][o] parents iid proportional to its own offspring for target t — exactly the
+// transmission block with device-decided amounts.  Every rank evaluates the same multinomial from the same inputs
+// (the gathered totals) with the same Philox stream, so no rank has to be told its row.
+__global__ void k_shard_publish_total(DevState *st, ExArgs ex) {
+    __shared__ uint64_t s_red[TPB / 32];
+    const uint64_t nt = tile_count(st);
+    uint64_t local = 0;
+    for (uint64_t t = threadIdx.x; t < nt; t += TPB) local += st->tile_sum[t];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, s);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t total = 0;
+        for (int w = 0; w < TPB / 32; w++) total += s_red[w];
+        s_red[0] = total;
+    }
+    __syncthreads();
+    const uint32_t t = threadIdx.x;
+    if (t < ex.world) {
+        *(volatile uint64_t *)ex.tot_out[t][ex.parity] = s_red[0];
+        __threadfence_system();
+        *(volatile unsigned long long *)ex.tot_flag_out[t][ex.parity] = ex.seq;
+    }
+}
+// wait for every rank's total, then split the draws: plan_amount[t] = n[t][rank]
+__global__ void k_shard_split(DevState *st, ExArgs ex, unsigned long long timeout_ns) {
+    __shared__ uint64_t s_W[EX_MAX_WORLD];
+    const uint32_t o = threadIdx.x;
+    if (o < ex.world) {
+        const unsigned long long t0 = vl_globaltimer();
+        volatile unsigned long long *f = (volatile unsigned long long *)(ex.tot_flag_in[ex.parity] + o);
+        while (*f < ex.seq) {
+            if (vl_globaltimer() - t0 > timeout_ns) { raise(st, DE_EXCHANGE_TIMEOUT); break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+        s_W[o] = ((volatile uint64_t *)ex.tot_in[ex.parity])[o];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const uint32_t G = ex.world;
+    uint64_t W = 0;
+    for (uint32_t g = 0; g < G; g++) W += s_W[g];
+    double target = (double)W * st->dilution;
+    const double cap = (double)st->max_population;
+    if (!(target <= cap)) target = cap;
+    uint64_t left = f64_as_usize(target);
+    st->offspring_total = W;
+    st->target_size = target;
+    if (W == 0) { raise(st, DE_ALL_ZERO_WEIGHTS); left = 0; }
+    // sequential conditional binomials over the G*G cells in (target, origin) order; cell weight W_o (the factor 1/G is common)
+    double wleft = (double)W * (double)G;
+    for (uint32_t t = 0; t < G; t++)
+        for (uint32_t g = 0; g < G; g++) {
+            const double w = (double)s_W[g];
+            uint64_t c = 0;
+            if (left > 0 && w > 0.0) {
+                if (!(w < wleft)) c = left;  // the last cell with weight takes what is left
+                else {
+                    Philox rng(ex.shard_seed, 0xFFFFFFFEu, st->generation, PH_SHARD, (uint64_t)t * G + g);
+                    c = binomial(rng, left, w / wleft);
+                }
+            }
+            left -= c;
+            wleft -= w;
+            if (g == ex.rank) st->plan_amount[t] = c;
+        }
 }
 
 }  // namespace vl

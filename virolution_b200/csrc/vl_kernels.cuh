@@ -1500,9 +1500,9 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
             double a = (double)total * st->dilution, b = (double)st->max_population;
             target = a <= b ? a : b;
         }
-        uint64_t size = pa.use_amount ? pa.amount[tid] : f64_as_usize(pa.factor[tid] * target);
+        uint64_t size = pa.use_amount == 2 ? st->plan_amount[tid] : pa.use_amount ? pa.amount[tid] : f64_as_usize(pa.factor[tid] * target);
         if (n == 0) size = 0;
-        if (n > 0 && total == 0) { if (lead) raise(st, DE_ALL_ZERO_WEIGHTS); size = 0; }
+        if (n > 0 && total == 0) { if (lead && !(pa.use_amount == 2 && size == 0)) raise(st, DE_ALL_ZERO_WEIGHTS); size = 0; }
         if (pa.set_next && size > st->cap_inf) { if (lead) raise(st, DE_INF_CAPACITY); size = st->cap_inf; }
         if (lead) {
             if (tid == 0) {

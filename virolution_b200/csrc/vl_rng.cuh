@@ -19,7 +19,7 @@ namespace vl {
 
 enum Phase : uint32_t {
     PH_INFECT = 1, PH_MUTCOUNT = 2, PH_MUTATE = 3, PH_RECOMB = 4, PH_OFFSPRING = 5, PH_PLAN = 6,
-    PH_RESAMPLE = 7, PH_MIGRANT = 8, PH_TEST = 9, PH_PLAN_FILL = 10, PH_PLAN_TREE = 11, PH_RESAMPLE_RETRY = 12
+    PH_RESAMPLE = 7, PH_MIGRANT = 8, PH_TEST = 9, PH_PLAN_FILL = 10, PH_PLAN_TREE = 11, PH_RESAMPLE_RETRY = 12, PH_SHARD = 13
 };
 
 // ---- stateless block function: block `blk` of stream (index, generation, phase) under key (seed, compartment)

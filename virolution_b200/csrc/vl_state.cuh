@@ -157,6 +157,7 @@ struct DevState {
     uint64_t plan_acc[4][MAX_PARTS];   // draws made per Poissonisation stage and part, summed over the plan CTAs
     uint64_t plan_part[32][MAX_PARTS]; // draws per CTA slice of tiles and part
     uint64_t plan_size[MAX_PARTS];     // sample size of every part of the last plan
+    uint64_t plan_amount[MAX_PARTS];   // sample sizes decided on the device (sharded compartment), PlanArgs::use_amount == 2
     uint64_t tile_stride;              // tile_cnt / tile_base hold MAX_PARTS rows of this many tiles
 
     // ---- haplotype table (double-buffered for compaction; the live set is swapped on device)

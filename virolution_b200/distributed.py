@@ -180,6 +180,23 @@ class CompartmentExchange:
         self.transmit()
 
 
+def sharded_simulation(wildtype, parameters, host_specs, rank: int, world: int, seed: int = 0, device: int = 0, n0: int = 0):
+    """The handle of rank `rank`'s shard of ONE compartment (include/virolution_gpu.h, vl_exchange_create sharded): the local
+    range of hosts (every spec's range scaled by 1/world), the global max_population, room for 1.4 x its share."""
+    from .abi import HostSpec, Parameters
+    from .simulation import GpuSimulation
+    H, M = int(parameters.host_population_size), int(parameters.max_population)
+    if H % world:
+        raise ValueError("host_population_size must be a multiple of the number of shards")
+    local = Parameters(parameters.mutation_rate, parameters.recombination_rate, H // world, parameters.basic_reproductive_number, M,
+                       parameters.dilution, parameters.substitution_matrix, parameters.n_hits)
+    specs = [HostSpec(s.lo // world, s.hi // world, s.reproductive, s.infective) for s in host_specs]
+    sim = GpuSimulation(wildtype, local, specs, seed=seed, device=device, compartment_id=rank,
+                        capacity_infectants=int(1.4 * M / world) + 65536)
+    sim.set_population_wildtype(n0 // world)
+    return sim
+
+
 class PeerExchange:
     """The same loop body with the transport fused into the kernels: every origin writes its migrants straight into the
     targets' device memory over NVLink (CUDA IPC mappings), sizes stay on the device, the host only enqueues
@@ -187,11 +204,15 @@ class PeerExchange:
     hand the 64-byte IPC handles around."""
 
     def __init__(self, sim, rank: int, world: int, transfer: Optional[np.ndarray] = None, migration: float = 0.1,
-                 words_per_migrant: int = 0, group=None):
+                 words_per_migrant: int = 0, group=None, sharded: bool = False, shard_seed: int = 0):
         from .simulation import PeerExchangeHandle
         self.sim, self.rank, self.world = sim, rank, world
-        self.T = np.asarray(migration_matrix(world, migration) if transfer is None else transfer, dtype=np.float64)
-        self.handle = PeerExchangeHandle(sim, rank, world, self.T, words_per_migrant)
+        if sharded:  # one compartment over all ranks (sim from sharded_simulation): the split of the draws is decided on the device
+            self.T = None
+            self.handle = PeerExchangeHandle(sim, rank, world, None, words_per_migrant, sharded=True, shard_seed=shard_seed)
+        else:
+            self.T = np.asarray(migration_matrix(world, migration) if transfer is None else transfer, dtype=np.float64)
+            self.handle = PeerExchangeHandle(sim, rank, world, self.T, words_per_migrant)
         dev = torch.device("cuda", sim.device)
         mine = torch.from_numpy(self.handle.ipc_handle.copy()).to(dev)
         allh = torch.empty(world * mine.numel(), dtype=torch.uint8, device=dev)

@@ -71,7 +71,8 @@ SIGNATURES = {
     "vl_migrants_export_device": (C.c_int, [_vp, C.POINTER(_vp), C.c_uint32, C.POINTER(vl_migrant_image), u64p, u64p]),
     "vl_migrants_import_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.POINTER(_vp)]),
     "vl_subsample_populations": (C.c_int, [_vp, f64p, C.c_uint32, C.POINTER(_vp)]),
-    "vl_exchange_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, f64p, C.c_uint64, C.POINTER(_vp), _vp]),
+    "vl_exchange_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, f64p, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(_vp), _vp]),
+    "vl_exchange_begin": (C.c_int, [_vp]),
     "vl_exchange_recv_buffer": (C.c_int, [_vp, C.POINTER(_vp), u64p]),
     "vl_exchange_connect": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "vl_exchange_step": (C.c_int, [_vp]),
@@ -486,15 +487,20 @@ class PeerExchangeHandle:
     """vl_exchange of one rank: receive buffer + peer mappings + the per-generation enqueue (include/virolution_gpu.h)."""
     IPC_BYTES = 64
 
-    def __init__(self, sim: GpuSimulation, rank: int, world: int, transfer, words_per_migrant: int = 0):
+    def __init__(self, sim: GpuSimulation, rank: int, world: int, transfer=None, words_per_migrant: int = 0,
+                 sharded: bool = False, shard_seed: int = 0):
         self.sim, self.rank, self.world = sim, rank, world
-        T = np.ascontiguousarray(transfer, dtype=np.float64)
-        if T.shape != (world, world):
-            raise ValueError(f"transfer matrix is {T.shape}, expected {(world, world)}")
+        T = None
+        if transfer is not None:
+            T = np.ascontiguousarray(transfer, dtype=np.float64)
+            if T.shape != (world, world):
+                raise ValueError(f"transfer matrix is {T.shape}, expected {(world, world)}")
+        elif not sharded:
+            raise ValueError("a transfer matrix is required unless the compartment is sharded")
         self.ipc_handle = np.zeros(self.IPC_BYTES, dtype=np.uint8)
         ptr = _vp()
-        sim._check(sim.lib.vl_exchange_create(sim.ptr, rank, world, _p(T, C.c_double), words_per_migrant, C.byref(ptr),
-                                              self.ipc_handle.ctypes.data_as(_vp)))
+        sim._check(sim.lib.vl_exchange_create(sim.ptr, rank, world, None if T is None else _p(T, C.c_double), words_per_migrant,
+                                              int(sharded), shard_seed, C.byref(ptr), self.ipc_handle.ctypes.data_as(_vp)))
         self.ptr = ptr
 
     def recv_buffer(self) -> int:
@@ -512,6 +518,9 @@ class PeerExchangeHandle:
 
     def step(self):
         self.sim._check(self.sim.lib.vl_exchange_step(self.ptr))
+
+    def begin(self):
+        self.sim._check(self.sim.lib.vl_exchange_begin(self.ptr))
 
     def push(self):
         self.sim._check(self.sim.lib.vl_exchange_push(self.ptr))
