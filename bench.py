@@ -208,7 +208,6 @@ def run_b200(args, rank, world):
         barrier()
         t_wall = time.perf_counter() - t_wall
     if runner is not None and runner.trace is not None and rank == 0:
-        print("export C call cumulative s (warm-up + timed):", getattr(runner.c, "t_export_c", None), file=sys.stderr)
         print("exchange host seconds per phase over the timed steps:", {k: round(v, 4) for k, v in runner.trace.items()}, file=sys.stderr)
     ig = sim.infectant_generations(reset=True)
     launches = sim.get_counters()["kernels_launched"] - l0

@@ -46,7 +46,8 @@ struct vl_sim {
     uint64_t graph_key[5] = {0, 0, 0, 0, 0};
     uint64_t graph_launches = 0;
     bool graph_disabled = false;
-    int experiment = 0;  // VL_EXPERIMENT bit mask: kernel-variant switches for A/B timing (development aid, default 0)
+    int experiment = 0;  // VL_EXPERIMENT bit mask, A/B timing aid (default 0): 1 = infect before mutate in the fused generation,
+                         // 2 = 512-thread bucketed infect, 4 = unstaged bucket sort, 64 = no CUDA-graph replay
     cudaStream_t stream = nullptr;
     std::recursive_mutex mu;
     DevState h;            // host mirror: configuration + buffer pointers (dynamic fields live on the device)
@@ -493,14 +494,6 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CTRY(dev_alloc(sim, &h.bucket_pos, MAX_BUCKETS + 2));
     CCU(cudaFuncSetAttribute((k_bucket_sort<1024, BSORT_STAGE_RECS>), cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
     { const char *e = getenv("VL_EXPERIMENT"); sim->experiment = e ? atoi(e) : 0; }
-    if (sim->experiment & 16) {
-        size_t g = 0;
-        cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity);
-        cudaError_t ge = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (sim->experiment & 32) ? 128 : 32);
-        size_t g2 = 0;
-        cudaDeviceGetLimit(&g2, cudaLimitMaxL2FetchGranularity);
-        fprintf(stderr, "L2 fetch granularity %zu -> %zu (%s)\n", g, g2, cudaGetErrorString(ge));
-    }
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
     CTRY(dev_alloc(sim, &h.hm, cap_hap)); CTRY(dev_alloc(sim, &h.hm_alt, cap_hap));
@@ -1102,12 +1095,9 @@ static int ensure_buf(vl_sim *sim, vl_sim::DevBuf &b, uint64_t bytes) {
     CU(sim, cudaMalloc(&b.p, b.bytes));
     return VL_OK;
 }
-static double g_seg[8];
-static inline double now_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts, vl_migrant_image *image,
                                      uint64_t *migrants_per_part, uint64_t *words_per_part) {
     ENTER(sim);
-    double t0 = now_s();
     if (!image || (n_parts && (!parts || !migrants_per_part || !words_per_part))) return fail(sim, VL_ERR_ARGUMENT, "null argument");
     if (n_parts > 60) return fail(sim, VL_ERR_ARGUMENT, "too many parts");
     bool pending = false;
@@ -1134,7 +1124,6 @@ VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t
         m0 += parts[k]->n;
     }
     TRY((launch_scan<uint64_t, true>(sim, words, off, nullptr, M, M, sim->gc_totals + 10, 1, nullptr)));
-    g_seg[0] += now_s() - t0; t0 = now_s();
     m0 = 0;
     for (uint32_t k = 0; k < n_parts; k++) {  // word offset of every part boundary
         CU(sim, cudaMemcpyAsync(sim->pin + 64 + k, off + m0, 8, cudaMemcpyDeviceToHost, sim->stream));
@@ -1143,10 +1132,8 @@ VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t
     CU(sim, cudaMemcpyAsync(sim->pin + 64 + n_parts, sim->gc_totals + 10, 8, cudaMemcpyDeviceToHost, sim->stream));
     CU(sim, cudaStreamSynchronize(sim->stream));
     const uint64_t W = sim->pin[64 + n_parts];
-    g_seg[1] += now_s() - t0; t0 = now_s();
     for (uint32_t k = 0; k < n_parts; k++) words_per_part[k] = sim->pin[64 + k + 1] - sim->pin[64 + k];
     TRY(ensure_buf(sim, sim->mig[4], (W + 1) * 4));
-    g_seg[2] += now_s() - t0; t0 = now_s();
     uint32_t *entries = (uint32_t *)sim->mig[4].p;
     m0 = 0;
     for (uint32_t k = 0; k < n_parts; k++) {
@@ -1154,8 +1141,6 @@ VL_API int vl_migrants_export_device(vl_sim *sim, vl_pop *const *parts, uint32_t
         m0 += parts[k]->n;
     }
     CU(sim, cudaStreamSynchronize(sim->stream));
-    g_seg[3] += now_s() - t0;
-    if (sim->experiment & 8) fprintf(stderr, "export segs (cum s): launch %.4f sync1 %.4f ensure %.4f copy+sync %.4f\n", g_seg[0], g_seg[1], g_seg[2], g_seg[3]);
     image->len_device = len;
     image->raw_device = raw;
     image->entries_device = entries;

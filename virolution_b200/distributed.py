@@ -76,11 +76,7 @@ class GpuCompartment:
         return self.sim.subsample_populations(factors)
 
     def export_parts(self, parts):
-        import os, time
-        t0 = time.perf_counter()
         img, m, w = self.sim.export_migrants(parts)
-        if os.environ.get("VL_TRACE"):
-            self.t_export_c = getattr(self, "t_export_c", 0.0) + time.perf_counter() - t0
         P = int(img.n_providers)
         self.n_providers = P
         M, W = int(img.n_migrants), int(img.n_words)
