@@ -60,3 +60,24 @@ def test_hill_utility_within_tolerance():
     for g in range(c["generations"]):
         helpers.replay_generation(gpu, helpers.oracle_generation(w), 1, rtol=1e-12)
     gpu.close()
+
+
+def test_replay_bitexact_at_1e5():
+    """SURVEY.md Appendix C asks for a 10^5 run besides the K1-size cases: HIV-shaped parameters (hiv.yaml's substitution
+    matrix shape, R0 6, dilution 1) on N = H = 10^5, three replayed generations, host tiles and multi-tile resampling."""
+    from virolution_b200.abi import FitnessProvider, HostSpec, Parameters
+    from virolution_b200.config import exponential_table
+    wt = helpers.random_wildtype(2600, 31)
+    n = 100_000
+    par = Parameters(2e-4, 0.0, n, 6.0, n, 1.0, helpers.HIV_SUBST)
+    tab = exponential_table(wt, rng=np.random.default_rng(32))
+    c = dict(wildtype=wt, parameters=par, specs=[HostSpec(0, n, FitnessProvider("NonEpistatic", table=tab, utility=helpers.ALG))],
+             n0=n, generations=3, seed=33)
+    w = helpers.make_oracle(c)
+    gpu = helpers.make_gpu(c)
+    for g in range(c["generations"]):
+        helpers.replay_generation(gpu, helpers.oracle_generation(w), 1)
+    eo, ep, eb = gpu.export_mutations()
+    oo, op, ob = w.export_mutations()
+    assert np.array_equal(eo, oo) and np.array_equal(ep, op) and np.array_equal(eb, ob)
+    gpu.close()
