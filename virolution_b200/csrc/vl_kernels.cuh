@@ -1653,6 +1653,8 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
 // mode 0: write the haplotype ids of the drawn records to dst; mode 1: write the drawn infectant indices (u64).
 constexpr uint32_t GUIDE_BITS = 11;
 constexpr uint32_t GUIDE_SIZE = 1u << GUIDE_BITS;
+constexpr uint32_t RESAMPLE_DIRECT = 8192;  // largest tile offspring total staged as a direct table (32 KB of shared memory)
+static_assert(RESAMPLE_DIRECT * 4 >= 2 * RESAMPLE_TILE * 4 + GUIDE_SIZE * 2, "the direct table also hosts the CDF, payload and guide arrays");
 // Several parts (subsamples of the same offspring map) are drawn in the same pass: the tile is staged once, every part
 // has its own draw counts, output buffer and Philox stream.
 struct ResampleArgs {
@@ -1661,9 +1663,13 @@ struct ResampleArgs {
     uint32_t *dst[MAX_PARTS];  // nullptr = the population being assembled (hap_id_next)
 };
 __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra, uint64_t *__restrict__ dst64, int mode) {
-    __shared__ uint32_t s_cdf[RESAMPLE_TILE];
-    __shared__ uint32_t s_hap[RESAMPLE_TILE];   // haplotype id (mode 0) or position inside the tile (mode 1)
-    __shared__ uint16_t s_guide[GUIDE_SIZE];
+    // a tile whose offspring total fits RESAMPLE_DIRECT is staged as a direct table: the payload of the record that owns
+    // draw value r sits at s_direct[r], a draw is one lookup.  Larger totals use the compacted CDF + cut-point guide.
+    // Both map a draw value to the same record, so which one a tile takes does not change the result.
+    __shared__ uint32_t s_direct[RESAMPLE_DIRECT];
+    uint32_t *s_cdf = s_direct;                                                   // RESAMPLE_TILE
+    uint32_t *s_hap = s_direct + RESAMPLE_TILE;                                   // RESAMPLE_TILE: haplotype id (mode 0) or position in the tile (mode 1)
+    uint16_t *s_guide = reinterpret_cast<uint16_t *>(s_direct + 2 * RESAMPLE_TILE);  // GUIDE_SIZE
     __shared__ uint32_t s_wsum[TPB / 32], s_wcnt[TPB / 32];
     const uint64_t nt = tile_count(st);
     const uint32_t *__restrict__ offspring = st->offspring;
@@ -1674,16 +1680,18 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
     const uint32_t gen = st->generation;
     const uint64_t stride = st->tile_stride;
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        // the tile's descriptors are independent loads: issue them together, decide afterwards
         uint64_t any = 0;
         for (uint32_t p = 0; p < ra.n_parts; p++) any |= st->tile_cnt[p * stride + tile];
-        if (any == 0) continue;  // uniform across the CTA
-        if (st->tile_sum[tile] > 0xFFFFFFFFull) {  // the tile CDF is 32-bit
-            if (tid == 0) raise(st, DE_OFFSPRING_RANGE);
-            continue;
-        }
+        const uint64_t tsum = st->tile_sum[tile];
         uint64_t start;
         uint32_t tlen;
         tile_range(st, tile, start, tlen);
+        if (any == 0) continue;  // uniform across the CTA
+        if (tsum > 0xFFFFFFFFull) {  // the tile CDF is 32-bit
+            if (tid == 0) raise(st, DE_OFFSPRING_RANGE);
+            continue;
+        }
         if (tlen > RESAMPLE_TILE) {  // cannot happen: host tiles are only declared by a kernel that staged every tile
             if (tid == 0) raise(st, DE_TILE_OVERFLOW);
             continue;
@@ -1719,7 +1727,15 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
         }
         uint32_t cdf = woff + inc - run;   // exclusive prefix of this thread's first item
         uint32_t slot = coff + cinc - nz;  // compacted index of this thread's first non-zero item
+        const bool direct = total <= RESAMPLE_DIRECT;
         const double scale = (double)GUIDE_SIZE / (double)total;
+        if (direct) {
+#pragma unroll
+            for (uint32_t k = 0; k < PER; k++) {
+                for (uint32_t r = cdf; r < cdf + v[k]; r++) s_direct[r] = hp[k];
+                cdf += v[k];
+            }
+        } else
 #pragma unroll
         for (uint32_t k = 0; k < PER; k++) {
             if (!v[k]) continue;
@@ -1761,10 +1777,16 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
                     }
                 }
                 const uint32_t r = (uint32_t)(mm >> 32);
-                uint32_t i = s_guide[x >> (32 - GUIDE_BITS)];
-                while (s_cdf[i] <= r) i++;
-                if (mode == 0) dst[s] = s_hap[i];
-                else dst64[s] = rec[start + s_hap[i]].x;
+                uint32_t payload;
+                if (direct) {
+                    payload = s_direct[r];
+                } else {
+                    uint32_t i = s_guide[x >> (32 - GUIDE_BITS)];
+                    while (s_cdf[i] <= r) i++;
+                    payload = s_hap[i];
+                }
+                if (mode == 0) dst[s] = payload;
+                else dst64[s] = rec[start + payload].x;
             }
         }
         }
