@@ -1408,6 +1408,37 @@ __device__ __forceinline__ void plan_block_scan(const uint64_t *src, uint64_t *d
     __syncthreads();
     if (tid == 0) *s_carry = init;
     __syncthreads();
+    constexpr uint32_t E = 8;  // up to E consecutive elements per thread in ONE round: one latency, one block scan
+    if (nt <= (uint64_t)PLAN_THREADS * E) {
+        const uint64_t per = (nt + PLAN_THREADS - 1) / PLAN_THREADS;
+        const uint64_t lo = per * tid < nt ? per * tid : nt, hi = lo + per < nt ? lo + per : nt;
+        uint64_t x[E], sum = 0;
+#pragma unroll
+        for (uint32_t e = 0; e < E; e++) { x[e] = lo + e < hi ? __ldcg(&src[lo + e]) : 0; sum += x[e]; }
+        uint64_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        if (lane == 31) s_scan[wid] = inc;
+        __syncthreads();
+        uint64_t woff = 0, tot = 0;
+        for (int w = 0; w < PLAN_THREADS / 32; w++) {
+            uint64_t v = s_scan[w];
+            if (w < (int)wid) woff += v;
+            tot += v;
+        }
+        uint64_t run = init + woff + inc - sum;
+#pragma unroll
+        for (uint32_t e = 0; e < E; e++) {
+            if (lo + e < hi) { dst[lo + e] = inclusive ? run + x[e] : run; run += x[e]; }
+        }
+        __syncthreads();
+        if (tid == 0) *s_carry = init + tot;
+        __syncthreads();
+        return;
+    }
     for (uint64_t t0 = 0; t0 < nt; t0 += PLAN_THREADS) {
         const uint64_t t = t0 + tid;
         const uint64_t x = t < nt ? __ldcg(&src[t]) : 0;  // (other CTAs may have added to it: read past L1)
@@ -1440,11 +1471,12 @@ __device__ __forceinline__ void plan_block_scan(const uint64_t *src, uint64_t *d
 // over the tiles as an exact multinomial, every CTA drawing for its own slice of tiles.  Default: Poissonisation —
 // independent N_t ~ Poisson(mu * w_t / W) with mu a few standard deviations below `size` are, given their sum K,
 // Multinomial(K, w/W); the deficit size - K is Poissonised again (same argument, smaller means) until a handful of
-// draws remain, which are made one by one (binary search in the tile prefix) and added: a multinomial plus an
-// independent multinomial with the same cell probabilities is the multinomial of the summed size.  K > size
+// thousand draws remain, which are made one by one (binary search in the tile prefix, spread over all plan threads) and
+// added: a multinomial plus an independent multinomial with the same cell probabilities is the multinomial of the summed size.  K > size
 // (probability ~3e-7 per call) or `force_tree` falls back to walking a segment tree with conditional binomials on
 // CTA 0, which is also exact.  (3) exclusive scan of the per-tile draw counts, slice by slice.
 constexpr int PLAN_CTAS = 16;
+constexpr uint64_t PLAN_FILL_MAX = 32768;  // a deficit up to this many draws is filled draw by draw (two per plan thread), no further stage
 __device__ __forceinline__ void plan_grid_barrier(DevState *st, uint32_t &epoch) {
     __syncthreads();
     epoch += 1;
@@ -1546,7 +1578,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
             uint32_t active = 0;
             for (uint32_t p = 0; p < NP; p++) {
                 const uint64_t size = s_size[p];
-                if (K[p] <= size && size - K[p] > 64) {
+                if (K[p] <= size && size - K[p] > PLAN_FILL_MAX) {
                     const double d = (double)(size - K[p]);
                     if (d - 5.0 * sqrt(d) - 8.0 > 0.0) active |= 1u << p;
                 }
