@@ -259,11 +259,13 @@ __device__ __forceinline__ uint64_t poisson_draw(PhiloxKey key, uint64_t index, 
     return poisson_ptrs(key, index, generation, phase, lambda);
 }
 // The same inversion, decided in f32 whenever that is provably the f64 decision: the search runs on f32 copies of u
-// and of the CDF; the f32 CDF is within 2e-5 of the f64 one for lambda < 12 (expf to 2e-6 relative, <= 64 products
-// and sums at 6e-8 each), so if u stays more than POISSON_GUARD away from every CDF value it is compared with, both
-// searches stop at the same k.  Otherwise (about 2 draws in 1000) the f64 search above decides.  The result is the
+// and of the CDF.  For lambda < 12 and k <= 46 the f32 CDF is within 5e-6 of the f64 one: __expf(-lambda) is good to
+// 1.2e-6 relative (7e-7 from the rounded argument, 5e-7 from ex2.approx), every term multiplies in three roundings
+// (1.8e-7), so a term is good to 4e-6 relative after 16 steps and the terms sum to at most 1; the additions contribute
+// 46 x 6e-8.  If u stays more than POISSON_GUARD away from every CDF value it is compared with, both searches stop at
+// the same k.  Otherwise (about 5 draws in 10^4) the f64 search above decides.  The result is the
 // f64 inversion's for every (u, lambda): vl_test_poisson_fast checks that draw for draw.
-constexpr float POISSON_GUARD = 1.0e-4f;
+constexpr float POISSON_GUARD = 3.0e-5f;  // 6x the 5e-6 bound derived above
 __device__ __forceinline__ uint32_t poisson_inversion_f64(double u, double lambda, const double *rcp) {
     double p = exp(-lambda), cdf = p;
     uint32_t k = 0;
