@@ -807,7 +807,9 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
     const uint32_t smem_tiles = (uint32_t)std::min<uint64_t>(nt_bound, sim->plan_smem_tiles);
     zero_device(sim, (char *)sim->d + FIELD_OFF(plan_sync), 8 + sizeof(((DevState *)0)->plan_acc));
     // a handful of co-resident CTAs: each draws for its slice of tiles, a counter in DevState is the grid barrier
-    const unsigned ctas = (unsigned)std::min<uint64_t>(PLAN_CTAS, std::max<uint64_t>(1, nt_bound / 256));
+    // (enough CTAs for the tiles, and for the draws a small sample makes one by one: two per thread)
+    const uint64_t direct_draws = std::min<uint64_t>(sim->h.max_population, PLAN_FILL_MAX);
+    const unsigned ctas = (unsigned)std::min<uint64_t>(PLAN_CTAS, std::max<uint64_t>(std::max<uint64_t>(1, nt_bound / 256), direct_draws / (2 * PLAN_THREADS)));
     LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, pa, smem_tiles);
     LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, ra, dst64, mode);
     return VL_OK;

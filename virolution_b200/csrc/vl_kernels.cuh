@@ -1556,7 +1556,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
         for (uint32_t p = 0; p < NP; p++) {  // stage 0
             const uint64_t size = s_size[p];
             double mu = (double)size - 5.0 * sqrt((double)size) - 8.0;
-            if (!(mu > 0.0)) mu = 0.0;
+            if (!(mu > 0.0) || size <= PLAN_FILL_MAX) mu = 0.0;  // a small sample is drawn one by one below, no Poissonisation needed
             uint64_t *cnt = st->tile_cnt + p * stride;
             const uint64_t salt = (uint64_t)pa.salt[p] << 48;
             uint64_t mine = 0;

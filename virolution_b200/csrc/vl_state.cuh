@@ -38,6 +38,7 @@ constexpr uint32_t RESAMPLE_TILE = 2048;  // CSR positions per resample tile (on
 constexpr int MAX_PARTS = 16;              // subsamples of one offspring map that one plan + one resample pass can draw together
 constexpr uint32_t HT_MAX_HOSTS = 2048;   // most hosts a host-range tile may span (DevState::host_tiles holds the actual number)
 constexpr uint32_t HT_MIN_HOSTS = 256;    // below this the fused replicate kernel is not worth launching
+constexpr double HT_SPREAD_CTAS = 148.0;  // tiles of a small host population are shrunk until there are about two per SM of a B200
 
 // error bits raised by kernels (sticky until vl_* reports them)
 enum DevError : uint32_t {
@@ -188,7 +189,12 @@ __host__ __device__ inline uint32_t host_tile_size(uint64_t n, uint64_t H) {
     double ht = floor(mean_max * (double)H / (double)(n ? n : 1));
     if (ht > (double)HT_MAX_HOSTS) ht = (double)HT_MAX_HOSTS;
     if (ht > (double)H) ht = (double)H;
-    return ht < (double)HT_MIN_HOSTS ? 0u : (uint32_t)ht;
+    if (ht < (double)HT_MIN_HOSTS) return 0u;
+    // small host populations: rather many small tiles than a handful of full ones (a tile is one CTA; a generation of
+    // 10^4 infectants should still spread over the SMs)
+    const double spread = ceil((double)H / (2.0 * HT_SPREAD_CTAS));
+    if (ht > spread) ht = spread > (double)HT_MIN_HOSTS ? spread : (double)HT_MIN_HOSTS;
+    return (uint32_t)ht;
 }
 
 // ---- resample tiles: a tile is what one CTA stages in shared memory, either RESAMPLE_TILE consecutive CSR positions
