@@ -469,7 +469,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
         size_t free_b = 0, total_b = 0;
         CCU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t P = std::max<uint32_t>(h.n_providers, 1);
-        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 80 + ch * (52 + 32 * P) + ca * 8; };
+        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 80 + ch * (180 + 32 * P) + ca * 8; };
         if (!cfg->capacity_haplotypes || !cfg->capacity_arena_words) {
             for (int it = 0; it < 64 && need(cap_hap, cap_arena) > (uint64_t)(0.7 * (double)free_b); it++) {
                 if (!cfg->capacity_arena_words && cap_arena > (1ull << 20)) cap_arena = cap_arena * 3 / 4;
@@ -497,6 +497,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
     CTRY(dev_alloc(sim, &h.hm, cap_hap)); CTRY(dev_alloc(sim, &h.hm_alt, cap_hap));
+    CTRY(dev_alloc(sim, &h.mh, cap_hap)); CTRY(dev_alloc(sim, &h.mh_alt, cap_hap));
     for (uint32_t p = 0; p < h.n_providers; p++) {
         CTRY(dev_alloc(sim, &h.h_raw[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_raw_alt[p], cap_hap));
         CTRY(dev_alloc(sim, &h.h_fit[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_fit_alt[p], cap_hap));

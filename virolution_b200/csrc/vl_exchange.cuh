@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(TPB) k_ex_import(DevState *st, ExArgs ex, cons
             const uint32_t *src = ex.in[o].entries[par] + (word_off[idx] - word_off[sc->imp_start[o]]);
             uint32_t *dst = st->arena + off;
             for (uint32_t q = 0; q < l; q++) dst[q] = __ldcg(src + q);
+            write_head(st, id, off, l, dst);
         }
         if (slot < cap) st->hap_id_next[slot] = id;
     }

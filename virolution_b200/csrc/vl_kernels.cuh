@@ -43,8 +43,20 @@ __device__ __forceinline__ void set_fitness(DevState *st, uint32_t p, uint64_t i
     st->h_raw[p][id] = raw;
     st->h_fit[p][id] = utility_apply(st->prov[p], raw);
 }
+// the one-line view of record `id` for the mutate kernel (MutHead); `entries` may point anywhere readable
+__device__ __forceinline__ void write_head(DevState *st, uint64_t id, uint64_t off, uint32_t len, const uint32_t *entries) {
+    MutHead h;
+    h.off = off;
+    h.len = len;
+    h.valid = 1u;
+    h.raw0 = st->n_providers ? st->h_raw[0][id] : 1.0;
+#pragma unroll
+    for (uint32_t k = 0; k < HEAD_INLINE; k++) h.inl[k] = k < len ? entries[k] : 0xFFFFFFFFu;
+    st->mh[id] = h;
+}
 __global__ void k_init_wildtype(DevState *st) {  // haplotype 0: no entries, raw fitness = empty product (src/core/fitness/table.rs:72-79)
     for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, 0, 1.0);
+    write_head(st, 0, 0, 0, nullptr);
 }
 __device__ __forceinline__ uint64_t vl_globaltimer() {
     uint64_t t;
@@ -657,6 +669,7 @@ __device__ inline uint32_t make_recombinant(DevState *st, uint32_t left, uint32_
     st->hm[r.id].len = o;
     st->hm[r.id].parent = left;
     for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, r.id, compute_fitness_full(st->prov[p], out, o));
+    write_head(st, r.id, r.off, o, out);
     return r.id;
 }
 
@@ -798,7 +811,8 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
 // patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist.
 constexpr uint32_t MUT_LOCAL_PARENT = 16;  // parent records up to this length are staged in thread-local memory
 constexpr uint32_t MUT_LOCAL_CHANGES = 8;  // mutation events up to this many sites keep their change words there too
-constexpr uint32_t MUT_SCRATCH_STRIDE = MUT_LOCAL_PARENT + MUT_LOCAL_CHANGES + 1;  // odd: consecutive threads hit distinct banks
+constexpr uint32_t MUT_SCRATCH_STRIDE = MUT_LOCAL_PARENT + MUT_LOCAL_CHANGES + HEAD_INLINE + 1;  // odd: consecutive threads hit distinct banks
+static_assert(MUT_SCRATCH_STRIDE % 2 == 1 && HEAD_INLINE <= MUT_LOCAL_PARENT, "scratch layout");
 // parent_in_item: the worklist items carry the infectant's current haplotype id in .w (k_mutcount_fast)
 __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
     __shared__ uint32_t s_scratch[TPB * MUT_SCRATCH_STRIDE];
@@ -814,13 +828,17 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
         const bool active = w < n_list;
         uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32;
         HapMeta pm{0, 0, NONE32};
+        MutHead ph;
+        ph.valid = 0u;
         if (active) {
             const uint4 item = st->mut_list[w];
             i = item.x;
             nm = item.y;
             tpos = item.z;
             pid = parent_in_item ? item.w : st->hap_id[i];
-            pm = st->hm[pid];  // one 16-byte load: arena offset, length, parent
+            ph = st->mh[pid];  // ONE 64-byte line: arena offset, length, raw fitness and the first entries of the parent
+            if (ph.valid) { pm.off = ph.off; pm.len = ph.len; }
+            else pm = st->hm[pid];
             plen = pm.len;
         }
         const uint32_t words = active ? plen + 2 * nm : 0u;
@@ -850,8 +868,13 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
         // every lookup below is then a shared-memory access instead of a dependent trip to L2/HBM (thread-local arrays
         // would be indexed dynamically, i.e. live in local memory and cost L2 write traffic of their own)
         uint32_t *pe_local = s_scratch + threadIdx.x * MUT_SCRATCH_STRIDE, *ch_local = pe_local + MUT_LOCAL_PARENT;
+        uint32_t *hd_local = ch_local + MUT_LOCAL_CHANGES;  // the first entries of the new record, for its own head
         const uint32_t *pe = st->arena + pm.off;
-        if (plen <= MUT_LOCAL_PARENT) {
+        if (ph.valid && plen <= HEAD_INLINE) {  // the parent's entries came with its head: no arena read at all
+#pragma unroll
+            for (uint32_t k = 0; k < HEAD_INLINE; k++) pe_local[k] = ph.inl[k];
+            pe = pe_local;
+        } else if (plen <= MUT_LOCAL_PARENT) {
 #pragma unroll
             for (uint32_t k = 0; k < MUT_LOCAL_PARENT; k++) pe_local[k] = k < plen ? pe[k] : 0xFFFFFFFFu;
             pe = pe_local;
@@ -893,7 +916,9 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
             uint32_t pa = a < plen ? entry_pos(pe[a]) : 0xFFFFFFFFu;
             uint32_t pb = b < nm ? ch_pos(chs[b]) : 0xFFFFFFFFu;
             if (pa < pb) {
-                out[o++] = pe[a++];
+                const uint32_t e = pe[a++];
+                if (o < HEAD_INLINE) hd_local[o] = e;
+                out[o++] = e;
             } else {
                 const uint32_t first_to = ch_to(chs[b]);
                 uint32_t last_to = first_to;
@@ -901,14 +926,19 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
                 if (pa == pb) a++;
                 const uint32_t w0 = wt[pb];
                 const uint32_t m = (last_to == w0) ? 4u : last_to;
-                if (!(first_to == w0 && m == 4u)) out[o++] = make_entry(pb, first_to, m);
+                if (!(first_to == w0 && m == 4u)) {
+                    const uint32_t e = make_entry(pb, first_to, m);
+                    if (o < HEAD_INLINE) hd_local[o] = e;
+                    out[o++] = e;
+                }
             }
         }
+        double raw0_new = 1.0;
         for (uint32_t p = 0; p < st->n_providers; p++) {
             const DevProvider &pr = st->prov[p];
             double raw = 1.0;
             if (pr.kind != VL_FITNESS_NEUTRAL) {
-                const double praw = st->h_raw[p][pid];
+                const double praw = (p == 0 && ph.valid) ? ph.raw0 : st->h_raw[p][pid];
                 double acc = 1.;
                 for (uint32_t k = 0; k < nm; k++) {
                     const uint64_t row = (uint64_t)ch_pos(chs[k]) * 4;
@@ -918,6 +948,17 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
                 raw = praw * acc;
             }
             set_fitness(st, p, new_id, raw);
+            if (p == 0) raw0_new = raw;
+        }
+        {
+            MutHead nh;
+            nh.off = roff;
+            nh.len = o;
+            nh.valid = 1u;
+            nh.raw0 = raw0_new;
+#pragma unroll
+            for (uint32_t k = 0; k < HEAD_INLINE; k++) nh.inl[k] = k < o ? hd_local[k] : 0xFFFFFFFFu;
+            st->mh[new_id] = nh;
         }
         st->hm[new_id] = HapMeta{roff, o, pid};
         st->hap_id[i] = new_id;
@@ -1877,6 +1918,11 @@ __global__ void __launch_bounds__(TPB) k_gc_copy(DevState *st) {
         const uint32_t *src = st->arena + st->hm[h].off;
         uint32_t *dst = st->arena_alt + noff;
         for (uint32_t k = 0; k < len; k++) dst[k] = src[k];
+        {
+            MutHead mh = st->mh[h];
+            mh.off = noff;
+            st->mh_alt[nid] = mh;
+        }
         st->hm_alt[nid].off = noff;
         st->hm_alt[nid].len = len;
         const uint32_t par = st->hm[h].parent;
@@ -1895,7 +1941,7 @@ __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
     st->n_hap = gc_totals[0];
     st->arena_top = gc_totals[1];
 #define VL_SWAP(a, b) { auto t = st->a; st->a = st->b; st->b = t; }
-    VL_SWAP(hm, hm_alt) VL_SWAP(arena, arena_alt)
+    VL_SWAP(hm, hm_alt) VL_SWAP(mh, mh_alt) VL_SWAP(arena, arena_alt)
     for (uint32_t p = 0; p < st->n_providers; p++) { VL_SWAP(h_raw[p], h_raw_alt[p]) VL_SWAP(h_fit[p], h_fit_alt[p]) }
 #undef VL_SWAP
     st->gc_runs += 1;

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(TPB) k_unpack(DevState *st, const uint8_t *__r
             st->hm[id].len = i_len[u];
             st->hm[id].parent = NONE32;
             for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, id, i_raw[(uint64_t)p * hd.n_unique + u]);
+            write_head(st, id, a0 + i_off[u], i_len[u], i_ent + i_off[u]);
         }
         for (uint64_t w = tid; w < hd.n_words; w += span) st->arena[a0 + w] = i_ent[w];
     }
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(TPB) k_mig_import(DevState *st, const uint32_t
         const uint32_t *src = entries_in + word_off[i];
         uint32_t *dst = st->arena + off;
         for (uint32_t k = 0; k < l; k++) dst[k] = src[k];
+        write_head(st, id, off, l, src);
         ids_out[i] = (uint32_t)id;
     }
 }

@@ -66,12 +66,11 @@ struct Philox {
     PhiloxKey key;
     uint64_t index;
     uint32_t generation, phase, blk;
-    uint32_t out[4];
+    uint4 out;  // (selected by comparisons, never indexed: the generator stays in registers)
     int have;
 
     __host__ __device__ inline void block() {
-        uint4 b = philox_block(key, index, generation, phase, blk);
-        out[0] = b.x; out[1] = b.y; out[2] = b.z; out[3] = b.w;
+        out = philox_block(key, index, generation, phase, blk);
         blk += 1;  // low 24 bits of the last counter word count blocks within a stream
         have = 4;
     }
@@ -80,7 +79,9 @@ struct Philox {
         : key(philox_key(seed, compartment)), index(index_), generation(generation_), phase(phase_), blk(first_block), have(0) {}
     __host__ __device__ inline uint32_t u32() {
         if (have == 0) block();
-        return out[4 - (have--)];
+        const uint32_t r = have == 4 ? out.x : have == 3 ? out.y : have == 2 ? out.z : out.w;
+        have -= 1;
+        return r;
     }
     __host__ __device__ inline uint64_t u64() {
         uint64_t lo = u32();

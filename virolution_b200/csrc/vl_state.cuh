@@ -89,6 +89,20 @@ struct alignas(16) HapMeta {
     uint32_t parent; // id of the haplotype it was derived from (NONE32 for the wildtype / migrants)
 };
 
+// What k_mutate needs of a parent, gathered into ONE 64-byte line: metadata, raw fitness under provider 0 and the first
+// entries of the flattened record.  hm / h_raw / arena stay the source of truth (every other kernel reads those); this
+// is a cache that turns the four dependent random reads per mutation (metadata, raw fitness, one or two arena lines)
+// into one.  `valid` is written by whoever creates the record.
+constexpr uint32_t HEAD_INLINE = 10;
+struct alignas(64) MutHead {
+    uint64_t off;
+    uint32_t len;
+    uint32_t valid;
+    double raw0;
+    uint32_t inl[HEAD_INLINE];
+};
+static_assert(sizeof(MutHead) == 64, "one line per haplotype");
+
 struct DevState {
     // ---- configuration (BasicHost.parameters are the values captured at vl_create, the simulation's
     //      are updatable through vl_set_parameters; src/simulation.rs:41-52 vs :351-363)
@@ -168,6 +182,7 @@ struct DevState {
     uint32_t gc_active;
     uint32_t _pad1;
     HapMeta *hm, *hm_alt;  // 16 bytes per haplotype: arena offset, length, parent
+    MutHead *mh, *mh_alt;  // 64 bytes per haplotype: the mutate kernel's one-line view of a parent
     double *h_raw[MAX_PROVIDERS], *h_raw_alt[MAX_PROVIDERS];  // memoised raw fitness per provider
     double *h_fit[MAX_PROVIDERS], *h_fit_alt[MAX_PROVIDERS];  // utility(raw): what readers of get_or_compute see (attributes.rs:220-241)
     uint32_t *arena, *arena_alt;
