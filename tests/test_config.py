@@ -108,3 +108,29 @@ schedule:
     assert specs[0].infective is None
     assert np.array_equal(schedule.get_transfer_matrix(7), np.array([[0.9, 0.1], [0.1, 0.9]]))
     assert schedule.get_sample_size(400) == 1000 and schedule.get_sample_size(401) == 0
+
+
+def test_load_parameters_single_block(tmp_path):
+    """Parameters::read_from_file (src/config/parameters.rs:182-186): what a `settings` event points to."""
+    from virolution_b200.config import load_parameters
+    p = tmp_path / "p.yaml"
+    p.write_text("""mutation_rate: 2e-6
+recombination_rate: 1e-4
+host_population_size: 777
+basic_reproductive_number: 50.0
+max_population: 555
+dilution: 0.5
+n_hits: 3
+substitution_matrix:
+  - [0.0, 1.0, 2.0, 1.0]
+  - [1.0, 0.0, 1.0, 1.0]
+  - [1.0, 1.0, 0.0, 1.0]
+  - [1.0, 1.0, 1.0, 0.0]
+host_model: !SingleHost
+  reproductive:
+    distribution: !Neutral
+""")
+    par = load_parameters(str(p))
+    assert (par.mutation_rate, par.recombination_rate, par.host_population_size, par.basic_reproductive_number,
+            par.max_population, par.dilution, par.n_hits) == (2e-6, 1e-4, 777, 50.0, 555, 0.5, 3)
+    assert par.substitution_matrix[0][2] == 2.0

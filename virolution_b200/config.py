@@ -244,9 +244,20 @@ class Schedule:
 
 # ------------------------------------------------------------------------- YAML settings (config/settings.rs)
 
+def load_parameters(path: str) -> Parameters:
+    """Parameters::read_from_file (src/config/parameters.rs:182-186): ONE parameter block as a YAML document — what a
+    `settings` event of the schedule points to (src/config/schedule.rs:210-222).  Only the numeric parameters reach the
+    simulation (set_parameters, src/simulation.rs:355-363): host specs and providers are built once, at start-up."""
+    return _load(path, single=True)
+
+
 def load_settings(path: str):
     """Settings{parameters: Vec<Parameters>, schedule} from the reference's YAML dialect (serde tags
     !SingleHost / !MultiHost / !Exponential / !Lognormal / !File / !Epistatic / !Algebraic / !Hill / !Neutral)."""
+    return _load(path, single=False)
+
+
+def _load(path: str, single: bool):
     import yaml
 
     class _Tagged(dict):
@@ -292,7 +303,7 @@ def load_settings(path: str):
         return HostFitness(model(h.get("reproductive")), model(h.get("infective")))
 
     params, host_models = [], []
-    plist = doc["parameters"]
+    plist = [doc] if single else doc["parameters"]
     for p in plist:
         hm = p["host_model"]
         if hm.tag == "SingleHost":
@@ -304,6 +315,8 @@ def load_settings(path: str):
                                  int(p["host_population_size"]), float(p["basic_reproductive_number"]),
                                  int(p["max_population"]), float(p["dilution"]), p["substitution_matrix"],
                                  int(p.get("n_hits", 1))))
+    if single:
+        return params[0]
     schedule = Schedule([ScheduleRecord(str(r["generation"]), str(r["event"]), str(r["value"]))
                          for r in doc.get("schedule", [])])
     return params, host_models, schedule

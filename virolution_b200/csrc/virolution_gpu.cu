@@ -587,6 +587,7 @@ VL_API int vl_set_parameters(vl_sim *sim, const vl_parameters *p) {
     TRY(push_population_pointers(sim));
     sim->csr_valid = false;
     sim->bucket_pending = false;
+    if (sim->gen_graph) { cudaGraphExecDestroy(sim->gen_graph); sim->gen_graph = nullptr; }  // captured with the old parameters
     return VL_OK;
 }
 static int population_len(vl_sim *sim, uint64_t *out) {

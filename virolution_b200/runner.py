@@ -1,6 +1,7 @@
 """Host-side mirror of `Runner` (src/runner.rs) for the GPU path: the generation loop of the parallel build
 (src/runner.rs:336-423) over `GpuSimulation` handles, with the outputs the reference's integration tests look for —
-`<provider>_table.npy`, `virolution.log`, `sample_<generation>_<compartment>.csv`, `final.<i>.csv`
+`<provider>_table.npy`, `virolution.log`, `samples/sample_<generation>_<compartment>.{fasta,csv}`,
+`samples/barcodes.csv`, `final.<i>.csv`
 (src/main.rs:63-154, src/runner.rs:137-152,230-240, src/readwrite/sample_writer.rs:29-61,243-263).
 
 Everything that costs time stays on the device: one `vl_step` per generation (infect, mutate, replicate, the
@@ -18,7 +19,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .config import load_settings, read_fasta_wildtype
+from .config import load_parameters, load_settings, read_fasta_wildtype
 from .simulation import GpuSimulation, step
 
 LETTERS = "ATCG"
@@ -46,14 +47,23 @@ class GpuRunner:
 
     def __init__(self, settings: str, sequence, generations: int = 200, n_compartments: int = 1, outdir: str = ".",
                  initial_population_size: Optional[int] = None, seed: int = 0, device: int = 0, table_seed: int = 0,
-                 logfile: str = "virolution.log"):
+                 logfile: str = "virolution.log", name: str = "simulation", sampling_format: str = "fasta"):
         self.wildtype = read_fasta_wildtype(sequence) if isinstance(sequence, str) else np.asarray(sequence, dtype=np.uint8)
         self.parameters, self.host_models, self.schedule = load_settings(settings)
         if not self.schedule.check_transfer_table_sizes(n_compartments):
             # Runner::new (src/runner.rs:78-85)
             raise ValueError("Transfer tables are too small for the number of compartments.")
         self.generations, self.n_compartments, self.outdir = generations, n_compartments, outdir
+        self.settings_dir = os.path.dirname(os.path.abspath(settings))
+        if sampling_format not in ("fasta", "csv"):
+            raise ValueError("Unknown sampling format.")  # src/runner.rs:329-332
+        self.name, self.sampling_format = name, sampling_format
         os.makedirs(outdir, exist_ok=True)
+        # SampleWriter::init_barcode_file (src/readwrite/sample_writer.rs:75-86): <outdir>/samples/barcodes.csv, truncated
+        self.samples_dir = os.path.join(outdir, "samples")
+        os.makedirs(self.samples_dir, exist_ok=True)
+        with open(os.path.join(self.samples_dir, "barcodes.csv"), "w", newline="") as f:
+            csv.writer(f, lineterminator="\n").writerow(["barcode", "experiment", "time", "replicate", "compartment"])
         par = self.parameters[0]
         base = os.path.dirname(os.path.abspath(settings))
         # the reference's table generator is unseeded; here the tables come from `table_seed`
@@ -102,18 +112,36 @@ class GpuRunner:
 
     def write_sample(self, generation: int, sample_size: int, rng: np.random.Generator):
         """SampleWriter::sample_from_simulations (src/readwrite/sample_writer.rs:29-61): `choose_multiple` = a uniform
-        sample without replacement of min(size, n) infectants (src/core/population.rs:353-370)."""
+        sample without replacement of min(size, n) infectants (src/core/population.rs:353-370), written as
+        samples/sample_<generation>_<compartment>.{fasta,csv} plus one line of samples/barcodes.csv (src/barcode.rs)."""
         for c, sim in enumerate(self.sims):
             n = sim.population_len()
             idx = rng.choice(n, size=min(sample_size, n), replace=False) if n else np.zeros(0, dtype=np.int64)
             g = sim.get_generation()
-            with open(os.path.join(self.outdir, f"sample_{g}_{c}.csv"), "w", newline="") as f:
-                w = csv.writer(f)
-                w.writerow(["block_id", "compartment_id", "generation", "haplotype", "count"])
-                for hid, text, count in self._rows(sim, idx):
-                    w.writerow([block_id(hid), c, g, text, count])
-            with open(os.path.join(self.outdir, "barcodes.csv"), "a", newline="") as f:
-                csv.writer(f).writerow([f"sample_{g}_{c}", "simulation", g, 0, c])
+            barcode = f"sample_{g}_{c}"
+            if self.sampling_format == "csv":
+                # CsvSampleWriter::write (:228-266): one row per distinct haplotype of the sample
+                with open(os.path.join(self.samples_dir, f"{barcode}.csv"), "w", newline="") as f:
+                    w = csv.writer(f, lineterminator="\n")
+                    w.writerow(["block_id", "compartment_id", "generation", "haplotype", "count"])
+                    for hid, text, count in self._rows(sim, idx):
+                        w.writerow([block_id(hid), c, g, text, count])
+            else:
+                # FastaSampleWriter::write (:161-208): one record per sampled infectant, the whole sequence on one line
+                # (Haplotype::get_sequence, src/core/haplotype.rs:410-419: wildtype overwritten by get_mutations())
+                ids = sim.get_haplotype_ids()
+                off, pos, base = sim.export_mutations()
+                letters = np.frombuffer(LETTERS.encode(), dtype=np.uint8)
+                wt = letters[self.wildtype]
+                with open(os.path.join(self.samples_dir, f"{barcode}.fasta"), "wb") as f:
+                    for k, i in enumerate(idx):
+                        seq = wt.copy()
+                        a, b = int(off[i]), int(off[i + 1])
+                        seq[pos[a:b]] = letters[base[a:b]]
+                        f.write(f">sequence_id={k};block_id={block_id(int(ids[i]))};compartment_id={c};generation={g}\n".encode())
+                        f.write(seq.tobytes() + b"\n")
+            with open(os.path.join(self.samples_dir, "barcodes.csv"), "a", newline="") as f:
+                csv.writer(f, lineterminator="\n").writerow([barcode, self.name, g, 0, c])
 
     def finish(self):
         """Runner::finish (src/runner.rs:137-152): final.<compartment>.csv with header haplotype,count."""
@@ -124,6 +152,52 @@ class GpuRunner:
                 for _, text, count in self._rows(sim):
                     w.writerow([text, count])
         self.log.close()
+
+    # ------------------------------------------------------------------ schedule events other than transmission / sample
+    def adjust_settings(self, generation: int):
+        """`settings` event (src/runner.rs:373-379, src/config/schedule.rs:210-222): the value is the path of a YAML file
+        holding one parameter block; every compartment gets it.  A file that cannot be read is reported and skipped, as
+        `get_settings` does (`.ok()`)."""
+        value = self.schedule.get_event_value("settings", generation)
+        if value is None:
+            return None
+        path = value if os.path.isabs(value) or os.path.exists(value) else os.path.join(self.settings_dir, value)
+        try:
+            parameters = load_parameters(path)
+        except Exception as err:
+            self.log.write(f"Error reading settings file `{value}`: {err!r}\n")
+            return None
+        self.log.write(f"Adjust settings to:\n{parameters}\n")
+        for sim in self.sims:
+            sim.set_parameters(parameters)
+        return parameters
+
+    def collect_stats(self, generation: int):
+        """`stats` event (src/runner.rs:634-673; only the serial build of the reference has it): comma-separated list of
+        diversity / average-fitness / distance, computed on the offspring-producing population of this generation with
+        device reductions (src/stats/population.rs:13-75) and written to the log in the reference's wording."""
+        stats = self.schedule.get_event_value("stats", generation)
+        out = {}
+        for stat in (stats.split(",") if stats else []):
+            if stat == "diversity":
+                out["frequencies"] = [sim.frequencies().reshape(-1, 4) for sim in self.sims]
+                for idx, freq in enumerate(out["frequencies"]):
+                    self.log.write(f"({idx})frequencies={np.array2string(freq, precision=3, threshold=64)}\n")
+            elif stat == "average-fitness":
+                out["mean"] = []
+                for idx, sim in enumerate(self.sims):
+                    self.log.write(f"compartment={idx}\n")
+                    for s, spec in enumerate(self.specs):
+                        for which, (name, prov) in enumerate((("reproductive_fitness", spec.reproductive), ("infective_fitness", spec.infective))):
+                            if prov is None:
+                                continue
+                            mean = sim.mean_fitness(s, which)
+                            out["mean"].append((idx, s, name, mean))
+                            self.log.write(f"mean({name}_{s})={mean}\n")
+            elif stat == "distance":
+                out["distance"] = [a.distance(b) for a in self.sims for b in self.sims]
+                self.log.write(f"distance={out['distance']}\n")
+        return out
 
     # ------------------------------------------------------------------ the loop
     def start(self, sample_seed: int = 0):
@@ -137,6 +211,8 @@ class GpuRunner:
                 self.write_sample(generation, sample_size, rng)
             if generation == self.generations:
                 break
+            self.adjust_settings(generation)
+            self.collect_stats(generation)
             self.infectant_generations += sum(sizes)
             # increment_generation, infect, mutate_infectants, replicate_infectants and the transmission block of every
             # compartment (src/runner.rs:382-422) as one call; T = schedule.get_transfer_matrix(generation), row = target
@@ -161,8 +237,12 @@ def main(argv=None):
     ap.add_argument("--initial-population-size", type=int, default=None)
     ap.add_argument("--seed", type=int, default=0, help="the reference has no seed (rand::rng()); this one is ours")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--name", default="simulation")
+    ap.add_argument("--sampling-format", default="fasta", choices=["fasta", "csv"])
+    ap.add_argument("--logfile", default="virolution.log")
     a = ap.parse_args(argv)
-    r = GpuRunner(a.settings, a.sequence, a.generations, a.n_compartments, a.outdir, a.initial_population_size, a.seed, a.device)
+    r = GpuRunner(a.settings, a.sequence, a.generations, a.n_compartments, a.outdir, a.initial_population_size, a.seed, a.device,
+                  logfile=a.logfile, name=a.name, sampling_format=a.sampling_format)
     r.start()
     print(f"{r.infectant_generations} infectant-generations; outputs in {a.outdir}")
     r.close()
