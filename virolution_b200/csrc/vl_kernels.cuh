@@ -814,15 +814,20 @@ constexpr uint32_t MUT_LOCAL_CHANGES = 8;  // mutation events up to this many si
 constexpr uint32_t MUT_SCRATCH_STRIDE = MUT_LOCAL_PARENT + MUT_LOCAL_CHANGES + HEAD_INLINE + 1;  // odd: consecutive threads hit distinct banks
 static_assert(MUT_SCRATCH_STRIDE % 2 == 1 && HEAD_INLINE <= MUT_LOCAL_PARENT, "scratch layout");
 // parent_in_item: the worklist items carry the infectant's current haplotype id in .w (k_mutcount_fast)
-__global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
+__global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
     __shared__ uint32_t s_scratch[TPB * MUT_SCRATCH_STRIDE];
     const uint32_t n_list = st->n_mut_list;
     const uint32_t L = st->L;
     const uint8_t *__restrict__ wt = st->wildtype;
     const uint32_t span = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31;
-    // every warp walks the worklist 32 items at a time: record ids and arena words are reserved per warp (two atomics
-    // per 32 records, no CTA-wide barrier anywhere in this kernel)
+    // Every warp walks the worklist 32 items at a time.  Same-address atomics are served one after the other by L2, so
+    // none is spent per record or per 32 records: a record's id is its worklist position behind the record count the
+    // kernel started with (published by the last CTA to leave), and arena words come out of a chunk the warp reserves
+    // for all the rounds it still has to do (12.5 % slack; what is left over is reclaimed by the next compaction).
+    const unsigned long long id_base = st->n_hap;
+    unsigned long long chunk_off = 0;
+    uint32_t chunk_left = 0;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_list; base += span) {
         const uint32_t w = base + lane;
         const bool active = w < n_list;
@@ -849,17 +854,19 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
             if (lane >= (uint32_t)d) inc += y;
         }
         const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
-        unsigned long long abase = 0, ibase = 0;
-        if (lane == 0) {
-            abase = atomicAdd(&st->arena_top, (unsigned long long)wtot);
-            ibase = atomicAdd(&st->n_hap, (unsigned long long)__popc(amask));
+        if (wtot > chunk_left) {  // (warp-uniform)
+            const uint32_t rounds = (n_list - base + span - 1) / span;
+            const unsigned long long want = (unsigned long long)wtot * rounds + ((unsigned long long)wtot * rounds >> 3) + 32u;
+            chunk_left = (uint32_t)(want < 0xFFFFFFFFull ? want : (unsigned long long)wtot);
+            if (lane == 0) chunk_off = atomicAdd(&st->arena_top, (unsigned long long)chunk_left);
+            chunk_off = __shfl_sync(0xFFFFFFFFu, chunk_off, 0);
         }
-        abase = __shfl_sync(0xFFFFFFFFu, abase, 0);
-        ibase = __shfl_sync(0xFFFFFFFFu, ibase, 0);
+        const unsigned long long abase = chunk_off;
+        chunk_off += wtot;
+        chunk_left -= wtot;
         if (!active) continue;
         const uint64_t roff = abase + (inc - words);
-        const uint64_t id64 = ibase + __popc(amask & ((1u << lane) - 1u));
+        const uint64_t id64 = id_base + w;
         if (id64 >= st->cap_hap) { raise(st, DE_HAP_CAPACITY); continue; }
         if (roff + words > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); continue; }
         const uint32_t new_id = (uint32_t)id64;
@@ -971,6 +978,15 @@ __global__ void __launch_bounds__(TPB) k_mutate(DevState *st, ReplayMut rp, int 
                 for (uint32_t q = sb; q < se; q++)
                     if (st->rec[q].x == i) { st->rec[q].y = new_id; break; }
             }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&st->mut_ctas_done, 1u) == gridDim.x - 1) {
+            const unsigned long long top = id_base + n_list;
+            st->n_hap = top < st->cap_hap ? top : st->cap_hap;
+            st->mut_ctas_done = 0;
         }
     }
 }

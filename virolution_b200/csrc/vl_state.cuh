@@ -153,6 +153,7 @@ struct DevState {
     // ---- mutation worklist
     uint4 *mut_list;       // (infectant index, n_mut, position in the bucket-partitioned records, -) where n_mut > 0
     uint32_t n_mut_list;
+    uint32_t mut_ctas_done;  // CTAs of the running k_mutate that have left (the last one publishes n_hap)
     uint32_t _pad0;
     BinvConst binv;        // Binomial(L, mu) inversion constants (captured BasicHost parameters)
 
