@@ -1735,15 +1735,21 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
     if (lead && tid == 0) st->dbg[4] = vl_globaltimer();
 }
 
-// One CTA per tile of CSR positions.  The tile's records with offspring > 0 are compacted into shared memory as
-// an inclusive CDF (u32) plus their haplotype ids; a guide table maps the top 11 bits of a draw's random word
-// to the first CDF entry that can contain it (cut-point method), so a draw costs one guide lookup and ~1-2 CDF
-// probes instead of a binary search.  One Philox block serves four consecutive output slots.  No global gathers.
+// One CTA per tile of CSR positions.  The tile's records with offspring > 0 are compacted into shared memory (payload =
+// haplotype id or position); a draw value r in [0, total) belongs to the record whose run [lo, hi) of the offspring CDF
+// contains it.  Two ways to find it, same answer (so which one a tile takes does not change the result):
+//  - rank select (totals up to RESAMPLE_RANK_MAX, every K configuration): a bit mask over the draw values has a bit at
+//    every run start; the record of r is the number of set bits at or below r, i.e. one mask word, one per-word prefix
+//    count and a popc.  Building it costs one shared atomicOr per record — nothing per offspring;
+//  - compacted inclusive CDF + cut-point guide table on the top 11 bits of the random word (one guide lookup and ~1-2
+//    CDF probes) for larger totals.
+// One Philox block serves four consecutive output slots.  No global gathers.
 // mode 0: write the haplotype ids of the drawn records to dst; mode 1: write the drawn infectant indices (u64).
 constexpr uint32_t GUIDE_BITS = 11;
 constexpr uint32_t GUIDE_SIZE = 1u << GUIDE_BITS;
-constexpr uint32_t RESAMPLE_DIRECT = 8192;  // largest tile offspring total staged as a direct table (32 KB of shared memory)
-static_assert(RESAMPLE_DIRECT * 4 >= 2 * RESAMPLE_TILE * 4 + GUIDE_SIZE * 2, "the direct table also hosts the CDF, payload and guide arrays");
+constexpr uint32_t RESAMPLE_RANK_MAX = 32768;  // largest tile offspring total served by the bit mask (4 KB of shared memory)
+constexpr uint32_t RANK_WORDS = RESAMPLE_RANK_MAX / 32;
+static_assert(RANK_WORDS % TPB == 0, "every thread owns RANK_WORDS / TPB consecutive mask words");
 // Several parts (subsamples of the same offspring map) are drawn in the same pass: the tile is staged once, every part
 // has its own draw counts, output buffer and Philox stream.
 struct ResampleArgs {
@@ -1751,14 +1757,13 @@ struct ResampleArgs {
     uint32_t salt[MAX_PARTS];
     uint32_t *dst[MAX_PARTS];  // nullptr = the population being assembled (hap_id_next)
 };
-__global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra, uint64_t *__restrict__ dst64, int mode) {
-    // a tile whose offspring total fits RESAMPLE_DIRECT is staged as a direct table: the payload of the record that owns
-    // draw value r sits at s_direct[r], a draw is one lookup.  Larger totals use the compacted CDF + cut-point guide.
-    // Both map a draw value to the same record, so which one a tile takes does not change the result.
-    __shared__ uint32_t s_direct[RESAMPLE_DIRECT];
-    uint32_t *s_cdf = s_direct;                                                   // RESAMPLE_TILE
-    uint32_t *s_hap = s_direct + RESAMPLE_TILE;                                   // RESAMPLE_TILE: haplotype id (mode 0) or position in the tile (mode 1)
-    uint16_t *s_guide = reinterpret_cast<uint16_t *>(s_direct + 2 * RESAMPLE_TILE);  // GUIDE_SIZE
+__global__ void __launch_bounds__(TPB, 4) k_resample(DevState *st, ResampleArgs ra, uint64_t *__restrict__ dst64, int mode) {
+    __shared__ uint32_t s_hap[RESAMPLE_TILE];   // compacted payloads: haplotype id (mode 0) or position in the tile (mode 1)
+    __shared__ uint32_t s_cdf[RESAMPLE_TILE];   // compacted inclusive CDF (guide path only)
+    __shared__ uint16_t s_guide[GUIDE_SIZE];
+    __shared__ uint32_t s_mask[RANK_WORDS + 1];
+    __shared__ uint16_t s_pre[RANK_WORDS];      // set bits in the mask words before this one
+    __shared__ uint32_t s_wbits[TPB / 32];
     __shared__ uint32_t s_wsum[TPB / 32], s_wcnt[TPB / 32];
     const uint64_t nt = tile_count(st);
     const uint32_t *__restrict__ offspring = st->offspring;
@@ -1776,6 +1781,11 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
         uint64_t start;
         uint32_t tlen;
         tile_range(st, tile, start, tlen);
+        // the range of the tile this CTA takes next: asked for now, used at the bottom of the loop to pull that tile's
+        // offspring counts and records towards L2 while this tile's draws are written
+        uint64_t next_start = 0;
+        uint32_t next_len = 0;
+        if (tile + gridDim.x < nt) tile_range(st, tile + gridDim.x, next_start, next_len);
         if (any == 0) continue;  // uniform across the CTA
         if (tsum > 0xFFFFFFFFull) {  // the tile CDF is 32-bit
             if (tid == 0) raise(st, DE_OFFSPRING_RANGE);
@@ -1793,8 +1803,8 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
             const uint64_t p = p0 + k;
             const bool in = tid * PER + k < tlen;
             v[k] = in ? offspring[p] : 0u;
-            hp[k] = 0;
-            if (in && v[k]) hp[k] = mode == 0 ? rec[p].y : (uint32_t)(p - start);
+            // (asked for whether or not the record has offspring: the sector comes anyway, and the load does not wait for v)
+            hp[k] = !in ? 0u : mode == 0 ? rec[p].y : (uint32_t)(p - start);
         }
         uint32_t run = 0, nz = 0;
 #pragma unroll
@@ -1806,6 +1816,9 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
             if (lane >= (uint32_t)d) { inc += y; cinc += z; }
         }
         if (lane == 31) { s_wsum[wid] = inc; s_wcnt[wid] = cinc; }
+        constexpr uint32_t WPT = RANK_WORDS / TPB;  // mask words per thread
+#pragma unroll
+        for (uint32_t k = 0; k < WPT; k++) s_mask[tid * WPT + k] = 0u;
         __syncthreads();
         uint32_t woff = 0, total = 0, coff = 0;
 #pragma unroll
@@ -1816,14 +1829,35 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
         }
         uint32_t cdf = woff + inc - run;   // exclusive prefix of this thread's first item
         uint32_t slot = coff + cinc - nz;  // compacted index of this thread's first non-zero item
-        const bool direct = total <= RESAMPLE_DIRECT;
+        const bool direct = total <= RESAMPLE_RANK_MAX;
         const double scale = (double)GUIDE_SIZE / (double)total;
         if (direct) {
 #pragma unroll
             for (uint32_t k = 0; k < PER; k++) {
-                for (uint32_t r = cdf; r < cdf + v[k]; r++) s_direct[r] = hp[k];
+                if (!v[k]) continue;
+                atomicOr(&s_mask[cdf >> 5], 1u << (cdf & 31));
+                s_hap[slot++] = hp[k];
                 cdf += v[k];
             }
+            __syncthreads();
+            // set bits before every mask word: per-thread popc, warp scan, warp totals
+            uint32_t bits[WPT], mine = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < WPT; k++) { bits[k] = __popc(s_mask[tid * WPT + k]); mine += bits[k]; }
+            uint32_t binc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, binc, d);
+                if (lane >= (uint32_t)d) binc += y;
+            }
+            if (lane == 31) s_wbits[wid] = binc;
+            __syncthreads();
+            uint32_t before = binc - mine;
+#pragma unroll
+            for (int w = 0; w < TPB / 32; w++)
+                if (w < (int)wid) before += s_wbits[w];
+#pragma unroll
+            for (uint32_t k = 0; k < WPT; k++) { s_pre[tid * WPT + k] = (uint16_t)before; before += bits[k]; }
         } else
 #pragma unroll
         for (uint32_t k = 0; k < PER; k++) {
@@ -1868,7 +1902,8 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
                 const uint32_t r = (uint32_t)(mm >> 32);
                 uint32_t payload;
                 if (direct) {
-                    payload = s_direct[r];
+                    const uint32_t upto = s_mask[r >> 5] & (0xFFFFFFFFu >> (31 - (r & 31)));  // run starts at or below r in its word
+                    payload = s_hap[(uint32_t)s_pre[r >> 5] + __popc(upto) - 1u];
                 } else {
                     uint32_t i = s_guide[x >> (32 - GUIDE_BITS)];
                     while (s_cdf[i] <= r) i++;
@@ -1878,6 +1913,13 @@ __global__ void __launch_bounds__(TPB) k_resample(DevState *st, ResampleArgs ra,
                 else dst64[s] = rec[start + payload].x;
             }
         }
+        }
+        if (tid * 8u < next_len) {  // 32 bytes of offspring counts and 64 bytes of records per thread
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(offspring + next_start + tid * 8u));
+            if (mode == 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + next_start + tid * 8u));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + next_start + tid * 8u + 4u));
+            }
         }
         __syncthreads();
     }
