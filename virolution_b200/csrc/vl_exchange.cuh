@@ -83,9 +83,11 @@ __global__ void __launch_bounds__(TPB) k_ex_lens(DevState *st, ExArgs ex, const 
         const uint32_t t = ex_find(sc->part_start, ex.world, idx);
         const uint64_t k = idx - sc->part_start[t];
         const uint32_t id = ex.part[t][k];
-        const uint32_t len = id == 0 ? 0u : st->hm[id].len;
+        // the record's one-line view carries its length and the raw fitness of provider 0: one random line per migrant
+        const MutHead hd = st->mh[id];
+        const uint32_t len = id == 0 ? 0u : hd.valid ? hd.len : st->hm[id].len;
         ex.out[t].len[par][k] = id == 0 ? MIG_WILDTYPE : len;
-        for (uint32_t p = 0; p < P; p++) ex.out[t].raw[par][k * P + p] = hap_raw(st, p, id);
+        for (uint32_t p = 0; p < P; p++) ex.out[t].raw[par][k * P + p] = (p == 0 && hd.valid) ? hd.raw0 : hap_raw(st, p, id);
         words[idx] = len;
     }
 }
@@ -99,11 +101,20 @@ __global__ void __launch_bounds__(TPB) k_ex_copy(DevState *st, ExArgs ex, const 
         const uint32_t t = ex_find(sc->part_start, ex.world, idx);
         const uint32_t id = ex.part[t][idx - sc->part_start[t]];
         if (id == 0) continue;
-        const HapMeta hm = st->hm[id];
-        const uint32_t *src = st->arena + hm.off;
-        if (woff[idx] + hm.len > stage_cap) { raise(st, DE_ARENA_CAPACITY); continue; }  // (the target's block would overflow too)
+        const MutHead hd = st->mh[id];  // (the line k_ex_lens just read: an L2 hit; short records come with it)
+        uint64_t off = hd.off;
+        uint32_t len = hd.len;
+        if (!hd.valid) { const HapMeta hm = st->hm[id]; off = hm.off; len = hm.len; }
+        if (woff[idx] + len > stage_cap) { raise(st, DE_ARENA_CAPACITY); continue; }  // (the target's block would overflow too)
         uint32_t *dst = stage + woff[idx];
-        for (uint32_t k = 0; k < hm.len; k++) dst[k] = src[k];
+        if (hd.valid && len <= HEAD_INLINE) {
+#pragma unroll
+            for (uint32_t k = 0; k < HEAD_INLINE; k++)
+                if (k < len) dst[k] = hd.inl[k];
+        } else {
+            const uint32_t *src = st->arena + off;
+            for (uint32_t k = 0; k < len; k++) dst[k] = src[k];
+        }
     }
 }
 __global__ void __launch_bounds__(TPB) k_ex_stream(DevState *st, ExArgs ex, const ExScratch *sc, const uint64_t *__restrict__ woff,

@@ -1565,6 +1565,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
     __shared__ uint64_t s_scan[PLAN_THREADS / 32];
     __shared__ uint64_t s_carry;
     __shared__ uint64_t s_size[MAX_PARTS], s_W;
+    __shared__ unsigned long long s_acc[MAX_PARTS];
     __shared__ double s_rcp[POISSON_RCP];
     poisson_rcp_init(s_rcp);
     const bool lead = blockIdx.x == 0;
@@ -1609,24 +1610,31 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
     if (lead && tid == 0) st->dbg[1] = vl_globaltimer();
     uint32_t tree_mask = pa.force_tree ? (NP >= 32 ? 0xFFFFFFFFu : (1u << NP) - 1u) : 0u;
     uint64_t K[MAX_PARTS];
+    // Every stage below works on all (part, tile) pairs of this CTA's slice at once: a warp takes 32 consecutive tiles of
+    // one part, so eight parts cost what one does instead of eight passes with a third of the threads busy.
+    const uint32_t lane = tid & 31, wid = tid >> 5;
+    const uint32_t chunks = (uint32_t)((t_hi - t_lo + 31) / 32);  // warp-sized runs of tiles in this CTA's slice
     if (!pa.force_tree) {
-        for (uint32_t p = 0; p < NP; p++) {  // stage 0
+        if (tid < (uint32_t)MAX_PARTS) s_acc[tid] = 0ull;
+        __syncthreads();
+        for (uint32_t ch = wid; ch < NP * chunks; ch += PLAN_THREADS / 32) {  // stage 0
+            const uint32_t p = ch / chunks;
+            const uint64_t t = t_lo + (uint64_t)(ch - p * chunks) * 32 + lane;
             const uint64_t size = s_size[p];
             double mu = (double)size - 5.0 * sqrt((double)size) - 8.0;
             if (!(mu > 0.0) || size <= PLAN_FILL_MAX) mu = 0.0;  // a small sample is drawn one by one below, no Poissonisation needed
-            uint64_t *cnt = st->tile_cnt + p * stride;
-            const uint64_t salt = (uint64_t)pa.salt[p] << 48;
-            uint64_t mine = 0;
-            for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) {
+            uint64_t c = 0;
+            if (t < t_hi) {
                 const uint64_t w = st->tile_sum[t];
-                uint64_t c = 0;
-                if (w > 0 && mu > 0.0) c = poisson_draw(key, t | salt, gen, PH_PLAN, mu * ((double)w / (double)W), s_rcp);
-                cnt[t] = c;
-                mine += c;
+                if (w > 0 && mu > 0.0) c = poisson_draw(key, t | ((uint64_t)pa.salt[p] << 48), gen, PH_PLAN, mu * ((double)w / (double)W), s_rcp);
+                st->tile_cnt[p * stride + t] = c;
             }
-            mine = plan_block_sum(mine, s_scan);
-            if (tid == 0 && mine) atomicAdd((unsigned long long *)&st->plan_acc[0][p], (unsigned long long)mine);
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, sh);
+            if (lane == 0 && c) atomicAdd(&s_acc[p], (unsigned long long)c);
         }
+        __syncthreads();
+        if (tid < NP && s_acc[tid]) atomicAdd((unsigned long long *)&st->plan_acc[0][tid], s_acc[tid]);
         plan_grid_barrier(st, epoch);
         for (uint32_t p = 0; p < NP; p++) K[p] = plan_ld(&st->plan_acc[0][p]);
         if (lead && tid == 0) st->dbg[2] = vl_globaltimer();
@@ -1641,24 +1649,28 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
                 }
             }
             if (!active) break;  // the same decision in every CTA: K comes from the shared accumulators
-            for (uint32_t p = 0; p < NP; p++) {
-                if (!(active >> p & 1u)) continue;
+            if (tid < (uint32_t)MAX_PARTS) s_acc[tid] = 0ull;
+            __syncthreads();
+            for (uint32_t ch = wid; ch < NP * chunks; ch += PLAN_THREADS / 32) {
+                const uint32_t p = ch / chunks;
+                if (!(active >> p & 1u)) continue;  // (warp-uniform)
+                const uint64_t t = t_lo + (uint64_t)(ch - p * chunks) * 32 + lane;
                 const double d = (double)(s_size[p] - K[p]);
                 const double mu2 = d - 5.0 * sqrt(d) - 8.0;
-                uint64_t *cnt = st->tile_cnt + p * stride;
-                const uint64_t salt = ((uint64_t)pa.salt[p] << 48) | ((uint64_t)stage << 40);
-                uint64_t add = 0;
-                for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) {
+                uint64_t c = 0;
+                if (t < t_hi) {
                     const uint64_t w = st->tile_sum[t];
                     if (w > 0) {
-                        const uint64_t c = poisson_draw(key, t | salt, gen, PH_PLAN, mu2 * ((double)w / (double)W), s_rcp);
-                        cnt[t] += c;
-                        add += c;
+                        c = poisson_draw(key, t | ((uint64_t)pa.salt[p] << 48) | ((uint64_t)stage << 40), gen, PH_PLAN, mu2 * ((double)w / (double)W), s_rcp);
+                        st->tile_cnt[p * stride + t] += c;
                     }
                 }
-                add = plan_block_sum(add, s_scan);
-                if (tid == 0 && add) atomicAdd((unsigned long long *)&st->plan_acc[stage][p], (unsigned long long)add);
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, sh);
+                if (lane == 0 && c) atomicAdd(&s_acc[p], (unsigned long long)c);
             }
+            __syncthreads();
+            if (tid < NP && (active >> tid & 1u) && s_acc[tid]) atomicAdd((unsigned long long *)&st->plan_acc[stage][tid], s_acc[tid]);
             plan_grid_barrier(st, epoch);
             for (uint32_t p = 0; p < NP; p++) if (active >> p & 1u) K[p] += plan_ld(&st->plan_acc[stage][p]);
         }
@@ -1719,18 +1731,51 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
     plan_grid_barrier(st, epoch);  // every count is final
     if (lead && tid == 0) st->dbg[3] = vl_globaltimer();
     // ---- (3) exclusive scan of the counts: slice totals first, then every CTA scans its slice from its base
-    for (uint32_t p = 0; p < NP; p++) {
+    if (NP < 4) {  // few parts: the whole CTA scans one part's slice after the other
+        for (uint32_t p = 0; p < NP; p++) {
+            const uint64_t *cnt = st->tile_cnt + p * stride;
+            uint64_t part = 0;
+            for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) part += __ldcg(&cnt[t]);
+            part = plan_block_sum(part, s_scan);
+            if (tid == 0) st->plan_part[blockIdx.x][p] = part;
+        }
+        plan_grid_barrier(st, epoch);
+        for (uint32_t p = 0; p < NP; p++) {
+            uint64_t base = 0;
+            for (uint32_t g = 0; g < blockIdx.x; g++) base += plan_ld(&st->plan_part[g][p]);
+            plan_block_scan(st->tile_cnt + p * stride + t_lo, st->tile_base + p * stride + t_lo, t_hi - t_lo, false, base, s_scan, &s_carry);
+        }
+        if (lead && tid == 0) st->dbg[4] = vl_globaltimer();
+        return;
+    }
+    // many parts: one warp per part (round robin): the slice total, then — once every CTA's totals are known — the scan of
+    // the slice, 32 tiles at a time (other CTAs may have added to the counts: read past L1)
+    for (uint32_t p = wid; p < NP; p += PLAN_THREADS / 32) {
         const uint64_t *cnt = st->tile_cnt + p * stride;
         uint64_t part = 0;
-        for (uint64_t t = t_lo + tid; t < t_hi; t += PLAN_THREADS) part += __ldcg(&cnt[t]);
-        part = plan_block_sum(part, s_scan);
-        if (tid == 0) st->plan_part[blockIdx.x][p] = part;
+        for (uint64_t t = t_lo + lane; t < t_hi; t += 32) part += __ldcg(&cnt[t]);
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, sh);
+        if (lane == 0) st->plan_part[blockIdx.x][p] = part;
     }
     plan_grid_barrier(st, epoch);
-    for (uint32_t p = 0; p < NP; p++) {
-        uint64_t base = 0;
-        for (uint32_t g = 0; g < blockIdx.x; g++) base += plan_ld(&st->plan_part[g][p]);
-        plan_block_scan(st->tile_cnt + p * stride + t_lo, st->tile_base + p * stride + t_lo, t_hi - t_lo, false, base, s_scan, &s_carry);
+    for (uint32_t p = wid; p < NP; p += PLAN_THREADS / 32) {
+        uint64_t run = 0;
+        for (uint32_t g = 0; g < blockIdx.x; g++) run += plan_ld(&st->plan_part[g][p]);
+        const uint64_t *cnt = st->tile_cnt + p * stride;
+        uint64_t *base = st->tile_base + p * stride;
+        for (uint64_t t0 = t_lo; t0 < t_hi; t0 += 32) {
+            const uint64_t t = t0 + lane;
+            const uint64_t x = t < t_hi ? __ldcg(&cnt[t]) : 0;
+            uint64_t inc = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += y;
+            }
+            if (t < t_hi) base[t] = run + inc - x;
+            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
     }
     if (lead && tid == 0) st->dbg[4] = vl_globaltimer();
 }
@@ -1764,6 +1809,7 @@ __global__ void __launch_bounds__(TPB, 4) k_resample(DevState *st, ResampleArgs 
     __shared__ uint32_t s_mask[RANK_WORDS + 1];
     __shared__ uint16_t s_pre[RANK_WORDS];      // set bits in the mask words before this one
     __shared__ uint32_t s_wbits[TPB / 32];
+    __shared__ uint64_t s_pcnt[MAX_PARTS], s_pbase[MAX_PARTS];
     __shared__ uint32_t s_wsum[TPB / 32], s_wcnt[TPB / 32];
     const uint64_t nt = tile_count(st);
     const uint32_t *__restrict__ offspring = st->offspring;
@@ -1774,9 +1820,19 @@ __global__ void __launch_bounds__(TPB, 4) k_resample(DevState *st, ResampleArgs 
     const uint32_t gen = st->generation;
     const uint64_t stride = st->tile_stride;
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-        // the tile's descriptors are independent loads: issue them together, decide afterwards
+        // the tile's descriptors are independent loads: issue them together, decide afterwards (with several parts every
+        // part's draw count and first output slot are parked in shared memory: no dependent load per part later)
         uint64_t any = 0;
-        for (uint32_t p = 0; p < ra.n_parts; p++) any |= st->tile_cnt[p * stride + tile];
+        if (ra.n_parts == 1) {
+            any = st->tile_cnt[tile];
+        } else {
+            if (tid < ra.n_parts) {
+                s_pcnt[tid] = st->tile_cnt[tid * stride + tile];
+                s_pbase[tid] = st->tile_base[tid * stride + tile];
+            }
+            __syncthreads();
+            for (uint32_t p = 0; p < ra.n_parts; p++) any |= s_pcnt[p];
+        }
         const uint64_t tsum = st->tile_sum[tile];
         uint64_t start;
         uint32_t tlen;
@@ -1875,15 +1931,35 @@ __global__ void __launch_bounds__(TPB, 4) k_resample(DevState *st, ResampleArgs 
             slot++;
         }
         __syncthreads();
-        // ---- draws of every part: output slots [base, base + c), four per Philox block
-        for (uint32_t part = 0; part < ra.n_parts; part++) {
-        const uint64_t c = st->tile_cnt[part * stride + tile];
-        if (c == 0) continue;
-        const uint64_t base = st->tile_base[part * stride + tile];
-        const uint64_t salt = (uint64_t)ra.salt[part] << 48;
-        uint32_t *__restrict__ dst = ra.dst[part] ? ra.dst[part] : st->hap_id_next;
-        const uint64_t q_lo = base >> 2, q_hi = (base + c - 1) >> 2;
-        for (uint64_t q = q_lo + tid; q <= q_hi; q += TPB) {
+        // ---- draws of every part: output slots [base, base + c), four per Philox block.  The Philox blocks of all parts
+        // form one index space dealt to the threads, so the handful of draws of a small part does not cost a pass of its own.
+        uint32_t blocks_total = 0;  // (every thread computes the same prefix from shared memory: <= 16 parts)
+        if (ra.n_parts > 1) {
+            for (uint32_t p = 0; p < ra.n_parts; p++) {
+                const uint64_t c = s_pcnt[p], b = s_pbase[p];
+                blocks_total += c ? (uint32_t)(((b + c - 1) >> 2) - (b >> 2) + 1) : 0u;
+            }
+        } else {
+            const uint64_t b = st->tile_base[tile];
+            blocks_total = (uint32_t)(((b + any - 1) >> 2) - (b >> 2) + 1);
+        }
+        for (uint32_t e = tid; e < blocks_total; e += TPB) {
+            uint32_t part = 0, before = 0;
+            uint64_t c = any, base = 0;
+            if (ra.n_parts > 1) {
+                for (;; part++) {
+                    c = s_pcnt[part];
+                    base = s_pbase[part];
+                    const uint32_t nb = c ? (uint32_t)(((base + c - 1) >> 2) - (base >> 2) + 1) : 0u;
+                    if (e < before + nb) break;
+                    before += nb;
+                }
+            } else {
+                base = st->tile_base[tile];
+            }
+            const uint64_t salt = (uint64_t)ra.salt[part] << 48;
+            uint32_t *__restrict__ dst = ra.dst[part] ? ra.dst[part] : st->hap_id_next;
+            const uint64_t q = (base >> 2) + (e - before);
             const uint4 blk = philox_block(key, q | salt, gen, PH_RESAMPLE, 0);
             const uint32_t xs[4] = {blk.x, blk.y, blk.z, blk.w};
 #pragma unroll
@@ -1912,7 +1988,6 @@ __global__ void __launch_bounds__(TPB, 4) k_resample(DevState *st, ResampleArgs 
                 if (mode == 0) dst[s] = payload;
                 else dst64[s] = rec[start + payload].x;
             }
-        }
         }
         if (tid * 8u < next_len) {  // 32 bytes of offspring counts and 64 bytes of records per thread
             asm volatile("prefetch.global.L2 [%0];" ::"l"(offspring + next_start + tid * 8u));
