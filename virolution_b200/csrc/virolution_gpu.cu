@@ -811,7 +811,9 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
     // a handful of co-resident CTAs: each draws for its slice of tiles, a counter in DevState is the grid barrier
     // (enough CTAs for the tiles, and for the draws a small sample makes one by one: two per thread)
     const uint64_t direct_draws = std::min<uint64_t>(sim->h.max_population, PLAN_FILL_MAX);
-    const unsigned ctas = (unsigned)std::min<uint64_t>(PLAN_CTAS, std::max<uint64_t>(std::max<uint64_t>(1, nt_bound / 256), direct_draws / (2 * PLAN_THREADS)));
+    // (several parts: more (part, tile) pairs to draw for, up to the 32 slices DevState::plan_part has room for)
+    const uint64_t max_ctas = n >= 4 ? 2 * PLAN_CTAS : PLAN_CTAS;
+    const unsigned ctas = (unsigned)std::min<uint64_t>(max_ctas, std::max<uint64_t>(std::max<uint64_t>(1, nt_bound * n / 256), direct_draws / (2 * PLAN_THREADS)));
     LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, pa, smem_tiles);
     LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, ra, dst64, mode);
     return VL_OK;

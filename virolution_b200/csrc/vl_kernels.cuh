@@ -1674,22 +1674,29 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
             plan_grid_barrier(st, epoch);
             for (uint32_t p = 0; p < NP; p++) if (active >> p & 1u) K[p] += plan_ld(&st->plan_acc[stage][p]);
         }
+        // what is still missing is drawn one by one; the draws of all parts form one index space over all plan threads
+        uint64_t D_total = 0;
         for (uint32_t p = 0; p < NP; p++) {
-            const uint64_t size = s_size[p];
-            if (K[p] > size) { tree_mask |= 1u << p; continue; }
-            const uint64_t D = size - K[p];
-            uint64_t *cnt = st->tile_cnt + p * stride;
-            for (uint64_t j = (uint64_t)blockIdx.x * PLAN_THREADS + tid; j < D; j += (uint64_t)gridDim.x * PLAN_THREADS) {
-                // Uniform(0, W): 64-bit widening multiply with rejection
-                Philox g(st->seed, st->compartment, gen, PH_PLAN_FILL, j | ((uint64_t)pa.salt[p] << 48));
-                const uint64_t r = g.below(W);
-                uint64_t lo = 0, hi = nt;  // first tile with prefix > r
-                while (lo < hi) {
-                    const uint64_t mid = (lo + hi) >> 1;
-                    if (prefix[mid] <= r) lo = mid + 1; else hi = mid;
-                }
-                atomicAdd((unsigned long long *)&cnt[lo], 1ull);
+            if (K[p] > s_size[p]) tree_mask |= 1u << p;
+            else D_total += s_size[p] - K[p];
+        }
+        for (uint64_t e = (uint64_t)blockIdx.x * PLAN_THREADS + tid; e < D_total; e += (uint64_t)gridDim.x * PLAN_THREADS) {
+            uint32_t p = 0;
+            uint64_t j = e;
+            for (;; p++) {
+                const uint64_t D = K[p] > s_size[p] ? 0 : s_size[p] - K[p];
+                if (j < D) break;
+                j -= D;
             }
+            // Uniform(0, W): 64-bit widening multiply with rejection
+            Philox g(st->seed, st->compartment, gen, PH_PLAN_FILL, j | ((uint64_t)pa.salt[p] << 48));
+            const uint64_t r = g.below(W);
+            uint64_t lo = 0, hi = nt;  // first tile with prefix > r
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (prefix[mid] <= r) lo = mid + 1; else hi = mid;
+            }
+            atomicAdd((unsigned long long *)&st->tile_cnt[p * stride + lo], 1ull);
         }
     }
     if (tree_mask) plan_grid_barrier(st, epoch);  // (uniform) stage counts of the parts that fall back are about to be overwritten
