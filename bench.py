@@ -197,7 +197,8 @@ def run_b200(args, rank, world):
     sim.infectant_generations(reset=True)
     if runner is not None and runner.trace is not None:
         runner.trace = {}
-    l0 = sim.get_counters()["kernels_launched"]
+    ct0 = sim.get_counters()
+    l0 = ct0["kernels_launched"]
     # ---- timed region: exactly K generations, device-resident
     with ClockSampler(local_rank) as clocks:
         barrier()
@@ -210,7 +211,8 @@ def run_b200(args, rank, world):
     if runner is not None and runner.trace is not None and rank == 0:
         print("exchange host seconds per phase over the timed steps:", {k: round(v, 4) for k, v in runner.trace.items()}, file=sys.stderr)
     ig = sim.infectant_generations(reset=True)
-    launches = sim.get_counters()["kernels_launched"] - l0
+    ct1 = sim.get_counters()
+    launches = ct1["kernels_launched"] - l0
     if dist is not None:
         import torch
         t = torch.tensor([ms, float(ig)], dtype=torch.float64, device="cuda")
@@ -220,6 +222,29 @@ def run_b200(args, rank, world):
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, ig = float(tmax[0]), int(tsum[1])
     value = ig / (ms / 1e3)
+
+    # ---- compaction of the record tables (the stand-in for Rc/Arc drops): how many ran inside the timed region, what one
+    # costs (forced once here, on the table as the timed region left it, timed with CUDA events) and how often a long run
+    # needs one, so that the amortised share can be read off whether or not the timed window happened to contain one
+    compaction = None
+    if rank == 0 and runner is None:
+        cap = sim.get_capacities()
+        runs = ct1["gc_runs"] - ct0["gc_runs"]
+        rec_per_gen = (ct1["haplotype_records"] - ct0["haplotype_records"]) / args.steps if runs == 0 else None
+        sim.timer_start()
+        sim.collect_garbage()
+        gc_ms = sim.timer_stop()
+        live = sim.get_counters()["haplotype_records"]
+        compaction = {"runs_in_timed_region": int(runs), "ms_per_run": round(gc_ms, 4), "records_before": ct1["haplotype_records"],
+                      "live_records_after": int(live), "record_capacity": cap["haplotype_records"],
+                      "trigger": "record table or arena half full"}
+        if rec_per_gen and rec_per_gen > 0:
+            period = max(1.0, (cap["haplotype_records"] / 2 - live) / rec_per_gen)
+            # a run at the trigger point passes over capacity/2 records: scale the measured run to that table size
+            at_trigger = gc_ms * max(1.0, (cap["haplotype_records"] / 2) / max(ct1["haplotype_records"], 1))
+            compaction.update({"new_records_per_generation": round(rec_per_gen), "period_generations": round(period, 1),
+                               "ms_per_run_at_trigger": round(at_trigger, 4), "amortised_ms_per_step": round(at_trigger / period, 5),
+                               "value_with_amortised_compaction": value * (ms / args.steps) / (ms / args.steps + at_trigger / period)})
 
     # ---- per-kernel CUDA-event durations over the same loop (separate pass: events perturb the step time)
     roofline, kernels = None, {}
@@ -346,6 +371,8 @@ def run_b200(args, rank, world):
                           "host_sum": "reference-ordered CSR"},
                "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clk, "roofline": roofline, "kernels": kernels,
                "e2e": e2e}
+        if compaction is not None:
+            out["compaction"] = compaction
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, wl, threads=1)
     if runner is not None and hasattr(runner, "close"):

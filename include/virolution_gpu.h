@@ -207,6 +207,9 @@ int vl_stats_mean_fitness(vl_sim *sim, uint32_t spec, int which, double *out);  
 int vl_get_haplotype_ids(vl_sim *sim, uint32_t *out, uint64_t n);      /* device-local ids (labels) */
 /* counters: [0] live+dead haplotype records, [1] arena words used, [2] gc runs, [3] kernels launched */
 int vl_get_counters(vl_sim *sim, uint64_t *out4);
+/* capacities: [0] infectant slots, [1] haplotype records, [2] arena words, [3] generations between compaction checks
+ * (a compaction runs when the record table or the arena is half full: the stand-in for Rc/Arc drops, src/references/sync.rs:107-115) */
+int vl_get_capacities(vl_sim *sim, uint64_t *out4);
 int vl_collect_garbage(vl_sim *sim);
 
 /* ---- migrant exchange between handles / GPUs --------------------------- */

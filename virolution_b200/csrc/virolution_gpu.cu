@@ -462,7 +462,17 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     // ---- capacities
     uint64_t cap_inf = cfg->capacity_infectants ? cfg->capacity_infectants : std::max<uint64_t>(2 * par.max_population, 4096);
     // room for several generations of new records between compactions (HBM is plentiful: 180 GB)
-    uint64_t cap_hap = cfg->capacity_haplotypes ? cfg->capacity_haplotypes : 6 * cap_inf + 65536;
+    // The record tables get up to ~45 % of the free device memory (≈ 340 bytes per record with both copies and its share of
+    // the arena), between 6 and 16 records of room per infectant slot: a compaction costs a pass over the whole table plus
+    // a copy of the live records, so the rarer it runs the cheaper a generation is.
+    uint64_t hap_room = 6;
+    {
+        size_t free_b = 0, total_b = 0;
+        CCU(cudaMemGetInfo(&free_b, &total_b));
+        const double fit = 0.45 * (double)free_b / ((double)cap_inf * 340.0);
+        hap_room = (uint64_t)std::min(16.0, std::max(6.0, floor(fit)));
+    }
+    uint64_t cap_hap = cfg->capacity_haplotypes ? cfg->capacity_haplotypes : hap_room * cap_inf + 65536;
     if (cap_hap >= 0xFFFFFFF0ull) cap_hap = 0xFFFFFFF0ull;
     uint64_t cap_arena = cfg->capacity_arena_words ? cfg->capacity_arena_words : std::max<uint64_t>(16 * cap_hap, 1ull << 20);
     {
@@ -1994,6 +2004,11 @@ VL_API int vl_get_counters(vl_sim *sim, uint64_t *out4) {
     TRY(read_field(sim, FIELD_OFF(arena_top), &at));
     TRY(read_field(sim, FIELD_OFF(gc_runs), &runs));
     out4[0] = nh; out4[1] = at; out4[2] = runs; out4[3] = sim->launches;
+    return VL_OK;
+}
+VL_API int vl_get_capacities(vl_sim *sim, uint64_t *out4) {
+    ENTER(sim);
+    out4[0] = sim->h.cap_inf; out4[1] = sim->h.cap_hap; out4[2] = sim->h.cap_arena; out4[3] = sim->gc_period;
     return VL_OK;
 }
 VL_API int vl_debug_stamps(vl_sim *sim, uint64_t *out8) {

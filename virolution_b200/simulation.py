@@ -65,6 +65,7 @@ SIGNATURES = {
     "vl_stats_mean_fitness": (C.c_int, [_vp, C.c_uint32, C.c_int, f64p]),
     "vl_get_haplotype_ids": (C.c_int, [_vp, u32p, C.c_uint64]),
     "vl_get_counters": (C.c_int, [_vp, u64p]),
+    "vl_get_capacities": (C.c_int, [_vp, u64p]),
     "vl_collect_garbage": (C.c_int, [_vp]),
     "vl_pop_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), u64p]),
     "vl_pop_unpack_device": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
@@ -456,6 +457,11 @@ class GpuSimulation:
         self._check(self.lib.vl_get_counters(self.ptr, _p(out, C.c_uint64)))
         return {"haplotype_records": int(out[0]), "arena_words": int(out[1]), "gc_runs": int(out[2]),
                 "kernels_launched": int(out[3])}
+
+    def get_capacities(self):
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.vl_get_capacities(self.ptr, _p(out, C.c_uint64)))
+        return {"infectants": int(out[0]), "haplotype_records": int(out[1]), "arena_words": int(out[2]), "gc_check_period": int(out[3])}
 
     def collect_garbage(self):
         self._check(self.lib.vl_collect_garbage(self.ptr))
