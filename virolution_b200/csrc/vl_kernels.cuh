@@ -1833,6 +1833,7 @@ __global__ void __launch_bounds__(TPB, 4) k_resample(DevState *st, ResampleArgs 
         if (ra.n_parts == 1) {
             any = st->tile_cnt[tile];
         } else {
+            __syncthreads();  // (a tile without draws is left without a barrier: nobody may still be reading its entries)
             if (tid < ra.n_parts) {
                 s_pcnt[tid] = st->tile_cnt[tid * stride + tile];
                 s_pbase[tid] = st->tile_base[tid * stride + tile];
