@@ -4,8 +4,8 @@
  * Drop-in boundary for virolution's `trait Simulation<S>` (reference
  * src/simulation.rs:177-219).  A Rust `impl Simulation<Nt> for GpuSimulation`
  *  binds exactly these entry points; in this repository
- * the C++ mirror `include/virolution_gpu.hpp` and the Python harness
- * `virolution_b200/` call them.  Plain pointers and sizes only.
+ * the Python harness `virolution_b200/` (ctypes, `virolution_b200/abi.py`)
+ * calls them.  Plain pointers and sizes only.
  *
  * Conventions
  *  - every function returns `int`: 0 = ok, <0 = error class (vl_status);
@@ -120,9 +120,12 @@ enum {
                                draws and H >= 65536, this flag lets tests compare the two) */
     VL_FLAG_GENERAL_REPLICATE = 8, /* never use the fused replicate kernel (one pass over whole hosts per CTA); the
                                       general kernels give the same result, this flag lets tests compare the two */
-    VL_FLAG_TREE_PLAN = 2 /* split the resampling draws over tiles with the conditional-binomial tree instead of
-                             Poissonisation (both exact; the tree is the rare-case fallback, this flag lets tests
-                             exercise it) */
+    VL_FLAG_TREE_PLAN = 2, /* split the resampling draws over tiles with the conditional-binomial tree instead of
+                              Poissonisation (both exact; the tree is the rare-case fallback, this flag lets tests
+                              exercise it) */
+    VL_FLAG_NO_TILES = 16 /* device-resident loops (vl_run, vl_next_generation) never take the tile-strided generation
+                             (records appended per host tile, mapped fitness carried with the infectant); the general
+                             kernels give the same populations, this flag lets tests compare the two */
 };
 
 /* ---- lifecycle -------------------------------------------------------- */

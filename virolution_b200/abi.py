@@ -23,6 +23,7 @@ VL_ERR_ARGUMENT = -6
 VL_FLAG_TREE_PLAN = 2
 VL_FLAG_NO_BUCKETS = 4
 VL_FLAG_GENERAL_REPLICATE = 8
+VL_FLAG_NO_TILES = 16
 
 UTILITY_LINEAR, UTILITY_ALGEBRAIC, UTILITY_HILL = 0, 1, 2
 FITNESS_NONE, FITNESS_NEUTRAL, FITNESS_NONEPISTATIC, FITNESS_EPISTATIC = 0, 1, 2, 3

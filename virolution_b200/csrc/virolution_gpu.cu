@@ -20,6 +20,7 @@
 #include "vl_kernels.cuh"
 #include "vl_migrate.cuh"
 #include "vl_exchange.cuh"
+#include "vl_tiles.cuh"
 
 using namespace vl;
 
@@ -80,6 +81,7 @@ struct vl_sim {
     bool mutcounts_ready = false; // the fused infect pass already filled the mutation worklist
     bool bucket_pending = false;  // records are bucket-partitioned, the host map is not built yet
     bool uniform_infection = false;  // the host map came from uniform Philox draws over [0, H) (no replay, DevState::fast_infect)
+    bool pop_fit_valid = false;   // pop_fit[] holds the mapped reproductive fitness of every infectant of the current population
     uint32_t plan_smem_tiles = 0;
     uint32_t salt = 0;        // distinguishes the sampling streams of one generation
     uint32_t gens_since_gc = 0, gc_period = 1;
@@ -231,6 +233,45 @@ static void free_population_buffers(vl_sim *sim) {
                     h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_node, h.tile_base, sim->stage64, h.tmp_rec};
     for (void *p : olds) if (p) cudaFree(p);
     h.tmp_rec = nullptr;
+    if (h.pop_fit) cudaFree(h.pop_fit);
+    if (h.pop_fit_next) cudaFree(h.pop_fit_next);
+    h.pop_fit = h.pop_fit_next = nullptr;
+}
+// one reproductive provider for every host (or none): the mapped fitness of an infectant does not depend on its host
+static bool single_reproductive_provider(const DevState &h) {
+    for (uint32_t s = 1; s < h.n_specs; s++) if (h.specs[s].repro != h.specs[0].repro) return false;
+    return true;
+}
+// tile-strided generation (vl_tiles.cuh): uniform infection, Binomial(L, mu) in the inversion regime, no recombination,
+// fitness independent of the host
+static bool tiles_possible(const vl_sim *sim) {
+    const DevState &h = sim->h;
+    return h.fast_infect && h.binv.ok && !(h.host_recombination_rate > 0.0) && single_reproductive_provider(h) && h.tl_tiles_cap > 0 &&
+           !(sim->flags & (VL_FLAG_NO_BUCKETS | VL_FLAG_GENERAL_REPLICATE | VL_FLAG_NO_TILES)) && !(sim->experiment & 8);
+}
+static void free_tile_buffers(vl_sim *sim) {
+    DevState &h = sim->h;
+    void *olds[] = {h.tl_rec, h.tl_hl, h.tl_sorted, h.tl_fill};
+    for (void *p : olds) if (p) cudaFree(p);
+    h.tl_rec = nullptr; h.tl_hl = nullptr; h.tl_sorted = nullptr; h.tl_fill = nullptr;
+    h.tl_tiles_cap = 0;
+}
+// room for the tiles of the fullest population the handle can hold (the fewer hosts a tile spans, the more tiles)
+static int alloc_tile_buffers(vl_sim *sim) {
+    DevState &h = sim->h;
+    free_tile_buffers(sim);
+    if (!h.fast_infect || (sim->flags & VL_FLAG_NO_TILES)) return VL_OK;
+    const uint32_t ht = host_tile_size(h.cap_inf, h.H);
+    if (ht == 0) return VL_OK;
+    const uint64_t tiles = (h.H + ht - 1) / ht + 1;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || tiles * TL_CAP * 34ull > free_b / 2) return VL_OK;  // (the general kernels run instead)
+    TRY(dev_alloc(sim, &h.tl_rec, tiles * TL_CAP, false));
+    TRY(dev_alloc(sim, &h.tl_hl, tiles * TL_CAP, false));
+    TRY(dev_alloc(sim, &h.tl_sorted, tiles * TL_CAP, false));
+    TRY(dev_alloc(sim, &h.tl_fill, tiles * TL_FILL_STRIDE + 32, false));
+    h.tl_tiles_cap = tiles;
+    return VL_OK;
 }
 // tiles the plan/resample arrays can describe: position tiles of the largest population, or host tiles of as many hosts
 static inline uint64_t tile_capacity(uint64_t cap_inf) { return (cap_inf + HT_MIN_HOSTS - 1) / HT_MIN_HOSTS + 2; }
@@ -272,8 +313,11 @@ static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     TRY(dev_alloc(sim, &h.tile_base, nt * MAX_PARTS, false));
     h.tile_stride = nt;
     TRY(dev_alloc(sim, &sim->stage64, cap + 4, false));
+    TRY(dev_alloc(sim, &h.pop_fit, cap + 4, false));
+    TRY(dev_alloc(sim, &h.pop_fit_next, cap + 4, false));
     h.cap_inf = cap;
     TRY(alloc_bucket_buffers(sim));
+    TRY(alloc_tile_buffers(sim));
     return VL_OK;
 }
 // push the host mirror's population pointers/capacity into the device state
@@ -288,6 +332,8 @@ static int push_population_pointers(vl_sim *sim) {
     tmp.tile_stride = h.tile_stride;
     tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.H = h.H; tmp.fast_infect = h.fast_infect;
     tmp.n_buckets = h.n_buckets; tmp.tmp_rec = h.tmp_rec; tmp.cap_tmp = h.cap_tmp;
+    tmp.tl_rec = h.tl_rec; tmp.tl_hl = h.tl_hl; tmp.tl_sorted = h.tl_sorted; tmp.tl_fill = h.tl_fill; tmp.tl_tiles_cap = h.tl_tiles_cap;
+    tmp.pop_fit = h.pop_fit; tmp.pop_fit_next = h.pop_fit_next;
     CU(sim, cudaMemcpy(sim->d, &tmp, sizeof(DevState), cudaMemcpyHostToDevice));
     return VL_OK;
 }
@@ -389,6 +435,7 @@ static void destroy_sim(vl_sim *sim) {
     if (sim->gen_graph) cudaGraphExecDestroy(sim->gen_graph);
     for (auto &b : sim->id_pool) cudaFree(b.p);
     free_population_buffers(sim);
+    free_tile_buffers(sim);
     if (sim->h.offsets) cudaFree(sim->h.offsets);
     if (sim->count) cudaFree(sim->count);
     for (void *p : sim->fixed_allocs) cudaFree(p);
@@ -503,6 +550,8 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CTRY(dev_alloc(sim, &h.bucket_fill, MAX_BUCKETS + 1));
     CTRY(dev_alloc(sim, &h.bucket_pos, MAX_BUCKETS + 2));
     CCU(cudaFuncSetAttribute((k_bucket_sort<1024, BSORT_STAGE_RECS>), cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
+    CCU(cudaFuncSetAttribute(k_sort_replicate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_SMEM_BYTES));
+    CCU(cudaFuncSetAttribute(k_sort_replicate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_SMEM_BYTES));
     { const char *e = getenv("VL_EXPERIMENT"); sim->experiment = e ? atoi(e) : 0; }
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
@@ -594,6 +643,7 @@ VL_API int vl_set_parameters(vl_sim *sim, const vl_parameters *p) {
     h.n_hits = p->n_hits; h.dilution = p->dilution; h.max_population = p->max_population;
     update_fast_infect(sim);
     TRY(alloc_bucket_buffers(sim));
+    TRY(alloc_tile_buffers(sim));
     TRY(push_population_pointers(sim));
     sim->csr_valid = false;
     sim->bucket_pending = false;
@@ -622,6 +672,7 @@ VL_API int vl_set_population_wildtype(vl_sim *sim, uint64_t n) {
         TRY(push_population_pointers(sim));
     }
     LAUNCH(sim, k_fill_population, grid_for(sim, n), TPB, 0, sim->d, n, 0u);
+    sim->pop_fit_valid = false;
     sim->n_known = n;
     sim->n_bound = n;
     sim->n_valid = true;
@@ -728,6 +779,7 @@ static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
 }
 static int enqueue_mutate(vl_sim *sim) {
     const DevState &h = sim->h;
+    sim->pop_fit_valid = false;  // recombinants and mutants replace haplotypes of the current population
     const bool replay = sim->has_rp_mut || sim->has_rp_rec;
     ReplayRecomb rr{sim->rp_rec_n, sim->rp_rec_host, sim->rp_rec_i, sim->rp_rec_j, sim->rp_rec_s0, sim->rp_rec_s1, sim->rp_rec_which};
     ReplayMut rm{sim->rp_mut_off, sim->rp_mut_sites, sim->rp_mut_bases};
@@ -752,6 +804,7 @@ static int enqueue_mutate(vl_sim *sim) {
         LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
     }
     LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0);
+    sim->pop_fit_valid = false;  // haplotypes of the current population changed
     sim->mutcounts_ready = false;
     sim->has_rp_mut = false;
     sim->has_rp_rec = false;
@@ -799,7 +852,7 @@ static inline uint64_t tile_bound(const vl_sim *sim) {
 static inline unsigned grid_resample(const vl_sim *sim) { return (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8); }
 // plan + draws of n parts of the current offspring map in one pass each (n <= MAX_PARTS)
 static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, int use_amount, const uint64_t *amount, int set_next,
-                                uint32_t *const *dst, uint64_t *dst64, int mode) {
+                                uint32_t *const *dst, uint64_t *dst64, int mode, bool tiles = false, double *const *dst_fit = nullptr) {
     if (n == 0 || n > (uint32_t)MAX_PARTS) return fail(sim, VL_ERR_ARGUMENT, "between 1 and %d parts per pass", MAX_PARTS);
     PlanArgs pa;
     ResampleArgs ra;
@@ -825,6 +878,15 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
     const uint64_t max_ctas = n >= 4 ? 2 * PLAN_CTAS : PLAN_CTAS;
     const unsigned ctas = (unsigned)std::min<uint64_t>(max_ctas, std::max<uint64_t>(std::max<uint64_t>(1, nt_bound * n / 256), direct_draws / (2 * PLAN_THREADS)));
     LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, pa, smem_tiles);
+    if (tiles) {  // the offspring map is tile-strided (DevState::layout == 1): haplotype and mapped fitness of the drawn parents
+        if (mode != 0) return fail(sim, VL_ERR_IMPLEMENTATION, "the tile-strided layout serves haplotype draws only");
+        ResampleTlArgs rt;
+        memset(&rt, 0, sizeof rt);
+        rt.n_parts = n;
+        for (uint32_t k = 0; k < n; k++) { rt.salt[k] = ra.salt[k]; rt.dst[k] = ra.dst[k]; rt.dst_fit[k] = dst_fit ? dst_fit[k] : nullptr; }
+        LAUNCH(sim, k_resample_tl, (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8), RT_TPB, 0, sim->d, rt);
+        return VL_OK;
+    }
     LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, ra, dst64, mode);
     return VL_OK;
 }
@@ -859,6 +921,7 @@ static int maybe_gc(vl_sim *sim) {
 static void swap_population(vl_sim *sim) {
     LAUNCH(sim, k_swap_population, 1, 1, 0, sim->d);
     std::swap(sim->h.hap_id, sim->h.hap_id_next);
+    sim->pop_fit_valid = false;  // (assembled from parts: the per-infectant fitness array was not filled)
 }
 
 VL_API int vl_infect(vl_sim *sim) {
@@ -1307,8 +1370,41 @@ static int enqueue_generation_front(vl_sim *sim) {
     TRY(enqueue_replicate(sim, 0, fast_flow));
     return VL_OK;
 }
+// ---- the tile-strided generation (vl_tiles.cuh)
+static bool tiles_now(const vl_sim *sim) {
+    const DevState &h = sim->h;
+    const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
+    if (replay || !tiles_possible(sim)) return false;
+    const uint32_t ht = host_tile_size(sim->n_bound, h.H);
+    if (!ht) return false;
+    const uint64_t nt = (h.H + ht - 1) / ht;
+    return nt <= h.tl_tiles_cap && nt + 1 <= tile_capacity(h.cap_inf);
+}
+static int enqueue_generation_tiles(vl_sim *sim) {
+    const DevState &h = sim->h;
+    sim->salt = 0;
+    const uint32_t ht = host_tile_size(sim->n_bound, h.H);
+    const uint64_t nt = (h.H + ht - 1) / ht;
+    LAUNCH(sim, k_begin_generation_tl, 1, 1024, 0, sim->d);
+    const unsigned pg = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + PF_TPB * PF_ITEMS - 1) / (PF_TPB * PF_ITEMS)), (uint64_t)sim->n_sms * 32);
+    if (sim->pop_fit_valid) LAUNCH(sim, k_prefill<false>, pg, PF_TPB, 0, sim->d);
+    else LAUNCH(sim, k_prefill<true>, pg, PF_TPB, 0, sim->d);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, 0, sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 3, 1);
+    const unsigned sg = (unsigned)std::min<uint64_t>(std::max<uint64_t>(nt, 1), (uint64_t)sim->n_sms * 24);
+    if (h.host_r0 < 12.0) LAUNCH(sim, k_sort_replicate<true>, sg, SR_TPB, SR_SMEM_BYTES, sim->d);
+    else LAUNCH(sim, k_sort_replicate<false>, sg, SR_TPB, SR_SMEM_BYTES, sim->d);
+    const double one = 1.0;
+    uint32_t *dsts[1] = {nullptr};
+    TRY(launch_plan_resample(sim, 1, &one, 0, nullptr, 1, dsts, nullptr, 0, true));
+    LAUNCH(sim, k_swap_population_tl, 1, 1, 0, sim->d);
+    sim->uniform_infection = true;
+    sim->mutcounts_ready = false;
+    sim->bucket_pending = false;
+    return VL_OK;
+}
 // the kernels of one whole generation (everything but the occasional compaction)
-static int enqueue_generation_kernels(vl_sim *sim) {
+static int enqueue_generation_kernels(vl_sim *sim, bool tiles) {
+    if (tiles) return enqueue_generation_tiles(sim);
     TRY(enqueue_generation_front(sim));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
     LAUNCH(sim, k_swap_population, 1, 1, 0, sim->d);
@@ -1323,15 +1419,17 @@ static bool graph_wanted(const vl_sim *sim) {
 }
 static int enqueue_generation(vl_sim *sim) {
     // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
+    const bool tiles = tiles_now(sim);
     if (graph_wanted(sim)) {
         const DevState &h = sim->h;
-        const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets, (uint64_t)sim->flags};
+        const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets ^ (uint64_t)(uintptr_t)h.tl_rec,
+                                 (uint64_t)sim->flags | (tiles ? 1ull << 40 : 0) | (sim->pop_fit_valid ? 1ull << 41 : 0)};
         if (!sim->gen_graph || memcmp(key, sim->graph_key, sizeof key) != 0) {
             if (sim->gen_graph) { cudaGraphExecDestroy(sim->gen_graph); sim->gen_graph = nullptr; }
             cudaGraph_t graph = nullptr;
             const uint64_t l0 = sim->launches;
             if (cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                const int rc = enqueue_generation_kernels(sim);
+                const int rc = enqueue_generation_kernels(sim, tiles);
                 const cudaError_t ce = cudaStreamEndCapture(sim->stream, &graph);
                 if (rc == VL_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&sim->gen_graph, graph, 0) == cudaSuccess) {
                     memcpy(sim->graph_key, key, sizeof key);
@@ -1356,12 +1454,14 @@ static int enqueue_generation(vl_sim *sim) {
             sim->bucket_pending = false;
             sim->has_rp_off = false;
         } else {
-            TRY(enqueue_generation_kernels(sim));
+            TRY(enqueue_generation_kernels(sim, tiles));
         }
     } else {
-        TRY(enqueue_generation_kernels(sim));
+        TRY(enqueue_generation_kernels(sim, tiles));
     }
     std::swap(sim->h.hap_id, sim->h.hap_id_next);
+    if (tiles) std::swap(sim->h.pop_fit, sim->h.pop_fit_next);
+    sim->pop_fit_valid = tiles;  // the children inherited their parents' mapped fitness (k_resample_tl)
     sim->n_valid = false;
     sim->n_bound = std::min<uint64_t>(sim->h.cap_inf, sim->h.max_population);
     sim->csr_valid = false;

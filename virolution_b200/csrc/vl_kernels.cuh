@@ -808,7 +808,9 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
 // on the pre-mutation haplotype, draw the substitution, merge into a new flattened record and update the
 // raw fitness of every provider incrementally: raw(parent) * fold(acc * T[pos,to] / T[pos,from])
 // (src/core/fitness/table.rs:65-68) [* epistatic update].  patch_records: 1 = the infectant's CSR record is
-// patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist.
+// patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist,
+// 3 = tile-strided generation: items are (infectant, n_mut | host-in-tile << 16, reserved slot, parent) and the
+// slot's record is written here.
 constexpr uint32_t MUT_LOCAL_PARENT = 16;  // parent records up to this length are staged in thread-local memory
 constexpr uint32_t MUT_LOCAL_CHANGES = 8;  // mutation events up to this many sites keep their change words there too
 constexpr uint32_t MUT_SCRATCH_STRIDE = MUT_LOCAL_PARENT + MUT_LOCAL_CHANGES + HEAD_INLINE + 1;  // odd: consecutive threads hit distinct banks
@@ -831,7 +833,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_list; base += span) {
         const uint32_t w = base + lane;
         const bool active = w < n_list;
-        uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32;
+        uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32, hl = 0;
         HapMeta pm{0, 0, NONE32};
         MutHead ph;
         ph.valid = 0u;
@@ -839,6 +841,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
             const uint4 item = st->mut_list[w];
             i = item.x;
             nm = item.y;
+            if (patch_records == 3) { hl = nm >> 16; nm &= 0xFFFFu; }
             tpos = item.z;
             pid = parent_in_item ? item.w : st->hap_id[i];
             ph = st->mh[pid];  // ONE 64-byte line: arena offset, length, raw fitness and the first entries of the parent
@@ -940,7 +943,8 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
                 }
             }
         }
-        double raw0_new = 1.0;
+        double raw0_new = 1.0, fit_repro = 1.0;  // fit_repro: mapped fitness under the reproductive provider of spec 0 (patch_records == 3)
+        const int pi_repro = st->specs[0].repro;
         for (uint32_t p = 0; p < st->n_providers; p++) {
             const DevProvider &pr = st->prov[p];
             double raw = 1.0;
@@ -954,8 +958,11 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
                 if (pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, out, o);
                 raw = praw * acc;
             }
-            set_fitness(st, p, new_id, raw);
+            const double mapped = utility_apply(pr, raw);
+            st->h_raw[p][new_id] = raw;
+            st->h_fit[p][new_id] = mapped;
             if (p == 0) raw0_new = raw;
+            if ((int)p == pi_repro) fit_repro = mapped;
         }
         {
             MutHead nh;
@@ -969,7 +976,15 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
         }
         st->hm[new_id] = HapMeta{roff, o, pid};
         st->hap_id[i] = new_id;
-        if (patch_records == 2) {
+        if (patch_records == 3) {
+            // tile-strided generation: the slot of this infectant's record was reserved by the prefill pass, the record
+            // itself is written here, with the new haplotype and its mapped fitness
+            if (tpos != NONE32) {
+                const unsigned long long fb = (unsigned long long)__double_as_longlong(fit_repro);
+                st->tl_rec[tpos] = make_uint4(i, new_id, (uint32_t)fb, (uint32_t)(fb >> 32));
+                st->tl_hl[tpos] = (uint16_t)hl;
+            }
+        } else if (patch_records == 2) {
             if (tpos != NONE32) st->tmp_rec[tpos].y = new_id;  // the bucket-partitioned record, not yet sorted
         } else if (patch_records) {
             const uint32_t h = st->host_id[i];
@@ -1220,7 +1235,9 @@ __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t 
             } else {
                 if (l > 0.0) {
                     if (SMALL_ONLY && !(l < 12.0)) raise(st, DE_UNDEFINED_OFFSPRING);  // f > S: negative fitness values in the slice
-                    uint64_t v = poisson_draw<SMALL_ONLY>(key, p, gen, PH_OFFSPRING, l, s_rcp);
+                    // the stream of a draw is addressed by the infectant, not by where its record sits: every layout of
+                    // the host map (dense CSR positions here, tile-strided in vl_tiles.cuh) draws the same count
+                    uint64_t v = poisson_draw<SMALL_ONLY>(key, rec[p].x, gen, PH_OFFSPRING, l, s_rcp);
                     if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
                     off = (uint32_t)v;
                 }
@@ -1387,9 +1404,10 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
                 off = (uint32_t)v;
             } else if (l > 0.0) {
                 uint64_t v;
-                if (l < 12.0) v = poisson_draw_small_fast(key, p, gen, PH_OFFSPRING, l, c_rcp64, kmax)  /* the f64 fallback reads 1/k from constant memory */;
+                const uint64_t who = s_rec[q].x;  // (streams are addressed by the infectant: see k_offspring)
+                if (l < 12.0) v = poisson_draw_small_fast(key, who, gen, PH_OFFSPRING, l, c_rcp64, kmax)  /* the f64 fallback reads 1/k from constant memory */;
                 else if (SMALL_ONLY) { raise(st, DE_UNDEFINED_OFFSPRING); v = 0; }  // f > S: negative fitness values in the slice
-                else v = poisson_ptrs(key, p, gen, PH_OFFSPRING, l);
+                else v = poisson_ptrs(key, who, gen, PH_OFFSPRING, l);
                 if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
                 off = (uint32_t)v;
             }

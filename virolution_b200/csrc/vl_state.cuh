@@ -39,6 +39,10 @@ constexpr int MAX_PARTS = 16;              // subsamples of one offspring map th
 constexpr uint32_t HT_MAX_HOSTS = 2048;   // most hosts a host-range tile may span (DevState::host_tiles holds the actual number)
 constexpr uint32_t HT_MIN_HOSTS = 256;    // below this the fused replicate kernel is not worth launching
 constexpr double HT_SPREAD_CTAS = 148.0;  // tiles of a small host population are shrunk until there are about two per SM of a B200
+// ---- tile-strided layout of the fused generation (vl_tiles.cuh): a host tile is a power-of-two range of hosts, its
+// records live at [tile * TL_CAP, tile * TL_CAP + fill[tile]) — no dense CSR positions, no offsets[] array
+constexpr uint32_t TL_CAP = RESAMPLE_TILE;  // records a host tile can hold (what one CTA stages)
+constexpr uint32_t TL_FILL_STRIDE = 32;     // u32 words between the append cursors of consecutive tiles
 
 // error bits raised by kernels (sticky until vl_* reports them)
 enum DevError : uint32_t {
@@ -52,7 +56,8 @@ enum DevError : uint32_t {
     DE_REPLAY = 128u,           // malformed replay log
     DE_BUCKET_OVERFLOW = 256u,  // a host bucket received 12 standard deviations more records than its mean
     DE_TILE_OVERFLOW = 512u,    // a host tile holds more records than a CTA stages (uniform infection: > 8 sd)
-    DE_EXCHANGE_TIMEOUT = 1024u // a peer's migrants did not arrive in time (vl_exchange_step)
+    DE_EXCHANGE_TIMEOUT = 1024u, // a peer's migrants did not arrive in time (vl_exchange_step)
+    DE_PLAN_TIMEOUT = 2048u     // the CTAs of the resample plan did not all become resident (grid barrier)
 };
 constexpr uint32_t BUCKET_SHIFT = 13;
 constexpr uint32_t BUCKET_HOSTS = 1u << BUCKET_SHIFT;  // hosts per bucket: their histogram lives in shared memory
@@ -150,6 +155,16 @@ struct DevState {
     uint4 *tmp_rec;        // bucket-partitioned records (index, haplotype, host, -), bucket b at [b * stride, b * stride + fill)
     uint64_t cap_tmp;
 
+    // ---- tile-strided generation (vl_tiles.cuh): records appended per host tile, sorted and replicated per tile
+    uint4 *tl_rec;         // (infectant index, haplotype, mapped fitness lo, hi) as appended, tile t at [t * TL_CAP, ..)
+    uint16_t *tl_hl;       // host - first host of the tile, per appended record
+    uint4 *tl_sorted;      // per tile position in host order: (offspring, haplotype, mapped fitness lo, hi)
+    uint32_t *tl_fill;     // records per tile (append cursors), TL_FILL_STRIDE words apart
+    uint64_t tl_tiles_cap; // tiles the three arrays have room for
+    uint32_t tl_shift;     // log2(hosts per tile) of the records in tl_rec
+    uint32_t layout;       // 0: offspring[] / rec[] at dense CSR positions, 1: tl_sorted (tile-strided)
+    double *pop_fit, *pop_fit_next;  // mapped reproductive fitness per infectant, parallel to hap_id / hap_id_next (valid when the host says so)
+
     // ---- mutation worklist
     uint4 *mut_list;       // (infectant index, n_mut, position in the bucket-partitioned records, -) where n_mut > 0
     uint32_t n_mut_list;
@@ -210,7 +225,11 @@ __host__ __device__ inline uint32_t host_tile_size(uint64_t n, uint64_t H) {
     // 10^4 infectants should still spread over the SMs)
     const double spread = ceil((double)H / (2.0 * HT_SPREAD_CTAS));
     if (ht > spread) ht = spread > (double)HT_MIN_HOSTS ? spread : (double)HT_MIN_HOSTS;
-    return (uint32_t)ht;
+    // a power of two (HT_MIN_HOSTS and HT_MAX_HOSTS are): the tile of a host is a shift, and every path that tiles by
+    // hosts — the trait-level fused replicate kernel and the tile-strided generation — cuts the same tiles
+    uint32_t p = HT_MIN_HOSTS;
+    while ((double)(2u * p) <= ht) p *= 2u;
+    return p;
 }
 
 // ---- resample tiles: a tile is what one CTA stages in shared memory, either RESAMPLE_TILE consecutive CSR positions
@@ -220,7 +239,11 @@ __device__ __forceinline__ uint64_t tile_count(const DevState *st) {
     return ht ? (st->H + ht - 1) / ht : (st->n_sorted + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
 }
 __device__ __forceinline__ void tile_range(const DevState *st, uint64_t tile, uint64_t &start, uint32_t &len) {
-    if (st->host_tiles) {
+    if (st->layout) {
+        start = tile * TL_CAP;
+        len = st->tl_fill[tile * TL_FILL_STRIDE];
+        if (len > TL_CAP) len = TL_CAP;
+    } else if (st->host_tiles) {
         const uint64_t ht = st->host_tiles;
         const uint64_t h0 = tile * ht, h1 = h0 + ht < st->H ? h0 + ht : st->H;
         start = st->offsets[h0];
