@@ -83,6 +83,8 @@ def case(name):
         t0 = exponential_table(wt, weights=(0.3, 0.6, 0.0, 0.1), rng=np.random.default_rng(15))
         t1 = exponential_table(wt, weights=(0.3, 0.6, 0.0, 0.1), rng=np.random.default_rng(16))
         ti = exponential_table(wt, weights=(0.1, 0.8, 0.0, 0.1), rng=np.random.default_rng(17))
+        for t in (t0, t1, ti):  # (deleterious entries are max(1 - Exp, 0): about one in a hundred comes out exactly 0)
+            np.maximum(t, 0.02, out=t)
         specs = [HostSpec(0, 500, FitnessProvider("NonEpistatic", table=t0, utility=ALG),
                           FitnessProvider("NonEpistatic", table=ti, utility=UtilityFunction("Algebraic", upper=1.2))),
                  HostSpec(500, 1000, FitnessProvider("NonEpistatic", table=t1, utility=UtilityFunction("Linear")), None)]

@@ -39,7 +39,7 @@ def test_step_sizes_agree_in_distribution_with_oracle(rule, T):
         sets = helpers.mutation_sets(off, pos, base)
         row += [len(set(sets)), float(np.mean([len(s) for s in sets])) if sets else 0.0]
         rows_o.append(row)
-        sims = [helpers.make_gpu(cc, seed=9000 + r, compartment_id=k) for k in range(C)]
+        sims = [helpers.make_gpu(cc, seed=50000 + r, compartment_id=k) for k in range(C)]
         row = []
         for _ in range(G):
             step(sims, T, rule)

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvirolution_gpu.so")
 SOURCES = ["virolution_gpu.cu"]
-HEADERS = ["vl_kernels.cuh", "vl_migrate.cuh", "vl_exchange.cuh", "vl_tiles.cuh", "vl_rng.cuh", "vl_scan.cuh", "vl_state.cuh",
+HEADERS = ["vl_kernels.cuh", "vl_migrate.cuh", "vl_exchange.cuh", "vl_fused.cuh", "vl_rng.cuh", "vl_scan.cuh", "vl_state.cuh",
            os.path.join("..", "..", "include", "virolution_gpu.h")]
 
 # -fmad=false: the fitness arithmetic must round like the reference's scalar f64 code (no FMA contraction of

@@ -20,7 +20,7 @@
 #include "vl_kernels.cuh"
 #include "vl_migrate.cuh"
 #include "vl_exchange.cuh"
-#include "vl_tiles.cuh"
+#include "vl_fused.cuh"
 
 using namespace vl;
 
@@ -78,6 +78,7 @@ struct vl_sim {
     bool csr_valid = false;       // rec/offsets hold the host map of the current population
     bool slices_ordered = false;  // ... and every slice is in the reference's descending order
     bool layout_valid = false;    // rec/offspring/tile_sum describe an offspring map (host map or identity layout)
+    bool layout_identity = false; // ... in infectant order (record p = infectant p), what every resample draws from
     bool mutcounts_ready = false; // the fused infect pass already filled the mutation worklist
     bool bucket_pending = false;  // records are bucket-partitioned, the host map is not built yet
     bool uniform_infection = false;  // the host map came from uniform Philox draws over [0, H) (no replay, DevState::fast_infect)
@@ -242,36 +243,12 @@ static bool single_reproductive_provider(const DevState &h) {
     for (uint32_t s = 1; s < h.n_specs; s++) if (h.specs[s].repro != h.specs[0].repro) return false;
     return true;
 }
-// tile-strided generation (vl_tiles.cuh): uniform infection, Binomial(L, mu) in the inversion regime, no recombination,
+// device-resident generation (vl_fused.cuh): uniform infection, Binomial(L, mu) in the inversion regime, no recombination,
 // fitness independent of the host
-static bool tiles_possible(const vl_sim *sim) {
+static bool fused_possible(const vl_sim *sim) {
     const DevState &h = sim->h;
-    return h.fast_infect && h.binv.ok && !(h.host_recombination_rate > 0.0) && single_reproductive_provider(h) && h.tl_tiles_cap > 0 &&
+    return h.fast_infect && h.binv.ok && !(h.host_recombination_rate > 0.0) && single_reproductive_provider(h) && h.hsum[0] != nullptr &&
            !(sim->flags & (VL_FLAG_NO_BUCKETS | VL_FLAG_GENERAL_REPLICATE | VL_FLAG_NO_TILES)) && !(sim->experiment & 8);
-}
-static void free_tile_buffers(vl_sim *sim) {
-    DevState &h = sim->h;
-    void *olds[] = {h.tl_rec, h.tl_hl, h.tl_sorted, h.tl_fill};
-    for (void *p : olds) if (p) cudaFree(p);
-    h.tl_rec = nullptr; h.tl_hl = nullptr; h.tl_sorted = nullptr; h.tl_fill = nullptr;
-    h.tl_tiles_cap = 0;
-}
-// room for the tiles of the fullest population the handle can hold (the fewer hosts a tile spans, the more tiles)
-static int alloc_tile_buffers(vl_sim *sim) {
-    DevState &h = sim->h;
-    free_tile_buffers(sim);
-    if (!h.fast_infect || (sim->flags & VL_FLAG_NO_TILES)) return VL_OK;
-    const uint32_t ht = host_tile_size(h.cap_inf, h.H);
-    if (ht == 0) return VL_OK;
-    const uint64_t tiles = (h.H + ht - 1) / ht + 1;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || tiles * TL_CAP * 34ull > free_b / 2) return VL_OK;  // (the general kernels run instead)
-    TRY(dev_alloc(sim, &h.tl_rec, tiles * TL_CAP, false));
-    TRY(dev_alloc(sim, &h.tl_hl, tiles * TL_CAP, false));
-    TRY(dev_alloc(sim, &h.tl_sorted, tiles * TL_CAP, false));
-    TRY(dev_alloc(sim, &h.tl_fill, tiles * TL_FILL_STRIDE + 32, false));
-    h.tl_tiles_cap = tiles;
-    return VL_OK;
 }
 // tiles the plan/resample arrays can describe: position tiles of the largest population, or host tiles of as many hosts
 static inline uint64_t tile_capacity(uint64_t cap_inf) { return (cap_inf + HT_MIN_HOSTS - 1) / HT_MIN_HOSTS + 2; }
@@ -317,7 +294,6 @@ static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     TRY(dev_alloc(sim, &h.pop_fit_next, cap + 4, false));
     h.cap_inf = cap;
     TRY(alloc_bucket_buffers(sim));
-    TRY(alloc_tile_buffers(sim));
     return VL_OK;
 }
 // push the host mirror's population pointers/capacity into the device state
@@ -332,8 +308,7 @@ static int push_population_pointers(vl_sim *sim) {
     tmp.tile_stride = h.tile_stride;
     tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.H = h.H; tmp.fast_infect = h.fast_infect;
     tmp.n_buckets = h.n_buckets; tmp.tmp_rec = h.tmp_rec; tmp.cap_tmp = h.cap_tmp;
-    tmp.tl_rec = h.tl_rec; tmp.tl_hl = h.tl_hl; tmp.tl_sorted = h.tl_sorted; tmp.tl_fill = h.tl_fill; tmp.tl_tiles_cap = h.tl_tiles_cap;
-    tmp.pop_fit = h.pop_fit; tmp.pop_fit_next = h.pop_fit_next;
+    tmp.pop_fit = h.pop_fit; tmp.pop_fit_next = h.pop_fit_next; tmp.hsum[0] = h.hsum[0]; tmp.hsum[1] = h.hsum[1];
     CU(sim, cudaMemcpy(sim->d, &tmp, sizeof(DevState), cudaMemcpyHostToDevice));
     return VL_OK;
 }
@@ -343,6 +318,35 @@ static int alloc_host_buffers(vl_sim *sim, uint64_t H) {
     if (sim->count) cudaFree(sim->count);
     TRY(dev_alloc(sim, &h.offsets, H + 8, false));
     TRY(dev_alloc(sim, &sim->count, H + 8, false));
+    // per-host fitness sums of the device-resident generation (vl_fused.cuh), both cleared: a generation accumulates into
+    // hsum[parity] and clears the other.  One allocation, kept in L2 as far as the device allows: every infectant does one
+    // scattered f64 reduction and one scattered load on it per generation, everything else streams past.
+    if (h.hsum[0]) cudaFree(h.hsum[0]);
+    h.hsum[0] = h.hsum[1] = nullptr;
+    if (!(sim->flags & VL_FLAG_NO_TILES)) {
+        const uint64_t per = (H + 8 + 15) & ~15ull;
+        TRY(dev_alloc(sim, &h.hsum[0], 2 * per, false));
+        h.hsum[1] = h.hsum[0] + per;
+        CU(sim, cudaMemset(h.hsum[0], 0, 2 * per * sizeof(double)));
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, sim->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, sim->device);
+        if (max_persist > 0 && max_window > 0 && !(sim->experiment & 16)) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            const uint64_t bytes = std::min<uint64_t>(2 * per * sizeof(double), (uint64_t)max_window);
+            av.accessPolicyWindow.base_ptr = h.hsum[0];
+            av.accessPolicyWindow.num_bytes = bytes;
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(sim->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            if (getenv("VL_DEBUG")) fprintf(stderr, "[vl] persisting L2: max %d B, window max %d B, hsum %llu B, hit ratio %.3f\n", max_persist, max_window,
+                                            (unsigned long long)(2 * per * sizeof(double)), av.accessPolicyWindow.hitRatio);
+            cudaGetLastError();
+        }
+    }
     sim->cap_H = H;
     return VL_OK;
 }
@@ -435,7 +439,7 @@ static void destroy_sim(vl_sim *sim) {
     if (sim->gen_graph) cudaGraphExecDestroy(sim->gen_graph);
     for (auto &b : sim->id_pool) cudaFree(b.p);
     free_population_buffers(sim);
-    free_tile_buffers(sim);
+    if (sim->h.hsum[0]) cudaFree(sim->h.hsum[0]);
     if (sim->h.offsets) cudaFree(sim->h.offsets);
     if (sim->count) cudaFree(sim->count);
     for (void *p : sim->fixed_allocs) cudaFree(p);
@@ -550,8 +554,6 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CTRY(dev_alloc(sim, &h.bucket_fill, MAX_BUCKETS + 1));
     CTRY(dev_alloc(sim, &h.bucket_pos, MAX_BUCKETS + 2));
     CCU(cudaFuncSetAttribute((k_bucket_sort<1024, BSORT_STAGE_RECS>), cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
-    CCU(cudaFuncSetAttribute(k_sort_replicate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_SMEM_BYTES));
-    CCU(cudaFuncSetAttribute(k_sort_replicate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SR_SMEM_BYTES));
     { const char *e = getenv("VL_EXPERIMENT"); sim->experiment = e ? atoi(e) : 0; }
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
@@ -643,7 +645,6 @@ VL_API int vl_set_parameters(vl_sim *sim, const vl_parameters *p) {
     h.n_hits = p->n_hits; h.dilution = p->dilution; h.max_population = p->max_population;
     update_fast_infect(sim);
     TRY(alloc_bucket_buffers(sim));
-    TRY(alloc_tile_buffers(sim));
     TRY(push_population_pointers(sim));
     sim->csr_valid = false;
     sim->bucket_pending = false;
@@ -842,6 +843,7 @@ static int enqueue_replicate(vl_sim *sim, int store_lambda = 1, bool tiles_plann
     sim->slices_ordered = true;
     sim->has_rp_off = false;
     sim->layout_valid = true;
+    sim->layout_identity = false;
     return VL_OK;
 }
 // upper bound of the number of resample tiles of the current offspring map (either tile kind)
@@ -850,10 +852,27 @@ static inline uint64_t tile_bound(const vl_sim *sim) {
     return std::max<uint64_t>((sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE, ht ? (sim->h.H + ht - 1) / ht : 0) + 1;
 }
 static inline unsigned grid_resample(const vl_sim *sim) { return (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8); }
+// Every resample draws from the offspring map in INFECTANT order, tiles of RESAMPLE_TILE consecutive infectants: an
+// offspring map the replicate kernels left at CSR positions is moved there first (one scatter + tile totals).  The draws of
+// a generation then do not depend on which kernels built its map (host Vec<usize>, host-map kernels, vl_fused.cuh).
+static int canonical_layout(vl_sim *sim) {
+    if (!sim->layout_valid) return fail(sim, VL_ERR_IMPLEMENTATION, "no offspring map on the device: call vl_replicate_infectants first or pass one");
+    if (sim->layout_identity) return VL_OK;
+    uint32_t *tmp = sim->h.rank;  // per-infectant scratch, free once the records are scattered
+    zero_device(sim, tmp, (sim->n_bound + 4) * 4);
+    LAUNCH(sim, k_unsort_offspring32, grid_for(sim, sim->n_bound), TPB, 0, sim->d, tmp);
+    LAUNCH(sim, k_identity_from, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (const uint32_t *)tmp);
+    LAUNCH(sim, k_tile_sums, grid_tiles(sim, sim->n_bound, RESAMPLE_TILE), TPB, 0, sim->d);
+    sim->csr_valid = false;
+    sim->slices_ordered = false;
+    sim->layout_identity = true;
+    return VL_OK;
+}
 // plan + draws of n parts of the current offspring map in one pass each (n <= MAX_PARTS)
 static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, int use_amount, const uint64_t *amount, int set_next,
                                 uint32_t *const *dst, uint64_t *dst64, int mode, bool tiles = false, double *const *dst_fit = nullptr) {
     if (n == 0 || n > (uint32_t)MAX_PARTS) return fail(sim, VL_ERR_ARGUMENT, "between 1 and %d parts per pass", MAX_PARTS);
+    if (!tiles) TRY(canonical_layout(sim));
     PlanArgs pa;
     ResampleArgs ra;
     memset(&pa, 0, sizeof pa);
@@ -878,13 +897,13 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
     const uint64_t max_ctas = n >= 4 ? 2 * PLAN_CTAS : PLAN_CTAS;
     const unsigned ctas = (unsigned)std::min<uint64_t>(max_ctas, std::max<uint64_t>(std::max<uint64_t>(1, nt_bound * n / 256), direct_draws / (2 * PLAN_THREADS)));
     LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, pa, smem_tiles);
-    if (tiles) {  // the offspring map is tile-strided (DevState::layout == 1): haplotype and mapped fitness of the drawn parents
-        if (mode != 0) return fail(sim, VL_ERR_IMPLEMENTATION, "the tile-strided layout serves haplotype draws only");
-        ResampleTlArgs rt;
+    if (tiles) {  // offspring counts in infectant order next to hap_id[] / pop_fit[] (vl_fused.cuh): haplotype and mapped fitness of the drawn parents
+        if (mode != 0) return fail(sim, VL_ERR_IMPLEMENTATION, "the device-resident generation serves haplotype draws only");
+        ResamplePosArgs rt;
         memset(&rt, 0, sizeof rt);
         rt.n_parts = n;
         for (uint32_t k = 0; k < n; k++) { rt.salt[k] = ra.salt[k]; rt.dst[k] = ra.dst[k]; rt.dst_fit[k] = dst_fit ? dst_fit[k] : nullptr; }
-        LAUNCH(sim, k_resample_tl, (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8), RT_TPB, 0, sim->d, rt);
+        LAUNCH(sim, k_resample_pos, (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8), RT_TPB, 0, sim->d, rt);
         return VL_OK;
     }
     LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, ra, dst64, mode);
@@ -946,6 +965,7 @@ static int upload_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n) 
     sim->csr_valid = false;
     sim->slices_ordered = false;
     sim->layout_valid = true;
+    sim->layout_identity = true;
     sim->uniform_infection = false;
     return VL_OK;
 }
@@ -1370,33 +1390,26 @@ static int enqueue_generation_front(vl_sim *sim) {
     TRY(enqueue_replicate(sim, 0, fast_flow));
     return VL_OK;
 }
-// ---- the tile-strided generation (vl_tiles.cuh)
-static bool tiles_now(const vl_sim *sim) {
-    const DevState &h = sim->h;
+// ---- the device-resident generation without a host map (vl_fused.cuh)
+static bool fused_now(const vl_sim *sim) {
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
-    if (replay || !tiles_possible(sim)) return false;
-    const uint32_t ht = host_tile_size(sim->n_bound, h.H);
-    if (!ht) return false;
-    const uint64_t nt = (h.H + ht - 1) / ht;
-    return nt <= h.tl_tiles_cap && nt + 1 <= tile_capacity(h.cap_inf);
+    return !replay && fused_possible(sim);
 }
-static int enqueue_generation_tiles(vl_sim *sim) {
+static int enqueue_generation_fused(vl_sim *sim) {
     const DevState &h = sim->h;
     sim->salt = 0;
-    const uint32_t ht = host_tile_size(sim->n_bound, h.H);
-    const uint64_t nt = (h.H + ht - 1) / ht;
-    LAUNCH(sim, k_begin_generation_tl, 1, 1024, 0, sim->d);
-    const unsigned pg = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + PF_TPB * PF_ITEMS - 1) / (PF_TPB * PF_ITEMS)), (uint64_t)sim->n_sms * 32);
-    if (sim->pop_fit_valid) LAUNCH(sim, k_prefill<false>, pg, PF_TPB, 0, sim->d);
-    else LAUNCH(sim, k_prefill<true>, pg, PF_TPB, 0, sim->d);
+    LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d);
+    const unsigned ig = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + IS_TPB * IS_ITEMS - 1) / (IS_TPB * IS_ITEMS)), (uint64_t)sim->n_sms * 32);
+    if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
+    else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
     LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, 0, sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 3, 1);
-    const unsigned sg = (unsigned)std::min<uint64_t>(std::max<uint64_t>(nt, 1), (uint64_t)sim->n_sms * 24);
-    if (h.host_r0 < 12.0) LAUNCH(sim, k_sort_replicate<true>, sg, SR_TPB, SR_SMEM_BYTES, sim->d);
-    else LAUNCH(sim, k_sort_replicate<false>, sg, SR_TPB, SR_SMEM_BYTES, sim->d);
+    const unsigned og = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
+    if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, og, OS_TPB, 0, sim->d);
+    else LAUNCH(sim, k_offspring_sum<false>, og, OS_TPB, 0, sim->d);
     const double one = 1.0;
     uint32_t *dsts[1] = {nullptr};
     TRY(launch_plan_resample(sim, 1, &one, 0, nullptr, 1, dsts, nullptr, 0, true));
-    LAUNCH(sim, k_swap_population_tl, 1, 1, 0, sim->d);
+    LAUNCH(sim, k_swap_population_fused, 1, 1, 0, sim->d);
     sim->uniform_infection = true;
     sim->mutcounts_ready = false;
     sim->bucket_pending = false;
@@ -1404,7 +1417,7 @@ static int enqueue_generation_tiles(vl_sim *sim) {
 }
 // the kernels of one whole generation (everything but the occasional compaction)
 static int enqueue_generation_kernels(vl_sim *sim, bool tiles) {
-    if (tiles) return enqueue_generation_tiles(sim);
+    if (tiles) return enqueue_generation_fused(sim);
     TRY(enqueue_generation_front(sim));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
     LAUNCH(sim, k_swap_population, 1, 1, 0, sim->d);
@@ -1419,10 +1432,10 @@ static bool graph_wanted(const vl_sim *sim) {
 }
 static int enqueue_generation(vl_sim *sim) {
     // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
-    const bool tiles = tiles_now(sim);
+    const bool tiles = fused_now(sim);
     if (graph_wanted(sim)) {
         const DevState &h = sim->h;
-        const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets ^ (uint64_t)(uintptr_t)h.tl_rec,
+        const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets ^ (uint64_t)(uintptr_t)h.hsum[0],
                                  (uint64_t)sim->flags | (tiles ? 1ull << 40 : 0) | (sim->pop_fit_valid ? 1ull << 41 : 0)};
         if (!sim->gen_graph || memcmp(key, sim->graph_key, sizeof key) != 0) {
             if (sim->gen_graph) { cudaGraphExecDestroy(sim->gen_graph); sim->gen_graph = nullptr; }
@@ -1461,7 +1474,7 @@ static int enqueue_generation(vl_sim *sim) {
     }
     std::swap(sim->h.hap_id, sim->h.hap_id_next);
     if (tiles) std::swap(sim->h.pop_fit, sim->h.pop_fit_next);
-    sim->pop_fit_valid = tiles;  // the children inherited their parents' mapped fitness (k_resample_tl)
+    sim->pop_fit_valid = tiles;  // the children inherited their parents' mapped fitness (k_resample_pos)
     sim->n_valid = false;
     sim->n_bound = std::min<uint64_t>(sim->h.cap_inf, sim->h.max_population);
     sim->csr_valid = false;

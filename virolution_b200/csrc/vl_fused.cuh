@@ -1,0 +1,444 @@
+// vl_fused.cuh — the device-resident generation (vl_run, vl_next_generation) for compartments with uniform infection
+// (every draw infects, hosts iid uniform: DevState::fast_infect), a reproductive fitness that does not depend on the
+// host, no recombination and Binomial(L, mu) in the inversion regime — K1, K2 and K4 of SURVEY.md §8.
+//
+// The reference builds a host map (counting sort by host, src/core/hosts.rs:166-192) because BasicHost::replicate needs
+// the fitness sum of every host's infectants (src/simulation.rs:137-152).  With H ~ N the slices have one member on
+// average, so grouping costs far more than the sums it enables: a scatter of one record per infectant is bound by the
+// SM's load/store pipeline (one 32-byte request per lane), and the measured sort + replicate kernels of that design spent
+// their issue slots on slice bookkeeping (profiles/r2_a_*).  Here nothing is grouped:
+//
+//   k_infect_sum      host ~ U[0, H) and the Binomial(L, mu) count of every infectant from one Philox block; the host is
+//                     kept per infectant (the reference's `infections`), the infectant's MAPPED FITNESS — carried with it
+//                     since it was drawn — is added to hsum[host] by an f64 atomic; mutating infectants go to the worklist
+//   k_mutate          (vl_kernels.cuh) new records; the new haplotype's mapped fitness replaces the carried value and is
+//                     added to hsum[host]
+//   k_offspring_sum   per infectant: S = hsum[host], lambda = f * R0 / S, Poisson(lambda) from the infectant's own
+//                     stream; offspring counts stay in infectant order; clears the other hsum buffer for the next generation
+//   k_plan_resample   (vl_kernels.cuh) sample size, exact multinomial split of the draws over tiles of RESAMPLE_TILE
+//                     consecutive infectants
+//   k_resample_pos    draws inside every tile; the drawn parent's haplotype AND mapped fitness become the child's
+//
+// Per infectant and generation: one scattered f64 reduction and one scattered 8-byte load on an H-entry array that L2
+// holds (80 MB at H = 10^7), everything else streams.  No per-haplotype array is read except by k_mutate.
+//
+// Per-host sums: the reference adds a host's fitness values in slice order (src/simulation.rs:144).  An atomic sum adds
+// them in arrival order.  For hosts with one or two members (74 % of the infectants at N = H) the two are the same f64
+// (one addition, commutative); with three or more members they can differ in the last bit, which moves lambda by one ulp
+// and changes a Poisson draw only if its uniform lies within ~1e-16 of a CDF value.  The replay path (bit-exactness
+// against the recorded draws) does not use this file; tests/test_gpu_fused_scale.py checks that the populations of vl_run and
+// of the trait-level calls agree infectant by infectant and that lambda agrees to 1e-15.
+//
+// Same draws as the trait-level path: hosts, mutation counts, mutations, offspring counts and resample draws are
+// addressed by (seed, compartment, generation, infectant / output slot), and every path resamples over tiles of
+// consecutive infectants (canonical_layout in virolution_gpu.cu).
+#pragma once
+#include "vl_kernels.cuh"
+
+namespace vl {
+
+// generation += 1 and the counters of a generation (one launch)
+__global__ void k_begin_generation_fused(DevState *st) {
+    st->generation += 1;  // Simulation::increment_generation (src/simulation.rs:178)
+    st->n_mut_list = 0;
+    st->n_heavy = 0;
+    st->n_medium = 0;
+    st->fused_failed = 0;
+    st->infectant_generations += st->n;
+}
+__global__ void __launch_bounds__(TPB) k_zero_f64(double *p, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = 0.0;
+}
+
+// ---- infect + mutation count + per-host sum ---------------------------------------------------------------------------
+// BasicSimulation::infect for uniform infection (src/simulation.rs:365-387 with one always-accepting draw per
+// infectant) and the Binomial(L, mu) count of BasicHost::mutate (:94-95), both from block 0 of the infectant's PH_INFECT
+// stream like k_infect / k_mutcount_fast.  GATHER: the mapped fitness comes from the per-haplotype memo (population
+// installed by anything but k_resample_pos) and is stored per infectant, otherwise it came with the infectant.
+constexpr int IS_TPB = 256;
+constexpr int IS_ITEMS = 4;
+template <bool GATHER>
+__device__ __forceinline__ void infect_sum_chunk(DevState *st, uint64_t c, uint64_t n, uint32_t H32, uint32_t thr, uint32_t gen, PhiloxKey key,
+                                                 const uint32_t *__restrict__ hap_id, double *__restrict__ pop_fit, const double *__restrict__ hfit,
+                                                 uint32_t *__restrict__ host_id, double *__restrict__ hsum, uint32_t *s_w, uint32_t *s_base) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr uint64_t CHUNK = (uint64_t)IS_TPB * IS_ITEMS;
+    uint32_t hp[IS_ITEMS], hh[IS_ITEMS], nmv[IS_ITEMS];
+    double ft[IS_ITEMS];
+#pragma unroll
+    for (int e = 0; e < IS_ITEMS; e++) {
+        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
+        hp[e] = i < n ? hap_id[i] : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < IS_ITEMS; e++) {
+        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
+        ft[e] = 0.0;
+        if (i < n) ft[e] = GATHER ? (hfit ? hfit[hp[e]] : 1.0) : pop_fit[i];
+    }
+    uint32_t mine = 0;
+#pragma unroll
+    for (int e = 0; e < IS_ITEMS; e++) {
+        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
+        hh[e] = NONE32;
+        nmv[e] = 0;
+        if (i >= n) continue;
+        const uint4 b0 = philox_block(key, i, gen, PH_INFECT, 0);
+        uint64_t m = (uint64_t)b0.x * H32;  // Uniform(0, H): widening multiply, biased zone rejected exactly (as k_infect)
+        if ((uint32_t)m < H32) {
+            for (uint32_t blk = 1; (uint32_t)m < thr; blk++) m = (uint64_t)philox_block(key, i, gen, PH_INFECT, blk).x * H32;
+        }
+        hh[e] = (uint32_t)(m >> 32);
+        nmv[e] = mutation_count_small(st, key, i, gen, b0);
+        mine += nmv[e] ? 1u : 0u;
+    }
+#pragma unroll
+    for (int e = 0; e < IS_ITEMS; e++) {
+        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
+        if (i >= n) continue;
+        host_id[i] = hh[e];
+        if (GATHER) pop_fit[i] = ft[e];
+        // a mutating infectant's fitness is about to change: k_mutate adds the new value (f == 0.0 adds nothing)
+        if (nmv[e] == 0u && ft[e] != 0.0) atomicAdd(&hsum[hh[e]], ft[e]);
+    }
+    // mutation worklist: (infectant, n_mut, host, parent haplotype); one global atomic per chunk
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += y;
+    }
+    __syncthreads();  // (s_w / s_base of the previous chunk have been read)
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < IS_TPB / 32; w++) {
+        const uint32_t t = s_w[w];
+        if (w < (int)wid) woff += t;
+        tot += t;
+    }
+    if (tid == 0) *s_base = tot ? atomicAdd(&st->n_mut_list, tot) : 0u;
+    __syncthreads();
+    if (mine) {
+        uint32_t o = *s_base + woff + inc - mine;
+#pragma unroll
+        for (int e = 0; e < IS_ITEMS; e++) {
+            const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
+            if (i < n && nmv[e]) st->mut_list[o++] = make_uint4((uint32_t)i, nmv[e], hh[e], hp[e]);
+        }
+    }
+}
+template <bool GATHER>
+__global__ void __launch_bounds__(IS_TPB, 4) k_infect_sum(DevState *st) {
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_w[IS_TPB / 32];
+    const uint64_t n = st->n;
+    const uint32_t H32 = (uint32_t)st->H;
+    if (H32 == 0) return;
+    const uint32_t thr = (uint32_t)(-H32) % H32;
+    const int pi0 = st->specs[0].repro;
+    constexpr uint64_t CHUNK = (uint64_t)IS_TPB * IS_ITEMS;
+    const uint64_t n_chunks = (n + CHUNK - 1) / CHUNK;
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
+        infect_sum_chunk<GATHER>(st, c, n, H32, thr, st->generation, philox_key(st->seed, st->compartment), st->hap_id, st->pop_fit,
+                                 pi0 >= 0 ? st->h_fit[pi0] : nullptr, st->host_id, st->hsum[st->hsum_parity], s_w, &s_base);
+}
+
+// ---- offspring counts in infectant order -------------------------------------------------------------------------------
+// BasicHost::replicate (src/simulation.rs:120-154) per infectant: lambda_i = f_i * R0 / S_host, Poisson(lambda_i) from the
+// infectant's PH_OFFSPRING stream (the same address k_offspring / k_replicate_fused use).  One CTA per resample tile
+// (RESAMPLE_TILE consecutive infectants) so that the tile's offspring total comes out of the same pass.  The grid also
+// clears the other hsum buffer: the next generation's sums start from zero without a pass of their own.
+constexpr int OS_TPB = 256;
+constexpr int OS_PER = RESAMPLE_TILE / OS_TPB;
+template <bool SMALL_ONLY>
+__global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
+    __shared__ uint64_t s_red[OS_TPB / 32];
+    const uint64_t n = st->n;
+    const uint64_t n_tiles = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint32_t *__restrict__ host_id = st->host_id;
+    const double *__restrict__ pop_fit = st->pop_fit;
+    const double *hsum = st->hsum[st->hsum_parity];
+    uint32_t *__restrict__ offspring = st->offspring;
+    const uint32_t gen = st->generation;
+    const double R0 = st->host_r0;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    const uint32_t kmax = poisson_kmax(R0 < 12.0 ? R0 : 12.0);  // lambda = R0 * f / S <= R0 for non-negative fitness
+    const uint32_t tid = threadIdx.x;
+    if (blockIdx.x == 0 && tid == 0) { st->n_sorted = n; st->host_tiles = 0; }  // tiles of consecutive infectants (tile_range)
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t p0 = tile * RESAMPLE_TILE;
+        uint32_t h[OS_PER];
+        double f[OS_PER], S[OS_PER];
+#pragma unroll
+        for (int j = 0; j < OS_PER; j++) {
+            const uint64_t p = p0 + (uint64_t)j * OS_TPB + tid;
+            h[j] = p < n ? host_id[p] : NONE32;
+            f[j] = p < n ? pop_fit[p] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < OS_PER; j++) S[j] = h[j] != NONE32 ? __ldcg(&hsum[h[j]]) : 1.0;
+        uint32_t local = 0;
+#pragma unroll
+        for (int j = 0; j < OS_PER; j++) {
+            const uint64_t p = p0 + (uint64_t)j * OS_TPB + tid;
+            if (p >= n) continue;
+            uint32_t off = 0;
+            const double l = checked_lambda(st, f[j], R0, S[j]);  // lambda_i = f_i * R0 / S_host (src/simulation.rs:148-150)
+            if (l > 0.0) {
+                uint64_t v;
+                if (l < 12.0) v = poisson_draw_small_fast(key, p, gen, PH_OFFSPRING, l, c_rcp64, kmax);
+                else if (SMALL_ONLY) { raise(st, DE_UNDEFINED_OFFSPRING); v = 0; }  // f > S: negative fitness values in the host
+                else v = poisson_ptrs(key, p, gen, PH_OFFSPRING, l);
+                if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
+                off = (uint32_t)v;
+            }
+            offspring[p] = off;
+            local += off;
+        }
+        uint64_t tot = local;
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, sh);
+        __syncthreads();
+        if ((tid & 31) == 0) s_red[tid >> 5] = tot;
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t t = 0;
+            for (int w = 0; w < OS_TPB / 32; w++) t += s_red[w];
+            st->tile_sum[tile] = t;
+        }
+    }
+    // the buffer the next generation accumulates into
+    double *other = st->hsum[st->hsum_parity ^ 1u];
+    const uint64_t H = st->H;
+    for (uint64_t k = (uint64_t)blockIdx.x * OS_TPB + tid; k < H; k += (uint64_t)gridDim.x * OS_TPB) other[k] = 0.0;
+}
+
+// ---- resample over tiles of consecutive infectants ---------------------------------------------------------------------
+// k_resample (vl_kernels.cuh) for offspring counts kept in infectant order next to hap_id[] / pop_fit[]: same tiles, same
+// record order inside a tile, same draw values and the same value -> record rule as k_resample on the identity layout of
+// the same offspring map, so the drawn haplotypes are the same.  The staged payload is (haplotype, mapped fitness): the
+// child inherits both.
+constexpr int RT_TPB = 512;
+constexpr int RT_PER = RESAMPLE_TILE / RT_TPB;  // stripes: item q = k * RT_TPB + tid (coalesced loads)
+static_assert(RANK_WORDS % RT_TPB == 0, "every thread owns RANK_WORDS / RT_TPB consecutive mask words");
+struct ResamplePosArgs {
+    uint32_t n_parts;
+    uint32_t salt[MAX_PARTS];
+    uint32_t *dst[MAX_PARTS];    // nullptr = the population being assembled (hap_id_next, pop_fit_next)
+    double *dst_fit[MAX_PARTS];  // mapped fitness of the drawn parents (may be nullptr when dst is a detached buffer)
+};
+__global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, ResamplePosArgs ra) {
+    __shared__ uint32_t s_hap[RESAMPLE_TILE];   // compacted payloads of the records with offspring
+    __shared__ double s_fit[RESAMPLE_TILE];
+    __shared__ uint32_t s_cdf[RESAMPLE_TILE];   // compacted inclusive CDF (guide path only)
+    __shared__ uint16_t s_guide[GUIDE_SIZE];
+    __shared__ uint32_t s_mask[RANK_WORDS + 1];
+    __shared__ uint16_t s_pre[RANK_WORDS];
+    __shared__ uint32_t s_wbits[RT_TPB / 32];
+    __shared__ uint64_t s_pcnt[MAX_PARTS], s_pbase[MAX_PARTS];
+    __shared__ uint32_t s_tv[RT_PER * (RT_TPB / 32)], s_tc[RT_PER * (RT_TPB / 32)];  // per (stripe, warp): offspring / non-zero records
+    __shared__ uint32_t s_total;
+    const uint64_t n = st->n;
+    const uint64_t nt = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    const uint32_t *__restrict__ offspring = st->offspring;
+    const uint32_t *__restrict__ hap_id = st->hap_id;
+    const double *__restrict__ pop_fit = st->pop_fit;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr uint32_t NW = RT_TPB / 32;
+    const PhiloxKey key = philox_key(st->seed, st->compartment);
+    const uint32_t gen = st->generation;
+    const uint64_t stride = st->tile_stride;
+    for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        uint64_t any = 0;
+        __syncthreads();  // (a tile without draws is left early: nobody may still be reading the shared arrays)
+        if (ra.n_parts == 1) {
+            any = st->tile_cnt[tile];
+        } else {
+            if (tid < ra.n_parts) {
+                s_pcnt[tid] = st->tile_cnt[tid * stride + tile];
+                s_pbase[tid] = st->tile_base[tid * stride + tile];
+            }
+            __syncthreads();
+            for (uint32_t p = 0; p < ra.n_parts; p++) any |= s_pcnt[p];
+        }
+        const uint64_t tsum = st->tile_sum[tile];
+        const uint64_t tbase1 = st->tile_base[tile];  // (single part; asked for with the other descriptors)
+        const uint64_t start = tile * RESAMPLE_TILE;
+        const uint32_t tlen = (uint32_t)(n - start < RESAMPLE_TILE ? n - start : RESAMPLE_TILE);
+        if (any == 0) continue;  // uniform across the CTA
+        if (tsum > 0xFFFFFFFFull) {  // the tile CDF is 32-bit
+            if (tid == 0) raise(st, DE_OFFSPRING_RANGE);
+            continue;
+        }
+        // ---- stripes of RT_TPB consecutive positions: warp scans of offspring and of the non-zero flags
+        uint32_t v[RT_PER], hp[RT_PER], iv[RT_PER], ic[RT_PER];
+        double ft[RT_PER];
+#pragma unroll
+        for (int k = 0; k < RT_PER; k++) {
+            const uint32_t q = k * RT_TPB + tid;
+            v[k] = q < tlen ? offspring[start + q] : 0u;
+            hp[k] = q < tlen ? hap_id[start + q] : 0u;
+            ft[k] = q < tlen ? pop_fit[start + q] : 0.0;
+        }
+        constexpr uint32_t WPT = RANK_WORDS / RT_TPB;  // mask words per thread
+#pragma unroll
+        for (uint32_t k = 0; k < WPT; k++) s_mask[tid * WPT + k] = 0u;
+        if (tid == 0) s_mask[RANK_WORDS] = 0u;
+#pragma unroll
+        for (int k = 0; k < RT_PER; k++) {
+            uint32_t a = v[k], c = v[k] ? 1u : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, a, d), z = __shfl_up_sync(0xFFFFFFFFu, c, d);
+                if (lane >= (uint32_t)d) { a += y; c += z; }
+            }
+            iv[k] = a;
+            ic[k] = c;
+            if (lane == 31) { s_tv[k * NW + wid] = a; s_tc[k * NW + wid] = c; }
+        }
+        __syncthreads();
+        if (wid == 0) {  // exclusive scan of the RT_PER * NW (stripe, warp) totals: two entries per lane
+            constexpr uint32_t NE = RT_PER * NW, EPL = (NE + 31) / 32;
+            uint32_t xa[EPL], xc[EPL], sa = 0, sc = 0;
+#pragma unroll
+            for (uint32_t u = 0; u < EPL; u++) {
+                const uint32_t idx = lane * EPL + u;
+                xa[u] = idx < NE ? s_tv[idx] : 0u;
+                xc[u] = idx < NE ? s_tc[idx] : 0u;
+                sa += xa[u];
+                sc += xc[u];
+            }
+            uint32_t ia = sa, icc = sc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, ia, d), z = __shfl_up_sync(0xFFFFFFFFu, icc, d);
+                if (lane >= (uint32_t)d) { ia += y; icc += z; }
+            }
+            if (lane == 31) s_total = ia;
+            uint32_t ra_ = ia - sa, rc_ = icc - sc;
+#pragma unroll
+            for (uint32_t u = 0; u < EPL; u++) {
+                const uint32_t idx = lane * EPL + u;
+                if (idx < NE) { s_tv[idx] = ra_; s_tc[idx] = rc_; }
+                ra_ += xa[u];
+                rc_ += xc[u];
+            }
+        }
+        __syncthreads();
+        const uint32_t total = s_total;
+        const bool direct = total <= RESAMPLE_RANK_MAX;
+        const double scale = (double)GUIDE_SIZE / (double)total;
+#pragma unroll
+        for (int k = 0; k < RT_PER; k++) {
+            if (!v[k]) continue;
+            const uint32_t lo = s_tv[k * NW + wid] + iv[k] - v[k];  // exclusive prefix of the offspring counts
+            const uint32_t slot = s_tc[k * NW + wid] + ic[k] - 1u;  // compacted index
+            s_hap[slot] = hp[k];
+            s_fit[slot] = ft[k];
+            if (direct) {
+                atomicOr(&s_mask[lo >> 5], 1u << (lo & 31));
+            } else {
+                const uint32_t hi = lo + v[k];
+                s_cdf[slot] = hi;
+                // guide[b] = this entry for every bucket b whose first reachable draw value (b*total) >> GUIDE_BITS lies in [lo, hi)
+                uint32_t bf = (uint32_t)((double)lo * scale);
+                if (bf > GUIDE_SIZE) bf = GUIDE_SIZE;
+                while (bf > 0 && (uint32_t)(((uint64_t)(bf - 1) * total) >> GUIDE_BITS) >= lo) bf--;
+                while (bf < GUIDE_SIZE && (uint32_t)(((uint64_t)bf * total) >> GUIDE_BITS) < lo) bf++;
+                for (uint32_t b = bf; b < GUIDE_SIZE && (uint32_t)(((uint64_t)b * total) >> GUIDE_BITS) < hi; b++) s_guide[b] = (uint16_t)slot;
+            }
+        }
+        __syncthreads();
+        if (direct) {  // set bits before every mask word: per-thread popc, warp scan, warp totals
+            uint32_t bits[WPT], mine = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < WPT; k++) { bits[k] = __popc(s_mask[tid * WPT + k]); mine += bits[k]; }
+            uint32_t binc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, binc, d);
+                if (lane >= (uint32_t)d) binc += y;
+            }
+            if (lane == 31) s_wbits[wid] = binc;
+            __syncthreads();
+            uint32_t before = binc - mine;
+#pragma unroll
+            for (int w = 0; w < (int)NW; w++)
+                if (w < (int)wid) before += s_wbits[w];
+#pragma unroll
+            for (uint32_t k = 0; k < WPT; k++) { s_pre[tid * WPT + k] = (uint16_t)before; before += bits[k]; }
+            __syncthreads();
+        }
+        // ---- draws of every part: output slots [base, base + c), four per Philox block (as k_resample)
+        uint32_t blocks_total = 0;
+        if (ra.n_parts > 1) {
+            for (uint32_t p = 0; p < ra.n_parts; p++) {
+                const uint64_t c = s_pcnt[p], b = s_pbase[p];
+                blocks_total += c ? (uint32_t)(((b + c - 1) >> 2) - (b >> 2) + 1) : 0u;
+            }
+        } else {
+            blocks_total = (uint32_t)(((tbase1 + any - 1) >> 2) - (tbase1 >> 2) + 1);
+        }
+        for (uint32_t e = tid; e < blocks_total; e += RT_TPB) {
+            uint32_t part = 0, before = 0;
+            uint64_t c = any, base = tbase1;
+            if (ra.n_parts > 1) {
+                for (;; part++) {
+                    c = s_pcnt[part];
+                    base = s_pbase[part];
+                    const uint32_t nb = c ? (uint32_t)(((base + c - 1) >> 2) - (base >> 2) + 1) : 0u;
+                    if (e < before + nb) break;
+                    before += nb;
+                }
+            }
+            const uint64_t salt = (uint64_t)ra.salt[part] << 48;
+            uint32_t *__restrict__ dst = ra.dst[part] ? ra.dst[part] : st->hap_id_next;
+            double *__restrict__ dstf = ra.dst[part] ? ra.dst_fit[part] : st->pop_fit_next;
+            const uint64_t q = (base >> 2) + (e - before);
+            const uint4 blk = philox_block(key, q | salt, gen, PH_RESAMPLE, 0);
+            const uint32_t xs[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint64_t s = q * 4 + w;
+                if (s < base || s >= base + c) continue;
+                uint32_t x = xs[w];
+                uint64_t mm = (uint64_t)x * total;
+                if ((uint32_t)mm < total) {  // biased zone of the widening multiply: exact rejection
+                    const uint32_t thr = (uint32_t)(-total) % total;
+                    if ((uint32_t)mm < thr) {
+                        Philox g(st->seed, st->compartment, gen, PH_RESAMPLE_RETRY, s | salt);
+                        do { x = g.u32(); mm = (uint64_t)x * total; } while ((uint32_t)mm < thr);
+                    }
+                }
+                const uint32_t r = (uint32_t)(mm >> 32);
+                uint32_t slot;
+                if (direct) {
+                    const uint32_t upto = s_mask[r >> 5] & (0xFFFFFFFFu >> (31 - (r & 31)));  // run starts at or below r in its word
+                    slot = (uint32_t)s_pre[r >> 5] + __popc(upto) - 1u;
+                } else {
+                    slot = s_guide[x >> (32 - GUIDE_BITS)];
+                    while (s_cdf[slot] <= r) slot++;
+                }
+                dst[s] = s_hap[slot];
+                if (dstf) dstf[s] = s_fit[slot];
+            }
+        }
+    }
+}
+
+// set_population of the device-resident generation: both per-infectant arrays swap, the sums change sides
+__global__ void k_swap_population_fused(DevState *st) {
+    uint32_t *t = st->hap_id;
+    st->hap_id = st->hap_id_next;
+    st->hap_id_next = t;
+    double *f = st->pop_fit;
+    st->pop_fit = st->pop_fit_next;
+    st->pop_fit_next = f;
+    st->n = st->n_next;
+    st->n_sorted = 0;
+    st->hsum_parity ^= 1u;
+}
+
+}  // namespace vl

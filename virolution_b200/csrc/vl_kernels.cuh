@@ -525,6 +525,18 @@ __global__ void __launch_bounds__(TPB) k_identity_records(DevState *st) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_sorted = n; st->host_tiles = 0; }
 }
 
+// offspring counts moved from CSR positions to infectant order (tmp[i], zero for uninfected infectants): every path
+// resamples over tiles of RESAMPLE_TILE consecutive infectants, so the draws of a generation do not depend on which
+// kernels built its offspring map
+__global__ void __launch_bounds__(TPB) k_identity_from(DevState *st, const uint32_t *__restrict__ tmp) {
+    const uint64_t n = st->n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        st->offspring[i] = tmp[i];
+        st->rec[i] = make_uint2((uint32_t)i, st->hap_id[i]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->n_sorted = n; st->host_tiles = 0; }
+}
+
 // ------------------------------------------------------------------------------------------ haplotype records
 struct NewRecord {
     uint32_t id;
@@ -809,8 +821,8 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
 // raw fitness of every provider incrementally: raw(parent) * fold(acc * T[pos,to] / T[pos,from])
 // (src/core/fitness/table.rs:65-68) [* epistatic update].  patch_records: 1 = the infectant's CSR record is
 // patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist,
-// 3 = tile-strided generation: items are (infectant, n_mut | host-in-tile << 16, reserved slot, parent) and the
-// slot's record is written here.
+// 3 = device-resident generation (vl_fused.cuh): items are (infectant, n_mut, host, parent); the carried fitness of the
+// infectant is replaced and added to its host's sum.
 constexpr uint32_t MUT_LOCAL_PARENT = 16;  // parent records up to this length are staged in thread-local memory
 constexpr uint32_t MUT_LOCAL_CHANGES = 8;  // mutation events up to this many sites keep their change words there too
 constexpr uint32_t MUT_SCRATCH_STRIDE = MUT_LOCAL_PARENT + MUT_LOCAL_CHANGES + HEAD_INLINE + 1;  // odd: consecutive threads hit distinct banks
@@ -833,7 +845,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_list; base += span) {
         const uint32_t w = base + lane;
         const bool active = w < n_list;
-        uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32, hl = 0;
+        uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32;
         HapMeta pm{0, 0, NONE32};
         MutHead ph;
         ph.valid = 0u;
@@ -841,7 +853,6 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
             const uint4 item = st->mut_list[w];
             i = item.x;
             nm = item.y;
-            if (patch_records == 3) { hl = nm >> 16; nm &= 0xFFFFu; }
             tpos = item.z;
             pid = parent_in_item ? item.w : st->hap_id[i];
             ph = st->mh[pid];  // ONE 64-byte line: arena offset, length, raw fitness and the first entries of the parent
@@ -977,13 +988,10 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
         st->hm[new_id] = HapMeta{roff, o, pid};
         st->hap_id[i] = new_id;
         if (patch_records == 3) {
-            // tile-strided generation: the slot of this infectant's record was reserved by the prefill pass, the record
-            // itself is written here, with the new haplotype and its mapped fitness
-            if (tpos != NONE32) {
-                const unsigned long long fb = (unsigned long long)__double_as_longlong(fit_repro);
-                st->tl_rec[tpos] = make_uint4(i, new_id, (uint32_t)fb, (uint32_t)(fb >> 32));
-                st->tl_hl[tpos] = (uint16_t)hl;
-            }
+            // device-resident generation (vl_fused.cuh): items carry the host in .z; the new haplotype's mapped fitness
+            // replaces the infectant's carried value and joins its host's sum (the infect pass left mutating infectants out)
+            st->pop_fit[i] = fit_repro;
+            if (tpos != NONE32 && fit_repro != 0.0) atomicAdd(&st->hsum[st->hsum_parity][tpos], fit_repro);
         } else if (patch_records == 2) {
             if (tpos != NONE32) st->tmp_rec[tpos].y = new_id;  // the bucket-partitioned record, not yet sorted
         } else if (patch_records) {

@@ -39,11 +39,6 @@ constexpr int MAX_PARTS = 16;              // subsamples of one offspring map th
 constexpr uint32_t HT_MAX_HOSTS = 2048;   // most hosts a host-range tile may span (DevState::host_tiles holds the actual number)
 constexpr uint32_t HT_MIN_HOSTS = 256;    // below this the fused replicate kernel is not worth launching
 constexpr double HT_SPREAD_CTAS = 148.0;  // tiles of a small host population are shrunk until there are about two per SM of a B200
-// ---- tile-strided layout of the fused generation (vl_tiles.cuh): a host tile is a power-of-two range of hosts, its
-// records live at [tile * TL_CAP, tile * TL_CAP + fill[tile]) — no dense CSR positions, no offsets[] array
-constexpr uint32_t TL_CAP = RESAMPLE_TILE;  // records a host tile can hold (what one CTA stages)
-constexpr uint32_t TL_FILL_STRIDE = 32;     // u32 words between the append cursors of consecutive tiles
-
 // error bits raised by kernels (sticky until vl_* reports them)
 enum DevError : uint32_t {
     DE_HAP_CAPACITY = 1u,       // haplotype table full
@@ -155,14 +150,10 @@ struct DevState {
     uint4 *tmp_rec;        // bucket-partitioned records (index, haplotype, host, -), bucket b at [b * stride, b * stride + fill)
     uint64_t cap_tmp;
 
-    // ---- tile-strided generation (vl_tiles.cuh): records appended per host tile, sorted and replicated per tile
-    uint4 *tl_rec;         // (infectant index, haplotype, mapped fitness lo, hi) as appended, tile t at [t * TL_CAP, ..)
-    uint16_t *tl_hl;       // host - first host of the tile, per appended record
-    uint4 *tl_sorted;      // per tile position in host order: (offspring, haplotype, mapped fitness lo, hi)
-    uint32_t *tl_fill;     // records per tile (append cursors), TL_FILL_STRIDE words apart
-    uint64_t tl_tiles_cap; // tiles the three arrays have room for
-    uint32_t tl_shift;     // log2(hosts per tile) of the records in tl_rec
-    uint32_t layout;       // 0: offspring[] / rec[] at dense CSR positions, 1: tl_sorted (tile-strided)
+    // ---- device-resident generation (vl_fused.cuh): per-host fitness sums by f64 atomics, no host map
+    double *hsum[2];       // H sums each: generation g accumulates into hsum[hsum_parity] and clears the other one
+    uint32_t hsum_parity;
+    uint32_t _pad5;
     double *pop_fit, *pop_fit_next;  // mapped reproductive fitness per infectant, parallel to hap_id / hap_id_next (valid when the host says so)
 
     // ---- mutation worklist
@@ -239,11 +230,7 @@ __device__ __forceinline__ uint64_t tile_count(const DevState *st) {
     return ht ? (st->H + ht - 1) / ht : (st->n_sorted + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
 }
 __device__ __forceinline__ void tile_range(const DevState *st, uint64_t tile, uint64_t &start, uint32_t &len) {
-    if (st->layout) {
-        start = tile * TL_CAP;
-        len = st->tl_fill[tile * TL_FILL_STRIDE];
-        if (len > TL_CAP) len = TL_CAP;
-    } else if (st->host_tiles) {
+    if (st->host_tiles) {
         const uint64_t ht = st->host_tiles;
         const uint64_t h0 = tile * ht, h1 = h0 + ht < st->H ? h0 + ht : st->H;
         start = st->offsets[h0];
