@@ -83,6 +83,8 @@ struct vl_sim {
     bool bucket_pending = false;  // records are bucket-partitioned, the host map is not built yet
     bool uniform_infection = false;  // the host map came from uniform Philox draws over [0, H) (no replay, DevState::fast_infect)
     bool pop_fit_valid = false;   // pop_fit[] holds the mapped reproductive fitness of every infectant of the current population
+    bool prefilled = false;       // the last resample drew the next generation's hosts and mutation counts (k_resample_pos<true>)
+    bool hsum_dirty = false;      // ... and that work was dropped: hsum[parity] holds stale sums, cleared before the next infect pass
     uint32_t plan_smem_tiles = 0;
     uint32_t salt = 0;        // distinguishes the sampling streams of one generation
     uint32_t gens_since_gc = 0, gc_period = 1;
@@ -94,6 +96,12 @@ struct vl_sim {
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     char err[512] = {0};
 };
+
+// whatever changes the population, the parameters or the record ids between two generations of the device-resident
+// loop drops the infection the last resample prepared (hosts, mutation worklist, per-host sums of the next generation)
+static inline void drop_prefill(vl_sim *sim) {
+    if (sim->prefilled) { sim->prefilled = false; sim->hsum_dirty = true; }
+}
 
 // records the start event of a profiled launch and returns the stop event to record after it
 static cudaEvent_t prof_begin(vl_sim *sim, const char *name) {
@@ -319,8 +327,8 @@ static int alloc_host_buffers(vl_sim *sim, uint64_t H) {
     TRY(dev_alloc(sim, &h.offsets, H + 8, false));
     TRY(dev_alloc(sim, &sim->count, H + 8, false));
     // per-host fitness sums of the device-resident generation (vl_fused.cuh), both cleared: a generation accumulates into
-    // hsum[parity] and clears the other.  One allocation, kept in L2 as far as the device allows: every infectant does one
-    // scattered f64 reduction and one scattered load on it per generation, everything else streams past.
+    // hsum[parity] and clears the other.  (Pinning the array in L2 with an access-policy window was measured and dropped:
+    // the 83 MB set aside for it cost the other kernels more than it saved — 1.66 against 0.96 ms per generation at K2.)
     if (h.hsum[0]) cudaFree(h.hsum[0]);
     h.hsum[0] = h.hsum[1] = nullptr;
     if (!(sim->flags & VL_FLAG_NO_TILES)) {
@@ -328,24 +336,6 @@ static int alloc_host_buffers(vl_sim *sim, uint64_t H) {
         TRY(dev_alloc(sim, &h.hsum[0], 2 * per, false));
         h.hsum[1] = h.hsum[0] + per;
         CU(sim, cudaMemset(h.hsum[0], 0, 2 * per * sizeof(double)));
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, sim->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, sim->device);
-        if (max_persist > 0 && max_window > 0 && !(sim->experiment & 16)) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-            cudaStreamAttrValue av;
-            memset(&av, 0, sizeof av);
-            const uint64_t bytes = std::min<uint64_t>(2 * per * sizeof(double), (uint64_t)max_window);
-            av.accessPolicyWindow.base_ptr = h.hsum[0];
-            av.accessPolicyWindow.num_bytes = bytes;
-            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)bytes);
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(sim->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-            if (getenv("VL_DEBUG")) fprintf(stderr, "[vl] persisting L2: max %d B, window max %d B, hsum %llu B, hit ratio %.3f\n", max_persist, max_window,
-                                            (unsigned long long)(2 * per * sizeof(double)), av.accessPolicyWindow.hitRatio);
-            cudaGetLastError();
-        }
     }
     sim->cap_H = H;
     return VL_OK;
@@ -520,7 +510,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     {
         size_t free_b = 0, total_b = 0;
         CCU(cudaMemGetInfo(&free_b, &total_b));
-        const double fit = 0.45 * (double)free_b / ((double)cap_inf * 340.0);
+        const double fit = 0.45 * (double)free_b / ((double)cap_inf * 230.0);
         hap_room = (uint64_t)std::min(16.0, std::max(6.0, floor(fit)));
     }
     uint64_t cap_hap = cfg->capacity_haplotypes ? cfg->capacity_haplotypes : hap_room * cap_inf + 65536;
@@ -530,7 +520,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
         size_t free_b = 0, total_b = 0;
         CCU(cudaMemGetInfo(&free_b, &total_b));
         const uint64_t P = std::max<uint32_t>(h.n_providers, 1);
-        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 80 + ch * (180 + 32 * P) + ca * 8; };
+        auto need = [&](uint64_t ch, uint64_t ca) { return cap_inf * 100 + ch * (130 + 32 * P) + ca * 8; };
         if (!cfg->capacity_haplotypes || !cfg->capacity_arena_words) {
             for (int it = 0; it < 64 && need(cap_hap, cap_arena) > (uint64_t)(0.7 * (double)free_b); it++) {
                 if (!cfg->capacity_arena_words && cap_arena > (1ull << 20)) cap_arena = cap_arena * 3 / 4;
@@ -548,6 +538,8 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     h.binv = make_binv(L, par.mutation_rate);
     CCU(cudaFuncSetAttribute(k_plan_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CCU(cudaFuncSetAttribute(k_host_sum_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
+    CCU(cudaFuncSetAttribute(k_mutate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute(k_resample_pos<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
     h.gc_arena_threshold = cap_arena / 2;
@@ -557,26 +549,24 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     { const char *e = getenv("VL_EXPERIMENT"); sim->experiment = e ? atoi(e) : 0; }
     CTRY(alloc_population_buffers(sim, cap_inf));
     CTRY(alloc_host_buffers(sim, h.H));
-    CTRY(dev_alloc(sim, &h.hm, cap_hap)); CTRY(dev_alloc(sim, &h.hm_alt, cap_hap));
-    CTRY(dev_alloc(sim, &h.mh, cap_hap)); CTRY(dev_alloc(sim, &h.mh_alt, cap_hap));
+    CTRY(dev_alloc(sim, &h.head, cap_hap)); CTRY(dev_alloc(sim, &h.head_alt, cap_hap));
     for (uint32_t p = 0; p < h.n_providers; p++) {
         CTRY(dev_alloc(sim, &h.h_raw[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_raw_alt[p], cap_hap));
         CTRY(dev_alloc(sim, &h.h_fit[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_fit_alt[p], cap_hap));
     }
-    CTRY(dev_alloc(sim, &h.arena, cap_arena)); CTRY(dev_alloc(sim, &h.arena_alt, cap_arena));
-    CTRY(dev_alloc(sim, &h.gc_mark, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_newid, cap_hap + 1)); CTRY(dev_alloc(sim, &h.gc_len, cap_hap + 1));
-    CTRY(dev_alloc(sim, &h.gc_newoff, cap_hap + 1));
+    CTRY(dev_alloc(sim, &h.arena, cap_arena + 16)); CTRY(dev_alloc(sim, &h.arena_alt, cap_arena + 16));  // (padded: the search window of entries_lower_interp may overhang a list)
+    {
+        const uint64_t gw = cap_hap / 32 + 8;  // one bit-map word per 32 records
+        CTRY(dev_alloc(sim, &h.gc_bits, gw)); CTRY(dev_alloc(sim, &h.gc_wcnt, gw)); CTRY(dev_alloc(sim, &h.gc_wlen, gw));
+        CTRY(dev_alloc(sim, &h.gc_cbase, gw)); CTRY(dev_alloc(sim, &h.gc_lbase, gw));
+    }
     CTRY(dev_alloc(sim, &sim->gc_totals, 16));
     CCU(cudaMemset(sim->gc_totals, 0, 16 * 8));
-    sim->scan_work_words = 8 + (std::max<uint64_t>(std::max<uint64_t>(cap_hap, h.H), cap_inf) + SCAN_TILE) / SCAN_TILE;
+    sim->scan_work_words = 8 + (std::max<uint64_t>(std::max<uint64_t>(cap_hap / 32 + 8, h.H), cap_inf) + SCAN_TILE) / SCAN_TILE;
     CTRY(dev_alloc(sim, &sim->scan_work, sim->scan_work_words, false));
     // haplotype 0 = wildtype: no entries, raw fitness = empty product (src/core/fitness/table.rs:72-79)
     h.n_hap = 1;
     h.arena_top = 0;
-    {
-        HapMeta wt{0, 0, NONE32};
-        CCU(cudaMemcpy(h.hm, &wt, sizeof(HapMeta), cudaMemcpyHostToDevice));
-    }
     CTRY(dev_alloc(sim, &sim->d, 1));
     CCU(cudaMemcpy(sim->d, &h, sizeof(DevState), cudaMemcpyHostToDevice));
     k_init_wildtype<<<1, 1, 0, sim->stream>>>(sim->d);  // raw fitness 1 and its mapped value under every provider
@@ -612,6 +602,7 @@ VL_API int vl_synchronize(vl_sim *sim) {
 // ---------------------------------------------------------------------------------------------- trait: scalars
 VL_API int vl_increment_generation(vl_sim *sim) {
     ENTER(sim);
+    drop_prefill(sim);
     LAUNCH(sim, k_tick, 1, 1, 0, sim->d);
     sim->salt = 0;
     return VL_OK;
@@ -626,11 +617,13 @@ VL_API int vl_get_generation(const vl_sim *csim, uint64_t *out) {
 }
 VL_API int vl_set_generation(vl_sim *sim, uint64_t generation) {
     ENTER(sim);
+    drop_prefill(sim);
     return write_field(sim, FIELD_OFF(generation), (uint32_t)generation);
 }
 VL_API int vl_set_parameters(vl_sim *sim, const vl_parameters *p) {
     ENTER(sim);
     if (!p) return fail(sim, VL_ERR_ARGUMENT, "null parameters");
+    drop_prefill(sim);
     if (p->host_population_size >= 0xFFFFFFFFull) return fail(sim, VL_ERR_ARGUMENT, "host_population_size must fit 32 bits");
     // BasicSimulation::set_parameters (src/simulation.rs:355-363) replaces the simulation's copy only; the
     // BasicHost copies (mutation/recombination rate, R0, substitution matrix) keep their construction values.
@@ -666,6 +659,7 @@ VL_API int vl_population_len(vl_sim *sim, uint64_t *out) {
 }
 VL_API int vl_set_population_wildtype(vl_sim *sim, uint64_t n) {
     ENTER(sim);
+    drop_prefill(sim);
     if (n > sim->h.cap_inf) {
         CU(sim, cudaStreamSynchronize(sim->stream));
         if (!sim->pops.empty()) return fail(sim, VL_ERR_CAPACITY, "population of %llu exceeds capacity_infectants %llu", (unsigned long long)n, (unsigned long long)sim->h.cap_inf);
@@ -734,6 +728,7 @@ static int enqueue_bucket_host_map(vl_sim *sim) {
 }
 static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
     const DevState &h = sim->h;
+    drop_prefill(sim);
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec;
     const bool fuse = !replay && h.binv.ok;
     const bool fast = h.fast_infect != 0;
@@ -780,6 +775,7 @@ static int enqueue_infect(vl_sim *sim, bool defer_host_map = false) {
 }
 static int enqueue_mutate(vl_sim *sim) {
     const DevState &h = sim->h;
+    drop_prefill(sim);
     sim->pop_fit_valid = false;  // recombinants and mutants replace haplotypes of the current population
     const bool replay = sim->has_rp_mut || sim->has_rp_rec;
     ReplayRecomb rr{sim->rp_rec_n, sim->rp_rec_host, sim->rp_rec_i, sim->rp_rec_j, sim->rp_rec_s0, sim->rp_rec_s1, sim->rp_rec_which};
@@ -804,7 +800,7 @@ static int enqueue_mutate(vl_sim *sim) {
         TRY(zero_field32(sim, FIELD_OFF(n_mut_list)));
         LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, mutate_smem_bytes(h.L), sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0);
     sim->pop_fit_valid = false;  // haplotypes of the current population changed
     sim->mutcounts_ready = false;
     sim->has_rp_mut = false;
@@ -870,7 +866,8 @@ static int canonical_layout(vl_sim *sim) {
 }
 // plan + draws of n parts of the current offspring map in one pass each (n <= MAX_PARTS)
 static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, int use_amount, const uint64_t *amount, int set_next,
-                                uint32_t *const *dst, uint64_t *dst64, int mode, bool tiles = false, double *const *dst_fit = nullptr) {
+                                uint32_t *const *dst, uint64_t *dst64, int mode, bool tiles = false, double *const *dst_fit = nullptr,
+                                bool prefill = false) {
     if (n == 0 || n > (uint32_t)MAX_PARTS) return fail(sim, VL_ERR_ARGUMENT, "between 1 and %d parts per pass", MAX_PARTS);
     if (!tiles) TRY(canonical_layout(sim));
     PlanArgs pa;
@@ -903,7 +900,9 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
         memset(&rt, 0, sizeof rt);
         rt.n_parts = n;
         for (uint32_t k = 0; k < n; k++) { rt.salt[k] = ra.salt[k]; rt.dst[k] = ra.dst[k]; rt.dst_fit[k] = dst_fit ? dst_fit[k] : nullptr; }
-        LAUNCH(sim, k_resample_pos, (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8), RT_TPB, 0, sim->d, rt);
+        const unsigned rg = (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8);
+        if (prefill && n == 1 && !rt.dst[0]) LAUNCH(sim, k_resample_pos<true>, rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
+        else LAUNCH(sim, k_resample_pos<false>, rg, RT_TPB, 0, sim->d, rt);
         return VL_OK;
     }
     LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, ra, dst64, mode);
@@ -917,16 +916,18 @@ static int enqueue_resample(vl_sim *sim, double factor, int use_amount, uint64_t
 }
 static int enqueue_gc(vl_sim *sim, int force) {
     const DevState &h = sim->h;
+    drop_prefill(sim);  // (record ids change)
     const uint32_t *active = (const uint32_t *)((const char *)sim->d + FIELD_OFF(gc_active));
-    const uint64_t *nh_ptr = (const uint64_t *)((const char *)sim->d + FIELD_OFF(n_hap));
+    const uint64_t *nw_ptr = (const uint64_t *)((const char *)sim->d + FIELD_OFF(gc_nw));
+    const uint64_t gw = h.cap_hap / 32 + 8;
     LAUNCH(sim, k_gc_begin, 1, 1, 0, sim->d, force);
-    LAUNCH(sim, k_gc_clear, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
-    LAUNCH(sim, k_gc_mark, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (const uint32_t *)nullptr, (uint64_t)0, 1);
-    for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_mark, grid_for(sim, p->cap), TPB, 0, sim->d, (const uint32_t *)p->ids, p->n, 0);
-    LAUNCH(sim, k_gc_lens, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
-    TRY((launch_scan<uint32_t, true>(sim, h.gc_mark, h.gc_newid, nh_ptr, 0, h.cap_hap, sim->gc_totals + 0, 0, active)));
-    TRY((launch_scan<uint64_t, true>(sim, h.gc_len, h.gc_newoff, nh_ptr, 0, h.cap_hap, sim->gc_totals + 1, 0, active)));
-    LAUNCH(sim, k_gc_copy, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
+    LAUNCH(sim, k_gc_clear, grid_for(sim, gw), TPB, 0, sim->d, 1, 1);
+    LAUNCH(sim, k_gc_mark, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (const uint32_t *)nullptr, (uint64_t)0, 1, 1, 0);
+    for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_mark, grid_for(sim, p->cap), TPB, 0, sim->d, (const uint32_t *)p->ids, p->n, 0, 1, 0);
+    LAUNCH(sim, k_gc_words, grid_for(sim, gw), TPB, 0, sim->d, 1);
+    TRY((launch_scan<uint32_t, true>(sim, h.gc_wcnt, h.gc_cbase, nw_ptr, 0, gw, sim->gc_totals + 0, 0, active)));
+    TRY((launch_scan<uint64_t, true>(sim, h.gc_wlen, h.gc_lbase, nw_ptr, 0, gw, sim->gc_totals + 1, 0, active)));
+    LAUNCH(sim, k_gc_copy, grid_for(sim, gw), TPB, 0, sim->d);
     LAUNCH(sim, k_gc_remap, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (uint32_t *)nullptr, (uint64_t)0, 1);
     for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_remap, grid_for(sim, p->cap), TPB, 0, sim->d, p->ids, p->n, 0);
     LAUNCH(sim, k_gc_end, 1, 1, 0, sim->d, sim->gc_totals);
@@ -1129,19 +1130,20 @@ VL_API int vl_pop_free(vl_pop *pop) {
 static int pack_pop(vl_sim *sim, vl_pop *pop) {
     if (pop->image) return VL_OK;
     const DevState &h = sim->h;
-    const uint64_t *nh_ptr = (const uint64_t *)((const char *)sim->d + FIELD_OFF(n_hap));
-    LAUNCH(sim, k_pack_clear, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
-    LAUNCH(sim, k_pack_mark, grid_for(sim, pop->n), TPB, 0, sim->d, (const uint32_t *)pop->ids, pop->n);
-    LAUNCH(sim, k_pack_lens, grid_for(sim, h.cap_hap), TPB, 0, sim->d);
-    TRY((launch_scan<uint32_t, true>(sim, h.gc_mark, h.gc_newid, nh_ptr, 0, h.cap_hap, sim->gc_totals + 2, 0, nullptr)));
-    TRY((launch_scan<uint64_t, true>(sim, h.gc_len, h.gc_newoff, nh_ptr, 0, h.cap_hap, sim->gc_totals + 3, 0, nullptr)));
+    const uint64_t gw = h.cap_hap / 32 + 8;
+    const uint64_t *nw_ptr = (const uint64_t *)((const char *)sim->d + FIELD_OFF(gc_nw));
+    LAUNCH(sim, k_gc_clear, grid_for(sim, gw), TPB, 0, sim->d, 0, 0);
+    LAUNCH(sim, k_gc_mark, grid_for(sim, pop->n), TPB, 0, sim->d, (const uint32_t *)pop->ids, pop->n, 0, 0, 1);
+    LAUNCH(sim, k_gc_words, grid_for(sim, gw), TPB, 0, sim->d, 0);
+    TRY((launch_scan<uint32_t, true>(sim, h.gc_wcnt, h.gc_cbase, nw_ptr, 0, gw, sim->gc_totals + 2, 0, nullptr)));
+    TRY((launch_scan<uint64_t, true>(sim, h.gc_wlen, h.gc_lbase, nw_ptr, 0, gw, sim->gc_totals + 3, 0, nullptr)));
     CU(sim, cudaMemcpyAsync(sim->pin, sim->gc_totals + 2, 16, cudaMemcpyDeviceToHost, sim->stream));
     CU(sim, cudaStreamSynchronize(sim->stream));
     const uint64_t n_unique = sim->pin[0], n_words = sim->pin[1];
     PackHeader hd = make_pack_header(pop->n, n_unique, n_words, h.n_providers);
     CU(sim, cudaMalloc((void **)&pop->image, hd.bytes));
     pop->image_bytes = hd.bytes;
-    LAUNCH(sim, k_pack_copy, grid_for(sim, std::max<uint64_t>(h.cap_hap, pop->n)), TPB, 0, sim->d, (const uint32_t *)pop->ids, pop->image, hd);
+    LAUNCH(sim, k_pack_copy, grid_for(sim, std::max<uint64_t>(gw, pop->n)), TPB, 0, sim->d, (const uint32_t *)pop->ids, pop->image, hd);
     return VL_OK;
 }
 VL_API int vl_pop_pack_device(vl_sim *origin, vl_pop *pop, void **image_device, uint64_t *bytes) {
@@ -1302,6 +1304,7 @@ VL_API int vl_subsample_populations(vl_sim *sim, const double *factors, uint32_t
 
 VL_API int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts) {
     ENTER(sim);
+    drop_prefill(sim);
     uint64_t total = 0;
     for (uint32_t k = 0; k < n_parts; k++) {
         if (!parts[k]) return fail(sim, VL_ERR_ARGUMENT, "null part");
@@ -1364,6 +1367,7 @@ VL_API int vl_set_population(vl_sim *sim, vl_pop *const *parts, uint32_t n_parts
 // (src/runner.rs:382-399; the first half of Simulation::next_generation, src/simulation.rs:200-214)
 static int enqueue_generation_front(vl_sim *sim) {
     const DevState &h = sim->h;
+    drop_prefill(sim);
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
     sim->salt = 0;
     const bool fast_flow = !(sim->experiment & 1) && !replay && h.binv.ok && !(h.host_recombination_rate > 0.0) && buckets_possible(sim) &&
@@ -1373,7 +1377,7 @@ static int enqueue_generation_front(vl_sim *sim) {
         // depend on its host, so mutate first and build the host map from the already-mutated population
         LAUNCH(sim, k_begin_generation, 1, 1024, 0, sim->d);
         LAUNCH(sim, k_mutcount_fast, grid_tiles(sim, sim->n_bound, (uint64_t)TPB * MC_ITEMS, 8), TPB, 0, sim->d);
-        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, 0, sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0, 1);
+        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0, 1);
         const int btpb = (sim->experiment & 2) ? 512 : 1024;
         const unsigned chunks = (unsigned)std::max<uint64_t>(1, (sim->n_bound + btpb * BUCKET_ITEMS - 1) / (btpb * BUCKET_ITEMS));
         if (btpb == 1024) LAUNCH(sim, (k_infect_bucket<false, false, 1024>), chunks, 1024, 0, sim->d);
@@ -1395,29 +1399,42 @@ static bool fused_now(const vl_sim *sim) {
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
     return !replay && fused_possible(sim);
 }
-static int enqueue_generation_fused(vl_sim *sim) {
+__global__ void __launch_bounds__(TPB) k_zero_hsum_current(DevState *st) {
+    double *p = st->hsum[st->hsum_parity];
+    const uint64_t H = st->H;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < H; k += (uint64_t)gridDim.x * blockDim.x) p[k] = 0.0;
+}
+// prefill_next: this generation's resample also draws the next generation's hosts and mutation counts
+static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
     const DevState &h = sim->h;
     sim->salt = 0;
-    LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d);
-    const unsigned ig = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + IS_TPB * IS_ITEMS - 1) / (IS_TPB * IS_ITEMS)), (uint64_t)sim->n_sms * 32);
-    if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
-    else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, 0, sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 3, 1);
+    const bool prefilled = sim->prefilled;
+    LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d, prefilled ? 1 : 0);
+    if (!prefilled) {
+        if (sim->hsum_dirty) LAUNCH(sim, k_zero_hsum_current, grid_for(sim, h.H), TPB, 0, sim->d);
+        sim->hsum_dirty = false;
+        const unsigned ig = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
+        if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
+        else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
+    }
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, prefilled ? 4 : 3, 1);
     const unsigned og = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, og, OS_TPB, 0, sim->d);
     else LAUNCH(sim, k_offspring_sum<false>, og, OS_TPB, 0, sim->d);
     const double one = 1.0;
     uint32_t *dsts[1] = {nullptr};
-    TRY(launch_plan_resample(sim, 1, &one, 0, nullptr, 1, dsts, nullptr, 0, true));
+    TRY(launch_plan_resample(sim, 1, &one, 0, nullptr, 1, dsts, nullptr, 0, true, nullptr, prefill_next));
     LAUNCH(sim, k_swap_population_fused, 1, 1, 0, sim->d);
+    sim->prefilled = prefill_next;
     sim->uniform_infection = true;
     sim->mutcounts_ready = false;
     sim->bucket_pending = false;
     return VL_OK;
 }
 // the kernels of one whole generation (everything but the occasional compaction)
-static int enqueue_generation_kernels(vl_sim *sim, bool tiles) {
-    if (tiles) return enqueue_generation_fused(sim);
+static int enqueue_generation_kernels(vl_sim *sim, bool tiles, bool prefill_next) {
+    if (tiles) return enqueue_generation_fused(sim, prefill_next);
+    drop_prefill(sim);
     TRY(enqueue_generation_front(sim));
     TRY(enqueue_resample(sim, 1.0, 0, 0, nullptr, nullptr, 0, 1));
     LAUNCH(sim, k_swap_population, 1, 1, 0, sim->d);
@@ -1433,16 +1450,20 @@ static bool graph_wanted(const vl_sim *sim) {
 static int enqueue_generation(vl_sim *sim) {
     // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
     const bool tiles = fused_now(sim);
+    if (!tiles) drop_prefill(sim);
+    // (a compaction renumbers the records: the generation before one does not prepare the next)
+    const bool prefill_next = tiles && sim->gens_since_gc + 1 < sim->gc_period && !(sim->experiment & 32);
     if (graph_wanted(sim)) {
         const DevState &h = sim->h;
         const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets ^ (uint64_t)(uintptr_t)h.hsum[0],
-                                 (uint64_t)sim->flags | (tiles ? 1ull << 40 : 0) | (sim->pop_fit_valid ? 1ull << 41 : 0)};
+                                 (uint64_t)sim->flags | (tiles ? 1ull << 40 : 0) | (sim->pop_fit_valid ? 1ull << 41 : 0) | (sim->prefilled ? 1ull << 42 : 0) |
+                                     (prefill_next ? 1ull << 43 : 0) | (sim->hsum_dirty ? 1ull << 44 : 0)};
         if (!sim->gen_graph || memcmp(key, sim->graph_key, sizeof key) != 0) {
             if (sim->gen_graph) { cudaGraphExecDestroy(sim->gen_graph); sim->gen_graph = nullptr; }
             cudaGraph_t graph = nullptr;
             const uint64_t l0 = sim->launches;
             if (cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                const int rc = enqueue_generation_kernels(sim, tiles);
+                const int rc = enqueue_generation_kernels(sim, tiles, prefill_next);
                 const cudaError_t ce = cudaStreamEndCapture(sim->stream, &graph);
                 if (rc == VL_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&sim->gen_graph, graph, 0) == cudaSuccess) {
                     memcpy(sim->graph_key, key, sizeof key);
@@ -1462,15 +1483,16 @@ static int enqueue_generation(vl_sim *sim) {
         if (sim->gen_graph) {
             CU(sim, cudaGraphLaunch(sim->gen_graph, sim->stream));
             sim->launches += sim->graph_launches;
+            if (tiles) { sim->prefilled = prefill_next; sim->hsum_dirty = false; }
             sim->salt = 1;
             sim->mutcounts_ready = false;
             sim->bucket_pending = false;
             sim->has_rp_off = false;
         } else {
-            TRY(enqueue_generation_kernels(sim, tiles));
+            TRY(enqueue_generation_kernels(sim, tiles, prefill_next));
         }
     } else {
-        TRY(enqueue_generation_kernels(sim, tiles));
+        TRY(enqueue_generation_kernels(sim, tiles, prefill_next));
     }
     std::swap(sim->h.hap_id, sim->h.hap_id_next);
     if (tiles) std::swap(sim->h.pop_fit, sim->h.pop_fit_next);
@@ -1895,6 +1917,7 @@ static int upload_replace(vl_sim *sim, T **dev, const T *src, uint64_t n) {
 }
 VL_API int vl_replay_infections(vl_sim *sim, const int64_t *infections, uint64_t n) {
     ENTER(sim);
+    drop_prefill(sim);
     uint64_t cur = 0;
     TRY(population_len(sim, &cur));
     if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "infection log has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
@@ -1932,6 +1955,7 @@ VL_API int vl_replay_recombinations(vl_sim *sim, uint64_t n_events, const uint64
 }
 VL_API int vl_replay_offspring(vl_sim *sim, const uint64_t *offspring, uint64_t n) {
     ENTER(sim);
+    drop_prefill(sim);
     uint64_t cur = 0;
     TRY(population_len(sim, &cur));
     if (n != cur) return fail(sim, VL_ERR_ARGUMENT, "offspring log has %llu entries, population has %llu", (unsigned long long)n, (unsigned long long)cur);
@@ -2021,7 +2045,7 @@ VL_API int vl_get_raw_fitness(vl_sim *sim, uint32_t spec, int which, double *out
 VL_API int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, uint32_t *positions_out, uint8_t *bases_out, uint64_t *n_entries) {
     ENTER(sim);
     TRY(expect_len(sim, n));
-    uint32_t *cnt = (uint32_t *)sim->h.mut_list;  // per-infectant scratch, free outside the mutate phase
+    uint32_t *cnt = sim->h.rank;  // per-infectant scratch (the mutation worklist may hold the next generation's items: k_resample_pos<true>)
     LAUNCH(sim, k_export_count, grid_for(sim, n), TPB, 0, sim->d, cnt);
     TRY((launch_scan<uint64_t, true>(sim, cnt, sim->stage64, nullptr, n, n, sim->gc_totals + 6, 0, nullptr)));
     CU(sim, cudaMemcpyAsync(sim->pin, sim->gc_totals + 6, 8, cudaMemcpyDeviceToHost, sim->stream));

@@ -84,10 +84,10 @@ __global__ void __launch_bounds__(TPB) k_ex_lens(DevState *st, ExArgs ex, const 
         const uint64_t k = idx - sc->part_start[t];
         const uint32_t id = ex.part[t][k];
         // the record's one-line view carries its length and the raw fitness of provider 0: one random line per migrant
-        const MutHead hd = st->mh[id];
-        const uint32_t len = id == 0 ? 0u : hd.valid ? hd.len : st->hm[id].len;
+        const HapHead hd = st->head[id];
+        const uint32_t len = id == 0 ? 0u : head_mlen(hd);  // entries of the flattened record
         ex.out[t].len[par][k] = id == 0 ? MIG_WILDTYPE : len;
-        for (uint32_t p = 0; p < P; p++) ex.out[t].raw[par][k * P + p] = (p == 0 && hd.valid) ? hd.raw0 : hap_raw(st, p, id);
+        for (uint32_t p = 0; p < P; p++) ex.out[t].raw[par][k * P + p] = p == 0 ? hd.raw0 : hap_raw(st, p, id);
         words[idx] = len;
     }
 }
@@ -101,20 +101,10 @@ __global__ void __launch_bounds__(TPB) k_ex_copy(DevState *st, ExArgs ex, const 
         const uint32_t t = ex_find(sc->part_start, ex.world, idx);
         const uint32_t id = ex.part[t][idx - sc->part_start[t]];
         if (id == 0) continue;
-        const MutHead hd = st->mh[id];  // (the line k_ex_lens just read: an L2 hit; short records come with it)
-        uint64_t off = hd.off;
-        uint32_t len = hd.len;
-        if (!hd.valid) { const HapMeta hm = st->hm[id]; off = hm.off; len = hm.len; }
+        const HapHead hd = st->head[id];  // (the line k_ex_lens just read: an L2 hit)
+        const uint32_t len = head_mlen(hd);
         if (woff[idx] + len > stage_cap) { raise(st, DE_ARENA_CAPACITY); continue; }  // (the target's block would overflow too)
-        uint32_t *dst = stage + woff[idx];
-        if (hd.valid && len <= HEAD_INLINE) {
-#pragma unroll
-            for (uint32_t k = 0; k < HEAD_INLINE; k++)
-                if (k < len) dst[k] = hd.inl[k];
-        } else {
-            const uint32_t *src = st->arena + off;
-            for (uint32_t k = 0; k < len; k++) dst[k] = src[k];
-        }
+        flatten_record(st, hd, stage + woff[idx]);
     }
 }
 __global__ void __launch_bounds__(TPB) k_ex_stream(DevState *st, ExArgs ex, const ExScratch *sc, const uint64_t *__restrict__ woff,
@@ -216,12 +206,11 @@ __global__ void __launch_bounds__(TPB) k_ex_import(DevState *st, ExArgs ex, cons
         if (l != MIG_WILDTYPE && ok) {
             id = (uint32_t)(id0 + rec_off[idx]);
             const uint64_t off = a0 + word_off[idx];
-            st->hm[id] = HapMeta{off, l, NONE32};
             for (uint32_t p = 0; p < P; p++) set_fitness(st, p, id, __ldcg(ex.in[o].raw[par] + k * P + p));
             const uint32_t *src = ex.in[o].entries[par] + (word_off[idx] - word_off[sc->imp_start[o]]);
             uint32_t *dst = st->arena + off;
             for (uint32_t q = 0; q < l; q++) dst[q] = __ldcg(src + q);
-            write_head(st, id, off, l, dst);
+            write_flat_head(st, id, off, l);
         }
         if (slot < cap) st->hap_id_next[slot] = id;
     }

@@ -37,10 +37,11 @@
 
 namespace vl {
 
-// generation += 1 and the counters of a generation (one launch)
-__global__ void k_begin_generation_fused(DevState *st) {
+// generation += 1 and the counters of a generation (one launch).  prefilled: the previous generation's resample has
+// already drawn this generation's hosts and mutation counts (k_resample_pos<true>): the worklist is kept.
+__global__ void k_begin_generation_fused(DevState *st, int prefilled) {
     st->generation += 1;  // Simulation::increment_generation (src/simulation.rs:178)
-    st->n_mut_list = 0;
+    if (!prefilled) st->n_mut_list = 0;
     st->n_heavy = 0;
     st->n_medium = 0;
     st->fused_failed = 0;
@@ -53,96 +54,123 @@ __global__ void __launch_bounds__(TPB) k_zero_f64(double *p, uint64_t n) {
 // ---- infect + mutation count + per-host sum ---------------------------------------------------------------------------
 // BasicSimulation::infect for uniform infection (src/simulation.rs:365-387 with one always-accepting draw per
 // infectant) and the Binomial(L, mu) count of BasicHost::mutate (:94-95), both from block 0 of the infectant's PH_INFECT
-// stream like k_infect / k_mutcount_fast.  GATHER: the mapped fitness comes from the per-haplotype memo (population
-// installed by anything but k_resample_pos) and is stored per infectant, otherwise it came with the infectant.
-constexpr int IS_TPB = 256;
-constexpr int IS_ITEMS = 4;
-template <bool GATHER>
-__device__ __forceinline__ void infect_sum_chunk(DevState *st, uint64_t c, uint64_t n, uint32_t H32, uint32_t thr, uint32_t gen, PhiloxKey key,
-                                                 const uint32_t *__restrict__ hap_id, double *__restrict__ pop_fit, const double *__restrict__ hfit,
-                                                 uint32_t *__restrict__ host_id, double *__restrict__ hsum, uint32_t *s_w, uint32_t *s_base) {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr uint64_t CHUNK = (uint64_t)IS_TPB * IS_ITEMS;
-    uint32_t hp[IS_ITEMS], hh[IS_ITEMS], nmv[IS_ITEMS];
-    double ft[IS_ITEMS];
-#pragma unroll
-    for (int e = 0; e < IS_ITEMS; e++) {
-        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
-        hp[e] = i < n ? hap_id[i] : 0u;
+// stream like k_infect / k_mutcount_fast.  The draws of infectant i in generation g depend on (seed, compartment, g, i)
+// only, so they can be made as soon as i's haplotype is known: by k_infect_sum at the start of generation g, or by the
+// resample of generation g - 1 for the children it has just drawn (k_resample_pos<true>) — same results either way.
+struct InfectCtx {
+    uint32_t H32, thr, gen;
+    PhiloxKey key;
+    uint32_t *host_id;
+    double *hsum;
+};
+__device__ __forceinline__ void infect_draw(DevState *st, const InfectCtx &c, uint64_t i, double fit, uint32_t &h, uint32_t &nm) {
+    const uint4 b0 = philox_block(c.key, i, c.gen, PH_INFECT, 0);
+    uint64_t m = (uint64_t)b0.x * c.H32;  // Uniform(0, H): widening multiply, biased zone rejected exactly (as k_infect)
+    if ((uint32_t)m < c.H32) {
+        for (uint32_t blk = 1; (uint32_t)m < c.thr; blk++) m = (uint64_t)philox_block(c.key, i, c.gen, PH_INFECT, blk).x * c.H32;
     }
-#pragma unroll
-    for (int e = 0; e < IS_ITEMS; e++) {
-        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
-        ft[e] = 0.0;
-        if (i < n) ft[e] = GATHER ? (hfit ? hfit[hp[e]] : 1.0) : pop_fit[i];
-    }
-    uint32_t mine = 0;
-#pragma unroll
-    for (int e = 0; e < IS_ITEMS; e++) {
-        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
-        hh[e] = NONE32;
-        nmv[e] = 0;
-        if (i >= n) continue;
-        const uint4 b0 = philox_block(key, i, gen, PH_INFECT, 0);
-        uint64_t m = (uint64_t)b0.x * H32;  // Uniform(0, H): widening multiply, biased zone rejected exactly (as k_infect)
-        if ((uint32_t)m < H32) {
-            for (uint32_t blk = 1; (uint32_t)m < thr; blk++) m = (uint64_t)philox_block(key, i, gen, PH_INFECT, blk).x * H32;
-        }
-        hh[e] = (uint32_t)(m >> 32);
-        nmv[e] = mutation_count_small(st, key, i, gen, b0);
-        mine += nmv[e] ? 1u : 0u;
-    }
-#pragma unroll
-    for (int e = 0; e < IS_ITEMS; e++) {
-        const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
-        if (i >= n) continue;
-        host_id[i] = hh[e];
-        if (GATHER) pop_fit[i] = ft[e];
-        // a mutating infectant's fitness is about to change: k_mutate adds the new value (f == 0.0 adds nothing)
-        if (nmv[e] == 0u && ft[e] != 0.0) atomicAdd(&hsum[hh[e]], ft[e]);
-    }
-    // mutation worklist: (infectant, n_mut, host, parent haplotype); one global atomic per chunk
-    uint32_t inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= (uint32_t)d) inc += y;
-    }
-    __syncthreads();  // (s_w / s_base of the previous chunk have been read)
-    if (lane == 31) s_w[wid] = inc;
-    __syncthreads();
-    uint32_t woff = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < IS_TPB / 32; w++) {
-        const uint32_t t = s_w[w];
-        if (w < (int)wid) woff += t;
-        tot += t;
-    }
-    if (tid == 0) *s_base = tot ? atomicAdd(&st->n_mut_list, tot) : 0u;
-    __syncthreads();
-    if (mine) {
-        uint32_t o = *s_base + woff + inc - mine;
-#pragma unroll
-        for (int e = 0; e < IS_ITEMS; e++) {
-            const uint64_t i = c * CHUNK + (uint64_t)e * IS_TPB + tid;
-            if (i < n && nmv[e]) st->mut_list[o++] = make_uint4((uint32_t)i, nmv[e], hh[e], hp[e]);
-        }
+    h = (uint32_t)(m >> 32);
+    nm = mutation_count_small(st, c.key, i, c.gen, b0);
+    c.host_id[i] = h;
+    // (a mutating infectant's fitness is about to change: k_mutate stores the new value and adds it to the host's sum;
+    // f == 0.0 adds nothing)
+    if (nm == 0u && fit != 0.0) red_add_f64(&c.hsum[h], fit);
+}
+// Mutation worklist staged per CTA in shared memory: (infectant, n_mut, host, parent haplotype), appended with one vote
+// and one shared atomic per warp round, flushed with ONE global atomic per CTA pass (same-address global atomics are
+// served one after the other by L2).
+constexpr uint32_t CL_CAP = RESAMPLE_TILE;  // items a pass can stage: every infectant of a tile may mutate
+struct CtaList {
+    uint4 *buf;
+    uint32_t *cnt;  // [0] staged items, [1] global base of the flush
+};
+__device__ __forceinline__ void cl_push(CtaList &cl, bool has, uint4 item) {  // (called by converged warps)
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, has);
+    if (!mask) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&cl.cnt[0], (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (has) {
+        const uint32_t k = base + __popc(mask & ((1u << lane) - 1u));
+        if (k < CL_CAP) cl.buf[k] = item;
     }
 }
+// (called by every thread of the CTA, after the pass's pushes) hap_out != nullptr: the id of a new record is the record
+// count k_mutate starts with plus the item's worklist position — if k_mutate is the next kernel to touch the table, the
+// infectant's haplotype can be written here, in stream order, instead of being patched by k_mutate
+__device__ __forceinline__ void cl_flush(DevState *st, CtaList &cl, uint32_t *hap_out, unsigned long long id_base) {
+    __syncthreads();
+    const uint32_t n = cl.cnt[0] < CL_CAP ? cl.cnt[0] : CL_CAP;
+    if (threadIdx.x == 0) {
+        if (cl.cnt[0] > CL_CAP) raise(st, DE_TILE_OVERFLOW);
+        cl.cnt[1] = n ? atomicAdd(&st->n_mut_list, n) : 0u;
+    }
+    __syncthreads();
+    const uint32_t gbase = cl.cnt[1];
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const uint4 it = cl.buf[k];
+        st->mut_list[gbase + k] = it;
+        if (hap_out) hap_out[it.x] = (uint32_t)(id_base + gbase + k);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) cl.cnt[0] = 0u;
+    __syncthreads();
+}
+// GATHER: the mapped fitness comes from the per-haplotype memo (population installed by anything but k_resample_pos)
+// and is stored per infectant, otherwise it came with the infectant.
+constexpr int IS_TPB = 256;
+constexpr int IS_ITEMS = RESAMPLE_TILE / IS_TPB;
 template <bool GATHER>
 __global__ void __launch_bounds__(IS_TPB, 4) k_infect_sum(DevState *st) {
-    __shared__ uint32_t s_base;
-    __shared__ uint32_t s_w[IS_TPB / 32];
+    __shared__ uint4 s_items[CL_CAP];
+    __shared__ uint32_t s_cnt[2];
     const uint64_t n = st->n;
     const uint32_t H32 = (uint32_t)st->H;
     if (H32 == 0) return;
-    const uint32_t thr = (uint32_t)(-H32) % H32;
+    const uint32_t tid = threadIdx.x;
+    InfectCtx c;
+    c.H32 = H32;
+    c.thr = (uint32_t)(-H32) % H32;
+    c.gen = st->generation;
+    c.key = philox_key(st->seed, st->compartment);
+    c.host_id = st->host_id;
+    c.hsum = st->hsum[st->hsum_parity];
+    const unsigned long long id_base = st->n_hap;
+    CtaList cl{s_items, s_cnt};
+    if (tid == 0) s_cnt[0] = 0u;
+    __syncthreads();
+    uint32_t *hap_id = st->hap_id;
+    double *pop_fit = st->pop_fit;
     const int pi0 = st->specs[0].repro;
-    constexpr uint64_t CHUNK = (uint64_t)IS_TPB * IS_ITEMS;
-    const uint64_t n_chunks = (n + CHUNK - 1) / CHUNK;
-    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x)
-        infect_sum_chunk<GATHER>(st, c, n, H32, thr, st->generation, philox_key(st->seed, st->compartment), st->hap_id, st->pop_fit,
-                                 pi0 >= 0 ? st->h_fit[pi0] : nullptr, st->host_id, st->hsum[st->hsum_parity], s_w, &s_base);
+    const double *__restrict__ hfit = pi0 >= 0 ? st->h_fit[pi0] : nullptr;
+    const uint64_t n_chunks = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
+    for (uint64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        uint32_t hp[IS_ITEMS];
+        double ft[IS_ITEMS];
+#pragma unroll
+        for (int e = 0; e < IS_ITEMS; e++) {
+            const uint64_t i = ch * RESAMPLE_TILE + (uint64_t)e * IS_TPB + tid;
+            hp[e] = i < n ? hap_id[i] : 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < IS_ITEMS; e++) {
+            const uint64_t i = ch * RESAMPLE_TILE + (uint64_t)e * IS_TPB + tid;
+            ft[e] = 0.0;
+            if (i < n) {
+                if (GATHER) { ft[e] = hfit ? hfit[hp[e]] : 1.0; pop_fit[i] = ft[e]; }
+                else ft[e] = pop_fit[i];
+            }
+        }
+#pragma unroll 2
+        for (int e = 0; e < IS_ITEMS; e++) {
+            const uint64_t i = ch * RESAMPLE_TILE + (uint64_t)e * IS_TPB + tid;
+            uint32_t h = 0, nm = 0;
+            if (i < n) infect_draw(st, c, i, ft[e], h, nm);
+            cl_push(cl, nm != 0u, make_uint4((uint32_t)i, nm, h, hp[e]));
+        }
+        cl_flush(st, cl, hap_id, id_base);
+    }
 }
 
 // ---- offspring counts in infectant order -------------------------------------------------------------------------------
@@ -166,7 +194,11 @@ __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t kmax = poisson_kmax(R0 < 12.0 ? R0 : 12.0);  // lambda = R0 * f / S <= R0 for non-negative fitness
     const uint32_t tid = threadIdx.x;
-    if (blockIdx.x == 0 && tid == 0) { st->n_sorted = n; st->host_tiles = 0; }  // tiles of consecutive infectants (tile_range)
+    if (blockIdx.x == 0 && tid == 0) {
+        st->n_sorted = n;
+        st->host_tiles = 0;   // tiles of consecutive infectants (tile_range)
+        st->n_mut_list = 0;   // k_mutate is done with this generation's worklist: the resample may start the next one
+    }
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t p0 = tile * RESAMPLE_TILE;
         uint32_t h[OS_PER];
@@ -229,7 +261,14 @@ struct ResamplePosArgs {
     uint32_t *dst[MAX_PARTS];    // nullptr = the population being assembled (hap_id_next, pop_fit_next)
     double *dst_fit[MAX_PARTS];  // mapped fitness of the drawn parents (may be nullptr when dst is a detached buffer)
 };
+// PREFILL: the children written to the population (single part, dst == nullptr) get their hosts and mutation counts for
+// the NEXT generation right here (infect_draw with generation + 1): host_id[], the other hsum buffer (cleared by
+// k_offspring_sum of this generation) and the worklist are ready when the next generation begins, which then starts with
+// k_mutate.  The children are as they would be without it; k_infect_sum makes the same draws from the same streams.
+template <bool PREFILL>
 __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, ResamplePosArgs ra) {
+    extern __shared__ uint4 s_items_dyn[];      // PREFILL: CL_CAP staged worklist items
+    __shared__ uint32_t s_clcnt[2];
     __shared__ uint32_t s_hap[RESAMPLE_TILE];   // compacted payloads of the records with offspring
     __shared__ double s_fit[RESAMPLE_TILE];
     __shared__ uint32_t s_cdf[RESAMPLE_TILE];   // compacted inclusive CDF (guide path only)
@@ -250,6 +289,17 @@ __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, Resamp
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t gen = st->generation;
     const uint64_t stride = st->tile_stride;
+    InfectCtx ictx;
+    CtaList cl{s_items_dyn, s_clcnt};
+    if (PREFILL) {
+        ictx.H32 = (uint32_t)st->H;
+        ictx.thr = ictx.H32 ? (uint32_t)(-ictx.H32) % ictx.H32 : 0u;
+        ictx.gen = gen + 1;
+        ictx.key = key;
+        ictx.host_id = st->host_id;
+        ictx.hsum = st->hsum[st->hsum_parity ^ 1u];
+        if (tid == 0) s_clcnt[0] = 0u;
+    }
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
         uint64_t any = 0;
         __syncthreads();  // (a tile without draws is left early: nobody may still be reading the shared arrays)
@@ -381,10 +431,12 @@ __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, Resamp
         } else {
             blocks_total = (uint32_t)(((tbase1 + any - 1) >> 2) - (tbase1 >> 2) + 1);
         }
-        for (uint32_t e = tid; e < blocks_total; e += RT_TPB) {
+        for (uint32_t e0 = wid * 32; e0 < blocks_total; e0 += RT_TPB) {  // (warp-uniform bound: the worklist votes need converged warps)
+            const uint32_t e = e0 + lane;
+            const bool live = e < blocks_total;
             uint32_t part = 0, before = 0;
             uint64_t c = any, base = tbase1;
-            if (ra.n_parts > 1) {
+            if (live && ra.n_parts > 1) {
                 for (;; part++) {
                     c = s_pcnt[part];
                     base = s_pbase[part];
@@ -397,34 +449,43 @@ __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, Resamp
             uint32_t *__restrict__ dst = ra.dst[part] ? ra.dst[part] : st->hap_id_next;
             double *__restrict__ dstf = ra.dst[part] ? ra.dst_fit[part] : st->pop_fit_next;
             const uint64_t q = (base >> 2) + (e - before);
-            const uint4 blk = philox_block(key, q | salt, gen, PH_RESAMPLE, 0);
+            uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+            if (live) blk = philox_block(key, q | salt, gen, PH_RESAMPLE, 0);
             const uint32_t xs[4] = {blk.x, blk.y, blk.z, blk.w};
 #pragma unroll
             for (int w = 0; w < 4; w++) {
                 const uint64_t s = q * 4 + w;
-                if (s < base || s >= base + c) continue;
-                uint32_t x = xs[w];
-                uint64_t mm = (uint64_t)x * total;
-                if ((uint32_t)mm < total) {  // biased zone of the widening multiply: exact rejection
-                    const uint32_t thr = (uint32_t)(-total) % total;
-                    if ((uint32_t)mm < thr) {
-                        Philox g(st->seed, st->compartment, gen, PH_RESAMPLE_RETRY, s | salt);
-                        do { x = g.u32(); mm = (uint64_t)x * total; } while ((uint32_t)mm < thr);
+                const bool valid = live && s >= base && s < base + c;
+                uint32_t hap = 0, h = 0, nm = 0;
+                if (valid) {
+                    uint32_t x = xs[w];
+                    uint64_t mm = (uint64_t)x * total;
+                    if ((uint32_t)mm < total) {  // biased zone of the widening multiply: exact rejection
+                        const uint32_t thr = (uint32_t)(-total) % total;
+                        if ((uint32_t)mm < thr) {
+                            Philox g(st->seed, st->compartment, gen, PH_RESAMPLE_RETRY, s | salt);
+                            do { x = g.u32(); mm = (uint64_t)x * total; } while ((uint32_t)mm < thr);
+                        }
                     }
+                    const uint32_t r = (uint32_t)(mm >> 32);
+                    uint32_t slot;
+                    if (direct) {
+                        const uint32_t upto = s_mask[r >> 5] & (0xFFFFFFFFu >> (31 - (r & 31)));  // run starts at or below r in its word
+                        slot = (uint32_t)s_pre[r >> 5] + __popc(upto) - 1u;
+                    } else {
+                        slot = s_guide[x >> (32 - GUIDE_BITS)];
+                        while (s_cdf[slot] <= r) slot++;
+                    }
+                    hap = s_hap[slot];
+                    const double fit = s_fit[slot];
+                    dst[s] = hap;
+                    if (dstf) dstf[s] = fit;
+                    if (PREFILL) infect_draw(st, ictx, s, fit, h, nm);
                 }
-                const uint32_t r = (uint32_t)(mm >> 32);
-                uint32_t slot;
-                if (direct) {
-                    const uint32_t upto = s_mask[r >> 5] & (0xFFFFFFFFu >> (31 - (r & 31)));  // run starts at or below r in its word
-                    slot = (uint32_t)s_pre[r >> 5] + __popc(upto) - 1u;
-                } else {
-                    slot = s_guide[x >> (32 - GUIDE_BITS)];
-                    while (s_cdf[slot] <= r) slot++;
-                }
-                dst[s] = s_hap[slot];
-                if (dstf) dstf[s] = s_fit[slot];
+                if (PREFILL) cl_push(cl, nm != 0u, make_uint4((uint32_t)s, nm, h, hap));
             }
         }
+        if (PREFILL) cl_flush(st, cl, nullptr, 0ull);
     }
 }
 

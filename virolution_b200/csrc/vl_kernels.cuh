@@ -36,6 +36,10 @@ constexpr uint32_t SMEM_SORT_MAX = 4096;  // slices up to this length are sorted
 constexpr int INFECT_ITEMS = 4;           // infectants per thread and round in k_infect / k_scatter
 
 __device__ __forceinline__ void raise(DevState *st, uint32_t bit) { atomicOr(&st->error, bit); }
+// f64 reduction into global memory without a return value (RED, not ATOM: nothing waits for the old value)
+__device__ __forceinline__ void red_add_f64(double *p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
 // memoise a record's raw fitness under provider p together with the mapped value utility(raw): the raw value is what
 // descendants multiply (FitnessProvider::get_fitness, src/providers/fitness.rs:212-223), the mapped value is what
 // infect and replicate read (AttributeSet::get_or_compute, src/core/attributes.rs:220-241) — N reads per generation
@@ -43,20 +47,28 @@ __device__ __forceinline__ void set_fitness(DevState *st, uint32_t p, uint64_t i
     st->h_raw[p][id] = raw;
     st->h_fit[p][id] = utility_apply(st->prov[p], raw);
 }
-// the one-line view of record `id` for the mutate kernel (MutHead); `entries` may point anywhere readable
-__device__ __forceinline__ void write_head(DevState *st, uint64_t id, uint64_t off, uint32_t len, const uint32_t *entries) {
-    MutHead h;
+// head of a record that owns a flat list (no delta): recombinants, imported migrants, compacted records.  The fitness
+// of every provider has been memoised before (set_fitness).
+__device__ __forceinline__ void write_flat_head(DevState *st, uint64_t id, uint64_t off, uint32_t len) {
+    HapHead h;
     h.off = off;
     h.len = len;
-    h.valid = 1u;
+    h.nd_mlen = len << 8;
     h.raw0 = st->n_providers ? st->h_raw[0][id] : 1.0;
+    h.fit0 = st->n_providers ? st->h_fit[0][id] : 1.0;
 #pragma unroll
-    for (uint32_t k = 0; k < HEAD_INLINE; k++) h.inl[k] = k < len ? entries[k] : 0xFFFFFFFFu;
-    st->mh[id] = h;
+    for (uint32_t k = 0; k < HEAD_DELTA; k++) h.d[k] = 0xFFFFFFFFu;
+    st->head[id] = h;
 }
 __global__ void k_init_wildtype(DevState *st) {  // haplotype 0: no entries, raw fitness = empty product (src/core/fitness/table.rs:72-79)
     for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, 0, 1.0);
-    write_head(st, 0, 0, 0, nullptr);
+    write_flat_head(st, 0, 0, 0);
+}
+// the merged (flattened) record of `id` written to out[]; returns its length (= head_mlen)
+__device__ inline uint32_t flatten_record(const DevState *st, const HapHead &h, uint32_t *out) {
+    uint32_t o = 0;
+    merged_for_each(st->arena + h.off, h.len, h.d, head_nd(h), [&](uint32_t e) { out[o++] = e; });
+    return o;
 }
 __device__ __forceinline__ uint64_t vl_globaltimer() {
     uint64_t t;
@@ -608,13 +620,14 @@ __device__ inline void heap_sort_u32(uint32_t *a, uint32_t n) {
 
 // change word in scratch: pos << 8 | from << 4 | to
 __device__ __forceinline__ uint32_t ch_pos(uint32_t c) { return c >> 8; }
-__device__ __forceinline__ uint32_t ch_from(uint32_t c) { return (c >> 4) & 0xF; }
+__device__ __forceinline__ uint32_t ch_from(uint32_t c) { return (c >> 4) & 0x7; }
+__device__ __forceinline__ uint32_t ch_present(uint32_t c) { return (c >> 7) & 1u; }  // the pre-mutation haplotype had an entry at this site
 __device__ __forceinline__ uint32_t ch_to(uint32_t c) { return c & 0xF; }
 
 // EpistasisTable::update_fitness (src/core/fitness/epistasis.rs:105-173) on a freshly merged record.
 // Quirks kept: candidates are the changes whose (pos,to) has a row (`from` is never tested); entries of the
 // mutation set at positions <= the change that belong to this node's own changes are skipped.
-__device__ inline double epi_update(const DevProvider &p, const uint32_t *chs, uint32_t n_ch, const uint32_t *ent, uint32_t n_ent) {
+__device__ inline double epi_update(const DevProvider &p, const uint32_t *chs, uint32_t n_ch, const uint32_t *base, uint32_t len, const uint32_t *d, uint32_t nd) {
     bool any = false;
     for (uint32_t k = 0; k < n_ch && !any; k++) {
         uint32_t lo, hi;
@@ -629,21 +642,20 @@ __device__ inline double epi_update(const DevProvider &p, const uint32_t *chs, u
         epi_row(p, ekey(cpos, ch_to(chs[k])), alo, ahi);
         if (ahi == alo) continue;
         epi_row(p, ekey(cpos, ch_from(chs[k])), rlo, rhi);
-        for (uint32_t m = 0; m < n_ent; m++) {
-            const uint32_t mb = entry_m(ent[m]);
-            if (mb >= 4) continue;
-            const uint32_t pos = entry_pos(ent[m]);
+        // the new record's mutation set M in ascending position (the reference walks a HashMap; the factors commute up to rounding)
+        merged_for_each(base, len, d, nd, [&](uint32_t e) {
+            const uint32_t mb = entry_m(e);
+            if (mb >= 4) return;
+            const uint32_t pos = entry_pos(e);
             if (pos <= cpos) {
-                bool own = false;
-                for (uint32_t q = 0; q < n_ch; q++) if (ch_pos(chs[q]) == pos) { own = true; break; }
-                if (own) continue;
+                for (uint32_t q = 0; q < n_ch; q++) if (ch_pos(chs[q]) == pos) return;  // one of this node's own changes
             }
             if (pos != cpos) {
                 double v;
                 if (epi_get(p, alo, ahi, ekey(pos, mb), v)) fitness *= v;
                 if (rhi > rlo && epi_get(p, rlo, rhi, ekey(pos, mb), v)) fitness /= v;
             }
-        }
+        });
     }
     return fitness;
 }
@@ -664,24 +676,17 @@ struct ReplayRecomb {
 // right entries outside; raw fitness by full recomputation like FitnessProvider::get_fitness does for
 // nodes without changes (src/providers/fitness.rs:224-227).
 __device__ inline uint32_t make_recombinant(DevState *st, uint32_t left, uint32_t right, uint32_t s0, uint32_t s1) {
-    const uint32_t ll = st->hm[left].len, lr = st->hm[right].len;
-    NewRecord r = reserve_record_single(st, ll + lr);
+    const HapHead hl = st->head[left], hr = st->head[right];
+    NewRecord r = reserve_record_single(st, head_mlen(hl) + head_mlen(hr));
     if (!r.ok) return left;
-    const uint32_t *el = st->arena + st->hm[left].off, *er = st->arena + st->hm[right].off;
     uint32_t *out = st->arena + r.off;
     uint32_t o = 0;
-    uint32_t k = 0;
-    for (; k < lr && entry_pos(er[k]) < s0; k++) out[o++] = er[k];
-    for (uint32_t q = 0; q < ll; q++) {
-        uint32_t p = entry_pos(el[q]);
-        if (p >= s0 && p < s1) out[o++] = el[q];
-    }
-    for (; k < lr; k++) if (entry_pos(er[k]) >= s1) out[o++] = er[k];
-    st->hm[r.id].off = r.off;
-    st->hm[r.id].len = o;
-    st->hm[r.id].parent = left;
+    // right entries below s0, left entries inside [s0, s1), right entries from s1 on: three passes over the merged views
+    merged_for_each(st->arena + hr.off, hr.len, hr.d, head_nd(hr), [&](uint32_t e) { if (entry_pos(e) < s0) out[o++] = e; });
+    merged_for_each(st->arena + hl.off, hl.len, hl.d, head_nd(hl), [&](uint32_t e) { const uint32_t p = entry_pos(e); if (p >= s0 && p < s1) out[o++] = e; });
+    merged_for_each(st->arena + hr.off, hr.len, hr.d, head_nd(hr), [&](uint32_t e) { if (entry_pos(e) >= s1) out[o++] = e; });
     for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, r.id, compute_fitness_full(st->prov[p], out, o));
-    write_head(st, r.id, r.off, o, out);
+    write_flat_head(st, r.id, r.off, o);
     return r.id;
 }
 
@@ -816,51 +821,102 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
     }
 }
 
-// One thread per mutated infectant: draw sites (with replacement) and sort them, look up the current base
-// on the pre-mutation haplotype, draw the substitution, merge into a new flattened record and update the
-// raw fitness of every provider incrementally: raw(parent) * fold(acc * T[pos,to] / T[pos,from])
-// (src/core/fitness/table.rs:65-68) [* epistatic update].  patch_records: 1 = the infectant's CSR record is
-// patched in place, 2 = its bucket-partitioned record is (host map not built yet), 0 = no records exist,
-// 3 = device-resident generation (vl_fused.cuh): items are (infectant, n_mut, host, parent); the carried fitness of the
-// infectant is replaced and added to its host's sum.
-constexpr uint32_t MUT_LOCAL_PARENT = 16;  // parent records up to this length are staged in thread-local memory
-constexpr uint32_t MUT_LOCAL_CHANGES = 8;  // mutation events up to this many sites keep their change words there too
-constexpr uint32_t MUT_SCRATCH_STRIDE = MUT_LOCAL_PARENT + MUT_LOCAL_CHANGES + HEAD_INLINE + 1;  // odd: consecutive threads hit distinct banks
-static_assert(MUT_SCRATCH_STRIDE % 2 == 1 && HEAD_INLINE <= MUT_LOCAL_PARENT, "scratch layout");
-// parent_in_item: the worklist items carry the infectant's current haplotype id in .w (k_mutcount_fast)
-__global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
-    __shared__ uint32_t s_scratch[TPB * MUT_SCRATCH_STRIDE];
-    const uint32_t n_list = st->n_mut_list;
+// One thread per mutated infectant: draw sites (with replacement) and sort them, look up the current base on the
+// pre-mutation haplotype (its delta, then its base list), draw the substitution, and derive the child's record from the
+// parent's 64-byte line: the changes are merged into the inline delta, or — when the delta would overflow — the record is
+// flattened into a fresh base list (HapHead, vl_state.cuh).  Raw fitness of every provider incrementally:
+// raw(parent) * fold(acc * T[pos,to] / T[pos,from]) (src/core/fitness/table.rs:65-68) [* epistatic update].
+// patch_records: 1 = the infectant's CSR record is patched in place, 2 = its bucket-partitioned record is (host map not
+// built yet), 0 = no records exist, 3 / 4 = device-resident generation (vl_fused.cuh): items are (infectant, n_mut, host,
+// parent); the carried fitness of the infectant is replaced and added to its host's sum.
+constexpr uint32_t MUT_LOCAL = HEAD_DELTA;              // events up to this many sites keep their scratch in shared memory
+constexpr uint32_t MUT_STRIDE = 3 * HEAD_DELTA + 2 * MUT_LOCAL + 1;  // per thread: parent delta (8), merged delta (16), change words (8), new entries (8); odd stride
+constexpr uint32_t MUT_WT_MAX_SITES = 65536;           // wildtypes up to this length are staged in shared memory, 2 bits per site
+__host__ __device__ inline uint32_t mutate_wt_words(uint32_t L) { return L <= MUT_WT_MAX_SITES ? (L + 15u) / 16u : 0u; }
+__host__ __device__ inline uint32_t mutate_smem_bytes(uint32_t L) { return (TPB * MUT_STRIDE + mutate_wt_words(L)) * 4u; }
+
+// One flatten job done by the whole warp: out[] = base list (pe, plen) overridden by the merged delta dmv[0..ndm),
+// ndm <= 32, tombstones dropped; returns the number of entries written.  Every lane j < ndm places its delta entry
+// (lower bound in the base list by interpolation), the base entries are copied 32 at a time: nothing is serial in the
+// list's length.
+__device__ __forceinline__ uint32_t warp_flatten(const uint32_t *pe, uint32_t plen, const uint32_t *dmv, uint32_t ndm, uint32_t *out, uint32_t L) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t e = 0, bj = 0;
+    bool hit = false, keep = false;
+    if (lane < ndm) {  // every delta entry finds its place in the base list (one memory latency, all entries at once)
+        e = dmv[lane];
+        bj = entries_lower_interp(pe, plen, entry_pos(e), L);
+        hit = bj < plen && entry_pos(pe[bj]) == entry_pos(e);
+        keep = !entry_is_tombstone(e);
+    }
+    const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit), keepmask = __ballot_sync(0xFFFFFFFFu, keep);
+    const uint32_t below = (1u << lane) - 1u;
+    if (keep) out[bj - __popc(hitmask & below) + __popc(keepmask & below)] = e;
+    // every base entry finds the delta entries before it (bisection over <= 32 positions in shared memory)
+    for (uint32_t a0 = 0; a0 < plen; a0 += 32) {
+        const uint32_t a = a0 + lane;
+        if (a >= plen) continue;
+        const uint32_t be = pe[a], q = entry_pos(be);
+        uint32_t lo = 0, hi = ndm;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (entry_pos(dmv[mid]) < q) lo = mid + 1; else hi = mid;
+        }
+        if (lo < ndm && entry_pos(dmv[lo]) == q) continue;  // overridden (or removed) by the delta
+        const uint32_t m = (1u << lo) - 1u;
+        out[a - __popc(hitmask & m) + __popc(keepmask & m)] = be;
+    }
+    return plen - __popc(hitmask) + __popc(keepmask);
+}
+
+// parent_in_item: the worklist items carry the infectant's current haplotype id in .w
+__global__ void __launch_bounds__(TPB, 3) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
+    extern __shared__ uint32_t s_mut_dyn[];
+    __shared__ double s_subst[16];
+    uint32_t *s_scratch = s_mut_dyn;
+    uint32_t *s_wt = s_mut_dyn + TPB * MUT_STRIDE;  // wildtype, 16 sites per word
     const uint32_t L = st->L;
     const uint8_t *__restrict__ wt = st->wildtype;
+    const uint32_t wt_words = mutate_wt_words(L);
+    if (threadIdx.x < 16) s_subst[threadIdx.x] = st->host_subst[threadIdx.x];
+    for (uint32_t k = threadIdx.x; k < wt_words; k += blockDim.x) {
+        uint32_t word = 0;
+        for (uint32_t q = 0; q < 16; q++) {
+            const uint32_t site = k * 16 + q;
+            if (site < L) word |= (uint32_t)wt[site] << (2 * q);
+        }
+        s_wt[k] = word;
+    }
+    __syncthreads();
+    auto wt_at = [&](uint32_t site) -> uint32_t { return wt_words ? (s_wt[site >> 4] >> ((site & 15u) * 2u)) & 3u : (uint32_t)wt[site]; };
+    const uint32_t n_list = st->n_mut_list;
     const uint32_t span = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31;
     // Every warp walks the worklist 32 items at a time.  Same-address atomics are served one after the other by L2, so
     // none is spent per record or per 32 records: a record's id is its worklist position behind the record count the
-    // kernel started with (published by the last CTA to leave), and arena words come out of a chunk the warp reserves
-    // for all the rounds it still has to do (12.5 % slack; what is left over is reclaimed by the next compaction).
+    // kernel started with (published by the last CTA to leave), and arena words (needed only by the records that are
+    // flattened) come out of a chunk the warp reserves for all the rounds it still has to do.
     const unsigned long long id_base = st->n_hap;
     unsigned long long chunk_off = 0;
     uint32_t chunk_left = 0;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_list; base += span) {
         const uint32_t w = base + lane;
-        const bool active = w < n_list;
-        uint32_t i = 0, nm = 0, pid = 0, plen = 0, tpos = NONE32;
-        HapMeta pm{0, 0, NONE32};
-        MutHead ph;
-        ph.valid = 0u;
-        if (active) {
+        bool ok = w < n_list;
+        uint32_t i = 0, nm = 0, pid = 0, tpos = NONE32;
+        HapHead ph;
+        ph.off = 0; ph.len = 0; ph.nd_mlen = 0; ph.raw0 = 1.0; ph.fit0 = 1.0;
+        if (ok) {
             const uint4 item = st->mut_list[w];
             i = item.x;
             nm = item.y;
             tpos = item.z;
             pid = parent_in_item ? item.w : st->hap_id[i];
-            ph = st->mh[pid];  // ONE 64-byte line: arena offset, length, raw fitness and the first entries of the parent
-            if (ph.valid) { pm.off = ph.off; pm.len = ph.len; }
-            else pm = st->hm[pid];
-            plen = pm.len;
+            ph = st->head[pid];  // ONE 64-byte line: base list, inline delta, fitness of the parent
         }
-        const uint32_t words = active ? plen + 2 * nm : 0u;
+        const uint32_t nd = head_nd(ph), plen = ph.len, mlen = head_mlen(ph);
+        const bool flat = ok && nd + nm > HEAD_DELTA;  // the delta would overflow: this record gets a base list of its own
+        const bool big = nm > MUT_LOCAL;               // (implies flat)
+        const uint32_t words = flat ? mlen + (big ? 4u * nm + HEAD_DELTA : nm) : 0u;
         uint32_t inc = words;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -878,121 +934,151 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
         const unsigned long long abase = chunk_off;
         chunk_off += wtot;
         chunk_left -= wtot;
-        if (!active) continue;
         const uint64_t roff = abase + (inc - words);
         const uint64_t id64 = id_base + w;
-        if (id64 >= st->cap_hap) { raise(st, DE_HAP_CAPACITY); continue; }
-        if (roff + words > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); continue; }
+        if (ok && id64 >= st->cap_hap) { raise(st, DE_HAP_CAPACITY); ok = false; }
+        if (ok && flat && roff + words > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); ok = false; }
         const uint32_t new_id = (uint32_t)id64;
-        uint32_t *out = st->arena + roff;
-        // parent entries and change words in the thread's slice of shared memory when they are short (the usual case):
-        // every lookup below is then a shared-memory access instead of a dependent trip to L2/HBM (thread-local arrays
-        // would be indexed dynamically, i.e. live in local memory and cost L2 write traffic of their own)
-        uint32_t *pe_local = s_scratch + threadIdx.x * MUT_SCRATCH_STRIDE, *ch_local = pe_local + MUT_LOCAL_PARENT;
-        uint32_t *hd_local = ch_local + MUT_LOCAL_CHANGES;  // the first entries of the new record, for its own head
-        const uint32_t *pe = st->arena + pm.off;
-        if (ph.valid && plen <= HEAD_INLINE) {  // the parent's entries came with its head: no arena read at all
+        const uint32_t *pe = st->arena + ph.off;
+        uint32_t *out = st->arena + roff;  // (flat only) merged list [0, mlen + nm), then scratch of large events
+        uint32_t *pd = s_scratch + threadIdx.x * MUT_STRIDE, *dl = pd + HEAD_DELTA, *ch_local = dl + 2 * HEAD_DELTA, *ne_local = ch_local + MUT_LOCAL;
+        uint32_t *chs = big ? out + mlen + nm : ch_local;          // change words: pos << 8 | present << 7 | from << 4 | to
+        uint32_t *nev = big ? out + mlen + 2 * nm : ne_local;      // the event's entries, one per distinct site
+        uint32_t *dm = big ? out + mlen + 3 * nm : dl;             // parent delta merged with the event's entries
+        uint32_t ndm = 0;
+        int32_t dlen = 0;
+        HapHead nh;
+        nh.raw0 = 1.0;
+        nh.fit0 = 1.0;
+        double fit_repro = 1.0;  // mapped fitness under the reproductive provider of spec 0 (patch_records == 3)
+        if (ok) {
 #pragma unroll
-            for (uint32_t k = 0; k < HEAD_INLINE; k++) pe_local[k] = ph.inl[k];
-            pe = pe_local;
-        } else if (plen <= MUT_LOCAL_PARENT) {
-#pragma unroll
-            for (uint32_t k = 0; k < MUT_LOCAL_PARENT; k++) pe_local[k] = k < plen ? pe[k] : 0xFFFFFFFFu;
-            pe = pe_local;
-        }
-        uint32_t *chs = nm <= MUT_LOCAL_CHANGES ? ch_local : out + plen + nm;
-        if (replay) {
-            const uint64_t ro = rp.offsets[i];
-            for (uint32_t k = 0; k < nm; k++) {
-                uint32_t site = rp.sites[ro + k];
-                if (site >= L || (k > 0 && site < ch_pos(chs[k - 1])) || rp.bases[ro + k] > 3) { raise(st, DE_REPLAY); site = site % L; }
-                uint32_t cur = entries_get_base(pe, plen, site, wt);
-                uint32_t to = rp.bases[ro + k] & 3;
-                if (cur == to) raise(st, DE_SAME_BASE);
-                chs[k] = (site << 8) | (cur << 4) | to;
-            }
-        } else {
-            Philox g(st->seed, st->compartment, st->generation, PH_MUTATE, i);
-            for (uint32_t k = 0; k < nm; k++) chs[k] = (uint32_t)g.below(L);
-            if (nm <= 16) {
-                for (uint32_t a = 1; a < nm; a++) {
-                    uint32_t x = chs[a], c = a;
-                    while (c > 0 && chs[c - 1] > x) { chs[c] = chs[c - 1]; c--; }
-                    chs[c] = x;
+            for (uint32_t k = 0; k < HEAD_DELTA; k++) pd[k] = ph.d[k];  // (indexed dynamically below: shared memory, not local memory)
+            if (replay) {
+                const uint64_t ro = rp.offsets[i];
+                for (uint32_t k = 0; k < nm; k++) {
+                    uint32_t site = rp.sites[ro + k];
+                    if (site >= L || (k > 0 && site < ch_pos(chs[k - 1])) || rp.bases[ro + k] > 3) { raise(st, DE_REPLAY); site = site % L; }
+                    const uint32_t e = merged_find(pe, plen, pd, nd, site, L);
+                    const uint32_t cur = e != 0xFFFFFFFFu ? entry_g(e) : wt_at(site);
+                    const uint32_t to = rp.bases[ro + k] & 3;
+                    if (cur == to) raise(st, DE_SAME_BASE);
+                    chs[k] = (site << 8) | (e != 0xFFFFFFFFu ? 0x80u : 0u) | (cur << 4) | to;
                 }
             } else {
-                heap_sort_u32(chs, nm);
+                Philox g(st->seed, st->compartment, st->generation, PH_MUTATE, i);
+                for (uint32_t k = 0; k < nm; k++) chs[k] = (uint32_t)g.below(L);
+                if (nm <= 16) {
+                    for (uint32_t a = 1; a < nm; a++) {
+                        uint32_t x = chs[a], c = a;
+                        while (c > 0 && chs[c - 1] > x) { chs[c] = chs[c - 1]; c--; }
+                        chs[c] = x;
+                    }
+                } else {
+                    heap_sort_u32(chs, nm);
+                }
+                for (uint32_t k = 0; k < nm; k++) {
+                    const uint32_t site = chs[k];
+                    // Haplotype::get_base on the PRE-mutation haplotype (duplicate sites of one event see the same base)
+                    const uint32_t e = merged_find(pe, plen, pd, nd, site, L);
+                    const uint32_t cur = e != 0xFFFFFFFFu ? entry_g(e) : wt_at(site);
+                    const uint32_t to = (uint32_t)weighted4(g, &s_subst[cur * 4]);
+                    if (cur == to) raise(st, DE_SAME_BASE);
+                    chs[k] = (site << 8) | (e != 0xFFFFFFFFu ? 0x80u : 0u) | (cur << 4) | to;
+                }
             }
-            for (uint32_t k = 0; k < nm; k++) {
-                uint32_t site = chs[k];
-                uint32_t cur = entries_get_base(pe, plen, site, wt);
-                uint32_t to = (uint32_t)weighted4(g, &st->host_subst[cur * 4]);
-                if (cur == to) raise(st, DE_SAME_BASE);
-                chs[k] = (site << 8) | (cur << 4) | to;
-            }
-        }
-        // merge parent entries with the change groups
-        uint32_t a = 0, b = 0, o = 0;
-        while (a < plen || b < nm) {
-            uint32_t pa = a < plen ? entry_pos(pe[a]) : 0xFFFFFFFFu;
-            uint32_t pb = b < nm ? ch_pos(chs[b]) : 0xFFFFFFFFu;
-            if (pa < pb) {
-                const uint32_t e = pe[a++];
-                if (o < HEAD_INLINE) hd_local[o] = e;
-                out[o++] = e;
-            } else {
-                const uint32_t first_to = ch_to(chs[b]);
+            // the event's entries: per distinct site g = first change's base (get_base: first matching change wins), m = last
+            // change's base, absent when that is the wildtype base (get_mutations: last change wins, back-mutation removes the key)
+            uint32_t n_new = 0;
+            for (uint32_t b = 0; b < nm;) {
+                const uint32_t pb = ch_pos(chs[b]), first_to = ch_to(chs[b]), present = ch_present(chs[b]);
                 uint32_t last_to = first_to;
                 while (b < nm && ch_pos(chs[b]) == pb) { last_to = ch_to(chs[b]); b++; }
-                if (pa == pb) a++;
-                const uint32_t w0 = wt[pb];
+                const uint32_t w0 = wt_at(pb);
                 const uint32_t m = (last_to == w0) ? 4u : last_to;
-                if (!(first_to == w0 && m == 4u)) {
-                    const uint32_t e = make_entry(pb, first_to, m);
-                    if (o < HEAD_INLINE) hd_local[o] = e;
-                    out[o++] = e;
+                const bool gone = first_to == w0 && m == 4u;   // indistinguishable from the wildtype at this site
+                if (gone && !present) continue;                 // nothing to override (a tombstone the parent's delta may hold stays)
+                nev[n_new++] = gone ? make_entry(pb, w0, ENTRY_TOMBSTONE) : make_entry(pb, first_to, m);
+                dlen += present ? (gone ? -1 : 0) : 1;
+            }
+            // parent delta merged with the event's entries (same position: the event wins)
+            {
+                uint32_t a = 0, b = 0;
+                while (a < nd || b < n_new) {
+                    const uint32_t pa = a < nd ? entry_pos(pd[a]) : 0xFFFFFFFFu, pb = b < n_new ? entry_pos(nev[b]) : 0xFFFFFFFFu;
+                    if (pa < pb) dm[ndm++] = pd[a++];
+                    else { if (pa == pb) a++; dm[ndm++] = nev[b++]; }
                 }
             }
-        }
-        double raw0_new = 1.0, fit_repro = 1.0;  // fit_repro: mapped fitness under the reproductive provider of spec 0 (patch_records == 3)
-        const int pi_repro = st->specs[0].repro;
-        for (uint32_t p = 0; p < st->n_providers; p++) {
-            const DevProvider &pr = st->prov[p];
-            double raw = 1.0;
-            if (pr.kind != VL_FITNESS_NEUTRAL) {
-                const double praw = (p == 0 && ph.valid) ? ph.raw0 : st->h_raw[p][pid];
-                double acc = 1.;
-                for (uint32_t k = 0; k < nm; k++) {
-                    const uint64_t row = (uint64_t)ch_pos(chs[k]) * 4;
-                    acc = acc * pr.table[row + ch_to(chs[k])] / pr.table[row + ch_from(chs[k])];
+            const int pi_repro = st->specs[0].repro;
+            for (uint32_t p = 0; p < st->n_providers; p++) {
+                const DevProvider &pr = st->prov[p];
+                double raw = 1.0;
+                if (pr.kind != VL_FITNESS_NEUTRAL) {
+                    const double praw = p == 0 ? ph.raw0 : st->h_raw[p][pid];
+                    double acc = 1.;
+                    for (uint32_t k = 0; k < nm; k++) {
+                        const uint64_t row = (uint64_t)ch_pos(chs[k]) * 4;
+                        acc = acc * pr.table[row + ch_to(chs[k])] / pr.table[row + ch_from(chs[k])];
+                    }
+                    if (pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, pe, plen, dm, ndm);
+                    raw = praw * acc;
                 }
-                if (pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, out, o);
-                raw = praw * acc;
+                const double mapped = utility_apply(pr, raw);
+                st->h_raw[p][new_id] = raw;
+                st->h_fit[p][new_id] = mapped;
+                if (p == 0) { nh.raw0 = raw; nh.fit0 = mapped; }
+                if ((int)p == pi_repro) fit_repro = mapped;
             }
-            const double mapped = utility_apply(pr, raw);
-            st->h_raw[p][new_id] = raw;
-            st->h_fit[p][new_id] = mapped;
-            if (p == 0) raw0_new = raw;
-            if ((int)p == pi_repro) fit_repro = mapped;
         }
+        // ---- records that get a list of their own: flattened by the whole warp, one after the other (the merged deltas
+        // sit in shared memory — or, for events of more than MUT_LOCAL sites, in the arena — where every lane can read them)
+        uint32_t flat_len = 0;
         {
-            MutHead nh;
-            nh.off = roff;
-            nh.len = o;
-            nh.valid = 1u;
-            nh.raw0 = raw0_new;
-#pragma unroll
-            for (uint32_t k = 0; k < HEAD_INLINE; k++) nh.inl[k] = k < o ? hd_local[k] : 0xFFFFFFFFu;
-            st->mh[new_id] = nh;
+            uint32_t jobs = __ballot_sync(0xFFFFFFFFu, ok && flat && !big);
+            while (jobs) {
+                const uint32_t src = __ffs(jobs) - 1;
+                jobs &= jobs - 1;
+                const uint64_t pe_s = __shfl_sync(0xFFFFFFFFu, (uint64_t)(uintptr_t)pe, src);
+                const uint64_t dm_s = __shfl_sync(0xFFFFFFFFu, (uint64_t)(uintptr_t)dm, src);
+                const uint64_t out_s = __shfl_sync(0xFFFFFFFFu, (uint64_t)(uintptr_t)out, src);
+                const uint32_t plen_s = __shfl_sync(0xFFFFFFFFu, plen, src), ndm_s = __shfl_sync(0xFFFFFFFFu, ndm, src);
+                const uint32_t o = warp_flatten((const uint32_t *)(uintptr_t)pe_s, plen_s, (const uint32_t *)(uintptr_t)dm_s, ndm_s, (uint32_t *)(uintptr_t)out_s, L);
+                if (lane == src) flat_len = o;
+            }
+            if (ok && flat && big) {  // rare: more sites in one event than the shared scratch holds
+                uint32_t o = 0;
+                merged_for_each(pe, plen, dm, ndm, [&](uint32_t e) { out[o++] = e; });
+                flat_len = o;
+            }
         }
-        st->hm[new_id] = HapMeta{roff, o, pid};
-        st->hap_id[i] = new_id;
-        if (patch_records == 3) {
-            // device-resident generation (vl_fused.cuh): items carry the host in .z; the new haplotype's mapped fitness
-            // replaces the infectant's carried value and joins its host's sum (the infect pass left mutating infectants out)
+        if (!ok) continue;
+        if (flat) {
+            nh.off = roff;
+            nh.len = flat_len;
+            nh.nd_mlen = flat_len << 8;
+#pragma unroll
+            for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = 0xFFFFFFFFu;
+        } else {
+            nh.off = ph.off;
+            nh.len = plen;
+            nh.nd_mlen = ndm | ((uint32_t)((int32_t)mlen + dlen) << 8);
+#pragma unroll
+            for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = k < ndm ? dm[k] : 0xFFFFFFFFu;
+        }
+        st->head[new_id] = nh;
+        if (patch_records >= 3) {
+            // device-resident generation (vl_fused.cuh): items carry the host in .z.  The new haplotype's mapped fitness
+            // replaces the infectant's carried value and joins its host's sum (the infect pass left it out).  3: the infect
+            // pass ran in this generation and has already written the new record's id into the population (ids are worklist
+            // positions); 4: the items were staged by the previous generation's resample, the population is patched here.
             st->pop_fit[i] = fit_repro;
-            if (tpos != NONE32 && fit_repro != 0.0) atomicAdd(&st->hsum[st->hsum_parity][tpos], fit_repro);
-        } else if (patch_records == 2) {
+            if (tpos != NONE32 && fit_repro != 0.0) red_add_f64(&st->hsum[st->hsum_parity][tpos], fit_repro);
+            if (patch_records == 4) st->hap_id[i] = new_id;
+            continue;
+        }
+        st->hap_id[i] = new_id;
+        if (patch_records == 2) {
             if (tpos != NONE32) st->tmp_rec[tpos].y = new_id;  // the bucket-partitioned record, not yet sorted
         } else if (patch_records) {
             const uint32_t h = st->host_id[i];
@@ -2054,53 +2140,89 @@ __global__ void k_swap_population(DevState *st) {
 }
 
 // ------------------------------------------------------------------------------------------ garbage collection
-// Flattened records have no ancestors to keep alive: a record is live iff an infectant (or a detached
-// population) references it.  Compaction runs only when the table or the arena passes its threshold.
+// A record is live iff an infectant (or a detached population) references it: records hold no references to other
+// records (a child shares its parent's base LIST, which is arena words, not a record).  Compaction runs only when the
+// table or the arena passes its threshold, and works on a bit map of the records, one word per 32:
+//   mark    one atomic OR per infectant (the map of 10^8 records is 12 MB: it stays in L2),
+//   words   live records and live (merged) entries per word, two scans over the words,
+//   copy    every live record is FLATTENED into the other arena (its own list, empty delta) under its new id =
+//           scan value of its word + set bits below it in the word; fitness memos move along,
+//   remap   every infectant looks its new id up with the same two reads.
+// The cost is proportional to the live records and the population, not to the records created since the last run.
+__device__ __forceinline__ uint32_t gc_new_id(const DevState *st, uint32_t id) {
+    const uint32_t w = id >> 5;
+    return st->gc_cbase[w] + __popc(st->gc_bits[w] & ((1u << (id & 31)) - 1u));
+}
 __global__ void k_gc_begin(DevState *st, int force) {
     st->gc_active = (force || st->n_hap > st->gc_hap_threshold || st->arena_top > st->gc_arena_threshold) ? 1u : 0u;
 }
-__global__ void __launch_bounds__(TPB) k_gc_clear(DevState *st) {
-    if (!st->gc_active) return;
-    const uint64_t nh = st->n_hap;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_mark[h] = (h == 0) ? 1u : 0u;
+// keep_wildtype: record 0 exists on every handle and keeps its id (compaction); the dedup of a detached population
+// (vl_pop_pack_device) never ships it
+__global__ void __launch_bounds__(TPB) k_gc_clear(DevState *st, int guarded, int keep_wildtype) {
+    if (guarded && !st->gc_active) return;
+    const uint64_t nw = (st->n_hap + 31) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->gc_nw = nw;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (uint64_t)gridDim.x * blockDim.x)
+        st->gc_bits[w] = (w == 0 && keep_wildtype) ? 1u : 0u;
 }
-__global__ void __launch_bounds__(TPB) k_gc_mark(DevState *st, const uint32_t *__restrict__ ids, uint64_t m, int use_population) {
-    if (!st->gc_active) return;
+__global__ void __launch_bounds__(TPB) k_gc_mark(DevState *st, const uint32_t *__restrict__ ids, uint64_t m, int use_population, int guarded, int skip_wildtype) {
+    if (guarded && !st->gc_active) return;
     if (use_population) { ids = st->hap_id; m = st->n; }
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) st->gc_mark[ids[i]] = 1u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        if (skip_wildtype && id == 0) continue;
+        atomicOr(&st->gc_bits[id >> 5], 1u << (id & 31));
+    }
 }
-__global__ void __launch_bounds__(TPB) k_gc_lens(DevState *st) {
-    if (!st->gc_active) return;
-    const uint64_t nh = st->n_hap;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_len[h] = st->gc_mark[h] ? st->hm[h].len : 0u;
+__global__ void __launch_bounds__(TPB) k_gc_words(DevState *st, int guarded) {
+    if (guarded && !st->gc_active) return;
+    const uint64_t nw = (st->n_hap + 31) >> 5;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t bits = st->gc_bits[w], len = 0;
+        st->gc_wcnt[w] = __popc(bits);
+        while (bits) {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            len += st->head[(w << 5) + b].nd_mlen >> 8;
+        }
+        st->gc_wlen[w] = len;
+    }
 }
 __global__ void __launch_bounds__(TPB) k_gc_copy(DevState *st) {
     if (!st->gc_active) return;
-    const uint64_t nh = st->n_hap;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) {
-        if (!st->gc_mark[h]) continue;
-        const uint32_t nid = st->gc_newid[h];
-        const uint64_t noff = st->gc_newoff[h];
-        const uint32_t len = st->hm[h].len;
-        const uint32_t *src = st->arena + st->hm[h].off;
-        uint32_t *dst = st->arena_alt + noff;
-        for (uint32_t k = 0; k < len; k++) dst[k] = src[k];
-        {
-            MutHead mh = st->mh[h];
-            mh.off = noff;
-            st->mh_alt[nid] = mh;
+    const uint64_t nw = (st->n_hap + 31) >> 5;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t bits = st->gc_bits[w];
+        if (!bits) continue;
+        uint32_t nid = st->gc_cbase[w];
+        uint64_t noff = st->gc_lbase[w];
+        while (bits) {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint64_t h = (w << 5) + b;
+            const HapHead hd = st->head[h];
+            uint32_t *dst = st->arena_alt + noff;
+            uint32_t o = 0;
+            merged_for_each(st->arena + hd.off, hd.len, hd.d, head_nd(hd), [&](uint32_t e) { dst[o++] = e; });
+            HapHead nh;
+            nh.off = noff;
+            nh.len = o;
+            nh.nd_mlen = o << 8;
+            nh.raw0 = hd.raw0;
+            nh.fit0 = hd.fit0;
+#pragma unroll
+            for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = 0xFFFFFFFFu;
+            st->head_alt[nid] = nh;
+            for (uint32_t p = 0; p < st->n_providers; p++) { hap_raw_alt(st, p, nid) = hap_raw(st, p, h); st->h_fit_alt[p][nid] = st->h_fit[p][h]; }
+            nid += 1;
+            noff += o;
         }
-        st->hm_alt[nid].off = noff;
-        st->hm_alt[nid].len = len;
-        const uint32_t par = st->hm[h].parent;
-        st->hm_alt[nid].parent = (par != NONE32 && st->gc_mark[par]) ? st->gc_newid[par] : NONE32;
-        for (uint32_t p = 0; p < st->n_providers; p++) { hap_raw_alt(st, p, nid) = hap_raw(st, p, h); st->h_fit_alt[p][nid] = st->h_fit[p][h]; }
     }
 }
 __global__ void __launch_bounds__(TPB) k_gc_remap(DevState *st, uint32_t *ids, uint64_t m, int use_population) {
     if (!st->gc_active) return;
     if (use_population) { ids = st->hap_id; m = st->n; }
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) ids[i] = st->gc_newid[ids[i]];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) ids[i] = gc_new_id(st, ids[i]);
 }
 // gc_totals[0] = live records, gc_totals[1] = live arena words (written by the two scans)
 __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
@@ -2108,7 +2230,7 @@ __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
     st->n_hap = gc_totals[0];
     st->arena_top = gc_totals[1];
 #define VL_SWAP(a, b) { auto t = st->a; st->a = st->b; st->b = t; }
-    VL_SWAP(hm, hm_alt) VL_SWAP(mh, mh_alt) VL_SWAP(arena, arena_alt)
+    VL_SWAP(head, head_alt) VL_SWAP(arena, arena_alt)
     for (uint32_t p = 0; p < st->n_providers; p++) { VL_SWAP(h_raw[p], h_raw_alt[p]) VL_SWAP(h_fit[p], h_fit_alt[p]) }
 #undef VL_SWAP
     st->gc_runs += 1;

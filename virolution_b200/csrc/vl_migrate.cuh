@@ -37,23 +37,11 @@ __host__ inline PackHeader make_pack_header(uint64_t n_pop, uint64_t n_unique, u
     return h;
 }
 
-__global__ void __launch_bounds__(TPB) k_pack_clear(DevState *st) {
-    const uint64_t nh = st->n_hap;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_mark[h] = 0u;
-}
-// the wildtype (id 0) exists on every handle and is never shipped
-__global__ void __launch_bounds__(TPB) k_pack_mark(DevState *st, const uint32_t *__restrict__ ids, uint64_t m) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t id = ids[i];
-        if (id != 0) st->gc_mark[id] = 1u;
-    }
-}
-__global__ void __launch_bounds__(TPB) k_pack_lens(DevState *st) {
-    const uint64_t nh = st->n_hap;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (uint64_t)gridDim.x * blockDim.x) st->gc_len[h] = st->gc_mark[h] ? st->hm[h].len : 0u;
-}
+// The distinct haplotypes of a detached population are found with the compaction's bit map (k_gc_clear / k_gc_mark /
+// k_gc_words + the two scans, vl_kernels.cuh; the wildtype — id 0, present on every handle — is never shipped); every one
+// is written once, flattened.
 __global__ void __launch_bounds__(TPB) k_pack_copy(DevState *st, const uint32_t *__restrict__ ids, uint8_t *image, PackHeader hd) {
-    const uint64_t nh = st->n_hap;
+    const uint64_t nw = (st->n_hap + 31) >> 5;
     uint32_t *o_idx = reinterpret_cast<uint32_t *>(image + hd.off_idx);
     uint32_t *o_len = reinterpret_cast<uint32_t *>(image + hd.off_len);
     uint64_t *o_off = reinterpret_cast<uint64_t *>(image + hd.off_off);
@@ -61,20 +49,27 @@ __global__ void __launch_bounds__(TPB) k_pack_copy(DevState *st, const uint32_t 
     uint32_t *o_ent = reinterpret_cast<uint32_t *>(image + hd.off_entries);
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, span = (uint64_t)gridDim.x * blockDim.x;
     if (tid == 0) *reinterpret_cast<PackHeader *>(image) = hd;
-    for (uint64_t h = tid; h < nh; h += span) {
-        if (!st->gc_mark[h]) continue;
-        const uint32_t u = st->gc_newid[h];
-        const uint64_t noff = st->gc_newoff[h];
-        const uint32_t len = st->hm[h].len;
-        o_len[u] = len;
-        o_off[u] = noff;
-        for (uint32_t p = 0; p < st->n_providers; p++) o_raw[(uint64_t)p * hd.n_unique + u] = hap_raw(st, p, h);
-        const uint32_t *src = st->arena + st->hm[h].off;
-        for (uint32_t k = 0; k < len; k++) o_ent[noff + k] = src[k];
+    for (uint64_t w = tid; w < nw; w += span) {
+        uint32_t bits = st->gc_bits[w];
+        if (!bits) continue;
+        uint32_t u = st->gc_cbase[w];
+        uint64_t noff = st->gc_lbase[w];
+        while (bits) {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint64_t h = (w << 5) + b;
+            const HapHead hh = st->head[h];
+            const uint32_t len = flatten_record(st, hh, o_ent + noff);
+            o_len[u] = len;
+            o_off[u] = noff;
+            for (uint32_t p = 0; p < st->n_providers; p++) o_raw[(uint64_t)p * hd.n_unique + u] = hap_raw(st, p, h);
+            u += 1;
+            noff += len;
+        }
     }
     for (uint64_t i = tid; i < hd.n_pop; i += span) {
         const uint32_t id = ids[i];
-        o_idx[i] = id == 0 ? NONE32 : st->gc_newid[id];
+        o_idx[i] = id == 0 ? NONE32 : gc_new_id(st, id);
     }
 }
 
@@ -104,11 +99,8 @@ __global__ void __launch_bounds__(TPB) k_unpack(DevState *st, const uint8_t *__r
     if (ok) {
         for (uint64_t u = tid; u < hd.n_unique; u += span) {
             const uint64_t id = id0 + u;
-            st->hm[id].off = a0 + i_off[u];
-            st->hm[id].len = i_len[u];
-            st->hm[id].parent = NONE32;
             for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, id, i_raw[(uint64_t)p * hd.n_unique + u]);
-            write_head(st, id, a0 + i_off[u], i_len[u], i_ent + i_off[u]);
+            write_flat_head(st, id, a0 + i_off[u], i_len[u]);
         }
         for (uint64_t w = tid; w < hd.n_words; w += span) st->arena[a0 + w] = i_ent[w];
     }
@@ -132,7 +124,7 @@ __global__ void __launch_bounds__(TPB) k_mig_lens(DevState *st, const uint32_t *
     const uint32_t P = st->n_providers;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t id = ids[i];
-        const uint32_t len = id == 0 ? 0u : st->hm[id].len;
+        const uint32_t len = id == 0 ? 0u : st->head[id].nd_mlen >> 8;  // entries of the flattened record
         len_out[m0 + i] = id == 0 ? MIG_WILDTYPE : len;
         words_out[m0 + i] = len;
         for (uint32_t p = 0; p < P; p++) raw_out[(m0 + i) * P + p] = hap_raw(st, p, id);
@@ -143,10 +135,8 @@ __global__ void __launch_bounds__(TPB) k_mig_copy(DevState *st, const uint32_t *
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t id = ids[i];
         if (id == 0) continue;
-        const HapMeta hm = st->hm[id];
-        const uint32_t *src = st->arena + hm.off;
-        uint32_t *dst = entries_out + word_off[m0 + i];
-        for (uint32_t k = 0; k < hm.len; k++) dst[k] = src[k];
+        const HapHead hh = st->head[id];
+        flatten_record(st, hh, entries_out + word_off[m0 + i]);
     }
 }
 // words per migrant of a received image (the wildtype marker carries no words)
@@ -180,12 +170,11 @@ __global__ void __launch_bounds__(TPB) k_mig_import(DevState *st, const uint32_t
         const uint32_t l = len_in[i];
         if (l == MIG_WILDTYPE || !ok) { ids_out[i] = 0u; continue; }
         const uint64_t id = id0 + rec_off[i], off = a0 + word_off[i];
-        st->hm[id] = HapMeta{off, l, NONE32};
         for (uint32_t p = 0; p < P; p++) set_fitness(st, p, id, raw_in[i * P + p]);
         const uint32_t *src = entries_in + word_off[i];
         uint32_t *dst = st->arena + off;
         for (uint32_t k = 0; k < l; k++) dst[k] = src[k];
-        write_head(st, id, off, l, src);
+        write_flat_head(st, id, off, l);
         ids_out[i] = (uint32_t)id;
     }
 }
@@ -234,11 +223,9 @@ __global__ void __launch_bounds__(TPB) k_target_size(DevState *st) {
 __global__ void __launch_bounds__(TPB) k_export_count(DevState *st, uint32_t *__restrict__ cnt) {
     const uint64_t n = st->n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t id = st->hap_id[i];
-        const uint32_t *e = st->arena + st->hm[id].off;
-        const uint32_t len = st->hm[id].len;
+        const HapHead hh = st->head[st->hap_id[i]];
         uint32_t c = 0;
-        for (uint32_t k = 0; k < len; k++) c += entry_m(e[k]) < 4 ? 1u : 0u;
+        merged_for_each(st->arena + hh.off, hh.len, hh.d, head_nd(hh), [&](uint32_t e) { c += entry_m(e) < 4 ? 1u : 0u; });
         cnt[i] = c;
     }
 }
@@ -246,13 +233,11 @@ __global__ void __launch_bounds__(TPB) k_export_fill(DevState *st, const uint64_
                                                      uint8_t *__restrict__ base_out) {
     const uint64_t n = st->n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t id = st->hap_id[i];
-        const uint32_t *e = st->arena + st->hm[id].off;
-        const uint32_t len = st->hm[id].len;
+        const HapHead hh = st->head[st->hap_id[i]];
         uint64_t o = offsets[i];
-        for (uint32_t k = 0; k < len; k++) {
-            if (entry_m(e[k]) < 4) { pos_out[o] = entry_pos(e[k]); base_out[o] = (uint8_t)entry_m(e[k]); o++; }
-        }
+        merged_for_each(st->arena + hh.off, hh.len, hh.d, head_nd(hh), [&](uint32_t e) {
+            if (entry_m(e) < 4) { pos_out[o] = entry_pos(e); base_out[o] = (uint8_t)entry_m(e); o++; }
+        });
     }
 }
 // ---- population statistics (src/stats/population.rs) ---------------------------------------------------------------
@@ -261,13 +246,11 @@ __global__ void __launch_bounds__(TPB) k_export_fill(DevState *st, const uint64_
 __global__ void __launch_bounds__(TPB) k_stats_counts(DevState *st, uint32_t *__restrict__ counts) {
     const uint64_t n = st->n;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t id = st->hap_id[i];
-        const HapMeta hm = st->hm[id];
-        const uint32_t *e = st->arena + hm.off;
-        for (uint32_t k = 0; k < hm.len; k++) {
-            const uint32_t m = entry_m(e[k]);
-            if (m < 4) atomicAdd(&counts[(uint64_t)entry_pos(e[k]) * 4 + m], 1u);
-        }
+        const HapHead hh = st->head[st->hap_id[i]];
+        merged_for_each(st->arena + hh.off, hh.len, hh.d, head_nd(hh), [&](uint32_t e) {
+            const uint32_t m = entry_m(e);
+            if (m < 4) atomicAdd(&counts[(uint64_t)entry_pos(e) * 4 + m], 1u);
+        });
     }
 }
 // PopulationStatistics::mean (:50-56): sum of the mapped attribute over infectants; one partial sum per CTA in a fixed
@@ -289,8 +272,9 @@ __global__ void __launch_bounds__(TPB) k_stats_fitness_sum(DevState *st, int pro
 }
 __global__ void k_get_base(DevState *st, uint64_t infectant, uint32_t pos, uint32_t *out) {
     if (infectant >= st->n || pos >= st->L) { *out = 0xFFu; return; }
-    const uint32_t id = st->hap_id[infectant];
-    *out = entries_get_base(st->arena + st->hm[id].off, st->hm[id].len, pos, st->wildtype);
+    const HapHead hh = st->head[st->hap_id[infectant]];
+    const uint32_t e = merged_find(st->arena + hh.off, hh.len, hh.d, head_nd(hh), pos, st->L);
+    *out = e != 0xFFFFFFFFu ? entry_g(e) : st->wildtype[pos];  // Haplotype::get_base (src/core/haplotype.rs:402-408)
 }
 
 }  // namespace vl

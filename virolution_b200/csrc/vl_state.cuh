@@ -9,8 +9,8 @@
 //                                             the haplotype id carried along, so everything downstream of the
 //                                             counting sort streams over host-contiguous records
 //   replication    lam[p] f64 (Poisson mean of the record at CSR position p), offspring[p] u32, tile_sum[] u64
-//   haplotypes     hm[id] = {arena offset u64, length u32, parent u32} (16 B) + h_raw[provider][id] f64
-//                  + arena of u32 entries
+//   haplotypes     head[id] = {base list offset u64, length u32, delta count | merged length, raw0, fit0, 8 delta entries}
+//                  (64 B) + h_raw[provider][id], h_fit[provider][id] f64 + arena of u32 entries
 //
 // A haplotype record is the *flattened* form of the reference's delta chain (Wildtype / Mutant{changes} /
 // Recombinant{left,right,window}, src/core/haplotype.rs:45-56,241-288): the position-sorted list of sites where
@@ -83,25 +83,28 @@ struct DevSpec {
     int32_t repro, infect;  // provider index or -1
 };
 
-struct alignas(16) HapMeta {
-    uint64_t off;    // first arena word
-    uint32_t len;    // entries
-    uint32_t parent; // id of the haplotype it was derived from (NONE32 for the wildtype / migrants)
+// One haplotype record = one 64-byte line.  The reference stores a delta chain (Mutant{parent, changes},
+// src/core/haplotype.rs:45-56,570-594): a mutation costs O(1) whatever the depth, a base lookup walks the chain
+// (:661-667).  Here a record is a BASE LIST (position-sorted flattened entries in the arena, shared with the ancestors it
+// was inherited from) plus up to HEAD_DELTA DELTA ENTRIES inline (position-sorted, each overriding the base entry at its
+// position; m == ENTRY_TOMBSTONE removes it).  A mutation copies the 64-byte line and merges its changes into the
+// delta — O(1) in the haplotype's length; when the delta would overflow, the record is flattened into a fresh base list
+// (one O(length) copy per HEAD_DELTA mutations of a lineage, the stand-in for Mutant::try_merge_node, :743-784).
+// Lookups scan the delta, then search the base list by interpolation (sites are drawn uniformly, so the list is
+// uniformly spaced: ~2 probes).  The compaction (k_gc_*) flattens every live record.
+constexpr uint32_t HEAD_DELTA = 8;
+constexpr uint32_t ENTRY_TOMBSTONE = 5;  // m field of a delta entry that removes the base entry at its position
+struct alignas(64) HapHead {
+    uint64_t off;       // first arena word of the base list
+    uint32_t len;       // base entries
+    uint32_t nd_mlen;   // delta entries (low 8 bits) | entries of the merged record << 8
+    double raw0;        // raw fitness under provider 0 (copy of h_raw[0][id]: the mutate kernel reads ONE line per parent)
+    double fit0;        // mapped fitness under provider 0 (copy of h_fit[0][id])
+    uint32_t d[HEAD_DELTA];
 };
-
-// What k_mutate needs of a parent, gathered into ONE 64-byte line: metadata, raw fitness under provider 0 and the first
-// entries of the flattened record.  hm / h_raw / arena stay the source of truth (every other kernel reads those); this
-// is a cache that turns the four dependent random reads per mutation (metadata, raw fitness, one or two arena lines)
-// into one.  `valid` is written by whoever creates the record.
-constexpr uint32_t HEAD_INLINE = 10;
-struct alignas(64) MutHead {
-    uint64_t off;
-    uint32_t len;
-    uint32_t valid;
-    double raw0;
-    uint32_t inl[HEAD_INLINE];
-};
-static_assert(sizeof(MutHead) == 64, "one line per haplotype");
+static_assert(sizeof(HapHead) == 64, "one line per haplotype");
+__host__ __device__ inline uint32_t head_nd(const HapHead &h) { return h.nd_mlen & 0xFFu; }
+__host__ __device__ inline uint32_t head_mlen(const HapHead &h) { return h.nd_mlen >> 8; }
 
 struct DevState {
     // ---- configuration (BasicHost.parameters are the values captured at vl_create, the simulation's
@@ -188,13 +191,15 @@ struct DevState {
     unsigned long long arena_top;
     uint32_t gc_active;
     uint32_t _pad1;
-    HapMeta *hm, *hm_alt;  // 16 bytes per haplotype: arena offset, length, parent
-    MutHead *mh, *mh_alt;  // 64 bytes per haplotype: the mutate kernel's one-line view of a parent
+    HapHead *head, *head_alt;  // 64 bytes per haplotype: base list, inline delta, fitness under provider 0
     double *h_raw[MAX_PROVIDERS], *h_raw_alt[MAX_PROVIDERS];  // memoised raw fitness per provider
     double *h_fit[MAX_PROVIDERS], *h_fit_alt[MAX_PROVIDERS];  // utility(raw): what readers of get_or_compute see (attributes.rs:220-241)
     uint32_t *arena, *arena_alt;
-    uint32_t *gc_mark, *gc_newid, *gc_len;
-    uint64_t *gc_newoff;
+    // compaction / dedup scratch, one entry per 32 records: live bit map, live records and live (merged) entries per word,
+    // exclusive scans of the two
+    uint32_t *gc_bits, *gc_wcnt, *gc_wlen, *gc_cbase;
+    uint64_t *gc_lbase;
+    uint64_t gc_nw;        // words of the bit map in use: ceil(n_hap / 32), written by k_gc_clear for the scans
     uint64_t gc_hap_threshold, gc_arena_threshold;
     uint64_t gc_runs;
     uint64_t kernels_launched;  // maintained by the host, mirrored here for export
@@ -243,7 +248,7 @@ __device__ __forceinline__ void tile_range(const DevState *st, uint64_t tile, ui
 }
 
 // memoised raw fitness of haplotype `id` under provider p (AttributeSet::get_or_compute_raw, src/core/attributes.rs:196-217)
-// (kept apart from HapMeta: the per-infectant fitness gather wants the densest possible array)
+// (kept apart from the 64-byte heads: the per-infectant fitness gather wants the densest possible array)
 __host__ __device__ inline double &hap_raw(DevState *st, uint32_t p, uint64_t id) { return st->h_raw[p][id]; }
 __host__ __device__ inline const double &hap_raw(const DevState *st, uint32_t p, uint64_t id) { return st->h_raw[p][id]; }
 __host__ __device__ inline double &hap_raw_alt(DevState *st, uint32_t p, uint64_t id) { return st->h_raw_alt[p][id]; }
@@ -253,6 +258,81 @@ __host__ __device__ inline uint32_t make_entry(uint32_t pos, uint32_t g, uint32_
 __host__ __device__ inline uint32_t entry_pos(uint32_t e) { return e >> 8; }
 __host__ __device__ inline uint32_t entry_g(uint32_t e) { return (e >> 4) & 0xF; }
 __host__ __device__ inline uint32_t entry_m(uint32_t e) { return e & 0xF; }  // 4 = not in the mutation set
+
+__host__ __device__ inline bool entry_is_tombstone(uint32_t e) { return (e & 0xFu) == ENTRY_TOMBSTONE; }
+
+// lower bound by position in a sorted entry list whose positions are spread uniformly over [0, L) (mutation sites are
+// uniform draws).  On the device: the interpolated guess is off by a few entries at most (binomial spread), so the eight
+// entries around it are fetched with two 16-byte loads issued together (aligned on the arena, words outside the list are
+// masked) and almost every search ends there after ONE memory latency; otherwise interpolation steps alternate with
+// bisection steps on the rest (O(log n) on any list).  The arena is padded, so the window may overhang the list.
+__host__ __device__ inline uint32_t entries_lower_interp(const uint32_t *e, uint32_t n, uint32_t pos, uint32_t L) {
+    uint32_t lo = 0, hi = n, plo = 0, phi = L;  // positions of e[lo..hi) lie in [plo, phi]
+    if (n == 0) return 0;
+#ifdef __CUDA_ARCH__
+    {
+        uint32_t g = (uint32_t)((float)pos * ((float)n / (float)L));
+        if (g >= n) g = n - 1;
+        // window of 8 words starting at a 16-byte boundary of the arena, two entries before the guess
+        const uintptr_t first = (uintptr_t)(e + (g >= 2 ? g - 2 : 0)) & ~(uintptr_t)15;
+        const int32_t k0 = (int32_t)(((intptr_t)first - (intptr_t)(uintptr_t)e) / 4);  // list index of the first window word (may be negative)
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(first), v1 = *reinterpret_cast<const uint4 *>(first + 16);
+        const uint32_t wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint32_t below = 0, inside = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int32_t k = k0 + j;
+            const bool in = k >= 0 && k < (int32_t)n;
+            inside += in ? 1u : 0u;
+            below += (in && entry_pos(wv[j]) < pos) ? 1u : 0u;
+        }
+        const int32_t kb = k0 < 0 ? 0 : k0;                     // first list index inside the window
+        const int32_t ke = kb + (int32_t)inside;               // one past the last
+        // the entries are sorted: `below` of them, the first ones of the window, are smaller
+        if ((below > 0 || kb == 0) && (below < inside || ke == (int32_t)n)) return (uint32_t)kb + below;
+        if (below == 0) { hi = (uint32_t)kb; } else { lo = (uint32_t)ke; }
+    }
+#endif
+    bool interp = true;
+    while (lo < hi) {
+        uint32_t mid;
+        if (interp && pos >= plo && phi > plo) {
+            const float t = (float)(pos - plo) * ((float)(hi - lo) / (float)(phi - plo + 1u));
+            const uint32_t ti = (uint32_t)t;
+            mid = lo + (ti < hi - lo - 1u ? ti : hi - lo - 1u);
+        } else {
+            mid = (lo + hi) >> 1;
+        }
+        interp = !interp;
+        const uint32_t p = entry_pos(e[mid]);
+        if (p < pos) { lo = mid + 1; plo = p + 1u; } else { hi = mid; phi = p; }
+    }
+    return lo;
+}
+
+// merged view of a record: base list overridden by the delta, tombstones dropped; f(entry) in ascending position order
+template <typename F>
+__host__ __device__ inline void merged_for_each(const uint32_t *base, uint32_t len, const uint32_t *d, uint32_t nd, F &&f) {
+    uint32_t a = 0, b = 0;
+    while (a < len || b < nd) {
+        const uint32_t pa = a < len ? entry_pos(base[a]) : 0xFFFFFFFFu, pb = b < nd ? entry_pos(d[b]) : 0xFFFFFFFFu;
+        if (pa < pb) {
+            f(base[a++]);
+        } else {
+            if (pa == pb) a++;
+            const uint32_t e = d[b++];
+            if (!entry_is_tombstone(e)) f(e);
+        }
+    }
+}
+// entry of the merged record at `pos`, or 0xFFFFFFFF when it has none
+__host__ __device__ inline uint32_t merged_find(const uint32_t *base, uint32_t len, const uint32_t *d, uint32_t nd, uint32_t pos, uint32_t L) {
+    for (uint32_t k = 0; k < nd; k++)
+        if (entry_pos(d[k]) == pos) return entry_is_tombstone(d[k]) ? 0xFFFFFFFFu : d[k];
+    const uint32_t i = entries_lower_interp(base, len, pos, L);
+    if (i < len && entry_pos(base[i]) == pos) return base[i];
+    return 0xFFFFFFFFu;
+}
 
 // lower bound by position in a sorted entry list
 __host__ __device__ inline uint32_t entries_lower(const uint32_t *e, uint32_t n, uint32_t pos) {
