@@ -1444,7 +1444,7 @@ constexpr uint64_t GRAPH_MAX_POPULATION = 4u << 20;  // above this a generation 
 static bool graph_wanted(const vl_sim *sim) {
     const DevState &h = sim->h;
     const bool replay = sim->has_rp_inf || sim->has_rp_mut || sim->has_rp_rec || sim->has_rp_off;
-    return !sim->graph_disabled && !sim->profiling && !(sim->experiment & 64) && !replay && sim->n_bound <= GRAPH_MAX_POPULATION &&
+    return !sim->graph_disabled && !sim->profiling && !(sim->experiment & 64) && !replay && (sim->n_bound <= GRAPH_MAX_POPULATION || (sim->experiment & 128)) &&
            sim->n_bound == std::min<uint64_t>(h.cap_inf, h.max_population);  // the bound every later generation has too
 }
 static int enqueue_generation(vl_sim *sim) {

@@ -62,6 +62,7 @@ struct InfectCtx {
     PhiloxKey key;
     uint32_t *host_id;
     double *hsum;
+    uint64_t keep, stream;  // L2 policies: per-host sums stay, per-infectant streams pass
 };
 __device__ __forceinline__ void infect_draw(DevState *st, const InfectCtx &c, uint64_t i, double fit, uint32_t &h, uint32_t &nm) {
     const uint4 b0 = philox_block(c.key, i, c.gen, PH_INFECT, 0);
@@ -71,10 +72,10 @@ __device__ __forceinline__ void infect_draw(DevState *st, const InfectCtx &c, ui
     }
     h = (uint32_t)(m >> 32);
     nm = mutation_count_small(st, c.key, i, c.gen, b0);
-    c.host_id[i] = h;
+    st_u32_hint(&c.host_id[i], h, c.stream);
     // (a mutating infectant's fitness is about to change: k_mutate stores the new value and adds it to the host's sum;
     // f == 0.0 adds nothing)
-    if (nm == 0u && fit != 0.0) red_add_f64(&c.hsum[h], fit);
+    if (nm == 0u && fit != 0.0) red_add_f64_hint(&c.hsum[h], fit, c.keep);
 }
 // Mutation worklist staged per CTA in shared memory: (infectant, n_mut, host, parent haplotype), appended with one vote
 // and one shared atomic per warp round, flushed with ONE global atomic per CTA pass (same-address global atomics are
@@ -136,6 +137,8 @@ __global__ void __launch_bounds__(IS_TPB, 4) k_infect_sum(DevState *st) {
     c.key = philox_key(st->seed, st->compartment);
     c.host_id = st->host_id;
     c.hsum = st->hsum[st->hsum_parity];
+    c.keep = l2_keep_policy();
+    c.stream = l2_stream_policy();
     const unsigned long long id_base = st->n_hap;
     CtaList cl{s_items, s_cnt};
     if (tid == 0) s_cnt[0] = 0u;
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t kmax = poisson_kmax(R0 < 12.0 ? R0 : 12.0);  // lambda = R0 * f / S <= R0 for non-negative fitness
     const uint32_t tid = threadIdx.x;
+    const uint64_t keep = l2_keep_policy(), stream = l2_stream_policy();
     if (blockIdx.x == 0 && tid == 0) {
         st->n_sorted = n;
         st->host_tiles = 0;   // tiles of consecutive infectants (tile_range)
@@ -206,11 +210,11 @@ __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
 #pragma unroll
         for (int j = 0; j < OS_PER; j++) {
             const uint64_t p = p0 + (uint64_t)j * OS_TPB + tid;
-            h[j] = p < n ? host_id[p] : NONE32;
-            f[j] = p < n ? pop_fit[p] : 0.0;
+            h[j] = p < n ? ld_u32_hint(&host_id[p], stream) : NONE32;
+            f[j] = p < n ? ld_f64_stream(&pop_fit[p], stream) : 0.0;
         }
 #pragma unroll
-        for (int j = 0; j < OS_PER; j++) S[j] = h[j] != NONE32 ? __ldcg(&hsum[h[j]]) : 1.0;
+        for (int j = 0; j < OS_PER; j++) S[j] = h[j] != NONE32 ? ld_f64_hint(&hsum[h[j]], keep) : 1.0;
         uint32_t local = 0;
 #pragma unroll
         for (int j = 0; j < OS_PER; j++) {
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
                 if (v > 0xFFFFFFFFull) { raise(st, DE_OFFSPRING_RANGE); v = 0xFFFFFFFFull; }
                 off = (uint32_t)v;
             }
-            offspring[p] = off;
+            st_u32_hint(&offspring[p], off, stream);
             local += off;
         }
         uint64_t tot = local;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
     // the buffer the next generation accumulates into
     double *other = st->hsum[st->hsum_parity ^ 1u];
     const uint64_t H = st->H;
-    for (uint64_t k = (uint64_t)blockIdx.x * OS_TPB + tid; k < H; k += (uint64_t)gridDim.x * OS_TPB) other[k] = 0.0;
+    for (uint64_t k = (uint64_t)blockIdx.x * OS_TPB + tid; k < H; k += (uint64_t)gridDim.x * OS_TPB) st_f64_hint(&other[k], 0.0, keep);
 }
 
 // ---- resample over tiles of consecutive infectants ---------------------------------------------------------------------
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
 // record order inside a tile, same draw values and the same value -> record rule as k_resample on the identity layout of
 // the same offspring map, so the drawn haplotypes are the same.  The staged payload is (haplotype, mapped fitness): the
 // child inherits both.
-constexpr int RT_TPB = 512;
+constexpr int RT_TPB = 256;
 constexpr int RT_PER = RESAMPLE_TILE / RT_TPB;  // stripes: item q = k * RT_TPB + tid (coalesced loads)
 static_assert(RANK_WORDS % RT_TPB == 0, "every thread owns RANK_WORDS / RT_TPB consecutive mask words");
 struct ResamplePosArgs {
@@ -266,7 +270,7 @@ struct ResamplePosArgs {
 // k_offspring_sum of this generation) and the worklist are ready when the next generation begins, which then starts with
 // k_mutate.  The children are as they would be without it; k_infect_sum makes the same draws from the same streams.
 template <bool PREFILL>
-__global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, ResamplePosArgs ra) {
+__global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, ResamplePosArgs ra) {
     extern __shared__ uint4 s_items_dyn[];      // PREFILL: CL_CAP staged worklist items
     __shared__ uint32_t s_clcnt[2];
     __shared__ uint32_t s_hap[RESAMPLE_TILE];   // compacted payloads of the records with offspring
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, Resamp
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t gen = st->generation;
     const uint64_t stride = st->tile_stride;
+    const uint64_t l2s = l2_stream_policy();
     InfectCtx ictx;
     CtaList cl{s_items_dyn, s_clcnt};
     if (PREFILL) {
@@ -298,6 +303,8 @@ __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, Resamp
         ictx.key = key;
         ictx.host_id = st->host_id;
         ictx.hsum = st->hsum[st->hsum_parity ^ 1u];
+        ictx.keep = l2_keep_policy();
+        ictx.stream = l2_stream_policy();
         if (tid == 0) s_clcnt[0] = 0u;
     }
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
@@ -328,9 +335,9 @@ __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, Resamp
 #pragma unroll
         for (int k = 0; k < RT_PER; k++) {
             const uint32_t q = k * RT_TPB + tid;
-            v[k] = q < tlen ? offspring[start + q] : 0u;
-            hp[k] = q < tlen ? hap_id[start + q] : 0u;
-            ft[k] = q < tlen ? pop_fit[start + q] : 0.0;
+            v[k] = q < tlen ? ld_u32_hint(&offspring[start + q], l2s) : 0u;
+            hp[k] = q < tlen ? ld_u32_hint(&hap_id[start + q], l2s) : 0u;
+            ft[k] = q < tlen ? ld_f64_stream(&pop_fit[start + q], l2s) : 0.0;
         }
         constexpr uint32_t WPT = RANK_WORDS / RT_TPB;  // mask words per thread
 #pragma unroll
@@ -478,8 +485,8 @@ __global__ void __launch_bounds__(RT_TPB, 2) k_resample_pos(DevState *st, Resamp
                     }
                     hap = s_hap[slot];
                     const double fit = s_fit[slot];
-                    dst[s] = hap;
-                    if (dstf) dstf[s] = fit;
+                    st_u32_hint(&dst[s], hap, l2s);
+                    if (dstf) st_f64_hint(&dstf[s], fit, l2s);
                     if (PREFILL) infect_draw(st, ictx, s, fit, h, nm);
                 }
                 if (PREFILL) cl_push(cl, nm != 0u, make_uint4((uint32_t)s, nm, h, hap));

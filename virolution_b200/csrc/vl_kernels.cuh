@@ -36,9 +36,46 @@ constexpr uint32_t SMEM_SORT_MAX = 4096;  // slices up to this length are sorted
 constexpr int INFECT_ITEMS = 4;           // infectants per thread and round in k_infect / k_scatter
 
 __device__ __forceinline__ void raise(DevState *st, uint32_t bit) { atomicOr(&st->error, bit); }
+// ---- L2 residency hints.  The per-host sums of the device-resident generation (H x 8 bytes, 80 MB at H = 10^7) are the
+// only array a generation touches at random: they are accessed with an evict-last policy, the per-infectant streams that
+// flow past them with evict-first, so that the sums stay in L2 instead of costing a DRAM sector per access.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_stream_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // f64 reduction into global memory without a return value (RED, not ATOM: nothing waits for the old value)
 __device__ __forceinline__ void red_add_f64(double *p, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_f64_hint(double *p, double v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(__cvta_generic_to_global(p)), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double ld_f64_hint(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_u32_hint(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ld_f64_stream(const double *p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_u32_hint(uint32_t *p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(__cvta_generic_to_global(p)), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_f64_hint(double *p, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(__cvta_generic_to_global(p)), "d"(v), "l"(pol) : "memory");
 }
 // memoise a record's raw fitness under provider p together with the mapped value utility(raw): the raw value is what
 // descendants multiply (FitnessProvider::get_fitness, src/providers/fitness.rs:212-223), the mapped value is what
@@ -1073,7 +1110,7 @@ __global__ void __launch_bounds__(TPB, 3) k_mutate(DevState *st, ReplayMut rp, i
             // pass ran in this generation and has already written the new record's id into the population (ids are worklist
             // positions); 4: the items were staged by the previous generation's resample, the population is patched here.
             st->pop_fit[i] = fit_repro;
-            if (tpos != NONE32 && fit_repro != 0.0) red_add_f64(&st->hsum[st->hsum_parity][tpos], fit_repro);
+            if (tpos != NONE32 && fit_repro != 0.0) red_add_f64_hint(&st->hsum[st->hsum_parity][tpos], fit_repro, l2_keep_policy());
             if (patch_records == 4) st->hap_id[i] = new_id;
             continue;
         }
@@ -1366,14 +1403,14 @@ __global__ void __launch_bounds__(TPB) k_offspring(DevState *st, const uint64_t 
 // the general kernels redo the phase (`fail_is_error`: the caller enqueued no fallback because uniform infection
 // makes that a > 8 sigma event).
 constexpr int REPL_TPB = 512;
-constexpr int REPL_PER = RESAMPLE_TILE / REPL_TPB;
+constexpr int REPL_PER = HOST_TILE_CAP / REPL_TPB;
 template <bool SMALL_ONLY>
 __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, const uint64_t *__restrict__ replay_off, int store_lambda,
                                                                  int fail_is_error, uint32_t tiles_per_cta) {
     __shared__ uint32_t s_off[HT_MAX_HOSTS + 1];
-    __shared__ uint32_t s_head[RESAMPLE_TILE / 32 + 2];
-    __shared__ double s_f[RESAMPLE_TILE];
-    __shared__ uint2 s_rec[RESAMPLE_TILE];
+    __shared__ uint32_t s_head[HOST_TILE_CAP / 32 + 2];
+    __shared__ double s_f[HOST_TILE_CAP];
+    __shared__ uint2 s_rec[HOST_TILE_CAP];
     __shared__ uint32_t s_red[REPL_TPB / 32];
     const uint64_t H = st->H;
     const uint32_t ht = st->ht_planned;  // host_tile_size(n, H), from the state, not from the launch (k_plan_host_tiles)
@@ -1402,10 +1439,10 @@ __global__ void __launch_bounds__(REPL_TPB, 3) k_replicate_fused(DevState *st, c
         const uint32_t nh = (uint32_t)(H - h0 < ht ? H - h0 : ht);
         __syncthreads();  // shared arrays of the previous tile are free
         for (uint32_t k = tid; k <= nh; k += REPL_TPB) s_off[k] = offsets[h0 + k];
-        for (uint32_t k = tid; k < RESAMPLE_TILE / 32 + 2; k += REPL_TPB) s_head[k] = 0u;
+        for (uint32_t k = tid; k < HOST_TILE_CAP / 32 + 2; k += REPL_TPB) s_head[k] = 0u;
         __syncthreads();
         const uint32_t p0 = s_off[0], cnt = s_off[nh] - p0;
-        if (cnt > RESAMPLE_TILE) {  // uniform across the CTA
+        if (cnt > HOST_TILE_CAP) {  // uniform across the CTA
             if (tid == 0) { st->fused_failed = 1u; st->tile_sum[tile] = 0; if (fail_is_error) raise(st, DE_TILE_OVERFLOW); }
             continue;
         }

@@ -34,9 +34,10 @@ namespace vl {
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr int MAX_SPECS = 8;
 constexpr int MAX_PROVIDERS = 16;
-constexpr uint32_t RESAMPLE_TILE = 2048;  // CSR positions per resample tile (one CTA stages one tile in smem)
+constexpr uint32_t RESAMPLE_TILE = 1024;  // infectants per resample tile (one CTA stages one tile in shared memory)
+constexpr uint32_t HOST_TILE_CAP = 2048;  // records a host tile of the fused replicate kernel may hold
 constexpr int MAX_PARTS = 16;              // subsamples of one offspring map that one plan + one resample pass can draw together
-constexpr uint32_t HT_MAX_HOSTS = 2048;   // most hosts a host-range tile may span (DevState::host_tiles holds the actual number)
+constexpr uint32_t HT_MAX_HOSTS = HOST_TILE_CAP;   // most hosts a host-range tile may span (DevState::host_tiles holds the actual number)
 constexpr uint32_t HT_MIN_HOSTS = 256;    // below this the fused replicate kernel is not worth launching
 constexpr double HT_SPREAD_CTAS = 148.0;  // tiles of a small host population are shrunk until there are about two per SM of a B200
 // error bits raised by kernels (sticky until vl_* reports them)
