@@ -891,7 +891,7 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
     // (enough CTAs for the tiles, and for the draws a small sample makes one by one: two per thread)
     const uint64_t direct_draws = std::min<uint64_t>(sim->h.max_population, PLAN_FILL_MAX);
     // (several parts: more (part, tile) pairs to draw for, up to the 32 slices DevState::plan_part has room for)
-    const uint64_t max_ctas = n >= 4 ? 2 * PLAN_CTAS : PLAN_CTAS;
+    const uint64_t max_ctas = (n >= 4 || nt_bound > 6000) ? 2 * PLAN_CTAS : PLAN_CTAS;
     const unsigned ctas = (unsigned)std::min<uint64_t>(max_ctas, std::max<uint64_t>(std::max<uint64_t>(1, nt_bound * n / 256), direct_draws / (2 * PLAN_THREADS)));
     LAUNCH(sim, k_plan_resample, ctas, PLAN_THREADS, smem_tiles * 8, sim->d, pa, smem_tiles);
     if (tiles) {  // offspring counts in infectant order next to hap_id[] / pop_fit[] (vl_fused.cuh): haplotype and mapped fitness of the drawn parents
@@ -1417,7 +1417,7 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
         if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
         else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, prefilled ? 4 : 3, 1);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 3, 1);
     const unsigned og = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, og, OS_TPB, 0, sim->d);
     else LAUNCH(sim, k_offspring_sum<false>, og, OS_TPB, 0, sim->d);
@@ -1447,12 +1447,14 @@ static bool graph_wanted(const vl_sim *sim) {
     return !sim->graph_disabled && !sim->profiling && !(sim->experiment & 64) && !replay && (sim->n_bound <= GRAPH_MAX_POPULATION || (sim->experiment & 128)) &&
            sim->n_bound == std::min<uint64_t>(h.cap_inf, h.max_population);  // the bound every later generation has too
 }
-static int enqueue_generation(vl_sim *sim) {
+// more_follow: the caller enqueues another generation right after this one (vl_run): this generation's resample may then
+// draw the next generation's hosts and mutation counts.  Nothing of that prepared state outlives the call.
+static int enqueue_generation(vl_sim *sim, bool more_follow) {
     // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
     const bool tiles = fused_now(sim);
     if (!tiles) drop_prefill(sim);
     // (a compaction renumbers the records: the generation before one does not prepare the next)
-    const bool prefill_next = tiles && sim->gens_since_gc + 1 < sim->gc_period && !(sim->experiment & 32);
+    const bool prefill_next = tiles && more_follow && sim->gens_since_gc + 1 < sim->gc_period && !(sim->experiment & 32);
     if (graph_wanted(sim)) {
         const DevState &h = sim->h;
         const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets ^ (uint64_t)(uintptr_t)h.hsum[0],
@@ -1512,13 +1514,13 @@ VL_API int vl_advance_to_offspring(vl_sim *sim) {
 }
 VL_API int vl_next_generation(vl_sim *sim) {
     ENTER(sim);
-    TRY(enqueue_generation(sim));
+    TRY(enqueue_generation(sim, false));
     CU(sim, cudaGetLastError());
     return VL_OK;
 }
 VL_API int vl_run(vl_sim *sim, uint64_t n_generations) {
     ENTER(sim);
-    for (uint64_t g = 0; g < n_generations; g++) TRY(enqueue_generation(sim));
+    for (uint64_t g = 0; g < n_generations; g++) TRY(enqueue_generation(sim, g + 1 < n_generations));
     CU(sim, cudaGetLastError());
     return VL_OK;
 }

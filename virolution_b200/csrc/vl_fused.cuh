@@ -265,8 +265,8 @@ struct ResamplePosArgs {
     uint32_t *dst[MAX_PARTS];    // nullptr = the population being assembled (hap_id_next, pop_fit_next)
     double *dst_fit[MAX_PARTS];  // mapped fitness of the drawn parents (may be nullptr when dst is a detached buffer)
 };
-// PREFILL: the children written to the population (single part, dst == nullptr) get their hosts and mutation counts for
-// the NEXT generation right here (infect_draw with generation + 1): host_id[], the other hsum buffer (cleared by
+// PREFILL (only when the caller enqueues the next generation right behind this one): the children written to the
+// population (single part, dst == nullptr) get their hosts and mutation counts for the NEXT generation right here (infect_draw with generation + 1): host_id[], the other hsum buffer (cleared by
 // k_offspring_sum of this generation) and the worklist are ready when the next generation begins, which then starts with
 // k_mutate.  The children are as they would be without it; k_infect_sum makes the same draws from the same streams.
 template <bool PREFILL>
@@ -492,7 +492,9 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
                 if (PREFILL) cl_push(cl, nm != 0u, make_uint4((uint32_t)s, nm, h, hap));
             }
         }
-        if (PREFILL) cl_flush(st, cl, nullptr, 0ull);
+        // (the staged children mutate at the start of the next generation, which follows at once (vl_run): their new
+        // records' ids are known — record count + worklist position — and go into the population here)
+        if (PREFILL) cl_flush(st, cl, st->hap_id_next, st->n_hap);
     }
 }
 

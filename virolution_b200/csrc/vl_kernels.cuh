@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
 // flattened into a fresh base list (HapHead, vl_state.cuh).  Raw fitness of every provider incrementally:
 // raw(parent) * fold(acc * T[pos,to] / T[pos,from]) (src/core/fitness/table.rs:65-68) [* epistatic update].
 // patch_records: 1 = the infectant's CSR record is patched in place, 2 = its bucket-partitioned record is (host map not
-// built yet), 0 = no records exist, 3 / 4 = device-resident generation (vl_fused.cuh): items are (infectant, n_mut, host,
+// built yet), 0 = no records exist, 3 = device-resident generation (vl_fused.cuh): items are (infectant, n_mut, host,
 // parent); the carried fitness of the infectant is replaced and added to its host's sum.
 constexpr uint32_t MUT_LOCAL = HEAD_DELTA;              // events up to this many sites keep their scratch in shared memory
 constexpr uint32_t MUT_STRIDE = 3 * HEAD_DELTA + 2 * MUT_LOCAL + 1;  // per thread: parent delta (8), merged delta (16), change words (8), new entries (8); odd stride
@@ -1104,14 +1104,12 @@ __global__ void __launch_bounds__(TPB, 3) k_mutate(DevState *st, ReplayMut rp, i
             for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = k < ndm ? dm[k] : 0xFFFFFFFFu;
         }
         st->head[new_id] = nh;
-        if (patch_records >= 3) {
-            // device-resident generation (vl_fused.cuh): items carry the host in .z.  The new haplotype's mapped fitness
-            // replaces the infectant's carried value and joins its host's sum (the infect pass left it out).  3: the infect
-            // pass ran in this generation and has already written the new record's id into the population (ids are worklist
-            // positions); 4: the items were staged by the previous generation's resample, the population is patched here.
+        if (patch_records == 3) {
+            // device-resident generation (vl_fused.cuh): items carry the host in .z.  The pass that staged the items has
+            // already written the new record's id into the population (ids are worklist positions); the new haplotype's
+            // mapped fitness replaces the infectant's carried value and joins its host's sum (that pass left it out).
             st->pop_fit[i] = fit_repro;
             if (tpos != NONE32 && fit_repro != 0.0) red_add_f64_hint(&st->hsum[st->hsum_parity][tpos], fit_repro, l2_keep_policy());
-            if (patch_records == 4) st->hap_id[i] = new_id;
             continue;
         }
         st->hap_id[i] = new_id;
