@@ -283,6 +283,11 @@ int vl_timer_start(vl_sim *sim);
 int vl_timer_stop(vl_sim *sim, double *ms_out);            /* synchronises; device time since vl_timer_start */
 int vl_profile(vl_sim *sim, int enable);                   /* bracket every kernel launch with events */
 int vl_profile_report(vl_sim *sim, char *buf, uint64_t cap); /* "<kernel> <launches> <total_ms>\n" per kernel */
+int vl_debug_last_generation(vl_sim *sim, uint64_t *offspring_out, int64_t *hosts_out, double *host_sums_out, double *fitness_out,
+                             uint64_t n); /* diagnostic: what the last generation of vl_run / vl_next_generation left on the
+                                             device, in the order of the population it STARTED with (n = its size): offspring
+                                             counts, hosts, per-host fitness sums and carried mapped fitness.  Only after a
+                                             device-resident generation without a host map (no reference analogue; tests) */
 int vl_debug_stamps(vl_sim *sim, uint64_t *out8);          /* %globaltimer stamps of the last plan kernel's phases */
 
 /* ---- device sampler hooks (distribution tests of the Philox-driven samplers that stand in for

@@ -2150,6 +2150,39 @@ VL_API int vl_get_capacities(vl_sim *sim, uint64_t *out4) {
     out4[0] = sim->h.cap_inf; out4[1] = sim->h.cap_hap; out4[2] = sim->h.cap_arena; out4[3] = sim->gc_period;
     return VL_OK;
 }
+__global__ void __launch_bounds__(TPB) k_debug_last_generation(DevState *st, uint64_t n, uint64_t *off, int64_t *hosts, double *sums, double *fit) {
+    // the generation has swapped the population: what it started with sits in the *_next buffers, its sums in the other hsum
+    const double *hs = st->hsum[st->hsum_parity ^ 1u];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t h = st->host_id[i];
+        off[i] = st->offspring[i];
+        hosts[i] = h;
+        sums[i] = hs[h];
+        fit[i] = st->pop_fit_next[i];
+    }
+}
+VL_API int vl_debug_last_generation(vl_sim *sim, uint64_t *offspring_out, int64_t *hosts_out, double *host_sums_out, double *fitness_out, uint64_t n) {
+    ENTER(sim);
+    if (!offspring_out || !hosts_out || !host_sums_out || !fitness_out) return fail(sim, VL_ERR_ARGUMENT, "null argument");
+    if (!sim->h.hsum[0] || n > sim->h.cap_inf) return fail(sim, VL_ERR_IMPLEMENTATION, "no device-resident generation has run on this handle");
+    void *tmp = nullptr;
+    CU(sim, cudaMalloc(&tmp, std::max<uint64_t>(n, 1) * 32));
+    uint64_t *d_off = (uint64_t *)tmp;
+    int64_t *d_h = (int64_t *)(d_off + n);
+    double *d_s = (double *)(d_h + n), *d_f = d_s + n;
+    LAUNCH(sim, k_debug_last_generation, grid_for(sim, n), TPB, 0, sim->d, n, d_off, d_h, d_s, d_f);
+    cudaError_t e = cudaSuccess;
+    if (n) {
+        e = cudaMemcpyAsync(offspring_out, d_off, n * 8, cudaMemcpyDeviceToHost, sim->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hosts_out, d_h, n * 8, cudaMemcpyDeviceToHost, sim->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host_sums_out, d_s, n * 8, cudaMemcpyDeviceToHost, sim->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(fitness_out, d_f, n * 8, cudaMemcpyDeviceToHost, sim->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sim->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(sim, VL_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
+    return VL_OK;
+}
 VL_API int vl_debug_stamps(vl_sim *sim, uint64_t *out8) {
     ENTER(sim);
     CU(sim, cudaMemcpyAsync(sim->pin + 16, (const char *)sim->d + FIELD_OFF(dbg), 64, cudaMemcpyDeviceToHost, sim->stream));

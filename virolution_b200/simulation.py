@@ -85,6 +85,7 @@ SIGNATURES = {
     "vl_profile": (C.c_int, [_vp, C.c_int]),
     "vl_profile_report": (C.c_int, [_vp, C.c_char_p, C.c_uint64]),
     "vl_debug_stamps": (C.c_int, [_vp, u64p]),
+    "vl_debug_last_generation": (C.c_int, [_vp, u64p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint64]),
     "vl_test_poisson": (C.c_int, [C.c_uint64, C.c_double, C.c_uint64, u64p]),
     "vl_test_poisson_fast": (C.c_int, [C.c_uint64, C.c_double, C.c_uint64, u64p]),
     "vl_test_binomial": (C.c_int, [C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, u64p]),
@@ -451,6 +452,17 @@ class GpuSimulation:
         out = np.zeros(self.population_len(), dtype=np.uint32)
         self._check(self.lib.vl_get_haplotype_ids(self.ptr, _p(out, C.c_uint32), out.size))
         return out
+
+    def debug_last_generation(self, n: int):
+        """(offspring, hosts, host_sums, fitness) of the last device-resident generation, in the order of the population
+        it started with (diagnostic; tests)."""
+        off = np.zeros(n, dtype=np.uint64)
+        hosts = np.zeros(n, dtype=np.int64)
+        sums = np.zeros(n, dtype=np.float64)
+        fit = np.zeros(n, dtype=np.float64)
+        self._check(self.lib.vl_debug_last_generation(self.ptr, _p(off, C.c_uint64), _p(hosts, C.c_int64), _p(sums, C.c_double),
+                                                      _p(fit, C.c_double), n))
+        return off, hosts, sums, fit
 
     def get_counters(self) -> dict:
         out = np.zeros(4, dtype=np.uint64)
