@@ -82,6 +82,7 @@ def lib():
             "orc_test_binomial": (None, [C.c_uint64, C.c_uint64, C.c_double, C.c_uint64, u64p]),
             "orc_test_alias": (C.c_int, [C.c_uint64, u64p, C.c_uint64, C.c_uint64, u64p]),
             "orc_num_threads": (C.c_int, [vp]),
+            "orc_set_mode": (None, [vp, C.c_int]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -323,6 +324,11 @@ class OracleWorld:
 
     def num_threads(self):
         return int(lib().orc_num_threads(self.ptr))
+
+    def set_mode(self, no_logs=False, fully_parallel=False):
+        """Timing runs: no draw logs (the reference keeps none); fully_parallel: infect, replicate and the sample draws
+        run over all threads too (the reference's rayon build runs them serially)."""
+        lib().orc_set_mode(self.ptr, (1 if no_logs else 0) | (2 if fully_parallel else 0))
 
 
 def test_poisson(seed, lam, n):

@@ -248,6 +248,8 @@ typedef struct orc_world {
     double *raw[MAX_PROVIDERS][MAX_CHUNKS]; uint8_t *has[MAX_PROVIDERS][MAX_CHUNKS];
     Sim *sims; uint32_t n_sims;
     int n_threads;
+    int mode; /* bit 0: no draw logs (timing runs: the reference keeps none); bit 1: "fully parallel CPU" variant — infect,
+                 replicate and the sample draws run over all threads too (the reference's rayon build runs them serially) */
     Rng *trng; /* per-thread generators (rayon for_each_init(rand::rng)) */
     uint64_t **last_idx; uint64_t *last_idx_n; /* [t*C+o] sample indices of last step */
     char err[256];
@@ -257,16 +259,20 @@ static inline Node *node_at(orc_world *w, int64_t id) { return &w->chunks[id >> 
 static inline const Change *node_changes(const Node *n) { return n->n_ch > 1 ? n->chs : &n->ch1; }
 
 static int64_t node_alloc(orc_world *w) {
-    int64_t id;
+    /* ids come from an atomic counter (the reference allocates nodes with the global allocator, no shared lock); the
+     * tables grow a chunk at a time under a lock that is taken once per 2^CHUNK_BITS nodes */
+    int64_t id = (int64_t)__atomic_fetch_add(&w->n_nodes, 1, __ATOMIC_RELAXED);
+    uint64_t c = (uint64_t)id >> CHUNK_BITS;
+    if (!__atomic_load_n(&w->chunks[c], __ATOMIC_ACQUIRE)) {
 #pragma omp critical(orc_node_alloc)
-    {
-        id = (int64_t)w->n_nodes++;
-        uint64_t c = (uint64_t)id >> CHUNK_BITS;
-        if (!w->chunks[c]) {
-            w->chunks[c] = (Node *)calloc(CHUNK, sizeof(Node));
-            for (int p = 0; p < w->n_prov; p++) {
-                w->raw[p][c] = (double *)calloc(CHUNK, sizeof(double));
-                w->has[p][c] = (uint8_t *)calloc(CHUNK, 1);
+        {
+            if (!w->chunks[c]) {
+                for (int p = 0; p < w->n_prov; p++) {
+                    w->raw[p][c] = (double *)calloc(CHUNK, sizeof(double));
+                    w->has[p][c] = (uint8_t *)calloc(CHUNK, 1);
+                }
+                Node *nc = (Node *)calloc(CHUNK, sizeof(Node));
+                __atomic_store_n(&w->chunks[c], nc, __ATOMIC_RELEASE);
             }
         }
     }
@@ -618,14 +624,17 @@ ORC_EXPORT int orc_infect(orc_world *w, uint32_t c) {
     uint64_t H = s->par.host_population_size;
     sim_reserve(s, s->n, H);
     s->infectant_generations += s->n;
+    const int par_all = (w->mode & 2) && w->n_threads > 1 && !omp_in_parallel();
+#pragma omp parallel for schedule(static) num_threads(w->n_threads) if (par_all)
     for (uint64_t i = 0; i < s->n; i++) {
+        Rng *rng = par_all ? &w->trng[omp_get_thread_num()] : &s->rng;
         int64_t inf = -1;
         for (uint64_t hit = 0; hit < s->par.n_hits; hit++) {
-            uint64_t cand = rng_below(&s->rng, H);
+            uint64_t cand = rng_below(rng, H);
             const Spec *sp = spec_of_host(w, cand, NULL);
             if (!sp) continue;
             double infectivity = sp->infect >= 0 ? mapped_fitness(w, sp->infect, s->pop[i]) : 1.;
-            if (rng_f64(&s->rng) < infectivity) { inf = (int64_t)cand; break; }
+            if (rng_f64(rng) < infectivity) { inf = (int64_t)cand; break; }
         }
         s->infections[i] = inf;
     }
@@ -663,6 +672,7 @@ static void host_mutate(orc_world *w, Sim *s, uint32_t spec_idx, uint64_t host, 
             int64_t rec = hap_create_recombinant(w, g[i], g[j], s0, s1);
             uint8_t which = (uint8_t)rng_below(rng, 2); /* [i, j].choose(rng) */
             g[which ? j : i] = rec;
+            if (!(w->mode & 1))
 #pragma omp critical(orc_log)
             {
                 if (s->n_rlog == s->cap_rlog) { s->cap_rlog = s->cap_rlog * 2 + 64; s->rlog = (RecLog *)realloc(s->rlog, s->cap_rlog * sizeof(RecLog)); }
@@ -684,6 +694,7 @@ static void host_mutate(orc_world *w, Sim *s, uint32_t spec_idx, uint64_t host, 
             bases[m] = (uint8_t)rng_weighted4(rng, &hp->substitution_matrix[cur * 4]);
         }
         g[a] = hap_create_descendant(w, g[a], sites, bases, (uint32_t)nm, NULL);
+        if (!(w->mode & 1))
 #pragma omp critical(orc_log)
         { for (uint64_t m = 0; m < nm; m++) push_mlog(s, (uint32_t)ids[a], sites[m], bases[m]); }
         if (nm > 16) { free(sites); free(bases); }
@@ -737,7 +748,10 @@ ORC_EXPORT int orc_replicate(orc_world *w, uint32_t c, uint64_t *offspring_out) 
     for (uint32_t si = 0; si < w->n_specs; si++) {
         const Spec *sp = &w->specs[si];
         uint64_t hi = sp->hi < s->par.host_population_size ? sp->hi : s->par.host_population_size;
+        const int par_all = (w->mode & 2) && w->n_threads > 1 && !omp_in_parallel();
+#pragma omp parallel for schedule(static) num_threads(w->n_threads) if (par_all)
         for (uint64_t h = sp->lo; h < hi; h++) {
+            Rng *prng = par_all ? &w->trng[omp_get_thread_num()] : &s->rng;
             uint64_t b = s->offsets[h], e = s->offsets[h + 1];
             if (e == b) continue;
             double sum = 0.0;
@@ -751,7 +765,7 @@ ORC_EXPORT int orc_replicate(orc_world *w, uint32_t c, uint64_t *offspring_out) 
                 uint64_t i = s->hosts[a];
                 double lam = s->fit[i] * R0 / sum;
                 s->hsum[i] = sum; s->lam[i] = lam;
-                int ok; double x = rng_poisson(&s->rng, lam, &ok);
+                int ok; double x = rng_poisson(prng, lam, &ok);
                 if (ok) s->offspring[i] = (uint64_t)x;
                 else { uint64_t bits; memcpy(&bits, &s->fit[i], 8); s->offspring[i] = bits; } /* float view left in place */
             }
@@ -778,7 +792,9 @@ ORC_EXPORT int orc_sample_indices(orc_world *w, uint32_t c, const uint64_t *off,
     if (n == 0) return 0;
     Alias a;
     if (alias_build(&a, off, n) != 0) { snprintf(w->err, sizeof w->err, "WeightedAliasIndex::new: all weights zero"); return -1; }
-    for (uint64_t k = 0; k < amount; k++) out[k] = alias_sample(&a, &s->rng);
+    const int par_all = (w->mode & 2) && w->n_threads > 1 && !omp_in_parallel();
+#pragma omp parallel for schedule(static) num_threads(w->n_threads) if (par_all)
+    for (uint64_t k = 0; k < amount; k++) out[k] = alias_sample(&a, par_all ? &w->trng[omp_get_thread_num()] : &s->rng);
     alias_free(&a);
     return 0;
 }
@@ -1022,3 +1038,4 @@ ORC_EXPORT int orc_test_alias(uint64_t seed, const uint64_t *wts, uint64_t nw, u
     alias_free(&a); return 0;
 }
 ORC_EXPORT int orc_num_threads(orc_world *w) { return w->n_threads; }
+ORC_EXPORT void orc_set_mode(orc_world *w, int mode) { w->mode = mode; }

@@ -543,6 +543,12 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
     h.gc_arena_threshold = cap_arena / 2;
+    {   // compaction is cheap (bit map + ranks, cost ~ population + live records) and a compact table keeps the random
+        // reads of k_mutate closer together: run it every few generations' worth of new records, not when memory runs out
+        const char *e = getenv("VL_GC_RECORDS");
+        const uint64_t target = e ? (uint64_t)atof(e) : 2 * cap_inf;
+        if (!cfg->capacity_haplotypes && target > 0) h.gc_hap_threshold = std::min<uint64_t>(h.gc_hap_threshold, std::max<uint64_t>(target, 1u << 16));
+    }
     CTRY(dev_alloc(sim, &h.bucket_fill, MAX_BUCKETS + 1));
     CTRY(dev_alloc(sim, &h.bucket_pos, MAX_BUCKETS + 2));
     CCU(cudaFuncSetAttribute((k_bucket_sort<1024, BSORT_STAGE_RECS>), cudaFuncAttributeMaxDynamicSharedMemorySize, BSORT_SMEM_BYTES));
@@ -574,7 +580,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     {
         double p_mut = 1.0 - pow(1.0 - par.mutation_rate, (double)L);
         double per_gen = (double)cap_inf * std::min(1.0, 3.0 * p_mut + 0.01 + (par.recombination_rate > 0 ? 0.05 : 0.0));
-        double room = (double)(cap_hap - h.gc_hap_threshold);
+        double room = (double)std::min<uint64_t>(cap_hap - h.gc_hap_threshold, h.gc_hap_threshold);
         double period = floor(room / std::max(per_gen, 1.0));
         sim->gc_period = (uint32_t)std::min(64.0, std::max(1.0, period));
     }
@@ -916,7 +922,6 @@ static int enqueue_resample(vl_sim *sim, double factor, int use_amount, uint64_t
 }
 static int enqueue_gc(vl_sim *sim, int force) {
     const DevState &h = sim->h;
-    drop_prefill(sim);  // (record ids change)
     const uint32_t *active = (const uint32_t *)((const char *)sim->d + FIELD_OFF(gc_active));
     const uint64_t *nw_ptr = (const uint64_t *)((const char *)sim->d + FIELD_OFF(gc_nw));
     const uint64_t gw = h.cap_hap / 32 + 8;
@@ -924,12 +929,14 @@ static int enqueue_gc(vl_sim *sim, int force) {
     LAUNCH(sim, k_gc_clear, grid_for(sim, gw), TPB, 0, sim->d, 1, 1);
     LAUNCH(sim, k_gc_mark, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (const uint32_t *)nullptr, (uint64_t)0, 1, 1, 0);
     for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_mark, grid_for(sim, p->cap), TPB, 0, sim->d, (const uint32_t *)p->ids, p->n, 0, 1, 0);
+    if (sim->prefilled) LAUNCH(sim, k_gc_mark_pending, grid_for(sim, sim->n_bound), TPB, 0, sim->d);
     LAUNCH(sim, k_gc_words, grid_for(sim, gw), TPB, 0, sim->d, 1);
     TRY((launch_scan<uint32_t, true>(sim, h.gc_wcnt, h.gc_cbase, nw_ptr, 0, gw, sim->gc_totals + 0, 0, active)));
     TRY((launch_scan<uint64_t, true>(sim, h.gc_wlen, h.gc_lbase, nw_ptr, 0, gw, sim->gc_totals + 1, 0, active)));
     LAUNCH(sim, k_gc_copy, grid_for(sim, gw), TPB, 0, sim->d);
-    LAUNCH(sim, k_gc_remap, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (uint32_t *)nullptr, (uint64_t)0, 1);
-    for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_remap, grid_for(sim, p->cap), TPB, 0, sim->d, p->ids, p->n, 0);
+    LAUNCH(sim, k_gc_remap, grid_for(sim, sim->n_bound), TPB, 0, sim->d, (uint32_t *)nullptr, (uint64_t)0, 1, (const uint64_t *)sim->gc_totals);
+    for (vl_pop *p : sim->pops) LAUNCH(sim, k_gc_remap, grid_for(sim, p->cap), TPB, 0, sim->d, p->ids, p->n, 0, (const uint64_t *)sim->gc_totals);
+    if (sim->prefilled) LAUNCH(sim, k_gc_remap_pending, grid_for(sim, sim->n_bound), TPB, 0, sim->d);
     LAUNCH(sim, k_gc_end, 1, 1, 0, sim->d, sim->gc_totals);
     sim->gens_since_gc = 0;
     return VL_OK;
@@ -1453,8 +1460,7 @@ static int enqueue_generation(vl_sim *sim, bool more_follow) {
     // Simulation::next_generation (src/simulation.rs:200-218).  An empty population makes every kernel a no-op.
     const bool tiles = fused_now(sim);
     if (!tiles) drop_prefill(sim);
-    // (a compaction renumbers the records: the generation before one does not prepare the next)
-    const bool prefill_next = tiles && more_follow && sim->gens_since_gc + 1 < sim->gc_period && !(sim->experiment & 32);
+    const bool prefill_next = tiles && more_follow && !(sim->experiment & 32);
     if (graph_wanted(sim)) {
         const DevState &h = sim->h;
         const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets ^ (uint64_t)(uintptr_t)h.hsum[0],

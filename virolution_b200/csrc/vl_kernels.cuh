@@ -953,6 +953,10 @@ __global__ void __launch_bounds__(TPB, 3) k_mutate(DevState *st, ReplayMut rp, i
         const uint32_t nd = head_nd(ph), plen = ph.len, mlen = head_mlen(ph);
         const bool flat = ok && nd + nm > HEAD_DELTA;  // the delta would overflow: this record gets a base list of its own
         const bool big = nm > MUT_LOCAL;               // (implies flat)
+        if (flat) {  // the whole base list is about to be copied: pull it towards L2 while the sites are drawn
+            const uint32_t *pl = st->arena + ph.off;
+            for (uint32_t k = 0; k < plen; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + k));
+        }
         const uint32_t words = flat ? mlen + (big ? 4u * nm + HEAD_DELTA : nm) : 0u;
         uint32_t inc = words;
 #pragma unroll
@@ -2206,8 +2210,25 @@ __global__ void __launch_bounds__(TPB) k_gc_mark(DevState *st, const uint32_t *_
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t id = ids[i];
         if (skip_wildtype && id == 0) continue;
+        if (id >= st->n_hap) continue;  // (the id of a pending record: nothing to keep yet)
         atomicOr(&st->gc_bits[id >> 5], 1u << (id & 31));
     }
+}
+// The worklist of a generation the last resample prepared (k_resample_pos<true>) refers to records too: the parents of
+// the pending mutants stay live, and the population already holds the ids the pending records WILL get (record count +
+// worklist position), which move down with the record count.
+__global__ void __launch_bounds__(TPB) k_gc_mark_pending(DevState *st) {
+    if (!st->gc_active) return;
+    const uint32_t m = st->n_mut_list;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const uint32_t id = st->mut_list[i].w;
+        atomicOr(&st->gc_bits[id >> 5], 1u << (id & 31));
+    }
+}
+__global__ void __launch_bounds__(TPB) k_gc_remap_pending(DevState *st) {
+    if (!st->gc_active) return;
+    const uint32_t m = st->n_mut_list;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) st->mut_list[i].w = gc_new_id(st, st->mut_list[i].w);
 }
 __global__ void __launch_bounds__(TPB) k_gc_words(DevState *st, int guarded) {
     if (guarded && !st->gc_active) return;
@@ -2254,10 +2275,15 @@ __global__ void __launch_bounds__(TPB) k_gc_copy(DevState *st) {
         }
     }
 }
-__global__ void __launch_bounds__(TPB) k_gc_remap(DevState *st, uint32_t *ids, uint64_t m, int use_population) {
+__global__ void __launch_bounds__(TPB) k_gc_remap(DevState *st, uint32_t *ids, uint64_t m, int use_population, const uint64_t *gc_totals) {
     if (!st->gc_active) return;
     if (use_population) { ids = st->hap_id; m = st->n; }
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) ids[i] = gc_new_id(st, ids[i]);
+    const uint64_t n_old = st->n_hap, n_live = gc_totals[0];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = ids[i];
+        // (an id at or beyond the record count is the id a pending record will get: see k_gc_mark_pending)
+        ids[i] = id < n_old ? gc_new_id(st, id) : (uint32_t)(n_live + (id - n_old));
+    }
 }
 // gc_totals[0] = live records, gc_totals[1] = live arena words (written by the two scans)
 __global__ void k_gc_end(DevState *st, const uint64_t *gc_totals) {
