@@ -1,7 +1,7 @@
 #!/bin/bash
 # short bench line + kernel table: profiles/benchshort.sh <tag> [extra bench args]
 tag=$1; shift
-python bench.py --steps 20 --warmup 20 --no-cpu-baseline --no-e2e "$@" > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+python bench.py --steps 20 --warmup 20 --no-cpu-baseline --no-e2e --no-extra "$@" > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_$tag.json"))
