@@ -1438,6 +1438,28 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
     sim->bucket_pending = false;
     return VL_OK;
 }
+// increment_generation + infect + mutate_infectants + replicate_infectants on the kernels of vl_fused.cuh, offspring map
+// left on the device in infectant order (what vl_exchange_begin enqueues when the compartment qualifies)
+static int enqueue_generation_front_fused(vl_sim *sim) {
+    const DevState &h = sim->h;
+    drop_prefill(sim);
+    sim->salt = 0;
+    LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d, 0);
+    if (sim->hsum_dirty) LAUNCH(sim, k_zero_hsum_current, grid_for(sim, h.H), TPB, 0, sim->d);
+    sim->hsum_dirty = false;
+    const unsigned ig = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
+    if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
+    else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 3, 1);
+    if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, ig, OS_TPB, 0, sim->d);
+    else LAUNCH(sim, k_offspring_sum<false>, ig, OS_TPB, 0, sim->d);
+    sim->uniform_infection = true;
+    sim->mutcounts_ready = false;
+    sim->bucket_pending = false;
+    sim->csr_valid = false;
+    sim->layout_valid = false;
+    return VL_OK;
+}
 // the kernels of one whole generation (everything but the occasional compaction)
 static int enqueue_generation_kernels(vl_sim *sim, bool tiles, bool prefill_next) {
     if (tiles) return enqueue_generation_fused(sim, prefill_next);
@@ -1550,6 +1572,8 @@ struct vl_exchange {
     ExArgs args;
     ExScratch *scratch = nullptr;
     uint32_t *part_ids[EX_MAX_WORLD] = {nullptr};
+    double *own_fit = nullptr;   // mapped fitness of my own part (device-resident generation)
+    bool fused_step = false;     // the generation in flight runs on the kernels of vl_fused.cuh
     uint32_t *words_out = nullptr, *words_in = nullptr, *recs_in = nullptr, *rec_off = nullptr;
     uint64_t *woff = nullptr, *word_off = nullptr;
     uint32_t *stage = nullptr;  // leaving entries in concatenation order, before they are streamed to the targets
@@ -1614,7 +1638,7 @@ static void ex_free(vl_exchange *ex) {
         if (ex->peer[t] && ex->peer_ipc[t]) cudaIpcCloseMemHandle(ex->peer[t]);
         if (ex->part_ids[t]) cudaFree(ex->part_ids[t]);
     }
-    void *bufs[] = {ex->recv, ex->scratch, ex->words_out, ex->words_in, ex->recs_in, ex->rec_off, ex->woff, ex->word_off, ex->stage};
+    void *bufs[] = {ex->recv, ex->scratch, ex->words_out, ex->words_in, ex->recs_in, ex->rec_off, ex->woff, ex->word_off, ex->stage, ex->own_fit};
     for (void *b : bufs) if (b) cudaFree(b);
     delete ex;
 }
@@ -1659,6 +1683,7 @@ VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const 
         if (!(m >= 2.0)) m = 2.0;
         XCU(cudaMalloc((void **)&ex->part_ids[t], (uint64_t)m * 4));
         ex->args.part[t] = ex->part_ids[t];
+        if (t == rank) XCU(cudaMalloc((void **)&ex->own_fit, (uint64_t)m * 8));
         if (t != rank) ex->m_out_bound += (uint64_t)m;
     }
     XCU(cudaMalloc((void **)&ex->words_out, (ex->m_out_bound + 2) * 4));
@@ -1719,7 +1744,9 @@ VL_API int vl_exchange_begin(vl_exchange *ex) {
     ENTER(sim);
     if (!ex->connected) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_connect has not run");
     if (ex->begun || ex->pushed) return fail(sim, VL_ERR_IMPLEMENTATION, "the previous generation of this exchange is not finished");
-    TRY(enqueue_generation_front(sim));
+    ex->fused_step = fused_now(sim);
+    if (ex->fused_step) TRY(enqueue_generation_front_fused(sim));
+    else TRY(enqueue_generation_front(sim));
     ex->seq += 1;
     if (ex->sharded) {
         ExArgs a = ex->args;
@@ -1747,13 +1774,16 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
     double factors[EX_MAX_WORLD];
     uint32_t *dsts[EX_MAX_WORLD];
     for (uint32_t t = 0; t < W; t++) { factors[t] = ex->T[(size_t)t * W + r]; dsts[t] = ex->part_ids[t]; }
+    double *fits[EX_MAX_WORLD];
+    for (uint32_t t = 0; t < W; t++) fits[t] = t == r ? ex->own_fit : nullptr;  // (migrants get theirs from the record they become)
+    a.own_fit = ex->fused_step ? ex->own_fit : nullptr;
     if (ex->sharded) {
         // every rank's offspring total has been published (vl_exchange_begin): wait for them, split the N' draws over
         // the (target, origin) cells, draw my row of parts with the amounts the split left in DevState::plan_amount
         LAUNCH(sim, k_shard_split, 1, 32, 0, sim->d, a, 20ull * 1000000000ull);
-        TRY(launch_plan_resample(sim, W, nullptr, 2, nullptr, 0, dsts, nullptr, 0));
+        TRY(launch_plan_resample(sim, W, nullptr, 2, nullptr, 0, dsts, nullptr, 0, ex->fused_step, fits));
     } else {
-        TRY(launch_plan_resample(sim, W, factors, 0, nullptr, 0, dsts, nullptr, 0));
+        TRY(launch_plan_resample(sim, W, factors, 0, nullptr, 0, dsts, nullptr, 0, ex->fused_step, fits));
     }
     ExScratch *sc = ex->scratch;
     const uint64_t *n_out = (const uint64_t *)((const char *)sc + offsetof(ExScratch, n_out));
@@ -1790,8 +1820,16 @@ VL_API int vl_exchange_pull(vl_exchange *ex) {
     TRY((launch_scan<uint64_t, true>(sim, ex->words_in, ex->word_off, n_imp, 0, ex->m_in_bound, totals + 1, 1, nullptr)));
     LAUNCH(sim, k_ex_reserve, 1, 1, 0, sim->d, sc);
     LAUNCH(sim, k_ex_import, grid_for(sim, ex->m_in_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, (const uint32_t *)ex->rec_off, (const uint64_t *)ex->word_off);
+    a.own_fit = ex->fused_step ? ex->own_fit : nullptr;
     LAUNCH(sim, k_ex_own, grid_for(sim, sim->h.max_population), TPB, 0, sim->d, a, (const ExScratch *)sc);
-    swap_population(sim);
+    if (ex->fused_step) {  // both per-infectant arrays swap, the per-host sums change sides (k_offspring_sum cleared the other buffer)
+        LAUNCH(sim, k_swap_population_fused, 1, 1, 0, sim->d);
+        std::swap(sim->h.hap_id, sim->h.hap_id_next);
+        std::swap(sim->h.pop_fit, sim->h.pop_fit_next);
+    } else {
+        swap_population(sim);
+    }
+    sim->pop_fit_valid = ex->fused_step;  // k_ex_import and k_ex_own filled the carried fitness of the new population
     sim->n_valid = false;
     {   // upper bound of the new population: every origin sends at most its block capacity, the own part its cap
         uint64_t bound = 0;

@@ -43,6 +43,7 @@ struct ExArgs {
     ExBlock out[EX_MAX_WORLD];        // my block on every target (peer memory), [rank] unused
     ExBlock in[EX_MAX_WORLD];         // the block of every origin in my own buffer, [rank] unused
     const uint32_t *part[EX_MAX_WORLD];  // ids of the part drawn for every target (my memory)
+    const double *own_fit;               // mapped fitness of the infectants of my own part (device-resident generation), or nullptr
 };
 // device scratch of one exchange (my memory)
 struct ExScratch {
@@ -212,14 +213,23 @@ __global__ void __launch_bounds__(TPB) k_ex_import(DevState *st, ExArgs ex, cons
             for (uint32_t q = 0; q < l; q++) dst[q] = __ldcg(src + q);
             write_flat_head(st, id, off, l);
         }
-        if (slot < cap) st->hap_id_next[slot] = id;
+        if (slot < cap) {
+            st->hap_id_next[slot] = id;
+            // the mapped reproductive fitness travels with the infectant from here on (vl_fused.cuh)
+            const int pi0 = st->specs[0].repro;
+            st->pop_fit_next[slot] = pi0 >= 0 ? st->h_fit[pi0][id] : 1.0;
+        }
     }
 }
 __global__ void __launch_bounds__(TPB) k_ex_own(DevState *st, ExArgs ex, const ExScratch *sc) {
     const uint64_t m = st->plan_size[ex.rank], s0 = sc->in_start[ex.rank], cap = st->cap_inf;
     const uint32_t *__restrict__ src = ex.part[ex.rank];
+    const int pi0 = st->specs[0].repro;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < m; k += (uint64_t)gridDim.x * blockDim.x)
-        if (s0 + k < cap) st->hap_id_next[s0 + k] = src[k];
+        if (s0 + k < cap) {
+            st->hap_id_next[s0 + k] = src[k];
+            st->pop_fit_next[s0 + k] = ex.own_fit ? ex.own_fit[k] : (pi0 >= 0 ? st->h_fit[pi0][src[k]] : 1.0);
+        }
 }
 
 // ---- one compartment sharded over the ranks ----------------------------------------------------
