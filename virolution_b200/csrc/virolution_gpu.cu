@@ -560,7 +560,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
         CTRY(dev_alloc(sim, &h.h_raw[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_raw_alt[p], cap_hap));
         CTRY(dev_alloc(sim, &h.h_fit[p], cap_hap)); CTRY(dev_alloc(sim, &h.h_fit_alt[p], cap_hap));
     }
-    CTRY(dev_alloc(sim, &h.arena, cap_arena + 16)); CTRY(dev_alloc(sim, &h.arena_alt, cap_arena + 16));  // (padded: the search window of entries_lower_interp may overhang a list)
+    CTRY(dev_alloc(sim, &h.arena, cap_arena + 32)); CTRY(dev_alloc(sim, &h.arena_alt, cap_arena + 32));  // (padded: the search window of entries_lower_interp may overhang a list)
     {
         const uint64_t gw = cap_hap / 32 + 8;  // one bit-map word per 32 records
         CTRY(dev_alloc(sim, &h.gc_bits, gw)); CTRY(dev_alloc(sim, &h.gc_wcnt, gw)); CTRY(dev_alloc(sim, &h.gc_wlen, gw));

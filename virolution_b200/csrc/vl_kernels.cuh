@@ -889,19 +889,29 @@ __device__ __forceinline__ uint32_t warp_flatten(const uint32_t *pe, uint32_t pl
     const uint32_t hitmask = __ballot_sync(0xFFFFFFFFu, hit), keepmask = __ballot_sync(0xFFFFFFFFu, keep);
     const uint32_t below = (1u << lane) - 1u;
     if (keep) out[bj - __popc(hitmask & below) + __popc(keepmask & below)] = e;
-    // every base entry finds the delta entries before it (bisection over <= 32 positions in shared memory)
-    for (uint32_t a0 = 0; a0 < plen; a0 += 32) {
-        const uint32_t a = a0 + lane;
-        if (a >= plen) continue;
-        const uint32_t be = pe[a], q = entry_pos(be);
-        uint32_t lo = 0, hi = ndm;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (entry_pos(dmv[mid]) < q) lo = mid + 1; else hi = mid;
+    // every base entry finds the delta entries before it (bisection over <= 32 positions in shared memory); four chunks of
+    // 32 entries are in flight at a time
+    for (uint32_t a0 = 0; a0 < plen; a0 += 128) {
+        uint32_t be[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t a = a0 + u * 32 + lane;
+            be[u] = a < plen ? pe[a] : 0u;
         }
-        if (lo < ndm && entry_pos(dmv[lo]) == q) continue;  // overridden (or removed) by the delta
-        const uint32_t m = (1u << lo) - 1u;
-        out[a - __popc(hitmask & m) + __popc(keepmask & m)] = be;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t a = a0 + u * 32 + lane;
+            if (a >= plen) continue;
+            const uint32_t q = entry_pos(be[u]);
+            uint32_t lo = 0, hi = ndm;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (entry_pos(dmv[mid]) < q) lo = mid + 1; else hi = mid;
+            }
+            if (lo < ndm && entry_pos(dmv[lo]) == q) continue;  // overridden (or removed) by the delta
+            const uint32_t m = (1u << lo) - 1u;
+            out[a - __popc(hitmask & m) + __popc(keepmask & m)] = be[u];
+        }
     }
     return plen - __popc(hitmask) + __popc(keepmask);
 }
@@ -2192,8 +2202,13 @@ __device__ __forceinline__ uint32_t gc_new_id(const DevState *st, uint32_t id) {
     const uint32_t w = id >> 5;
     return st->gc_cbase[w] + __popc(st->gc_bits[w] & ((1u << (id & 31)) - 1u));
 }
+// gc_active: 0 = nothing to do, 2 = compaction: every live record is flattened into the other arena under its new id.
+// Flattening the SURVIVORS every few generations is what keeps k_mutate cheap: a lineage mutates ~0.2 times per
+// generation at K2, so between two compactions its delta rarely overflows and almost no record is flattened by the
+// mutate kernel itself (which would copy a list per mutation of lineages that mostly die out).  (Compacting the heads
+// only and leaving the lists in place was measured and dropped: 1.63 against 1.30 ms per generation at generation 1000.)
 __global__ void k_gc_begin(DevState *st, int force) {
-    st->gc_active = (force || st->n_hap > st->gc_hap_threshold || st->arena_top > st->gc_arena_threshold) ? 1u : 0u;
+    st->gc_active = (force || st->n_hap > st->gc_hap_threshold || st->arena_top > st->gc_arena_threshold) ? 2u : 0u;
 }
 // keep_wildtype: record 0 exists on every handle and keeps its id (compaction); the dedup of a detached population
 // (vl_pop_pack_device) never ships it
@@ -2244,34 +2259,88 @@ __global__ void __launch_bounds__(TPB) k_gc_words(DevState *st, int guarded) {
         st->gc_wlen[w] = len;
     }
 }
+// One CTA per TPB bit-map words: every thread lists the live records of its word (old id, new id, new arena offset) in
+// shared memory, then the CTA copies the listed records one per thread — the loads of different records overlap instead
+// of being chained inside one thread's walk over its word.
+constexpr uint32_t GC_LONG = 24;   // records longer than this are copied by a whole warp
+constexpr uint32_t GC_LIST = 2048;  // live records a CTA pass can list (TPB words hold up to 32 * TPB; longer lists are copied by the lister)
 __global__ void __launch_bounds__(TPB) k_gc_copy(DevState *st) {
+    __shared__ uint32_t s_old[GC_LIST], s_new[GC_LIST];
+    __shared__ unsigned long long s_off[GC_LIST];
+    __shared__ uint32_t s_delta[TPB / 32][HEAD_DELTA];
+    __shared__ uint32_t s_cnt;
     if (!st->gc_active) return;
     const uint64_t nw = (st->n_hap + 31) >> 5;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nw; w += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t bits = st->gc_bits[w];
-        if (!bits) continue;
-        uint32_t nid = st->gc_cbase[w];
-        uint64_t noff = st->gc_lbase[w];
-        while (bits) {
-            const uint32_t b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint64_t h = (w << 5) + b;
-            const HapHead hd = st->head[h];
-            uint32_t *dst = st->arena_alt + noff;
-            uint32_t o = 0;
-            merged_for_each(st->arena + hd.off, hd.len, hd.d, head_nd(hd), [&](uint32_t e) { dst[o++] = e; });
-            HapHead nh;
-            nh.off = noff;
-            nh.len = o;
-            nh.nd_mlen = o << 8;
-            nh.raw0 = hd.raw0;
-            nh.fit0 = hd.fit0;
+    auto copy_one = [&](uint64_t h, uint32_t nid, uint64_t noff) {
+        const HapHead hd = st->head[h];
+        uint32_t *dst = st->arena_alt + noff;
+        uint32_t o = 0;
+        merged_for_each(st->arena + hd.off, hd.len, hd.d, head_nd(hd), [&](uint32_t e) { dst[o++] = e; });
+        HapHead nh;
+        nh.off = noff;
+        nh.len = o;
+        nh.nd_mlen = o << 8;
+        nh.raw0 = hd.raw0;
+        nh.fit0 = hd.fit0;
 #pragma unroll
-            for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = 0xFFFFFFFFu;
-            st->head_alt[nid] = nh;
-            for (uint32_t p = 0; p < st->n_providers; p++) { hap_raw_alt(st, p, nid) = hap_raw(st, p, h); st->h_fit_alt[p][nid] = st->h_fit[p][h]; }
-            nid += 1;
-            noff += o;
+        for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = 0xFFFFFFFFu;
+        st->head_alt[nid] = nh;
+        for (uint32_t p = 0; p < st->n_providers; p++) { hap_raw_alt(st, p, nid) = hap_raw(st, p, h); st->h_fit_alt[p][nid] = st->h_fit[p][h]; }
+    };
+    for (uint64_t w0 = (uint64_t)blockIdx.x * TPB; w0 < nw; w0 += (uint64_t)gridDim.x * TPB) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt = 0u;
+        __syncthreads();
+        const uint64_t w = w0 + threadIdx.x;
+        uint32_t bits = w < nw ? st->gc_bits[w] : 0u;
+        if (bits) {
+            const uint32_t c = __popc(bits);
+            const uint32_t slot = atomicAdd(&s_cnt, c);
+            uint32_t nid = st->gc_cbase[w];
+            uint64_t noff = st->gc_lbase[w];
+            uint32_t k = 0;
+            while (bits) {
+                const uint32_t b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint64_t h = (w << 5) + b;
+                const uint32_t len = st->head[h].nd_mlen >> 8;
+                if (slot + k < GC_LIST) { s_old[slot + k] = (uint32_t)h; s_new[slot + k] = nid; s_off[slot + k] = noff; }
+                else copy_one(h, nid, noff);  // (more live records under this CTA's words than the list holds)
+                k++;
+                nid += 1;
+                noff += len;
+            }
+        }
+        __syncthreads();
+        const uint32_t m = s_cnt < GC_LIST ? s_cnt : GC_LIST;
+        // short records: one thread each; long ones are left to whole warps (nothing serial in the list's length)
+        for (uint32_t k = threadIdx.x; k < m; k += TPB) {
+            if ((st->head[s_old[k]].nd_mlen >> 8) <= GC_LONG) { copy_one(s_old[k], s_new[k], s_off[k]); s_old[k] = NONE32; }
+        }
+        __syncthreads();
+        const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (uint32_t k = wid; k < m; k += TPB / 32) {
+            const uint32_t h = s_old[k];
+            if (h == NONE32) continue;  // (warp-uniform)
+            const HapHead hd = st->head[h];
+            if (lane < HEAD_DELTA) s_delta[wid][lane] = hd.d[lane];
+            __syncwarp();
+            const uint64_t noff = s_off[k];
+            const uint32_t o = warp_flatten(st->arena + hd.off, hd.len, s_delta[wid], head_nd(hd), st->arena_alt + noff, st->L);
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t nid = s_new[k];
+                HapHead nh;
+                nh.off = noff;
+                nh.len = o;
+                nh.nd_mlen = o << 8;
+                nh.raw0 = hd.raw0;
+                nh.fit0 = hd.fit0;
+#pragma unroll
+                for (uint32_t q = 0; q < HEAD_DELTA; q++) nh.d[q] = 0xFFFFFFFFu;
+                st->head_alt[nid] = nh;
+                for (uint32_t p = 0; p < st->n_providers; p++) { hap_raw_alt(st, p, nid) = hap_raw(st, p, h); st->h_fit_alt[p][nid] = st->h_fit[p][h]; }
+            }
         }
     }
 }

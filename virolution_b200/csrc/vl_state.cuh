@@ -274,16 +274,22 @@ __host__ __device__ inline uint32_t entries_lower_interp(const uint32_t *e, uint
     {
         uint32_t g = (uint32_t)((float)pos * ((float)n / (float)L));
         if (g >= n) g = n - 1;
-        // window of 8 words starting at a 16-byte boundary of the arena, two entries before the guess
-        const uintptr_t first = (uintptr_t)(e + (g >= 2 ? g - 2 : 0)) & ~(uintptr_t)15;
+        // window of W words starting at a 16-byte boundary of the arena, centred on the guess: 8 words for short lists,
+        // 16 for long ones (the guess is off by ~sqrt(n) / 2 entries)
+        const bool wide = n > 48;
+        const uint32_t back = wide ? 6u : 2u;
+        const uintptr_t first = (uintptr_t)(e + (g >= back ? g - back : 0)) & ~(uintptr_t)15;
         const int32_t k0 = (int32_t)(((intptr_t)first - (intptr_t)(uintptr_t)e) / 4);  // list index of the first window word (may be negative)
         const uint4 v0 = *reinterpret_cast<const uint4 *>(first), v1 = *reinterpret_cast<const uint4 *>(first + 16);
-        const uint32_t wv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        uint4 v2 = make_uint4(0u, 0u, 0u, 0u), v3 = v2;
+        if (wide) { v2 = *reinterpret_cast<const uint4 *>(first + 32); v3 = *reinterpret_cast<const uint4 *>(first + 48); }
+        const uint32_t wv[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+        const int32_t W = wide ? 16 : 8;
         uint32_t below = 0, inside = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 16; j++) {
             const int32_t k = k0 + j;
-            const bool in = k >= 0 && k < (int32_t)n;
+            const bool in = j < W && k >= 0 && k < (int32_t)n;
             inside += in ? 1u : 0u;
             below += (in && entry_pos(wv[j]) < pos) ? 1u : 0u;
         }
