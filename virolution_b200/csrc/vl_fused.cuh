@@ -185,7 +185,8 @@ constexpr int OS_TPB = 256;
 constexpr int OS_PER = RESAMPLE_TILE / OS_TPB;
 template <bool SMALL_ONLY>
 __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
-    __shared__ uint64_t s_red[OS_TPB / 32];
+    __shared__ uint64_t s_red[2][OS_TPB / 32];
+    uint32_t it = 0;
     const uint64_t n = st->n;
     const uint64_t n_tiles = (n + RESAMPLE_TILE - 1) / RESAMPLE_TILE;
     const uint32_t *__restrict__ host_id = st->host_id;
@@ -236,12 +237,14 @@ __global__ void __launch_bounds__(OS_TPB, 4) k_offspring_sum(DevState *st) {
         uint64_t tot = local;
 #pragma unroll
         for (int sh = 16; sh > 0; sh >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, sh);
-        __syncthreads();
-        if ((tid & 31) == 0) s_red[tid >> 5] = tot;
+        // one barrier per tile: the warps' totals alternate between two rows of shared memory
+        uint64_t *row = s_red[it & 1u];
+        it++;
+        if ((tid & 31) == 0) row[tid >> 5] = tot;
         __syncthreads();
         if (tid == 0) {
             uint64_t t = 0;
-            for (int w = 0; w < OS_TPB / 32; w++) t += s_red[w];
+            for (int w = 0; w < OS_TPB / 32; w++) t += row[w];
             st->tile_sum[tile] = t;
         }
     }
@@ -494,6 +497,10 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
         }
         // (the staged children mutate at the start of the next generation, which follows at once (vl_run): their new
         // records' ids are known — record count + worklist position — and go into the population here)
+        // (the staged children mutate at the start of the next generation, which follows at once (vl_run): their new
+        // records' ids are known — record count + worklist position — and go into the population here.  Flushing after every
+        // tile keeps the worklist in tile order; holding the items back until the list is half full was measured: slower,
+        // 0.97 against 0.93 ms per generation, the mutate kernel included)
         if (PREFILL) cl_flush(st, cl, st->hap_id_next, st->n_hap);
     }
 }
