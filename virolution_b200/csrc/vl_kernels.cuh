@@ -917,7 +917,7 @@ __device__ __forceinline__ uint32_t warp_flatten(const uint32_t *pe, uint32_t pl
 }
 
 // parent_in_item: the worklist items carry the infectant's current haplotype id in .w
-__global__ void __launch_bounds__(TPB, 3) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
+__global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
     extern __shared__ uint32_t s_mut_dyn[];
     __shared__ double s_subst[16];
     uint32_t *s_scratch = s_mut_dyn;
@@ -1626,7 +1626,7 @@ __device__ __forceinline__ void plan_block_scan(const uint64_t *src, uint64_t *d
     __syncthreads();
     if (tid == 0) *s_carry = init;
     __syncthreads();
-    constexpr uint32_t E = 8;  // up to E consecutive elements per thread in ONE round: one latency, one block scan
+    constexpr uint32_t E = 16;  // up to E consecutive elements per thread in ONE round: one latency, one block scan
     if (nt <= (uint64_t)PLAN_THREADS * E) {
         const uint64_t per = (nt + PLAN_THREADS - 1) / PLAN_THREADS;
         const uint64_t lo = per * tid < nt ? per * tid : nt, hi = lo + per < nt ? lo + per : nt;
