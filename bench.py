@@ -277,8 +277,11 @@ def run_b200(args, rank, world):
         if runner is None:
             sim.run(k)
         else:
-            for _ in range(k):
-                runner.step()
+            if hasattr(runner, "run") and os.environ.get("VL_EXCHANGE_STEPWISE") != "1":
+                runner.run(k)
+            else:
+                for _ in range(k):
+                    runner.step()
 
     def barrier():
         sim.synchronize()

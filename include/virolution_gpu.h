@@ -276,6 +276,9 @@ int vl_exchange_begin(vl_exchange *ex); /* increment_generation .. replicate_inf
 int vl_exchange_push(vl_exchange *ex);  /* calls vl_exchange_begin if the caller has not */
 int vl_exchange_pull(vl_exchange *ex);
 int vl_exchange_step(vl_exchange *ex);
+/* n generations of vl_exchange_step enqueued back to back; every generation but the last also prepares the next one's
+ * infection while it draws and imports (what vl_run does for a single device).  Same populations as n vl_exchange_step calls. */
+int vl_exchange_run(vl_exchange *ex, uint64_t n_generations);
 int vl_exchange_destroy(vl_exchange *ex);
 
 /* ---- measurement hooks (bench.py): CUDA events on the handle's own stream ------------------ */

@@ -241,3 +241,91 @@ def test_sharded_compartment_agrees_with_the_unsharded_one():
     for k in cols:
         p = stats.ks_2samp(ra[:, k], rb[:, k]).pvalue
         assert p > 0.01 / len(cols), f"column {k}: KS p={p:.2e} (one handle mean {ra[:, k].mean():.6g}, sharded mean {rb[:, k].mean():.6g})"
+
+
+def _exchange_pair(wl, seed, T, monkeypatch=None, experiment=None):
+    from virolution_b200.simulation import GpuSimulation, PeerExchangeHandle
+    import os
+    old = os.environ.get("VL_EXPERIMENT")
+    if experiment is not None:
+        os.environ["VL_EXPERIMENT"] = str(experiment)  # read when the handle is created
+    try:
+        sims = [GpuSimulation(wl["wildtype"], wl["parameters"], wl["specs"], seed=seed, compartment_id=k) for k in range(2)]
+    finally:
+        if experiment is not None:
+            if old is None:
+                del os.environ["VL_EXPERIMENT"]
+            else:
+                os.environ["VL_EXPERIMENT"] = old
+    for s in sims:
+        s.set_population_wildtype(wl["n0"])
+    ex = [PeerExchangeHandle(sims[k], k, 2, T, words_per_migrant=32) for k in range(2)]
+    bufs = [e.recv_buffer() for e in ex]
+    for k in range(2):
+        ex[k].connect(None, [bufs[t] if t != k else 0 for t in range(2)])
+    return sims, ex
+
+
+def _population_state(g):
+    off, pos, base = g.export_mutations()
+    return off, pos, base, g.get_raw_fitness().view(np.uint64)
+
+
+@pytest.mark.parametrize("name", ["k2_hiv", "k1_singlehost"])
+def test_exchange_run_equals_steps_and_general_kernels(name):
+    """The loop bench.py times at --gpus N (vl_exchange_run: own part drawn in place, one-pass export and import, the next
+    generation's infection prepared by the draws and the import) against the same generations as single vl_exchange_step
+    calls and against the general exchange kernels (several passes, own part copied): the same populations, infectant by
+    infectant, on both ranks."""
+    from virolution_b200.distributed import migration_matrix
+    from virolution_b200.workloads import workload
+    wl = workload(name, 150_000)
+    if name == "k1_singlehost":
+        wl["parameters"].mutation_rate = 2e-5
+    T = np.asarray(migration_matrix(2, 0.1), dtype=np.float64)
+    arms = {"run": _exchange_pair(wl, 31, T), "steps": _exchange_pair(wl, 31, T), "general": _exchange_pair(wl, 31, T, experiment=256),
+            "overlap": _exchange_pair(wl, 31, T, experiment=1024)}  # (own part mutated on the main stream while the migrants travel on a side stream)
+    G = 5
+    for arm in ("run", "overlap"):
+        for e in arms[arm][1]:          # both ranks enqueue all generations; they meet on the device
+            e.run(G)
+    for arm in ("steps", "general"):
+        sims, ex = arms[arm]
+        for _ in range(G):
+            for e in ex:
+                e.push()
+            for e in ex:
+                e.pull()
+    for sims, _ in arms.values():
+        for s in sims:
+            s.synchronize()
+    for k in range(2):
+        ref = _population_state(arms["steps"][0][k])
+        assert arms["steps"][0][k].population_len() > 100_000
+        assert (np.diff(ref[0].astype(np.int64)) > 0).sum() > 1000, "the run must have produced mutants"
+        for arm in ("run", "general", "overlap"):
+            got = _population_state(arms[arm][0][k])
+            for x, y, what in zip(got, ref, ("mutation offsets", "positions", "bases", "raw fitness bits")):
+                assert np.array_equal(x, y), f"{name}, rank {k}, {arm} vs steps: {what} differ"
+    # and the run continues from the same state: two more generations, compaction forced in between
+    for arm in ("run", "steps"):
+        sims, ex = arms[arm]
+        for s in sims:
+            s.collect_garbage()
+    for e in arms["run"][1]:
+        e.run(2)
+    sims, ex = arms["steps"]
+    for _ in range(2):
+        for e in ex:
+            e.push()
+        for e in ex:
+            e.pull()
+    for k in range(2):
+        a, b = _population_state(arms["run"][0][k]), _population_state(arms["steps"][0][k])
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), f"{name}, rank {k}: after compaction"
+    for sims, ex in arms.values():
+        for e in ex:
+            e.close()
+        for s in sims:
+            s.close()

@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -84,6 +85,8 @@ struct vl_sim {
     bool uniform_infection = false;  // the host map came from uniform Philox draws over [0, H) (no replay, DevState::fast_infect)
     bool pop_fit_valid = false;   // pop_fit[] holds the mapped reproductive fitness of every infectant of the current population
     bool prefilled = false;       // the last resample drew the next generation's hosts and mutation counts (k_resample_pos<true>)
+    bool prefill_patch = false;   // ... and records were created after it (imported migrants): k_mutate patches the population itself
+    bool prefill_own_done = false; // ... and the items [0, mut_own) of the prepared worklist have been mutated already (k_mutate range 1)
     bool hsum_dirty = false;      // ... and that work was dropped: hsum[parity] holds stale sums, cleared before the next infect pass
     uint32_t plan_smem_tiles = 0;
     uint32_t salt = 0;        // distinguishes the sampling streams of one generation
@@ -100,7 +103,7 @@ struct vl_sim {
 // whatever changes the population, the parameters or the record ids between two generations of the device-resident
 // loop drops the infection the last resample prepared (hosts, mutation worklist, per-host sums of the next generation)
 static inline void drop_prefill(vl_sim *sim) {
-    if (sim->prefilled) { sim->prefilled = false; sim->hsum_dirty = true; }
+    if (sim->prefilled) { sim->prefilled = false; sim->prefill_own_done = false; sim->hsum_dirty = true; }
 }
 
 // records the start event of a profiled launch and returns the stop event to record after it
@@ -141,6 +144,13 @@ static int fail(vl_sim *sim, int code, const char *fmt, ...) {
         if (pe_) cudaEventRecord(pe_, (sim)->stream);                       \
         (sim)->launches++;                                                  \
     } while (0)
+// launches of a scope go to another stream of the same handle
+struct StreamScope {
+    vl_sim *sim;
+    cudaStream_t saved;
+    StreamScope(vl_sim *s, cudaStream_t other) : sim(s), saved(s->stream) { s->stream = other; }
+    ~StreamScope() { sim->stream = saved; }
+};
 #define ENTER(sim)                                                   \
     if (!(sim)) return fail(nullptr, VL_ERR_ARGUMENT, "null handle"); \
     std::lock_guard<std::recursive_mutex> lock_((sim)->mu);           \
@@ -540,6 +550,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CCU(cudaFuncSetAttribute(k_host_sum_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
     CCU(cudaFuncSetAttribute(k_mutate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
     CCU(cudaFuncSetAttribute(k_resample_pos<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
+    CCU(cudaFuncSetAttribute(k_ex_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_SMEM_BYTES));
     sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
     h.gc_arena_threshold = cap_arena / 2;
@@ -806,7 +817,7 @@ static int enqueue_mutate(vl_sim *sim) {
         TRY(zero_field32(sim, FIELD_OFF(n_mut_list)));
         LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, mutate_smem_bytes(h.L), sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, mutate_smem_bytes(h.L), sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0, 0);
     sim->pop_fit_valid = false;  // haplotypes of the current population changed
     sim->mutcounts_ready = false;
     sim->has_rp_mut = false;
@@ -870,10 +881,18 @@ static int canonical_layout(vl_sim *sim) {
     sim->layout_identity = true;
     return VL_OK;
 }
+// how the draws of the device-resident generation (k_resample_pos) land
+struct PosOpts {
+    bool prefill = false;              // also draw the children's hosts and mutation counts of the next generation
+    int own_part = -1;                 // the part written straight into the population being assembled
+    const uint64_t *own_off = nullptr; // device: its first slot there (nullptr = 0)
+    bool predict_ids = false;          // nothing creates records between these draws and the next k_mutate
+    std::function<int()> between;      // enqueued between the plan and the draws (the plan's part sizes are final there)
+};
 // plan + draws of n parts of the current offspring map in one pass each (n <= MAX_PARTS)
 static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, int use_amount, const uint64_t *amount, int set_next,
                                 uint32_t *const *dst, uint64_t *dst64, int mode, bool tiles = false, double *const *dst_fit = nullptr,
-                                bool prefill = false) {
+                                const PosOpts *po = nullptr) {
     if (n == 0 || n > (uint32_t)MAX_PARTS) return fail(sim, VL_ERR_ARGUMENT, "between 1 and %d parts per pass", MAX_PARTS);
     if (!tiles) TRY(canonical_layout(sim));
     PlanArgs pa;
@@ -906,8 +925,14 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
         memset(&rt, 0, sizeof rt);
         rt.n_parts = n;
         for (uint32_t k = 0; k < n; k++) { rt.salt[k] = ra.salt[k]; rt.dst[k] = ra.dst[k]; rt.dst_fit[k] = dst_fit ? dst_fit[k] : nullptr; }
+        rt.own_part = po ? po->own_part : -1;
+        rt.own_off = po ? po->own_off : nullptr;
+        rt.predict_ids = po && po->predict_ids ? 1 : 0;
+        for (uint32_t k = 0; k < n; k++)
+            if ((int)k != rt.own_part && !rt.dst[k]) return fail(sim, VL_ERR_IMPLEMENTATION, "part %u has no destination", k);
+        if (po && po->between) TRY(po->between());
         const unsigned rg = (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8);
-        if (prefill && n == 1 && !rt.dst[0]) LAUNCH(sim, k_resample_pos<true>, rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
+        if (po && po->prefill && rt.own_part >= 0) LAUNCH(sim, k_resample_pos<true>, rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
         else LAUNCH(sim, k_resample_pos<false>, rg, RT_TPB, 0, sim->d, rt);
         return VL_OK;
     }
@@ -1384,7 +1409,7 @@ static int enqueue_generation_front(vl_sim *sim) {
         // depend on its host, so mutate first and build the host map from the already-mutated population
         LAUNCH(sim, k_begin_generation, 1, 1024, 0, sim->d);
         LAUNCH(sim, k_mutcount_fast, grid_tiles(sim, sim->n_bound, (uint64_t)TPB * MC_ITEMS, 8), TPB, 0, sim->d);
-        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0, 1);
+        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0, 1, 0);
         const int btpb = (sim->experiment & 2) ? 512 : 1024;
         const unsigned chunks = (unsigned)std::max<uint64_t>(1, (sim->n_bound + btpb * BUCKET_ITEMS - 1) / (btpb * BUCKET_ITEMS));
         if (btpb == 1024) LAUNCH(sim, (k_infect_bucket<false, false, 1024>), chunks, 1024, 0, sim->d);
@@ -1424,15 +1449,22 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
         if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
         else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 3, 1);
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
+           prefilled && sim->prefill_patch ? 4 : 3, 1, prefilled && sim->prefill_own_done ? 2 : 0);
     const unsigned og = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, og, OS_TPB, 0, sim->d);
     else LAUNCH(sim, k_offspring_sum<false>, og, OS_TPB, 0, sim->d);
     const double one = 1.0;
     uint32_t *dsts[1] = {nullptr};
-    TRY(launch_plan_resample(sim, 1, &one, 0, nullptr, 1, dsts, nullptr, 0, true, nullptr, prefill_next));
+    PosOpts po;
+    po.prefill = prefill_next;
+    po.own_part = 0;
+    po.predict_ids = true;
+    TRY(launch_plan_resample(sim, 1, &one, 0, nullptr, 1, dsts, nullptr, 0, true, nullptr, &po));
     LAUNCH(sim, k_swap_population_fused, 1, 1, 0, sim->d);
     sim->prefilled = prefill_next;
+    sim->prefill_patch = false;
+    sim->prefill_own_done = false;
     sim->uniform_infection = true;
     sim->mutcounts_ready = false;
     sim->bucket_pending = false;
@@ -1442,15 +1474,19 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
 // left on the device in infectant order (what vl_exchange_begin enqueues when the compartment qualifies)
 static int enqueue_generation_front_fused(vl_sim *sim) {
     const DevState &h = sim->h;
-    drop_prefill(sim);
     sim->salt = 0;
-    LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d, 0);
-    if (sim->hsum_dirty) LAUNCH(sim, k_zero_hsum_current, grid_for(sim, h.H), TPB, 0, sim->d);
-    sim->hsum_dirty = false;
+    const bool prefilled = sim->prefilled;  // (the previous exchange generation of the same vl_exchange_run call prepared this one)
+    LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d, prefilled ? 1 : 0);
     const unsigned ig = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
-    if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
-    else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 3, 1);
+    if (!prefilled) {
+        if (sim->hsum_dirty) LAUNCH(sim, k_zero_hsum_current, grid_for(sim, h.H), TPB, 0, sim->d);
+        sim->hsum_dirty = false;
+        if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
+        else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
+    }
+    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
+           prefilled && sim->prefill_patch ? 4 : 3, 1, prefilled && sim->prefill_own_done ? 2 : 0);
+    sim->prefilled = false;
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, ig, OS_TPB, 0, sim->d);
     else LAUNCH(sim, k_offspring_sum<false>, ig, OS_TPB, 0, sim->d);
     sim->uniform_infection = true;
@@ -1574,6 +1610,12 @@ struct vl_exchange {
     uint32_t *part_ids[EX_MAX_WORLD] = {nullptr};
     double *own_fit = nullptr;   // mapped fitness of my own part (device-resident generation)
     bool fused_step = false;     // the generation in flight runs on the kernels of vl_fused.cuh
+    bool fast_step = false;      // ... and on the one-pass export / import kernels (own part drawn in place)
+    bool prefill_step = false;   // ... and prepares the next generation's infection (vl_exchange_run, all but the last generation)
+    bool more_follow = false;
+    bool overlap_step = false;   // ... and mutates its own part of the next generation while the migrants travel (side stream)
+    cudaStream_t side = nullptr; // export, wait and import of an overlapped generation
+    cudaEvent_t ev_drawn = nullptr, ev_imported = nullptr;
     uint32_t *words_out = nullptr, *words_in = nullptr, *recs_in = nullptr, *rec_off = nullptr;
     uint64_t *woff = nullptr, *word_off = nullptr;
     uint32_t *stage = nullptr;  // leaving entries in concatenation order, before they are streamed to the targets
@@ -1582,6 +1624,7 @@ struct vl_exchange {
 struct ExLayout {
     uint64_t tflag_off[2], tot_off[2];  // sharded compartment: world flags + world offspring totals per parity
     uint64_t flag_off[2][EX_MAX_WORLD], header_off[2][EX_MAX_WORLD], len_off[2][EX_MAX_WORLD], raw_off[2][EX_MAX_WORLD], ent_off[2][EX_MAX_WORLD];
+    uint64_t eflag_off[2][EX_MAX_WORLD], meta_off[2][EX_MAX_WORLD];
     uint64_t m_cap[EX_MAX_WORLD], w_cap[EX_MAX_WORLD];
     uint64_t bytes;
 };
@@ -1598,6 +1641,8 @@ static ExLayout ex_layout(uint32_t world, uint32_t target, const double *T, uint
     uint64_t off = 0;
     for (int par = 0; par < 2; par++)
         for (uint32_t o = 0; o < world; o++) { L.flag_off[par][o] = off; off += 8; }
+    for (int par = 0; par < 2; par++)
+        for (uint32_t o = 0; o < world; o++) { L.eflag_off[par][o] = off; off += 8; }
     for (int par = 0; par < 2; par++) { L.tflag_off[par] = off; off += 8ull * world; }
     for (int par = 0; par < 2; par++) { L.tot_off[par] = off; off += 8ull * world; }
     off = (off + 255) & ~255ull;
@@ -1612,6 +1657,7 @@ static ExLayout ex_layout(uint32_t world, uint32_t target, const double *T, uint
             if (o == target) continue;
             L.header_off[par][o] = off; off += EX_HEADER_BYTES;
             L.len_off[par][o] = off; off = (off + L.m_cap[o] * 4 + 255) & ~255ull;
+            L.meta_off[par][o] = off; off = (off + L.m_cap[o] * sizeof(uint4) + 255) & ~255ull;
             L.raw_off[par][o] = off; off = (off + L.m_cap[o] * P * 8 + 255) & ~255ull;
             L.ent_off[par][o] = off; off = (off + L.w_cap[o] * 4 + 255) & ~255ull;
         }
@@ -1625,6 +1671,8 @@ static void ex_block(ExBlock &b, uint8_t *base, const ExLayout &L, uint32_t orig
         b.raw[par] = (double *)(base + L.raw_off[par][origin]);
         b.entries[par] = (uint32_t *)(base + L.ent_off[par][origin]);
         b.flag[par] = (unsigned long long *)(base + L.flag_off[par][origin]);
+        b.eflag[par] = (unsigned long long *)(base + L.eflag_off[par][origin]);
+        b.meta[par] = (uint4 *)(base + L.meta_off[par][origin]);
     }
     b.m_cap = L.m_cap[origin];
     b.w_cap = L.w_cap[origin];
@@ -1638,9 +1686,37 @@ static void ex_free(vl_exchange *ex) {
         if (ex->peer[t] && ex->peer_ipc[t]) cudaIpcCloseMemHandle(ex->peer[t]);
         if (ex->part_ids[t]) cudaFree(ex->part_ids[t]);
     }
+    if (ex->side) { cudaStreamSynchronize(ex->side); cudaStreamDestroy(ex->side); }
+    if (ex->ev_drawn) cudaEventDestroy(ex->ev_drawn);
+    if (ex->ev_imported) cudaEventDestroy(ex->ev_imported);
     void *bufs[] = {ex->recv, ex->scratch, ex->words_out, ex->words_in, ex->recs_in, ex->rec_off, ex->woff, ex->word_off, ex->stage, ex->own_fit};
     for (void *b : bufs) if (b) cudaFree(b);
     delete ex;
+}
+// Kernels are loaded lazily, and loading one may wait for every running kernel of the context.  A rank whose stream is
+// waiting (on the device) for a peer that lives in the same process must therefore never be the reason a launch blocks:
+// every kernel of the exchange loop is loaded before the first generation is enqueued.
+static void preload_exchange_kernels() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const void *ks[] = {
+            (const void *)k_zero_words, (const void *)k_begin_generation_fused, (const void *)k_zero_hsum_current,
+            (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate,
+            (const void *)k_offspring_sum<false>, (const void *)k_offspring_sum<true>, (const void *)k_plan_resample,
+            (const void *)k_resample_pos<false>, (const void *)k_resample_pos<true>, (const void *)k_swap_population_fused,
+            (const void *)k_ex_sizes, (const void *)k_ex_wait_sizes, (const void *)k_ex_export, (const void *)k_ex_publish_fused,
+            (const void *)k_ex_wait, (const void *)k_ex_import_fused, (const void *)k_ex_own_items, (const void *)k_shard_publish_total, (const void *)k_shard_split,
+            (const void *)k_ex_out_starts, (const void *)k_ex_lens, (const void *)k_ex_copy, (const void *)k_ex_stream, (const void *)k_ex_publish,
+            (const void *)k_ex_in_starts, (const void *)k_ex_in_words, (const void *)k_ex_reserve, (const void *)k_ex_import, (const void *)k_ex_own,
+            (const void *)k_swap_population, (const void *)k_scan_u32<uint32_t, true>, (const void *)k_scan_u32<uint64_t, true>,
+            (const void *)k_gc_begin, (const void *)k_gc_clear, (const void *)k_gc_mark, (const void *)k_gc_mark_pending, (const void *)k_gc_words,
+            (const void *)k_gc_copy, (const void *)k_gc_remap, (const void *)k_gc_remap_pending, (const void *)k_gc_end,
+        };
+        for (const void *k : ks) {
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, k);
+        }
+    });
 }
 VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const double *transfer, uint64_t words_per_migrant,
                               int sharded, uint64_t shard_seed, vl_exchange **out, void *ipc_handle_out) {
@@ -1693,7 +1769,19 @@ VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const 
     XCU(cudaMalloc((void **)&ex->recs_in, (ex->m_in_bound + 2) * 4));
     XCU(cudaMalloc((void **)&ex->rec_off, (ex->m_in_bound + 2) * 4));
     XCU(cudaMalloc((void **)&ex->word_off, (ex->m_in_bound + 2) * 8));
+    {   // the side stream carries the NVLink-bound kernels: they need few SMs but should get them at once
+        int lo = 0, hi = 0;
+        XCU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        XCU(cudaStreamCreateWithPriority(&ex->side, cudaStreamNonBlocking, hi));
+    }
+    XCU(cudaEventCreateWithFlags(&ex->ev_drawn, cudaEventDisableTiming));
+    XCU(cudaEventCreateWithFlags(&ex->ev_imported, cudaEventDisableTiming));
 #undef XCU
+    preload_exchange_kernels();
+    {   // the scans of the loop (imports, compaction) must not have to grow their work area (that synchronises)
+        const int rc = zero_scan_work(sim, std::max<uint64_t>(h.cap_hap / 32 + 16, std::max(ex->m_in_bound, ex->m_out_bound) + 16));
+        if (rc != VL_OK) { ex_free(ex); return rc; }
+    }
     *out = ex;
     return VL_OK;
 }
@@ -1745,6 +1833,12 @@ VL_API int vl_exchange_begin(vl_exchange *ex) {
     if (!ex->connected) return fail(sim, VL_ERR_IMPLEMENTATION, "vl_exchange_connect has not run");
     if (ex->begun || ex->pushed) return fail(sim, VL_ERR_IMPLEMENTATION, "the previous generation of this exchange is not finished");
     ex->fused_step = fused_now(sim);
+    ex->fast_step = ex->fused_step && !(sim->experiment & 256);
+    ex->prefill_step = ex->fast_step && ex->more_follow && !(sim->experiment & 32);
+    // (measured at 2 x 10^7, K2: the own part's k_mutate and the export slow each other down — both wait on scattered DRAM
+    // reads — and the step gets longer, not shorter; the overlapped order stays available for A/B runs)
+    ex->overlap_step = ex->prefill_step && (sim->experiment & 1024);
+    if (!ex->fused_step) drop_prefill(sim);
     if (ex->fused_step) TRY(enqueue_generation_front_fused(sim));
     else TRY(enqueue_generation_front(sim));
     ex->seq += 1;
@@ -1777,17 +1871,56 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
     double *fits[EX_MAX_WORLD];
     for (uint32_t t = 0; t < W; t++) fits[t] = t == r ? ex->own_fit : nullptr;  // (migrants get theirs from the record they become)
     a.own_fit = ex->fused_step ? ex->own_fit : nullptr;
+    ExScratch *sc = ex->scratch;
+    PosOpts po;
+    if (ex->fast_step) {
+        // the part sizes are final once the plan has run: announce them, learn every origin's, and draw my own part
+        // straight into its place in the new population (with the children's next infection when another generation follows)
+        po.own_part = (int)r;
+        po.own_off = (const uint64_t *)((const char *)sc + offsetof(ExScratch, own_off));
+        po.prefill = ex->prefill_step;
+        po.predict_ids = false;  // the imported migrants become records before the next k_mutate runs
+        po.between = [=]() -> int {
+            LAUNCH(sim, k_ex_sizes, 1, 32, 0, sim->d, a, sc);
+            LAUNCH(sim, k_ex_wait_sizes, 1, 32, 0, sim->d, a, sc, 20ull * 1000000000ull);
+            return VL_OK;
+        };
+    }
     if (ex->sharded) {
         // every rank's offspring total has been published (vl_exchange_begin): wait for them, split the N' draws over
         // the (target, origin) cells, draw my row of parts with the amounts the split left in DevState::plan_amount
         LAUNCH(sim, k_shard_split, 1, 32, 0, sim->d, a, 20ull * 1000000000ull);
-        TRY(launch_plan_resample(sim, W, nullptr, 2, nullptr, 0, dsts, nullptr, 0, ex->fused_step, fits));
+        TRY(launch_plan_resample(sim, W, nullptr, 2, nullptr, 0, dsts, nullptr, 0, ex->fused_step, fits, &po));
     } else {
-        TRY(launch_plan_resample(sim, W, factors, 0, nullptr, 0, dsts, nullptr, 0, ex->fused_step, fits));
+        TRY(launch_plan_resample(sim, W, factors, 0, nullptr, 0, dsts, nullptr, 0, ex->fused_step, fits, &po));
     }
-    ExScratch *sc = ex->scratch;
+    if (ex->fast_step) {
+        const unsigned eg = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ex->m_out_bound + EXP_TPB - 1) / EXP_TPB), (uint64_t)sim->n_sms * 4);
+        if (ex->overlap_step) {
+            static const int side_ctas = getenv("VL_EX_CTAS") ? atoi(getenv("VL_EX_CTAS")) : 2;
+            const unsigned eg = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ex->m_out_bound + EXP_TPB - 1) / EXP_TPB), (uint64_t)sim->n_sms * side_ctas);
+            // The migrants leave on the side stream.  Meanwhile this stream mutates the children just drawn for the next
+            // generation (their worklist items and the ids of their new records are fixed first: the import appends
+            // items and creates records of its own while that runs).
+            LAUNCH(sim, k_ex_own_items, 1, 1, 0, sim->d);
+            CU(sim, cudaEventRecord(ex->ev_drawn, sim->stream));
+            CU(sim, cudaStreamWaitEvent(ex->side, ex->ev_drawn, 0));
+            {
+                StreamScope on_side(sim, ex->side);
+                LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
+                LAUNCH(sim, k_ex_publish_fused, 1, 32, 0, sim->d, a, (const ExScratch *)sc);
+            }
+            LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(sim->h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 4, 1, 1);
+        } else {
+            LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
+            LAUNCH(sim, k_ex_publish_fused, 1, 32, 0, sim->d, a, (const ExScratch *)sc);
+        }
+        ex->pushed = true;
+        CU(sim, cudaGetLastError());
+        return VL_OK;
+    }
     const uint64_t *n_out = (const uint64_t *)((const char *)sc + offsetof(ExScratch, n_out));
-    // ---- push
+    // ---- push (general kernels: any flow, several passes)
     LAUNCH(sim, k_ex_out_starts, 1, 1, 0, sim->d, a, sc);
     LAUNCH(sim, k_ex_lens, grid_for(sim, ex->m_out_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, ex->words_out);
     TRY((launch_scan<uint64_t, true>(sim, ex->words_out, ex->woff, n_out, 0, ex->m_out_bound, nullptr, 1, nullptr)));
@@ -1813,6 +1946,18 @@ VL_API int vl_exchange_pull(vl_exchange *ex) {
     ExScratch *sc = ex->scratch;
     const uint64_t *n_imp = (const uint64_t *)((const char *)sc + offsetof(ExScratch, n_imp));
     uint64_t *totals = (uint64_t *)((char *)sc + offsetof(ExScratch, totals));
+    if (ex->fast_step) {
+        const unsigned ig = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ex->m_in_bound + EXP_TPB - 1) / EXP_TPB), (uint64_t)sim->n_sms * 4);
+        {
+            StreamScope on_side(sim, ex->overlap_step ? ex->side : sim->stream);
+            LAUNCH(sim, k_ex_wait, 1, 32, 0, sim->d, a, 20ull * 1000000000ull);
+            LAUNCH(sim, k_ex_import_fused, ig, EXP_TPB, 0, sim->d, a, (const ExScratch *)sc, ex->prefill_step ? 1 : 0);
+        }
+        if (ex->overlap_step) {
+            CU(sim, cudaEventRecord(ex->ev_imported, ex->side));
+            CU(sim, cudaStreamWaitEvent(sim->stream, ex->ev_imported, 0));
+        }
+    } else {
     LAUNCH(sim, k_ex_wait, 1, 32, 0, sim->d, a, 20ull * 1000000000ull);
     LAUNCH(sim, k_ex_in_starts, 1, 1, 0, sim->d, a, sc);
     LAUNCH(sim, k_ex_in_words, grid_for(sim, ex->m_in_bound), TPB, 0, a, (const ExScratch *)sc, ex->words_in, ex->recs_in);
@@ -1822,6 +1967,7 @@ VL_API int vl_exchange_pull(vl_exchange *ex) {
     LAUNCH(sim, k_ex_import, grid_for(sim, ex->m_in_bound), TPB, 0, sim->d, a, (const ExScratch *)sc, (const uint32_t *)ex->rec_off, (const uint64_t *)ex->word_off);
     a.own_fit = ex->fused_step ? ex->own_fit : nullptr;
     LAUNCH(sim, k_ex_own, grid_for(sim, sim->h.max_population), TPB, 0, sim->d, a, (const ExScratch *)sc);
+    }
     if (ex->fused_step) {  // both per-infectant arrays swap, the per-host sums change sides (k_offspring_sum cleared the other buffer)
         LAUNCH(sim, k_swap_population_fused, 1, 1, 0, sim->d);
         std::swap(sim->h.hap_id, sim->h.hap_id_next);
@@ -1830,6 +1976,9 @@ VL_API int vl_exchange_pull(vl_exchange *ex) {
         swap_population(sim);
     }
     sim->pop_fit_valid = ex->fused_step;  // k_ex_import and k_ex_own filled the carried fitness of the new population
+    sim->prefilled = ex->prefill_step;
+    sim->prefill_patch = ex->prefill_step;
+    sim->prefill_own_done = ex->overlap_step;
     sim->n_valid = false;
     {   // upper bound of the new population: every origin sends at most its block capacity, the own part its cap
         uint64_t bound = 0;
@@ -1851,6 +2000,20 @@ VL_API int vl_exchange_pull(vl_exchange *ex) {
 VL_API int vl_exchange_step(vl_exchange *ex) {
     TRY(vl_exchange_push(ex));
     return vl_exchange_pull(ex);
+}
+// n generations enqueued back to back (the ranks meet on the device only).  Every generation but the last also prepares the
+// infection of the next one while it draws and imports (as vl_run does); nothing of that prepared state outlives the call.
+VL_API int vl_exchange_run(vl_exchange *ex, uint64_t n_generations) {
+    if (!ex) return fail(nullptr, VL_ERR_ARGUMENT, "null exchange");
+    std::lock_guard<std::recursive_mutex> lock_(ex->sim->mu);
+    for (uint64_t g = 0; g < n_generations; g++) {
+        ex->more_follow = g + 1 < n_generations;
+        int rc = vl_exchange_push(ex);
+        if (rc == VL_OK) rc = vl_exchange_pull(ex);
+        ex->more_follow = false;
+        if (rc != VL_OK) return rc;
+    }
+    return VL_OK;
 }
 
 static inline uint64_t f64_as_usize_host(double x) {

@@ -16,16 +16,22 @@
 // after its import of g.
 #pragma once
 #include "vl_migrate.cuh"
+#include "vl_fused.cuh"
 
 namespace vl {
 
 constexpr uint32_t EX_MAX_WORLD = MAX_PARTS;
 constexpr uint64_t EX_HEADER_BYTES = 64;
+constexpr uint32_t MIG_WILD_META = 0xFFFFFFFFu;
 
 // where one (target <- origin) block lives, for both parities; pointers are valid on the GPU that dereferences them
 struct ExBlock {
-    uint64_t *header[2];  // {m, w}
+    uint64_t *header[2];  // {m, w, m announced early (k_ex_sizes)}
     uint32_t *len[2];
+    uint4 *meta[2];       // fast path, per migrant: {first word inside entries[] (MIG_WILD_META for the wildtype), base list length,
+                          // HapHead::nd_mlen, 0}; its words are the base list followed by the nd delta entries of its head,
+                          // and the words of a block are not in migrant order
+    unsigned long long *eflag[2];  // raised by the origin as soon as its part sizes are decided
     double *raw[2];
     uint32_t *entries[2];
     unsigned long long *flag[2];  // written last by the origin: the sequence number of the generation the block holds
@@ -54,6 +60,8 @@ struct ExScratch {
     uint64_t n_imp, w_imp;
     uint64_t totals[2];                     // records / words needed by the import (from the scans)
     uint64_t reserve[2];
+    unsigned long long wcur[EX_MAX_WORLD];  // fast path: entry words written so far into every target's block
+    uint64_t own_off;                       // fast path: first slot of my own part in the new population (= in_start[rank])
 };
 
 __device__ __forceinline__ uint32_t ex_find(const uint64_t *start, uint32_t world, uint64_t idx) {
@@ -230,6 +238,359 @@ __global__ void __launch_bounds__(TPB) k_ex_own(DevState *st, ExArgs ex, const E
             st->hap_id_next[s0 + k] = src[k];
             st->pop_fit_next[s0 + k] = ex.own_fit ? ex.own_fit[k] : (pi0 >= 0 ? st->h_fit[pi0][src[k]] : 1.0);
         }
+}
+
+// ---- fast path: compartments that run the device-resident generation (vl_fused.cuh) ---------------------------------------
+// Five kernels between the offspring map and the new population instead of seventeen, and no pass that only computes sizes:
+//   k_ex_sizes        the part sizes are known as soon as the plan has run: every target is told at once (header + early flag)
+//   k_ex_wait_sizes   every rank learns how many migrants each origin will send -> the layout of its new population; its OWN
+//                     part can then be drawn straight into place (k_resample_pos, which also prepares the children's next
+//                     infection: no k_ex_own copy, no k_infect_sum pass next generation)
+//   k_ex_export       length, raw fitness and entries of every leaving migrant in ONE pass: a CTA takes 256 consecutive
+//                     migrants, reserves their entry words in the targets' blocks with one atomic per target, gathers the
+//                     flattened records in shared memory and streams them to the peers in full lines; every migrant carries
+//                     the offset of its words (the blocks are filled in the order CTAs arrive)
+//   k_ex_publish      header, system fence, flag (as before)
+//   k_ex_wait, k_ex_import_fused   records, arena words and population slots of the imported migrants in ONE pass (ids and
+//                     words reserved per CTA), their carried fitness, and their infection for the next generation
+__global__ void k_ex_sizes(DevState *st, ExArgs ex, ExScratch *sc) {
+    __shared__ uint64_t s_m[EX_MAX_WORLD];
+    const uint32_t t = threadIdx.x;
+    if (t < ex.world) {
+        uint64_t m = t == ex.rank ? 0 : st->plan_size[t];
+        if (t != ex.rank && m > ex.out[t].m_cap) { raise(st, DE_INF_CAPACITY); m = ex.out[t].m_cap; }
+        s_m[t] = m;
+        sc->wcur[t] = 0ull;
+        if (t != ex.rank) {
+            ((volatile uint64_t *)ex.out[t].header[ex.parity])[2] = m;
+            __threadfence_system();
+            *(volatile unsigned long long *)ex.out[t].eflag[ex.parity] = ex.seq;
+        }
+    }
+    __syncthreads();
+    if (t == 0) {  // concatenation order of what leaves (targets ascending, own part skipped)
+        uint64_t acc = 0;
+        for (uint32_t q = 0; q < ex.world; q++) { sc->part_start[q] = acc; acc += s_m[q]; }
+        sc->part_start[ex.world] = acc;
+        sc->n_out = acc;
+    }
+}
+__global__ void k_ex_wait_sizes(DevState *st, ExArgs ex, ExScratch *sc, unsigned long long timeout_ns) {
+    __shared__ uint64_t s_m[EX_MAX_WORLD];
+    const uint32_t o = threadIdx.x;
+    if (o < ex.world) {
+        if (o == ex.rank) {
+            s_m[o] = st->plan_size[o];
+        } else {
+            const unsigned long long t0 = vl_globaltimer();
+            volatile unsigned long long *f = (volatile unsigned long long *)ex.in[o].eflag[ex.parity];
+            while (*f < ex.seq) {
+                if (vl_globaltimer() - t0 > timeout_ns) { raise(st, DE_EXCHANGE_TIMEOUT); break; }
+                __nanosleep(100);
+            }
+            __threadfence_system();
+            uint64_t m = ((volatile uint64_t *)ex.in[o].header[ex.parity])[2];
+            if (m > ex.in[o].m_cap) { raise(st, DE_REPLAY); m = 0; }
+            s_m[o] = m;
+        }
+    }
+    __syncthreads();
+    if (o != 0) return;
+    uint64_t pop = 0, imp = 0;  // layout of the new population (origins ascending, own part at its rank) and of the imported migrants
+    for (uint32_t q = 0; q < ex.world; q++) {
+        sc->in_start[q] = pop;
+        sc->imp_start[q] = imp;
+        pop += s_m[q];
+        if (q != ex.rank) imp += s_m[q];
+    }
+    sc->in_start[ex.world] = pop;
+    sc->imp_start[ex.world] = imp;
+    sc->n_imp = imp;
+    sc->own_off = sc->in_start[ex.rank];
+    if (pop > st->cap_inf) { raise(st, DE_INF_CAPACITY); pop = st->cap_inf; }
+    st->n_next = pop;
+}
+constexpr int EXP_TPB = 256;
+// last record of the round whose first word is at or before word g (s_pref: exclusive prefix sums of the round's lengths)
+__device__ __forceinline__ uint32_t ex_owner(const uint32_t *s_pref, uint32_t g) {
+    uint32_t lo = 0, hi = EXP_TPB;  // s_pref[lo] <= g < s_pref[hi] (s_pref[EXP_TPB] = total)
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_pref[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// A record travels as it is: its (possibly shared) base list and the delta entries of its head, 16 bytes of lengths and
+// its raw fitness values; the receiver rebuilds the head.  Shared-memory staging of a round (dynamic): the words in
+// destination order.  What a round sends to one target is one contiguous, 16-byte aligned run of words: it leaves with
+// ONE bulk copy (cp.async.bulk shared -> global, the peer's memory being the global side), or, bulk == 0, with 16-byte
+// stores of consecutive threads.
+constexpr uint32_t EXP_STAGE = 8192;  // words a round can stage (else the round's words are stored one by one)
+constexpr uint32_t EXP_SMEM_BYTES = EXP_STAGE * 4;
+__device__ __forceinline__ void bulk_store(void *dst_global, const void *src_shared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst_global)),
+                 "r"((uint32_t)__cvta_generic_to_shared(src_shared)), "r"(bytes)
+                 : "memory");
+}
+__global__ void __launch_bounds__(EXP_TPB) k_ex_export(DevState *st, ExArgs ex, ExScratch *sc, int bulk) {
+    extern __shared__ __align__(128) uint8_t s_exp_dyn[];
+    uint32_t *s_stage = (uint32_t *)s_exp_dyn;
+    __shared__ uint32_t s_pref[EXP_TPB + 1], s_pos[EXP_TPB], s_blen[EXP_TPB];
+    __shared__ uint32_t s_delta[EXP_TPB][HEAD_DELTA];
+    __shared__ uint64_t s_src[EXP_TPB];
+    __shared__ uint32_t s_sum[EX_MAX_WORLD], s_first[EX_MAX_WORLD], s_soff[EX_MAX_WORLD + 1];
+    __shared__ unsigned long long s_base[EX_MAX_WORLD];
+    __shared__ uint32_t s_w[EXP_TPB / 32];
+    const uint64_t M = sc->n_out;
+    const uint32_t P = ex.n_providers, par = ex.parity, W = ex.world;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t *__restrict__ arena = st->arena;
+    for (uint64_t c0 = (uint64_t)blockIdx.x * EXP_TPB; c0 < M; c0 += (uint64_t)gridDim.x * EXP_TPB) {
+        const uint64_t idx = c0 + tid;
+        const bool active = idx < M;
+        uint32_t t = 0, id = 0, len = 0, blen = 0, nd = 0;
+        uint64_t k = 0;
+        HapHead hd;
+        hd.off = 0; hd.len = 0u; hd.nd_mlen = 0u; hd.raw0 = 1.0;
+        if (active) {
+            t = ex_find(sc->part_start, W, idx);
+            k = idx - sc->part_start[t];
+            id = ex.part[t][k];
+            hd = st->head[id];  // ONE 64-byte line
+            if (id != 0) { blen = hd.len; nd = head_nd(hd); len = blen + nd; }
+        }
+        uint32_t inc = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        if (bulk && tid < W) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // (my copies of the previous round have read their data)
+        __syncthreads();  // (the shared arrays of the previous round are free)
+        if (lane == 31) s_w[wid] = inc;
+        if (tid < W) { s_sum[tid] = 0u; s_first[tid] = 0u; }
+        __syncthreads();
+        uint32_t pre = inc - len, tot = 0;
+#pragma unroll
+        for (int w = 0; w < EXP_TPB / 32; w++) {
+            const uint32_t v = s_w[w];
+            if (w < (int)wid) pre += v;
+            tot += v;
+        }
+        if (active) {
+            if (len) atomicAdd(&s_sum[t], len);
+            if (tid == 0 || idx == sc->part_start[t]) s_first[t] = pre;  // the first migrant of target t in this round
+        }
+        __syncthreads();
+        // every target's words of the round: a multiple of four words reserved in its block (so that every run starts
+        // 16-byte aligned there) and a 16-byte aligned run of the staging area
+        if (tid < W && s_sum[tid]) s_base[tid] = atomicAdd(&sc->wcur[tid], (unsigned long long)((s_sum[tid] + 3u) & ~3u));
+        if (tid == 0) {
+            uint32_t acc = 0;
+            for (uint32_t q = 0; q < W; q++) { s_soff[q] = acc; acc += (s_sum[q] + 3u) & ~3u; }
+            s_soff[W] = acc;
+        }
+        __syncthreads();
+        const bool staged = s_soff[W] <= EXP_STAGE;
+        s_pref[tid] = pre;
+        if (tid == 0) s_pref[EXP_TPB] = tot;
+        if (active) {
+            const uint32_t in_run = pre - s_first[t];
+            unsigned long long woff = len ? s_base[t] + in_run : 0ull;
+            bool fits = true;
+            if (woff + len + 3 > ex.out[t].w_cap) { raise(st, DE_ARENA_CAPACITY); fits = false; woff = 0ull; blen = 0u; }  // block too small: words_per_migrant
+            s_src[tid] = hd.off;
+            s_blen[tid] = blen;
+            s_pos[tid] = staged ? s_soff[t] + in_run : (fits ? (uint32_t)woff : 0xFFFFFFFFu);
+#pragma unroll
+            for (uint32_t q = 0; q < HEAD_DELTA; q++) s_delta[tid][q] = hd.d[q];
+            if (P) ex.out[t].raw[par][k * P] = hd.raw0;
+            for (uint32_t p = 1; p < P; p++) ex.out[t].raw[par][k * P + p] = hap_raw(st, p, id);
+            ex.out[t].meta[par][k] = make_uint4(id == 0 ? MIG_WILD_META : (uint32_t)woff, blen, fits ? hd.nd_mlen : 0u, 0u);
+        }
+        __syncthreads();
+        // the round's words over the whole CTA (four per thread in flight): base lists from the arena, deltas from the heads
+        for (uint32_t g0 = tid; g0 < tot; g0 += 4 * EXP_TPB) {
+            uint32_t v[4], j4[4], r4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t g = g0 + u * EXP_TPB;
+                if (g < tot) {
+                    const uint32_t j = ex_owner(s_pref, g), r = g - s_pref[j], bl = s_blen[j];
+                    j4[u] = j;
+                    r4[u] = r;
+                    v[u] = r < bl ? arena[s_src[j] + r] : s_delta[j][(r - bl) & (HEAD_DELTA - 1)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (g0 + u * EXP_TPB >= tot) continue;
+                if (staged) s_stage[s_pos[j4[u]] + r4[u]] = v[u];
+                else if (s_pos[j4[u]] != 0xFFFFFFFFu) {
+                    const uint32_t q = ex_find(sc->part_start, W, c0 + j4[u]);
+                    ex.out[q].entries[par][s_pos[j4[u]] + r4[u]] = v[u];
+                }
+            }
+        }
+        if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (my generic-proxy writes, before the barrier the copying threads pass)
+        __syncthreads();
+        if (!staged) continue;
+        if (bulk) {
+            if (tid < W) {
+                const uint32_t words = s_soff[tid + 1] - s_soff[tid];
+                if (words && s_base[tid] + words <= ex.out[tid].w_cap) {
+                    bulk_store(ex.out[tid].entries[par] + s_base[tid], s_stage + s_soff[tid], words * 4u);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        } else {
+            for (uint32_t q = 0; q < W; q++) {
+                const uint32_t nq = (s_soff[q + 1] - s_soff[q]) / 4;
+                if (nq && s_base[q] + nq * 4ull <= ex.out[q].w_cap) {
+                    const uint4 *src = (const uint4 *)(s_stage + s_soff[q]);
+                    uint4 *dst = (uint4 *)(ex.out[q].entries[par] + s_base[q]);
+                    for (uint32_t c = tid; c < nq; c += EXP_TPB) dst[c] = src[c];
+                }
+            }
+        }
+    }
+    if (bulk && tid < W) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // (all my copies are complete before the kernel ends)
+}
+// the worklist items staged so far (the children of my own part) and the ids of the records k_mutate (range 1) gives them
+__global__ void k_ex_own_items(DevState *st) {
+    const uint32_t n = st->n_mut_list;
+    st->mut_own = n;
+    st->mut_own_base = atomicAdd(&st->n_hap, (unsigned long long)n);
+}
+// headers, then (after a system-scope fence) the flags the targets wait on
+__global__ void k_ex_publish_fused(DevState *st, ExArgs ex, const ExScratch *sc) {
+    const uint32_t t = threadIdx.x;
+    if (t >= ex.world || t == ex.rank) return;
+    uint64_t w = sc->wcur[t];
+    if (w > ex.out[t].w_cap) w = ex.out[t].w_cap;
+    ex.out[t].header[ex.parity][0] = sc->part_start[t + 1] - sc->part_start[t];
+    ex.out[t].header[ex.parity][1] = w;
+    __threadfence_system();
+    *(volatile unsigned long long *)ex.out[t].flag[ex.parity] = ex.seq;
+}
+// imported migrants become records of their own and members of the new population; prefill: they are infected for the
+// next generation here (their slot in the new population is known), like the children k_resample_pos draws
+__global__ void __launch_bounds__(EXP_TPB, 4) k_ex_import_fused(DevState *st, ExArgs ex, const ExScratch *sc, int prefill) {
+    __shared__ uint4 s_items[EXP_TPB];
+    __shared__ uint32_t s_clcnt[2];
+    __shared__ uint32_t s_pref[EXP_TPB + 1], s_src[EXP_TPB], s_org[EXP_TPB];
+    __shared__ uint32_t s_wr[EXP_TPB / 32], s_ww[EXP_TPB / 32];
+    __shared__ unsigned long long s_rbase, s_wbase;
+    const uint64_t M = sc->n_imp;
+    const uint32_t P = ex.n_providers, par = ex.parity;
+    const uint64_t cap = st->cap_inf;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int pi0 = st->specs[0].repro;
+    InfectCtx ic;
+    ic.H32 = (uint32_t)st->H;
+    ic.thr = ic.H32 ? (uint32_t)(-ic.H32) % ic.H32 : 0u;
+    ic.gen = st->generation + 1;
+    ic.key = philox_key(st->seed, st->compartment);
+    ic.host_id = st->host_id;
+    ic.hsum = st->hsum[st->hsum_parity ^ 1u];
+    ic.keep = l2_keep_policy();
+    ic.stream = l2_stream_policy();
+    if (tid == 0) s_clcnt[0] = 0u;
+    for (uint64_t c0 = (uint64_t)blockIdx.x * EXP_TPB; c0 < M; c0 += (uint64_t)gridDim.x * EXP_TPB) {
+        const uint64_t idx = c0 + tid;
+        const bool active = idx < M;
+        uint32_t o = 0;
+        uint64_t k = 0, slot = 0;
+        uint4 meta = make_uint4(MIG_WILD_META, 0u, 0u, 0u);
+        if (active) {
+            o = ex_find(sc->imp_start, ex.world, idx);
+            k = idx - sc->imp_start[o];
+            slot = sc->in_start[o] + k;
+            meta = __ldcg(ex.in[o].meta[par] + k);
+        }
+        const uint32_t is_rec = (active && meta.x != MIG_WILD_META) ? 1u : 0u;
+        uint32_t words = is_rec ? meta.y : 0u;  // arena words: the base list (the delta entries go into the head)
+        const uint32_t nd = is_rec ? (meta.z & 0xFFu) : 0u;
+        if (is_rec && ((uint64_t)meta.x + words + nd > ex.in[o].w_cap || nd > HEAD_DELTA)) { raise(st, DE_REPLAY); words = 0u; meta.y = 0u; meta.z = 0u; }
+        uint32_t ir = is_rec, iw = words;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, ir, d), z = __shfl_up_sync(0xFFFFFFFFu, iw, d);
+            if (lane >= (uint32_t)d) { ir += y; iw += z; }
+        }
+        __syncthreads();
+        if (lane == 31) { s_wr[wid] = ir; s_ww[wid] = iw; }
+        __syncthreads();
+        uint32_t rpre = ir - is_rec, wpre = iw - words, rtot = 0, wtot = 0;
+#pragma unroll
+        for (int w = 0; w < EXP_TPB / 32; w++) {
+            if (w < (int)wid) { rpre += s_wr[w]; wpre += s_ww[w]; }
+            rtot += s_wr[w];
+            wtot += s_ww[w];
+        }
+        if (tid == 0) {  // records and arena words of the round: one reservation each
+            unsigned long long rb = rtot ? atomicAdd(&st->n_hap, (unsigned long long)rtot) : 0ull;
+            unsigned long long wb = wtot ? atomicAdd(&st->arena_top, (unsigned long long)wtot) : 0ull;
+            if (rb + rtot > st->cap_hap) { raise(st, DE_HAP_CAPACITY); rb = ~0ull; }
+            if (wb + wtot > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); rb = ~0ull; }
+            s_rbase = rb;
+            s_wbase = wb;
+        }
+        __syncthreads();
+        const bool room = s_rbase != ~0ull;
+        const unsigned long long wbase = s_wbase;
+        s_pref[tid] = wpre;
+        if (tid == 0) s_pref[EXP_TPB] = wtot;
+        s_src[tid] = meta.x;
+        s_org[tid] = o;
+        uint32_t id = 0;
+        if (is_rec && room) {
+            id = (uint32_t)(s_rbase + rpre);
+            for (uint32_t p = 0; p < P; p++) set_fitness(st, p, id, __ldcg(ex.in[o].raw[par] + k * P + p));
+            HapHead hd;
+            hd.off = wbase + wpre;
+            hd.len = meta.y;
+            hd.nd_mlen = meta.z;
+            hd.raw0 = P ? st->h_raw[0][id] : 1.0;
+            hd.fit0 = P ? st->h_fit[0][id] : 1.0;
+            const uint32_t *dsrc = ex.in[o].entries[par] + meta.x + meta.y;  // the delta entries follow the base list
+            const uint32_t ndh = meta.z & 0xFFu;
+#pragma unroll
+            for (uint32_t q = 0; q < HEAD_DELTA; q++) hd.d[q] = q < ndh ? __ldcg(dsrc + q) : 0xFFFFFFFFu;
+            st->head[id] = hd;
+        }
+        uint32_t h = 0, nm = 0;
+        if (active && room && slot < cap) {
+            const double fit = pi0 >= 0 ? st->h_fit[pi0][id] : 1.0;
+            st->hap_id_next[slot] = id;
+            st->pop_fit_next[slot] = fit;  // the mapped reproductive fitness travels with the infectant from here on (vl_fused.cuh)
+            if (prefill) infect_draw(st, ic, slot, fit, h, nm);
+        }
+        __syncthreads();
+        if (room) {  // the round's base lists into the arena words just reserved: consecutive stores over the whole CTA
+            uint32_t *__restrict__ out = st->arena + wbase;
+            for (uint32_t g0 = tid; g0 < wtot; g0 += 4 * EXP_TPB) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t g = g0 + u * EXP_TPB;
+                    if (g < wtot) {
+                        const uint32_t j = ex_owner(s_pref, g), r = g - s_pref[j];
+                        v[u] = __ldcg(ex.in[s_org[j]].entries[par] + s_src[j] + r);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (g0 + u * EXP_TPB < wtot) out[g0 + u * EXP_TPB] = v[u];
+            }
+        }
+        if (prefill) {  // (one item per thread and round: the list cannot overflow)
+            CtaList cl{s_items, s_clcnt};
+            cl_push(cl, nm != 0u, make_uint4((uint32_t)slot, nm, h, id));
+            cl_flush(st, cl, nullptr, 0ull);
+        }
+    }
 }
 
 // ---- one compartment sharded over the ranks ----------------------------------------------------

@@ -265,11 +265,15 @@ static_assert(RANK_WORDS % RT_TPB == 0, "every thread owns RANK_WORDS / RT_TPB c
 struct ResamplePosArgs {
     uint32_t n_parts;
     uint32_t salt[MAX_PARTS];
-    uint32_t *dst[MAX_PARTS];    // nullptr = the population being assembled (hap_id_next, pop_fit_next)
-    double *dst_fit[MAX_PARTS];  // mapped fitness of the drawn parents (may be nullptr when dst is a detached buffer)
+    uint32_t *dst[MAX_PARTS];    // detached id buffer of every part but the own one
+    double *dst_fit[MAX_PARTS];  // mapped fitness of the drawn parents (may be nullptr)
+    int own_part;                // the part that goes straight into the population being assembled (hap_id_next, pop_fit_next), or -1
+    const uint64_t *own_off;     // device: first slot of that part in the new population (nullptr = 0)
+    int predict_ids;             // PREFILL: the next kernel to touch the record table is k_mutate, so the ids of the staged
+                                 // children's new records are known and go into the population here (else k_mutate patches it)
 };
 // PREFILL (only when the caller enqueues the next generation right behind this one): the children written to the
-// population (single part, dst == nullptr) get their hosts and mutation counts for the NEXT generation right here (infect_draw with generation + 1): host_id[], the other hsum buffer (cleared by
+// population (the own part) get their hosts and mutation counts for the NEXT generation right here (infect_draw with generation + 1): host_id[], the other hsum buffer (cleared by
 // k_offspring_sum of this generation) and the worklist are ready when the next generation begins, which then starts with
 // k_mutate.  The children are as they would be without it; k_infect_sum makes the same draws from the same streams.
 template <bool PREFILL>
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
     const uint32_t gen = st->generation;
     const uint64_t stride = st->tile_stride;
     const uint64_t l2s = l2_stream_policy();
+    const uint64_t own_off = ra.own_off ? *ra.own_off : 0ull;
     InfectCtx ictx;
     CtaList cl{s_items_dyn, s_clcnt};
     if (PREFILL) {
@@ -456,8 +461,9 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
                 }
             }
             const uint64_t salt = (uint64_t)ra.salt[part] << 48;
-            uint32_t *__restrict__ dst = ra.dst[part] ? ra.dst[part] : st->hap_id_next;
-            double *__restrict__ dstf = ra.dst[part] ? ra.dst_fit[part] : st->pop_fit_next;
+            const bool own = (int)part == ra.own_part;
+            uint32_t *__restrict__ dst = own ? st->hap_id_next + own_off : ra.dst[part];
+            double *__restrict__ dstf = own ? st->pop_fit_next + own_off : ra.dst_fit[part];
             const uint64_t q = (base >> 2) + (e - before);
             uint4 blk = make_uint4(0u, 0u, 0u, 0u);
             if (live) blk = philox_block(key, q | salt, gen, PH_RESAMPLE, 0);
@@ -490,18 +496,16 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
                     const double fit = s_fit[slot];
                     st_u32_hint(&dst[s], hap, l2s);
                     if (dstf) st_f64_hint(&dstf[s], fit, l2s);
-                    if (PREFILL) infect_draw(st, ictx, s, fit, h, nm);
+                    if (PREFILL && own) infect_draw(st, ictx, own_off + s, fit, h, nm);
                 }
-                if (PREFILL) cl_push(cl, nm != 0u, make_uint4((uint32_t)s, nm, h, hap));
+                if (PREFILL) cl_push(cl, nm != 0u, make_uint4((uint32_t)(own_off + s), nm, h, hap));
             }
         }
-        // (the staged children mutate at the start of the next generation, which follows at once (vl_run): their new
-        // records' ids are known — record count + worklist position — and go into the population here)
         // (the staged children mutate at the start of the next generation, which follows at once (vl_run): their new
         // records' ids are known — record count + worklist position — and go into the population here.  Flushing after every
         // tile keeps the worklist in tile order; holding the items back until the list is half full was measured: slower,
         // 0.97 against 0.93 ms per generation, the mutate kernel included)
-        if (PREFILL) cl_flush(st, cl, st->hap_id_next, st->n_hap);
+        if (PREFILL) cl_flush(st, cl, ra.predict_ids ? st->hap_id_next : nullptr, st->n_hap);
     }
 }
 

@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(TPB) k_mutcount_fast(DevState *st) {
 // flattened into a fresh base list (HapHead, vl_state.cuh).  Raw fitness of every provider incrementally:
 // raw(parent) * fold(acc * T[pos,to] / T[pos,from]) (src/core/fitness/table.rs:65-68) [* epistatic update].
 // patch_records: 1 = the infectant's CSR record is patched in place, 2 = its bucket-partitioned record is (host map not
-// built yet), 0 = no records exist, 3 = device-resident generation (vl_fused.cuh): items are (infectant, n_mut, host,
+// built yet), 0 = no records exist, 3 / 4 = device-resident generation (vl_fused.cuh): items are (infectant, n_mut, host,
 // parent); the carried fitness of the infectant is replaced and added to its host's sum.
 constexpr uint32_t MUT_LOCAL = HEAD_DELTA;              // events up to this many sites keep their scratch in shared memory
 constexpr uint32_t MUT_STRIDE = 3 * HEAD_DELTA + 2 * MUT_LOCAL + 1;  // per thread: parent delta (8), merged delta (16), change words (8), new entries (8); odd stride
@@ -917,7 +917,10 @@ __device__ __forceinline__ uint32_t warp_flatten(const uint32_t *pe, uint32_t pl
 }
 
 // parent_in_item: the worklist items carry the infectant's current haplotype id in .w
-__global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item) {
+// range: 0 = the whole worklist.  1 = items [0, mut_own) AHEAD of their generation: the population they belong to is still
+// being assembled (hap_id_next / pop_fit_next / the other hsum buffer, generation + 1), their ids were reserved
+// (mut_own_base), other kernels create records meanwhile.  2 = the items behind those, once the generation has begun.
+__global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item, int range) {
     extern __shared__ uint32_t s_mut_dyn[];
     __shared__ double s_subst[16];
     uint32_t *s_scratch = s_mut_dyn;
@@ -936,14 +939,20 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
     }
     __syncthreads();
     auto wt_at = [&](uint32_t site) -> uint32_t { return wt_words ? (s_wt[site >> 4] >> ((site & 15u) * 2u)) & 3u : (uint32_t)wt[site]; };
-    const uint32_t n_list = st->n_mut_list;
+    const uint32_t w_first = range == 2 ? st->mut_own : 0u;
+    const uint32_t n_list = (range == 1 ? st->mut_own : st->n_mut_list) - w_first;  // items of this launch
+    const uint4 *__restrict__ mut_list = st->mut_list + w_first;
+    const uint32_t gen = st->generation + (range == 1 ? 1u : 0u);
+    uint32_t *pop_hap = range == 1 ? st->hap_id_next : st->hap_id;
+    double *pop_fit = range == 1 ? st->pop_fit_next : st->pop_fit;
+    double *hsum = st->hsum[range == 1 ? st->hsum_parity ^ 1u : st->hsum_parity];
     const uint32_t span = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31;
     // Every warp walks the worklist 32 items at a time.  Same-address atomics are served one after the other by L2, so
     // none is spent per record or per 32 records: a record's id is its worklist position behind the record count the
     // kernel started with (published by the last CTA to leave), and arena words (needed only by the records that are
     // flattened) come out of a chunk the warp reserves for all the rounds it still has to do.
-    const unsigned long long id_base = st->n_hap;
+    const unsigned long long id_base = range == 1 ? st->mut_own_base : st->n_hap;
     unsigned long long chunk_off = 0;
     uint32_t chunk_left = 0;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_list; base += span) {
@@ -953,11 +962,11 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
         HapHead ph;
         ph.off = 0; ph.len = 0; ph.nd_mlen = 0; ph.raw0 = 1.0; ph.fit0 = 1.0;
         if (ok) {
-            const uint4 item = st->mut_list[w];
+            const uint4 item = mut_list[w];
             i = item.x;
             nm = item.y;
             tpos = item.z;
-            pid = parent_in_item ? item.w : st->hap_id[i];
+            pid = parent_in_item ? item.w : pop_hap[i];
             ph = st->head[pid];  // ONE 64-byte line: base list, inline delta, fitness of the parent
         }
         const uint32_t nd = head_nd(ph), plen = ph.len, mlen = head_mlen(ph);
@@ -1017,7 +1026,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
                     chs[k] = (site << 8) | (e != 0xFFFFFFFFu ? 0x80u : 0u) | (cur << 4) | to;
                 }
             } else {
-                Philox g(st->seed, st->compartment, st->generation, PH_MUTATE, i);
+                Philox g(st->seed, st->compartment, gen, PH_MUTATE, i);
                 for (uint32_t k = 0; k < nm; k++) chs[k] = (uint32_t)g.below(L);
                 if (nm <= 16) {
                     for (uint32_t a = 1; a < nm; a++) {
@@ -1118,15 +1127,17 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
             for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = k < ndm ? dm[k] : 0xFFFFFFFFu;
         }
         st->head[new_id] = nh;
-        if (patch_records == 3) {
-            // device-resident generation (vl_fused.cuh): items carry the host in .z.  The pass that staged the items has
-            // already written the new record's id into the population (ids are worklist positions); the new haplotype's
-            // mapped fitness replaces the infectant's carried value and joins its host's sum (that pass left it out).
-            st->pop_fit[i] = fit_repro;
-            if (tpos != NONE32 && fit_repro != 0.0) red_add_f64_hint(&st->hsum[st->hsum_parity][tpos], fit_repro, l2_keep_policy());
+        if (patch_records >= 3) {
+            // device-resident generation (vl_fused.cuh): items carry the host in .z.  The new haplotype's mapped fitness
+            // replaces the infectant's carried value and joins its host's sum (the pass that staged the item left it out).
+            // 3: that pass has already written the new record's id into the population (ids are worklist positions);
+            // 4: records were created between that pass and this kernel (imported migrants): the population is patched here.
+            pop_fit[i] = fit_repro;
+            if (tpos != NONE32 && fit_repro != 0.0) red_add_f64_hint(&hsum[tpos], fit_repro, l2_keep_policy());
+            if (patch_records == 4) pop_hap[i] = new_id;
             continue;
         }
-        st->hap_id[i] = new_id;
+        pop_hap[i] = new_id;
         if (patch_records == 2) {
             if (tpos != NONE32) st->tmp_rec[tpos].y = new_id;  // the bucket-partitioned record, not yet sorted
         } else if (patch_records) {
@@ -1138,6 +1149,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
             }
         }
     }
+    if (range == 1) return;  // (the ids were reserved up front)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();

@@ -220,6 +220,10 @@ class PeerExchange:
     def step(self):
         self.handle.step()
 
+    def run(self, n_generations: int):
+        """n generations enqueued back to back (vl_exchange_run): the ranks meet on the device only."""
+        self.handle.run(n_generations)
+
     def close(self):
         self.sim.synchronize()
         dist.barrier()

@@ -77,6 +77,7 @@ SIGNATURES = {
     "vl_exchange_recv_buffer": (C.c_int, [_vp, C.POINTER(_vp), u64p]),
     "vl_exchange_connect": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "vl_exchange_step": (C.c_int, [_vp]),
+    "vl_exchange_run": (C.c_int, [_vp, C.c_uint64]),
     "vl_exchange_push": (C.c_int, [_vp]),
     "vl_exchange_pull": (C.c_int, [_vp]),
     "vl_exchange_destroy": (C.c_int, [_vp]),
@@ -536,6 +537,9 @@ class PeerExchangeHandle:
 
     def step(self):
         self.sim._check(self.sim.lib.vl_exchange_step(self.ptr))
+
+    def run(self, n_generations: int):
+        self.sim._check(self.sim.lib.vl_exchange_run(self.ptr, int(n_generations)))
 
     def begin(self):
         self.sim._check(self.sim.lib.vl_exchange_begin(self.ptr))
