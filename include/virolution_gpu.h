@@ -279,6 +279,9 @@ int vl_exchange_step(vl_exchange *ex);
 /* n generations of vl_exchange_step enqueued back to back; every generation but the last also prepares the next one's
  * infection while it draws and imports (what vl_run does for a single device).  Same populations as n vl_exchange_step calls. */
 int vl_exchange_run(vl_exchange *ex, uint64_t n_generations);
+/* A new transfer matrix from the next vl_exchange_push on (the schedule's `transmission` events, src/config/schedule.rs:196-266).
+ * Every entry must be <= the entry the exchange was created with: create it with the entry-wise maximum over the schedule. */
+int vl_exchange_set_transfer(vl_exchange *ex, const double *transfer);
 int vl_exchange_destroy(vl_exchange *ex);
 
 /* ---- measurement hooks (bench.py): CUDA events on the handle's own stream ------------------ */

@@ -329,3 +329,38 @@ def test_exchange_run_equals_steps_and_general_kernels(name):
             e.close()
         for s in sims:
             s.close()
+
+
+def test_exchange_follows_a_transfer_matrix_that_changes():
+    """A `transmission` event of the schedule replaces the matrix mid-run (src/config/schedule.rs:196-266): the peer exchange,
+    created with the entry-wise maximum of the schedule's matrices, against vl_step called with the matrix of each
+    generation.  A matrix with an entry above the creation matrix is refused."""
+    from test_gpu_stochastic import big_singlehost, population_signature
+    from virolution_b200.simulation import PeerExchangeHandle, VirolutionError, step
+    c = big_singlehost(n=100000, mu=1e-4, seed=91)
+    T1 = np.array([[0.9, 0.1], [0.1, 0.9]])
+    T2 = np.array([[0.6, 0.35], [0.4, 0.65]])
+    Tcap = np.maximum(T1, T2)
+    a = [helpers.make_gpu(c, compartment_id=k) for k in range(2)]
+    b = [helpers.make_gpu(c, compartment_id=k) for k in range(2)]
+    ex = [PeerExchangeHandle(b[k], k, 2, Tcap, words_per_migrant=32) for k in range(2)]
+    bufs = [e.recv_buffer() for e in ex]
+    for k in range(2):
+        ex[k].connect(None, [bufs[t] if t != k else 0 for t in range(2)])
+    for T in (T1, T1, T2, T2, T1):
+        step(a, T, rule=0)
+        for e in ex:
+            e.set_transfer(T)
+        for e in ex:
+            e.push()
+        for e in ex:
+            e.pull()
+        for k in range(2):
+            assert a[k].population_len() == b[k].population_len() == int(T[k, 0] * 100000) + int(T[k, 1] * 100000)
+            assert population_signature(a[k]) == population_signature(b[k])
+    with pytest.raises(VirolutionError):
+        ex[0].set_transfer(np.array([[0.95, 0.1], [0.1, 0.9]]))
+    for e in ex:
+        e.close()
+    for s in a + b:
+        s.close()

@@ -1597,7 +1597,8 @@ struct vl_exchange {
     vl_sim *sim = nullptr;
     uint32_t rank = 0, world = 0;
     uint64_t wpm = 0, seq = 0;
-    std::vector<double> T;
+    std::vector<double> T;         // the matrix of the generation being enqueued (vl_exchange_set_transfer)
+    std::vector<double> Tcap;      // the matrix the buffers were sized for (vl_exchange_create): an upper bound of every T, entry by entry
     uint8_t *recv = nullptr;       // my receive buffer (IPC-exported)
     uint64_t recv_bytes = 0;
     void *peer[EX_MAX_WORLD] = {nullptr};
@@ -1729,9 +1730,10 @@ VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const 
     ex->sharded = sharded != 0;
     if (transfer) ex->T.assign(transfer, transfer + (size_t)world * world);
     else ex->T.assign((size_t)world * world, 1.0 / (double)world);
+    ex->Tcap = ex->T;
     const DevState &h = sim->h;
     ex->max_pop = h.max_population;
-    const ExLayout L = ex_layout(world, rank, ex->T.data(), h.max_population, h.n_providers, ex->wpm, ex->sharded);
+    const ExLayout L = ex_layout(world, rank, ex->Tcap.data(), h.max_population, h.n_providers, ex->wpm, ex->sharded);
     ex->recv_bytes = L.bytes;
 #define XCU(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { ex_free(ex); return fail(sim, VL_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); } } while (0)
     XCU(cudaMalloc((void **)&ex->recv, L.bytes));
@@ -1755,7 +1757,7 @@ VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const 
     }
     for (uint32_t t = 0; t < world; t++) {  // one id buffer per target part (my column of T)
         double m = ex->sharded ? (double)shard_cell_capacity(h.max_population, world) + 1.0
-                               : floor(ex->T[(size_t)t * world + rank] * (double)h.max_population) + 2.0;
+                               : floor(ex->Tcap[(size_t)t * world + rank] * (double)h.max_population) + 2.0;
         if (!(m >= 2.0)) m = 2.0;
         XCU(cudaMalloc((void **)&ex->part_ids[t], (uint64_t)m * 4));
         ex->args.part[t] = ex->part_ids[t];
@@ -1809,7 +1811,7 @@ VL_API int vl_exchange_connect(vl_exchange *ex, const void *ipc_handles, void *c
             CU(sim, cudaIpcOpenMemHandle(&ex->peer[t], hd, cudaIpcMemLazyEnablePeerAccess));
             ex->peer_ipc[t] = true;
         }
-        const ExLayout L = ex_layout(ex->world, t, ex->T.data(), h.max_population, h.n_providers, ex->wpm, ex->sharded);
+        const ExLayout L = ex_layout(ex->world, t, ex->Tcap.data(), h.max_population, h.n_providers, ex->wpm, ex->sharded);
         ex_block(ex->args.out[t], (uint8_t *)ex->peer[t], L, ex->rank);
         for (int par = 0; par < 2; par++) {
             ex->args.tot_out[t][par] = (uint64_t *)((uint8_t *)ex->peer[t] + L.tot_off[par]) + ex->rank;
@@ -1817,6 +1819,25 @@ VL_API int vl_exchange_connect(vl_exchange *ex, const void *ipc_handles, void *c
         }
     }
     ex->connected = true;
+    return VL_OK;
+}
+// The schedule resolves a transfer matrix per generation (src/config/schedule.rs:196-266, used at src/runner.rs:382-422).
+// The buffers keep the sizes of the creation matrix, so every entry of the new one must stay at or below it (create the
+// exchange with the entry-wise maximum over the schedule).  Takes effect with the next vl_exchange_push; every rank must
+// set the same matrix for the same generation.
+VL_API int vl_exchange_set_transfer(vl_exchange *ex, const double *transfer) {
+    if (!ex || !transfer) return fail(nullptr, VL_ERR_ARGUMENT, "null argument");
+    vl_sim *sim = ex->sim;
+    ENTER(sim);
+    if (ex->sharded) return fail(sim, VL_ERR_ARGUMENT, "a sharded compartment has no transfer matrix");
+    if (ex->pushed) return fail(sim, VL_ERR_IMPLEMENTATION, "a generation of this exchange is in flight: set the matrix after vl_exchange_pull");
+    const size_t n = (size_t)ex->world * ex->world;
+    for (size_t k = 0; k < n; k++) {
+        if (!(transfer[k] >= 0.0) || !(transfer[k] <= ex->Tcap[k]))
+            return fail(sim, VL_ERR_ARGUMENT, "transfer[%zu][%zu] = %g is outside [0, %g], the entry the exchange was created with", k / ex->world,
+                        k % ex->world, transfer[k], ex->Tcap[k]);
+    }
+    ex->T.assign(transfer, transfer + n);
     return VL_OK;
 }
 VL_API int vl_exchange_destroy(vl_exchange *ex) {

@@ -224,6 +224,12 @@ class PeerExchange:
         """n generations enqueued back to back (vl_exchange_run): the ranks meet on the device only."""
         self.handle.run(n_generations)
 
+    def set_transfer(self, T):
+        """A `transmission` event of the schedule: the matrix of the generations that follow.  The exchange must have been
+        created with the entry-wise maximum of all matrices of the schedule (the buffers are sized once)."""
+        self.T = np.asarray(T, dtype=np.float64)
+        self.handle.set_transfer(self.T)
+
     def close(self):
         self.sim.synchronize()
         dist.barrier()

@@ -78,6 +78,7 @@ SIGNATURES = {
     "vl_exchange_connect": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "vl_exchange_step": (C.c_int, [_vp]),
     "vl_exchange_run": (C.c_int, [_vp, C.c_uint64]),
+    "vl_exchange_set_transfer": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "vl_exchange_push": (C.c_int, [_vp]),
     "vl_exchange_pull": (C.c_int, [_vp]),
     "vl_exchange_destroy": (C.c_int, [_vp]),
@@ -540,6 +541,13 @@ class PeerExchangeHandle:
 
     def run(self, n_generations: int):
         self.sim._check(self.sim.lib.vl_exchange_run(self.ptr, int(n_generations)))
+
+    def set_transfer(self, T):
+        """The matrix of the generations enqueued from now on; entries must not exceed those the handle was created with."""
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        if T.shape != (self.world, self.world):
+            raise ValueError(f"transfer matrix must be {self.world} x {self.world}")
+        self.sim._check(self.sim.lib.vl_exchange_set_transfer(self.ptr, _p(T, C.c_double)))
 
     def begin(self):
         self.sim._check(self.sim.lib.vl_exchange_begin(self.ptr))
