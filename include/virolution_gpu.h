@@ -167,7 +167,10 @@ int vl_run(vl_sim *sim, uint64_t n_generations);
  * device: everything Runner::run does per compartment before the transmission block (runner.rs:382-399). */
 int vl_advance_to_offspring(vl_sim *sim);
 /* one generation over several compartments living in this process.
- * rule: 0 = parallel-build rule (runner.rs:401-416), 1 = serial-build rule (:550-631). */
+ * rule: 0 = parallel-build rule (runner.rs:401-416), 1 = serial-build rule (:550-631).
+ * Failure: VL_ERR_CAPACITY from the size check means no compartment was changed (every new population is checked against
+ * its capacity_infectants before any is installed).  Any other error may leave some compartments one generation ahead of
+ * the others: the handles must then be discarded (vl_destroy), like a Runner whose loop panicked. */
 int vl_step(vl_sim *const *sims, uint32_t n_sims, const double *transfer, int rule);
 int vl_synchronize(vl_sim *sim);
 /* sum over generations of population sizes at generation start since creation/reset. */

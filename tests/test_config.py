@@ -134,3 +134,18 @@ host_model: !SingleHost
     assert (par.mutation_rate, par.recombination_rate, par.host_population_size, par.basic_reproductive_number,
             par.max_population, par.dilution, par.n_hits) == (2e-6, 1e-4, 777, 50.0, 555, 0.5, 3)
     assert par.substitution_matrix[0][2] == 2.0
+
+
+def test_generation_expressions_are_parsed_not_executed():
+    """`eval_int_with_context` semantics of the schedule's generation column (src/config/schedule.rs:250-266): integer
+    arithmetic, `/` truncating, `%` with the dividend's sign, `^` = power; anything else is "Invalid generation"."""
+    from virolution_b200.config import _eval_generation_expr as ev
+    assert ev("x % 10", 20) == 0 and ev("{} % 10", 23) == 3 and ev("(generation - 5) % 7", 12) == 0
+    assert ev("x / 2 - 3", 7) == 0          # 7 / 2 == 3
+    assert ev("-7 / 2", 0) == -3 and ev("-7 % 3", 0) == -1
+    assert ev("2^3 - x", 8) == 0
+    for bad in ("9**9**9**9", "__import__('os').system('true')", "x.real", "1/0", "x % 0", "x if x else 1", "1.5 * x", "[x]", "x == 1", ""):
+        with pytest.raises(ValueError):
+            ev(bad, 3)
+    s = sched([("x % 4", "sample", "10"), ("(x - 1) % 4", "sample", "20")])
+    assert [s.get_sample_size(g) for g in range(6)] == [10, 20, 0, 0, 10, 20]

@@ -88,7 +88,7 @@ def test_runner_outputs(tmp_path, distribution):
         assert sum(int(x[1]) for x in rows[1:]) == sim.population_len()
         assert any(x[0] == "wt" for x in rows[1:])
         assert any("->" in x[0] for x in rows[1:]), "six generations at mu*L = 0.54 must leave mutants"
-        for g in (0, 3, 6):  # sample events: generation % 3 == 0, the generation attribute is the simulation's own counter
+        for g in (0, 6, 12):  # sample events at loop generations 0, 3, 6; labels count every compartment's increment
             srows = list(csv.reader(open(out / "samples" / f"sample_{g}_{c}.csv")))
             assert srows[0] == ["block_id", "compartment_id", "generation", "haplotype", "count"]
             assert sum(int(x[4]) for x in srows[1:]) == 100 and all(x[1] == str(c) and x[2] == str(g) for x in srows[1:])
@@ -97,7 +97,7 @@ def test_runner_outputs(tmp_path, distribution):
     # src/barcode.rs: header + one line per (sample event, compartment)
     barcodes = (out / "samples" / "barcodes.csv").read_text().splitlines()
     assert barcodes[0] == "barcode,experiment,time,replicate,compartment"
-    assert barcodes[1:] == [f"sample_{g}_{c},trial,{g},0,{c}" for g in (0, 3, 6) for c in (0, 1)]
+    assert barcodes[1:] == [f"sample_{g}_{c},trial,{g},0,{c}" for g in (0, 6, 12) for c in (0, 1)]
     r.close()
 
 

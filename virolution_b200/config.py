@@ -203,6 +203,60 @@ class ScheduleRecord:
     value: str
 
 
+def _eval_generation_expr(text: str, generation: int) -> int:
+    """`eval_int_with_context` of the schedule's generation column (src/config/schedule.rs:250-266): integer arithmetic over
+    x / generation / {} with + - * / % ^ and parentheses.  `/` truncates toward zero and `%` takes the sign of the dividend
+    (Rust i64), `^` is the power operator; anything else, a division by zero or a non-integer result is the reference's
+    "Invalid generation" panic.  The expression is parsed, never executed."""
+    bad = ValueError(f"Invalid generation `{text}`.")
+    expr = text.replace("{}", "x").replace("^", "**")
+    if len(expr) > 200:
+        raise bad
+    try:
+        tree = ast.parse(expr.strip(), mode="eval")
+    except SyntaxError:
+        raise bad from None
+
+    def ev(node) -> int:
+        if isinstance(node, ast.Expression):
+            return ev(node.body)
+        if isinstance(node, ast.Constant) and type(node.value) is int:
+            return node.value
+        if isinstance(node, ast.Name) and node.id in ("x", "generation"):
+            return generation
+        if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+            v = ev(node.operand)
+            return -v if isinstance(node.op, ast.USub) else v
+        if isinstance(node, ast.BinOp):
+            a, b = ev(node.left), ev(node.right)
+            if isinstance(node.op, ast.Add):
+                r = a + b
+            elif isinstance(node.op, ast.Sub):
+                r = a - b
+            elif isinstance(node.op, ast.Mult):
+                r = a * b
+            elif isinstance(node.op, (ast.Div, ast.FloorDiv)):
+                if b == 0:
+                    raise bad
+                r = abs(a) // abs(b) * (1 if (a >= 0) == (b >= 0) else -1)
+            elif isinstance(node.op, ast.Mod):
+                if b == 0:
+                    raise bad
+                r = abs(a) % abs(b) * (1 if a >= 0 else -1)
+            elif isinstance(node.op, ast.Pow):
+                if b < 0 or b > 64:
+                    raise bad
+                r = a ** b
+            else:
+                raise bad
+            if not -(1 << 63) <= r < (1 << 63):  # i64 overflow is an evaluation error in the reference
+                raise bad
+            return r
+        raise bad
+
+    return ev(tree)
+
+
 class Schedule:
     """Schedule (src/config/schedule.rs:110-266): first record whose generation matches (literal number, or an
     expression in x / generation / {} that evaluates to 0) and whose event name matches."""
@@ -219,10 +273,7 @@ class Schedule:
         try:
             return int(record.generation) == generation
         except ValueError:
-            expr = record.generation.replace("{}", "x")
-            if not re.fullmatch(r"[0-9x\sgenrationx+\-*/%()]+", expr):
-                raise ValueError(f"Invalid generation `{record.generation}`.")
-            return int(eval(expr, {"__builtins__": {}}, {"x": generation, "generation": generation})) == 0
+            return _eval_generation_expr(record.generation, generation) == 0
 
     def get_event_value(self, event: str, generation: int) -> Optional[str]:
         for r in self.table:

@@ -212,6 +212,7 @@ static int check_device_error(vl_sim *sim) {
     if (e & DE_SAME_BASE) return fail(sim, VL_ERR_REFERENCE_PANIC, "assert_ne!(from, to) in create_descendant (src/core/haplotype.rs:250)");
     if (e & DE_OFFSPRING_RANGE) return fail(sim, VL_ERR_IMPLEMENTATION, "offspring count does not fit 32 bits");
     if (e & DE_REPLAY) return fail(sim, VL_ERR_ARGUMENT, "malformed replay log or index out of range");
+    if (e & DE_PLAN_TIMEOUT) return fail(sim, VL_ERR_CUDA, "the CTAs of the resample plan did not become resident together within 2 s (grid barrier)");
     if (e & DE_EXCHANGE_TIMEOUT) return fail(sim, VL_ERR_CUDA, "migrant exchange timed out: a peer's block did not arrive");
     if (e & DE_TILE_OVERFLOW) return fail(sim, VL_ERR_IMPLEMENTATION, "host tile overflow (> 13 sigma under uniform infection): rerun with VL_FLAG_GENERAL_REPLICATE");
     if (e & DE_BUCKET_OVERFLOW) return fail(sim, VL_ERR_IMPLEMENTATION, "host bucket overflow (12 sigma event): rerun with VL_FLAG_NO_BUCKETS");
@@ -2119,11 +2120,26 @@ VL_API int vl_step(vl_sim *const *sims, uint32_t C, const double *T, int rule) {
     }
     if (rc != VL_OK) { cleanup(); return rc; }
     for (vl_pop *p : parts) finalize_pop(p);
+    // every compartment's new population must fit before ANY is installed: a step either happens for all compartments
+    // or (for this foreseeable failure) for none
+    for (uint32_t t = 0; t < C; t++) {
+        uint64_t total = 0;
+        for (uint32_t o = 0; o < C; o++) total += parts[(size_t)t * C + o] ? parts[(size_t)t * C + o]->n : 0;
+        if (total > sims[t]->h.cap_inf) {
+            cleanup();
+            return fail(s0, VL_ERR_CAPACITY, "compartment %u would receive %llu infectants, its capacity_infectants is %llu; no population was replaced", t,
+                        (unsigned long long)total, (unsigned long long)sims[t]->h.cap_inf);
+        }
+    }
     for (uint32_t t = 0; t < C; t++) {
         ON(t);
         rc = vl_set_population(sims[t], &parts[(size_t)t * C], C);
-        for (uint32_t o = 0; o < C; o++) parts[(size_t)t * C + o] = nullptr;
-        if (rc != VL_OK) { if (t != 0) fail(s0, rc, "%s", sims[t]->err); cleanup(); return rc; }
+        if (rc != VL_OK) {  // (a CUDA or record-capacity failure half way: compartments below t hold the new generation, the others the old one)
+            fail(s0, rc, "installing compartment %u failed, the handles of this step are no longer consistent: %s", t, sims[t]->err);
+            cleanup();
+            return rc;
+        }
+        for (uint32_t o = 0; o < C; o++) parts[(size_t)t * C + o] = nullptr;  // consumed by vl_set_population
     }
 #undef ON
     return VL_OK;

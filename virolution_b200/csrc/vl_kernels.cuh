@@ -1715,7 +1715,14 @@ __device__ __forceinline__ void plan_grid_barrier(DevState *st, uint32_t &epoch)
         atomicAdd(&st->plan_sync, 1u);
         const uint32_t target = epoch * gridDim.x;
         uint32_t seen;
-        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&st->plan_sync) : "memory"); } while (seen < target);
+        // The grid is at most 2 * PLAN_CTAS CTAs, far below what one B200 holds, but residency is not a guarantee (another
+        // stream may own the SMs for a while): a barrier nobody else reaches within two seconds is reported, not waited out.
+        const unsigned long long t0 = vl_globaltimer();
+        uint32_t polls = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&st->plan_sync) : "memory");
+            if (seen < target && (++polls & 1023u) == 0u && vl_globaltimer() - t0 > 2000000000ull) { raise(st, DE_PLAN_TIMEOUT); break; }
+        } while (seen < target);
     }
     __syncthreads();
 }

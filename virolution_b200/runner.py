@@ -117,7 +117,11 @@ class GpuRunner:
         for c, sim in enumerate(self.sims):
             n = sim.population_len()
             idx = rng.choice(n, size=min(sample_size, n), replace=False) if n else np.zeros(0, dtype=np.int64)
-            g = sim.get_generation()
+            # The reference's compartments share ONE generation attribute and each of them increments it
+            # (src/runner.rs:72,271,382-384, src/providers/generation.rs:31-33): after i loop iterations it reads
+            # i * n_compartments, and that is what file names, rows and barcodes carry.  Every handle here
+            # counts its own generations, so the label is rebuilt from it.
+            g = sim.get_generation() * len(self.sims)
             barcode = f"sample_{g}_{c}"
             if self.sampling_format == "csv":
                 # CsvSampleWriter::write (:228-266): one row per distinct haplotype of the sample
