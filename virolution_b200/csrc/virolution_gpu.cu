@@ -550,7 +550,8 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CCU(cudaFuncSetAttribute(k_plan_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CCU(cudaFuncSetAttribute(k_host_sum_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
     CCU(cudaFuncSetAttribute(k_mutate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
-    CCU(cudaFuncSetAttribute(k_resample_pos<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
+    CCU(cudaFuncSetAttribute((k_resample_pos<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
+    CCU(cudaFuncSetAttribute((k_resample_pos<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute(k_ex_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_SMEM_BYTES));
     sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
@@ -933,8 +934,12 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
             if ((int)k != rt.own_part && !rt.dst[k]) return fail(sim, VL_ERR_IMPLEMENTATION, "part %u has no destination", k);
         if (po && po->between) TRY(po->between());
         const unsigned rg = (unsigned)std::min<uint64_t>(tile_bound(sim), (uint64_t)sim->n_sms * 8);
-        if (po && po->prefill && rt.own_part >= 0) LAUNCH(sim, k_resample_pos<true>, rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
-        else LAUNCH(sim, k_resample_pos<false>, rg, RT_TPB, 0, sim->d, rt);
+        const bool single = n == 1 && rt.own_part == 0 && !rt.own_off;  // vl_run: the one part is the new population
+        const bool prefill = po && po->prefill && rt.own_part >= 0;
+        if (prefill && single) LAUNCH(sim, (k_resample_pos<true, false>), rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
+        else if (prefill) LAUNCH(sim, (k_resample_pos<true, true>), rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
+        else if (single) LAUNCH(sim, (k_resample_pos<false, false>), rg, RT_TPB, 0, sim->d, rt);
+        else LAUNCH(sim, (k_resample_pos<false, true>), rg, RT_TPB, 0, sim->d, rt);
         return VL_OK;
     }
     LAUNCH(sim, k_resample, grid_resample(sim), TPB, 0, sim->d, ra, dst64, mode);
@@ -1705,7 +1710,7 @@ static void preload_exchange_kernels() {
             (const void *)k_zero_words, (const void *)k_begin_generation_fused, (const void *)k_zero_hsum_current,
             (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate,
             (const void *)k_offspring_sum<false>, (const void *)k_offspring_sum<true>, (const void *)k_plan_resample,
-            (const void *)k_resample_pos<false>, (const void *)k_resample_pos<true>, (const void *)k_swap_population_fused,
+            (const void *)k_resample_pos<false, true>, (const void *)k_resample_pos<true, true>, (const void *)k_resample_pos<false, false>, (const void *)k_resample_pos<true, false>, (const void *)k_swap_population_fused,
             (const void *)k_ex_sizes, (const void *)k_ex_wait_sizes, (const void *)k_ex_export, (const void *)k_ex_publish_fused,
             (const void *)k_ex_wait, (const void *)k_ex_import_fused, (const void *)k_ex_own_items, (const void *)k_shard_publish_total, (const void *)k_shard_split,
             (const void *)k_ex_out_starts, (const void *)k_ex_lens, (const void *)k_ex_copy, (const void *)k_ex_stream, (const void *)k_ex_publish,

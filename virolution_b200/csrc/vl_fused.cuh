@@ -276,7 +276,8 @@ struct ResamplePosArgs {
 // population (the own part) get their hosts and mutation counts for the NEXT generation right here (infect_draw with generation + 1): host_id[], the other hsum buffer (cleared by
 // k_offspring_sum of this generation) and the worklist are ready when the next generation begins, which then starts with
 // k_mutate.  The children are as they would be without it; k_infect_sum makes the same draws from the same streams.
-template <bool PREFILL>
+// MULTI = false: one part, the whole new population (vl_run); nothing about parts is computed or kept in registers.
+template <bool PREFILL, bool MULTI>
 __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, ResamplePosArgs ra) {
     extern __shared__ uint4 s_items_dyn[];      // PREFILL: CL_CAP staged worklist items
     __shared__ uint32_t s_clcnt[2];
@@ -301,7 +302,8 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
     const uint32_t gen = st->generation;
     const uint64_t stride = st->tile_stride;
     const uint64_t l2s = l2_stream_policy();
-    const uint64_t own_off = ra.own_off ? *ra.own_off : 0ull;
+    const uint64_t own_off = MULTI && ra.own_off ? *ra.own_off : 0ull;
+    const uint32_t n_parts = MULTI ? ra.n_parts : 1u;
     InfectCtx ictx;
     CtaList cl{s_items_dyn, s_clcnt};
     if (PREFILL) {
@@ -318,15 +320,15 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
     for (uint64_t tile = blockIdx.x; tile < nt; tile += gridDim.x) {
         uint64_t any = 0;
         __syncthreads();  // (a tile without draws is left early: nobody may still be reading the shared arrays)
-        if (ra.n_parts == 1) {
+        if (n_parts == 1) {
             any = st->tile_cnt[tile];
         } else {
-            if (tid < ra.n_parts) {
+            if (tid < n_parts) {
                 s_pcnt[tid] = st->tile_cnt[tid * stride + tile];
                 s_pbase[tid] = st->tile_base[tid * stride + tile];
             }
             __syncthreads();
-            for (uint32_t p = 0; p < ra.n_parts; p++) any |= s_pcnt[p];
+            for (uint32_t p = 0; p < n_parts; p++) any |= s_pcnt[p];
         }
         const uint64_t tsum = st->tile_sum[tile];
         const uint64_t tbase1 = st->tile_base[tile];  // (single part; asked for with the other descriptors)
@@ -438,8 +440,8 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
         }
         // ---- draws of every part: output slots [base, base + c), four per Philox block (as k_resample)
         uint32_t blocks_total = 0;
-        if (ra.n_parts > 1) {
-            for (uint32_t p = 0; p < ra.n_parts; p++) {
+        if (n_parts > 1) {
+            for (uint32_t p = 0; p < n_parts; p++) {
                 const uint64_t c = s_pcnt[p], b = s_pbase[p];
                 blocks_total += c ? (uint32_t)(((b + c - 1) >> 2) - (b >> 2) + 1) : 0u;
             }
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
             const bool live = e < blocks_total;
             uint32_t part = 0, before = 0;
             uint64_t c = any, base = tbase1;
-            if (live && ra.n_parts > 1) {
+            if (live && n_parts > 1) {
                 for (;; part++) {
                     c = s_pcnt[part];
                     base = s_pbase[part];
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
                 }
             }
             const uint64_t salt = (uint64_t)ra.salt[part] << 48;
-            const bool own = (int)part == ra.own_part;
+            const bool own = !MULTI || (int)part == ra.own_part;
             uint32_t *__restrict__ dst = own ? st->hap_id_next + own_off : ra.dst[part];
             double *__restrict__ dstf = own ? st->pop_fit_next + own_off : ra.dst_fit[part];
             const uint64_t q = (base >> 2) + (e - before);

@@ -941,11 +941,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
     auto wt_at = [&](uint32_t site) -> uint32_t { return wt_words ? (s_wt[site >> 4] >> ((site & 15u) * 2u)) & 3u : (uint32_t)wt[site]; };
     const uint32_t w_first = range == 2 ? st->mut_own : 0u;
     const uint32_t n_list = (range == 1 ? st->mut_own : st->n_mut_list) - w_first;  // items of this launch
-    const uint4 *__restrict__ mut_list = st->mut_list + w_first;
-    const uint32_t gen = st->generation + (range == 1 ? 1u : 0u);
-    uint32_t *pop_hap = range == 1 ? st->hap_id_next : st->hap_id;
-    double *pop_fit = range == 1 ? st->pop_fit_next : st->pop_fit;
-    double *hsum = st->hsum[range == 1 ? st->hsum_parity ^ 1u : st->hsum_parity];
+    const bool ahead = range == 1;  // (the arrays of the population are picked where they are used: nothing more to keep in registers)
     const uint32_t span = gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31;
     // Every warp walks the worklist 32 items at a time.  Same-address atomics are served one after the other by L2, so
@@ -962,11 +958,11 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
         HapHead ph;
         ph.off = 0; ph.len = 0; ph.nd_mlen = 0; ph.raw0 = 1.0; ph.fit0 = 1.0;
         if (ok) {
-            const uint4 item = mut_list[w];
+            const uint4 item = st->mut_list[w_first + w];
             i = item.x;
             nm = item.y;
             tpos = item.z;
-            pid = parent_in_item ? item.w : pop_hap[i];
+            pid = parent_in_item ? item.w : (ahead ? st->hap_id_next : st->hap_id)[i];
             ph = st->head[pid];  // ONE 64-byte line: base list, inline delta, fitness of the parent
         }
         const uint32_t nd = head_nd(ph), plen = ph.len, mlen = head_mlen(ph);
@@ -1026,7 +1022,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
                     chs[k] = (site << 8) | (e != 0xFFFFFFFFu ? 0x80u : 0u) | (cur << 4) | to;
                 }
             } else {
-                Philox g(st->seed, st->compartment, gen, PH_MUTATE, i);
+                Philox g(st->seed, st->compartment, st->generation + (ahead ? 1u : 0u), PH_MUTATE, i);
                 for (uint32_t k = 0; k < nm; k++) chs[k] = (uint32_t)g.below(L);
                 if (nm <= 16) {
                     for (uint32_t a = 1; a < nm; a++) {
@@ -1132,12 +1128,12 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
             // replaces the infectant's carried value and joins its host's sum (the pass that staged the item left it out).
             // 3: that pass has already written the new record's id into the population (ids are worklist positions);
             // 4: records were created between that pass and this kernel (imported migrants): the population is patched here.
-            pop_fit[i] = fit_repro;
-            if (tpos != NONE32 && fit_repro != 0.0) red_add_f64_hint(&hsum[tpos], fit_repro, l2_keep_policy());
-            if (patch_records == 4) pop_hap[i] = new_id;
+            (ahead ? st->pop_fit_next : st->pop_fit)[i] = fit_repro;
+            if (tpos != NONE32 && fit_repro != 0.0) red_add_f64_hint(&st->hsum[ahead ? st->hsum_parity ^ 1u : st->hsum_parity][tpos], fit_repro, l2_keep_policy());
+            if (patch_records == 4) (ahead ? st->hap_id_next : st->hap_id)[i] = new_id;
             continue;
         }
-        pop_hap[i] = new_id;
+        st->hap_id[i] = new_id;
         if (patch_records == 2) {
             if (tpos != NONE32) st->tmp_rec[tpos].y = new_id;  // the bucket-partitioned record, not yet sorted
         } else if (patch_records) {
