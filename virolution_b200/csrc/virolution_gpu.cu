@@ -1711,7 +1711,7 @@ static void preload_exchange_kernels() {
             (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate,
             (const void *)k_offspring_sum<false>, (const void *)k_offspring_sum<true>, (const void *)k_plan_resample,
             (const void *)k_resample_pos<false, true>, (const void *)k_resample_pos<true, true>, (const void *)k_resample_pos<false, false>, (const void *)k_resample_pos<true, false>, (const void *)k_swap_population_fused,
-            (const void *)k_ex_sizes, (const void *)k_ex_wait_sizes, (const void *)k_ex_export, (const void *)k_ex_publish_fused,
+            (const void *)k_ex_sizes, (const void *)k_ex_export,
             (const void *)k_ex_wait, (const void *)k_ex_import_fused, (const void *)k_ex_own_items, (const void *)k_shard_publish_total, (const void *)k_shard_split,
             (const void *)k_ex_out_starts, (const void *)k_ex_lens, (const void *)k_ex_copy, (const void *)k_ex_stream, (const void *)k_ex_publish,
             (const void *)k_ex_in_starts, (const void *)k_ex_in_words, (const void *)k_ex_reserve, (const void *)k_ex_import, (const void *)k_ex_own,
@@ -1908,8 +1908,7 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
         po.prefill = ex->prefill_step;
         po.predict_ids = false;  // the imported migrants become records before the next k_mutate runs
         po.between = [=]() -> int {
-            LAUNCH(sim, k_ex_sizes, 1, 32, 0, sim->d, a, sc);
-            LAUNCH(sim, k_ex_wait_sizes, 1, 32, 0, sim->d, a, sc, 20ull * 1000000000ull);
+            LAUNCH(sim, k_ex_sizes, 1, 32, 0, sim->d, a, sc, 20ull * 1000000000ull);
             return VL_OK;
         };
     }
@@ -1935,12 +1934,10 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
             {
                 StreamScope on_side(sim, ex->side);
                 LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
-                LAUNCH(sim, k_ex_publish_fused, 1, 32, 0, sim->d, a, (const ExScratch *)sc);
             }
             LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(sim->h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 4, 1, 1);
         } else {
             LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
-            LAUNCH(sim, k_ex_publish_fused, 1, 32, 0, sim->d, a, (const ExScratch *)sc);
         }
         ex->pushed = true;
         CU(sim, cudaGetLastError());
@@ -1977,8 +1974,7 @@ VL_API int vl_exchange_pull(vl_exchange *ex) {
         const unsigned ig = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (ex->m_in_bound + EXP_TPB - 1) / EXP_TPB), (uint64_t)sim->n_sms * 4);
         {
             StreamScope on_side(sim, ex->overlap_step ? ex->side : sim->stream);
-            LAUNCH(sim, k_ex_wait, 1, 32, 0, sim->d, a, 20ull * 1000000000ull);
-            LAUNCH(sim, k_ex_import_fused, ig, EXP_TPB, 0, sim->d, a, (const ExScratch *)sc, ex->prefill_step ? 1 : 0);
+            LAUNCH(sim, k_ex_import_fused, ig, EXP_TPB, 0, sim->d, a, (const ExScratch *)sc, ex->prefill_step ? 1 : 0, 20ull * 1000000000ull);
         }
         if (ex->overlap_step) {
             CU(sim, cudaEventRecord(ex->ev_imported, ex->side));

@@ -62,6 +62,7 @@ struct ExScratch {
     uint64_t reserve[2];
     unsigned long long wcur[EX_MAX_WORLD];  // fast path: entry words written so far into every target's block
     uint64_t own_off;                       // fast path: first slot of my own part in the new population (= in_start[rank])
+    unsigned int exp_done;                  // fast path: CTAs of k_ex_export that have left (the last one publishes the blocks)
 };
 
 __device__ __forceinline__ uint32_t ex_find(const uint64_t *start, uint32_t world, uint64_t idx) {
@@ -241,19 +242,18 @@ __global__ void __launch_bounds__(TPB) k_ex_own(DevState *st, ExArgs ex, const E
 }
 
 // ---- fast path: compartments that run the device-resident generation (vl_fused.cuh) ---------------------------------------
-// Five kernels between the offspring map and the new population instead of seventeen, and no pass that only computes sizes:
-//   k_ex_sizes        the part sizes are known as soon as the plan has run: every target is told at once (header + early flag)
-//   k_ex_wait_sizes   every rank learns how many migrants each origin will send -> the layout of its new population; its OWN
-//                     part can then be drawn straight into place (k_resample_pos, which also prepares the children's next
-//                     infection: no k_ex_own copy, no k_infect_sum pass next generation)
-//   k_ex_export       length, raw fitness and entries of every leaving migrant in ONE pass: a CTA takes 256 consecutive
-//                     migrants, reserves their entry words in the targets' blocks with one atomic per target, gathers the
-//                     flattened records in shared memory and streams them to the peers in full lines; every migrant carries
-//                     the offset of its words (the blocks are filled in the order CTAs arrive)
-//   k_ex_publish      header, system fence, flag (as before)
-//   k_ex_wait, k_ex_import_fused   records, arena words and population slots of the imported migrants in ONE pass (ids and
-//                     words reserved per CTA), their carried fitness, and their infection for the next generation
-__global__ void k_ex_sizes(DevState *st, ExArgs ex, ExScratch *sc) {
+// Three kernels between the plan and the new population (the general kernels above: fourteen), and no pass that only
+// computes sizes:
+//   k_ex_sizes         the part sizes are known as soon as the plan has run: every target is told at once (header word + early
+//                      flag), then the same warp learns how many migrants each origin will send -> the layout of the new
+//                      population.  My OWN part can then be drawn straight into place (k_resample_pos, which also prepares the
+//                      children's next infection: no k_ex_own copy, no k_infect_sum pass next generation)
+//   k_ex_export        every leaving migrant in ONE pass (see the kernel); the last CTA to leave writes the block headers and,
+//                      after a system-scope fence, the flags
+//   k_ex_import_fused  waits for the origins' flags (bounded), then records, arena words and population slots of the
+//                      imported migrants in ONE pass (ids and words reserved per CTA), their carried fitness, and their
+//                      infection for the next generation
+__device__ __forceinline__ void ex_sizes_body(DevState *st, const ExArgs &ex, ExScratch *sc) {
     __shared__ uint64_t s_m[EX_MAX_WORLD];
     const uint32_t t = threadIdx.x;
     if (t < ex.world) {
@@ -273,9 +273,10 @@ __global__ void k_ex_sizes(DevState *st, ExArgs ex, ExScratch *sc) {
         for (uint32_t q = 0; q < ex.world; q++) { sc->part_start[q] = acc; acc += s_m[q]; }
         sc->part_start[ex.world] = acc;
         sc->n_out = acc;
+        sc->exp_done = 0u;
     }
 }
-__global__ void k_ex_wait_sizes(DevState *st, ExArgs ex, ExScratch *sc, unsigned long long timeout_ns) {
+__device__ __forceinline__ void ex_wait_sizes_body(DevState *st, const ExArgs &ex, ExScratch *sc, unsigned long long timeout_ns) {
     __shared__ uint64_t s_m[EX_MAX_WORLD];
     const uint32_t o = threadIdx.x;
     if (o < ex.world) {
@@ -309,6 +310,12 @@ __global__ void k_ex_wait_sizes(DevState *st, ExArgs ex, ExScratch *sc, unsigned
     sc->own_off = sc->in_start[ex.rank];
     if (pop > st->cap_inf) { raise(st, DE_INF_CAPACITY); pop = st->cap_inf; }
     st->n_next = pop;
+}
+// (one launch, one warp: announce my part sizes, then learn every origin's)
+__global__ void k_ex_sizes(DevState *st, ExArgs ex, ExScratch *sc, unsigned long long timeout_ns) {
+    ex_sizes_body(st, ex, sc);
+    __syncthreads();
+    ex_wait_sizes_body(st, ex, sc, timeout_ns);
 }
 constexpr int EXP_TPB = 256;
 // last record of the round whose first word is at or before word g (s_pref: exclusive prefix sums of the round's lengths)
@@ -455,7 +462,29 @@ __global__ void __launch_bounds__(EXP_TPB) k_ex_export(DevState *st, ExArgs ex, 
             }
         }
     }
-    if (bulk && tid < W) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // (all my copies are complete before the kernel ends)
+    // the last CTA to leave publishes the blocks: headers, then (after a system-scope fence) the flags the targets wait on
+    __shared__ uint32_t s_last;
+    if (bulk && tid < W) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // (all my copies are complete ...)
+        asm volatile("fence.proxy.async;" ::: "memory");           // (... and ordered before what this thread writes next)
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(&sc->exp_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (tid < W && tid != ex.rank) {
+        uint64_t w = *(volatile unsigned long long *)&sc->wcur[tid];
+        if (w > ex.out[tid].w_cap) w = ex.out[tid].w_cap;
+        ex.out[tid].header[par][0] = sc->part_start[tid + 1] - sc->part_start[tid];
+        ex.out[tid].header[par][1] = w;
+        __threadfence_system();
+        *(volatile unsigned long long *)ex.out[tid].flag[par] = ex.seq;
+    }
 }
 // the worklist items staged so far (the children of my own part) and the ids of the records k_mutate (range 1) gives them
 __global__ void k_ex_own_items(DevState *st) {
@@ -463,20 +492,9 @@ __global__ void k_ex_own_items(DevState *st) {
     st->mut_own = n;
     st->mut_own_base = atomicAdd(&st->n_hap, (unsigned long long)n);
 }
-// headers, then (after a system-scope fence) the flags the targets wait on
-__global__ void k_ex_publish_fused(DevState *st, ExArgs ex, const ExScratch *sc) {
-    const uint32_t t = threadIdx.x;
-    if (t >= ex.world || t == ex.rank) return;
-    uint64_t w = sc->wcur[t];
-    if (w > ex.out[t].w_cap) w = ex.out[t].w_cap;
-    ex.out[t].header[ex.parity][0] = sc->part_start[t + 1] - sc->part_start[t];
-    ex.out[t].header[ex.parity][1] = w;
-    __threadfence_system();
-    *(volatile unsigned long long *)ex.out[t].flag[ex.parity] = ex.seq;
-}
 // imported migrants become records of their own and members of the new population; prefill: they are infected for the
 // next generation here (their slot in the new population is known), like the children k_resample_pos draws
-__global__ void __launch_bounds__(EXP_TPB, 4) k_ex_import_fused(DevState *st, ExArgs ex, const ExScratch *sc, int prefill) {
+__global__ void __launch_bounds__(EXP_TPB, 4) k_ex_import_fused(DevState *st, ExArgs ex, const ExScratch *sc, int prefill, unsigned long long timeout_ns) {
     __shared__ uint4 s_items[EXP_TPB];
     __shared__ uint32_t s_clcnt[2];
     __shared__ uint32_t s_pref[EXP_TPB + 1], s_src[EXP_TPB], s_org[EXP_TPB];
@@ -497,6 +515,16 @@ __global__ void __launch_bounds__(EXP_TPB, 4) k_ex_import_fused(DevState *st, Ex
     ic.keep = l2_keep_policy();
     ic.stream = l2_stream_policy();
     if (tid == 0) s_clcnt[0] = 0u;
+    if (timeout_ns && tid < ex.world && tid != ex.rank) {  // every origin's block of this generation must have arrived (as k_ex_wait)
+        const unsigned long long t0 = vl_globaltimer();
+        volatile unsigned long long *f = (volatile unsigned long long *)ex.in[tid].flag[par];
+        while (*f < ex.seq) {
+            if (vl_globaltimer() - t0 > timeout_ns) { raise(st, DE_EXCHANGE_TIMEOUT); break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
     for (uint64_t c0 = (uint64_t)blockIdx.x * EXP_TPB; c0 < M; c0 += (uint64_t)gridDim.x * EXP_TPB) {
         const uint64_t idx = c0 + tid;
         const bool active = idx < M;
