@@ -117,6 +117,10 @@ static cudaEvent_t prof_begin(vl_sim *sim, const char *name) {
 }
 
 static thread_local char g_create_err[512];
+// Handles are independent, but three things touch the whole context: creating a handle (allocations, function attributes),
+// destroying one (cudaFree synchronises the device) and capturing a generation into a CUDA graph (no other thread may
+// synchronise the device meanwhile).  They take turns; nothing on the per-generation path takes this lock.
+static std::mutex g_context_mu;
 constexpr int PIN_SLOTS = 4096;
 constexpr int BSORT_SMEM_BYTES = BUCKET_HOSTS * 4 + BSORT_STAGE_RECS * 10;
 
@@ -475,6 +479,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     cudaError_t ce = cudaGetDeviceCount(&n_dev);
     if (ce != cudaSuccess || n_dev == 0) return fail(nullptr, VL_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(ce));
     if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, VL_ERR_ARGUMENT, "device ordinal %d out of range", cfg->device);
+    std::lock_guard<std::mutex> context_lock(g_context_mu);
     vl_sim *sim = new vl_sim();
     memset(&sim->h, 0, sizeof(DevState));
     sim->device = cfg->device;
@@ -599,7 +604,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     }
     sim->n_known = 0;
     sim->n_valid = true;
-    CCU(cudaDeviceSynchronize());
+    CCU(cudaStreamSynchronize(sim->stream));  // (not the device: another handle's stream may be capturing a graph)
 #undef CTRY
 #undef CCU
     *out = sim;
@@ -608,6 +613,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
 
 VL_API int vl_destroy(vl_sim *sim) {
     if (!sim) return VL_OK;
+    std::lock_guard<std::mutex> context_lock(g_context_mu);
     destroy_sim(sim);
     return VL_OK;
 }
@@ -1534,6 +1540,7 @@ static int enqueue_generation(vl_sim *sim, bool more_follow) {
             if (sim->gen_graph) { cudaGraphExecDestroy(sim->gen_graph); sim->gen_graph = nullptr; }
             cudaGraph_t graph = nullptr;
             const uint64_t l0 = sim->launches;
+            std::lock_guard<std::mutex> context_lock(g_context_mu);
             if (cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 const int rc = enqueue_generation_kernels(sim, tiles, prefill_next);
                 const cudaError_t ce = cudaStreamEndCapture(sim->stream, &graph);
@@ -1730,6 +1737,7 @@ VL_API int vl_exchange_create(vl_sim *sim, uint32_t rank, uint32_t world, const 
     ENTER(sim);
     if (!out || (!transfer && !sharded) || !ipc_handle_out) return fail(sim, VL_ERR_ARGUMENT, "null argument");
     if (world < 2 || world > EX_MAX_WORLD || rank >= world) return fail(sim, VL_ERR_ARGUMENT, "world must be in [2, %u] and rank below it", EX_MAX_WORLD);
+    std::lock_guard<std::mutex> context_lock(g_context_mu);
     vl_exchange *ex = new vl_exchange();
     ex->sim = sim; ex->rank = rank; ex->world = world;
     ex->wpm = words_per_migrant ? words_per_migrant : 64;
@@ -1849,6 +1857,7 @@ VL_API int vl_exchange_set_transfer(vl_exchange *ex, const double *transfer) {
 VL_API int vl_exchange_destroy(vl_exchange *ex) {
     if (!ex) return VL_OK;
     std::lock_guard<std::recursive_mutex> lock_(ex->sim->mu);
+    std::lock_guard<std::mutex> context_lock(g_context_mu);
     ex_free(ex);
     return VL_OK;
 }
