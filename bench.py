@@ -482,12 +482,48 @@ def run_b200(args, rank, world):
     if rank == 0 and world == 1 and not args.no_extra:
         out["long_run"] = long_run(local_rank)
         out["extra"] = extra_configs(local_rank)
+    if world > 1 and not args.no_extra and not sharded:
+        blk = extra_sharded_k5(rank, world, local_rank, dist)
+        if rank == 0:
+            out["extra"] = {"k5_sharded": blk}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(args, wl)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return out
+
+
+def extra_sharded_k5(rank, world, device, dist):
+    """BASELINE configs[4] shape, bounded: ONE K5 compartment (30 kb genome, recombination, R0 = 100, dilution 0.02) of 10^7
+    infectants sharded over all ranks, device-resident, a dozen generations."""
+    import torch
+    from virolution_b200.distributed import PeerExchange, sharded_simulation
+    from virolution_b200.workloads import workload
+    wl = workload("k5_sars", 10_000_000)
+    par = wl["parameters"]
+    sim = sharded_simulation(wl["wildtype"], par, wl["specs"], rank, world, seed=77, device=device, n0=wl["n0"])
+    px = PeerExchange(sim, rank, world, sharded=True, shard_seed=77)
+    warm, gens = 6, 12
+    px.run(warm)
+    sim.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sim.infectant_generations(reset=True)
+    sim.timer_start()
+    px.run(gens)
+    ms = sim.timer_stop()
+    work = sim.infectant_generations()
+    t = torch.tensor([float(work), ms, float(sim.population_len())], dtype=torch.float64, device="cuda")
+    tsum, tmax = t.clone(), t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    px.close()
+    sim.close()
+    return {"workload": wl["description"] + f", ONE compartment sharded over {world} GPUs", "ms_per_generation": round(float(tmax[1]) / gens, 5),
+            "value": float(tsum[0]) / (float(tmax[1]) * 1e-3), "unit": UNIT, "generations_timed": gens, "warmup": warm, "scaling": "strong",
+            "population_total_at_end": int(tsum[2]), "expected_total": int(par.max_population),
+            "bound": "general kernels (recombination needs the host map) + exchange of (world-1)/world of the population per generation"}
 
 
 def host_cores():
