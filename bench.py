@@ -237,6 +237,26 @@ def extra_configs(device):
                                                "ms_per_generation": round(dt / gens * 1e3, 4), "value": ig / dt, "unit": UNIT,
                                                "generations_timed": gens, "bound": "launch/host-bound: 8 compartments of 10^5 driven through trait-level "
                                                "enqueues with one synchronisation per generation (wall clock)"}
+    # the same eight compartments through the in-process peer exchange (CompartmentGroup): nothing but enqueues
+    from virolution_b200.simulation import CompartmentGroup
+    group = CompartmentGroup(sims, T)
+    group.run(10)
+    group.synchronize()
+    for s in sims:
+        s.infectant_generations(reset=True)
+    t0 = time.perf_counter()
+    gens = 100
+    group.run(gens)
+    group.synchronize()
+    dt = time.perf_counter() - t0
+    ig = sum(s.infectant_generations(reset=True) for s in sims)
+    sizes = [s.population_len() for s in sims]
+    out["k3_multihost_8_compartments_1gpu_group"] = {"workload": wl["description"] + f" x {C} compartments on one GPU, CompartmentGroup (peer exchange between "
+                                                     "the compartments of one process, parallel-build transmission rule)",
+                                                     "ms_per_generation": round(dt / gens * 1e3, 4), "value": ig / dt, "unit": UNIT, "generations_timed": gens,
+                                                     "population_per_compartment": sizes,
+                                                     "bound": "launch-bound: ~40 kernels per compartment and generation on eight streams (wall clock)"}
+    group.close()
     for s in sims:
         s.close()
     return out

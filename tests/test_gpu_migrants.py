@@ -364,3 +364,46 @@ def test_exchange_follows_a_transfer_matrix_that_changes():
         e.close()
     for s in a + b:
         s.close()
+
+
+@pytest.mark.parametrize("which", ["multihost", "k3_multihost"])
+def test_compartment_group_equals_vl_step(which):
+    """CompartmentGroup (the compartments of one process stepped through the peer exchange: what the runner mirror and the K3
+    block of the bench use) against vl_step's parallel-build rule on three compartments with two host specs each — infectant
+    by infectant — with a transfer matrix that changes, then `run` (chunks of generations enqueued per compartment)."""
+    from test_gpu_stochastic import population_signature
+    from virolution_b200.simulation import CompartmentGroup, step
+    from virolution_b200.workloads import workload
+    if which == "multihost":
+        c = helpers.case("multihost")     # infective fitness, n_hits 3: the general kernels
+        mk = lambda k, seed: helpers.make_gpu(c, seed=seed, compartment_id=k)
+    else:
+        wl = workload("k3_multihost", 30000)
+        wl["parameters"].mutation_rate = 2e-5
+
+        def mk(k, seed):
+            from virolution_b200.simulation import GpuSimulation
+            g = GpuSimulation(wl["wildtype"], wl["parameters"], wl["specs"], seed=seed, compartment_id=k)
+            g.set_population_wildtype(wl["n0"])
+            return g
+    T1 = np.array([[0.8, 0.1, 0.0], [0.2, 0.7, 0.3], [0.0, 0.2, 0.7]])
+    T2 = np.array([[0.6, 0.0, 0.2], [0.2, 0.9, 0.0], [0.2, 0.1, 0.8]])
+    a = [mk(k, 21) for k in range(3)]
+    b = [mk(k, 21) for k in range(3)]
+    group = CompartmentGroup(b, np.maximum(T1, T2), words_per_migrant=48)
+    for T in (T1, T2, T2, T1):
+        step(a, T, 0)
+        group.step(T)
+        for k in range(3):
+            assert a[k].population_len() == b[k].population_len()
+            assert population_signature(a[k]) == population_signature(b[k]), f"compartment {k}"
+    for _ in range(11):
+        step(a, T1, 0)
+    group.run(11)             # more than one chunk
+    group.synchronize()
+    for k in range(3):
+        assert population_signature(a[k]) == population_signature(b[k]), f"compartment {k} after run"
+        helpers.assert_f64_equal(a[k].get_raw_fitness(), b[k].get_raw_fitness(), "raw fitness")
+    group.close()
+    for s in a + b:
+        s.close()

@@ -4,8 +4,9 @@
 `samples/barcodes.csv`, `final.<i>.csv`
 (src/main.rs:63-154, src/runner.rs:137-152,230-240, src/readwrite/sample_writer.rs:29-61,243-263).
 
-Everything that costs time stays on the device: one `vl_step` per generation (infect, mutate, replicate, the
-transmission block), populations are only materialised on the host at sample events and at the end.
+Everything that costs time stays on the device: per generation one enqueue per compartment (infect, mutate, replicate and
+the transmission block, migrants written by the kernels into the other compartments' buffers), populations are only
+materialised on the host at sample events and at the end.
 
     python -m virolution_b200.runner --settings tests/singlehost/singlehost.yaml --sequence tests/singlehost/ref.fasta \\
         --generations 200 --n-compartments 2 --outdir out
@@ -20,7 +21,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from .config import load_parameters, load_settings, read_fasta_wildtype
-from .simulation import GpuSimulation, step
+from .simulation import CompartmentGroup, GpuSimulation, step
 
 LETTERS = "ATCG"
 
@@ -174,7 +175,30 @@ class GpuRunner:
         self.log.write(f"Adjust settings to:\n{parameters}\n")
         for sim in self.sims:
             sim.set_parameters(parameters)
+        self._drop_group()  # the exchange buffers were sized for the old max_population
         return parameters
+
+    # ------------------------------------------------------------------ the transmission block of several compartments
+    def _drop_group(self):
+        if getattr(self, "_group", None) is not None:
+            self._group.close()
+        self._group = None
+
+    def _transmit(self, T):
+        """One generation of every compartment.  Several compartments are stepped through the peer exchange between the
+        compartments of this process (`CompartmentGroup`: nothing is synchronised or copied to the host), sized for the
+        entry-wise maximum of the schedule's matrices; a single compartment through `vl_step`."""
+        C = self.n_compartments
+        if C < 2:
+            step(self.sims, T, rule=0)
+            return
+        if getattr(self, "_group", None) is None:
+            cap = np.array(T, dtype=np.float64)
+            for M in self.schedule.transfers.values():
+                if M.shape[0] >= C and M.shape[1] >= C:
+                    cap = np.maximum(cap, M[:C, :C])
+            self._group = CompartmentGroup(self.sims, cap)
+        self._group.step(T)
 
     def collect_stats(self, generation: int):
         """`stats` event (src/runner.rs:634-673; only the serial build of the reference has it): comma-separated list of
@@ -221,11 +245,12 @@ class GpuRunner:
             # increment_generation, infect, mutate_infectants, replicate_infectants and the transmission block of every
             # compartment (src/runner.rs:382-422) as one call; T = schedule.get_transfer_matrix(generation), row = target
             T = self.schedule.get_transfer_matrix(generation)[:C, :C]
-            step(self.sims, T, rule=0)
+            self._transmit(T)
         self.finish()
         return self
 
     def close(self):
+        self._drop_group()
         for s in self.sims:
             s.close()
         self.sims = []

@@ -583,6 +583,65 @@ def step(sims: Sequence[GpuSimulation], transfer: Optional[np.ndarray] = None, r
         raise (ReferencePanic if rc == abi.VL_ERR_REFERENCE_PANIC else VirolutionError)(rc, msg)
 
 
+class CompartmentGroup:
+    """The compartments of ONE process (any devices with peer access; normally one GPU) stepped through the peer exchange
+    instead of `vl_step`: every compartment writes its migrants into the others' receive buffers inside the kernels, sizes
+    stay on the device, and the host only enqueues — no detached populations, no synchronisation per generation.
+    Same transmission block (parallel build, src/runner.rs:382-422) and the same populations as `step(sims, T, 0)`
+    (tests/test_gpu_migrants.py).  `transfer_cap` is the entry-wise maximum of every matrix the schedule will ask for."""
+
+    CHUNK = 8  # generations enqueued per compartment before the next one gets its turn (bounded by the launch queue)
+
+    def __init__(self, sims: Sequence[GpuSimulation], transfer_cap, words_per_migrant: int = 0):
+        self.sims = list(sims)
+        C_ = len(self.sims)
+        if C_ < 2:
+            raise ValueError("a group has at least two compartments")
+        self.cap = np.ascontiguousarray(np.asarray(transfer_cap, dtype=np.float64)[:C_, :C_])
+        self.T = self.cap.copy()
+        self.ex = [PeerExchangeHandle(self.sims[k], k, C_, self.cap, words_per_migrant) for k in range(C_)]
+        bufs = [e.recv_buffer() for e in self.ex]
+        for k, e in enumerate(self.ex):
+            e.connect(None, [bufs[t] if t != k else 0 for t in range(C_)])
+
+    def set_transfer(self, T):
+        T = np.ascontiguousarray(np.asarray(T, dtype=np.float64)[:len(self.sims), :len(self.sims)])
+        if not np.array_equal(T, self.T):
+            for e in self.ex:
+                e.set_transfer(T)
+            self.T = T
+
+    def step(self, transfer=None):
+        """One generation of every compartment.  Compartments of one process push all before they pull any."""
+        if transfer is not None:
+            self.set_transfer(transfer)
+        for e in self.ex:
+            e.push()
+        for e in self.ex:
+            e.pull()
+
+    def run(self, n_generations: int):
+        """n generations; nothing is read back and nothing is waited for on the host."""
+        left = int(n_generations)
+        while left > 0:
+            k = min(left, self.CHUNK)
+            for e in self.ex:
+                e.run(k)
+            left -= k
+
+    def synchronize(self):
+        for s in self.sims:
+            s.synchronize()
+
+    def close(self):
+        for s in self.sims:
+            if s.ptr:
+                s.synchronize()
+        for e in self.ex:
+            e.close()
+        self.ex = []
+
+
 def sampler_poisson(seed: int, lam: float, n: int) -> np.ndarray:
     out = np.zeros(n, dtype=np.uint64)
     rc = load_library().vl_test_poisson(seed, lam, n, _p(out, C.c_uint64))
