@@ -85,6 +85,7 @@ struct vl_sim {
     bool uniform_infection = false;  // the host map came from uniform Philox draws over [0, H) (no replay, DevState::fast_infect)
     bool pop_fit_valid = false;   // pop_fit[] holds the mapped reproductive fitness of every infectant of the current population
     bool prefilled = false;       // the last resample drew the next generation's hosts and mutation counts (k_resample_pos<true>)
+    bool begun_ahead = false;     // ... and has begun that generation (counter, counters) as well: no k_begin_generation_fused launch
     bool prefill_patch = false;   // ... and records were created after it (imported migrants): k_mutate patches the population itself
     bool prefill_own_done = false; // ... and the items [0, mut_own) of the prepared worklist have been mutated already (k_mutate range 1)
     bool hsum_dirty = false;      // ... and that work was dropped: hsum[parity] holds stale sums, cleared before the next infect pass
@@ -896,6 +897,7 @@ struct PosOpts {
     const uint64_t *own_off = nullptr; // device: its first slot there (nullptr = 0)
     bool predict_ids = false;          // nothing creates records between these draws and the next k_mutate
     std::function<int()> between;      // enqueued between the plan and the draws (the plan's part sizes are final there)
+    int tail = 0;                      // ResamplePosArgs::tail: swap (1) and begin of the next generation (2) by the pass's last CTA
 };
 // plan + draws of n parts of the current offspring map in one pass each (n <= MAX_PARTS)
 static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, int use_amount, const uint64_t *amount, int set_next,
@@ -919,7 +921,7 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
     }
     const uint64_t nt_bound = tile_bound(sim);
     const uint32_t smem_tiles = (uint32_t)std::min<uint64_t>(nt_bound, sim->plan_smem_tiles);
-    zero_device(sim, (char *)sim->d + FIELD_OFF(plan_sync), 8 + sizeof(((DevState *)0)->plan_acc));
+    // (plan_sync .. plan_acc are zero here: cleared by the last CTA of the previous plan kernel, vl_kernels.cuh plan_leave)
     // a handful of co-resident CTAs: each draws for its slice of tiles, a counter in DevState is the grid barrier
     // (enough CTAs for the tiles, and for the draws a small sample makes one by one: two per thread)
     const uint64_t direct_draws = std::min<uint64_t>(sim->h.max_population, PLAN_FILL_MAX);
@@ -936,6 +938,7 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
         rt.own_part = po ? po->own_part : -1;
         rt.own_off = po ? po->own_off : nullptr;
         rt.predict_ids = po && po->predict_ids ? 1 : 0;
+        rt.tail = po ? po->tail : 0;
         for (uint32_t k = 0; k < n; k++)
             if ((int)k != rt.own_part && !rt.dst[k]) return fail(sim, VL_ERR_IMPLEMENTATION, "part %u has no destination", k);
         if (po && po->between) TRY(po->between());
@@ -1453,7 +1456,8 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
     const DevState &h = sim->h;
     sim->salt = 0;
     const bool prefilled = sim->prefilled;
-    LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d, prefilled ? 1 : 0);
+    if (sim->begun_ahead && !prefilled) return fail(sim, VL_ERR_IMPLEMENTATION, "a generation was begun ahead without its prepared infection");
+    if (!sim->begun_ahead) LAUNCH(sim, k_begin_generation_fused, 1, 1, 0, sim->d, prefilled ? 1 : 0);  // (else: the previous resample's last CTA did it)
     if (!prefilled) {
         if (sim->hsum_dirty) LAUNCH(sim, k_zero_hsum_current, grid_for(sim, h.H), TPB, 0, sim->d);
         sim->hsum_dirty = false;
@@ -1472,8 +1476,9 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
     po.prefill = prefill_next;
     po.own_part = 0;
     po.predict_ids = true;
+    po.tail = 1 | (prefill_next ? 2 : 0);  // the resample's last CTA installs the population and, if it prepared it, begins the next generation
     TRY(launch_plan_resample(sim, 1, &one, 0, nullptr, 1, dsts, nullptr, 0, true, nullptr, &po));
-    LAUNCH(sim, k_swap_population_fused, 1, 1, 0, sim->d);
+    sim->begun_ahead = prefill_next;
     sim->prefilled = prefill_next;
     sim->prefill_patch = false;
     sim->prefill_own_done = false;
@@ -1535,7 +1540,7 @@ static int enqueue_generation(vl_sim *sim, bool more_follow) {
         const DevState &h = sim->h;
         const uint64_t key[5] = {sim->n_bound, h.H, h.cap_inf, (uint64_t)(uintptr_t)h.tmp_rec ^ (uint64_t)(uintptr_t)h.offsets ^ (uint64_t)(uintptr_t)h.hsum[0],
                                  (uint64_t)sim->flags | (tiles ? 1ull << 40 : 0) | (sim->pop_fit_valid ? 1ull << 41 : 0) | (sim->prefilled ? 1ull << 42 : 0) |
-                                     (prefill_next ? 1ull << 43 : 0) | (sim->hsum_dirty ? 1ull << 44 : 0)};
+                                     (prefill_next ? 1ull << 43 : 0) | (sim->hsum_dirty ? 1ull << 44 : 0) | (sim->begun_ahead ? 1ull << 45 : 0)};
         if (!sim->gen_graph || memcmp(key, sim->graph_key, sizeof key) != 0) {
             if (sim->gen_graph) { cudaGraphExecDestroy(sim->gen_graph); sim->gen_graph = nullptr; }
             cudaGraph_t graph = nullptr;
@@ -1562,7 +1567,7 @@ static int enqueue_generation(vl_sim *sim, bool more_follow) {
         if (sim->gen_graph) {
             CU(sim, cudaGraphLaunch(sim->gen_graph, sim->stream));
             sim->launches += sim->graph_launches;
-            if (tiles) { sim->prefilled = prefill_next; sim->hsum_dirty = false; }
+            if (tiles) { sim->prefilled = prefill_next; sim->begun_ahead = prefill_next; sim->hsum_dirty = false; }
             sim->salt = 1;
             sim->mutcounts_ready = false;
             sim->bucket_pending = false;

@@ -39,13 +39,26 @@ namespace vl {
 
 // generation += 1 and the counters of a generation (one launch).  prefilled: the previous generation's resample has
 // already drawn this generation's hosts and mutation counts (k_resample_pos<true>): the worklist is kept.
-__global__ void k_begin_generation_fused(DevState *st, int prefilled) {
+__device__ __forceinline__ void begin_generation_fused(DevState *st, int prefilled) {
     st->generation += 1;  // Simulation::increment_generation (src/simulation.rs:178)
     if (!prefilled) st->n_mut_list = 0;
     st->n_heavy = 0;
     st->n_medium = 0;
     st->fused_failed = 0;
     st->infectant_generations += st->n;
+}
+__global__ void k_begin_generation_fused(DevState *st, int prefilled) { begin_generation_fused(st, prefilled); }
+// set_population of the device-resident generation: both per-infectant arrays swap, the sums change sides
+__device__ __forceinline__ void swap_population_fused(DevState *st) {
+    uint32_t *t = st->hap_id;
+    st->hap_id = st->hap_id_next;
+    st->hap_id_next = t;
+    double *f = st->pop_fit;
+    st->pop_fit = st->pop_fit_next;
+    st->pop_fit_next = f;
+    st->n = st->n_next;
+    st->n_sorted = 0;
+    st->hsum_parity ^= 1u;
 }
 __global__ void __launch_bounds__(TPB) k_zero_f64(double *p, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = 0.0;
@@ -271,6 +284,8 @@ struct ResamplePosArgs {
     const uint64_t *own_off;     // device: first slot of that part in the new population (nullptr = 0)
     int predict_ids;             // PREFILL: the next kernel to touch the record table is k_mutate, so the ids of the staged
                                  // children's new records are known and go into the population here (else k_mutate patches it)
+    int tail;                    // what the last CTA to leave does: bit 0 = install the new population (k_swap_population_fused),
+                                 // bit 1 = begin the next generation, whose infection this pass has prepared (k_begin_generation_fused)
 };
 // PREFILL (only when the caller enqueues the next generation right behind this one): the children written to the
 // population (the own part) get their hosts and mutation counts for the NEXT generation right here (infect_draw with generation + 1): host_id[], the other hsum buffer (cleared by
@@ -509,19 +524,22 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
         // 0.97 against 0.93 ms per generation, the mutate kernel included)
         if (PREFILL) cl_flush(st, cl, ra.predict_ids ? st->hap_id_next : nullptr, st->n_hap);
     }
+    // The last CTA to leave finishes the generation (two one-thread launches less per generation): every other CTA's
+    // writes are behind its fence, nobody reads the pointers any more.
+    if (ra.tail) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(&st->tail_done, 1u) == gridDim.x - 1) {
+                st->tail_done = 0u;
+                if (ra.tail & 1) swap_population_fused(st);
+                if (ra.tail & 2) begin_generation_fused(st, 1);
+            }
+        }
+    }
 }
 
 // set_population of the device-resident generation: both per-infectant arrays swap, the sums change sides
-__global__ void k_swap_population_fused(DevState *st) {
-    uint32_t *t = st->hap_id;
-    st->hap_id = st->hap_id_next;
-    st->hap_id_next = t;
-    double *f = st->pop_fit;
-    st->pop_fit = st->pop_fit_next;
-    st->pop_fit_next = f;
-    st->n = st->n_next;
-    st->n_sorted = 0;
-    st->hsum_parity ^= 1u;
-}
+__global__ void k_swap_population_fused(DevState *st) { swap_population_fused(st); }
 
 }  // namespace vl

@@ -1754,6 +1754,21 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
     const PhiloxKey key = philox_key(st->seed, st->compartment);
     const uint32_t gen = st->generation;
     uint32_t epoch = 0;
+    // leaving the kernel: the last CTA (every CTA has then passed every barrier) leaves the barrier counter and the stage
+    // accumulators cleared for the next launch — no clearing pass in front of the kernel
+    auto plan_leave = [&]() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&st->plan_exit, 1u) == gridDim.x - 1) {
+                for (int s = 0; s < 4; s++)
+                    for (int p = 0; p < MAX_PARTS; p++) st->plan_acc[s][p] = 0ull;
+                st->plan_exit = 0u;
+                __threadfence();
+                st->plan_sync = 0u;
+            }
+        }
+    };
     // this CTA's slice of tiles
     const uint64_t per = (nt + gridDim.x - 1) / gridDim.x;
     const uint64_t t_lo = per * blockIdx.x < nt ? per * blockIdx.x : nt, t_hi = t_lo + per < nt ? t_lo + per : nt;
@@ -1929,6 +1944,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
             plan_block_scan(st->tile_cnt + p * stride + t_lo, st->tile_base + p * stride + t_lo, t_hi - t_lo, false, base, s_scan, &s_carry);
         }
         if (lead && tid == 0) st->dbg[4] = vl_globaltimer();
+        plan_leave();
         return;
     }
     // many parts: one warp per part (round robin): the slice total, then — once every CTA's totals are known — the scan of
@@ -1961,6 +1977,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) k_plan_resample(DevState *st, Pl
         }
     }
     if (lead && tid == 0) st->dbg[4] = vl_globaltimer();
+    plan_leave();
 }
 
 // One CTA per tile of CSR positions.  The tile's records with offspring > 0 are compacted into shared memory (payload =

@@ -165,7 +165,7 @@ struct DevState {
     uint32_t n_mut_list;
     uint32_t mut_ctas_done;  // CTAs of the running k_mutate that have left (the last one publishes n_hap)
     uint32_t mut_own;        // worklist items [0, mut_own) are mutated ahead of their generation (vl_exchange_run: while the migrants travel)
-    uint32_t mut_pad_;
+    uint32_t tail_done;      // CTAs of the running k_resample_pos that have left (the last one installs the new population)
     unsigned long long mut_own_base;  // ... with record ids mut_own_base + worklist position (reserved by k_ex_own_items)
     uint32_t _pad0;
     BinvConst binv;        // Binomial(L, mu) inversion constants (captured BasicHost parameters)
@@ -181,8 +181,8 @@ struct DevState {
     uint64_t *tile_base;   // exclusive scan of draws per tile, per part
     uint64_t offspring_total;
     double target_size;    // of the last plan
-    uint32_t plan_sync;    // grid barrier counter of the plan kernel; plan_sync .. plan_acc are cleared before every launch
-    uint32_t _pad4;
+    uint32_t plan_sync;    // grid barrier counter of the plan kernel; plan_sync .. plan_acc are zero between launches: the last
+    uint32_t plan_exit;    // CTA to leave the kernel (plan_exit counts them) clears them for the next launch
     uint64_t plan_acc[4][MAX_PARTS];   // draws made per Poissonisation stage and part, summed over the plan CTAs
     uint64_t plan_part[32][MAX_PARTS]; // draws per CTA slice of tiles and part
     uint64_t plan_size[MAX_PARTS];     // sample size of every part of the last plan
