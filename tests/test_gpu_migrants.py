@@ -407,3 +407,43 @@ def test_compartment_group_equals_vl_step(which):
     group.close()
     for s in a + b:
         s.close()
+
+
+def test_fast_exchange_three_compartments_with_closed_links_and_small_blocks():
+    """The one-pass export / import with three compartments of one process, a transfer matrix with zero entries (targets that
+    receive nothing from an origin) and an empty compartment, against vl_step; then blocks that are too small for the
+    migrants' records: a capacity error, not a wrong population."""
+    from test_gpu_stochastic import population_signature
+    from virolution_b200.simulation import CompartmentGroup, GpuSimulation, VirolutionError, step
+    from virolution_b200.workloads import workload
+    wl = workload("k2_hiv", 60_000)
+    wl["parameters"].mutation_rate = 1e-4
+
+    def mk(k, n0):
+        g = GpuSimulation(wl["wildtype"], wl["parameters"], wl["specs"], seed=8, compartment_id=k)
+        g.set_population_wildtype(n0)
+        return g
+    T = np.array([[0.7, 0.0, 0.2], [0.3, 0.9, 0.0], [0.0, 0.1, 0.8]])
+    a = [mk(k, n0) for k, n0 in enumerate((60_000, 60_000, 0))]      # compartment 2 starts empty and is colonised by 1
+    b = [mk(k, n0) for k, n0 in enumerate((60_000, 60_000, 0))]
+    group = CompartmentGroup(b, T)
+    for g in range(6):
+        step(a, T, 0)
+        group.step()
+        for k in range(3):
+            assert a[k].population_len() == b[k].population_len(), (g, k)
+            assert population_signature(a[k]) == population_signature(b[k]), (g, k)
+    assert b[2].population_len() > 0
+    group.close()
+    for s in a + b:
+        s.close()
+    # blocks of one word per migrant: after a few generations the migrants' records do not fit
+    c = [mk(k, 60_000) for k in range(2)]
+    small = CompartmentGroup(c, np.array([[0.5, 0.5], [0.5, 0.5]]), words_per_migrant=1)
+    with pytest.raises(VirolutionError, match="capacity|arena|words"):
+        for _ in range(12):
+            small.step()
+        small.synchronize()
+    small.close()
+    for s in c:
+        s.close()

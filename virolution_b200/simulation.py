@@ -636,7 +636,10 @@ class CompartmentGroup:
     def close(self):
         for s in self.sims:
             if s.ptr:
-                s.synchronize()
+                try:
+                    s.synchronize()
+                except VirolutionError:
+                    pass  # (a failed handle stays failed: it is being torn down)
         for e in self.ex:
             e.close()
         self.ex = []
