@@ -428,6 +428,15 @@ static int add_provider(vl_sim *sim, const vl_fitness *f, uint64_t L, int *index
         if (!out.empty()) CU(sim, cudaMemcpy(dev, out.data(), out.size() * sizeof(EpiDir), cudaMemcpyHostToDevice));
         p.epi = dev;
         p.n_epi = (uint32_t)out.size();
+        // row index: first entry of every (position, base) key
+        std::vector<uint32_t> start((size_t)L * 4 + 1, 0);
+        for (const EpiDir &e : out) start[e.k1 + 1]++;
+        for (size_t k = 0; k < (size_t)L * 4; k++) start[k + 1] += start[k];
+        uint32_t *dstart = nullptr;
+        TRY(dev_alloc(sim, &dstart, start.size()));
+        CU(sim, cudaMemcpy(dstart, start.data(), start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        p.epi_start = dstart;
+        p.n_keys = (uint32_t)(L * 4);
     }
     *index_out = (int)h.n_providers++;
     return VL_OK;

@@ -75,8 +75,9 @@ struct DevProvider {
     double alg_factor, alg_uf;  // Algebraic: factor = 1/(upper-1) and upper*factor, rounded exactly as the reference forms them
     const double *table;  // L*4
     const EpiDir *epi;    // sorted by (k1, k2), duplicates resolved (last insert wins)
+    const uint32_t *epi_start;  // L*4 + 1: first entry of every key's row (row of key k = [epi_start[k], epi_start[k + 1])), or nullptr
     uint32_t n_epi;
-    uint32_t _pad;
+    uint32_t n_keys;      // L*4 when epi_start is set
 };
 
 struct DevSpec {
@@ -381,6 +382,13 @@ __host__ __device__ inline double utility_apply(const DevProvider &p, double f) 
 
 // nested-map row lookup: [lo,hi) of directed entries keyed k1
 __host__ __device__ inline void epi_row(const DevProvider &p, uint32_t k1, uint32_t &lo_out, uint32_t &hi_out) {
+#ifdef __CUDA_ARCH__
+    if (p.epi_start && k1 < p.n_keys) {  // two loads instead of two binary searches over the whole table
+        lo_out = p.epi_start[k1];
+        hi_out = p.epi_start[k1 + 1];
+        return;
+    }
+#endif
     uint32_t lo = 0, hi = p.n_epi;
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (p.epi[mid].k1 < k1) lo = mid + 1; else hi = mid; }
     uint32_t b = lo;
