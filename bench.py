@@ -382,9 +382,10 @@ def run_b200(args, rank, world):
         # k_mutate works per new haplotype record: item 16 + parent head 64 + base-list window 32 + table rows 32 read; head 64 + memo
         # 16 + carried fitness 8 + per-host sum 8 written; flattened lists are read and written once
         mutate_bytes = None
-        if c1["gc_runs"] == c0["gc_runs"] and "k_mutate" in rep and rep["k_mutate"][0]:
+        k_mut = next((k for k in rep if k.startswith("k_mutate")), None)  # k_mutate<false> / k_mutate<true> (epistatic providers)
+        if c1["gc_runs"] == c0["gc_runs"] and k_mut and rep[k_mut][0]:
             d_rec, d_words = c1["haplotype_records"] - c0["haplotype_records"], c1["arena_words"] - c0["arena_words"]
-            mutate_bytes = (240.0 * d_rec + 8.0 * max(d_words, 0)) / rep["k_mutate"][0]
+            mutate_bytes = (240.0 * d_rec + 8.0 * max(d_words, 0)) / rep[k_mut][0]
         tot_ms = sum(v[1] for v in rep.values())
         for name, (cnt, tms) in sorted(rep.items(), key=lambda kv: -kv[1][1]):
             per_launch_ms = tms / cnt
@@ -392,12 +393,12 @@ def run_b200(args, rank, world):
             kernels[name] = {"launches_per_step": cnt / args.profile_steps, "ms_per_launch": round(per_launch_ms, 5), "share": round(tms / tot_ms, 4)}
             if ab is not None:
                 kernels[name]["GBps"] = round(ab * n_now / (per_launch_ms * 1e-3) / 1e9, 1)
-            elif name == "k_mutate" and mutate_bytes is not None:
+            elif name == k_mut and mutate_bytes is not None:
                 kernels[name]["GBps"] = round(mutate_bytes / (per_launch_ms * 1e-3) / 1e9, 1)
                 kernels[name]["algorithmic_bytes_per_launch"] = round(mutate_bytes)
         launch_bytes = {k: ALGO_BYTES[k] * n_now for k in rep if k in ALGO_BYTES}
         if mutate_bytes is not None:
-            launch_bytes["k_mutate"] = mutate_bytes
+            launch_bytes[k_mut] = mutate_bytes
         if launch_bytes:
             dom = max(launch_bytes, key=lambda k: rep[k][1])  # the kernel that takes most of the step
             dcnt, dms = rep[dom]

@@ -84,6 +84,7 @@ struct vl_sim {
     bool bucket_pending = false;  // records are bucket-partitioned, the host map is not built yet
     bool uniform_infection = false;  // the host map came from uniform Philox draws over [0, H) (no replay, DevState::fast_infect)
     bool pop_fit_valid = false;   // pop_fit[] holds the mapped reproductive fitness of every infectant of the current population
+    bool has_epistasis = false;   // some provider is epistatic (k_mutate<true>)
     bool prefilled = false;       // the last resample drew the next generation's hosts and mutation counts (k_resample_pos<true>)
     bool begun_ahead = false;     // ... and has begun that generation (counter, counters) as well: no k_begin_generation_fused launch
     bool prefill_patch = false;   // ... and records were created after it (imported migrants): k_mutate patches the population itself
@@ -148,6 +149,12 @@ static int fail(vl_sim *sim, int code, const char *fmt, ...) {
         kernel<<<(grid), (block), (smem), (sim)->stream>>>(__VA_ARGS__);    \
         if (pe_) cudaEventRecord(pe_, (sim)->stream);                       \
         (sim)->launches++;                                                  \
+    } while (0)
+// k_mutate<EPI>: the instantiation with the pair-table code only for handles that have an epistatic provider
+#define LAUNCH_MUTATE(sim, grid, block, smem, ...)                                       \
+    do {                                                                                 \
+        if ((sim)->has_epistasis) LAUNCH(sim, k_mutate<true>, grid, block, smem, __VA_ARGS__); \
+        else LAUNCH(sim, k_mutate<false>, grid, block, smem, __VA_ARGS__);               \
     } while (0)
 // launches of a scope go to another stream of the same handle
 struct StreamScope {
@@ -437,6 +444,7 @@ static int add_provider(vl_sim *sim, const vl_fitness *f, uint64_t L, int *index
         CU(sim, cudaMemcpy(dstart, start.data(), start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         p.epi_start = dstart;
         p.n_keys = (uint32_t)(L * 4);
+        sim->has_epistasis = true;
     }
     *index_out = (int)h.n_providers++;
     return VL_OK;
@@ -564,7 +572,8 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     h.binv = make_binv(L, par.mutation_rate);
     CCU(cudaFuncSetAttribute(k_plan_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CCU(cudaFuncSetAttribute(k_host_sum_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
-    CCU(cudaFuncSetAttribute(k_mutate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute(k_mutate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute(k_mutate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute(k_ex_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_SMEM_BYTES));
@@ -835,7 +844,7 @@ static int enqueue_mutate(vl_sim *sim) {
         TRY(zero_field32(sim, FIELD_OFF(n_mut_list)));
         LAUNCH(sim, k_mutation_counts, grid_for(sim, sim->n_bound), TPB, 0, sim->d, rm, sim->has_rp_mut ? 1 : 0);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound, 4), TPB, mutate_smem_bytes(h.L), sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0, 0);
+    LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound, 4), TPB, mutate_smem_bytes(h.L), sim->d, rm, sim->has_rp_mut ? 1 : 0, sim->csr_valid ? 1 : (sim->bucket_pending ? 2 : 0), 0, 0);
     sim->pop_fit_valid = false;  // haplotypes of the current population changed
     sim->mutcounts_ready = false;
     sim->has_rp_mut = false;
@@ -1433,7 +1442,7 @@ static int enqueue_generation_front(vl_sim *sim) {
         // depend on its host, so mutate first and build the host map from the already-mutated population
         LAUNCH(sim, k_begin_generation, 1, 1024, 0, sim->d);
         LAUNCH(sim, k_mutcount_fast, grid_tiles(sim, sim->n_bound, (uint64_t)TPB * MC_ITEMS, 8), TPB, 0, sim->d);
-        LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0, 1, 0);
+        LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 0, 1, 0);
         const int btpb = (sim->experiment & 2) ? 512 : 1024;
         const unsigned chunks = (unsigned)std::max<uint64_t>(1, (sim->n_bound + btpb * BUCKET_ITEMS - 1) / (btpb * BUCKET_ITEMS));
         if (btpb == 1024) LAUNCH(sim, (k_infect_bucket<false, false, 1024>), chunks, 1024, 0, sim->d);
@@ -1474,7 +1483,7 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
         if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
         else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
+    LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
            prefilled && sim->prefill_patch ? 4 : 3, 1, prefilled && sim->prefill_own_done ? 2 : 0);
     const unsigned og = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, og, OS_TPB, 0, sim->d);
@@ -1510,7 +1519,7 @@ static int enqueue_generation_front_fused(vl_sim *sim) {
         if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
         else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
     }
-    LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
+    LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
            prefilled && sim->prefill_patch ? 4 : 3, 1, prefilled && sim->prefill_own_done ? 2 : 0);
     sim->prefilled = false;
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, ig, OS_TPB, 0, sim->d);
@@ -1729,7 +1738,7 @@ static void preload_exchange_kernels() {
     std::call_once(once, [] {
         const void *ks[] = {
             (const void *)k_zero_words, (const void *)k_begin_generation_fused, (const void *)k_zero_hsum_current,
-            (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate,
+            (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate<false>, (const void *)k_mutate<true>,
             (const void *)k_offspring_sum<false>, (const void *)k_offspring_sum<true>, (const void *)k_plan_resample,
             (const void *)k_resample_pos<false, true>, (const void *)k_resample_pos<true, true>, (const void *)k_resample_pos<false, false>, (const void *)k_resample_pos<true, false>, (const void *)k_swap_population_fused,
             (const void *)k_ex_sizes, (const void *)k_ex_export,
@@ -1958,7 +1967,7 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
                 StreamScope on_side(sim, ex->side);
                 LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
             }
-            LAUNCH(sim, k_mutate, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(sim->h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 4, 1, 1);
+            LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(sim->h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 4, 1, 1);
         } else {
             LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
         }

@@ -941,6 +941,8 @@ __device__ __forceinline__ uint32_t warp_flatten(const uint32_t *pe, uint32_t pl
 // range: 0 = the whole worklist.  1 = items [0, mut_own) AHEAD of their generation: the population they belong to is still
 // being assembled (hap_id_next / pop_fit_next / the other hsum buffer, generation + 1), their ids were reserved
 // (mut_own_base), other kernels create records meanwhile.  2 = the items behind those, once the generation has begun.
+// EPI: some provider is epistatic (the pair-table code is compiled into this instantiation only: the others stay leaner).
+template <bool EPI>
 __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item, int range) {
     extern __shared__ uint32_t s_mut_dyn[];
     __shared__ double s_subst[16];
@@ -1098,7 +1100,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
                         const uint64_t row = (uint64_t)ch_pos(chs[k]) * 4;
                         acc = acc * pr.table[row + ch_to(chs[k])] / pr.table[row + ch_from(chs[k])];
                     }
-                    if (pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, pe, plen, dm, ndm, L);
+                    if (EPI && pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, pe, plen, dm, ndm, L);
                     raw = praw * acc;
                 }
                 const double mapped = utility_apply(pr, raw);
