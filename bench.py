@@ -382,7 +382,7 @@ def run_b200(args, rank, world):
         # k_mutate works per new haplotype record: item 16 + parent head 64 + base-list window 32 + table rows 32 read; head 64 + memo
         # 16 + carried fitness 8 + per-host sum 8 written; flattened lists are read and written once
         mutate_bytes = None
-        k_mut = next((k for k in rep if k.startswith("k_mutate")), None)  # k_mutate<false> / k_mutate<true> (epistatic providers)
+        k_mut = next((k for k in rep if k.lstrip("(").startswith("k_mutate")), None)  # k_mutate<false> / k_mutate<true> (epistatic providers)
         if c1["gc_runs"] == c0["gc_runs"] and k_mut and rep[k_mut][0]:
             d_rec, d_words = c1["haplotype_records"] - c0["haplotype_records"], c1["arena_words"] - c0["arena_words"]
             mutate_bytes = (240.0 * d_rec + 8.0 * max(d_words, 0)) / rep[k_mut][0]

@@ -156,6 +156,11 @@ static int fail(vl_sim *sim, int code, const char *fmt, ...) {
         if ((sim)->has_epistasis) LAUNCH(sim, k_mutate<true>, grid, block, smem, __VA_ARGS__); \
         else LAUNCH(sim, k_mutate<false>, grid, block, smem, __VA_ARGS__);               \
     } while (0)
+#define LAUNCH_MUTATE_FUSED(sim, grid, block, smem, ...)                                 \
+    do {                                                                                 \
+        if ((sim)->has_epistasis) LAUNCH(sim, (k_mutate<true, true>), grid, block, smem, __VA_ARGS__); \
+        else LAUNCH(sim, (k_mutate<false, true>), grid, block, smem, __VA_ARGS__);       \
+    } while (0)
 // launches of a scope go to another stream of the same handle
 struct StreamScope {
     vl_sim *sim;
@@ -574,6 +579,8 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CCU(cudaFuncSetAttribute(k_host_sum_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
     CCU(cudaFuncSetAttribute(k_mutate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
     CCU(cudaFuncSetAttribute(k_mutate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute((k_mutate<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute((k_mutate<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute(k_ex_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_SMEM_BYTES));
@@ -1483,7 +1490,7 @@ static int enqueue_generation_fused(vl_sim *sim, bool prefill_next) {
         if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
         else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
     }
-    LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
+    LAUNCH_MUTATE_FUSED(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
            prefilled && sim->prefill_patch ? 4 : 3, 1, prefilled && sim->prefill_own_done ? 2 : 0);
     const unsigned og = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (sim->n_bound + RESAMPLE_TILE - 1) / RESAMPLE_TILE), (uint64_t)sim->n_sms * 32);
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, og, OS_TPB, 0, sim->d);
@@ -1519,7 +1526,7 @@ static int enqueue_generation_front_fused(vl_sim *sim) {
         if (sim->pop_fit_valid) LAUNCH(sim, k_infect_sum<false>, ig, IS_TPB, 0, sim->d);
         else LAUNCH(sim, k_infect_sum<true>, ig, IS_TPB, 0, sim->d);
     }
-    LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
+    LAUNCH_MUTATE_FUSED(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0,
            prefilled && sim->prefill_patch ? 4 : 3, 1, prefilled && sim->prefill_own_done ? 2 : 0);
     sim->prefilled = false;
     if (h.host_r0 < 12.0) LAUNCH(sim, k_offspring_sum<true>, ig, OS_TPB, 0, sim->d);
@@ -1738,7 +1745,7 @@ static void preload_exchange_kernels() {
     std::call_once(once, [] {
         const void *ks[] = {
             (const void *)k_zero_words, (const void *)k_begin_generation_fused, (const void *)k_zero_hsum_current,
-            (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate<false>, (const void *)k_mutate<true>,
+            (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate<false>, (const void *)k_mutate<true>, (const void *)k_mutate<false, true>, (const void *)k_mutate<true, true>,
             (const void *)k_offspring_sum<false>, (const void *)k_offspring_sum<true>, (const void *)k_plan_resample,
             (const void *)k_resample_pos<false, true>, (const void *)k_resample_pos<true, true>, (const void *)k_resample_pos<false, false>, (const void *)k_resample_pos<true, false>, (const void *)k_swap_population_fused,
             (const void *)k_ex_sizes, (const void *)k_ex_export,
@@ -1967,7 +1974,7 @@ VL_API int vl_exchange_push(vl_exchange *ex) {
                 StreamScope on_side(sim, ex->side);
                 LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
             }
-            LAUNCH_MUTATE(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(sim->h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 4, 1, 1);
+            LAUNCH_MUTATE_FUSED(sim, grid_for(sim, sim->n_bound / 4 + 1, 8), TPB, mutate_smem_bytes(sim->h.L), sim->d, ReplayMut{nullptr, nullptr, nullptr}, 0, 4, 1, 1);
         } else {
             LAUNCH(sim, k_ex_export, eg, EXP_TPB, EXP_SMEM_BYTES, sim->d, a, sc, (sim->experiment & 512) ? 0 : 1);
         }

@@ -942,8 +942,13 @@ __device__ __forceinline__ uint32_t warp_flatten(const uint32_t *pe, uint32_t pl
 // being assembled (hap_id_next / pop_fit_next / the other hsum buffer, generation + 1), their ids were reserved
 // (mut_own_base), other kernels create records meanwhile.  2 = the items behind those, once the generation has begun.
 // EPI: some provider is epistatic (the pair-table code is compiled into this instantiation only: the others stay leaner).
-template <bool EPI>
-__global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay, int patch_records, int parent_in_item, int range) {
+// FUSED: launched by the device-resident generation (no replay log, items carry parent and host, patch_records 3 or 4):
+// the replay and host-map patching code is compiled out.
+template <bool EPI, bool FUSED = false>
+__global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay_arg, int patch_records_arg, int parent_in_item_arg, int range) {
+    const int replay = FUSED ? 0 : replay_arg;
+    const int patch_records = FUSED ? (patch_records_arg == 4 ? 4 : 3) : patch_records_arg;
+    const int parent_in_item = FUSED ? 1 : parent_in_item_arg;
     extern __shared__ uint32_t s_mut_dyn[];
     __shared__ double s_subst[16];
     uint32_t *s_scratch = s_mut_dyn;
