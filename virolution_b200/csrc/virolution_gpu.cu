@@ -156,10 +156,18 @@ static int fail(vl_sim *sim, int code, const char *fmt, ...) {
         if ((sim)->has_epistasis) LAUNCH(sim, k_mutate<true>, grid, block, smem, __VA_ARGS__); \
         else LAUNCH(sim, k_mutate<false>, grid, block, smem, __VA_ARGS__);               \
     } while (0)
+// device-resident generation: events with more sites than the per-thread shared scratch holds (> 8 in one genome and
+// generation) are set aside by the main pass and worked off by a second, tiny launch — the main pass then addresses its
+// scratch as shared memory only
 #define LAUNCH_MUTATE_FUSED(sim, grid, block, smem, ...)                                 \
     do {                                                                                 \
-        if ((sim)->has_epistasis) LAUNCH(sim, (k_mutate<true, true>), grid, block, smem, __VA_ARGS__); \
-        else LAUNCH(sim, (k_mutate<false, true>), grid, block, smem, __VA_ARGS__);       \
+        if ((sim)->has_epistasis) {                                                      \
+            LAUNCH(sim, (k_mutate<true, true, 1>), grid, block, smem, __VA_ARGS__);      \
+            LAUNCH(sim, (k_mutate<true, true, 2>), 8, block, smem, __VA_ARGS__);         \
+        } else {                                                                         \
+            LAUNCH(sim, (k_mutate<false, true, 1>), grid, block, smem, __VA_ARGS__);     \
+            LAUNCH(sim, (k_mutate<false, true, 2>), 8, block, smem, __VA_ARGS__);        \
+        }                                                                                \
     } while (0)
 // launches of a scope go to another stream of the same handle
 struct StreamScope {
@@ -266,7 +274,7 @@ static int launch_scan(vl_sim *sim, const uint32_t *in, OutT *out, const uint64_
 // ---------------------------------------------------------------------------------------------- buffers
 static void free_population_buffers(vl_sim *sim) {
     DevState &h = sim->h;
-    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.rec, h.heavy_hosts, h.medium_hosts, h.mut_list, h.lam, h.hs, h.offspring,
+    void *olds[] = {h.hap_id, h.hap_id_next, h.host_id, h.rank, h.rec, h.heavy_hosts, h.medium_hosts, h.mut_list, h.big_list, h.lam, h.hs, h.offspring,
                     h.tile_sum, h.tile_tree, h.tile_cnt, h.tile_node, h.tile_base, sim->stage64, h.tmp_rec};
     for (void *p : olds) if (p) cudaFree(p);
     h.tmp_rec = nullptr;
@@ -316,6 +324,7 @@ static int alloc_population_buffers(vl_sim *sim, uint64_t cap) {
     TRY(dev_alloc(sim, &h.heavy_hosts, cap / THREAD_TIER + 1, false));
     TRY(dev_alloc(sim, &h.medium_hosts, cap / 5 + 1, false));
     TRY(dev_alloc(sim, &h.mut_list, cap + 4, false));
+    TRY(dev_alloc(sim, &h.big_list, cap + 4, false));
     TRY(dev_alloc(sim, &h.lam, cap + 4, false));
     TRY(dev_alloc(sim, &h.hs, cap + 4, false));
     TRY(dev_alloc(sim, &h.offspring, cap + 4, false));
@@ -339,7 +348,7 @@ static int push_population_pointers(vl_sim *sim) {
     CU(sim, cudaMemcpy(&tmp, sim->d, sizeof(DevState), cudaMemcpyDeviceToHost));
     const DevState &h = sim->h;
     tmp.hap_id = h.hap_id; tmp.hap_id_next = h.hap_id_next; tmp.host_id = h.host_id; tmp.rank = h.rank; tmp.rec = h.rec;
-    tmp.heavy_hosts = h.heavy_hosts; tmp.medium_hosts = h.medium_hosts; tmp.mut_list = h.mut_list; tmp.lam = h.lam; tmp.hs = h.hs; tmp.offspring = h.offspring;
+    tmp.heavy_hosts = h.heavy_hosts; tmp.medium_hosts = h.medium_hosts; tmp.mut_list = h.mut_list; tmp.big_list = h.big_list; tmp.lam = h.lam; tmp.hs = h.hs; tmp.offspring = h.offspring;
     tmp.tile_sum = h.tile_sum; tmp.tile_tree = h.tile_tree; tmp.tile_cnt = h.tile_cnt; tmp.tile_node = h.tile_node; tmp.tile_base = h.tile_base;
     tmp.tile_stride = h.tile_stride;
     tmp.cap_inf = h.cap_inf; tmp.offsets = h.offsets; tmp.H = h.H; tmp.fast_infect = h.fast_infect;
@@ -579,8 +588,10 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CCU(cudaFuncSetAttribute(k_host_sum_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SORT_MAX * 16));
     CCU(cudaFuncSetAttribute(k_mutate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
     CCU(cudaFuncSetAttribute(k_mutate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
-    CCU(cudaFuncSetAttribute((k_mutate<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
-    CCU(cudaFuncSetAttribute((k_mutate<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute((k_mutate<false, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute((k_mutate<true, true, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute((k_mutate<false, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
+    CCU(cudaFuncSetAttribute((k_mutate<true, true, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mutate_smem_bytes(MUT_WT_MAX_SITES)));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute(k_ex_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_SMEM_BYTES));
@@ -1745,7 +1756,7 @@ static void preload_exchange_kernels() {
     std::call_once(once, [] {
         const void *ks[] = {
             (const void *)k_zero_words, (const void *)k_begin_generation_fused, (const void *)k_zero_hsum_current,
-            (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate<false>, (const void *)k_mutate<true>, (const void *)k_mutate<false, true>, (const void *)k_mutate<true, true>,
+            (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate<false>, (const void *)k_mutate<true>, (const void *)k_mutate<false, true, 1>, (const void *)k_mutate<true, true, 1>, (const void *)k_mutate<false, true, 2>, (const void *)k_mutate<true, true, 2>,
             (const void *)k_offspring_sum<false>, (const void *)k_offspring_sum<true>, (const void *)k_plan_resample,
             (const void *)k_resample_pos<false, true>, (const void *)k_resample_pos<true, true>, (const void *)k_resample_pos<false, false>, (const void *)k_resample_pos<true, false>, (const void *)k_swap_population_fused,
             (const void *)k_ex_sizes, (const void *)k_ex_export,

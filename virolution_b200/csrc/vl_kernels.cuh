@@ -944,7 +944,10 @@ __device__ __forceinline__ uint32_t warp_flatten(const uint32_t *pe, uint32_t pl
 // EPI: some provider is epistatic (the pair-table code is compiled into this instantiation only: the others stay leaner).
 // FUSED: launched by the device-resident generation (no replay log, items carry parent and host, patch_records 3 or 4):
 // the replay and host-map patching code is compiled out.
-template <bool EPI, bool FUSED = false>
+// BIGMODE: 0 = events of any size are handled where they are met (scratch of the large ones in the arena); 1 = events of
+// more than MUT_LOCAL sites are set aside (DevState::big_list) and every scratch pointer is a shared-memory pointer;
+// 2 = the pass that works off the list (same ids: a record's id is its worklist position).
+template <bool EPI, bool FUSED = false, int BIGMODE = 0>
 __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, int replay_arg, int patch_records_arg, int parent_in_item_arg, int range) {
     const int replay = FUSED ? 0 : replay_arg;
     const int patch_records = FUSED ? (patch_records_arg == 4 ? 4 : 3) : patch_records_arg;
@@ -976,12 +979,14 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
     // none is spent per record or per 32 records: a record's id is its worklist position behind the record count the
     // kernel started with (published by the last CTA to leave), and arena words (needed only by the records that are
     // flattened) come out of a chunk the warp reserves for all the rounds it still has to do.
-    const unsigned long long id_base = range == 1 ? st->mut_own_base : st->n_hap;
+    // (BIGMODE 2 runs behind the main pass, which has already moved the record count past this launch's ids)
+    const unsigned long long id_base = range == 1 ? st->mut_own_base : (BIGMODE == 2 ? st->n_hap - n_list : st->n_hap);
+    const uint32_t n_items = BIGMODE == 2 ? st->n_big : n_list;
     unsigned long long chunk_off = 0;
     uint32_t chunk_left = 0;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_list; base += span) {
-        const uint32_t w = base + lane;
-        bool ok = w < n_list;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_items; base += span) {
+        bool ok = base + lane < n_items;
+        const uint32_t w = BIGMODE == 2 ? (ok ? st->big_list[base + lane] : 0u) : base + lane;
         uint32_t i = 0, nm = 0, pid = 0, tpos = NONE32;
         HapHead ph;
         ph.off = 0; ph.len = 0; ph.nd_mlen = 0; ph.raw0 = 1.0; ph.fit0 = 1.0;
@@ -991,11 +996,17 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
             nm = item.y;
             tpos = item.z;
             pid = parent_in_item ? item.w : (ahead ? st->hap_id_next : st->hap_id)[i];
-            ph = st->head[pid];  // ONE 64-byte line: base list, inline delta, fitness of the parent
+            if (BIGMODE == 1 && nm > MUT_LOCAL) {  // set aside for the second pass
+                st->big_list[atomicAdd(&st->n_big, 1u)] = w;
+                ok = false;
+                nm = 0;
+            } else {
+                ph = st->head[pid];  // ONE 64-byte line: base list, inline delta, fitness of the parent
+            }
         }
         const uint32_t nd = head_nd(ph), plen = ph.len, mlen = head_mlen(ph);
         const bool flat = ok && nd + nm > HEAD_DELTA;  // the delta would overflow: this record gets a base list of its own
-        const bool big = nm > MUT_LOCAL;               // (implies flat)
+        const bool big = BIGMODE == 1 ? false : nm > MUT_LOCAL;  // (implies flat)
         if (flat) {  // the whole base list is about to be copied: pull it towards L2 while the sites are drawn
             const uint32_t *pl = st->arena + ph.off;
             for (uint32_t k = 0; k < plen; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pl + k));
@@ -1009,7 +1020,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
         }
         const uint32_t wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
         if (wtot > chunk_left) {  // (warp-uniform)
-            const uint32_t rounds = (n_list - base + span - 1) / span;
+            const uint32_t rounds = (n_items - base + span - 1) / span;
             const unsigned long long want = (unsigned long long)wtot * rounds + ((unsigned long long)wtot * rounds >> 3) + 32u;
             chunk_left = (uint32_t)(want < 0xFFFFFFFFull ? want : (unsigned long long)wtot);
             if (lane == 0) chunk_off = atomicAdd(&st->arena_top, (unsigned long long)chunk_left);
@@ -1173,13 +1184,17 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
             }
         }
     }
-    if (range == 1) return;  // (the ids were reserved up front)
+    if (BIGMODE != 2 && range == 1) return;  // (the ids were reserved up front)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&st->mut_ctas_done, 1u) == gridDim.x - 1) {
-            const unsigned long long top = id_base + n_list;
-            st->n_hap = top < st->cap_hap ? top : st->cap_hap;
+        if (atomicAdd(&st->mut_ctas_done, 1u) == gridDim.x - 1) {  // the last CTA to leave
+            if (BIGMODE == 2) {
+                st->n_big = 0;  // (the list is done)
+            } else {
+                const unsigned long long top = id_base + n_list;
+                st->n_hap = top < st->cap_hap ? top : st->cap_hap;
+            }
             st->mut_ctas_done = 0;
         }
     }

@@ -163,10 +163,13 @@ struct DevState {
 
     // ---- mutation worklist
     uint4 *mut_list;       // (infectant index, n_mut, position in the bucket-partitioned records, -) where n_mut > 0
+    uint32_t *big_list;    // worklist positions of the events with more sites than the shared scratch holds (k_mutate, deferred pass)
     uint32_t n_mut_list;
     uint32_t mut_ctas_done;  // CTAs of the running k_mutate that have left (the last one publishes n_hap)
     uint32_t mut_own;        // worklist items [0, mut_own) are mutated ahead of their generation (vl_exchange_run: while the migrants travel)
     uint32_t tail_done;      // CTAs of the running k_resample_pos that have left (the last one installs the new population)
+    uint32_t n_big;          // entries of big_list (zero between generations)
+    uint32_t big_pad_;
     unsigned long long mut_own_base;  // ... with record ids mut_own_base + worklist position (reserved by k_ex_own_items)
     uint32_t _pad0;
     BinvConst binv;        // Binomial(L, mu) inversion constants (captured BasicHost parameters)
