@@ -101,6 +101,13 @@ __global__ void k_init_wildtype(DevState *st) {  // haplotype 0: no entries, raw
     for (uint32_t p = 0; p < st->n_providers; p++) set_fitness(st, p, 0, 1.0);
     write_flat_head(st, 0, 0, 0);
 }
+// A pointer read from DevState is a generic pointer to the compiler; every array it names lives in global memory.
+// Saying so where the pointer is used turns generic LD / ST into LDG / STG without keeping the pointer in a register.
+template <typename T>
+__device__ __forceinline__ T *gptr(T *p) {
+    __builtin_assume(__isGlobal(p));
+    return p;
+}
 // the merged (flattened) record of `id` written to out[]; returns its length (= head_mlen)
 __device__ inline uint32_t flatten_record(const DevState *st, const HapHead &h, uint32_t *out) {
     uint32_t o = 0;
@@ -986,22 +993,22 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
     uint32_t chunk_left = 0;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_items; base += span) {
         bool ok = base + lane < n_items;
-        const uint32_t w = BIGMODE == 2 ? (ok ? st->big_list[base + lane] : 0u) : base + lane;
+        const uint32_t w = BIGMODE == 2 ? (ok ? gptr(st->big_list)[base + lane] : 0u) : base + lane;
         uint32_t i = 0, nm = 0, pid = 0, tpos = NONE32;
         HapHead ph;
         ph.off = 0; ph.len = 0; ph.nd_mlen = 0; ph.raw0 = 1.0; ph.fit0 = 1.0;
         if (ok) {
-            const uint4 item = st->mut_list[w_first + w];
+            const uint4 item = gptr(st->mut_list)[w_first + w];
             i = item.x;
             nm = item.y;
             tpos = item.z;
-            pid = parent_in_item ? item.w : (ahead ? st->hap_id_next : st->hap_id)[i];
+            pid = parent_in_item ? item.w : gptr(ahead ? st->hap_id_next : st->hap_id)[i];
             if (BIGMODE == 1 && nm > MUT_LOCAL) {  // set aside for the second pass
                 st->big_list[atomicAdd(&st->n_big, 1u)] = w;
                 ok = false;
                 nm = 0;
             } else {
-                ph = st->head[pid];  // ONE 64-byte line: base list, inline delta, fitness of the parent
+                ph = gptr(st->head)[pid];  // ONE 64-byte line: base list, inline delta, fitness of the parent
             }
         }
         const uint32_t nd = head_nd(ph), plen = ph.len, mlen = head_mlen(ph);
@@ -1034,8 +1041,8 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
         if (ok && id64 >= st->cap_hap) { raise(st, DE_HAP_CAPACITY); ok = false; }
         if (ok && flat && roff + words > st->cap_arena) { raise(st, DE_ARENA_CAPACITY); ok = false; }
         const uint32_t new_id = (uint32_t)id64;
-        const uint32_t *pe = st->arena + ph.off;
-        uint32_t *out = st->arena + roff;  // (flat only) merged list [0, mlen + nm), then scratch of large events
+        const uint32_t *pe = gptr(st->arena) + ph.off;
+        uint32_t *out = gptr(st->arena) + roff;  // (flat only) merged list [0, mlen + nm), then scratch of large events
         uint32_t *pd = s_scratch + threadIdx.x * MUT_STRIDE, *dl = pd + HEAD_DELTA, *ch_local = dl + 2 * HEAD_DELTA, *ne_local = ch_local + MUT_LOCAL;
         uint32_t *chs = big ? out + mlen + nm : ch_local;          // change words: pos << 8 | present << 7 | from << 4 | to
         uint32_t *nev = big ? out + mlen + 2 * nm : ne_local;      // the event's entries, one per distinct site
@@ -1110,18 +1117,18 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
                 const DevProvider &pr = st->prov[p];
                 double raw = 1.0;
                 if (pr.kind != VL_FITNESS_NEUTRAL) {
-                    const double praw = p == 0 ? ph.raw0 : st->h_raw[p][pid];
+                    const double praw = p == 0 ? ph.raw0 : gptr(st->h_raw[p])[pid];
                     double acc = 1.;
                     for (uint32_t k = 0; k < nm; k++) {
                         const uint64_t row = (uint64_t)ch_pos(chs[k]) * 4;
-                        acc = acc * pr.table[row + ch_to(chs[k])] / pr.table[row + ch_from(chs[k])];
+                        acc = acc * gptr(pr.table)[row + ch_to(chs[k])] / gptr(pr.table)[row + ch_from(chs[k])];
                     }
                     if (EPI && pr.kind == VL_FITNESS_EPISTATIC) acc = acc * epi_update(pr, chs, nm, pe, plen, dm, ndm, L);
                     raw = praw * acc;
                 }
                 const double mapped = utility_apply(pr, raw);
-                st->h_raw[p][new_id] = raw;
-                st->h_fit[p][new_id] = mapped;
+                gptr(st->h_raw[p])[new_id] = raw;
+                gptr(st->h_fit[p])[new_id] = mapped;
                 if (p == 0) { nh.raw0 = raw; nh.fit0 = mapped; }
                 if ((int)p == pi_repro) fit_repro = mapped;
             }
@@ -1161,15 +1168,15 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
 #pragma unroll
             for (uint32_t k = 0; k < HEAD_DELTA; k++) nh.d[k] = k < ndm ? dm[k] : 0xFFFFFFFFu;
         }
-        st->head[new_id] = nh;
+        gptr(st->head)[new_id] = nh;
         if (patch_records >= 3) {
             // device-resident generation (vl_fused.cuh): items carry the host in .z.  The new haplotype's mapped fitness
             // replaces the infectant's carried value and joins its host's sum (the pass that staged the item left it out).
             // 3: that pass has already written the new record's id into the population (ids are worklist positions);
             // 4: records were created between that pass and this kernel (imported migrants): the population is patched here.
-            (ahead ? st->pop_fit_next : st->pop_fit)[i] = fit_repro;
+            gptr(ahead ? st->pop_fit_next : st->pop_fit)[i] = fit_repro;
             if (tpos != NONE32 && fit_repro != 0.0) red_add_f64_hint(&st->hsum[ahead ? st->hsum_parity ^ 1u : st->hsum_parity][tpos], fit_repro, l2_keep_policy());
-            if (patch_records == 4) (ahead ? st->hap_id_next : st->hap_id)[i] = new_id;
+            if (patch_records == 4) gptr(ahead ? st->hap_id_next : st->hap_id)[i] = new_id;
             continue;
         }
         st->hap_id[i] = new_id;
