@@ -292,7 +292,10 @@ struct ResamplePosArgs {
 // k_offspring_sum of this generation) and the worklist are ready when the next generation begins, which then starts with
 // k_mutate.  The children are as they would be without it; k_infect_sum makes the same draws from the same streams.
 // MULTI = false: one part, the whole new population (vl_run); nothing about parts is computed or kept in registers.
-template <bool PREFILL, bool MULTI>
+// SMALL: every Poisson mean is below 12 (host_r0 < 12, as k_offspring_sum<true>), so a tile of 1024 infectants cannot
+// reach the 32768 offspring beyond which draws go through the CDF + guide table: that path is compiled out (a tile that
+// does reach it is reported, DE_OFFSPRING_RANGE).
+template <bool PREFILL, bool MULTI, bool SMALL = false>
 __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, ResamplePosArgs ra) {
     extern __shared__ uint4 s_items_dyn[];      // PREFILL: CL_CAP staged worklist items
     __shared__ uint32_t s_clcnt[2];
@@ -410,7 +413,11 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
         }
         __syncthreads();
         const uint32_t total = s_total;
-        const bool direct = total <= RESAMPLE_RANK_MAX;
+        if (SMALL && total > RESAMPLE_RANK_MAX) {  // (uniform)
+            if (tid == 0) raise(st, DE_OFFSPRING_RANGE);
+            continue;
+        }
+        const bool direct = SMALL ? true : total <= RESAMPLE_RANK_MAX;
         const double scale = (double)GUIDE_SIZE / (double)total;
 #pragma unroll
         for (int k = 0; k < RT_PER; k++) {
