@@ -98,3 +98,22 @@ def test_vl_run_full_k2_properties():
     raw = g.get_raw_fitness()
     assert np.all(np.isfinite(raw)) and np.all(raw >= 0)
     g.close()
+
+
+def test_events_of_many_sites_take_the_second_pass():
+    """mu * L = 5: one event in fifteen hits more than 8 sites — more than the per-thread shared scratch of the main k_mutate
+    pass holds.  The device-resident generation sets those aside for a second pass (same record ids, same draws); the
+    general fused kernels and the trait-level calls handle them in place.  Same populations."""
+    from test_gpu_stochastic import big_singlehost
+    c = big_singlehost(n=120_000, mu=5.0 / 3000, seed=3)
+    wl = dict(wildtype=c["wildtype"], parameters=c["parameters"], specs=c["specs"], n0=c["n0"])
+    a, b, d = make(wl, 19), make(wl, 19), make(wl, 19, flags=abi.VL_FLAG_NO_TILES)
+    a.run(4)
+    stepwise(b, 4)
+    d.run(4)
+    assert_same_population(a, b, "many-site events: vl_run vs trait-level calls")
+    assert_same_population(a, d, "many-site events: device-resident vs general fused kernels")
+    off = state(a)[0]
+    assert np.diff(off.astype(np.int64)).max() > 12
+    for g in (a, b, d):
+        g.close()

@@ -2340,7 +2340,7 @@ VL_API int vl_get_raw_fitness(vl_sim *sim, uint32_t spec, int which, double *out
     LAUNCH(sim, k_gather_raw, grid_for(sim, n), TPB, 0, sim->d, (uint32_t)pi, tmp);
     if (n) CU(sim, cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, sim->stream));
     CU(sim, cudaStreamSynchronize(sim->stream));
-    return VL_OK;
+    return check_device_error(sim);
 }
 VL_API int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, uint32_t *positions_out, uint8_t *bases_out, uint64_t *n_entries) {
     ENTER(sim);
@@ -2351,6 +2351,7 @@ VL_API int vl_export_mutations(vl_sim *sim, uint64_t *offsets_out, uint64_t n, u
     CU(sim, cudaMemcpyAsync(sim->pin, sim->gc_totals + 6, 8, cudaMemcpyDeviceToHost, sim->stream));
     CU(sim, cudaStreamSynchronize(sim->stream));
     const uint64_t total = sim->pin[0];
+    TRY(check_device_error(sim));  // (whatever was enqueued before has run: a population that a failed kernel left behind is not exported)
     if (n_entries) *n_entries = total;
     if (offsets_out) {
         if (n) CU(sim, cudaMemcpy(offsets_out, sim->stage64, n * 8, cudaMemcpyDeviceToHost));

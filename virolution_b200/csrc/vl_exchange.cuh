@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(EXP_TPB, 4) k_ex_import_fused(DevState *st, Ex
             }
         }
         if (prefill) {  // (one item per thread and round: the list cannot overflow)
-            CtaList cl{s_items, s_clcnt};
+            CtaList cl{s_items, s_clcnt, EXP_TPB};
             cl_push(cl, nm != 0u, make_uint4((uint32_t)slot, nm, h, id));
             cl_flush(st, cl, nullptr, 0ull);
         }

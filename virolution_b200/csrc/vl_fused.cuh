@@ -93,10 +93,11 @@ __device__ __forceinline__ void infect_draw(DevState *st, const InfectCtx &c, ui
 // Mutation worklist staged per CTA in shared memory: (infectant, n_mut, host, parent haplotype), appended with one vote
 // and one shared atomic per warp round, flushed with ONE global atomic per CTA pass (same-address global atomics are
 // served one after the other by L2).
-constexpr uint32_t CL_CAP = RESAMPLE_TILE;  // items a pass can stage: every infectant of a tile may mutate
+constexpr uint32_t CL_CAP = RESAMPLE_TILE + RESAMPLE_TILE / 4;  // items the resample can stage between flushes (a tile's share of the draws is 1024 on average)
 struct CtaList {
     uint4 *buf;
     uint32_t *cnt;  // [0] staged items, [1] global base of the flush
+    uint32_t cap;   // entries of buf (the owner flushes before more than that can have been pushed)
 };
 __device__ __forceinline__ void cl_push(CtaList &cl, bool has, uint4 item) {  // (called by converged warps)
     const uint32_t lane = threadIdx.x & 31;
@@ -107,7 +108,7 @@ __device__ __forceinline__ void cl_push(CtaList &cl, bool has, uint4 item) {  //
     base = __shfl_sync(0xFFFFFFFFu, base, 0);
     if (has) {
         const uint32_t k = base + __popc(mask & ((1u << lane) - 1u));
-        if (k < CL_CAP) cl.buf[k] = item;
+        if (k < cl.cap) cl.buf[k] = item;
     }
 }
 // (called by every thread of the CTA, after the pass's pushes) hap_out != nullptr: the id of a new record is the record
@@ -115,9 +116,9 @@ __device__ __forceinline__ void cl_push(CtaList &cl, bool has, uint4 item) {  //
 // infectant's haplotype can be written here, in stream order, instead of being patched by k_mutate
 __device__ __forceinline__ void cl_flush(DevState *st, CtaList &cl, uint32_t *hap_out, unsigned long long id_base) {
     __syncthreads();
-    const uint32_t n = cl.cnt[0] < CL_CAP ? cl.cnt[0] : CL_CAP;
+    const uint32_t n = cl.cnt[0] < cl.cap ? cl.cnt[0] : cl.cap;
     if (threadIdx.x == 0) {
-        if (cl.cnt[0] > CL_CAP) raise(st, DE_TILE_OVERFLOW);
+        if (cl.cnt[0] > cl.cap) raise(st, DE_TILE_OVERFLOW);  // (cannot happen: every owner flushes in time)
         cl.cnt[1] = n ? atomicAdd(&st->n_mut_list, n) : 0u;
     }
     __syncthreads();
@@ -137,7 +138,7 @@ constexpr int IS_TPB = 256;
 constexpr int IS_ITEMS = RESAMPLE_TILE / IS_TPB;
 template <bool GATHER>
 __global__ void __launch_bounds__(IS_TPB, 4) k_infect_sum(DevState *st) {
-    __shared__ uint4 s_items[CL_CAP];
+    __shared__ uint4 s_items[RESAMPLE_TILE];  // one item per infectant of a chunk at most
     __shared__ uint32_t s_cnt[2];
     const uint64_t n = st->n;
     const uint32_t H32 = (uint32_t)st->H;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(IS_TPB, 4) k_infect_sum(DevState *st) {
     c.keep = l2_keep_policy();
     c.stream = l2_stream_policy();
     const unsigned long long id_base = st->n_hap;
-    CtaList cl{s_items, s_cnt};
+    CtaList cl{s_items, s_cnt, RESAMPLE_TILE};
     if (tid == 0) s_cnt[0] = 0u;
     __syncthreads();
     uint32_t *hap_id = st->hap_id;
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
     const uint64_t own_off = MULTI && ra.own_off ? *ra.own_off : 0ull;
     const uint32_t n_parts = MULTI ? ra.n_parts : 1u;
     InfectCtx ictx;
-    CtaList cl{s_items_dyn, s_clcnt};
+    CtaList cl{s_items_dyn, s_clcnt, CL_CAP};
     if (PREFILL) {
         ictx.H32 = (uint32_t)st->H;
         ictx.thr = ictx.H32 ? (uint32_t)(-ictx.H32) % ictx.H32 : 0u;
@@ -470,7 +471,14 @@ __global__ void __launch_bounds__(RT_TPB, 4) k_resample_pos(DevState *st, Resamp
         } else {
             blocks_total = (uint32_t)(((tbase1 + any - 1) >> 2) - (tbase1 >> 2) + 1);
         }
-        for (uint32_t e0 = wid * 32; e0 < blocks_total; e0 += RT_TPB) {  // (warp-uniform bound: the worklist votes need converged warps)
+        // Every warp makes every pass (a pass = RT_TPB blocks = at most 1024 draws): the worklist votes need converged
+        // warps.  Every child may mutate (mu * L large), so a tile with more draws than the list holds — far above its
+        // average share — flushes between passes; the decision is the same for every thread of the CTA.
+        const uint32_t passes = (blocks_total + RT_TPB - 1) / RT_TPB;
+        const bool tight = PREFILL && 4ull * blocks_total > CL_CAP;
+        for (uint32_t pass = 0; pass < passes; pass++) {
+            if (tight && pass) cl_flush(st, cl, ra.predict_ids ? st->hap_id_next : nullptr, st->n_hap);
+            const uint32_t e0 = pass * RT_TPB + wid * 32;
             const uint32_t e = e0 + lane;
             const bool live = e < blocks_total;
             uint32_t part = 0, before = 0;
