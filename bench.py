@@ -44,7 +44,7 @@ ALGO_BYTES = {
     "k_offspring_sum<false>": 4 + 8 + 8 + 4 + 8,
     # <PREFILL, MULTI>: offspring, hap, fitness in; hap, fitness out; PREFILL: next generation's host out + per-host sum (reduction)
     "(k_resample_pos<true, false>)": 4 + 4 + 8 + 4 + 8 + 4 + 8, "(k_resample_pos<true, true>)": 4 + 4 + 8 + 4 + 8 + 4 + 8,
-    "(k_resample_pos<true, false, true>)": 4 + 4 + 8 + 4 + 8 + 4 + 8,
+    "(k_resample_pos<true, false, true>)": 4 + 4 + 8 + 4 + 8 + 4 + 8, "(k_resample_pos<true, true, true>)": 4 + 4 + 8 + 4 + 8 + 4 + 8,
     "(k_resample_pos<false, false>)": 4 + 4 + 8 + 4 + 8, "(k_resample_pos<false, true>)": 4 + 4 + 8 + 4 + 8,
     "k_infect_sum<false>": 4 + 8 + 4 + 8, "k_infect_sum<true>": 4 + 8 + 8 + 4 + 8,
     # general kernels (trait-level path)
@@ -54,7 +54,7 @@ ALGO_BYTES = {
 }
 # the kernels SURVEY.md §8d's 72 B figure covers (fitness gather + per-host sum + offspring + scan/plan + resample); in the
 # device-resident generation the resample also draws the next generation's hosts and mutation counts (+ 8 B "infect")
-FITNESS_REPLICATION = ("k_offspring_sum<true>", "k_offspring_sum<false>", "k_plan_resample", "(k_resample_pos<true, false>)", "(k_resample_pos<true, true>)", "(k_resample_pos<true, false, true>)",
+FITNESS_REPLICATION = ("k_offspring_sum<true>", "k_offspring_sum<false>", "k_plan_resample", "(k_resample_pos<true, false>)", "(k_resample_pos<true, true>)", "(k_resample_pos<true, false, true>)", "(k_resample_pos<true, true, true>)",
                        "(k_resample_pos<false, false>)", "(k_resample_pos<false, true>)",
                        "k_infect_sum<false>", "k_infect_sum<true>", "k_replicate_fused<true>", "k_replicate_fused<false>", "k_fitness",
                        "k_host_sum", "k_host_sum_medium", "k_host_sum_heavy", "k_offspring<true>", "k_offspring<false>", "k_resample")

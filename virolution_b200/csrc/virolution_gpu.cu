@@ -595,6 +595,7 @@ VL_API int vl_create(const vl_config *cfg, vl_sim **out) {
     CCU(cudaFuncSetAttribute((k_resample_pos<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute((k_resample_pos<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
+    CCU(cudaFuncSetAttribute((k_resample_pos<true, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CL_CAP * sizeof(uint4))));
     CCU(cudaFuncSetAttribute(k_ex_export, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXP_SMEM_BYTES));
     sim->plan_smem_tiles = 200 * 1024 / 8;
     h.gc_hap_threshold = cap_hap / 2;
@@ -985,6 +986,7 @@ static int launch_plan_resample(vl_sim *sim, uint32_t n, const double *factor, i
         const bool small = sim->h.host_r0 < 12.0;  // (the same condition k_offspring_sum<true> is launched under)
         if (prefill && single && small) LAUNCH(sim, (k_resample_pos<true, false, true>), rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
         else if (prefill && single) LAUNCH(sim, (k_resample_pos<true, false>), rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
+        else if (prefill && small) LAUNCH(sim, (k_resample_pos<true, true, true>), rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
         else if (prefill) LAUNCH(sim, (k_resample_pos<true, true>), rg, RT_TPB, CL_CAP * sizeof(uint4), sim->d, rt);
         else if (single) LAUNCH(sim, (k_resample_pos<false, false>), rg, RT_TPB, 0, sim->d, rt);
         else LAUNCH(sim, (k_resample_pos<false, true>), rg, RT_TPB, 0, sim->d, rt);
@@ -1761,7 +1763,7 @@ static void preload_exchange_kernels() {
             (const void *)k_zero_words, (const void *)k_begin_generation_fused, (const void *)k_zero_hsum_current,
             (const void *)k_infect_sum<false>, (const void *)k_infect_sum<true>, (const void *)k_mutate<false>, (const void *)k_mutate<true>, (const void *)k_mutate<false, true, 1>, (const void *)k_mutate<true, true, 1>, (const void *)k_mutate<false, true, 2>, (const void *)k_mutate<true, true, 2>,
             (const void *)k_offspring_sum<false>, (const void *)k_offspring_sum<true>, (const void *)k_plan_resample,
-            (const void *)k_resample_pos<false, true>, (const void *)k_resample_pos<true, true>, (const void *)k_resample_pos<false, false>, (const void *)k_resample_pos<true, false>, (const void *)k_resample_pos<true, false, true>, (const void *)k_swap_population_fused,
+            (const void *)k_resample_pos<false, true>, (const void *)k_resample_pos<true, true>, (const void *)k_resample_pos<true, true, true>, (const void *)k_resample_pos<false, false>, (const void *)k_resample_pos<true, false>, (const void *)k_resample_pos<true, false, true>, (const void *)k_swap_population_fused,
             (const void *)k_ex_sizes, (const void *)k_ex_export,
             (const void *)k_ex_wait, (const void *)k_ex_import_fused, (const void *)k_ex_own_items, (const void *)k_shard_publish_total, (const void *)k_shard_split,
             (const void *)k_ex_out_starts, (const void *)k_ex_lens, (const void *)k_ex_copy, (const void *)k_ex_stream, (const void *)k_ex_publish,
