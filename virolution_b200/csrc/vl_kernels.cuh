@@ -959,6 +959,7 @@ __global__ void __launch_bounds__(TPB, 4) k_mutate(DevState *st, ReplayMut rp, i
     const int replay = FUSED ? 0 : replay_arg;
     const int patch_records = FUSED ? (patch_records_arg == 4 ? 4 : 3) : patch_records_arg;
     const int parent_in_item = FUSED ? 1 : parent_in_item_arg;
+    if (BIGMODE == 2 && st->n_big == 0u) return;  // (nearly always: nothing was set aside)
     extern __shared__ uint32_t s_mut_dyn[];
     __shared__ double s_subst[16];
     uint32_t *s_scratch = s_mut_dyn;
